@@ -1,0 +1,313 @@
+"""Generates tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE (through oracle/ref_shim.py).
+
+TEST INFRASTRUCTURE ONLY; run in the build container where /root/reference is mounted:
+
+    python oracle/make_golden.py            # rewrites every fixture
+
+The reference ships no golden vectors, so these fixtures — outputs of the
+reference's own code on seeded inputs — are the parity pin for both the oracle restatement
+and the CUDA path.  Weights are rebuilt from seeds by tests/synth.py and are not stored.
+"""
+import argparse
+import contextlib
+import io
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+warnings.filterwarnings("ignore")
+
+import ref_shim  # noqa: E402
+import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **_np(arrays))
+    print(f"  {name}.npz  {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+# ------------------------------------------------------------------------------------------
+def golden_rules(ns):
+    """Single-rule fixtures through lrp_modules.*.propagate_relevance (lrp_modules.py)."""
+    lm = ns.lrp_modules
+    g = torch.Generator().manual_seed(100)
+    out = {}
+    # conv alpha-beta, general alpha/beta, stride 2, mixed-sign input, with and without bias
+    conv = nn.Conv2d(5, 7, 3, stride=2, padding=1)
+    conv.weight.data = torch.randn(7, 5, 3, 3, generator=g) * 0.3
+    conv.bias.data = torch.randn(7, generator=g) * 0.1
+    x = torch.randn(2, 5, 9, 9, generator=g)
+    r = torch.randn(2, 7, 5, 5, generator=g)
+    conv.input = (x,)
+    for tag, params in [("a1b0", dict(alpha=1., beta=0., ignore_bias=True)),
+                        ("a2b1", dict(alpha=2., beta=1., ignore_bias=True)),
+                        ("a2b1_bias", dict(alpha=2., beta=1., ignore_bias=False))]:
+        ri = lm.Conv2d().propagate_relevance(conv, (torch.zeros_like(x), conv.weight, conv.bias), (r,),
+                                             "alpha_beta", params)[0]
+        out["conv_R_" + tag] = ri
+    out.update(conv_w=conv.weight.data, conv_b=conv.bias.data, conv_x=x, conv_r=r)
+    # conv 3x3 s1 p1 on a non-negative input (the VGG case)
+    conv2 = nn.Conv2d(6, 4, 3, padding=1)
+    conv2.weight.data = torch.randn(4, 6, 3, 3, generator=g) * 0.3
+    x2 = torch.randn(1, 6, 8, 8, generator=g).clamp(min=0)
+    r2 = torch.randn(1, 4, 8, 8, generator=g)
+    conv2.input = (x2,)
+    out["conv2_R"] = lm.Conv2d().propagate_relevance(conv2, (torch.zeros_like(x2), conv2.weight, conv2.bias), (r2,),
+                                                     "alpha_beta", dict(alpha=1., beta=0., ignore_bias=True))[0]
+    out.update(conv2_w=conv2.weight.data, conv2_x=x2, conv2_r=r2)
+    # max-pool 2x2 (VGG) with exact-zero windows, 3x3 s2 p1 (ResNet stem, overlapping), avg-pool 2x2
+    xp = torch.randn(2, 3, 8, 8, generator=g).clamp(min=0)
+    xp[0, 0, :2, :2] = 0
+    rp = torch.randn(2, 3, 4, 4, generator=g)
+    mp = nn.MaxPool2d(2, 2); mp.input = (xp,)
+    out["mp2_R"] = lm.Pool2d().propagate_relevance(mp, None, (rp,), "alpha_beta")[0]
+    out["mp2_idx"] = torch.nn.functional.max_pool2d(xp, 2, 2, return_indices=True)[1]
+    xq = torch.randn(2, 3, 9, 9, generator=g)
+    rq = torch.randn(2, 3, 5, 5, generator=g)
+    mp3 = nn.MaxPool2d(3, 2, 1); mp3.input = (xq,)
+    out["mp3_R"] = lm.Pool2d().propagate_relevance(mp3, None, (rq,), "alpha_beta")[0]
+    out["mp3_idx"] = torch.nn.functional.max_pool2d(xq, 3, 2, 1, return_indices=True)[1]
+    ap = nn.AvgPool2d(2, 2); ap.input = (xp,)
+    out["ap2_R"] = lm.Pool2d().propagate_relevance(ap, None, (rp,), "alpha_beta")[0]
+    out.update(pool_x=xp, pool_r=rp, pool3_x=xq, pool3_r=rq)
+    # BatchNorm2d abs-ratio
+    bn = nn.BatchNorm2d(3).eval()
+    bn.weight.data = torch.rand(3, generator=g) + 0.5; bn.bias.data = torch.randn(3, generator=g) * 0.3
+    bn.running_mean = torch.randn(3, generator=g) * 0.3; bn.running_var = torch.rand(3, generator=g) + 0.5
+    xb = torch.randn(2, 3, 4, 4, generator=g); xb[0, 0, 0, 0] = 0
+    rb = torch.randn(2, 3, 4, 4, generator=g)
+    bn.input = (xb,)
+    out["bn_R"] = lm.BatchNorm2d().propagate_relevance(bn, (None, None, None), (rb,), "epsilon")[0]
+    out.update(bn_x=xb, bn_r=rb, bn_gamma=bn.weight.data, bn_beta=bn.bias.data, bn_mean=bn.running_mean,
+               bn_var=bn.running_var, bn_eps=np.float32(bn.eps))
+    # Add
+    a1 = torch.randn(2, 3, 4, 4, generator=g); a2 = torch.randn(2, 3, 4, 4, generator=g)
+    a1[0, 0, 0, :2] = 0; a2[0, 0, 0, :2] = 0          # out == 0 -> 0.5/0.5 split
+    ra = torch.randn(2, 3, 4, 4, generator=g)
+    add = ns.resnet.Add(); add.input = (a1, a2)
+    R1, R2 = lm.Add().propagate_relevance(add, None, (ra,), "alpha_beta")
+    out.update(add_x1=a1, add_x2=a2, add_r=ra, add_R1=R1, add_R2=R2)
+    # Linear epsilon
+    lin = nn.Linear(6, 4)
+    lin.weight.data = torch.randn(4, 6, generator=g) * 0.5; lin.bias.data = torch.randn(4, generator=g) * 0.1
+    xl = torch.randn(3, 6, generator=g); xl[0, :2] = 0
+    rl = torch.randn(3, 4, generator=g)
+    for tag, ib in [("nobias", True), ("bias", False)]:
+        lin.input = (xl.clone(),)
+        out["lin_R_" + tag] = lm.Linear().propagate_relevance(
+            lin, (torch.zeros_like(xl), lin.weight.t()), (rl,), "epsilon", dict(ignore_bias=ib))[0]
+    out.update(lin_w=lin.weight.data, lin_b=lin.bias.data, lin_x=xl, lin_r=rl)
+    # ReLU mask (non-identity) and normalize_relevance
+    xr = torch.randn(2, 5, generator=g); rr = torch.randn(2, 5, generator=g)
+    relu = nn.ReLU(); relu.input = (xr,)
+    out["relu_R_mask"] = lm.ReLU().propagate_relevance(relu, None, (rr,), "mask")[0]
+    out.update(relu_x=xr, relu_r=rr)
+    xn = torch.randn(4, 6, generator=g); xn[1] = 0
+    out.update(norm_x=xn, norm_y=ns.utils.normalize_relevance(xn.clone(), dim=-1))
+    save("rules", **out)
+
+
+def golden_sequential_small(ns):
+    """A small conv/relu/maxpool Sequential through add_lrp + compute_lrp (lrp_wrapper.py:37-87)."""
+    cfg = [8, 8, "M", 16, 16, "M", 32]
+    net = ns.vgg.make_layers(cfg)
+    sd = synth.vgg_state(11, cfg)
+    net.load_state_dict(sd); net.eval()
+    ns.lrp_wrapper.add_lrp(net)
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 3, 16, 16, generator=g)
+    tgt = torch.randn(2, 32, 4, 4, generator=g)
+    rel, logits = net.compute_lrp(x.clone(), target=tgt, return_output=True)
+    # Q1: a second call on the same leaf accumulates into sample.grad
+    xs = x.clone()
+    r1 = net.compute_lrp(xs, target=tgt)
+    r2 = net.compute_lrp(xs, target=tgt)
+    save("seq_small", cfg=np.array([str(c) for c in cfg]), seed=11, x=x, target=tgt, rel=rel, logits=logits,
+         rel_second_call=r2, rel_first_call=r1)
+
+
+def golden_vgg16(ns):
+    for size, seed in [(64, 21), (224, 22)]:
+        net = ns.vgg.vgg16(pretrained=True).features[0:-1]      # gridTDmodel.py:33-34
+        net.load_state_dict(synth.vgg_state(seed)); net.eval()
+        ns.lrp_wrapper.add_lrp(net)
+        g = torch.Generator().manual_seed(seed + 1000)
+        x = torch.randn(1, 3, size, size, generator=g)
+        f = size // 16
+        tgt = torch.randn(1, 512, f, f, generator=g) * 1e-3
+        rel, feats = net.compute_lrp(x.clone(), target=tgt, return_output=True)
+        # the 224 fixture stores only the outputs; x/target are replayed from the seed (see tests)
+        extra = dict(x=x, target=tgt, feats=feats) if size == 64 else {}
+        save(f"vgg16_{size}", seed=seed, rel=rel, **extra)
+
+
+def golden_resnet(ns):
+    layers = (2, 1, 1, 1)
+    net = ns.resnet.ResNet(ns.resnet.Bottleneck, list(layers))
+    net.load_state_dict(synth.resnet_state(31, layers)); net.eval()
+    ns.lrp_wrapper.add_lrp(net)
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    tgt = torch.randn(2, 2048, 2, 2, generator=g)
+    rel, feats = net.compute_lrp(x.clone(), target=tgt, return_output=True)
+    save("resnet_2111", seed=31, layers=np.array(layers), x=x, target=tgt, rel=rel, feats=feats)
+
+
+class _StubEncoder(nn.Module):
+    """Stands in for models.gridTDmodel.Encoder (gridTDmodel.py:23-43): returns fixed features."""
+
+    def __init__(self, feats):
+        super().__init__()
+        self.feats = feats
+        self.encoder = nn.Identity()
+
+    def forward(self, img):
+        return self.feats, self.feats.mean((2, 3)).squeeze()
+
+
+def _features(seed, C, h, w):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(1, C, h, w, generator=g).clamp(min=0)       # post-ReLU like
+
+
+def golden_gridtd_decoder(ns):
+    for tag, (V, H, E, T, seed, ts) in {"gridtd_dec_512": (1000, 512, 512, 12, 41, [0, 7, 11]),
+                                        "gridtd_dec_small": (300, 96, 64, 6, 42, [3])}.items():
+        wm = synth.word_map(V)
+        with quiet():
+            model = ns.gridTDmodel.GridTDModel(E, H, V, "vgg16")
+        sd = synth.gridtd_decoder_state(seed, V, H, E)
+        model.load_state_dict(sd, strict=False)
+        feats = _features(seed + 1, 512, 14, 14)
+        model.img_encoder = _StubEncoder(feats)
+        toks = synth.tokens(seed + 2, T, V)
+        model.beam_search = lambda *a, **k: ([" ".join(f"w{t}" for t in toks[1:])], toks[1:])
+        args = argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                                  save_path="/tmp/lrpx_ref", dataset="syn", weight="")
+        ex = ns.gridTDmodel.ExplainGridTDAttention(args, wm, model=model)
+        ex.preprocess_img = lambda p: torch.zeros(1, 3, 224, 224)
+        with torch.no_grad(), quiet():
+            ex.get_hidden_parameters("x")
+        out = dict(V=V, H=H, E=E, T=T, seed=seed, tokens=np.array(toks), ts=np.array(ts), feats=feats,
+                   predictions=ex.predictions, alphas=ex.alphas, betas=ex.betas, h2t=ex.h2t, c1t=ex.c1t,
+                   context_hat=ex.context_hat)
+        for t in ts:
+            with torch.no_grad():
+                rf, rw = ex.explain_caption_wordt(t)
+            out[f"r_feat_{t}"] = rf
+            out[f"r_words_{t}"] = rw
+        save(tag, **out)
+
+
+def golden_aoa_decoder(ns):
+    cfgs = {"aoa_dec_512": dict(V=1000, H=512, E=512, C=512, hw=(14, 14), T=8, seed=51, cases=[(0, 0), (5, 3)]),
+            # config 3 (bottom-up features): 36 regions x 2048-d as a (1,2048,6,6) map, H=1024
+            "aoa_dec_bu": dict(V=500, H=1024, E=512, C=2048, hw=(6, 6), T=5, seed=52, cases=[(4, 2)])}
+    for tag, c in cfgs.items():
+        V, H, E, C, T, seed = c["V"], c["H"], c["E"], c["C"], c["T"], c["seed"]
+        wm = synth.word_map(V)
+        with quiet():
+            model = ns.aoamodel.AOAModel(E, H, 8, V, "vgg16")
+        model.img_projector = nn.Conv2d(C, H, 1)
+        model.encoder_raw_dim = C
+        model.load_state_dict(synth.aoa_decoder_state(seed, V, H, E, C), strict=False)
+        feats = _features(seed + 1, C, *c["hw"])
+        model.img_encoder = _StubEncoder(feats)
+        toks = synth.tokens(seed + 2, T, V)
+        model.beam_search = lambda *a, **k: ([" ".join(f"w{t}" for t in toks[1:])], toks[1:])
+        args = argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                                  save_path="/tmp/lrpx_ref", dataset="syn", weight="")
+        ex = ns.aoamodel.ExplainAOAAttention(args, wm, model=model)
+        ex.preprocess_img = lambda p: torch.zeros(1, 3, 224, 224)
+        with torch.no_grad(), quiet():
+            ex.get_hidden_parameters("x")
+        out = dict(V=V, H=H, E=E, C=C, T=T, seed=seed, tokens=np.array(toks), cases=np.array(c["cases"]), feats=feats,
+                   predictions=ex.predictions, alphas=ex.alphas, ht=ex.ht, context_aoa=ex.context_aoa)
+        for t, hd in c["cases"]:
+            with torch.no_grad():
+                rf, rw = ex.explain_caption_wordt(t, hd)
+            out[f"r_feat_{t}_{hd}"] = rf
+            out[f"r_words_{t}_{hd}"] = rw
+        save(tag, **out)
+
+
+def _rev_word_map(V, stop):
+    wm = synth.word_map(V)
+    rev = {v: k for k, v in wm.items()}
+    for i in range(V):
+        if stop[i] and rev[i].startswith("w"):
+            rev[i] = "the"                      # a member of the shim's stop-word list
+    return wm, rev
+
+
+def golden_lrp_weights(ns):
+    V, H, E, B = 200, 64, 32, 8
+    stop = synth.stop_mask(V)
+    wm, rev = _rev_word_map(V, stop)
+    with quiet():
+        gm = ns.gridTDmodel.GridTDModel(E, H, V, "vgg16")
+    sd = synth.gridtd_decoder_state(61, V, H, E)
+    gm.load_state_dict(sd, strict=False)
+    g = torch.Generator().manual_seed(62)
+    logits = torch.randn(B, V, generator=g); h = torch.randn(B, H, generator=g); c = torch.randn(B, H, generator=g)
+    logits[0, 7] = 9.0          # stop word (7 % 7 == 0)
+    logits[1, V - 1] = 9.0      # <end>
+    h[2] = 0; c[2] = 0          # all-zero relevance row -> weights 1
+    with torch.no_grad():
+        wc, wh = gm.get_lrp_weight_step(logits, rev, h, c)
+    save("lrp_weights", V=V, H=H, E=E, seed=61, logits=logits, h=h, ctx=c, w_ctx=wc, w_h=wh, stop=stop)
+
+
+def golden_tune(ns):
+    """forwardlrp_context (gridTDmodel.py:580-633) on the full model incl. the VGG16 encoder."""
+    V, H, E, B, L = 60, 32, 32, 2, 5
+    stop = synth.stop_mask(V)
+    wm, rev = _rev_word_map(V, stop)
+    with quiet():
+        gm = ns.gridTDmodel.GridTDModel(E, H, V, "vgg16")
+    gm.load_state_dict(synth.gridtd_decoder_state(71, V, H, E), strict=False)
+    gm.img_encoder.encoder.load_state_dict(synth.vgg_state(72))
+    gm.eval()
+    imgs = synth.images(73, B)
+    g = torch.Generator().manual_seed(74)
+    caps = torch.randint(1, V - 4, (B, L), generator=g)
+    caps[:, 0] = V - 2
+    caplens = torch.tensor([L, L - 1])
+    with torch.no_grad():
+        pred, wpred, maxlen = gm.forwardlrp_context(imgs, caps, caplens, rev)
+    save("tune_gridtd", V=V, H=H, E=E, seeds=np.array([71, 72, 73, 74]), caps=caps, caplens=caplens, stop=stop,
+         predictions=pred, weighted_predictions=wpred, max_length=int(maxlen))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    os.makedirs("/tmp/lrpx_ref", exist_ok=True)
+    ns = ref_shim.load_reference()
+    torch.manual_seed(0)
+    for fn in (golden_rules, golden_sequential_small, golden_vgg16, golden_resnet, golden_gridtd_decoder,
+               golden_aoa_decoder, golden_lrp_weights, golden_tune):
+        print(fn.__name__)
+        fn(ns)
+
+
+if __name__ == "__main__":
+    main()

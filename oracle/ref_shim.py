@@ -1,0 +1,134 @@
+"""Import shim for the UNMODIFIED reference (SunJiamei/LRP-imagecaptioning-pytorch).
+
+TEST INFRASTRUCTURE ONLY.  This file is used in the build container (where
+/root/reference is mounted) to (a) validate the oracle restatement in
+``oracle/lrp_oracle.py`` and (b) generate the golden vectors under
+``tests/golden/`` (see ``oracle/make_golden.py``).  It is never imported by the
+product path and never runs on the GPU box (the reference does not travel).
+
+What has to be stubbed to import the reference on a CPU-only, offline box
+(SURVEY.md Appendix A):
+  * matplotlib / skimage / nltk are not installed        -> empty stub modules
+  * torchvision.models.utils no longer exists            -> stub with load_state_dict_from_url
+  * vgg16(pretrained=True) wants the network             -> force pretrained=False
+  * hard-coded .cuda() calls                             -> identity on CPU
+  * gridTDmodel.py:444  ``beam_idx = top_words / vocab_size`` (true division on
+    torch>=1.6 -> IndexError)                            -> text patch to ``//`` (Q8)
+  * lrp_modules.py:14 in-place masked_fill_ on a saved input (Q9)
+                                                         -> ``.clone()`` first (only for Linear hooks)
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+REFERENCE_ROOT = os.environ.get("LRPX_REFERENCE_ROOT", "/root/reference")
+
+# A fixed English stop-word subset (nltk is not installed); the
+# synthetic vocabulary used by the tests draws stop words from here.
+STOP_WORDS = ["a", "an", "the", "of", "on", "in", "with", "and", "is", "are", "to", "at"]
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "LRPtools"))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def install_stubs():
+    if "matplotlib" not in sys.modules:
+        mpl = _stub("matplotlib")
+        plt = _stub("matplotlib.pyplot")
+        mpl.pyplot = plt
+    if "skimage" not in sys.modules:
+        sk = _stub("skimage")
+        skt = _stub("skimage.transform")
+        sk.transform = skt
+    if "nltk" not in sys.modules:
+        nl = _stub("nltk")
+        corpus = _stub("nltk.corpus")
+
+        class _SW:
+            @staticmethod
+            def words(lang):
+                return list(STOP_WORDS)
+
+        corpus.stopwords = _SW
+        nl.corpus = corpus
+    import torchvision.models as tvm
+
+    if "torchvision.models.utils" not in sys.modules:
+        u = _stub("torchvision.models.utils", load_state_dict_from_url=lambda *a, **k: {})
+        tvm.utils = u
+
+
+_loaded = {}
+
+
+def load_reference(cpu: bool = True):
+    """Returns a namespace with the reference modules (LRPtools.*, models.*)."""
+    if "ns" in _loaded:
+        return _loaded["ns"]
+    if not reference_available():
+        raise RuntimeError("reference not mounted at %s" % REFERENCE_ROOT)
+    install_stubs()
+    if cpu:
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        nn.Module.cuda = lambda self, *a, **k: self
+    # Make sure the reference's own top-level packages win over the repo's mirrors.
+    for k in [k for k in sys.modules if k.split(".")[0] in ("LRPtools", "models")]:
+        del sys.modules[k]
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        import LRPtools.utils as ref_utils  # noqa
+        import models.vgg as ref_vgg
+        import models.resnet as ref_resnet
+
+        # no network: never try to fetch pretrained weights
+        _orig_vgg = ref_vgg._vgg
+        ref_vgg._vgg = lambda arch, cfg, bn, pretrained, progress, **kw: _orig_vgg(arch, cfg, bn, False, progress, **kw)
+        _orig_r101 = ref_resnet.resnet101
+        ref_resnet.resnet101 = lambda pretrained=False, **kw: _orig_r101(pretrained=False, **kw)
+
+        # lrp_modules with the Q9 patch (clone before in-place fill)
+        src = open(os.path.join(REFERENCE_ROOT, "LRPtools/lrp_modules.py")).read()
+        src = src.replace("input_ = module.input[0]\n        input_.masked_fill_",
+                          "input_ = module.input[0].clone()\n        input_.masked_fill_")
+        spec = importlib.util.spec_from_loader("LRPtools.lrp_modules", loader=None)
+        ref_lrp_modules = importlib.util.module_from_spec(spec)
+        ref_lrp_modules.__file__ = os.path.join(REFERENCE_ROOT, "LRPtools/lrp_modules.py")
+        sys.modules["LRPtools.lrp_modules"] = ref_lrp_modules
+        exec(compile(src, ref_lrp_modules.__file__, "exec"), ref_lrp_modules.__dict__)
+        import LRPtools
+        LRPtools.lrp_modules = ref_lrp_modules
+        import LRPtools.lrp_wrapper as ref_lrp_wrapper
+
+        def _load_patched(modname, relpath):
+            src = open(os.path.join(REFERENCE_ROOT, relpath)).read()
+            src = src.replace("beam_idx = top_words / vocab_size", "beam_idx = top_words // vocab_size")
+            spec = importlib.util.spec_from_loader(modname, loader=None)
+            mod = importlib.util.module_from_spec(spec)
+            mod.__file__ = os.path.join(REFERENCE_ROOT, relpath)
+            sys.modules[modname] = mod
+            exec(compile(src, mod.__file__, "exec"), mod.__dict__)
+            return mod
+
+        ref_grid = _load_patched("models.gridTDmodel", "models/gridTDmodel.py")
+        ref_aoa = _load_patched("models.aoamodel", "models/aoamodel.py")
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+    ns = types.SimpleNamespace(utils=ref_utils, lrp_modules=ref_lrp_modules, lrp_wrapper=ref_lrp_wrapper,
+                               vgg=ref_vgg, resnet=ref_resnet, gridTDmodel=ref_grid, aoamodel=ref_aoa)
+    _loaded["ns"] = ns
+    # leave the reference's modules registered under private names only
+    for k in [k for k in sys.modules if k.split(".")[0] in ("LRPtools", "models")]:
+        sys.modules["_lrpx_ref_." + k] = sys.modules.pop(k)
+    return ns
