@@ -1,0 +1,281 @@
+/*
+ * lrpx.h — C ABI of liblrpx.so: layer-wise relevance propagation (LRP) kernels for sm_100a (B200).
+ *
+ * This is the drop-in boundary for the LRP hot path of SunJiamei/LRP-imagecaptioning-pytorch.
+ * The reference has no FFI of its own (pure Python); each entry point below
+ * replaces the arithmetic of one reference call site, cited as `file:line` relative to the
+ * reference repository.  The Python host layer (lrp-imagecaptioning-pytorch_b200/LRPtools, models)
+ * keeps the reference's own signatures and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (LRPX_E_*); lrpx_last_error() gives a
+ *     thread-local message.  No exceptions cross the boundary.
+ *   - all pointers are DEVICE pointers owned by the caller; nothing is allocated or freed here,
+ *     nothing synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - "f32" entry points: NCHW / row-major fp32, the reference's own layout and precision
+ *     (parity path, rtol 1e-4 / atol 1e-6 against the oracle).
+ *   - "tc" entry points: NHWC bf16 operands, fp32 accumulation on tcgen05 tensor cores
+ *     (throughput path; tolerance stated in tests/test_tc_parity.py).
+ *   - the library has no mutable global state apart from a once-initialised driver entry point.
+ */
+#ifndef LRPX_H_
+#define LRPX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRPX_OK 0
+#define LRPX_E_INVALID (-1)   /* bad argument (null pointer, unsupported shape, ...) */
+#define LRPX_E_CUDA (-2)      /* a CUDA runtime/driver call failed                    */
+#define LRPX_E_UNSUPPORTED (-3)
+
+/* constants of LRPtools/utils.py:7-14 */
+#define LRPX_EPSILON 0.01f
+#define LRPX_Z_EPSILON 1e-7f
+#define LRPX_RELEVANCE_RECT (-1e-6f)
+
+const char* lrpx_last_error(void);
+int lrpx_version(void);
+/* compute capability major*10+minor of the current device, or <0 */
+int lrpx_device_cc(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Conv2d relevance, fp32 NCHW (LRPtools/lrp_modules.py:56-170 + LRPtools/utils.py:16-31)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n, cin, h, w;        /* input  (n, cin, h, w)                 */
+  int cout, kh, kw;        /* weight (cout, cin, kh, kw), groups==1 */
+  int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+} lrpx_conv_shape;
+
+enum { LRPX_NET_POS = 0, LRPX_NET_NEG = 1, LRPX_NET_PLAIN = 2 };
+
+/* K1: z = net(a)  then  s = r_out / (z + 1e-7*[z==0])            (utils.py:16-18,26-27)
+ *   net POS : z = conv(a+,W+) + conv(a-,W-)                      (PosNetConv, lrp_modules.py:81-84)
+ *   net NEG : z = conv(a-,W+) + conv(a+,W-)                      (NegNetConv, lrp_modules.py:111-114)
+ *   net PLAIN (epsilon rule, "parity unpinned" for conv): zeros of `a` count as -1e-6, z = conv(a,W),
+ *             s = r_out / (z + 0.01*sign z, 0 -> 0.01)            (Linear rule, lrp_modules.py:13-22)
+ * bias may be NULL (ignore_bias=True); otherwise z += bias (clamp(b,min=0)+clamp(b,max=0) == b).
+ * z_out may be NULL; when given it receives z (used for conservation reports). */
+int lrpx_conv_rule_s_f32(const float* a, const float* w, const float* bias, const float* r_out, float* s,
+                         float* z_out, const lrpx_conv_shape* shp, int net, void* stream);
+
+/* K2: r_in (+)= scale * a (.) dgrad(net, s)                      (utils.py:29-30: Z.backward(S); X*X.grad)
+ * accumulate != 0 adds into r_in (used for  alpha*R_pos - beta*R_neg, lrp_modules.py:134-146). */
+int lrpx_conv_rule_rin_f32(const float* a, const float* w, const float* s, float* r_in,
+                           const lrpx_conv_shape* shp, int net, float scale, int accumulate, void* stream);
+
+/* plain forward conv (+bias, optional ReLU) used to produce the saved layer inputs (lrp_wrapper.py:70) */
+int lrpx_conv_forward_f32(const float* a, const float* w, const float* bias, float* out,
+                          const lrpx_conv_shape* shp, int relu, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Linear epsilon rule in GEMM form, fp32 row-major (LRPtools/lrp_modules.py:9-37)
+ *   a (n,in)  w (out,in)  r_out (n,out)  ->  r_in (n,in);  a is NOT modified (the reference fills
+ *   its zeros with -1e-6 in place, Q9; here the fill is applied on the fly).
+ * ------------------------------------------------------------------------------------------- */
+int lrpx_linear_eps_f32(const float* a, const float* w, const float* bias, const float* r_out, float* r_in,
+                        float* s_workspace /* n*out floats */, int n, int in_features, int out_features,
+                        int ignore_bias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pooling (LRPtools/lrp_modules.py:172-195), fp32 NCHW
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { int n, c, h, w, kh, kw, stride_h, stride_w, pad_h, pad_w; } lrpx_pool_shape;
+
+/* forward max-pool with PyTorch's argmax (flat index inside the (h,w) plane, first max in scan
+ * order, NaN wins) — the bit-exact index contract of SURVEY.md §8(a4). y and/or idx may be NULL. */
+int lrpx_maxpool_forward_f32(const float* x, float* y, int64_t* idx, const lrpx_pool_shape* shp, void* stream);
+/* winner-take-all: r_in = x * scatter(r_out / (max + 1e-7*[max==0])) — gather form, deterministic */
+int lrpx_maxpool_wta_f32(const float* x, const float* r_out, float* r_in, const lrpx_pool_shape* shp, void* stream);
+/* avg-pool: r_in = x * sum_windows( s / (kh*kw) ),  s = r_out / (avg + 1e-7*[avg==0])
+ * (count_include_pad=True, ceil_mode=False — the nn.AvgPool2d defaults) */
+int lrpx_avgpool_prop_f32(const float* x, const float* r_out, float* r_in, const lrpx_pool_shape* shp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Element-wise rules, fp32
+ * ------------------------------------------------------------------------------------------- */
+/* BatchNorm abs-ratio, lrp_modules.py:204-215 (x is (n,c,hw)) */
+int lrpx_bn_absratio_f32(const float* x, const float* r_out, float* r_in, const float* running_mean,
+                         const float* running_var, const float* gamma, const float* beta, float eps, int n,
+                         int c, int hw, void* stream);
+/* residual Add proportional split, lrp_modules.py:262-275 */
+int lrpx_add_split_f32(const float* x1, const float* x2, const float* r_out, float* r1, float* r2, size_t count,
+                       void* stream);
+/* ReLU non-identity rule, lrp_modules.py:48-54: r_in = r_out * [x > 0] */
+int lrpx_relu_mask_f32(const float* x, const float* r_out, float* r_in, size_t count, void* stream);
+/* utils.normalize_relevance (utils.py:55-64), row-wise over the last dim, temperature as given */
+int lrpx_normalize_relevance_f32(const float* x, float* y, int rows, int cols, float temperature, void* stream);
+/* sum of a buffer in double precision (conservation reports: sum R_in vs sum R_out); out is 1 double */
+int lrpx_sum_f64(const float* x, size_t count, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Decoder relevance, fp32 (models/gridTDmodel.py:1014-1135, models/aoamodel.py:812-862,1064-1156),
+ * batched over Q explanation requests (image b_q, target word t_q).
+ * Saved-state tensors are those of get_hidden_parameters (gridTDmodel.py:933-1012), stacked over
+ * B images and padded to T steps:   name[b][t][...]  row-major.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, T, H, E, P, C, V, Q;
+  /* per image */
+  const float* feat;      /* (B,P,C)  encoder output, pixel-major (NHWC)      gridTDmodel.py:1029-1030 */
+  const float* avg;       /* (B,C)                                                         :941       */
+  const float* A_pre;     /* (B,P,H)  1x1 projector output before ReLU                      :944,:950  */
+  const float* A;         /* (B,P,H)  after ReLU                                            :945-949   */
+  const float* glob_pre;  /* (B,E)                                                          :946       */
+  /* per image and step */
+  const float* x1;        /* (B,T,H+2E)  [h2_prev | glob | emb]                              :980,:995  */
+  const float* x2;        /* (B,T,2H)    [ctx_hat | h1]                                      :987,:996  */
+  const float* h1;        /* (B,T+1,H) row 0 = zeros                                         :1000      */
+  const float* c1;        /* (B,T+1,H) */
+  const float* h2;        /* (B,T+1,H) */
+  const float* c2;        /* (B,T+1,H) */
+  const float* g1;        /* (B,T,H) pre-tanh cell candidate                                 :1002      */
+  const float* i1;        /* (B,T,H) sigmoid(input gate) */
+  const float* f1;        /* (B,T,H) */
+  const float* g2;
+  const float* i2;
+  const float* f2;
+  const float* st;        /* (B,T,H) sentinel                                                :1010      */
+  const float* ctx;       /* (B,T,H) */
+  const float* ctx_hat;   /* (B,T,H) */
+  const float* alpha;     /* (B,T,P) */
+  const float* beta;      /* (B,T)   */
+  const float* pred;      /* (B,T,V) logits                                                  :997       */
+  /* weights */
+  const float* W_g1;      /* (H, 2H+2E) = [W_ih | W_hh] rows of gate g of AdaLSTM            :1019-1021 */
+  const float* W_g2;      /* (H, 3H)    same for LanguageLSTM                                :1022-1024 */
+  const float* W_fc;      /* (V, H)                                                          :735       */
+  const float* W_glob;    /* (E, C) global_img_feature_proj.weight                           :1119      */
+  const float* W_proj;    /* (H, C) img_projector.weight squeezed                            :1128      */
+  /* requests */
+  const int32_t* req_img;   /* (Q) image index b_q                 */
+  const int32_t* req_t;     /* (Q) target step t_q  (0 <= t_q < T) */
+  const int32_t* req_word;  /* (Q) vocabulary id of the explained word = tokens[b_q][t_q+1]  :1017 */
+  /* outputs */
+  float* r_feat;            /* (Q,P,C) relevance of the encoder output, pixel-major          :1133 */
+  float* r_words;           /* (Q,T)   normalised linguistic relevance, entries > t_q are 0  :1129-1132 */
+  float* r_words_raw;       /* (Q,T)   before the max-abs normalisation (may be NULL)        */
+} lrpx_gridtd_args;
+
+size_t lrpx_gridtd_decoder_workspace_bytes(const lrpx_gridtd_args* args);
+int lrpx_gridtd_decoder_lrp_f32(const lrpx_gridtd_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
+typedef struct {
+  int B, T, H, E, P, C, V, Q, num_head;
+  const float* feat;      /* (B,P,C)                                   aoamodel.py:1079-1080 */
+  const float* A_pre;     /* (B,P,H)                                              :1006      */
+  const float* A;         /* (B,P,H)                                              :1005      */
+  const float* glob;      /* (B,H) mean over pixels of A                          :1007      */
+  const float* value;     /* (B,P,H) decoder_v_proj(A)                            :1009      */
+  const float* x;         /* (B,T,E+H) [emb | glob]                               :1030,:1042 */
+  const float* h;         /* (B,T+1,H) */
+  const float* c;         /* (B,T+1,H) */
+  const float* g;         /* (B,T,H) */
+  const float* i;         /* (B,T,H) */
+  const float* ctx;       /* (B,T,H) attention output                             :1057      */
+  const float* caoa;      /* (B,T,H) sigmoid(gate)*linear                         :1059      */
+  const float* caoa_lin;  /* (B,T,H) decoder_aoa_linear(ctx)                      :1061      */
+  const float* alpha;     /* (B,T,heads,P)                                        :1046      */
+  const float* pred;      /* (B,T,V) */
+  const float* W_g;       /* (H, E+2H) gate-g rows [W_ih | W_hh]                  :1072-1074 */
+  const float* W_fc;      /* (V,H) */
+  const float* W_aoa;     /* (H,H) decoder_aoa_linear.weight                      :1110      */
+  const float* W_v;       /* (H,H) decoder_v_proj.weight                          :1144      */
+  const float* W_proj;    /* (H,C) */
+  const int32_t* req_img;
+  const int32_t* req_t;
+  const int32_t* req_word;
+  const int32_t* req_head;  /* (Q) head_idx                                       :1112-1113 */
+  float* r_feat;            /* (Q,P,C) */
+  float* r_words;           /* (Q,T) */
+  float* r_words_raw;
+} lrpx_aoa_args;
+
+size_t lrpx_aoa_decoder_workspace_bytes(const lrpx_aoa_args* args);
+int lrpx_aoa_decoder_lrp_f32(const lrpx_aoa_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
+/* lrp_tune weights, batched (gridTDmodel.py:549-578, aoamodel.py:597-626, utils.py:55-64):
+ *   w = argmax logits[b]; if is_stop[w] -> weights 1; else r = fc-row eps rule, split to h / ctx,
+ *   weights = r / max|r| + 1.   No host synchronisation; is_stop is a device byte mask (V). */
+int lrpx_fc_lrp_weights_f32(const float* logits, const float* h, const float* ctx, const float* W_fc,
+                            const uint8_t* is_stop, float* w_ctx, float* w_h, int32_t* argmax_out /* may be NULL */,
+                            int B, int V, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core path (tcgen05 + TMA, bf16 operands / fp32 accumulate), NHWC.
+ * One implicit-GEMM kernel family serves the activation-producing forward, the z+ pass and the
+ * relevance (transposed-conv) pass of 3x3/stride-1/pad-1 and 1x1 convolutions:
+ *      acc[m][n] = sum_{r,s,c} A[pixel m shifted by (r,s)][c] * Wt[n][(r,s,c)]
+ * ------------------------------------------------------------------------------------------- */
+enum {
+  /* out_bf16[m][n] = relu(acc[m][n] + bias[n])                      (forward, lrp_wrapper.py:70) */
+  LRPX_TC_EPI_BIAS_RELU = 0,
+  /* dual tile: columns [0,BN/2) hold W, [BN/2,BN) hold W+ of the same output channels:
+   *   act[m][n]  = relu(acc_w + bias[n])                            (forward)
+   *   gain[m][n] = act[m][n] / (acc_wplus + 1e-7*[acc_wplus==0])    (a_{l+1}/safe(z+_l), utils.py:16-18) */
+  LRPX_TC_EPI_FWD_GAIN = 1,
+  /* s_prev[m][n] = acc[m][n] * gain[img(m)][hw(m)][n]               (R_in = a (.) c then / z+ of the
+   *                                                                   layer below; lrp_modules.py:134, utils.py:26-30) */
+  LRPX_TC_EPI_MUL = 2,
+  /* as MUL but the tile is at pooled resolution: gain is pooled-size, `pool_idx` holds the 2-bit
+   * argmax of each 2x2 window; writes 4 fine positions (value at the winner, 0 elsewhere)
+   * (max-pool winner-take-all, lrp_modules.py:186-191) */
+  LRPX_TC_EPI_MUL_UNPOOL = 3,
+  /* first layer: acc has 2*cin_img columns (W+ block, W- block);
+   *   r_img[n][c][h][w] (fp32 NCHW) = max(x,0)*acc[c] + min(x,0)*acc[cin_img + c]   (lrp_modules.py:81-84) */
+  LRPX_TC_EPI_INPUT = 4,
+  /* out_f32[m][n] = acc[m][n] (debug / generic) */
+  LRPX_TC_EPI_STORE_F32 = 5,
+};
+
+typedef struct {
+  int n_img;            /* images (or explanations) in A                                  */
+  int h, w;             /* spatial size of A (== output size: stride 1, "same" padding)   */
+  int cin;              /* channels of A (multiple of 16)                                 */
+  int ncol;             /* rows of Wt == GEMM N (multiple of 16)                          */
+  int ksize;            /* 1 or 3                                                         */
+  int epilogue;         /* LRPX_TC_EPI_*                                                  */
+  const void* a;        /* bf16 (n_img,h,w,cin)                                           */
+  const void* wt;       /* bf16 (ncol, ksize*ksize*cin), K ordered (r,s,c)                */
+  const float* bias;    /* (ncol) or NULL                                                 */
+  const void* gain;     /* bf16, see epilogues                                            */
+  const int32_t* row_img; /* (n_img) image index of each explanation for `gain`/`x`; NULL = identity */
+  const uint8_t* pool_idx;/* (n_gain_img, h, w, ncol) argmax 0..3 for MUL_UNPOOL          */
+  const float* x;       /* fp32 NCHW input images for EPI_INPUT                           */
+  void* out;            /* bf16 NHWC (or fp32, see epilogue)                              */
+  void* out2;           /* second output (gain) for FWD_GAIN                              */
+} lrpx_tc_conv_args;
+
+int lrpx_tc_conv(const lrpx_tc_conv_args* args, void* stream);
+
+/* One-time weight preparation (replaces the per-call PosNetConv/NegNetConv clones,
+ * lrp_modules.py:59-76): from fp32 (cout,cin,kh,kw) build bf16 GEMM operands.
+ *   mode 0: forward      Wt[co][(r,s,ci)]            = W[co][ci][r][s]
+ *   mode 1: forward W+   Wt[co][(r,s,ci)]            = max(W,0)
+ *   mode 2: relevance    Wt[ci][(r,s,co)]            = max(W[co][ci][kh-1-r][kw-1-s],0)   (transposed conv)
+ *   mode 3: relevance W- Wt[ci][(r,s,co)]            = min(W[co][ci][kh-1-r][kw-1-s],0)
+ * rows/cols beyond the source are zero-filled up to (rows_pad, k_pad_c) so tiles never read junk. */
+int lrpx_weight_prep_bf16(const float* w, void* wt, int cout, int cin, int kh, int kw, int mode, int rows_pad,
+                          int chan_pad, void* stream);
+
+/* NCHW fp32 <-> NHWC bf16 helpers (image / target in, nothing else is converted on the hot path) */
+int lrpx_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int n, int c, int h, int w, int c_pad, void* stream);
+int lrpx_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int n, int c, int h, int w, int c_pad, void* stream);
+/* 2x2/2 max-pool on NHWC bf16 with argmax (0..3, PyTorch scan order) and pooled gain:
+ *   pooled[m][c] = max, idx[m][c], gain_pooled[m][c] = gain_fine[winner][c]
+ * (gain_fine = a/safe(z+) at conv-output resolution; at the winner a == pooled max) */
+int lrpx_tc_maxpool2_bf16(const void* act, const void* gain_fine, void* pooled, uint8_t* idx, void* gain_pooled,
+                          int n, int h, int w, int c, void* stream);
+/* s_top[m][c] = bf16( r_feat[m][c] * rz[img][hw][c] ) — entry of the relevance chain (fp32 in) */
+int lrpx_tc_scale_rows(const float* r, const void* gain, const int32_t* row_img, void* out, int n_expl, int hw, int c,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRPX_H_ */

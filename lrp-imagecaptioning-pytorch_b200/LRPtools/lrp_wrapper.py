@@ -1,0 +1,238 @@
+"""Mirror of LRPtools/lrp_wrapper.py (reference :7-87).
+
+The reference abuses the autograd engine as its reverse-topological scheduler: ``add_lrp`` hangs a forward
+hook (saves ``module.input``) and a *backward* hook on every leaf, and ``compute_lrp`` calls
+``logits.backward(target)`` so that "gradients" between modules are relevances (reference :14-25, :53-55,
+:70-80).  Here ``add_lrp`` records an explicit layer plan once and ``compute_lrp`` walks it: a forward that
+saves each rule's inputs on the module (same ``module.input`` attribute), then the rule objects of
+``lrp_modules`` in reverse — no autograd graph, no discarded true backward (wgrad), no per-call conv clones.
+Supported topologies: a Sequential of leaves (the VGG encoder slice) and the Bottleneck ResNet of
+models/resnet.py.  Anything else raises ``NotImplementedError`` in ``add_lrp``.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from lrpx import ops
+from . import lrp_modules
+
+
+class SequentialPresetA(object):
+    """reference :7-12"""
+
+    def __init__(self):
+        self.lrp_params = {"alpha": 1., "beta": 0., "ignore_bias": True}
+
+
+def get_lrp_hook(lrp_method, lrp_params=None):
+    """reference :14-21 — kept for API compatibility (the explicit walker calls the same rule objects)."""
+    def lrp_hook(module, relevance_input, relevance_output):
+        lrp_module = lrp_modules.get_lrp_module(module)
+        return lrp_module.propagate_relevance(module, relevance_input, relevance_output, lrp_method,
+                                              lrp_params=lrp_params)
+    return lrp_hook
+
+
+def save_input_hook(module, input_, output):
+    """reference :24-25"""
+    module.input = input_
+
+
+class LRPLoss(nn.Module):
+    """reference :28-34 — dummy anchor"""
+
+    def forward(self, x):
+        return x
+
+    def backward(self, x):
+        return x
+
+
+# ------------------------------------------------------------------------------------------------
+def _method_for(module):
+    """Rule selection of add_lrp (reference :43-56)."""
+    if type(module) in (nn.Linear, nn.BatchNorm2d, nn.BatchNorm1d):
+        return 'epsilon'
+    if type(module) == nn.ReLU:
+        return 'identity'
+    return 'alpha_beta'
+
+
+def _leaf_forward(m, *xs):
+    """Forward of one leaf on the CUDA kernels, saving the rule's inputs like save_input_hook."""
+    m.input = tuple(xs)
+    x = xs[0]
+    if isinstance(m, nn.Conv2d):
+        if m.groups != 1:
+            raise NotImplementedError("grouped convolutions are not supported")
+        return ops.conv_forward(x, m.weight.detach(), None if m.bias is None else m.bias.detach(), m.stride,
+                                m.padding, m.dilation)
+    if isinstance(m, nn.ReLU):
+        # an in-place ReLU aliases its saved input in the reference; the identity rule never reads it
+        return torch.relu(x)
+    if isinstance(m, nn.MaxPool2d):
+        return ops.maxpool_forward(x, m.kernel_size, m.stride, m.padding, return_indices=False)
+    if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+        if m.training:
+            raise NotImplementedError("LRP through BatchNorm needs eval() mode (running statistics)")
+        shape = [1, -1] + [1] * (x.dim() - 2)
+        w = (m.weight / torch.sqrt(m.running_var + m.eps)).detach().view(shape)
+        b = (m.bias - m.running_mean * m.weight / torch.sqrt(m.running_var + m.eps)).detach().view(shape)
+        return x * w + b
+    if isinstance(m, (nn.Dropout, nn.Dropout2d)):
+        if m.training:
+            raise NotImplementedError("LRP through Dropout needs eval() mode")
+        return x
+    if isinstance(m, nn.AvgPool2d):
+        return torch.nn.functional.avg_pool2d(x, m.kernel_size, m.stride, m.padding)
+    if isinstance(m, nn.Linear):
+        return torch.nn.functional.linear(x, m.weight.detach(), None if m.bias is None else m.bias.detach())
+    if isinstance(m, lrp_modules.resFlatten):
+        return x.reshape(x.size(0), -1)
+    if isinstance(m, lrp_modules.resAdd):
+        return xs[0] + xs[1]
+    if isinstance(m, nn.Identity):
+        return x
+    raise ValueError("Layer type {} not known.".format(type(m)))
+
+
+def _leaf_backward(m, R):
+    if isinstance(m, nn.Identity):
+        return (R,)
+    rule = lrp_modules.get_lrp_module(m)
+    return rule.propagate_relevance(m, None, (R,), m.lrp_method, lrp_params=m.lrp_params)
+
+
+def _flatten_sequential(model):
+    out = []
+    for child in model.children():
+        if isinstance(child, nn.Sequential):
+            out += _flatten_sequential(child)
+        elif len(list(child.children())) == 0:
+            out.append(child)
+        else:
+            raise NotImplementedError(f"add_lrp: unsupported container {type(child)} inside a Sequential")
+    return out
+
+
+class _SequentialPlan:
+    def __init__(self, model):
+        self.leaves = _flatten_sequential(model)
+
+    def forward(self, x):
+        for m in self.leaves:
+            x = _leaf_forward(m, x)
+        return x
+
+    def backward(self, R, trace=None):
+        for m in reversed(self.leaves):
+            R = _leaf_backward(m, R)[0]
+            if trace is not None:
+                trace.append((type(m).__name__, float(ops.sum_f64(R).item())))
+        return R
+
+
+class _ResNetPlan:
+    """Bottleneck ResNet (models/resnet.py): relevance at the block-input fork is the sum of both branches
+    (autograd accumulates it for free in the reference)."""
+
+    def __init__(self, model):
+        self.m = model
+        self.blocks = [b for L in (model.layer1, model.layer2, model.layer3, model.layer4) for b in L]
+        for b in self.blocks:
+            if not all(hasattr(b, a) for a in ("conv1", "bn1", "conv2", "bn2", "conv3", "bn3", "add")):
+                raise NotImplementedError("add_lrp: only Bottleneck blocks with an explicit Add module are supported")
+
+    def forward(self, x):
+        m = self.m
+        x = _leaf_forward(m.maxpool, _leaf_forward(m.relu, _leaf_forward(m.bn1, _leaf_forward(m.conv1, x))))
+        for b in self.blocks:
+            o = _leaf_forward(b.relu, _leaf_forward(b.bn1, _leaf_forward(b.conv1, x)))
+            o = _leaf_forward(b.relu, _leaf_forward(b.bn2, _leaf_forward(b.conv2, o)))
+            o = _leaf_forward(b.bn3, _leaf_forward(b.conv3, o))
+            idn = x
+            if b.downsample is not None:
+                idn = _leaf_forward(b.downsample[1], _leaf_forward(b.downsample[0], x))
+            x = _leaf_forward(b.relu, _leaf_forward(b.add, o, idn))
+        return x
+
+    def backward(self, R, trace=None):
+        m = self.m
+        for b in reversed(self.blocks):
+            r_o, r_idn = _leaf_backward(b.add, R)          # ReLU after the add: identity rule
+            r = _leaf_backward(b.bn3, r_o)[0]
+            r = _leaf_backward(b.conv3, r)[0]
+            r = _leaf_backward(b.bn2, r)[0]
+            r = _leaf_backward(b.conv2, r)[0]
+            r = _leaf_backward(b.bn1, r)[0]
+            r = _leaf_backward(b.conv1, r)[0]
+            if b.downsample is not None:
+                rd = _leaf_backward(b.downsample[1], r_idn)[0]
+                rd = _leaf_backward(b.downsample[0], rd)[0]
+            else:
+                rd = r_idn
+            R = r + rd
+            if trace is not None:
+                trace.append(("Bottleneck", float(ops.sum_f64(R).item())))
+        R = _leaf_backward(m.maxpool, R)[0]
+        R = _leaf_backward(m.bn1, R)[0]
+        R = _leaf_backward(m.conv1, R)[0]
+        return R
+
+
+def _build_plan(model):
+    if isinstance(model, nn.Sequential):
+        return _SequentialPlan(model)
+    if all(hasattr(model, a) for a in ("conv1", "bn1", "maxpool", "layer1", "layer2", "layer3", "layer4")):
+        return _ResNetPlan(model)
+    raise NotImplementedError(f"add_lrp: unsupported model topology {type(model)}; supported: nn.Sequential of "
+                              "leaf layers (VGG encoder) and the Bottleneck ResNet of models/resnet.py")
+
+
+def add_lrp(model):
+    """reference :37-59.  Idempotent (the reference stacks another pair of hooks per call, Q2)."""
+    preset = SequentialPresetA()
+    for module in model.modules():
+        if len(list(module.children())) == 0:
+            module.lrp_method = _method_for(module)
+            module.lrp_params = preset.lrp_params
+    model._lrpx_plan = _build_plan(model)
+    model.compute_lrp = lambda sample, **kwargs: compute_lrp(model, sample, **kwargs)
+
+
+def compute_lrp(model, sample, target=None, return_output=False, rectify_logits=False, explain_diff=False,
+                conservation_trace=None):
+    """reference :63-87.  ``rectify_logits`` / ``explain_diff`` are accepted and ignored, as there.
+
+    Like the reference, the result is accumulated into ``sample.grad`` (the reference never zeroes it, so a
+    second call on the same tensor returns the running sum — Q1).  Set LRPX_NO_GRAD_ACCUMULATION=1 to get the
+    per-call relevance instead.  ``conservation_trace`` (a list) receives (layer, sum R) pairs.
+    """
+    if not hasattr(model, "_lrpx_plan"):
+        raise RuntimeError("call add_lrp(model) first")
+    if not sample.is_cuda:
+        raise RuntimeError("lrpx: compute_lrp needs a CUDA tensor (there is no CPU fallback)")
+    if target is None:
+        raise RuntimeError("grad can be implicitly created only for scalar outputs")   # what .backward(None) raises
+    with torch.no_grad():
+        x = sample.detach()
+        logits = model._lrpx_plan.forward(x)
+        if tuple(target.shape) != tuple(logits.shape):
+            raise RuntimeError(f"Mismatch in shape: grad_output[0] has a shape of {tuple(target.shape)} and "
+                               f"output[0] has a shape of {tuple(logits.shape)}.")
+        R = model._lrpx_plan.backward(target.detach().float(), conservation_trace)
+    if os.environ.get("LRPX_NO_GRAD_ACCUMULATION", "0") == "1":
+        output = R
+    else:
+        if sample.is_leaf and not sample.requires_grad:
+            sample.requires_grad = True
+        if sample.grad is None:
+            sample.grad = R.clone()
+        else:
+            sample.grad += R
+        assert sample.grad.sum() != 0
+        output = sample.grad.clone().detach()
+    if return_output:
+        return output, logits
+    return output

@@ -1,0 +1,589 @@
+// Decoder relevance (fp32), batched over Q = (image, target word) requests.
+//
+//   gridTD : ExplainGridTDAttention.explain_caption_wordt   models/gridTDmodel.py:1014-1135
+//   AoA    : ExplainAOAAttention.explain_caption_wordt      models/aoamodel.py:1064-1156 (+ lrp_mha :812-862)
+//   tune   : get_lrp_weight_step                            models/gridTDmodel.py:549-578, aoamodel.py:597-626
+//
+// The reference walks each vector with lrp_linear_eps (gridTDmodel.py:744-765), materialising
+// `weight * input` (out x in) and `eye(H)` on every call.  Here the same arithmetic is in closed form:
+//   ident(r,x,z) = x * r / stab(z)                     (weight = eye)
+//   lin(r,x,z,W) = x * ((r / stab(z)) @ W)              (GEMM over all requests at once)
+// The LSTM chain is sequential in the step index i (t..0) but independent across requests, so every
+// step is: one warp-friendly element-wise kernel + one (Q x H) @ (H x in) GEMM + one element-wise kernel.
+#include "lrpx_common.cuh"
+
+namespace lrpx {
+
+// ------------------------------------------------------------------------------------------------
+// SGEMM  C[M,N] = A[M,K] @ B[K,N]  (row-major), 64x64x16 tiles, 4x4 per thread, fused epilogues.
+// ------------------------------------------------------------------------------------------------
+enum { GE_STORE = 0, GE_FEAT = 1, GE_AOA_PROJ = 2 };
+
+struct GemmEpi {
+  // GE_FEAT: out[m][n] = feat[b][p][n] * (acc + add_q[q][n])      rows m = q*P + p
+  // GE_AOA_PROJ: out[m][n] = (A[b][p][n] * (acc + add_q[q][n])) / stab(A_pre[b][p][n])
+  const float* x0;       // feat / A          (B,P,N)
+  const float* x1;       // A_pre             (B,P,N)
+  const float* add_q;    // (Q,N) or null
+  const int32_t* req_img;
+  int P;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                       float* __restrict__ C, int M, int N, int K, int lda, int ldb,
+                                                       int ldc, GemmEpi e) {
+  constexpr int TBM = 64, TBN = 64, TBK = 16;
+  __shared__ float As[TBK][TBM + 4];
+  __shared__ float Bs[TBK][TBN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += TBK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {           // A tile: 64 x 16
+      int idx = tid + 256 * j;
+      int r = idx / TBK, c = idx % TBK;
+      int m = m0 + r, k = k0 + c;
+      As[c][r] = (m < M && k < K) ? A[(size_t)m * lda + k] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {           // B tile: 16 x 64
+      int idx = tid + 256 * j;
+      int r = idx / TBN, c = idx % TBN;
+      int k = k0 + r, n = n0 + c;
+      Bs[r][c] = (k < K && n < N) ? Bm[(size_t)k * ldb + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TBK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    int q = 0, pp = 0, b = 0;
+    if (EPI != GE_STORE) {
+      q = m / e.P;
+      pp = m % e.P;
+      b = e.req_img[q];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx + 16 * j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (EPI == GE_FEAT) {
+        float add = e.add_q ? e.add_q[(size_t)q * N + n] : 0.f;
+        v = e.x0[((size_t)b * e.P + pp) * N + n] * (v + add);
+      } else if (EPI == GE_AOA_PROJ) {
+        size_t o = ((size_t)b * e.P + pp) * N + n;
+        float add = e.add_q ? e.add_q[(size_t)q * N + n] : 0.f;
+        v = (e.x0[o] * (v + add)) / stab(e.x1[o]);
+      }
+      C[(size_t)m * ldc + n] = v;
+    }
+  }
+}
+
+template <int EPI>
+static int sgemm(const float* A, const float* B, float* C, int M, int N, int K, const GemmEpi& e, cudaStream_t st) {
+  if (M == 0) return LRPX_OK;
+  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+  sgemm_nn_kernel<EPI><<<grid, 256, 0, st>>>(A, B, C, M, N, K, K, N, N, e);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error("sgemm launch failed: %s", cudaGetErrorString(err));
+    return LRPX_E_CUDA;
+  }
+  return LRPX_OK;
+}
+
+// fc rule for the target word only (one-hot relevance): gridTDmodel.py:1033-1059
+//   r_sum = s_in * W_fc[word] * logit/stab(logit);  r_a = a * r_sum / stab(s_in), r_b likewise
+__device__ __forceinline__ void fc_split(float a, float b, float wrow, float coef, float& ra, float& rb) {
+  float s_in = a + b;
+  float r_sum = s_in * wrow * coef;
+  float d = stab(s_in);
+  ra = a * r_sum / d;
+  rb = b * r_sum / d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gridTD
+// ------------------------------------------------------------------------------------------------
+struct GridWs {
+  float *r_h2, *r_c2, *r_c1, *r_cth, *r_glob, *u, *v, *uctx, *coefavg, *wproj;
+};
+
+__global__ void grid_init_kernel(lrpx_gridtd_args a, GridWs w) {
+  int q = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q], word = a.req_word[q];
+  float logit = a.pred[((size_t)b * a.T + t) * a.V + word];
+  float coef = logit / stab(logit);
+  const float* h2 = a.h2 + ((size_t)b * (a.T + 1) + t + 1) * a.H;
+  const float* ch = a.ctx_hat + ((size_t)b * a.T + t) * a.H;
+  const float* wr = a.W_fc + (size_t)word * a.H;
+  for (int j = threadIdx.x; j < a.H; j += blockDim.x) {
+    float rh, rc;
+    fc_split(h2[j], ch[j], wr[j], coef, rh, rc);
+    size_t o = (size_t)q * a.H + j;
+    w.r_h2[o] = rh;
+    w.r_cth[o] = rc;
+    w.r_c2[o] = 0.f;
+    w.r_c1[o] = 0.f;
+  }
+  for (int j = threadIdx.x; j < a.E; j += blockDim.x) w.r_glob[(size_t)q * a.E + j] = 0.f;
+  for (int j = threadIdx.x; j < a.T; j += blockDim.x) {
+    a.r_words[(size_t)q * a.T + j] = 0.f;
+    if (a.r_words_raw) a.r_words_raw[(size_t)q * a.T + j] = 0.f;
+  }
+}
+
+// LanguageLSTM cell rule (:1061-1069) -> u = r_g2 / stab(g2)
+__global__ void grid_cell2_kernel(lrpx_gridtd_args a, GridWs w, int i) {
+  int q = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q];
+  bool active = i <= t;
+  size_t bi = ((size_t)b * a.T + i) * a.H, bi1 = ((size_t)b * (a.T + 1) + i + 1) * a.H,
+         bi0 = ((size_t)b * (a.T + 1) + i) * a.H;
+  for (int j = threadIdx.x; j < a.H; j += blockDim.x) {
+    size_t o = (size_t)q * a.H + j;
+    if (!active) { w.u[o] = 0.f; continue; }
+    float rc2 = w.r_c2[o] + w.r_h2[o];
+    float d = stab(a.c2[bi1 + j]);
+    float g = a.g2[bi + j];
+    float r_g = a.i2[bi + j] * tanhf(g) * rc2 / d;
+    w.r_c2[o] = a.f2[bi + j] * a.c2[bi0 + j] * rc2 / d;
+    w.u[o] = r_g / stab(g);
+  }
+}
+
+// after v = u @ W_g2 : slices of xh2 (:1070-1084), attention split, AdaLSTM cell rule (:1096-1105)
+__global__ void grid_post2_kernel(lrpx_gridtd_args a, GridWs w, int i) {
+  int q = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q];
+  bool active = i <= t;
+  const int H = a.H;
+  size_t bi = ((size_t)b * a.T + i) * H, bi1 = ((size_t)b * (a.T + 1) + i + 1) * H,
+         bi0 = ((size_t)b * (a.T + 1) + i) * H;
+  const float* x2 = a.x2 + ((size_t)b * a.T + i) * 2 * H;
+  const float* vq = w.v + (size_t)q * 3 * H;
+  float beta = a.beta[(size_t)b * a.T + i];
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    size_t o = (size_t)q * H + j;
+    if (!active) { w.u[o] = 0.f; continue; }
+    float rx_ctx = x2[j] * vq[j];                 // xh2[:H]   = ctx_hat_i
+    float rx_h1 = x2[H + j] * vq[H + j];          // xh2[H:2H] = h1_{i+1}
+    float rx_h2 = a.h2[bi0 + j] * vq[2 * H + j];  // xh2[2H:]  = h2_i
+    float rcth = (i == t ? w.r_cth[o] : 0.f) + rx_ctx;
+    float cth = a.ctx_hat[bi + j];
+    float dct = stab(cth);
+    float r_s = beta * a.st[bi + j] * rcth / dct;
+    float cx = a.ctx[bi + j];
+    float r_ctx = cx * (1.f - beta) * rcth / dct;
+    w.uctx[((size_t)q * a.T + i) * H + j] = r_ctx / stab(cx);
+    float rc1 = w.r_c1[o] + r_s + rx_h1;
+    float d = stab(a.c1[bi1 + j]);
+    float g = a.g1[bi + j];
+    float r_g = a.i1[bi + j] * tanhf(g) * rc1 / d;
+    w.r_c1[o] = a.f1[bi + j] * a.c1[bi0 + j] * rc1 / d;
+    w.u[o] = r_g / stab(g);
+    w.r_h2[o] = rx_h2;
+  }
+}
+
+// after v = u @ W_g1 : slices of xh1 (:1106-1115)
+__global__ void grid_post1_kernel(lrpx_gridtd_args a, GridWs w, int i) {
+  int q = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q];
+  if (i > t) return;
+  const int H = a.H, E = a.E;
+  const float* x1 = a.x1 + ((size_t)b * a.T + i) * (H + 2 * E);
+  const float* vq = w.v + (size_t)q * (2 * H + 2 * E);
+  float wsum = 0.f;
+  for (int k = threadIdx.x; k < H + 2 * E; k += blockDim.x) {
+    float rx = x1[k] * vq[k];
+    if (k < H) w.r_h2[(size_t)q * H + k] += rx;
+    else if (k < H + E) w.r_glob[(size_t)q * E + (k - H)] += rx;
+    else wsum += rx;
+  }
+  // r_h1[i] = rx1[H+2E:] is dead: it is overwritten at step i-1 before being read (:1075 vs :1110)
+  for (int o = 16; o; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  __shared__ float sm[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < (blockDim.x + 31) / 32; ++k) s += sm[k];
+    float* dst = a.r_words_raw ? a.r_words_raw : a.r_words;
+    dst[(size_t)q * a.T + i] = s;
+    if (a.r_words_raw) a.r_words[(size_t)q * a.T + i] = s;
+  }
+}
+
+// u_g = r_glob / stab(glob_pre)   (:1116-1119)
+__global__ void grid_glob_kernel(lrpx_gridtd_args a, GridWs w) {
+  int q = blockIdx.x, b = a.req_img[q];
+  for (int j = threadIdx.x; j < a.E; j += blockDim.x)
+    w.u[(size_t)q * a.E + j] = w.r_glob[(size_t)q * a.E + j] / stab(a.glob_pre[(size_t)b * a.E + j]);
+}
+// coefavg = avg * v / stab(avg) / P  (mean-pool rule, :1121-1124; r_avg = avg * v)
+__global__ void grid_avg_kernel(lrpx_gridtd_args a, GridWs w) {
+  int q = blockIdx.x, b = a.req_img[q];
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float av = a.avg[(size_t)b * a.C + c];
+    float r_avg = av * w.v[(size_t)q * a.C + c];
+    w.coefavg[(size_t)q * a.C + c] = r_avg / stab(av) / (float)a.P;
+  }
+}
+// wproj[q][p][h] = A * (sum_i alpha_i[p] * uctx_i[h]) / stab(A_pre)     (:1091-1095 then :1125-1128)
+__global__ void grid_attn_kernel(lrpx_gridtd_args a, GridWs w) {
+  int q = blockIdx.y, p = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q];
+  const float* al = a.alpha + (size_t)b * a.T * a.P + p;
+  size_t o0 = ((size_t)b * a.P + p) * a.H;
+  for (int h = threadIdx.x; h < a.H; h += blockDim.x) {
+    float acc = 0.f;
+    for (int i = t; i >= 0; --i) acc += al[(size_t)i * a.P] * w.uctx[((size_t)q * a.T + i) * a.H + h] * a.A[o0 + h];
+    w.wproj[((size_t)q * a.P + p) * a.H + h] = acc / stab(a.A_pre[o0 + h]);
+  }
+}
+// r_words / max|r_words|   (:1129-1132)
+__global__ void words_norm_kernel(float* r_words, const int32_t* req_t, int T) {
+  int q = blockIdx.x;
+  int t = req_t[q];
+  float* r = r_words + (size_t)q * T;
+  float m = 0.f;
+  for (int i = threadIdx.x; i <= t; i += 32) m = fmaxf(m, fabsf(r[i]));
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (m > 0.f)
+    for (int i = threadIdx.x; i <= t; i += 32) r[i] = r[i] / m;
+}
+
+static size_t align_up(size_t x) { return (x + 63) & ~(size_t)63; }
+
+static size_t grid_carve(const lrpx_gridtd_args* a, float* base, GridWs* w) {
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    float* p = base ? base + off : nullptr;
+    off += align_up(n);
+    return p;
+  };
+  size_t Q = a->Q, H = a->H, E = a->E;
+  size_t nmax = 3 * H > 2 * H + 2 * E ? 3 * H : 2 * H + 2 * E;
+  if ((size_t)a->C > nmax) nmax = a->C;
+  GridWs t;
+  t.r_h2 = take(Q * H); t.r_c2 = take(Q * H); t.r_c1 = take(Q * H); t.r_cth = take(Q * H);
+  t.r_glob = take(Q * E);
+  t.u = take(Q * (H > E ? H : E));
+  t.v = take(Q * nmax);
+  t.uctx = take(Q * a->T * H);
+  t.coefavg = take(Q * a->C);
+  t.wproj = take(Q * a->P * H);
+  if (w) *w = t;
+  return off * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
+// AoA
+// ------------------------------------------------------------------------------------------------
+struct AoaWs {
+  float *r_h, *r_glob, *u, *v, *uval, *addq, *wval, *w2;
+};
+
+__global__ void aoa_init_kernel(lrpx_aoa_args a, AoaWs w) {
+  int q = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q], word = a.req_word[q];
+  float logit = a.pred[((size_t)b * a.T + t) * a.V + word];
+  float coef = logit / stab(logit);
+  const float* h = a.h + ((size_t)b * (a.T + 1) + t + 1) * a.H;
+  const float* ca = a.caoa + ((size_t)b * a.T + t) * a.H;
+  const float* cl = a.caoa_lin + ((size_t)b * a.T + t) * a.H;
+  const float* wr = a.W_fc + (size_t)word * a.H;
+  for (int j = threadIdx.x; j < a.H; j += blockDim.x) {
+    float rh, rc;
+    fc_split(h[j], ca[j], wr[j], coef, rh, rc);               // :1092-1104
+    w.r_h[(size_t)q * a.H + j] = rh;
+    w.u[(size_t)q * a.H + j] = rc / stab(cl[j]);              // lin() through decoder_aoa_linear (:1107-1110)
+    w.r_glob[(size_t)q * a.H + j] = 0.f;
+  }
+  for (int j = threadIdx.x; j < a.T; j += blockDim.x) {
+    a.r_words[(size_t)q * a.T + j] = 0.f;
+    if (a.r_words_raw) a.r_words_raw[(size_t)q * a.T + j] = 0.f;
+  }
+}
+// r_ctx = ctx * v ;  uval = r_ctx / stab(ctx) on the chosen head, 0 elsewhere (lrp_mha :848-860, Q5)
+__global__ void aoa_ctx_kernel(lrpx_aoa_args a, AoaWs w) {
+  int q = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q], head = a.req_head[q];
+  int dk = a.H / a.num_head;
+  const float* cx = a.ctx + ((size_t)b * a.T + t) * a.H;
+  for (int j = threadIdx.x; j < a.H; j += blockDim.x) {
+    float r_ctx = cx[j] * w.v[(size_t)q * a.H + j];
+    w.uval[(size_t)q * a.H + j] = (j / dk == head) ? r_ctx / stab(cx[j]) : 0.f;
+  }
+}
+// LSTM chain without cell carry (Q4, :1115-1124): r_g = ident(r_h[i+1], i*tanh(g), c[i+1])
+__global__ void aoa_cell_kernel(lrpx_aoa_args a, AoaWs w, int i) {
+  int q = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q];
+  bool active = i <= t;
+  size_t bi = ((size_t)b * a.T + i) * a.H, bi1 = ((size_t)b * (a.T + 1) + i + 1) * a.H;
+  for (int j = threadIdx.x; j < a.H; j += blockDim.x) {
+    size_t o = (size_t)q * a.H + j;
+    if (!active) { w.u[o] = 0.f; continue; }
+    float g = a.g[bi + j];
+    float r_g = a.i[bi + j] * tanhf(g) * w.r_h[o] / stab(a.c[bi1 + j]);
+    w.u[o] = r_g / stab(g);
+  }
+}
+__global__ void aoa_post_kernel(lrpx_aoa_args a, AoaWs w, int i) {
+  int q = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q];
+  if (i > t) return;
+  const int H = a.H, E = a.E;
+  const float* x = a.x + ((size_t)b * a.T + i) * (E + H);
+  const float* hh = a.h + ((size_t)b * (a.T + 1) + i) * H;
+  const float* vq = w.v + (size_t)q * (E + 2 * H);
+  float wsum = 0.f;
+  for (int k = threadIdx.x; k < E + 2 * H; k += blockDim.x) {
+    float xv = k < E + H ? x[k] : hh[k - E - H];
+    float rx = xv * vq[k];
+    if (k < E) wsum += rx;                                            // :1130
+    else if (k < E + H) w.r_glob[(size_t)q * H + (k - E)] += rx;      // :1133
+    else w.r_h[(size_t)q * H + (k - E - H)] = rx;                     // :1129
+  }
+  for (int o = 16; o; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  __shared__ float sm[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < (blockDim.x + 31) / 32; ++k) s += sm[k];
+    a.r_words[(size_t)q * a.T + i] = s;
+    if (a.r_words_raw) a.r_words_raw[(size_t)q * a.T + i] = s;
+  }
+}
+// wval = r_val / stab(value), r_val = value * alpha[head][p] * uval   (:1112-1113, :1141-1144)
+// addq = r_glob / stab(glob) / P                                     (:1136-1139)
+__global__ void aoa_val_kernel(lrpx_aoa_args a, AoaWs w) {
+  int q = blockIdx.y, p = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q], head = a.req_head[q];
+  float al = a.alpha[(((size_t)b * a.T + t) * a.num_head + head) * a.P + p];
+  size_t o0 = ((size_t)b * a.P + p) * a.H;
+  for (int h = threadIdx.x; h < a.H; h += blockDim.x) {
+    float val = a.value[o0 + h];
+    w.wval[((size_t)q * a.P + p) * a.H + h] = val * al * w.uval[(size_t)q * a.H + h] / stab(val);
+    if (p == 0) w.addq[(size_t)q * a.H + h] = w.r_glob[(size_t)q * a.H + h] / stab(a.glob[(size_t)b * a.H + h]) / (float)a.P;
+  }
+}
+
+static size_t aoa_carve(const lrpx_aoa_args* a, float* base, AoaWs* w) {
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    float* p = base ? base + off : nullptr;
+    off += align_up(n);
+    return p;
+  };
+  size_t Q = a->Q, H = a->H;
+  AoaWs t;
+  t.r_h = take(Q * H); t.r_glob = take(Q * H); t.u = take(Q * H);
+  t.v = take(Q * (a->E + 2 * H));
+  t.uval = take(Q * H); t.addq = take(Q * H);
+  t.wval = take(Q * a->P * H);
+  t.w2 = take(Q * a->P * H);
+  if (w) *w = t;
+  return off * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lrp_tune weights: one block per sample
+// ------------------------------------------------------------------------------------------------
+__global__ void fc_lrp_weights_kernel(const float* __restrict__ logits, const float* __restrict__ h,
+                                      const float* __restrict__ ctx, const float* __restrict__ W_fc,
+                                      const uint8_t* __restrict__ is_stop, float* __restrict__ w_ctx,
+                                      float* __restrict__ w_h, int32_t* __restrict__ argmax_out, int V, int H) {
+  int b = blockIdx.x;
+  const float* lg = logits + (size_t)b * V;
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ float s_m[2][32];
+  // argmax, first index wins on ties (torch.argmax, gridTDmodel.py:555)
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    float v = lg[j];
+    if (v > bv || (v == bv && j < bi)) { bv = v; bi = j; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) / 32;
+  if (lane == 0) { s_val[wid] = bv; s_idx[wid] = bi; }
+  __syncthreads();
+  if (wid == 0) {
+    bv = lane < nw ? s_val[lane] : -INFINITY;
+    bi = lane < nw ? s_idx[lane] : 0x7fffffff;
+    for (int o = 16; o; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_val[0] = bv; s_idx[0] = bi; }
+  }
+  __syncthreads();
+  int word = s_idx[0];
+  float logit = s_val[0];
+  if (argmax_out && threadIdx.x == 0) argmax_out[b] = word;
+  bool stop = is_stop[word] != 0;                                   // Q15
+  float coef = logit / stab(logit);
+  const float* wr = W_fc + (size_t)word * H;
+  // pass 1: max |r|
+  float mh = 0.f, mc = 0.f;
+  if (!stop)
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+      float rh, rc;
+      fc_split(h[(size_t)b * H + j], ctx[(size_t)b * H + j], wr[j], coef, rh, rc);
+      mh = fmaxf(mh, fabsf(rh));
+      mc = fmaxf(mc, fabsf(rc));
+    }
+  for (int o = 16; o; o >>= 1) {
+    mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, o));
+    mc = fmaxf(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+  }
+  if (lane == 0) { s_m[0][wid] = mh; s_m[1][wid] = mc; }
+  __syncthreads();
+  mh = 0.f; mc = 0.f;
+  for (int k = 0; k < nw; ++k) { mh = fmaxf(mh, s_m[0][k]); mc = fmaxf(mc, s_m[1][k]); }
+  if (mh == 0.f) mh = 1.f;                                          // utils.py:59
+  if (mc == 0.f) mc = 1.f;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float rh = 0.f, rc = 0.f;
+    if (!stop) fc_split(h[(size_t)b * H + j], ctx[(size_t)b * H + j], wr[j], coef, rh, rc);
+    w_h[(size_t)b * H + j] = rh / mh + 1.f;
+    w_ctx[(size_t)b * H + j] = rc / mc + 1.f;
+  }
+}
+
+}  // namespace lrpx
+
+using namespace lrpx;
+
+#define RUN(expr)                 \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != LRPX_OK) return rc__; \
+  } while (0)
+
+extern "C" {
+
+size_t lrpx_gridtd_decoder_workspace_bytes(const lrpx_gridtd_args* a) {
+  if (!a) return 0;
+  return grid_carve(a, nullptr, nullptr);
+}
+
+int lrpx_gridtd_decoder_lrp_f32(const lrpx_gridtd_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  LRPX_CHECK_ARG(a, "null args");
+  LRPX_CHECK_ARG(a->B > 0 && a->T > 0 && a->H > 0 && a->E > 0 && a->P > 0 && a->C > 0 && a->V > 0 && a->Q >= 0,
+                 "bad dimensions");
+  if (a->Q == 0) return LRPX_OK;
+  LRPX_CHECK_ARG(a->feat && a->avg && a->A_pre && a->A && a->glob_pre && a->x1 && a->x2 && a->h1 && a->c1 && a->h2 &&
+                     a->c2 && a->g1 && a->i1 && a->f1 && a->g2 && a->i2 && a->f2 && a->st && a->ctx && a->ctx_hat &&
+                     a->alpha && a->beta && a->pred && a->W_g1 && a->W_g2 && a->W_fc && a->W_glob && a->W_proj &&
+                     a->req_img && a->req_t && a->req_word && a->r_feat && a->r_words,
+                 "null pointer in args");
+  GridWs w;
+  size_t need = grid_carve(a, (float*)workspace, &w);
+  LRPX_CHECK_ARG(workspace && workspace_bytes >= need, "workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int Q = a->Q, H = a->H, E = a->E, T = a->T;
+  int nt = H >= 256 ? 256 : 128;
+  GemmEpi none{};
+  grid_init_kernel<<<Q, nt, 0, st>>>(*a, w);
+  cudaMemsetAsync(w.uctx, 0, (size_t)Q * T * H * sizeof(float), st);
+  for (int i = T - 1; i >= 0; --i) {
+    grid_cell2_kernel<<<Q, nt, 0, st>>>(*a, w, i);
+    RUN(sgemm<GE_STORE>(w.u, a->W_g2, w.v, Q, 3 * H, H, none, st));
+    grid_post2_kernel<<<Q, nt, 0, st>>>(*a, w, i);
+    RUN(sgemm<GE_STORE>(w.u, a->W_g1, w.v, Q, 2 * H + 2 * E, H, none, st));
+    grid_post1_kernel<<<Q, 256, 0, st>>>(*a, w, i);
+  }
+  grid_glob_kernel<<<Q, 128, 0, st>>>(*a, w);
+  RUN(sgemm<GE_STORE>(w.u, a->W_glob, w.v, Q, a->C, E, none, st));
+  grid_avg_kernel<<<Q, 128, 0, st>>>(*a, w);
+  grid_attn_kernel<<<dim3(a->P, Q), nt, 0, st>>>(*a, w);
+  GemmEpi fe{a->feat, nullptr, w.coefavg, a->req_img, a->P};
+  RUN(sgemm<GE_FEAT>(w.wproj, a->W_proj, a->r_feat, Q * a->P, a->C, H, fe, st));
+  words_norm_kernel<<<Q, 32, 0, st>>>(a->r_words, a->req_t, T);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+size_t lrpx_aoa_decoder_workspace_bytes(const lrpx_aoa_args* a) {
+  if (!a) return 0;
+  return aoa_carve(a, nullptr, nullptr);
+}
+
+int lrpx_aoa_decoder_lrp_f32(const lrpx_aoa_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  LRPX_CHECK_ARG(a, "null args");
+  LRPX_CHECK_ARG(a->B > 0 && a->T > 0 && a->H > 0 && a->E > 0 && a->P > 0 && a->C > 0 && a->V > 0 && a->Q >= 0 &&
+                     a->num_head > 0 && a->H % a->num_head == 0,
+                 "bad dimensions");
+  if (a->Q == 0) return LRPX_OK;
+  LRPX_CHECK_ARG(a->feat && a->A_pre && a->A && a->glob && a->value && a->x && a->h && a->c && a->g && a->i &&
+                     a->ctx && a->caoa && a->caoa_lin && a->alpha && a->pred && a->W_g && a->W_fc && a->W_aoa &&
+                     a->W_v && a->W_proj && a->req_img && a->req_t && a->req_word && a->req_head && a->r_feat &&
+                     a->r_words,
+                 "null pointer in args");
+  AoaWs w;
+  size_t need = aoa_carve(a, (float*)workspace, &w);
+  LRPX_CHECK_ARG(workspace && workspace_bytes >= need, "workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int Q = a->Q, H = a->H, E = a->E, T = a->T;
+  int nt = H >= 256 ? 256 : 128;
+  GemmEpi none{};
+  aoa_init_kernel<<<Q, nt, 0, st>>>(*a, w);
+  RUN(sgemm<GE_STORE>(w.u, a->W_aoa, w.v, Q, H, H, none, st));
+  aoa_ctx_kernel<<<Q, nt, 0, st>>>(*a, w);
+  for (int i = T - 1; i >= 0; --i) {
+    aoa_cell_kernel<<<Q, nt, 0, st>>>(*a, w, i);
+    RUN(sgemm<GE_STORE>(w.u, a->W_g, w.v, Q, E + 2 * H, H, none, st));
+    aoa_post_kernel<<<Q, 256, 0, st>>>(*a, w, i);
+  }
+  aoa_val_kernel<<<dim3(a->P, Q), nt, 0, st>>>(*a, w);
+  GemmEpi pe{a->A, a->A_pre, w.addq, a->req_img, a->P};
+  RUN(sgemm<GE_AOA_PROJ>(w.wval, a->W_v, w.w2, Q * a->P, H, H, pe, st));
+  GemmEpi fe{a->feat, nullptr, nullptr, a->req_img, a->P};
+  RUN(sgemm<GE_FEAT>(w.w2, a->W_proj, a->r_feat, Q * a->P, a->C, H, fe, st));
+  words_norm_kernel<<<Q, 32, 0, st>>>(a->r_words, a->req_t, T);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_fc_lrp_weights_f32(const float* logits, const float* h, const float* ctx, const float* W_fc,
+                            const uint8_t* is_stop, float* w_ctx, float* w_h, int32_t* argmax_out, int B, int V, int H,
+                            void* stream) {
+  LRPX_CHECK_ARG(logits && h && ctx && W_fc && is_stop && w_ctx && w_h && B >= 0 && V > 0 && H > 0, "bad argument");
+  if (B == 0) return LRPX_OK;
+  fc_lrp_weights_kernel<<<B, 256, 0, as_stream(stream)>>>(logits, h, ctx, W_fc, is_stop, w_ctx, w_h, argmax_out, V, H);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+"""ctypes binding of liblrpx.so (include/lrpx.h).  The product path has NO CPU fallback: if the
+library is missing or a call fails, an exception is raised."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblrpx.so")
+
+
+class LrpxError(RuntimeError):
+    pass
+
+
+class ConvShape(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n", "cin", "h", "w", "cout", "kh", "kw", "stride_h", "stride_w", "pad_h",
+                                       "pad_w", "dil_h", "dil_w")]
+
+
+class PoolShape(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n", "c", "h", "w", "kh", "kw", "stride_h", "stride_w", "pad_h", "pad_w")]
+
+
+_P = C.c_void_p
+_GRID_PTRS = ["feat", "avg", "A_pre", "A", "glob_pre", "x1", "x2", "h1", "c1", "h2", "c2", "g1", "i1", "f1", "g2",
+              "i2", "f2", "st", "ctx", "ctx_hat", "alpha", "beta", "pred", "W_g1", "W_g2", "W_fc", "W_glob", "W_proj",
+              "req_img", "req_t", "req_word", "r_feat", "r_words", "r_words_raw"]
+
+
+class GridTDArgs(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("B", "T", "H", "E", "P", "C", "V", "Q")] + [(n, _P) for n in _GRID_PTRS]
+
+
+_AOA_PTRS = ["feat", "A_pre", "A", "glob", "value", "x", "h", "c", "g", "i", "ctx", "caoa", "caoa_lin", "alpha",
+             "pred", "W_g", "W_fc", "W_aoa", "W_v", "W_proj", "req_img", "req_t", "req_word", "req_head", "r_feat",
+             "r_words", "r_words_raw"]
+
+
+class AoaArgs(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("B", "T", "H", "E", "P", "C", "V", "Q", "num_head")] + \
+               [(n, _P) for n in _AOA_PTRS]
+
+
+class TcConvArgs(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n_img", "h", "w", "cin", "ncol", "ksize", "epilogue")] + \
+               [(n, _P) for n in ("a", "wt", "bias", "gain", "row_img", "pool_idx", "x", "out", "out2")]
+
+
+# every symbol include/lrpx.h declares: name -> (restype, argtypes)
+_i, _f, _sz = C.c_int, C.c_float, C.c_size_t
+SYMBOLS = {
+    "lrpx_last_error": (C.c_char_p, []),
+    "lrpx_version": (_i, []),
+    "lrpx_device_cc": (_i, []),
+    "lrpx_conv_rule_s_f32": (_i, [_P, _P, _P, _P, _P, _P, C.POINTER(ConvShape), _i, _P]),
+    "lrpx_conv_rule_rin_f32": (_i, [_P, _P, _P, _P, C.POINTER(ConvShape), _i, _f, _i, _P]),
+    "lrpx_conv_forward_f32": (_i, [_P, _P, _P, _P, C.POINTER(ConvShape), _i, _P]),
+    "lrpx_linear_eps_f32": (_i, [_P, _P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
+    "lrpx_maxpool_forward_f32": (_i, [_P, _P, _P, C.POINTER(PoolShape), _P]),
+    "lrpx_maxpool_wta_f32": (_i, [_P, _P, _P, C.POINTER(PoolShape), _P]),
+    "lrpx_avgpool_prop_f32": (_i, [_P, _P, _P, C.POINTER(PoolShape), _P]),
+    "lrpx_bn_absratio_f32": (_i, [_P, _P, _P, _P, _P, _P, _P, _f, _i, _i, _i, _P]),
+    "lrpx_add_split_f32": (_i, [_P, _P, _P, _P, _P, _sz, _P]),
+    "lrpx_relu_mask_f32": (_i, [_P, _P, _P, _sz, _P]),
+    "lrpx_normalize_relevance_f32": (_i, [_P, _P, _i, _i, _f, _P]),
+    "lrpx_sum_f64": (_i, [_P, _sz, _P, _P]),
+    "lrpx_gridtd_decoder_workspace_bytes": (_sz, [C.POINTER(GridTDArgs)]),
+    "lrpx_gridtd_decoder_lrp_f32": (_i, [C.POINTER(GridTDArgs), _P, _sz, _P]),
+    "lrpx_aoa_decoder_workspace_bytes": (_sz, [C.POINTER(AoaArgs)]),
+    "lrpx_aoa_decoder_lrp_f32": (_i, [C.POINTER(AoaArgs), _P, _sz, _P]),
+    "lrpx_fc_lrp_weights_f32": (_i, [_P, _P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
+    "lrpx_tc_conv": (_i, [C.POINTER(TcConvArgs), _P]),
+    "lrpx_weight_prep_bf16": (_i, [_P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),
+    "lrpx_nchw_f32_to_nhwc_bf16": (_i, [_P, _P, _i, _i, _i, _i, _i, _P]),
+    "lrpx_nhwc_bf16_to_nchw_f32": (_i, [_P, _P, _i, _i, _i, _i, _i, _P]),
+    "lrpx_tc_maxpool2_bf16": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
+    "lrpx_tc_scale_rows": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads liblrpx.so (once).  Raises LrpxError when it has not been built — there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LrpxError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (build()) first; "
+                            "lrpx has no CPU / PyTorch fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().lrpx_last_error().decode(errors="replace")
+        raise LrpxError(f"{what} failed ({rc}): {msg}")

@@ -1,0 +1,277 @@
+"""torch-tensor front ends of the fp32 C-ABI entry points (include/lrpx.h).
+
+torch is used only for device memory and streams; all arithmetic happens in liblrpx.so.
+Every function requires CUDA tensors and raises otherwise (no CPU fallback).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvShape, PoolShape, check, lib
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def _f32(t: torch.Tensor, name="tensor") -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.LrpxError(f"{name} must be a CUDA tensor: lrpx has no CPU fallback")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def conv_shape(a, w, stride, padding, dilation) -> ConvShape:
+    (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
+    n, cin, h, wd = a.shape
+    cout, cin_w, kh, kw = w.shape
+    if cin_w != cin:
+        raise _lib.LrpxError("grouped convolutions are not supported (weight cin != input cin)")
+    return ConvShape(n, cin, h, wd, cout, kh, kw, sh, sw, ph, pw, dh, dw)
+
+
+def conv_out_hw(shp: ConvShape):
+    P = (shp.h + 2 * shp.pad_h - shp.dil_h * (shp.kh - 1) - 1) // shp.stride_h + 1
+    Q = (shp.w + 2 * shp.pad_w - shp.dil_w * (shp.kw - 1) - 1) // shp.stride_w + 1
+    return P, Q
+
+
+NET_POS, NET_NEG, NET_PLAIN = 0, 1, 2
+
+
+def conv_forward(a, w, bias=None, stride=1, padding=0, dilation=1, relu=False):
+    a, w = _f32(a, "a"), _f32(w, "w")
+    bias = _f32(bias) if bias is not None else None
+    shp = conv_shape(a, w, stride, padding, dilation)
+    P, Q = conv_out_hw(shp)
+    out = torch.empty(shp.n, shp.cout, P, Q, device=a.device, dtype=torch.float32)
+    check(lib().lrpx_conv_forward_f32(_ptr(a), _ptr(w), _ptr(bias), _ptr(out), C.byref(shp), int(relu), _stream()),
+          "lrpx_conv_forward_f32")
+    return out
+
+
+def conv_rule_s(a, w, bias, r_out, stride=1, padding=0, dilation=1, net=NET_POS, want_z=False):
+    a, w, r_out = _f32(a, "a"), _f32(w, "w"), _f32(r_out, "r_out")
+    bias = _f32(bias) if bias is not None else None
+    shp = conv_shape(a, w, stride, padding, dilation)
+    P, Q = conv_out_hw(shp)
+    if tuple(r_out.shape) != (shp.n, shp.cout, P, Q):
+        raise _lib.LrpxError(f"r_out shape {tuple(r_out.shape)} != {(shp.n, shp.cout, P, Q)}")
+    s = torch.empty_like(r_out)
+    z = torch.empty_like(r_out) if want_z else None
+    check(lib().lrpx_conv_rule_s_f32(_ptr(a), _ptr(w), _ptr(bias), _ptr(r_out), _ptr(s), _ptr(z), C.byref(shp), net,
+                                     _stream()), "lrpx_conv_rule_s_f32")
+    return (s, z) if want_z else s
+
+
+def conv_rule_rin(a, w, s, stride=1, padding=0, dilation=1, net=NET_POS, scale=1.0, out=None):
+    a, w, s = _f32(a, "a"), _f32(w, "w"), _f32(s, "s")
+    shp = conv_shape(a, w, stride, padding, dilation)
+    acc = out is not None
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib().lrpx_conv_rule_rin_f32(_ptr(a), _ptr(w), _ptr(s), _ptr(out), C.byref(shp), net, float(scale),
+                                       int(acc), _stream()), "lrpx_conv_rule_rin_f32")
+    return out
+
+
+def conv_alpha_beta(a, w, bias, r_out, stride=1, padding=0, dilation=1, alpha=1.0, beta=0.0, ignore_bias=True):
+    """Conv2d alpha-beta rule (LRPtools/lrp_modules.py:124-152): alpha*R(pos-net) - beta*R(neg-net)."""
+    b = None if ignore_bias else bias
+    s = conv_rule_s(a, w, b, r_out, stride, padding, dilation, NET_POS)
+    r = conv_rule_rin(a, w, s, stride, padding, dilation, NET_POS, alpha)
+    if beta != 0.0:
+        s = conv_rule_s(a, w, b, r_out, stride, padding, dilation, NET_NEG)
+        conv_rule_rin(a, w, s, stride, padding, dilation, NET_NEG, -beta, out=r)
+    return r
+
+
+def conv_epsilon(a, w, bias, r_out, stride=1, padding=0, dilation=1, ignore_bias=True):
+    """Conv epsilon rule (Linear rule on the unfolded conv; parity unpinned, see oracle)."""
+    b = None if ignore_bias else bias
+    s = conv_rule_s(a, w, b, r_out, stride, padding, dilation, NET_PLAIN)
+    return conv_rule_rin(a, w, s, stride, padding, dilation, NET_PLAIN, 1.0)
+
+
+def linear_epsilon(a, w, bias, r_out, ignore_bias=True):
+    """Linear epsilon rule (LRPtools/lrp_modules.py:9-24) for a (n,in), w (out,in), r_out (n,out)."""
+    a, w, r_out = _f32(a, "a"), _f32(w, "w"), _f32(r_out, "r_out")
+    bias = _f32(bias) if (bias is not None and not ignore_bias) else None
+    n, fin = a.shape
+    fout = w.shape[0]
+    r_in = torch.empty_like(a)
+    ws = torch.empty(n, fout, device=a.device, dtype=torch.float32)
+    check(lib().lrpx_linear_eps_f32(_ptr(a), _ptr(w), _ptr(bias), _ptr(r_out), _ptr(r_in), _ptr(ws), n, fin, fout,
+                                    int(ignore_bias), _stream()), "lrpx_linear_eps_f32")
+    return r_in
+
+
+def _pool_shape(x, kernel_size, stride, padding) -> PoolShape:
+    (kh, kw) = _pair(kernel_size)
+    (sh, sw) = _pair(stride if stride is not None else kernel_size)
+    (ph, pw) = _pair(padding)
+    n, c, h, w = x.shape
+    return PoolShape(n, c, h, w, kh, kw, sh, sw, ph, pw)
+
+
+def maxpool_forward(x, kernel_size, stride=None, padding=0, return_indices=True):
+    x = _f32(x, "x")
+    shp = _pool_shape(x, kernel_size, stride, padding)
+    oh = (shp.h + 2 * shp.pad_h - shp.kh) // shp.stride_h + 1
+    ow = (shp.w + 2 * shp.pad_w - shp.kw) // shp.stride_w + 1
+    y = torch.empty(shp.n, shp.c, oh, ow, device=x.device, dtype=torch.float32)
+    idx = torch.empty(shp.n, shp.c, oh, ow, device=x.device, dtype=torch.int64) if return_indices else None
+    check(lib().lrpx_maxpool_forward_f32(_ptr(x), _ptr(y), _ptr(idx), C.byref(shp), _stream()),
+          "lrpx_maxpool_forward_f32")
+    return (y, idx) if return_indices else y
+
+
+def maxpool_wta(x, r_out, kernel_size, stride=None, padding=0):
+    x, r_out = _f32(x, "x"), _f32(r_out, "r_out")
+    shp = _pool_shape(x, kernel_size, stride, padding)
+    r_in = torch.empty_like(x)
+    check(lib().lrpx_maxpool_wta_f32(_ptr(x), _ptr(r_out), _ptr(r_in), C.byref(shp), _stream()), "lrpx_maxpool_wta_f32")
+    return r_in
+
+
+def avgpool_prop(x, r_out, kernel_size, stride=None, padding=0):
+    x, r_out = _f32(x, "x"), _f32(r_out, "r_out")
+    shp = _pool_shape(x, kernel_size, stride, padding)
+    r_in = torch.empty_like(x)
+    check(lib().lrpx_avgpool_prop_f32(_ptr(x), _ptr(r_out), _ptr(r_in), C.byref(shp), _stream()),
+          "lrpx_avgpool_prop_f32")
+    return r_in
+
+
+def bn_absratio(x, r_out, running_mean, running_var, gamma, beta, eps):
+    x, r_out = _f32(x, "x"), _f32(r_out, "r_out")
+    n, c = x.shape[0], x.shape[1]
+    hw = x.numel() // (n * c)
+    r_in = torch.empty_like(x)
+    check(lib().lrpx_bn_absratio_f32(_ptr(x), _ptr(r_out), _ptr(r_in), _ptr(_f32(running_mean)), _ptr(_f32(running_var)),
+                                     _ptr(_f32(gamma)), _ptr(_f32(beta)), float(eps), n, c, hw, _stream()),
+          "lrpx_bn_absratio_f32")
+    return r_in
+
+
+def add_split(x1, x2, r_out):
+    x1, x2, r_out = _f32(x1, "x1"), _f32(x2, "x2"), _f32(r_out, "r_out")
+    r1, r2 = torch.empty_like(x1), torch.empty_like(x2)
+    check(lib().lrpx_add_split_f32(_ptr(x1), _ptr(x2), _ptr(r_out), _ptr(r1), _ptr(r2), x1.numel(), _stream()),
+          "lrpx_add_split_f32")
+    return r1, r2
+
+
+def relu_mask(x, r_out):
+    x, r_out = _f32(x, "x"), _f32(r_out, "r_out")
+    r_in = torch.empty_like(r_out)
+    check(lib().lrpx_relu_mask_f32(_ptr(x), _ptr(r_out), _ptr(r_in), x.numel(), _stream()), "lrpx_relu_mask_f32")
+    return r_in
+
+
+def normalize_relevance(x, temperature=1.0):
+    x = _f32(x, "x")
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    y = torch.empty_like(x)
+    check(lib().lrpx_normalize_relevance_f32(_ptr(x), _ptr(y), rows, cols, float(temperature), _stream()),
+          "lrpx_normalize_relevance_f32")
+    return y
+
+
+def sum_f64(x) -> torch.Tensor:
+    x = _f32(x, "x")
+    out = torch.empty(1, device=x.device, dtype=torch.float64)
+    check(lib().lrpx_sum_f64(_ptr(x), x.numel(), _ptr(out), _stream()), "lrpx_sum_f64")
+    return out
+
+
+def fc_lrp_weights(logits, h, ctx, fc_weight, is_stop):
+    """Batched get_lrp_weight_step (gridTDmodel.py:549-578).  is_stop: uint8/bool (V,) device mask."""
+    logits, h, ctx, fc_weight = _f32(logits, "logits"), _f32(h, "h"), _f32(ctx, "ctx"), _f32(fc_weight, "fc")
+    if not is_stop.is_cuda:
+        raise _lib.LrpxError("is_stop must be a CUDA tensor")
+    stop = is_stop.to(torch.uint8).contiguous()
+    B, V = logits.shape
+    H = h.shape[1]
+    w_ctx, w_h = torch.empty_like(h), torch.empty_like(h)
+    am = torch.empty(B, device=h.device, dtype=torch.int32)
+    check(lib().lrpx_fc_lrp_weights_f32(_ptr(logits), _ptr(h), _ptr(ctx), _ptr(fc_weight), _ptr(stop), _ptr(w_ctx),
+                                        _ptr(w_h), _ptr(am), B, V, H, _stream()), "lrpx_fc_lrp_weights_f32")
+    return w_ctx, w_h, am
+
+
+def _fill_args(struct, fields: dict, keep: list):
+    for k, v in fields.items():
+        if torch.is_tensor(v):
+            keep.append(v)
+            setattr(struct, k, v.data_ptr())
+        elif v is None:
+            setattr(struct, k, None)
+        else:
+            setattr(struct, k, v)
+    return struct
+
+
+def gridtd_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, want_raw=False):
+    """state: tensors of lrpx_gridtd_args (stacked over B images), weights: W_g1,W_g2,W_fc,W_glob,W_proj.
+    Returns r_feat (Q,P,C), r_words (Q,T)[, r_words_raw]."""
+    dev = state["feat"].device
+    B, P, Cc = state["feat"].shape
+    T, H = state["g1"].shape[1], state["g1"].shape[2]
+    E = state["glob_pre"].shape[1]
+    V = state["pred"].shape[2]
+    Q = int(req_img.numel())
+    keep = []
+    a = _lib.GridTDArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q)
+    f = {k: _f32(state[k], k) for k in ["feat", "avg", "A_pre", "A", "glob_pre", "x1", "x2", "h1", "c1", "h2", "c2",
+                                        "g1", "i1", "f1", "g2", "i2", "f2", "st", "ctx", "ctx_hat", "alpha", "beta",
+                                        "pred"]}
+    f.update({k: _f32(weights[k], k) for k in ["W_g1", "W_g2", "W_fc", "W_glob", "W_proj"]})
+    f["req_img"] = req_img.to(device=dev, dtype=torch.int32).contiguous()
+    f["req_t"] = req_t.to(device=dev, dtype=torch.int32).contiguous()
+    f["req_word"] = req_word.to(device=dev, dtype=torch.int32).contiguous()
+    r_feat = torch.empty(Q, P, Cc, device=dev, dtype=torch.float32)
+    r_words = torch.zeros(Q, T, device=dev, dtype=torch.float32)
+    r_raw = torch.zeros(Q, T, device=dev, dtype=torch.float32) if want_raw else None
+    f.update(r_feat=r_feat, r_words=r_words, r_words_raw=r_raw)
+    _fill_args(a, f, keep)
+    nbytes = lib().lrpx_gridtd_decoder_workspace_bytes(C.byref(a))
+    ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
+    check(lib().lrpx_gridtd_decoder_lrp_f32(C.byref(a), _ptr(ws), nbytes, _stream()), "lrpx_gridtd_decoder_lrp_f32")
+    return (r_feat, r_words, r_raw) if want_raw else (r_feat, r_words)
+
+
+def aoa_decoder_lrp(state: dict, weights: dict, num_head, req_img, req_t, req_word, req_head, want_raw=False):
+    dev = state["feat"].device
+    B, P, Cc = state["feat"].shape
+    T, H = state["g"].shape[1], state["g"].shape[2]
+    E = state["x"].shape[2] - H
+    V = state["pred"].shape[2]
+    Q = int(req_img.numel())
+    keep = []
+    a = _lib.AoaArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q, num_head=num_head)
+    f = {k: _f32(state[k], k) for k in ["feat", "A_pre", "A", "glob", "value", "x", "h", "c", "g", "i", "ctx", "caoa",
+                                        "caoa_lin", "alpha", "pred"]}
+    f.update({k: _f32(weights[k], k) for k in ["W_g", "W_fc", "W_aoa", "W_v", "W_proj"]})
+    for k, v in (("req_img", req_img), ("req_t", req_t), ("req_word", req_word), ("req_head", req_head)):
+        f[k] = v.to(device=dev, dtype=torch.int32).contiguous()
+    r_feat = torch.empty(Q, P, Cc, device=dev, dtype=torch.float32)
+    r_words = torch.zeros(Q, T, device=dev, dtype=torch.float32)
+    r_raw = torch.zeros(Q, T, device=dev, dtype=torch.float32) if want_raw else None
+    f.update(r_feat=r_feat, r_words=r_words, r_words_raw=r_raw)
+    _fill_args(a, f, keep)
+    nbytes = lib().lrpx_aoa_decoder_workspace_bytes(C.byref(a))
+    ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
+    check(lib().lrpx_aoa_decoder_lrp_f32(C.byref(a), _ptr(ws), nbytes, _stream()), "lrpx_aoa_decoder_lrp_f32")
+    return (r_feat, r_words, r_raw) if want_raw else (r_feat, r_words)
