@@ -207,51 +207,70 @@ int lrpx_fc_lrp_weights_f32(const float* logits, const float* h, const float* ct
                             int B, int V, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Tensor-core path (tcgen05 + TMA, bf16 operands / fp32 accumulate), NHWC.
- * One implicit-GEMM kernel family serves the activation-producing forward, the z+ pass and the
- * relevance (transposed-conv) pass of 3x3/stride-1/pad-1 and 1x1 convolutions:
- *      acc[m][n] = sum_{r,s,c} A[pixel m shifted by (r,s)][c] * Wt[n][(r,s,c)]
+ * Tensor-core path (tcgen05 + TMA, bf16 operands / fp32 accumulate in TMEM).
+ *
+ * Layout "PF" (padded-flat NHWC bf16): an image of h x w pixels and C channels is a block of
+ * (h+1)*(w+1) pixel rows of C bf16; block row 0 and block column 0 are zero padding and pixel (y,x) sits
+ * at block offset (y+1)*(w+1)+(x+1).  The right/bottom halo of one image is the left/top padding of what
+ * follows, so the 3x3 neighbour (dy,dx) of flat row p is row p + dy*(w+1) + dx and a 3x3/stride-1/pad-1
+ * convolution is 9 accumulated GEMMs over row-shifted views of one 2-D (rows x channels) tensor.
+ *
+ * One implicit-GEMM kernel family serves the activation-producing forward (+ z+), and the relevance
+ * (transposed-conv) pass:      acc[p][n] = sum_{tap,c} A[p + off(tap)][c] * Wt[n][tap*cin + c]
+ *
+ * Relevance chain (alpha=1, beta=0; LRPtools/lrp_modules.py:81-84,134, LRPtools/utils.py:16-31): with
+ * gain_l = a_{l+1} / safe(z+_l) (per image, independent of the explained word) the per-explanation work of
+ * one conv layer is ONE contraction   s_{l-1} = gain_{l-1} (.) (W+_l^T * s_l),   s_l = R_{l+1}/safe(z+_l).
  * ------------------------------------------------------------------------------------------- */
 enum {
-  /* out_bf16[m][n] = relu(acc[m][n] + bias[n])                      (forward, lrp_wrapper.py:70) */
-  LRPX_TC_EPI_BIAS_RELU = 0,
-  /* dual tile: columns [0,BN/2) hold W, [BN/2,BN) hold W+ of the same output channels:
-   *   act[m][n]  = relu(acc_w + bias[n])                            (forward)
-   *   gain[m][n] = act[m][n] / (acc_wplus + 1e-7*[acc_wplus==0])    (a_{l+1}/safe(z+_l), utils.py:16-18) */
+  /* dual tile: Wt holds, per tile of `half` output channels, the W rows then the W+ rows (ncol = 2*cout):
+   *   act[p][n]  = relu(acc_w + bias[n])                                (forward, lrp_wrapper.py:70)
+   *   gain[p][n] = act[p][n] / safe(acc_w+)   (gain_mode 0)   or   1 / safe(acc_w+)   (gain_mode 1)
+   *   safe(z) = z + 1e-7*[z==0]                                          (utils.py:16-18)
+   * out = act (PF bf16), out2 = gain (PF bf16); padding rows are written as zeros. */
   LRPX_TC_EPI_FWD_GAIN = 1,
-  /* s_prev[m][n] = acc[m][n] * gain[img(m)][hw(m)][n]               (R_in = a (.) c then / z+ of the
-   *                                                                   layer below; lrp_modules.py:134, utils.py:26-30) */
+  /* out[p][n] = bf16(acc[p][n] * gain[img(p)][rem(p)][n]); padding rows -> 0
+   *   (R_in = a (.) c, then the division by z+ of the layer below: lrp_modules.py:134, utils.py:26-30) */
   LRPX_TC_EPI_MUL = 2,
-  /* as MUL but the tile is at pooled resolution: gain is pooled-size, `pool_idx` holds the 2-bit
-   * argmax of each 2x2 window; writes 4 fine positions (value at the winner, 0 elsewhere)
-   * (max-pool winner-take-all, lrp_modules.py:186-191) */
+  /* as MUL but the tile is at pooled resolution (h, w = pooled size): `gain` and `pool_idx` are pooled-size
+   * PF tensors, pool_idx holds the argmax 0..3 (dy*2+dx) of each 2x2 window; every pooled pixel writes its
+   * 4 fine pixels in the (2h x 2w) PF output, the product at the winner and 0 elsewhere
+   *   (max-pool winner-take-all, lrp_modules.py:186-191) */
   LRPX_TC_EPI_MUL_UNPOOL = 3,
-  /* first layer: acc has 2*cin_img columns (W+ block, W- block);
-   *   r_img[n][c][h][w] (fp32 NCHW) = max(x,0)*acc[c] + min(x,0)*acc[cin_img + c]   (lrp_modules.py:81-84) */
+  /* first layer: ncol = 16, acc columns 0..2 = W+^T s, 3..5 = W-^T s;
+   *   out_f32[e][c][y][x] (NCHW, unpadded) = max(x,0)*acc[c] + min(x,0)*acc[3+c]   (lrp_modules.py:81-84) */
   LRPX_TC_EPI_INPUT = 4,
-  /* out_f32[m][n] = acc[m][n] (debug / generic) */
+  /* out_f32[p][n] = acc[p][n] (debug / tests of the GEMM machinery) */
   LRPX_TC_EPI_STORE_F32 = 5,
 };
 
 typedef struct {
-  int n_img;            /* images (or explanations) in A                                  */
-  int h, w;             /* spatial size of A (== output size: stride 1, "same" padding)   */
-  int cin;              /* channels of A (multiple of 16)                                 */
-  int ncol;             /* rows of Wt == GEMM N (multiple of 16)                          */
-  int ksize;            /* 1 or 3                                                         */
-  int epilogue;         /* LRPX_TC_EPI_*                                                  */
-  const void* a;        /* bf16 (n_img,h,w,cin)                                           */
-  const void* wt;       /* bf16 (ncol, ksize*ksize*cin), K ordered (r,s,c)                */
-  const float* bias;    /* (ncol) or NULL                                                 */
-  const void* gain;     /* bf16, see epilogues                                            */
-  const int32_t* row_img; /* (n_img) image index of each explanation for `gain`/`x`; NULL = identity */
-  const uint8_t* pool_idx;/* (n_gain_img, h, w, ncol) argmax 0..3 for MUL_UNPOOL          */
-  const float* x;       /* fp32 NCHW input images for EPI_INPUT                           */
-  void* out;            /* bf16 NHWC (or fp32, see epilogue)                              */
-  void* out2;           /* second output (gain) for FWD_GAIN                              */
+  int n_img;            /* PF blocks in A (images or explanations)                                */
+  int h, w;             /* unpadded spatial size of A's blocks (== output size)                   */
+  int cin;              /* channels of A (multiple of 64)                                         */
+  int ncol;             /* rows of Wt == GEMM N                                                   */
+  int ksize;            /* 1 or 3                                                                 */
+  int epilogue;         /* LRPX_TC_EPI_*                                                          */
+  int gain_mode;        /* FWD_GAIN only                                                          */
+  const void* a;        /* bf16 PF (n_img, (h+1)*(w+1), cin)                                      */
+  const void* wt;       /* bf16 (ncol, ksize*ksize*cin), K ordered (tap, channel)                 */
+  const float* bias;    /* FWD_GAIN: (cout) or NULL                                               */
+  const void* gain;     /* bf16 PF (n_gain_img, blk, ncol), MUL / MUL_UNPOOL                      */
+  const int32_t* row_img; /* (n_img) block of `gain`/`pool_idx`/`x` used by each block of A; NULL = identity */
+  const uint8_t* pool_idx;/* PF (n_gain_img, blk, ncol) argmax bytes, MUL_UNPOOL                  */
+  const float* x;       /* fp32 NCHW (n_x, 3, h, w) input images, INPUT                           */
+  void* out;
+  void* out2;
 } lrpx_tc_conv_args;
 
 int lrpx_tc_conv(const lrpx_tc_conv_args* args, void* stream);
+
+/* First VGG layer forward on CUDA cores (cin = 3 is no tensor-core shape): from fp32 NCHW images
+ *   act  = relu(conv(x, W) + b)                       -> PF bf16 (n, blk, cout)
+ *   gain = act / safe(conv(x+, W+) + conv(x-, W-))    -> PF bf16                  (lrp_modules.py:81-84)
+ * cout must be a multiple of 8; 3x3, stride 1, pad 1. */
+int lrpx_tc_first_fwd(const float* x, const float* w, const float* bias, void* act, void* gain, int n, int h, int wd,
+                      int cout, void* stream);
 
 /* One-time weight preparation (replaces the per-call PosNetConv/NegNetConv clones,
  * lrp_modules.py:59-76): from fp32 (cout,cin,kh,kw) build bf16 GEMM operands.
@@ -259,21 +278,23 @@ int lrpx_tc_conv(const lrpx_tc_conv_args* args, void* stream);
  *   mode 1: forward W+   Wt[co][(r,s,ci)]            = max(W,0)
  *   mode 2: relevance    Wt[ci][(r,s,co)]            = max(W[co][ci][kh-1-r][kw-1-s],0)   (transposed conv)
  *   mode 3: relevance W- Wt[ci][(r,s,co)]            = min(W[co][ci][kh-1-r][kw-1-s],0)
- * rows/cols beyond the source are zero-filled up to (rows_pad, k_pad_c) so tiles never read junk. */
+ * rows/cols beyond the source are zero-filled up to (rows_pad, chan_pad) so tiles never read junk. */
 int lrpx_weight_prep_bf16(const float* w, void* wt, int cout, int cin, int kh, int kw, int mode, int rows_pad,
                           int chan_pad, void* stream);
 
-/* NCHW fp32 <-> NHWC bf16 helpers (image / target in, nothing else is converted on the hot path) */
-int lrpx_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int n, int c, int h, int w, int c_pad, void* stream);
-int lrpx_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int n, int c, int h, int w, int c_pad, void* stream);
-/* 2x2/2 max-pool on NHWC bf16 with argmax (0..3, PyTorch scan order) and pooled gain:
- *   pooled[m][c] = max, idx[m][c], gain_pooled[m][c] = gain_fine[winner][c]
- * (gain_fine = a/safe(z+) at conv-output resolution; at the winner a == pooled max) */
+/* 2x2/2 max-pool on PF bf16 with argmax (0..3 = dy*2+dx, PyTorch scan order: first maximum wins, NaN wins)
+ * and the gain gathered at the winner:  pooled[p][c] = max, idx[p][c], gain_pooled[p][c] = gain_fine[winner][c].
+ * (h, w) is the fine size (even).  gain_fine/gain_pooled may both be NULL; idx may be NULL. */
 int lrpx_tc_maxpool2_bf16(const void* act, const void* gain_fine, void* pooled, uint8_t* idx, void* gain_pooled,
                           int n, int h, int w, int c, void* stream);
-/* s_top[m][c] = bf16( r_feat[m][c] * rz[img][hw][c] ) — entry of the relevance chain (fp32 in) */
-int lrpx_tc_scale_rows(const float* r, const void* gain, const int32_t* row_img, void* out, int n_expl, int hw, int c,
-                       void* stream);
+/* entry of the relevance chain:  s_top[e][pf(p)][c] = bf16( r[e][p][c] * rz[row_img[e]][pf(p)][c] ),
+ * r is fp32 pixel-major (n_expl, h*w, c) as produced by the decoder kernels; padding rows -> 0 */
+int lrpx_tc_scale_rows(const float* r, const void* rz, const int32_t* row_img, void* out, int n_expl, int h, int w,
+                       int c, void* stream);
+/* PF bf16 (n, blk, c) -> dense fp32: layout 0 = pixel-major (n, h*w, c), 1 = NCHW (n, c, h, w) */
+int lrpx_tc_pf_to_dense_f32(const void* src, float* dst, int n, int h, int w, int c, int layout, void* stream);
+/* dense fp32 NCHW (n, c, h, w) -> PF bf16 (n, blk, c_pad), channels >= c zero-filled */
+int lrpx_tc_nchw_to_pf_bf16(const float* src, void* dst, int n, int c, int h, int w, int c_pad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,606 @@
-// placeholder until the tcgen05 kernel lands
+// Tensor-core relevance / forward convolution for sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM),
+// operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B), persistent warp-specialised CTAs.
+//
+// Reference arithmetic being replaced (per 3x3/stride-1/pad-1 conv layer, alpha=1 beta=0):
+//   LRPtools/lrp_modules.py:81-84   z+ = conv(a+, W+) + conv(a-, W-)
+//   LRPtools/utils.py:16-18,26-30   s = R / (z+ + 1e-7*[z+ == 0]);  c = d z+/d a (s);  R_in = a (.) c
+//   LRPtools/lrp_modules.py:186-191 max-pool winner-take-all
+//
+// Data layout ("PF", padded-flat NHWC bf16).  An image of h x w pixels and C channels is a block of
+// (h+1)*(w+1) pixel rows of C bf16 each; block row 0 and block column 0 are zero padding, pixel (y,x)
+// lives at block offset (y+1)*(w+1) + (x+1).  The right/bottom halo of an image is the left/top padding of
+// what follows, so for a flat pixel index p the 3x3 neighbour (dy,dx) is simply row p + dy*(w+1) + dx and
+// a 3x3 convolution is 9 accumulated GEMMs over row-shifted views of ONE 2-D tensor (rows x channels):
+// no im2col, every TMA box is a plain 2-D tile, out-of-range rows are zero-filled by TMA.
+//
+// GEMM:  acc[p][n] = sum_{tap, c} A[p + off(tap)][c] * Wt[n][tap*cin + c]      (both operands K-major)
+//   tile 128 (pixels) x BN (<=256) per CTA iteration, K step 64 channels (one 128-byte swizzle row),
+//   tcgen05.mma.cta_group::1.kind::f16  M=128, N=BN, K=16 (4 per K step), accumulators double-buffered in
+//   TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+// Warp roles: warp 0 = TMA producer (one thread), warp 1 = TMEM allocator + MMA issuer (one thread),
+//             warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
 #include "lrpx_common.cuh"
-extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* args, void* stream) {
-  lrpx::set_error("lrpx_tc_conv: not built yet");
-  return LRPX_E_UNSUPPORTED;
+#include <cuda.h>
+#include <mutex>
+
+namespace lrpx {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;             // channels per K step (128 bytes of bf16)
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_SMEM_BYTES = 200 * 1024;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KiB
+
+struct TcParams {
+  int m_total;       // rows of A (n_img * blk)
+  int blk;           // (h+1)*(w+1)
+  int h, w;          // unpadded spatial size of A's images
+  int wp1;           // w + 1
+  int cin;           // channels of A
+  int ncol;          // GEMM N (rows of Wt)
+  int bn;            // N tile
+  int half;          // FWD_GAIN: output channels per tile (= bn/2)
+  int taps;          // 1 or 9
+  int kc_per_tap;    // cin / 64
+  int num_m_tiles, num_n_tiles;
+  int stages;
+  int out_c;         // channel pitch of out / gain (elements per pixel row)
+  int gain_mode;     // FWD_GAIN: 0 -> act/safe(z+), 1 -> 1/safe(z+)
+  const float* bias;
+  const __nv_bfloat16* gain;
+  const int32_t* row_img;
+  const uint8_t* pool_idx;
+  const float* x;
+  void* out;
+  void* out2;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a broken pipeline traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (it == 1024) t0 = clock64();
+    if (it > 1024 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("lrpx tc_conv: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address
+  d |= (uint64_t)1 << 16;                          // leading-dimension byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride-dimension byte offset
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+#define TMEM_LD_X32(taddr, v)                                                                                   \
+  asm volatile(                                                                                                 \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                 \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "   \
+      "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                                               \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),         \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),   \
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])  \
+      : "r"(taddr)                                                                                              \
+      : "memory")
+#define TMEM_LD_X16(taddr, v)                                                                                   \
+  asm volatile(                                                                                                 \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                                 \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                          \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),         \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])    \
+      : "r"(taddr)                                                                                              \
+      : "memory")
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+// ------------------------------------------------------------------------------------------ epilogues
+// One thread owns one accumulator row (= one PF pixel) and walks its columns in chunks of 32.
+struct RowInfo {
+  int row;       // flat PF row
+  int e;         // image / explanation block
+  int rem;       // offset inside the block
+  int a, b;      // PF row / column inside the block (0 = padding)
+  bool in_range; // row < m_total
+  bool valid;    // a real pixel
+};
+
+__device__ __forceinline__ RowInfo row_info(const TcParams& p, int row) {
+  RowInfo r;
+  r.row = row;
+  r.in_range = row < p.m_total;
+  int rr = r.in_range ? row : 0;
+  r.e = rr / p.blk;
+  r.rem = rr - r.e * p.blk;
+  r.a = r.rem / p.wp1;
+  r.b = r.rem - r.a * p.wp1;
+  r.valid = r.in_range && r.a > 0 && r.b > 0;
+  return r;
+}
+
+// out[row][col..col+32) = bf16(acc * gain[img][rem][col..])
+__device__ __forceinline__ void epi_mul(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32]) {
+  if (!r.in_range) return;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * p.out_c + col;
+  uint4 o[4];
+  if (r.valid) {
+    int img = p.row_img ? p.row_img[r.e] : r.e;
+    const __nv_bfloat16* g = p.gain + ((size_t)img * p.blk + r.rem) * p.out_c + col;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 gv = ldg_nc_v4(g + 8 * q);
+      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float a0 = __uint_as_float(v[8 * q + 2 * k]) * bf16_lo(gw[k]);
+        float a1 = __uint_as_float(v[8 * q + 2 * k + 1]) * bf16_hi(gw[k]);
+        ow[k] = pack_bf16(a0, a1);
+      }
+      o[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(out)[q] = o[q];
+}
+
+// tile at pooled resolution; scatter to the 2x2 fine pixels chosen by pool_idx (others get 0)
+__device__ __forceinline__ void epi_mul_unpool(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32]) {
+  if (!r.in_range) return;
+  const int wf1 = 2 * p.w + 1;
+  const size_t blk_f = (size_t)(2 * p.h + 1) * wf1;
+  __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.e * blk_f * p.out_c + col;
+  uint32_t prod[16];   // bf16x2 products
+  uint32_t sel[8];     // packed argmax bytes
+  if (r.valid) {
+    int img = p.row_img ? p.row_img[r.e] : r.e;
+    size_t go = ((size_t)img * p.blk + r.rem) * p.out_c + col;
+    const __nv_bfloat16* g = p.gain + go;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 gv = ldg_nc_v4(g + 8 * q);
+      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float a0 = __uint_as_float(v[8 * q + 2 * k]) * bf16_lo(gw[k]);
+        float a1 = __uint_as_float(v[8 * q + 2 * k + 1]) * bf16_hi(gw[k]);
+        prod[4 * q + k] = pack_bf16(a0, a1);
+      }
+    }
+    uint4 s0 = ldg_nc_v4(p.pool_idx + go), s1 = ldg_nc_v4(p.pool_idx + go + 16);
+    sel[0] = s0.x; sel[1] = s0.y; sel[2] = s0.z; sel[3] = s0.w;
+    sel[4] = s1.x; sel[5] = s1.y; sel[6] = s1.z; sel[7] = s1.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int fr = 2 * r.a - 1 + (k >> 1), fc = 2 * r.b - 1 + (k & 1);
+    if (fr < 0 || fc < 0) continue;
+    uint4* dst = reinterpret_cast<uint4*>(outb + ((size_t)fr * wf1 + fc) * p.out_c);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t ow[4] = {0, 0, 0, 0};
+      if (r.valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // channels 8q+2j (low half) and 8q+2j+1 (high half); argmax bytes sit in sel[(8q+2j)/4]
+          uint32_t sw = sel[2 * q + (j >> 1)];
+          uint32_t b0 = (sw >> (16 * (j & 1))) & 0xFF, b1 = (sw >> (16 * (j & 1) + 8)) & 0xFF;
+          uint32_t pv = prod[4 * q + j];
+          ow[j] = (b0 == (uint32_t)k ? (pv & 0xFFFFu) : 0u) | (b1 == (uint32_t)k ? (pv & 0xFFFF0000u) : 0u);
+        }
+      }
+      dst[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+}
+
+// forward + gain: vw = acc of W, vp = acc of W+ (same 32 output channels starting at `ch`)
+__device__ __forceinline__ void epi_fwd_gain(const TcParams& p, const RowInfo& r, int ch, const uint32_t (&vw)[32],
+                                             const uint32_t (&vp)[32]) {
+  if (!r.in_range) return;
+  __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * p.out_c + ch;
+  __nv_bfloat16* gn = reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)r.row * p.out_c + ch;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t aw[4] = {0, 0, 0, 0}, gw[4] = {0, 0, 0, 0};
+    if (r.valid) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float z0 = __uint_as_float(vw[8 * q + 2 * k]), z1 = __uint_as_float(vw[8 * q + 2 * k + 1]);
+        if (p.bias) {
+          z0 += __ldg(p.bias + ch + 8 * q + 2 * k);
+          z1 += __ldg(p.bias + ch + 8 * q + 2 * k + 1);
+        }
+        float a0 = fmaxf(z0, 0.f), a1 = fmaxf(z1, 0.f);
+        float zp0 = __uint_as_float(vp[8 * q + 2 * k]), zp1 = __uint_as_float(vp[8 * q + 2 * k + 1]);
+        float g0 = safe_div(p.gain_mode ? 1.f : a0, zp0), g1 = safe_div(p.gain_mode ? 1.f : a1, zp1);
+        aw[k] = pack_bf16(a0, a1);
+        gw[k] = pack_bf16(g0, g1);
+      }
+    }
+    reinterpret_cast<uint4*>(act)[q] = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+    reinterpret_cast<uint4*>(gn)[q] = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+  }
+}
+
+// first layer: acc columns 0..2 = W+^T s, 3..5 = W-^T s  ->  fp32 NCHW heat-map
+__device__ __forceinline__ void epi_input(const TcParams& p, const RowInfo& r, const uint32_t (&v)[16]) {
+  if (!r.valid) return;
+  int img = p.row_img ? p.row_img[r.e] : r.e;
+  size_t hw = (size_t)p.h * p.w;
+  size_t pix = (size_t)(r.a - 1) * p.w + (r.b - 1);
+  float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float xv = __ldg(p.x + ((size_t)img * 3 + c) * hw + pix);
+    out[((size_t)r.e * 3 + c) * hw + pix] =
+        fmaxf(xv, 0.f) * __uint_as_float(v[c]) + fminf(xv, 0.f) * __uint_as_float(v[3 + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 1024-byte aligned tile ring (SWIZZLE_128B atoms are 1024 bytes)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
+  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = p.taps * p.kc_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[b]), TC_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (one thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+        const int m0 = m_tile * TC_BM, n0 = n_tile * p.bn;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int off = (p.taps == 9) ? ((tap / 3) - 1) * p.wp1 + ((tap % 3) - 1) : 0;
+          for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            mbar_expect_tx(fb, stage_bytes);
+            tma_load_2d(sa, &tmA, fb, kc * TC_BK, m0 + off);
+            tma_load_2d(sa + TC_A_BYTES, &tmB, fb, tap * p.cin + kc * TC_BK, n0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.bn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&tmem_empty_bar[buf]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&empty_bar[stage]));       // frees the smem stage once these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(smem_u32(&tmem_full_bar[buf]));        // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ================================ epilogue warps
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+      const int m0 = m_tile * TC_BM, n0 = n_tile * p.bn;
+      mbar_wait(smem_u32(&tmem_full_bar[buf]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
+      const RowInfo r = row_info(p, m0 + quarter * 32 + lane);
+      if (EPI == LRPX_TC_EPI_INPUT) {
+        uint32_t v[16];
+        TMEM_LD_X16(taddr, v);
+        tmem_ld_wait();
+        epi_input(p, r, v);
+      } else if (EPI == LRPX_TC_EPI_FWD_GAIN) {
+        for (int c = 0; c < p.half; c += 32) {
+          uint32_t vw[32], vp[32];
+          TMEM_LD_X32(taddr + c, vw);
+          TMEM_LD_X32(taddr + p.half + c, vp);
+          tmem_ld_wait();
+          epi_fwd_gain(p, r, n_tile * p.half + c, vw, vp);
+        }
+      } else {
+        for (int c = 0; c < p.bn; c += 32) {
+          uint32_t v[32];
+          TMEM_LD_X32(taddr + c, v);
+          tmem_ld_wait();
+          if (EPI == LRPX_TC_EPI_MUL) {
+            epi_mul(p, r, n0 + c, v);
+          } else if (EPI == LRPX_TC_EPI_MUL_UNPOOL) {
+            epi_mul_unpool(p, r, n0 + c, v);
+          } else {  // STORE_F32
+            if (r.in_range) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c);
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                     __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor (rows x cols, cols contiguous), box = (64 cols, box_rows), SWIZZLE_128B, zero OOB fill
+static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return LRPX_E_CUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r, (unsigned long long)rows,
+              (unsigned long long)cols, box_rows);
+    return LRPX_E_CUDA;
+  }
+  return LRPX_OK;
+}
+
+template <int EPI>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tc_conv_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
+    return LRPX_E_CUDA;
+  }
+  tc_conv_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma, mb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("tc_conv_kernel launch failed: %s", cudaGetErrorString(e));
+    return LRPX_E_CUDA;
+  }
+  return LRPX_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace lrpx
+
+using namespace lrpx;
+
+extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
+  LRPX_CHECK_ARG(a, "null args");
+  LRPX_CHECK_ARG(a->n_img > 0 && a->h > 0 && a->w > 0, "bad image dimensions");
+  LRPX_CHECK_ARG(a->cin > 0 && a->cin % TC_BK == 0, "cin must be a multiple of 64");
+  LRPX_CHECK_ARG(a->ksize == 1 || a->ksize == 3, "ksize must be 1 or 3");
+  LRPX_CHECK_ARG(a->a && a->wt && a->out, "null pointer");
+  LRPX_CHECK_ARG(a->ncol > 0 && a->ncol % 16 == 0, "ncol must be a multiple of 16");
+  const int epi = a->epilogue;
+  TcParams p{};
+  p.h = a->h; p.w = a->w; p.wp1 = a->w + 1;
+  p.blk = (a->h + 1) * (a->w + 1);
+  long long m_total = (long long)a->n_img * p.blk;
+  LRPX_CHECK_ARG(m_total < (1LL << 31) - 4096, "too many pixel rows for one call");
+  p.m_total = (int)m_total;
+  p.cin = a->cin; p.ncol = a->ncol;
+  p.taps = a->ksize * a->ksize;
+  p.kc_per_tap = a->cin / TC_BK;
+  p.bias = a->bias; p.gain = reinterpret_cast<const __nv_bfloat16*>(a->gain);
+  p.row_img = a->row_img; p.pool_idx = a->pool_idx; p.x = a->x; p.out = a->out; p.out2 = a->out2;
+  p.gain_mode = a->gain_mode;
+
+  if (epi == LRPX_TC_EPI_FWD_GAIN) {
+    // Wt holds, per tile of `half` output channels, the W rows followed by the W+ rows: ncol = 2 * cout
+    LRPX_CHECK_ARG(a->out2, "FWD_GAIN needs out2 (gain)");
+    int cout = a->ncol / 2;
+    LRPX_CHECK_ARG(cout % 32 == 0, "FWD_GAIN: output channels must be a multiple of 32");
+    p.half = cout < 128 ? cout : 128;
+    LRPX_CHECK_ARG(cout % p.half == 0, "FWD_GAIN: output channels must be <128 or a multiple of 128");
+    p.bn = 2 * p.half;
+    p.out_c = cout;
+  } else if (epi == LRPX_TC_EPI_INPUT) {
+    LRPX_CHECK_ARG(a->ncol == 16 && a->x, "INPUT epilogue: ncol must be 16 (3 W+ cols, 3 W- cols, padding) and x set");
+    p.bn = 16;
+    p.out_c = 3;
+  } else {
+    LRPX_CHECK_ARG(epi == LRPX_TC_EPI_MUL || epi == LRPX_TC_EPI_MUL_UNPOOL || epi == LRPX_TC_EPI_STORE_F32,
+                   "unknown epilogue");
+    LRPX_CHECK_ARG(a->ncol % 32 == 0, "ncol must be a multiple of 32 for this epilogue");
+    if (epi != LRPX_TC_EPI_STORE_F32) LRPX_CHECK_ARG(a->gain, "gain required");
+    if (epi == LRPX_TC_EPI_MUL_UNPOOL) LRPX_CHECK_ARG(a->pool_idx, "pool_idx required");
+    p.bn = a->ncol <= 256 ? a->ncol : 256;
+    LRPX_CHECK_ARG(a->ncol % p.bn == 0, "ncol must be <= 256 or a multiple of 256");
+    p.out_c = a->ncol;
+  }
+  p.num_n_tiles = a->ncol / p.bn;
+  p.num_m_tiles = (p.m_total + TC_BM - 1) / TC_BM;
+  const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;
+  p.stages = (TC_SMEM_BYTES - 1024) / stage_bytes;
+  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  LRPX_CHECK_ARG(p.stages >= 2, "tile does not fit in shared memory");
+
+  CUtensorMap ma, mb;
+  int rc = make_map_2d(&ma, a->a, (uint64_t)p.m_total, (uint64_t)a->cin, TC_BM);
+  if (rc) return rc;
+  rc = make_map_2d(&mb, a->wt, (uint64_t)a->ncol, (uint64_t)p.taps * a->cin, (uint32_t)p.bn);
+  if (rc) return rc;
+
+  int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  cudaStream_t st = as_stream(stream);
+  switch (epi) {
+    case LRPX_TC_EPI_FWD_GAIN: return launch_tc<LRPX_TC_EPI_FWD_GAIN>(ma, mb, p, grid, st);
+    case LRPX_TC_EPI_MUL: return launch_tc<LRPX_TC_EPI_MUL>(ma, mb, p, grid, st);
+    case LRPX_TC_EPI_MUL_UNPOOL: return launch_tc<LRPX_TC_EPI_MUL_UNPOOL>(ma, mb, p, grid, st);
+    case LRPX_TC_EPI_INPUT: return launch_tc<LRPX_TC_EPI_INPUT>(ma, mb, p, grid, st);
+    default: return launch_tc<LRPX_TC_EPI_STORE_F32>(ma, mb, p, grid, st);
+  }
 }

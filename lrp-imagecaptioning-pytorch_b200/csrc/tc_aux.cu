@@ -1,12 +1,18 @@
-// Layout / pooling helpers of the tensor-core path (NHWC bf16), all HBM-bound element-wise kernels.
+// Helpers of the tensor-core path: weight preparation, the cin=3 first layer, 2x2 max-pool with argmax and
+// gain gather, chain entry scaling and PF <-> dense conversions.  All HBM-bound, 16-byte vector accesses.
+// PF layout: see include/lrpx.h ("padded-flat NHWC bf16").
 #include "lrpx_common.cuh"
 
 namespace lrpx {
 
+static inline int grid_for(long long total, int block = 256) {
+  long long g = (total + block - 1) / block, cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
 // fp32 (cout,cin,kh,kw) -> bf16 GEMM operand, see lrpx_weight_prep_bf16 in lrpx.h
 __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, int cout, int cin,
                                    int kh, int kw, int mode, int rows_pad, int chan_pad) {
-  // output (rows_pad, kh*kw, chan_pad)
   long long total = (long long)rows_pad * kh * kw * chan_pad;
   bool transposed = mode >= 2;
   int rows = transposed ? cin : cout, chans = transposed ? cout : cin;
@@ -30,102 +36,199 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n, int c, int hw,
-                                    int c_pad) {
-  long long total = (long long)n * hw * c_pad;
+// ---------------------------------------------------------------- first layer (cin = 3), CUDA cores
+// lane = 4 pixels x 8 channel groups of 8 channels: a warp writes 4 contiguous 128-byte PF rows (cout = 64).
+template <int CG>   // channel groups per pixel = cout / 8
+__global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, uint4* __restrict__ act,
+                                                        uint4* __restrict__ gain, int n, int h, int wd) {
+  extern __shared__ float ws[];        // [27][cout] transposed weights, then bias[cout]
+  const int cout = CG * 8;
+  for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
+    int k = i / cout, co = i % cout;
+    ws[i] = w[co * 27 + k];            // k = (ci, r, s) of (cout,3,3,3)
+  }
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) ws[27 * cout + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int wp1 = wd + 1, blk = (h + 1) * wp1;
+  const long long total = (long long)n * blk * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int ch = (int)(i % c_pad);
-    long long pix = i / c_pad;
-    int img = (int)(pix / hw), p = (int)(pix % hw);
-    float v = ch < c ? src[((size_t)img * c + ch) * hw + p] : 0.f;
-    dst[i] = __float2bfloat16(v);
+    int cg = (int)(i % CG);
+    long long prow = i / CG;
+    int img = (int)(prow / blk), rem = (int)(prow % blk);
+    int a = rem / wp1, b = rem % wp1;
+    uint4 oa = make_uint4(0, 0, 0, 0), og = make_uint4(0, 0, 0, 0);
+    if (a > 0 && b > 0) {
+      int y = a - 1, xx = b - 1;
+      float z[8], zp[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { z[j] = ws[27 * cout + cg * 8 + j]; zp[j] = 0.f; }
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            int yy = y + r - 1, xs = xx + s - 1;
+            float xv = 0.f;
+            if (yy >= 0 && yy < h && xs >= 0 && xs < wd) xv = __ldg(x + (((size_t)img * 3 + ci) * h + yy) * wd + xs);
+            float xp = fmaxf(xv, 0.f), xn = fminf(xv, 0.f);
+            const float4* wr = reinterpret_cast<const float4*>(ws + ((ci * 3 + r) * 3 + s) * cout + cg * 8);
+            float4 w0 = wr[0], w1 = wr[1];
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              z[j] = fmaf(wv[j], xv, z[j]);
+              zp[j] = fmaf(fmaxf(wv[j], 0.f), xp, zp[j]);
+              zp[j] = fmaf(fminf(wv[j], 0.f), xn, zp[j]);
+            }
+          }
+      uint32_t pa[4], pg[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a0 = fmaxf(z[2 * j], 0.f), a1 = fmaxf(z[2 * j + 1], 0.f);
+        __nv_bfloat162 ta = __floats2bfloat162_rn(a0, a1);
+        __nv_bfloat162 tg = __floats2bfloat162_rn(safe_div(a0, zp[2 * j]), safe_div(a1, zp[2 * j + 1]));
+        pa[j] = *reinterpret_cast<uint32_t*>(&ta);
+        pg[j] = *reinterpret_cast<uint32_t*>(&tg);
+      }
+      oa = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+      og = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+    }
+    act[i] = oa;
+    gain[i] = og;
   }
 }
 
-__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int n, int c, int hw,
-                                    int c_pad) {
-  long long total = (long long)n * c * hw;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int p = (int)(i % hw);
-    int ch = (int)((i / hw) % c);
-    int img = (int)(i / ((long long)hw * c));
-    dst[i] = __bfloat162float(src[((size_t)img * hw + p) * c_pad + ch]);
-  }
-}
-
-// 2x2/2 max-pool over NHWC bf16, 8 channels (16 B) per thread.  Scan order (0,0),(0,1),(1,0),(1,1),
-// strict '>' so the first maximum wins, NaN wins (PyTorch max_pool2d_with_indices).
-__global__ void maxpool2_nhwc_kernel(const uint4* __restrict__ act, const uint4* __restrict__ gain,
-                                     uint4* __restrict__ pooled, uint2* __restrict__ idx, uint4* __restrict__ gpool,
-                                     int n, int h, int w, int c8) {
-  int oh = h / 2, ow = w / 2;
-  long long total = (long long)n * oh * ow * c8;
+// ---------------------------------------------------------------- 2x2/2 max-pool on PF, 8 channels / thread
+// Scan order (0,0),(0,1),(1,0),(1,1); strict '>' so the first maximum wins, NaN wins (max_pool2d_with_indices).
+__global__ void maxpool2_pf_kernel(const uint4* __restrict__ act, const uint4* __restrict__ gain,
+                                   uint4* __restrict__ pooled, uint2* __restrict__ idx, uint4* __restrict__ gpool,
+                                   int n, int h, int w, int c8) {
+  const int oh = h / 2, ow = w / 2;
+  const int wp1 = w + 1, owp1 = ow + 1;
+  const long long blk_f = (long long)(h + 1) * wp1, blk_p = (long long)(oh + 1) * owp1;
+  const long long total = (long long)n * blk_p * c8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int cc = (int)(i % c8);
-    long long pix = i / c8;
-    int q = (int)(pix % ow);
-    int p = (int)((pix / ow) % oh);
-    int img = (int)(pix / ((long long)ow * oh));
-    size_t base = (((size_t)img * h + 2 * p) * w + 2 * q) * c8 + cc;
-    size_t off[4] = {base, base + c8, base + (size_t)w * c8, base + (size_t)w * c8 + c8};
-    uint4 v[4], g[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = act[off[k]];
-      if (gain) g[k] = gain[off[k]];
-    }
-    uint4 outv, outg;
-    unsigned char bi[8];
-    const __nv_bfloat16* vb[4] = {(const __nv_bfloat16*)&v[0], (const __nv_bfloat16*)&v[1],
-                                  (const __nv_bfloat16*)&v[2], (const __nv_bfloat16*)&v[3]};
-    const __nv_bfloat16* gb[4] = {(const __nv_bfloat16*)&g[0], (const __nv_bfloat16*)&g[1],
-                                  (const __nv_bfloat16*)&g[2], (const __nv_bfloat16*)&g[3]};
-    __nv_bfloat16* ov = (__nv_bfloat16*)&outv;
-    __nv_bfloat16* og = (__nv_bfloat16*)&outg;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float best = -INFINITY;
-      int b = 0;
+    long long prow = i / c8;
+    int img = (int)(prow / blk_p), rem = (int)(prow % blk_p);
+    int a = rem / owp1, b = rem % owp1;
+    uint4 outv = make_uint4(0, 0, 0, 0), outg = make_uint4(0, 0, 0, 0);
+    uint2 pk = make_uint2(0, 0);
+    if (a > 0 && b > 0) {
+      // pooled pixel (a-1, b-1) covers fine PF rows 2a-1, 2a and columns 2b-1, 2b
+      size_t base = ((size_t)img * blk_f + (size_t)(2 * a - 1) * wp1 + (2 * b - 1)) * c8 + cc;
+      size_t off[4] = {base, base + c8, base + (size_t)wp1 * c8, base + (size_t)wp1 * c8 + c8};
+      uint4 v[4], g[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float f = __bfloat162float(vb[k][e]);
-        if (f > best || f != f) { best = f; b = k; }
+        v[k] = act[off[k]];
+        g[k] = gain ? gain[off[k]] : make_uint4(0, 0, 0, 0);
       }
-      bi[e] = (unsigned char)b;
-      ov[e] = vb[b][e];
-      if (gain) og[e] = gb[b][e];
+      const unsigned short* vb[4] = {(const unsigned short*)&v[0], (const unsigned short*)&v[1],
+                                     (const unsigned short*)&v[2], (const unsigned short*)&v[3]};
+      const unsigned short* gb[4] = {(const unsigned short*)&g[0], (const unsigned short*)&g[1],
+                                     (const unsigned short*)&g[2], (const unsigned short*)&g[3]};
+      unsigned short ov[8], og[8];
+      unsigned char bi[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float best = -INFINITY;
+        int bk = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float f = __uint_as_float((uint32_t)vb[k][e] << 16);
+          if (f > best || f != f) { best = f; bk = k; }
+        }
+        bi[e] = (unsigned char)bk;
+        ov[e] = vb[bk][e];
+        og[e] = gb[bk][e];
+      }
+#define PK16(a, b) ((uint32_t)(a) | ((uint32_t)(b) << 16))
+#define PK8(a, b, c, d) ((uint32_t)(a) | ((uint32_t)(b) << 8) | ((uint32_t)(c) << 16) | ((uint32_t)(d) << 24))
+      outv = make_uint4(PK16(ov[0], ov[1]), PK16(ov[2], ov[3]), PK16(ov[4], ov[5]), PK16(ov[6], ov[7]));
+      outg = make_uint4(PK16(og[0], og[1]), PK16(og[2], og[3]), PK16(og[4], og[5]), PK16(og[6], og[7]));
+      pk.x = PK8(bi[0], bi[1], bi[2], bi[3]);
+      pk.y = PK8(bi[4], bi[5], bi[6], bi[7]);
+#undef PK16
+#undef PK8
     }
     pooled[i] = outv;
-    if (idx) {
-      uint2 pk;
-      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
-      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
-      idx[i] = pk;
-    }
-    if (gain) gpool[i] = outg;
+    if (idx) idx[i] = pk;
+    if (gpool) gpool[i] = outg;
   }
 }
 
-__global__ void scale_rows_kernel(const float* __restrict__ r, const __nv_bfloat16* __restrict__ gain,
-                                  const int32_t* __restrict__ row_img, __nv_bfloat16* __restrict__ out, int hw, int c,
+// ---------------------------------------------------------------- chain entry: s_top = r * rz  (fp32 -> PF bf16)
+__global__ void scale_rows_kernel(const float* __restrict__ r, const uint4* __restrict__ rz,
+                                  const int32_t* __restrict__ row_img, uint4* __restrict__ out, int h, int w, int c8,
                                   long long total) {
+  const int wp1 = w + 1, blk = (h + 1) * wp1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int ch = (int)(i % c);
-    long long pix = i / c;
-    int e = (int)(pix / hw), p = (int)(pix % hw);
-    int img = row_img ? row_img[e] : e;
-    float g = __bfloat162float(gain[((size_t)img * hw + p) * c + ch]);
-    out[i] = __float2bfloat16(r[i] * g);
+    int cc = (int)(i % c8);
+    long long prow = i / c8;
+    int e = (int)(prow / blk), rem = (int)(prow % blk);
+    int a = rem / wp1, b = rem % wp1;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (a > 0 && b > 0) {
+      int img = row_img ? row_img[e] : e;
+      uint4 g = rz[((size_t)img * blk + rem) * c8 + cc];
+      const float4* rp = reinterpret_cast<const float4*>(r + (((size_t)e * h + (a - 1)) * w + (b - 1)) * (c8 * 8) + cc * 8);
+      float4 r0 = rp[0], r1 = rp[1];
+      const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+      const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float lo = rv[2 * k] * __uint_as_float(gw[k] << 16);
+        float hi = rv[2 * k + 1] * __uint_as_float(gw[k] & 0xFFFF0000u);
+        __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+        ow[k] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    out[i] = o;
   }
 }
 
-static inline int grid_for(long long total) {
-  long long g = (total + 255) / 256, cap = 148LL * 16;
-  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+// ---------------------------------------------------------------- PF <-> dense
+__global__ void pf_to_dense_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int n, int h, int w,
+                                   int c, int layout) {
+  const int wp1 = w + 1, blk = (h + 1) * wp1;
+  long long total = (long long)n * h * w * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch, y, x, img;
+    if (layout == 0) {
+      ch = (int)(i % c);
+      long long pix = i / c;
+      x = (int)(pix % w); y = (int)((pix / w) % h); img = (int)(pix / ((long long)w * h));
+    } else {
+      x = (int)(i % w); y = (int)((i / w) % h);
+      ch = (int)((i / ((long long)w * h)) % c); img = (int)(i / ((long long)w * h * c));
+    }
+    dst[i] = __bfloat162float(src[((size_t)img * blk + (size_t)(y + 1) * wp1 + (x + 1)) * c + ch]);
+  }
+}
+
+__global__ void nchw_to_pf_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n, int c, int h,
+                                  int w, int c_pad) {
+  const int wp1 = w + 1, blk = (h + 1) * wp1;
+  long long total = (long long)n * blk * c_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c_pad);
+    long long prow = i / c_pad;
+    int img = (int)(prow / blk), rem = (int)(prow % blk);
+    int a = rem / wp1, b = rem % wp1;
+    float v = 0.f;
+    if (a > 0 && b > 0 && ch < c) v = src[(((size_t)img * c + ch) * h + (a - 1)) * w + (b - 1)];
+    dst[i] = __float2bfloat16(v);
+  }
 }
 
 }  // namespace lrpx
@@ -146,18 +249,20 @@ int lrpx_weight_prep_bf16(const float* w, void* wt, int cout, int cin, int kh, i
   return LRPX_OK;
 }
 
-int lrpx_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int n, int c, int h, int w, int c_pad, void* stream) {
-  LRPX_CHECK_ARG(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && c_pad >= c, "bad argument");
-  long long total = (long long)n * h * w * c_pad;
-  nchw_to_nhwc_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, n, c, h * w, c_pad);
-  LRPX_CHECK_LAUNCH();
-  return LRPX_OK;
-}
-
-int lrpx_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int n, int c, int h, int w, int c_pad, void* stream) {
-  LRPX_CHECK_ARG(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && c_pad >= c, "bad argument");
-  long long total = (long long)n * h * w * c;
-  nhwc_to_nchw_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, dst, n, c, h * w, c_pad);
+int lrpx_tc_first_fwd(const float* x, const float* w, const float* bias, void* act, void* gain, int n, int h, int wd,
+                      int cout, void* stream) {
+  LRPX_CHECK_ARG(x && w && act && gain && n > 0 && h > 0 && wd > 0, "bad argument");
+  LRPX_CHECK_ARG(cout == 64 || cout == 32 || cout == 16 || cout == 8, "cout must be 8, 16, 32 or 64");
+  long long total = (long long)n * (h + 1) * (wd + 1) * (cout / 8);
+  size_t smem = (size_t)(27 * cout + cout) * sizeof(float);
+  cudaStream_t st = as_stream(stream);
+  int grid = grid_for(total);
+  switch (cout) {
+    case 64: first_fwd_kernel<8><<<grid, 256, smem, st>>>(x, w, bias, (uint4*)act, (uint4*)gain, n, h, wd); break;
+    case 32: first_fwd_kernel<4><<<grid, 256, smem, st>>>(x, w, bias, (uint4*)act, (uint4*)gain, n, h, wd); break;
+    case 16: first_fwd_kernel<2><<<grid, 256, smem, st>>>(x, w, bias, (uint4*)act, (uint4*)gain, n, h, wd); break;
+    default: first_fwd_kernel<1><<<grid, 256, smem, st>>>(x, w, bias, (uint4*)act, (uint4*)gain, n, h, wd); break;
+  }
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;
 }
@@ -167,20 +272,36 @@ int lrpx_tc_maxpool2_bf16(const void* act, const void* gain_fine, void* pooled, 
   LRPX_CHECK_ARG(act && pooled && n > 0 && h > 0 && w > 0 && c > 0 && (h % 2) == 0 && (w % 2) == 0 && (c % 8) == 0,
                  "bad argument (h, w even and c % 8 == 0 required)");
   LRPX_CHECK_ARG((gain_fine == nullptr) == (gain_pooled == nullptr), "gain_fine and gain_pooled go together");
-  long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  maxpool2_nhwc_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)act, (const uint4*)gain_fine,
-                                                                      (uint4*)pooled, (uint2*)idx, (uint4*)gain_pooled,
-                                                                      n, h, w, c / 8);
+  long long total = (long long)n * (h / 2 + 1) * (w / 2 + 1) * (c / 8);
+  maxpool2_pf_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)act, (const uint4*)gain_fine,
+                                                                    (uint4*)pooled, (uint2*)idx, (uint4*)gain_pooled, n,
+                                                                    h, w, c / 8);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;
 }
 
-int lrpx_tc_scale_rows(const float* r, const void* gain, const int32_t* row_img, void* out, int n_expl, int hw, int c,
-                       void* stream) {
-  LRPX_CHECK_ARG(r && gain && out && n_expl > 0 && hw > 0 && c > 0, "bad argument");
-  long long total = (long long)n_expl * hw * c;
-  scale_rows_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(r, (const __nv_bfloat16*)gain, row_img,
-                                                                   (__nv_bfloat16*)out, hw, c, total);
+int lrpx_tc_scale_rows(const float* r, const void* rz, const int32_t* row_img, void* out, int n_expl, int h, int w,
+                       int c, void* stream) {
+  LRPX_CHECK_ARG(r && rz && out && n_expl > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "bad argument");
+  long long total = (long long)n_expl * (h + 1) * (w + 1) * (c / 8);
+  scale_rows_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(r, (const uint4*)rz, row_img, (uint4*)out, h, w,
+                                                                   c / 8, total);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_tc_pf_to_dense_f32(const void* src, float* dst, int n, int h, int w, int c, int layout, void* stream) {
+  LRPX_CHECK_ARG(src && dst && n > 0 && h > 0 && w > 0 && c > 0 && (layout == 0 || layout == 1), "bad argument");
+  long long total = (long long)n * h * w * c;
+  pf_to_dense_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, dst, n, h, w, c, layout);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_tc_nchw_to_pf_bf16(const float* src, void* dst, int n, int c, int h, int w, int c_pad, void* stream) {
+  LRPX_CHECK_ARG(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && c_pad >= c, "bad argument");
+  long long total = (long long)n * (h + 1) * (w + 1) * c_pad;
+  nchw_to_pf_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, n, c, h, w, c_pad);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;
 }

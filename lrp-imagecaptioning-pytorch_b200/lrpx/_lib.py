@@ -41,7 +41,7 @@ class AoaArgs(C.Structure):
 
 
 class TcConvArgs(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("n_img", "h", "w", "cin", "ncol", "ksize", "epilogue")] + \
+    _fields_ = [(n, C.c_int) for n in ("n_img", "h", "w", "cin", "ncol", "ksize", "epilogue", "gain_mode")] + \
                [(n, _P) for n in ("a", "wt", "bias", "gain", "row_img", "pool_idx", "x", "out", "out2")]
 
 
@@ -70,10 +70,11 @@ SYMBOLS = {
     "lrpx_fc_lrp_weights_f32": (_i, [_P, _P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
     "lrpx_tc_conv": (_i, [C.POINTER(TcConvArgs), _P]),
     "lrpx_weight_prep_bf16": (_i, [_P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),
-    "lrpx_nchw_f32_to_nhwc_bf16": (_i, [_P, _P, _i, _i, _i, _i, _i, _P]),
-    "lrpx_nhwc_bf16_to_nchw_f32": (_i, [_P, _P, _i, _i, _i, _i, _i, _P]),
+    "lrpx_tc_first_fwd": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "lrpx_tc_maxpool2_bf16": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
-    "lrpx_tc_scale_rows": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
+    "lrpx_tc_scale_rows": (_i, [_P, _P, _P, _P, _i, _i, _i, _i, _P]),
+    "lrpx_tc_pf_to_dense_f32": (_i, [_P, _P, _i, _i, _i, _i, _i, _P]),
+    "lrpx_tc_nchw_to_pf_bf16": (_i, [_P, _P, _i, _i, _i, _i, _i, _P]),
 }
 
 _lib = None
@@ -95,7 +96,11 @@ def lib():
     return _lib
 
 
+CALLS = {}     # successful C-ABI calls by name (bench.py reports kernel launches from it)
+
+
 def check(rc, what=""):
+    CALLS[what] = CALLS.get(what, 0) + 1
     if rc != 0:
         msg = lib().lrpx_last_error().decode(errors="replace")
         raise LrpxError(f"{what} failed ({rc}): {msg}")

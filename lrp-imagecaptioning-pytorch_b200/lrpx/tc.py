@@ -1,0 +1,278 @@
+"""Tensor-core (tcgen05/TMA, bf16) encoder relevance engine for VGG-style encoders.
+
+Host side only: torch provides device memory and the stream; every arithmetic step is a liblrpx.so call
+(include/lrpx.h, "Tensor-core path").  There is no CPU or PyTorch fallback.
+
+What it replaces in the reference, for an encoder made of conv3x3(pad 1) + ReLU (+ 2x2 max-pool) blocks
+(models/vgg.py:62-83, gridTDmodel.py:32-35) under the alpha=1, beta=0 preset (lrp_wrapper.py:7-12):
+
+* ``encoder.compute_lrp(img, target=R)`` (lrp_wrapper.py:63-87) re-runs the forward for every explained word
+  and, per conv layer, builds 4 conv clones and runs 4 forward + 4 backward convolutions
+  (lrp_modules.py:56-170).  Here the forward runs ONCE per image and also produces, per layer,
+  ``gain_l = a_{l+1} / safe(z+_l)``; an explanation then costs one transposed-conv contraction per layer:
+  ``s_{l-1} = gain_{l-1} (.) (W+_l^T * s_l)`` with ``s_l = R_{l+1} / safe(z+_l)`` — algebraically the
+  reference's ``R_in = a (.) (W+^T (R / z+))`` chain (utils.py:21-31), max-pool winner-take-all
+  (lrp_modules.py:186-191) folded into the epilogue through the saved 2-bit argmax.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import TcConvArgs, check, lib
+
+EPI_FWD_GAIN, EPI_MUL, EPI_MUL_UNPOOL, EPI_INPUT, EPI_STORE_F32 = 1, 2, 3, 4, 5
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(t, name):
+    if not t.is_cuda:
+        raise _lib.LrpxError(f"{name} must be a CUDA tensor: lrpx has no CPU fallback")
+
+
+def pf_rows(n, h, w):
+    return n * (h + 1) * (w + 1)
+
+
+def tc_conv(a, wt, n_img, h, w, cin, ncol, ksize, epilogue, out, out2=None, bias=None, gain=None, row_img=None,
+            pool_idx=None, x=None, gain_mode=0):
+    """Thin wrapper of lrpx_tc_conv (all tensors preallocated by the caller)."""
+    args = TcConvArgs(n_img=n_img, h=h, w=w, cin=cin, ncol=ncol, ksize=ksize, epilogue=epilogue, gain_mode=gain_mode)
+    args.a, args.wt = a.data_ptr(), wt.data_ptr()
+    args.bias = bias.data_ptr() if bias is not None else None
+    args.gain = gain.data_ptr() if gain is not None else None
+    args.row_img = row_img.data_ptr() if row_img is not None else None
+    args.pool_idx = pool_idx.data_ptr() if pool_idx is not None else None
+    args.x = x.data_ptr() if x is not None else None
+    args.out = out.data_ptr()
+    args.out2 = out2.data_ptr() if out2 is not None else None
+    check(lib().lrpx_tc_conv(C.byref(args), _stream()), "lrpx_tc_conv")
+    return out
+
+
+def weight_prep(w, mode, rows_pad=None, chan_pad=None, out=None):
+    """lrpx_weight_prep_bf16: fp32 (cout,cin,kh,kw) -> bf16 (rows_pad, kh*kw*chan_pad)."""
+    _need_cuda(w, "w")
+    w = w.detach().float().contiguous()
+    cout, cin, kh, kw = w.shape
+    rows, chans = (cin, cout) if mode >= 2 else (cout, cin)
+    rows_pad = rows if rows_pad is None else rows_pad
+    chan_pad = chans if chan_pad is None else chan_pad
+    if out is None:
+        out = torch.empty(rows_pad, kh * kw * chan_pad, device=w.device, dtype=torch.bfloat16)
+    check(lib().lrpx_weight_prep_bf16(_ptr(w), _ptr(out), cout, cin, kh, kw, mode, rows_pad, chan_pad, _stream()),
+          "lrpx_weight_prep_bf16")
+    return out
+
+
+def dual_forward_weights(w):
+    """Per tile of ``half`` output channels: the W rows followed by the W+ rows (EPI_FWD_GAIN operand)."""
+    cout, cin, kh, kw = w.shape
+    half = cout if cout < 128 else 128
+    if cout % half:
+        raise _lib.LrpxError("output channels must be < 128 or a multiple of 128")
+    wt = torch.empty(2 * cout, kh * kw * cin, device=w.device, dtype=torch.bfloat16)
+    w = w.detach().float().contiguous()
+    for j in range(cout // half):
+        sl = w[j * half:(j + 1) * half].contiguous()
+        weight_prep(sl, 0, out=wt[2 * j * half:(2 * j + 1) * half])
+        weight_prep(sl, 1, out=wt[(2 * j + 1) * half:(2 * j + 2) * half])
+    return wt
+
+
+def nchw_to_pf(x, c_pad=None):
+    _need_cuda(x, "x")
+    x = x.detach().float().contiguous()
+    n, c, h, w = x.shape
+    c_pad = c if c_pad is None else c_pad
+    out = torch.empty(pf_rows(n, h, w), c_pad, device=x.device, dtype=torch.bfloat16)
+    check(lib().lrpx_tc_nchw_to_pf_bf16(_ptr(x), _ptr(out), n, c, h, w, c_pad, _stream()), "lrpx_tc_nchw_to_pf_bf16")
+    return out
+
+
+def pf_to_dense(pf, n, h, w, c, layout="nchw"):
+    out = torch.empty((n, c, h, w) if layout == "nchw" else (n, h * w, c), device=pf.device, dtype=torch.float32)
+    check(lib().lrpx_tc_pf_to_dense_f32(_ptr(pf), _ptr(out), n, h, w, c, 1 if layout == "nchw" else 0, _stream()),
+          "lrpx_tc_pf_to_dense_f32")
+    return out
+
+
+def maxpool2(act, gain, n, h, w, c, want_idx=True):
+    dev = act.device
+    rows = pf_rows(n, h // 2, w // 2)
+    pooled = torch.empty(rows, c, device=dev, dtype=torch.bfloat16)
+    idx = torch.empty(rows, c, device=dev, dtype=torch.uint8) if want_idx else None
+    gpool = torch.empty(rows, c, device=dev, dtype=torch.bfloat16) if gain is not None else None
+    check(lib().lrpx_tc_maxpool2_bf16(_ptr(act), _ptr(gain), _ptr(pooled), _ptr(idx), _ptr(gpool), n, h, w, c,
+                                      _stream()), "lrpx_tc_maxpool2_bf16")
+    return pooled, idx, gpool
+
+
+class _Conv:
+    __slots__ = ("cin", "cout", "h", "w", "pool_after", "w_f32", "bias", "w_dual", "w_rel")
+
+
+class VggState:
+    """Per-batch forward state shared by all explanations of the batch's images."""
+
+    def __init__(self):
+        self.n = 0
+        self.x = None           # fp32 NCHW images
+        self.gain = []          # per conv: PF bf16 gain at the resolution the relevance chain needs it
+        self.idx = []           # per conv: uint8 argmax of the pool after it (or None)
+        self.rz_last = None     # 1 / safe(z+) of the last conv
+        self.feat_pf = None     # encoder output, PF bf16
+        self.feat_hw = (0, 0)
+        self.feat_c = 0
+
+
+class TcVggEngine:
+    """conv3x3/ReLU/max-pool encoder on the tcgen05 kernels: ``forward`` once per image batch, ``relevance``
+    for any number of explanation requests against those images."""
+
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], cfg: Sequence,
+                 device=None):
+        device = torch.device(device or "cuda")
+        if device.type != "cuda":
+            raise _lib.LrpxError("TcVggEngine needs a CUDA device: lrpx has no CPU fallback")
+        self.device = device
+        self.convs: List[_Conv] = []
+        k = 0
+        for v in cfg:
+            if v == "M":
+                if not self.convs or self.convs[-1].pool_after:
+                    raise _lib.LrpxError("cfg: a pool must follow a conv")
+                self.convs[-1].pool_after = True
+                continue
+            c = _Conv()
+            w = weights[k].detach().to(device=device, dtype=torch.float32).contiguous()
+            c.cout, c.cin = int(w.shape[0]), int(w.shape[1])
+            if tuple(w.shape[2:]) != (3, 3) or c.cout != int(v):
+                raise _lib.LrpxError("TcVggEngine supports 3x3 convolutions matching cfg only")
+            c.pool_after = False
+            c.w_f32 = w
+            c.bias = None if biases[k] is None else biases[k].detach().to(device=device, dtype=torch.float32).contiguous()
+            if k == 0:
+                if c.cin != 3 or c.cout not in (8, 16, 32, 64):
+                    raise _lib.LrpxError("first conv must be 3 -> {8,16,32,64} channels")
+                # rows 0..2: W+ (flipped, transposed), rows 3..5: W-, rows 6..15: zero
+                c.w_rel = torch.zeros(16, 9 * c.cout, device=device, dtype=torch.bfloat16)
+                weight_prep(w, 2, out=c.w_rel[0:3])
+                weight_prep(w, 3, out=c.w_rel[3:6])
+                c.w_dual = None
+            else:
+                if c.cin % 64 or c.cout % 32:
+                    raise _lib.LrpxError("conv channels must be multiples of 64 (in) / 32 (out) on the tensor-core path")
+                c.w_dual = dual_forward_weights(w)
+                c.w_rel = weight_prep(w, 2)          # (cin, 9*cout): W+ flipped & transposed
+            self.convs.append(c)
+            k += 1
+        if self.convs[-1].pool_after:
+            raise _lib.LrpxError("the encoder slice must end with a conv (vgg16.features[0:-1])")
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> VggState:
+        """Activation-producing forward (lrp_wrapper.py:70) + per-layer gains; x is fp32 NCHW (n,3,h,w)."""
+        _need_cuda(x, "x")
+        x = x.detach().float().contiguous()
+        n, cin, h, w = x.shape
+        npool = sum(c.pool_after for c in self.convs)
+        if cin != 3 or h % (1 << npool) or w % (1 << npool):
+            raise _lib.LrpxError("images must be (n,3,h,w) with h, w divisible by 2**(number of pools)")
+        st = VggState()
+        st.n, st.x = n, x
+        dev = x.device
+        act = None
+        for li, c in enumerate(self.convs):
+            c.h, c.w = h, w
+            rows = pf_rows(n, h, w)
+            out = torch.empty(rows, c.cout, device=dev, dtype=torch.bfloat16)
+            gain = torch.empty(rows, c.cout, device=dev, dtype=torch.bfloat16)
+            last = li == len(self.convs) - 1
+            if li == 0:
+                check(lib().lrpx_tc_first_fwd(_ptr(x), _ptr(c.w_f32), _ptr(c.bias), _ptr(out), _ptr(gain), n, h, w,
+                                              c.cout, _stream()), "lrpx_tc_first_fwd")
+            else:
+                tc_conv(act, c.w_dual, n, h, w, c.cin, 2 * c.cout, 3, EPI_FWD_GAIN, out, out2=gain, bias=c.bias,
+                        gain_mode=1 if last else 0)
+            if c.pool_after:
+                act, idx, gain = maxpool2(out, gain, n, h, w, c.cout)
+                h, w = h // 2, w // 2
+                st.idx.append(idx)
+            else:
+                act = out
+                st.idx.append(None)
+            st.gain.append(gain)
+        st.rz_last = st.gain[-1]
+        st.feat_pf, st.feat_hw, st.feat_c = act, (h, w), self.convs[-1].cout
+        return st
+
+    def features(self, st: VggState, layout="nchw"):
+        """Encoder output as dense fp32: 'nchw' (n,C,h,w) or 'pixel' (n,h*w,C)."""
+        h, w = st.feat_hw
+        return pf_to_dense(st.feat_pf, st.n, h, w, st.feat_c, layout)
+
+    # ------------------------------------------------------------------------------------------
+    def relevance(self, st: VggState, r_feat: torch.Tensor, row_img: Optional[torch.Tensor] = None,
+                  chunk: int = 64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Image relevance for Q requests.  r_feat: fp32 (Q, h*w, C) pixel-major relevance of the encoder
+        output (what the decoder kernels emit); row_img: int32 (Q,) image of each request (None = identity).
+        Returns fp32 (Q, 3, H, W)."""
+        _need_cuda(r_feat, "r_feat")
+        r_feat = r_feat.detach().float().contiguous()
+        Q = r_feat.shape[0]
+        fh, fw = st.feat_hw
+        if tuple(r_feat.shape[1:]) != (fh * fw, st.feat_c):
+            raise _lib.LrpxError(f"r_feat must be (Q,{fh * fw},{st.feat_c}), got {tuple(r_feat.shape)}")
+        dev = r_feat.device
+        if row_img is None:
+            if Q != st.n:
+                raise _lib.LrpxError("row_img is required when the number of requests differs from the images")
+            row_img = torch.arange(Q, device=dev, dtype=torch.int32)
+        row_img = row_img.to(device=dev, dtype=torch.int32).contiguous()
+        H, W = self.convs[0].h, self.convs[0].w
+        if out is None:
+            out = torch.empty(Q, 3, H, W, device=dev, dtype=torch.float32)
+        # ping-pong s buffers sized for the largest layer of a chunk
+        chunk = max(1, min(chunk, Q))
+        max_elems = max(pf_rows(chunk, c.h, c.w) * c.cout for c in self.convs)
+        buf = [torch.empty(max_elems, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+        L = len(self.convs)
+        for q0 in range(0, Q, chunk):
+            q1 = min(Q, q0 + chunk)
+            nq = q1 - q0
+            rimg = row_img[q0:q1]
+            cur = 0
+            s = buf[cur]
+            check(lib().lrpx_tc_scale_rows(_ptr(r_feat[q0:q1]), _ptr(st.rz_last), _ptr(rimg), _ptr(s), nq, fh, fw,
+                                           st.feat_c, _stream()), "lrpx_tc_scale_rows")
+            for li in range(L - 1, 0, -1):
+                c, below = self.convs[li], self.convs[li - 1]
+                dst = buf[cur ^ 1]
+                if below.pool_after:
+                    tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL_UNPOOL, dst, gain=st.gain[li - 1],
+                            row_img=rimg, pool_idx=st.idx[li - 1])
+                else:
+                    tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL, dst, gain=st.gain[li - 1],
+                            row_img=rimg)
+                cur ^= 1
+                s = dst
+            c0 = self.convs[0]
+            tc_conv(s, c0.w_rel, nq, c0.h, c0.w, c0.cout, 16, 3, EPI_INPUT, out[q0:q1], row_img=rimg, x=st.x)
+        return out
+
+    def flops_per_explanation(self) -> float:
+        """Algorithmic FLOPs of one explanation's relevance chain (one contraction per conv layer)."""
+        return float(sum(2.0 * c.h * c.w * c.cin * c.cout * 9 for c in self.convs))
+
+    def flops_forward_per_image(self) -> float:
+        """Forward + z+ (two contractions per layer)."""
+        return float(sum(4.0 * c.h * c.w * c.cin * c.cout * 9 for c in self.convs))

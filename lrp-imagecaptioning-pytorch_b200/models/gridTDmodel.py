@@ -1,0 +1,606 @@
+"""Host-side mirror of the LRP entry points of the reference's models/gridTDmodel.py.
+
+Same class / method names, argument meaning and return values as the reference so that evaluation.py /
+train.py style callers can switch over:
+
+* ``GridTDModel``  — state_dict-compatible module (reference :106-131) with ``forward`` (:146-198),
+  ``beam_search`` (:400-478), and the lrp_tune entry points ``get_lrp_weight_step`` (:549-578),
+  ``forwardlrp_context`` (:580-633), ``sample_lrp`` (:635-702).
+* ``ExplainGridTDAttention`` — ``get_hidden_parameters`` (:933-1012), ``explain_caption_wordt`` (:1014-1135),
+  ``explain_cnn`` (:1137-1139), ``explain_caption`` (:1141-1156), ``teacherforce_forward`` (:892-931),
+  ``lrp_linear_eps`` (:744-765).
+
+What differs is HOW the relevance is computed: the per-vector python loops over ``lrp_linear_eps`` become one
+batched kernel call per caption (``lrpx_gridtd_decoder_lrp_f32``), the per-sample tuner loop becomes
+``lrpx_fc_lrp_weights_f32`` (no ``.item()`` sync), and the encoder relevance runs on the tcgen05 chain
+(``lrpx.tc.TcVggEngine``, bf16) or on the fp32 rule kernels through ``LRPtools`` (``precision='fp32'``).
+The forward passes that produce the saved state are plain torch tensor ops on the device (library GEMMs).
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+import models.resnet as resnet
+import models.vgg as vgg
+from LRPtools import lrp_wrapper
+from LRPtools import utils as LRPutil
+from lrpx import ops
+from lrpx import decoder as _dec
+
+try:  # the reference takes nltk's English list (gridTDmodel.py:17-20); fall back to a built-in copy of it
+    from nltk.corpus import stopwords as _sw
+    STOP_WORDS = list(set(_sw.words('english')))
+except Exception:  # pragma: no cover - nltk is not installed in this image
+    STOP_WORDS = """i me my myself we our ours ourselves you you're you've you'll you'd your yours yourself yourselves he
+    him his himself she she's her hers herself it it's its itself they them their theirs themselves what which who whom
+    this that that'll these those am is are was were be been being have has had having do does did doing a an the and
+    but if or because as until while of at by for with about against between into through during before after above
+    below to from up down in out on off over under again further then once here there when where why how all any both
+    each few more most other some such no nor not only own same so than too very s t can will just don don't should
+    should've now d ll m o re ve y ain aren aren't couldn couldn't didn didn't doesn doesn't hadn hadn't hasn hasn't
+    haven haven't isn isn't ma mightn mightn't mustn mustn't needn needn't shan shan't shouldn shouldn't wasn wasn't
+    weren weren't won won't wouldn wouldn't""".split()
+STOP_WORDS += ['<start>', '<end>', '<pad>', '<unk>']
+BAD_ENDINGS = ['with', 'in', 'on', 'of', 'a', 'at', 'to', 'for', 'an', 'this', 'his', 'her', 'that', 'the', 'and']
+
+
+class Encoder(nn.Module):
+    """reference :23-43"""
+
+    def __init__(self, encoder_type):
+        super().__init__()
+        if encoder_type == 'resnet101':
+            self.encoder = resnet.resnet101(pretrained=True)
+            self.feat_dim = self.encoder.feat_dim
+        elif encoder_type == 'renset50':          # (sic) the reference's spelling
+            self.encoder = resnet.resnet50(pretrained=True)
+            self.feat_dim = self.encoder.feat_dim
+        elif encoder_type == 'vgg16':
+            base_model = vgg.vgg16(pretrained=True)
+            self.encoder = base_model.features[0:-1]
+            self.feat_dim = base_model.feat_dim
+        else:
+            raise NotImplementedError("the encoder_type does not exist, please add your encoder_type options")
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+
+    def forward(self, img):
+        encoded_image = self.encoder(img)
+        return encoded_image, self.avgpool(encoded_image).squeeze()
+
+
+class AdaptiveLSTMCell(nn.Module):
+    """reference :46-58"""
+
+    def __init__(self, input_size, hidden_size):
+        super().__init__()
+        self.lstm_cell = nn.LSTMCell(input_size, hidden_size)
+        self.x_gate = nn.Linear(input_size, hidden_size)
+        self.h_gate = nn.Linear(hidden_size, hidden_size)
+
+    def forward(self, inp, states):
+        h_old, c_old = states
+        ht, ct = self.lstm_cell(inp, (h_old, c_old))
+        sen_gate = torch.sigmoid(self.x_gate(inp) + self.h_gate(h_old))
+        return ht, ct, sen_gate * torch.tanh(ct)
+
+
+class AdaptiveAttention(nn.Module):
+    """reference :61-103.  The h-projection is broadcast along the *pixel* axis in the image branch (the
+    reference's bmm with a ones matrix, :81-87; only shape-valid when the pixel count equals n_pixel, Q19)."""
+
+    def __init__(self, hidden_dim, n_pixel):
+        super().__init__()
+        self.hidden_dim = hidden_dim
+        self.num_pixel = n_pixel
+        self.W_v_proj = nn.Linear(hidden_dim, n_pixel)
+        self.W_s_proj = nn.Linear(hidden_dim, n_pixel)
+        self.W_g_proj = nn.Linear(hidden_dim, n_pixel, bias=False)
+        self.w_h = nn.Linear(n_pixel, 1, bias=False)
+
+    def project_image(self, V):
+        """V (bs, hidden, P) -> (V^T (bs,P,hidden), W_v V (bs,P,n_pixel)); constant over the time steps."""
+        Vt = V.transpose(1, 2)
+        return Vt, self.W_v_proj(Vt)
+
+    def attend(self, Vt, img_proj, ht, st):
+        ht_proj = self.W_g_proj(ht)                                        # (bs, n_pixel)
+        z_t = self.w_h(torch.tanh(img_proj + ht_proj.unsqueeze(2)))        # (bs, P, 1)
+        alpha_t = torch.softmax(z_t, dim=1)
+        context_t = torch.sum(Vt * alpha_t, dim=1)
+        attention_vs = self.w_h(torch.tanh(self.W_s_proj(st) + ht_proj))   # (bs, 1)
+        alpha_t_hat = torch.softmax(torch.cat([z_t, attention_vs.unsqueeze(-1)], dim=1), dim=1)
+        beta_t = alpha_t_hat[:, -1]                                        # (bs, 1)
+        c_t_hat = beta_t * st + (1 - beta_t) * context_t
+        return c_t_hat, context_t, alpha_t.squeeze(2), beta_t
+
+    def forward(self, V, ht, st):
+        Vt, img_proj = self.project_image(V)
+        return self.attend(Vt, img_proj, ht, st)
+
+
+def _lstm_forward(x, h, c, wi, wh, bi, bh):
+    """Hand-rolled LSTM cell returning the pre-tanh candidate and the gate activations (reference :581-592)."""
+    z = torch.matmul(x, wi.transpose(0, 1)) + torch.matmul(h, wh.transpose(0, 1)) + bi + bh
+    z0, z1, z2, z3 = z.chunk(4, dim=1)
+    i = torch.sigmoid(z0)
+    f = torch.sigmoid(z1)
+    c = f * c + i * torch.tanh(z2)
+    h = torch.sigmoid(z3) * torch.tanh(c)
+    return h, c, z2, i, f
+
+
+class GridTDModel(nn.Module):
+    """reference :106-702 (the LRP-related surface)."""
+    EPS = LRPutil.EPSILON
+
+    def __init__(self, embed_dim, hidden_dim, vocab_size, encoder_type, n_pixel=196):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.hidden_dim = hidden_dim
+        self.vocab_size = vocab_size
+        self.encoder_type = encoder_type
+        self.dropout = nn.Dropout(0.5)
+        self.img_encoder = Encoder(self.encoder_type)
+        self.encoder_raw_dim = self.img_encoder.feat_dim
+        self.img_projector = nn.Conv2d(self.encoder_raw_dim, self.hidden_dim, kernel_size=1, stride=1)
+        self.global_img_feature_proj = nn.Linear(self.encoder_raw_dim, self.embed_dim)
+        self.LanguageLSTM = nn.LSTMCell(2 * hidden_dim, hidden_dim)
+        self.AdaLSTM = AdaptiveLSTMCell(embed_dim * 2 + hidden_dim, hidden_dim)
+        self.AdaAttention = AdaptiveAttention(self.hidden_dim, n_pixel)
+        self.embedding = nn.Embedding(vocab_size, embed_dim)
+        self.fc = nn.Linear(hidden_dim, vocab_size)
+        self.relu = nn.ReLU()
+        self._stop_cache = {}
+
+    # ------------------------------------------------------------------ plain forward / search
+    def init_hidden_state(self, V):
+        h = torch.zeros(V.shape[0], self.hidden_dim, device=V.device)
+        return h, torch.zeros_like(h)
+
+    def predict_next_word(self, image_feature_proj, xt, states):
+        h1t, c1t, h2t, c2t = states
+        h1t, c1t, st = self.AdaLSTM(xt, (h1t, c1t))
+        context_t_hat, context_t, alpha_t, beta_t = self.AdaAttention(image_feature_proj, h1t, st)
+        h2t, c2t = self.LanguageLSTM(torch.cat((context_t_hat, h1t), dim=-1), (h2t, c2t))
+        predict_score_t = self.fc(self.dropout(context_t_hat + h2t))
+        return predict_score_t, alpha_t, beta_t, (h1t, c1t, h2t, c2t)
+
+    def _encode(self, images):
+        batch_size = images.size(0)
+        image_features, avg_feature = self.img_encoder(images)
+        before_act = self.img_projector(image_features)
+        image_feature_proj = self.relu(before_act).contiguous().view(batch_size, self.hidden_dim, -1)
+        global_before_act = self.global_img_feature_proj(avg_feature)
+        global_img_feature = self.relu(global_before_act)
+        if global_img_feature.dim() == 1:
+            global_img_feature = global_img_feature.unsqueeze(0)
+        return image_features, image_feature_proj, global_img_feature
+
+    def forward(self, images, encoded_captions, caption_lengths, ss_prob=None):
+        """Teacher-forced forward (reference :146-198; scheduled sampling is not part of the LRP path)."""
+        if ss_prob is not None:
+            raise NotImplementedError("scheduled sampling is outside the LRP hot path (SURVEY.md §2 #9)")
+        batch_size = images.size(0)
+        image_features, image_feature_proj, global_img_feature = self._encode(images)
+        num_pixels = image_feature_proj.size(-1)
+        state = self.init_hidden_state(image_feature_proj) + self.init_hidden_state(image_feature_proj)
+        max_length = int(max(caption_lengths)) - 1
+        predictions = torch.zeros(batch_size, max_length, self.vocab_size, device=images.device)
+        alphas = torch.zeros(batch_size, max_length, num_pixels, device=images.device)
+        betas = torch.zeros(batch_size, max_length, 1, device=images.device)
+        last_scores = None
+        for t in range(max_length):
+            word_embedding = self.embedding(encoded_captions[:, t])
+            xt = torch.cat((state[2], global_img_feature, word_embedding), dim=-1)
+            predict_score_t, alpha_t, beta_t, state = self.predict_next_word(image_feature_proj, xt, state)
+            predictions[:, t, :] = predict_score_t
+            alphas[:, t, :] = alpha_t
+            betas[:, t, :] = beta_t
+            last_scores = torch.log_softmax(predict_score_t, -1)
+        return predictions, alphas, betas, last_scores, max_length
+
+    def remove_bad_endings(self, sentences):
+        out = []
+        for s in sentences:
+            words = s.split(' ')
+            while words and words[-1] in BAD_ENDINGS:
+                words = words[:-1]
+            out.append(' '.join(words))
+        return out
+
+    def beam_search(self, imgs, word_map, beam_size=3, max_cap_length=20):
+        """reference :400-478 (batch size 1).  ``beam_idx`` uses floor division — the reference's true division
+        (:444) is an IndexError on torch >= 1.6 (Q8)."""
+        self.eval()
+        assert imgs.size(0) == 1
+        rev_word_map = {v: k for k, v in word_map.items()}
+        vocab_size = len(word_map)
+        dev = imgs.device
+        complete_seqs, complete_seqs_scores = [], []
+        with torch.no_grad():
+            k_prev_words = torch.full((beam_size, 1), word_map['<start>'], dtype=torch.long, device=dev)
+            top_k_scores = torch.zeros(beam_size, 1, device=dev)
+            seqs = k_prev_words.clone()
+            _, image_feature_proj, global_img_feature = self._encode(imgs)
+            image_feature_proj = image_feature_proj.expand(beam_size, *image_feature_proj.size()[1:])
+            global_img_feature = global_img_feature.expand(beam_size, global_img_feature.size(-1))
+            state = self.init_hidden_state(image_feature_proj) + self.init_hidden_state(image_feature_proj)
+            unfinished_num = beam_size
+            for step in range(max_cap_length):
+                word_embedding = self.embedding(k_prev_words).squeeze(1)
+                xt = torch.cat((state[2], global_img_feature, word_embedding), dim=-1)
+                predict_score_t, _, _, state = self.predict_next_word(image_feature_proj, xt, state)
+                scores = top_k_scores.expand((unfinished_num, vocab_size)) + torch.log_softmax(predict_score_t, dim=-1)
+                if step == 0:
+                    top_k_scores, top_words = scores[0].topk(beam_size, -1, True, True)
+                else:
+                    top_k_scores, top_words = scores.view(-1).topk(unfinished_num, -1, True, True)
+                beam_idx = top_words // vocab_size
+                next_word_idx = top_words % vocab_size
+                seqs = torch.cat([seqs[beam_idx], next_word_idx.unsqueeze(1)], dim=1)
+                nw = next_word_idx.tolist()
+                incomplete_inds = [i for i, w in enumerate(nw) if w != word_map['<end>']]
+                complete_inds = [i for i, w in enumerate(nw) if w == word_map['<end>']]
+                if complete_inds:
+                    complete_seqs.extend(seqs[complete_inds].tolist())
+                    complete_seqs_scores.extend(top_k_scores[complete_inds].tolist())
+                unfinished_num -= len(complete_inds)
+                if unfinished_num == 0:
+                    break
+                seqs = seqs[incomplete_inds]
+                keep = beam_idx[incomplete_inds]
+                state = tuple(s[keep] for s in state)
+                image_feature_proj = image_feature_proj[keep]
+                global_img_feature = global_img_feature[keep]
+                top_k_scores = top_k_scores[incomplete_inds].unsqueeze(1)
+                k_prev_words = next_word_idx[incomplete_inds].unsqueeze(1)
+            if complete_seqs:
+                seq = complete_seqs[complete_seqs_scores.index(max(complete_seqs_scores))]
+            else:
+                seq = seqs[0][:20].tolist()
+            special = {word_map['<start>'], word_map['<end>'], word_map['<unk>'], word_map['<pad>']}
+            sen_idx = [w for w in seq if w not in special]
+            sentence = self.remove_bad_endings([' '.join(rev_word_map[w] for w in sen_idx)])
+            return sentence, sen_idx
+
+    def sample_next_word(self, logprobs, sample_method, temperature):
+        if sample_method == 'greedy':
+            sampleLogprobs, it = torch.max(logprobs.data, 1)
+            return it.view(-1).long(), sampleLogprobs
+        prob = torch.exp(logprobs.data / temperature) if temperature != 1.0 else torch.exp(logprobs.data)
+        it = torch.multinomial(prob, 1)
+        return it.view(-1).long(), logprobs.gather(1, it)
+
+    # ------------------------------------------------------------------ lrp_tune
+    def lrp_linear_eps(self, r_out, forward_input, forward_output, weight):
+        """Vector epsilon rule (reference :522-547) as a tensor expression; kept for API compatibility — the
+        tuner and the explainer use the batched kernels instead of calling this per vector."""
+        assert r_out.dim() == 1 and forward_input.dim() == 1 and weight.dim() == 2
+        if type(forward_output) == bool:
+            forward_output = torch.matmul(forward_input, weight.transpose(0, 1))
+        z = self.EPS * forward_output.sign() + forward_output
+        z = z.masked_fill(z == 0, self.EPS)
+        return forward_input * torch.matmul(r_out / z, weight)
+
+    def _stop_mask(self, rev_word_map, device):
+        key = (id(rev_word_map), str(device))
+        m = self._stop_cache.get(key)
+        if m is None:
+            stop = set(STOP_WORDS)
+            m = torch.tensor([rev_word_map.get(i, '<unk>') in stop for i in range(self.vocab_size)],
+                             dtype=torch.uint8, device=device)
+            self._stop_cache = {key: m}
+        return m
+
+    def get_lrp_weight_step(self, predictions_t, rev_word_map, h2t_, context_hat):
+        """reference :549-578 — one batched kernel: argmax word (Q16), stop-word skip (Q15), fc epsilon rule,
+        split to h2 / context_hat, normalize_relevance (utils.py:55-64).  No host synchronisation."""
+        with torch.no_grad():
+            w_ctx, w_h, _ = ops.fc_lrp_weights(predictions_t.detach(), h2t_.detach(), context_hat.detach(),
+                                               self.fc.weight.detach(), self._stop_mask(rev_word_map, predictions_t.device))
+        return w_ctx, w_h
+
+    def _tune_step(self, image_feature_proj, Vt, img_proj, global_img_feature, word_embedding, state):
+        x1t_ = torch.cat((state[2], global_img_feature, word_embedding), dim=-1)
+        cell = self.AdaLSTM.lstm_cell
+        h1_, c1_, _, _, _ = _lstm_forward(x1t_, state[0], state[1], cell.weight_ih, cell.weight_hh, cell.bias_ih,
+                                          cell.bias_hh)
+        # the tuner takes the sentinel gate from the NEW h1 (reference :617, Q6)
+        st_ = torch.sigmoid(self.AdaLSTM.x_gate(x1t_) + self.AdaLSTM.h_gate(h1_)) * torch.tanh(c1_)
+        context_t_hat_, _, _, _ = self.AdaAttention.attend(Vt, img_proj, h1_, st_)
+        x2t_ = torch.cat((context_t_hat_, h1_), dim=-1)
+        L = self.LanguageLSTM
+        h2_, c2_, _, _, _ = _lstm_forward(x2t_, state[2], state[3], L.weight_ih, L.weight_hh, L.bias_ih, L.bias_hh)
+        return context_t_hat_, (h1_, c1_, h2_, c2_)
+
+    def forwardlrp_context(self, images, encoded_captions, caption_lengths, rev_word_map):
+        """reference :580-633 -> (predictions, weighted_predictions, max_length).  Differentiable w.r.t. the
+        model parameters; the LRP weights are constants computed under no_grad (:551)."""
+        batch_size = images.size(0)
+        _, image_feature_proj, global_img_feature = self._encode(images)
+        Vt, img_proj = self.AdaAttention.project_image(image_feature_proj)
+        state = self.init_hidden_state(image_feature_proj) + self.init_hidden_state(image_feature_proj)
+        max_length = int(max(caption_lengths)) - 1
+        predictions, weighted = [], []
+        for t in range(max_length):
+            context_t_hat_, state = self._tune_step(image_feature_proj, Vt, img_proj, global_img_feature,
+                                                    self.embedding(encoded_captions[:, t]), state)
+            h2_ = state[2]
+            predict_score_t = self.fc(context_t_hat_ + h2_)
+            weight_context_hat, weight_h2t = self.get_lrp_weight_step(predict_score_t, rev_word_map, h2_, context_t_hat_)
+            predictions.append(predict_score_t)
+            weighted.append(self.fc(context_t_hat_ * weight_context_hat + weight_h2t * h2_))
+        return torch.stack(predictions, 1), torch.stack(weighted, 1), max_length
+
+    def sample_lrp(self, images, rev_word_map, word_map, caption_lengths, opt={}):
+        """reference :635-702 -> (seq, seq_logprobs, max_length)."""
+        batch_size = images.size(0)
+        sample_method = opt.get('sample_method', 'greedy')
+        temperature = opt.get('temperature', 1.0)
+        max_length = int(max(caption_lengths)) - 1
+        _, image_feature_proj, global_img_feature = self._encode(images)
+        Vt, img_proj = self.AdaAttention.project_image(image_feature_proj)
+        state = self.init_hidden_state(image_feature_proj) + self.init_hidden_state(image_feature_proj)
+        dev = images.device
+        seq = torch.zeros(batch_size, max_length, dtype=torch.long, device=dev)
+        seq_logprobs = torch.zeros(batch_size, max_length, device=dev)
+        it = torch.full((batch_size,), word_map['<start>'], dtype=torch.long, device=dev)
+        unfinished = None
+        for t in range(max_length):
+            context_t_hat_, state = self._tune_step(image_feature_proj, Vt, img_proj, global_img_feature,
+                                                    self.embedding(it), state)
+            h2_ = state[2]
+            predict_score_t = self.fc(context_t_hat_ + h2_)
+            weight_context_hat, weight_h2t = self.get_lrp_weight_step(predict_score_t, rev_word_map, h2_, context_t_hat_)
+            logp = torch.log_softmax(self.fc(context_t_hat_ * weight_context_hat + weight_h2t * h2_), dim=-1)
+            it, sample_logprobs = self.sample_next_word(logp, sample_method, temperature)
+            finished = it == word_map['<end>']
+            unfinished = ~finished if unfinished is None else unfinished & ~finished
+            it = it * unfinished.type_as(it)
+            seq[:, t] = it
+            seq_logprobs[:, t] = sample_logprobs.view(-1)
+            if int(unfinished.sum()) == 0:
+                break
+        return seq, seq_logprobs, max_length
+
+
+# ----------------------------------------------------------------------------------------------------
+class ExplainGridTDAttention(object):
+    """reference :705-1211.  ``precision``: 'bf16' = tcgen05 encoder chain (VGG encoders), 'fp32' = the fp32
+    rule kernels through LRPtools (any supported encoder; the parity path)."""
+    EPS = LRPutil.EPSILON
+    EX_TYPE = 'lrp'
+    # the reference never zeroes sample.grad, so relevance_imgs[t] of explain_caption is the running sum over
+    # the words explained so far (Q1); set False for per-word heat-maps
+    ACCUMULATE_LIKE_REFERENCE = True
+
+    def __init__(self, args, word_map, model=None, precision=None):
+        self.args = args
+        self.word_map = word_map
+        self.vocab_size = len(word_map)
+        if model is not None:
+            self.model = model
+        else:
+            self.model = GridTDModel(args.embed_dim, args.hidden_dim, len(word_map), args.encoder)
+            checkpoint = torch.load(args.weight, map_location='cpu')
+            self.model.load_state_dict(checkpoint['state_dict'])
+            self.model.cuda()
+        self.model.eval()
+        # the forward passes are torch tensor ops; every relevance call below goes to liblrpx.so, which raises
+        # on non-CUDA tensors (there is no CPU fallback)
+        self.device = next(self.model.parameters()).device
+        is_vgg = isinstance(self.model.img_encoder.encoder, nn.Sequential)
+        self.precision = precision or ('bf16' if is_vgg else 'fp32')
+        if self.precision == 'bf16' and not is_vgg:
+            raise NotImplementedError("the tensor-core chain supports VGG-style encoders; use precision='fp32'")
+        self.mean = [0.485, 0.456, 0.406]
+        self.std = [0.229, 0.224, 0.225]
+        m = self.model
+        self.adalstm_weight_i, self.adalstm_weight_h = m.AdaLSTM.lstm_cell.weight_ih, m.AdaLSTM.lstm_cell.weight_hh
+        self.adalstm_bias_i, self.adalstm_bias_h = m.AdaLSTM.lstm_cell.bias_ih, m.AdaLSTM.lstm_cell.bias_hh
+        self.language_weight_i, self.language_weight_h = m.LanguageLSTM.weight_ih, m.LanguageLSTM.weight_hh
+        self.language_bias_i, self.language_bias_h = m.LanguageLSTM.bias_ih, m.LanguageLSTM.bias_hh
+        self.output_weight = m.fc.weight
+        self.visualizatioin_save_path = os.path.join(args.save_path, args.dataset + 'explanation')
+        os.makedirs(self.visualizatioin_save_path, exist_ok=True)
+        self._engine = None
+        self._weights = None
+        self._state = None
+
+    # ------------------------------------------------------------------ helpers
+    def lrp_linear_eps(self, r_out, forward_input, forward_output, weight):
+        """reference :744-765 (tensor expression, API compatibility)."""
+        if type(forward_output) == bool:
+            forward_output = torch.matmul(forward_input, weight.transpose(0, 1))
+        z = self.EPS * forward_output.sign() + forward_output
+        z = z.masked_fill(z == 0, self.EPS)
+        return forward_input * torch.matmul(r_out.reshape(-1) / z, weight)
+
+    def preprocess_img(self, img_filepath):
+        """reference :767-771: Resize((height,width)) -> ToTensor -> Normalize."""
+        from PIL import Image
+        import numpy as np
+        img = Image.open(img_filepath).convert('RGB').resize((self.args.width, self.args.height), Image.BILINEAR)
+        x = torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.).permute(2, 0, 1)
+        x = (x - torch.tensor(self.mean).view(3, 1, 1)) / torch.tensor(self.std).view(3, 1, 1)
+        return x.unsqueeze(0).to(self.device)
+
+    def _lrp_weights(self):
+        if self._weights is None:
+            sd = {k: v.detach() for k, v in self.model.state_dict().items()}
+            self._weights = _dec.gridtd_weights(sd)
+        return self._weights
+
+    def engine(self):
+        if self._engine is None:
+            from lrpx import tc
+            enc = self.model.img_encoder.encoder
+            convs = [m for m in enc if isinstance(m, nn.Conv2d)]
+            cfg = []
+            for m in enc:
+                if isinstance(m, nn.Conv2d):
+                    cfg.append(m.out_channels)
+                elif isinstance(m, nn.MaxPool2d):
+                    cfg.append("M")
+            self._engine = tc.TcVggEngine([c.weight for c in convs], [c.bias for c in convs], cfg, self.device)
+        return self._engine
+
+    def encode_images(self, imgs):
+        """Encoder forward -> (features (B,P,C) fp32 pixel-major, feature map size, encoder state)."""
+        if self.precision == 'bf16':
+            eng = self.engine()
+            est = eng.forward(imgs)
+            return eng.features(est, "pixel"), est.feat_hw, est
+        enc = self.model.img_encoder.encoder
+        if not hasattr(enc, "_lrpx_plan"):
+            lrp_wrapper.add_lrp(enc)
+        with torch.no_grad():
+            fmap = enc._lrpx_plan.forward(imgs.detach().float())
+        B, C, h, w = fmap.shape
+        return fmap.flatten(2).transpose(1, 2).contiguous(), (h, w), None
+
+    def explainer_forward(self, feat, tokens, quirk_double_bias_ih=True):
+        """The explainer's teacher-forced forward (reference :941-1012) batched over images.
+
+        feat: (B,P,C) pixel-major encoder output; tokens: (B,L) long, column 0 = <start>.  Returns the saved
+        state in the kernels' layout (lrpx_gridtd_args), T = L-1 steps.  ``quirk_double_bias_ih`` reproduces the
+        explainer's language LSTM adding bias_ih twice (:789, Q3)."""
+        m = self.model
+        B, P, C = feat.shape
+        H, E = m.hidden_dim, m.embed_dim
+        T = tokens.shape[1] - 1
+        with torch.no_grad():
+            avg = feat.mean(1)
+            Wp = m.img_projector.weight.reshape(H, C)
+            A_pre = feat @ Wp.t() + m.img_projector.bias
+            A = A_pre.clamp(min=0)
+            glob_pre = m.global_img_feature_proj(avg)
+            glob = glob_pre.clamp(min=0)
+            att = m.AdaAttention
+            img_proj = att.W_v_proj(A)
+            zeros = feat.new_zeros(B, H)
+            h1, c1, h2, c2 = [zeros], [zeros], [zeros], [zeros]
+            keys = ["x1", "x2", "g1", "i1", "f1", "g2", "i2", "f2", "st", "ctx", "ctx_hat", "alpha", "beta", "pred"]
+            seq = {k: [] for k in keys}
+            cell, L = m.AdaLSTM.lstm_cell, m.LanguageLSTM
+            lb2 = L.bias_ih if quirk_double_bias_ih else L.bias_hh
+            for t in range(T):
+                emb = m.embedding(tokens[:, t])
+                x1 = torch.cat((h2[t], glob, emb), dim=-1)
+                h1n, c1n, g1, i1, f1 = _lstm_forward(x1, h1[t], c1[t], cell.weight_ih, cell.weight_hh, cell.bias_ih,
+                                                     cell.bias_hh)
+                s = torch.sigmoid(m.AdaLSTM.x_gate(x1) + m.AdaLSTM.h_gate(h1[t])) * torch.tanh(c1n)   # OLD h1 (:982)
+                ctx_hat, ctx, alpha, beta = att.attend(A, img_proj, h1n, s)
+                x2 = torch.cat((ctx_hat, h1n), dim=-1)
+                h2n, c2n, g2, i2, f2 = _lstm_forward(x2, h2[t], c2[t], L.weight_ih, L.weight_hh, L.bias_ih, lb2)
+                pred = m.fc(ctx_hat + h2n)
+                for k, v in zip(keys, [x1, x2, g1, i1, f1, g2, i2, f2, s, ctx, ctx_hat, alpha, beta.squeeze(-1), pred]):
+                    seq[k].append(v)
+                h1.append(h1n); c1.append(c1n); h2.append(h2n); c2.append(c2n)
+            st = {k: torch.stack(v, 1).contiguous() for k, v in seq.items()}
+            for k, v in (("h1", h1), ("c1", c1), ("h2", h2), ("c2", c2)):
+                st[k] = torch.stack(v, 1).contiguous()
+            st.update(feat=feat.contiguous(), avg=avg, A_pre=A_pre.contiguous(), A=A.contiguous(), glob_pre=glob_pre)
+        return st
+
+    def teacherforce_forward(self, img, beam_caption_encode):
+        """reference :892-931 -> logits (len(beam_caption_encode), vocab)."""
+        feat, _, _ = self.encode_images(img)
+        toks = torch.tensor([list(beam_caption_encode) + [0]], dtype=torch.long, device=self.device)
+        return self.explainer_forward(feat, toks)["pred"][0]
+
+    # ------------------------------------------------------------------ reference entry points
+    def get_hidden_parameters(self, img_filepath):
+        self.img = self.preprocess_img(img_filepath)
+        self.beam_caption, self.beam_caption_encode = self.model.beam_search(self.img, self.word_map, beam_size=2,
+                                                                             max_cap_length=50)
+        self.beam_caption_encode = [self.word_map['<start>']] + self.beam_caption_encode
+        print(f'the predicted caption of {img_filepath} is "{self.beam_caption[0]}"')
+        self._set_state(self.img, self.beam_caption_encode)
+
+    def _set_state(self, img, tokens):
+        feat, (fh, fw), est = self.encode_images(img)
+        toks = torch.tensor([tokens], dtype=torch.long, device=self.device)
+        st = self.explainer_forward(feat, toks)
+        self._state, self._enc_state, self._feat_hw = st, est, (fh, fw)
+        self.caption_length = len(tokens) - 1
+        self.num_pixels = feat.shape[1]
+        # attributes the reference exposes (read by evaluation.py: .predictions .alphas .betas ...)
+        self.predictions, self.alphas, self.betas = st["pred"][0], st["alpha"][0], st["beta"][0]
+        self.x1t, self.x2t = st["x1"][0], st["x2"][0]
+        self.h1t, self.c1t, self.h2t, self.c2t = st["h1"][0], st["c1"][0], st["h2"][0], st["c2"][0]
+        self.g1t, self.i1t_act, self.f1t_act = st["g1"][0], st["i1"][0], st["f1"][0]
+        self.g2t, self.i2t_act, self.f2t_act = st["g2"][0], st["i2"][0], st["f2"][0]
+        self.st, self.context, self.context_hat = st["st"][0], st["ctx"][0], st["ctx_hat"][0]
+        C = feat.shape[2]
+        self.image_features = feat[0].t().reshape(1, C, fh, fw)
+        self.avg_feature = st["avg"][0]
+
+    def _decoder_lrp(self, ts):
+        toks = self.beam_caption_encode
+        dev = self.device
+        req_t = torch.tensor(ts, dtype=torch.int32, device=dev)
+        req_word = torch.tensor([toks[t + 1] for t in ts], dtype=torch.int32, device=dev)
+        req_img = torch.zeros(len(ts), dtype=torch.int32, device=dev)
+        return ops.gridtd_decoder_lrp(self._state, self._lrp_weights(), req_img, req_t, req_word)
+
+    def explain_caption_wordt(self, t):
+        """reference :1014-1135 -> (r_img_feature (1,C,h,w), r_words (t+1,))."""
+        assert t < self.caption_length
+        r_feat, r_words = self._decoder_lrp([t])
+        fh, fw = self._feat_hw
+        r_img_feature = r_feat[0].t().reshape(1, -1, fh, fw)
+        return r_img_feature, r_words[0, :t + 1]
+
+    def explain_cnn(self, r_img_feature):
+        """reference :1137-1139: relevance of the encoder output -> relevance of the image (1,3,H,W)."""
+        if self.precision == 'bf16':
+            r_pix = r_img_feature.flatten(2).transpose(1, 2).contiguous()
+            return self.engine().relevance(self._enc_state, r_pix)
+        enc = self.model.img_encoder.encoder
+        if not hasattr(enc, "_lrpx_plan"):
+            lrp_wrapper.add_lrp(enc)
+        return enc.compute_lrp(self.img, target=r_img_feature)
+
+    def explain_caption(self, img_filepath, t_list=None):
+        """reference :1141-1156 -> (relevance_imgs [T x (1,3,H,W)], relevance_preceeding_words [T x (t+1,)]).
+        All words of the caption are explained in one batched decoder call + one batched encoder chain."""
+        self.img_filepath = img_filepath
+        self.get_hidden_parameters(img_filepath)
+        T = self.caption_length
+        r_feat, r_words = self._decoder_lrp(list(range(T)))
+        if self.precision == 'bf16':
+            rows = torch.zeros(T, dtype=torch.int32, device=self.device)
+            heat = self.engine().relevance(self._enc_state, r_feat, rows)
+        else:
+            enc = self.model.img_encoder.encoder
+            lrp_wrapper.add_lrp(enc)
+            fh, fw = self._feat_hw
+            heat = torch.cat([lrp_wrapper.compute_lrp(enc, self.img.detach().clone(),
+                                                      target=r_feat[t].t().reshape(1, -1, fh, fw)) for t in range(T)])
+        if self.ACCUMULATE_LIKE_REFERENCE:
+            heat = torch.cumsum(heat, 0)
+        relevance_imgs = [heat[t:t + 1] for t in range(T)]
+        relevance_preceeding_words = [r_words[t, :t + 1] for t in range(T)]
+        self.visualize_explanations(relevance_imgs, t=t_list)
+        self.save_linguistic_explanation(relevance_preceeding_words)
+        return relevance_imgs, relevance_preceeding_words
+
+    def save_linguistic_explanation(self, relevance_preceeding_words):
+        """reference :1158-1174 (yaml dump of the per-word relevances)."""
+        import yaml
+        name = os.path.basename(self.img_filepath)
+        save_dir = os.path.join(self.visualizatioin_save_path, name[:-4] if name.endswith('.jpg') else name)
+        os.makedirs(save_dir, exist_ok=True)
+        words = ['<start>'] + self.beam_caption[0].split(' ')
+        out = []
+        for t in range(min(self.caption_length, len(words) - 1)):
+            rel = relevance_preceeding_words[t].tolist()
+            out.append({words[t + 1]: [{words[i]: rel[i]} for i in range(len(rel))]})
+        with open(os.path.join(save_dir, self.EX_TYPE + '_linguistic_explanation.yaml'), 'w') as f:
+            yaml.safe_dump(out, f)
+
+    def visualize_explanations(self, relevance_imgs, t=None):
+        """The reference renders matplotlib figures (:1176-1211); plotting is out of scope."""
+        return None

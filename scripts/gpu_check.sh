@@ -1,0 +1,15 @@
+#!/bin/bash
+# Runs on the GPU box (via gpurun): per-file GPU parity tests, smoke(), a short bench.  Logs -> gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,driver_version,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+for f in rules decoder encoder tc models; do
+  timeout 900 python -m pytest tests/test_gpu_$f.py -q -m gpu --tb=short -s > gpurun_out/test_$f.log 2>&1
+  echo "test_gpu_$f exit $?" | tee -a gpurun_out/summary.txt
+  tail -n 3 gpurun_out/test_$f.log
+done
+timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
+echo "smoke exit $?" | tee -a gpurun_out/summary.txt
+tail -n 2 gpurun_out/smoke.log
+timeout 900 python bench.py --steps 2 --warmup 3 ${BENCH_ARGS} > gpurun_out/bench.log 2>&1
+echo "bench exit $?" | tee -a gpurun_out/summary.txt
+tail -c 3000 gpurun_out/bench.log

@@ -1,0 +1,119 @@
+"""GPU parity through the reference-facing Python API: ExplainGridTDAttention / GridTDModel tuner entry points."""
+import argparse
+
+import pytest
+import torch
+
+import lrp_oracle as O
+import synth
+from conftest import assert_close, spearman
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _args(E, H, tmp_path):
+    return argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                              save_path=str(tmp_path), dataset="syn", weight="")
+
+
+def test_explainer_vs_reference_fixture(golden, tmp_path):
+    """get_hidden_parameters + explain_caption_wordt with the encoder stubbed by the fixture's features
+    (exactly how oracle/make_golden.py drove the reference)."""
+    from models import gridTDmodel as G
+    g = golden("gridtd_dec_512")
+    V, H, E = int(g["V"]), int(g["H"]), int(g["E"])
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(int(g["seed"]), V, H, E), strict=False)
+    model.to(DEV)
+    ex = G.ExplainGridTDAttention(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="fp32")
+    toks = g["tokens"].tolist()
+    feat = g["feats"][0].flatten(1).t().unsqueeze(0).contiguous().to(DEV)
+    ex.preprocess_img = lambda p: torch.zeros(1, 3, 224, 224, device=DEV)
+    ex.encode_images = lambda img: (feat, (14, 14), None)
+    model.beam_search = lambda *a, **k: ([" ".join(f"w{t}" for t in toks[1:])], toks[1:])
+    ex.get_hidden_parameters("x")
+    assert ex.caption_length == int(g["T"])
+    assert_close(ex.predictions, g["predictions"], atol=5e-5, what="predictions")
+    assert_close(ex.alphas, g["alphas"].reshape(ex.alphas.shape), atol=1e-6, what="alphas")
+    assert_close(ex.betas, g["betas"].reshape(-1), atol=1e-6, what="betas")
+    for t in g["ts"].tolist():
+        rf, rw = ex.explain_caption_wordt(t)
+        ref = g[f"r_feat_{t}"]
+        assert rf.shape == ref.shape
+        scale = ref.abs().max()
+        assert_close(rf / scale, ref / scale, rtol=1e-3, atol=2e-5, what=f"r_img_feature t={t}")
+        assert_close(rw, g[f"r_words_{t}"], rtol=1e-3, atol=2e-5, what=f"r_words t={t}")
+
+
+def test_forwardlrp_context_vs_reference_fixture(golden):
+    """lrp_tune step: predictions and LRP-weighted predictions of the full model (VGG16 encoder, 224x224)."""
+    from models import gridTDmodel as G
+    g = golden("tune_gridtd")
+    V, H, E = int(g["V"]), int(g["H"]), int(g["E"])
+    s = g["seeds"].tolist()
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(s[0], V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(s[1]))
+    model.to(DEV).eval()
+    wm = synth.word_map(V)
+    rev = {v: k for k, v in wm.items()}
+    for i in range(V):
+        if bool(g["stop"][i]) and rev[i].startswith("w"):
+            rev[i] = "the"
+    imgs = synth.images(s[2], 2).to(DEV)
+    with torch.no_grad():
+        pred, wpred, maxlen = model.forwardlrp_context(imgs, g["caps"].to(DEV), g["caplens"], rev)
+    assert maxlen == int(g["max_length"])
+    assert_close(pred, g["predictions"], rtol=1e-3, atol=1e-3, what="predictions")
+    assert_close(wpred, g["weighted_predictions"], rtol=2e-3, atol=2e-3, what="weighted predictions")
+    # differentiable w.r.t. the parameters, weights are constants
+    model.train()
+    pred, wpred, _ = model.forwardlrp_context(imgs, g["caps"].to(DEV), g["caplens"], rev)
+    (pred.sum() + wpred.sum()).backward()
+    assert model.fc.weight.grad is not None and torch.isfinite(model.fc.weight.grad).all()
+
+
+def test_explain_caption_end_to_end_both_precisions(tmp_path):
+    """Full drop-in call on a 224x224 image: the bf16 tensor-core chain agrees with the fp32 rule kernels
+    (Spearman >= 0.99 per word) and the per-word results match the CPU oracle for the fp32 path."""
+    from models import gridTDmodel as G
+    V, H, E = 60, 64, 32
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(81, V, H, E), strict=False)
+    vsd = synth.vgg_state(82)
+    model.img_encoder.encoder.load_state_dict(vsd)
+    model.to(DEV).eval()
+    img = synth.images(83, 1)
+    toks = synth.tokens(84, 3, V)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        ex = G.ExplainGridTDAttention(_args(E, H, tmp_path), synth.word_map(V), model=model, precision=prec)
+        ex.ACCUMULATE_LIKE_REFERENCE = False
+        ex.preprocess_img = lambda p: img.to(DEV)
+        model.beam_search = lambda *a, **k: (["a b c"], toks[1:])
+        outs[prec] = ex.explain_caption("synthetic.jpg")
+    heat32, words32 = outs["fp32"]
+    heat16, words16 = outs["bf16"]
+    assert len(heat32) == 3 and heat32[0].shape == (1, 3, 224, 224)
+    # fp32 path vs the oracle
+    layers = O.vgg_layers_from_state(vsd)
+    feats = O.sequential_forward(layers, img)[-1]
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    st = O.gridtd_explainer_forward(sd, feats[0], toks)
+    for t in range(3):
+        rf, rw, _ = O.gridtd_explain_wordt(sd, st, t)
+        ref = O.sequential_lrp(layers, img, rf.t().reshape(1, 512, 14, 14))
+        scale = ref.abs().max()
+        assert_close(heat32[t] / scale, ref / scale, rtol=2e-3, atol=2e-4, what=f"fp32 heat-map t={t}")
+        assert_close(words32[t], rw, rtol=1e-3, atol=1e-4, what=f"r_words t={t}")
+        sp = spearman(heat16[t], heat32[t])
+        l2 = float((heat16[t] - heat32[t]).norm() / heat32[t].norm())
+        print(f"word {t}: bf16 vs fp32 spearman {sp:.5f} rel L2 {l2:.3e}")
+        assert sp >= 0.99 and l2 <= 1e-1

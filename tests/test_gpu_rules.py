@@ -1,0 +1,171 @@
+"""GPU parity: every fp32 relevance rule kernel, called through the C ABI (lrpx.ops -> liblrpx.so), against
+the golden fixtures generated from the reference and against the oracle on seeded random shapes.
+Tolerance: north_star fp32 bar, rtol 1e-4 / atol 1e-6 (looser only where stated)."""
+import pytest
+import torch
+
+import lrp_oracle as O
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _c(*ts):
+    return [t.to(DEV) if t is not None else None for t in ts]
+
+
+def test_conv_alpha_beta_golden(golden):
+    from lrpx import ops
+    g = golden("rules")
+    x, w, b, r = _c(g["conv_x"], g["conv_w"], g["conv_b"], g["conv_r"])
+    assert_close(ops.conv_alpha_beta(x, w, b, r, 2, 1, 1, 1., 0.), g["conv_R_a1b0"], what="a1b0")
+    assert_close(ops.conv_alpha_beta(x, w, b, r, 2, 1, 1, 2., 1.), g["conv_R_a2b1"], rtol=2e-4, atol=2e-5, what="a2b1")
+    assert_close(ops.conv_alpha_beta(x, w, b, r, 2, 1, 1, 2., 1., ignore_bias=False), g["conv_R_a2b1_bias"],
+                 rtol=2e-4, atol=2e-5, what="a2b1 bias")   # alpha*R+ - beta*R- cancels: looser than the a1b0 bar
+    x2, w2, r2 = _c(g["conv2_x"], g["conv2_w"], g["conv2_r"])
+    assert_close(ops.conv_alpha_beta(x2, w2, None, r2, 1, 1), g["conv2_R"], what="conv2")
+
+
+@pytest.mark.parametrize("shape", [
+    # n, cin, h, w, cout, k, stride, pad, dil
+    (2, 3, 17, 13, 8, 3, 1, 1, 1),
+    (1, 16, 14, 14, 24, 3, 1, 1, 1),
+    (2, 8, 15, 15, 5, 1, 2, 0, 1),
+    (1, 3, 33, 29, 7, 7, 2, 3, 1),
+    (1, 6, 12, 12, 4, 3, 1, 2, 2),
+    (3, 130, 7, 7, 70, 3, 1, 1, 1),
+])
+def test_conv_alpha_beta_vs_oracle(shape):
+    from lrpx import ops
+    n, cin, h, w, cout, k, s, p, d = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w, generator=g)
+    x[0, 0, :2] = 0
+    wt = torch.randn(cout, cin, k, k, generator=g) * 0.2
+    b = torch.randn(cout, generator=g) * 0.1
+    P = (h + 2 * p - d * (k - 1) - 1) // s + 1
+    Q = (w + 2 * p - d * (k - 1) - 1) // s + 1
+    r = torch.randn(n, cout, P, Q, generator=g)
+    for alpha, beta, ib in [(1., 0., True), (2., 1., True), (1., 0., False)]:
+        ref = O.conv_alpha_beta(x.double(), wt.double(), b.double(), r.double(), s, p, d, 1, alpha, beta, ib)
+        got = ops.conv_alpha_beta(*_c(x, wt, b, r), s, p, d, alpha, beta, ib)
+        scale = ref.abs().max()
+        assert_close(got / scale, ref / scale, rtol=1e-4, atol=2e-6, what=f"conv {shape} a={alpha} b={beta} ib={ib}")
+    # conservation of the z+ rule without bias on a non-negative input: sum R_in == sum R_out
+    xp = x.clamp(min=0) + 0.01
+    got = ops.conv_alpha_beta(*_c(xp, wt, None, r), s, p, d)
+    zp = O._conv_signed_net(xp.double(), wt.double(), None, True, s, p, d, 1, True)[0]
+    expect = r.double()[zp != 0].sum()
+    assert abs(ops.sum_f64(got).item() - expect.item()) <= 1e-4 * r.abs().sum().item()
+
+
+def test_conv_forward_and_epsilon():
+    from lrpx import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 6, 11, 9, generator=g)
+    x[0, :, 3] = 0
+    w = torch.randn(10, 6, 3, 3, generator=g) * 0.3
+    b = torch.randn(10, generator=g)
+    ref = torch.nn.functional.conv2d(x, w, b, 2, 1)
+    assert_close(ops.conv_forward(*_c(x, w, b), 2, 1), ref, atol=1e-5, what="conv forward")
+    assert_close(ops.conv_forward(*_c(x, w, b), 2, 1, relu=True), ref.clamp(min=0), atol=1e-5, what="conv+relu")
+    r = torch.randn_like(ref)
+    for ib in (True, False):
+        want = O.conv_epsilon_unpinned(x.double(), w.double(), b.double(), r.double(), 2, 1, ignore_bias=ib)
+        got = ops.conv_epsilon(*_c(x, w, b, r), 2, 1, ignore_bias=ib)
+        scale = want.abs().max()
+        assert_close(got / scale, want / scale, rtol=1e-4, atol=2e-6, what=f"conv epsilon ib={ib}")
+
+
+def test_linear_epsilon(golden):
+    from lrpx import ops
+    g = golden("rules")
+    x, w, b, r = _c(g["lin_x"], g["lin_w"], g["lin_b"], g["lin_r"])
+    assert_close(ops.linear_epsilon(x, w, b, r, True), g["lin_R_nobias"], what="linear eps")
+    assert_close(ops.linear_epsilon(x, w, b, r, False), g["lin_R_bias"], what="linear eps bias")
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(37, 130, generator=gen); w = torch.randn(75, 130, generator=gen) * 0.1
+    r = torch.randn(37, 75, generator=gen)
+    want = O.linear_epsilon(x.double(), w.double(), None, r.double())
+    got = ops.linear_epsilon(*_c(x, w, None, r))
+    scale = want.abs().max()
+    assert_close(got / scale, want / scale, rtol=1e-4, atol=2e-6, what="linear eps big")
+
+
+def test_pools(golden):
+    from lrpx import ops
+    g = golden("rules")
+    x, r = _c(g["pool_x"], g["pool_r"])
+    assert_close(ops.maxpool_wta(x, r, 2, 2), g["mp2_R"], what="maxpool wta 2x2")
+    y, idx = ops.maxpool_forward(x, 2, 2)
+    assert torch.equal(idx.cpu(), g["mp2_idx"]), "argmax indices must be bit-exact"
+    assert torch.equal(y.cpu(), torch.nn.functional.max_pool2d(g["pool_x"], 2, 2))
+    x3, r3 = _c(g["pool3_x"], g["pool3_r"])
+    assert_close(ops.maxpool_wta(x3, r3, 3, 2, 1), g["mp3_R"], what="maxpool wta 3x3 s2 p1")
+    y, idx = ops.maxpool_forward(x3, 3, 2, 1)
+    assert torch.equal(idx.cpu(), g["mp3_idx"])
+    assert_close(ops.avgpool_prop(x, r, 2, 2), g["ap2_R"], what="avgpool")
+
+
+def test_maxpool_indices_ties_and_nan():
+    from lrpx import ops
+    x = torch.zeros(1, 2, 6, 6)
+    x[0, 0, 2:4, 2:4] = 1.0            # a window of equal maxima: first in scan order wins
+    x[0, 1, 1, 1] = float("nan")       # NaN wins
+    x[0, 1, 4, 4] = -1.0
+    for k, s, p in [(2, 2, 0), (3, 2, 1), (3, 1, 1)]:
+        y, idx = ops.maxpool_forward(x.to(DEV), k, s, p)
+        ry, ridx = torch.nn.functional.max_pool2d(x, k, s, p, return_indices=True)
+        assert torch.equal(idx.cpu(), ridx), (k, s, p)
+        assert torch.equal(torch.nan_to_num(y.cpu(), nan=7.0), torch.nan_to_num(ry, nan=7.0))
+    g = torch.Generator().manual_seed(3)
+    big = torch.randn(2, 5, 30, 22, generator=g).round(decimals=1)      # many ties
+    y, idx = ops.maxpool_forward(big.to(DEV), 3, 2, 1)
+    ry, ridx = torch.nn.functional.max_pool2d(big, 3, 2, 1, return_indices=True)
+    assert torch.equal(idx.cpu(), ridx) and torch.equal(y.cpu(), ry)
+
+
+def test_elementwise(golden):
+    from lrpx import ops
+    g = golden("rules")
+    got = ops.bn_absratio(*_c(g["bn_x"], g["bn_r"], g["bn_mean"], g["bn_var"], g["bn_gamma"], g["bn_beta"]),
+                          float(g["bn_eps"]))
+    assert_close(got, g["bn_R"], what="bn")
+    r1, r2 = ops.add_split(*_c(g["add_x1"], g["add_x2"], g["add_r"]))
+    assert_close(r1, g["add_R1"], what="add r1")
+    assert_close(r2, g["add_R2"], what="add r2")
+    assert_close(ops.relu_mask(*_c(g["relu_x"], g["relu_r"])), g["relu_R_mask"], what="relu mask")
+    assert_close(ops.normalize_relevance(g["norm_x"].to(DEV)), g["norm_y"], what="normalize")
+    x = torch.randn(1000, 37)
+    assert abs(ops.sum_f64(x.to(DEV)).item() - x.double().sum().item()) < 1e-6
+
+
+def test_empty_inputs():
+    from lrpx import ops
+    z = torch.zeros(0, device=DEV)
+    assert ops.relu_mask(z, z).numel() == 0
+    assert ops.add_split(z, z, z)[0].numel() == 0
+    assert ops.sum_f64(z).item() == 0.0
+
+
+def test_lrp_weights(golden):
+    import synth
+    from lrpx import ops
+    g = golden("lrp_weights")
+    p = synth.gridtd_decoder_state(int(g["seed"]), int(g["V"]), int(g["H"]), int(g["E"]))
+    wc, wh, am = ops.fc_lrp_weights(*_c(g["logits"], g["h"], g["ctx"], p["fc.weight"], g["stop"]))
+    assert torch.equal(am.cpu().long(), g["logits"].argmax(-1)), "argmax must be bit-exact"
+    assert_close(wc, g["w_ctx"], atol=1e-5, what="w_ctx")
+    assert_close(wh, g["w_h"], atol=1e-5, what="w_h")
+    gen = torch.Generator().manual_seed(4)
+    B, V, H = 64, 10000, 512
+    logits = torch.randn(B, V, generator=gen); h = torch.randn(B, H, generator=gen); c = torch.randn(B, H, generator=gen)
+    logits[5, 17] = logits[5, 4000] = 50.0                      # tie: first index wins
+    fc = torch.randn(V, H, generator=gen) * 0.05
+    stop = synth.stop_mask(V)
+    wc, wh, am = ops.fc_lrp_weights(*_c(logits, h, c, fc, stop))
+    rc, rh = O.lrp_weight_step(logits, h, c, fc, stop)
+    assert torch.equal(am.cpu().long(), logits.argmax(-1))
+    assert_close(wc, rc, atol=1e-5, what="w_ctx big")
+    assert_close(wh, rh, atol=1e-5, what="w_h big")

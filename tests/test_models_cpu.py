@@ -1,0 +1,72 @@
+"""CPU: host-side logic of the model mirrors — state_dict compatibility with the reference layout, the
+explainer's teacher-forced forward (incl. quirks Q3/Q19) against the reference fixtures, beam search."""
+import argparse
+
+import pytest
+import torch
+
+import lrp_oracle as O
+import synth
+from conftest import assert_close
+
+
+def _explainer(g, tmp_path):
+    from models import gridTDmodel as G
+    V, H, E = int(g["V"]), int(g["H"]), int(g["E"])
+    model = G.GridTDModel(E, H, V, "vgg16")
+    sd = synth.gridtd_decoder_state(int(g["seed"]), V, H, E)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("img_encoder.") for k in missing)
+    args = argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                              save_path=str(tmp_path), dataset="syn", weight="")
+    return G.ExplainGridTDAttention(args, synth.word_map(V), model=model), sd
+
+
+@pytest.mark.parametrize("name", ["gridtd_dec_small", "gridtd_dec_512"])
+def test_explainer_forward_matches_reference_fixture(golden, tmp_path, name):
+    g = golden(name)
+    ex, sd = _explainer(g, tmp_path)
+    feat = g["feats"][0].flatten(1).t().unsqueeze(0).contiguous()          # (1,P,C)
+    toks = torch.tensor([g["tokens"].tolist()])
+    st = ex.explainer_forward(feat, toks)
+    assert_close(st["pred"][0], g["predictions"], atol=3e-5, what="predictions")
+    assert_close(st["alpha"][0], g["alphas"].reshape(st["alpha"][0].shape), atol=1e-6, what="alphas")
+    assert_close(st["beta"][0], g["betas"].reshape(-1), atol=1e-6, what="betas")
+    assert_close(st["h2"][0], g["h2t"], atol=1e-5, what="h2t")
+    assert_close(st["c1"][0], g["c1t"], atol=1e-5, what="c1t")
+    assert_close(st["ctx_hat"][0], g["context_hat"], atol=1e-5, what="context_hat")
+    # and key-by-key against the oracle's restatement
+    ost = O.gridtd_explainer_forward(sd, g["feats"][0], g["tokens"].tolist())
+    for k, ok in [("x1", "x1"), ("x2", "x2"), ("g1", "g1"), ("i2", "i2"), ("st", "s"), ("ctx", "ctx"), ("A_pre", "A_pre")]:
+        assert_close(st[k][0], ost[ok], atol=2e-5, what=k)
+
+
+def test_state_dict_keys_match_reference_layout():
+    from models import gridTDmodel as G, vgg, resnet
+    m = G.GridTDModel(32, 48, 50, "vgg16")
+    keys = set(k for k in m.state_dict() if not k.startswith("img_encoder."))
+    assert keys == set(synth.gridtd_decoder_state(0, 50, 48, 32).keys())
+    enc_keys = set(k[len("img_encoder.encoder."):] for k in m.state_dict() if k.startswith("img_encoder.encoder."))
+    assert enc_keys == set(synth.vgg_state(0).keys())
+    r = resnet.ResNet(resnet.Bottleneck, [2, 1, 1, 1])
+    assert set(r.state_dict().keys()) == set(synth.resnet_state(0, (2, 1, 1, 1)).keys())
+
+
+def test_beam_search_runs_and_uses_floor_division():
+    from models import gridTDmodel as G
+    torch.manual_seed(0)
+    V = 40
+    m = G.GridTDModel(16, 24, V, "vgg16").eval()
+    wm = synth.word_map(V)
+    sent, idx = m.beam_search(torch.randn(1, 3, 224, 224), wm, beam_size=2, max_cap_length=6)
+    assert isinstance(sent, list) and all(0 < i < V - 3 for i in idx) and len(idx) <= 20
+
+
+def test_lrp_linear_eps_expression_matches_oracle():
+    from models import gridTDmodel as G
+    m = G.GridTDModel(8, 8, 20, "vgg16")
+    g = torch.Generator().manual_seed(1)
+    x, w, r = torch.randn(6, generator=g), torch.randn(5, 6, generator=g), torch.randn(5, generator=g)
+    z = w @ x
+    assert_close(m.lrp_linear_eps(r, x, z, w), O.lrp_linear_eps(r, x, z, w), what="lrp_linear_eps")
+    assert_close(m.lrp_linear_eps(r, x, False, w), O.lrp_linear_eps(r, x, False, w), what="lrp_linear_eps recompute")
