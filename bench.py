@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--vocab", type=int, default=10000)
     ap.add_argument("--chunk", type=int, default=64, help="explanations per relevance-chain launch group")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run 1 warm-up + 1 step and exit (the command line captured under ncu for profiles/)")
     ap.add_argument("--cpu-words", type=int, default=3, help="words of the bounded CPU sample")
     return ap.parse_args()
 
@@ -199,6 +201,28 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    if args.profile_step:
+        step(imgs_d, toks_d)
+        torch.cuda.synchronize()
+        step(imgs_d, toks_d)
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_step": "done", "explanations": Q}))
+        return
+
+    def breakdown():
+        """One instrumented step (outside the timed region): CUDA-event time of each phase."""
+        marks = [ev() for _ in range(6)]
+        marks[0].record()
+        est = eng.forward(imgs_d); marks[1].record()
+        feat = eng.features(est, "pixel")
+        st = ex.explainer_forward(feat, toks_d); marks[2].record()
+        r_feat, r_words = ops.gridtd_decoder_lrp(st, W, req_img, req_t, toks_d[:, 1:].reshape(-1).to(torch.int32))
+        marks[3].record()
+        eng.relevance(est, r_feat, req_img, chunk=args.chunk, out=heat); marks[4].record()
+        torch.cuda.synchronize()
+        names = ["encoder_forward_gains", "explainer_forward_torch", "decoder_relevance", "encoder_relevance_chain"]
+        return {n: round(marks[i].elapsed_time(marks[i + 1]), 3) for i, n in enumerate(names)}
+
     for _ in range(max(args.warmup, 3)):
         step(imgs_d, toks_d)
     calls0 = dict(_lib.CALLS)
@@ -210,6 +234,7 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    phase_ms = breakdown()
 
     # launches of OUR kernels inside the timed region: one per C-ABI call, except the decoder call which
     # enqueues 1 init + 1 memset-free zeroing + 5 per step + 5 tail kernels (csrc/decoder.cu)
@@ -242,6 +267,7 @@ def run_ours(args):
                          "share_of_step": chain_total / ms,
                          "algorithmic_gflop_per_explanation": eng.flops_per_explanation() / 1e9},
         }
+        out["breakdown_ms"] = phase_ms
         try:
             out["roofline"]["layers"] = layer_table(eng, args.chunk, dev, pk)
         except Exception as e:  # never lose the bench line to the per-layer microbenchmark

@@ -167,6 +167,8 @@ def bn_absratio(x, r_out, running_mean, running_var, gamma, beta, eps):
 def add_split(x1, x2, r_out):
     x1, x2, r_out = _f32(x1, "x1"), _f32(x2, "x2"), _f32(r_out, "r_out")
     r1, r2 = torch.empty_like(x1), torch.empty_like(x2)
+    if x1.numel() == 0:
+        return r1, r2
     check(lib().lrpx_add_split_f32(_ptr(x1), _ptr(x2), _ptr(r_out), _ptr(r1), _ptr(r2), x1.numel(), _stream()),
           "lrpx_add_split_f32")
     return r1, r2
@@ -175,6 +177,8 @@ def add_split(x1, x2, r_out):
 def relu_mask(x, r_out):
     x, r_out = _f32(x, "x"), _f32(r_out, "r_out")
     r_in = torch.empty_like(r_out)
+    if x.numel() == 0:
+        return r_in
     check(lib().lrpx_relu_mask_f32(_ptr(x), _ptr(r_out), _ptr(r_in), x.numel(), _stream()), "lrpx_relu_mask_f32")
     return r_in
 
@@ -184,6 +188,8 @@ def normalize_relevance(x, temperature=1.0):
     cols = x.shape[-1]
     rows = x.numel() // cols
     y = torch.empty_like(x)
+    if x.numel() == 0:
+        return y
     check(lib().lrpx_normalize_relevance_f32(_ptr(x), _ptr(y), rows, cols, float(temperature), _stream()),
           "lrpx_normalize_relevance_f32")
     return y
@@ -191,7 +197,9 @@ def normalize_relevance(x, temperature=1.0):
 
 def sum_f64(x) -> torch.Tensor:
     x = _f32(x, "x")
-    out = torch.empty(1, device=x.device, dtype=torch.float64)
+    out = torch.zeros(1, device=x.device, dtype=torch.float64)
+    if x.numel() == 0:
+        return out
     check(lib().lrpx_sum_f64(_ptr(x), x.numel(), _ptr(out), _stream()), "lrpx_sum_f64")
     return out
 

@@ -1,0 +1,385 @@
+"""Host-side mirror of the LRP entry points of the reference's models/aoamodel.py.
+
+* ``AOAModel`` — state_dict-compatible module (reference :111-139): ``forward`` (:160-211), ``beam_search``
+  (:405-485), tuner entry points ``get_lrp_weight_step`` (:597-626), ``forwardlrp_context`` (:628-677),
+  ``sample_lrp`` (:679-745).
+* ``ExplainAOAAttention`` — ``get_hidden_parameters`` (:990-1062), ``lrp_mha`` (:812-862),
+  ``explain_caption_wordt(t, head_idx)`` (:1064-1156), ``explain_cnn`` (:1158-1163), ``explain_caption``
+  (:1165-1181), ``explain_caption_words`` (:1183-1194).
+
+The relevance arithmetic runs in liblrpx.so (``lrpx_aoa_decoder_lrp_f32``, ``lrpx_fc_lrp_weights_f32``, the
+encoder kernels); see models/gridTDmodel.py for the shared conventions.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from LRPtools import lrp_wrapper
+from LRPtools import utils as LRPutil
+from lrpx import ops
+from lrpx import decoder as _dec
+from models.gridTDmodel import (BAD_ENDINGS, STOP_WORDS, Encoder, ExplainGridTDAttention, GridTDModel,  # noqa: F401
+                                _lstm_forward)
+
+
+class Add(nn.Module):
+    def forward(self, x, y):
+        return x + y
+
+
+class MultiHeadedDotAttention(nn.Module):
+    """reference :54-108.  The decoder instantiates it with project_k_v_flag=False, norm_q=False, aoa=False."""
+
+    def __init__(self, num_head, hidden_dim, dropout=0.3, project_k_v_flag=True, norm_q=True, aoa=True):
+        super().__init__()
+        assert hidden_dim % num_head == 0
+        self.d_k = hidden_dim // num_head
+        self.num_head = num_head
+        self.norm = nn.BatchNorm1d(hidden_dim, track_running_stats=True) if norm_q else (lambda x: x)
+        self.q_proj = nn.Linear(hidden_dim, hidden_dim)
+        if project_k_v_flag:
+            self.k_proj = nn.Linear(hidden_dim, hidden_dim)
+            self.v_proj = nn.Linear(hidden_dim, hidden_dim)
+        else:
+            self.k_proj = lambda x: x
+            self.v_proj = lambda x: x
+        self.aoa = aoa
+        if aoa:
+            self.aoa_layer = nn.Sequential(nn.Linear(2 * hidden_dim, 2 * hidden_dim), nn.GLU())
+            self.add = Add()
+        self.dropout = nn.Dropout(p=dropout)
+
+    def forward(self, query, key, value):
+        single_query = query.dim() == 2
+        if single_query:
+            query = query.unsqueeze(1)
+        bs = query.size(0)
+        query = self.norm(query.transpose(1, 2)).transpose(1, 2)
+        q = self.q_proj(query).view(bs, -1, self.num_head, self.d_k).transpose(1, 2)
+        k = self.k_proj(key).view(bs, -1, self.num_head, self.d_k).transpose(1, 2)
+        v = self.v_proj(value).view(bs, -1, self.num_head, self.d_k).transpose(1, 2)
+        scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(self.d_k)
+        alpha = torch.softmax(scores, dim=-1)
+        p = nn.functional.dropout(alpha, 0.1) if self.training else alpha
+        x = torch.matmul(p, v).transpose(1, 2).contiguous().view(bs, -1, self.num_head * self.d_k)
+        if self.aoa:
+            x = self.add(self.aoa_layer(self.dropout(torch.cat([x, query], -1))), query)
+        if single_query:
+            x, alpha = x.squeeze(1), alpha.squeeze(2)       # alpha: (bs, heads, P)
+        return x, alpha
+
+
+class AOAModel(nn.Module):
+    """reference :111-745 (the LRP-related surface)."""
+    EPS = LRPutil.EPSILON
+
+    def __init__(self, embed_dim, hidden_dim, num_head, vocab_size, encoder_type):
+        super().__init__()
+        self.embed_dim, self.hidden_dim, self.vocab_size = embed_dim, hidden_dim, vocab_size
+        self.encoder_type, self.num_head = encoder_type, num_head
+        if hidden_dim % num_head != 0:
+            raise TypeError("the number of head should be dividable by the hidden dim")
+        self.dropout = nn.Dropout(0.3)
+        self.img_encoder = Encoder(self.encoder_type)
+        self.encoder_raw_dim = self.img_encoder.feat_dim
+        self.img_projector = nn.Conv2d(self.encoder_raw_dim, self.hidden_dim, kernel_size=1, stride=1)
+        self.embedding = nn.Embedding(vocab_size, embed_dim)
+        self.LanguageLSTM = nn.LSTMCell(hidden_dim + embed_dim, hidden_dim)
+        self.decoder_k_proj = nn.Linear(hidden_dim, hidden_dim)
+        self.decoder_v_proj = nn.Linear(hidden_dim, hidden_dim)
+        self.decoder_multihead_attention = MultiHeadedDotAttention(num_head=num_head, hidden_dim=hidden_dim,
+                                                                   project_k_v_flag=False, norm_q=False, aoa=False)
+        self.decoder_aoa_linear_gate = nn.Linear(hidden_dim, hidden_dim)
+        self.decoder_aoa_linear = nn.Linear(hidden_dim, hidden_dim)
+        self.fc = nn.Linear(hidden_dim, vocab_size)
+        self.relu = nn.ReLU()
+        self._stop_cache = {}
+
+    init_hidden_state = GridTDModel.init_hidden_state
+    remove_bad_endings = GridTDModel.remove_bad_endings
+    sample_next_word = GridTDModel.sample_next_word
+    lrp_linear_eps = GridTDModel.lrp_linear_eps
+    _stop_mask = GridTDModel._stop_mask
+
+    def _encode(self, images):
+        bs = images.size(0)
+        image_features, _ = self.img_encoder(images)
+        before = self.img_projector(image_features)
+        proj = self.relu(before).contiguous().view(bs, self.hidden_dim, -1).transpose(1, 2)     # (bs, P, H)
+        return image_features, proj, torch.mean(proj, dim=1)
+
+    def _attend(self, ht, key, value):
+        context, alpha_t = self.decoder_multihead_attention(ht, key, value)
+        gate = self.decoder_aoa_linear_gate(ht)
+        lin = self.decoder_aoa_linear(context)
+        return torch.sigmoid(gate) * lin, alpha_t
+
+    def predict_next_word(self, image_feature_proj, xt, states):
+        ht, ct = self.LanguageLSTM(xt, states)
+        context_aoa, alpha_t = self._attend(ht, self.decoder_k_proj(image_feature_proj),
+                                            self.decoder_v_proj(image_feature_proj))
+        return self.fc(self.dropout(context_aoa + ht)), alpha_t, None, (ht, ct)
+
+    def forward(self, images, encoded_captions, caption_lengths, ss_prob=None):
+        if ss_prob is not None:
+            raise NotImplementedError("scheduled sampling is outside the LRP hot path (SURVEY.md §2 #9)")
+        _, proj, glob = self._encode(images)
+        state = self.init_hidden_state(proj)
+        max_length = int(max(caption_lengths)) - 1
+        preds, last_scores = [], None
+        for t in range(max_length):
+            xt = torch.cat((self.embedding(encoded_captions[:, t]), glob), dim=-1)
+            score, _, _, state = self.predict_next_word(proj, xt, state)
+            preds.append(score)
+            last_scores = torch.log_softmax(score, -1)
+        return torch.stack(preds, 1), None, None, last_scores, max_length
+
+    def beam_search(self, imgs, word_map, beam_size=3, max_cap_length=20):
+        """reference :405-485 (batch size 1)."""
+        self.eval()
+        assert imgs.size(0) == 1
+        rev_word_map = {v: k for k, v in word_map.items()}
+        vocab_size = len(word_map)
+        dev = imgs.device
+        complete_seqs, complete_seqs_scores = [], []
+        with torch.no_grad():
+            k_prev_words = torch.full((beam_size, 1), word_map['<start>'], dtype=torch.long, device=dev)
+            top_k_scores = torch.zeros(beam_size, 1, device=dev)
+            seqs = k_prev_words.clone()
+            _, proj, glob = self._encode(imgs)
+            proj = proj.expand(beam_size, *proj.size()[1:])
+            glob = glob.expand(beam_size, glob.size(-1))
+            state = self.init_hidden_state(proj)
+            unfinished_num = beam_size
+            for step in range(max_cap_length):
+                xt = torch.cat((self.embedding(k_prev_words).squeeze(1), glob), dim=-1)
+                score, _, _, state = self.predict_next_word(proj, xt, state)
+                scores = top_k_scores.expand((unfinished_num, vocab_size)) + torch.log_softmax(score, dim=-1)
+                if step == 0:
+                    top_k_scores, top_words = scores[0].topk(beam_size, -1, True, True)
+                else:
+                    top_k_scores, top_words = scores.view(-1).topk(unfinished_num, -1, True, True)
+                beam_idx = top_words // vocab_size
+                next_word_idx = top_words % vocab_size
+                seqs = torch.cat([seqs[beam_idx], next_word_idx.unsqueeze(1)], dim=1)
+                nw = next_word_idx.tolist()
+                incomplete = [i for i, w in enumerate(nw) if w != word_map['<end>']]
+                complete = [i for i, w in enumerate(nw) if w == word_map['<end>']]
+                if complete:
+                    complete_seqs.extend(seqs[complete].tolist())
+                    complete_seqs_scores.extend(top_k_scores[complete].tolist())
+                unfinished_num -= len(complete)
+                if unfinished_num == 0:
+                    break
+                seqs = seqs[incomplete]
+                keep = beam_idx[incomplete]
+                state = tuple(s[keep] for s in state)
+                proj, glob = proj[keep], glob[keep]
+                top_k_scores = top_k_scores[incomplete].unsqueeze(1)
+                k_prev_words = next_word_idx[incomplete].unsqueeze(1)
+            if complete_seqs:
+                seq = complete_seqs[complete_seqs_scores.index(max(complete_seqs_scores))]
+            else:
+                seq = seqs[0][:20].tolist()
+            special = {word_map['<start>'], word_map['<end>'], word_map['<unk>'], word_map['<pad>']}
+            sen_idx = [w for w in seq if w not in special]
+            return self.remove_bad_endings([' '.join(rev_word_map[w] for w in sen_idx)]), sen_idx
+
+    # ------------------------------------------------------------------ lrp_tune
+    def get_lrp_weight_step(self, predictions_t, rev_word_map, ht_, context_aoa):
+        """reference :597-626 -> (weight_of_context_aoa, weight_of_ht); one batched kernel."""
+        with torch.no_grad():
+            w_ctx, w_h, _ = ops.fc_lrp_weights(predictions_t.detach(), ht_.detach(), context_aoa.detach(),
+                                               self.fc.weight.detach(), self._stop_mask(rev_word_map, predictions_t.device))
+        return w_ctx, w_h
+
+    def _tune_step(self, glob, key, value, word_embedding, state):
+        L = self.LanguageLSTM
+        xt_ = torch.cat((word_embedding, glob), dim=-1)
+        h_, c_, _, _, _ = _lstm_forward(xt_, state[0], state[1], L.weight_ih, L.weight_hh, L.bias_ih, L.bias_hh)
+        context_aoa_, _ = self._attend(h_, key, value)
+        return context_aoa_, (h_, c_)
+
+    def forwardlrp_context(self, images, encoded_captions, caption_lengths, rev_word_map):
+        """reference :628-677 (dropout on both projections, Q7)."""
+        _, proj, glob = self._encode(images)
+        key, value = self.decoder_k_proj(proj), self.decoder_v_proj(proj)
+        state = self.init_hidden_state(proj)
+        max_length = int(max(caption_lengths)) - 1
+        predictions, weighted = [], []
+        for t in range(max_length):
+            context_aoa_, state = self._tune_step(glob, key, value, self.embedding(encoded_captions[:, t]), state)
+            h_ = state[0]
+            score = self.fc(self.dropout(context_aoa_ + h_))
+            w_ctx, w_h = self.get_lrp_weight_step(score, rev_word_map, h_, context_aoa_)
+            predictions.append(score)
+            weighted.append(self.fc(self.dropout(w_ctx * context_aoa_ + h_ * w_h)))
+        return torch.stack(predictions, 1), torch.stack(weighted, 1), max_length
+
+    def sample_lrp(self, images, rev_word_map, word_map, caption_lengths, opt={}):
+        """reference :679-745; the LRP step sees the log-softmax scores as forward output (:725-727, Q7)."""
+        bs = images.size(0)
+        sample_method = opt.get('sample_method', 'greedy')
+        temperature = opt.get('temperature', 1.0)
+        max_length = int(max(caption_lengths)) - 1
+        _, proj, glob = self._encode(images)
+        key, value = self.decoder_k_proj(proj), self.decoder_v_proj(proj)
+        state = self.init_hidden_state(proj)
+        dev = images.device
+        seq = torch.zeros(bs, max_length, dtype=torch.long, device=dev)
+        seq_logprobs = torch.zeros(bs, max_length, device=dev)
+        it = torch.full((bs,), word_map['<start>'], dtype=torch.long, device=dev)
+        unfinished = None
+        for t in range(max_length):
+            context_aoa_, state = self._tune_step(glob, key, value, self.embedding(it), state)
+            h_ = state[0]
+            score = torch.log_softmax(self.fc(self.dropout(context_aoa_ + h_)), dim=-1)
+            w_ctx, w_h = self.get_lrp_weight_step(score, rev_word_map, h_, context_aoa_)
+            logp = torch.log_softmax(self.fc(context_aoa_ * w_ctx + w_h * h_), dim=-1)
+            it, sample_logprobs = self.sample_next_word(logp, sample_method, temperature)
+            finished = it == word_map['<end>']
+            unfinished = ~finished if unfinished is None else unfinished & ~finished
+            it = it * unfinished.type_as(it)
+            seq[:, t] = it
+            seq_logprobs[:, t] = sample_logprobs.view(-1)
+            if int(unfinished.sum()) == 0:
+                break
+        return seq, seq_logprobs, max_length
+
+
+class ExplainAOAAttention(ExplainGridTDAttention):
+    """reference :748-1254."""
+
+    def __init__(self, args, word_map, model=None, precision=None):
+        self.rev_word_map = {v: k for k, v in word_map.items()}
+        self.num_head = args.num_head
+        self._common_init(args, word_map, model, precision,
+                          lambda: AOAModel(args.embed_dim, args.hidden_dim, args.num_head, len(word_map), args.encoder))
+        self.model.decoder_multihead_attention.eval()
+
+    def _lrp_weights(self):
+        if self._weights is None:
+            self._weights = _dec.aoa_weights({k: v.detach() for k, v in self.model.state_dict().items()})
+        return self._weights
+
+    def explainer_forward(self, feat, tokens, quirk_double_bias_ih=True):
+        """The explainer's teacher-forced forward (reference :999-1062) batched over images; returns the saved
+        state in the layout of lrpx_aoa_args.  Q3: the LSTM adds bias_ih twice (:873)."""
+        m = self.model
+        B, P, C = feat.shape
+        H = m.hidden_dim
+        T = tokens.shape[1] - 1
+        nh, dk = m.num_head, H // m.num_head
+        with torch.no_grad():
+            Wp = m.img_projector.weight.reshape(H, C)
+            A_pre = feat @ Wp.t() + m.img_projector.bias
+            A = A_pre.clamp(min=0)
+            glob = A.mean(1)
+            key, value = m.decoder_k_proj(A), m.decoder_v_proj(A)
+            kh = key.view(B, P, nh, dk).transpose(1, 2)
+            vh = value.view(B, P, nh, dk).transpose(1, 2)
+            mha = m.decoder_multihead_attention
+            L = m.LanguageLSTM
+            lb2 = L.bias_ih if quirk_double_bias_ih else L.bias_hh
+            zeros = feat.new_zeros(B, H)
+            h, c = [zeros], [zeros]
+            keys = ["x", "g", "i", "f", "ctx", "caoa", "caoa_lin", "caoa_gate", "alpha", "pred"]
+            seq = {k: [] for k in keys}
+            for t in range(T):
+                x = torch.cat((m.embedding(tokens[:, t]), glob), dim=-1)
+                hn, cn, g, i, f = _lstm_forward(x, h[t], c[t], L.weight_ih, L.weight_hh, L.bias_ih, lb2)
+                q = mha.q_proj(hn).view(B, nh, 1, dk)
+                alpha = torch.softmax(torch.matmul(q, kh.transpose(-2, -1)) / math.sqrt(dk), dim=-1)   # (B,nh,1,P)
+                ctx = torch.matmul(alpha, vh).transpose(1, 2).reshape(B, H)
+                gate = m.decoder_aoa_linear_gate(hn)
+                lin = m.decoder_aoa_linear(ctx)
+                caoa = torch.sigmoid(gate) * lin
+                pred = m.fc(caoa + hn)
+                for k, v in zip(keys, [x, g, i, f, ctx, caoa, lin, gate, alpha.squeeze(2), pred]):
+                    seq[k].append(v)
+                h.append(hn); c.append(cn)
+            st = {k: torch.stack(v, 1).contiguous() for k, v in seq.items()}
+            st["h"], st["c"] = torch.stack(h, 1).contiguous(), torch.stack(c, 1).contiguous()
+            st.update(feat=feat.contiguous(), A_pre=A_pre.contiguous(), A=A.contiguous(), glob=glob, key=key,
+                      value=value.contiguous())
+        return st
+
+    def get_hidden_parameters(self, img_filepath):
+        self.img = self.preprocess_img(img_filepath)
+        self.beam_caption, self.beam_caption_encode = self.model.beam_search(self.img, self.word_map, beam_size=3,
+                                                                             max_cap_length=20)
+        self.beam_caption_encode = [self.word_map['<start>']] + self.beam_caption_encode
+        print(f'the predicted caption of {img_filepath} is "{self.beam_caption[0]}"')
+        self._set_state(self.img, self.beam_caption_encode)
+
+    def _set_state(self, img, tokens):
+        feat, (fh, fw), est = self.encode_images(img)
+        toks = torch.tensor([tokens], dtype=torch.long, device=self.device)
+        st = self.explainer_forward(feat, toks)
+        self._state, self._enc_state, self._feat_hw = st, est, (fh, fw)
+        self.caption_length = len(tokens) - 1
+        self.num_pixels = feat.shape[1]
+        self.predictions, self.alphas = st["pred"][0], st["alpha"][0]
+        self.xt, self.ht, self.ct = st["x"][0], st["h"][0], st["c"][0]
+        self.gt, self.it_act, self.ft_act = st["g"][0], st["i"][0], st["f"][0]
+        self.context, self.context_aoa = st["ctx"][0], st["caoa"][0]
+        self.context_aoa_linear, self.context_aoa_gate = st["caoa_lin"][0], st["caoa_gate"][0]
+        self.key, self.value = st["key"], st["value"]
+        self.image_features = feat[0].t().reshape(1, feat.shape[2], fh, fw)
+
+    def _decoder_lrp(self, ts, head_idx):
+        toks = self.beam_caption_encode
+        dev = self.device
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+        return ops.aoa_decoder_lrp(self._state, self._lrp_weights(), self.num_head, i32([0] * len(ts)), i32(list(ts)),
+                                   i32([toks[t + 1] for t in ts]), i32([head_idx] * len(ts)))
+
+    def lrp_mha(self, alpha, value, context, r_context, head_idx):
+        """reference :812-862: relevance of the values of ONE head (others get 0, Q5).
+        alpha (heads,P), value (P,H), context (H,), r_context (H,) -> (P,H).  Tensor expression kept for API
+        compatibility; explain_caption_wordt runs the fused kernel."""
+        P, H = value.shape
+        dk = H // self.num_head
+        sl = slice(head_idx * dk, (head_idx + 1) * dk)
+        z = self.EPS * context.sign() + context
+        z = z.masked_fill(z == 0, self.EPS)
+        out = torch.zeros_like(value)
+        out[:, sl] = value[:, sl] * alpha[head_idx][:, None] * (r_context.reshape(-1)[sl] / z[sl])[None, :]
+        return out
+
+    def explain_caption_wordt(self, t, head_idx):
+        """reference :1064-1156 -> (r_img_feature (1,C,h,w), r_words (t+1,))."""
+        assert t < self.caption_length
+        r_feat, r_words = self._decoder_lrp([t], head_idx)
+        fh, fw = self._feat_hw
+        return r_feat[0].t().reshape(1, -1, fh, fw), r_words[0, :t + 1]
+
+    def explain_caption(self, img_filepath, head_idx, t_list=None):
+        """reference :1165-1181."""
+        self.img_filepath = img_filepath
+        self.get_hidden_parameters(img_filepath)
+        T = self.caption_length
+        r_feat, r_words = self._decoder_lrp(list(range(T)), head_idx)
+        if self.precision == 'bf16':
+            heat = self.engine().relevance(self._enc_state, r_feat, torch.zeros(T, dtype=torch.int32, device=self.device))
+        else:
+            enc = self.model.img_encoder.encoder
+            lrp_wrapper.add_lrp(enc)
+            fh, fw = self._feat_hw
+            heat = torch.cat([lrp_wrapper.compute_lrp(enc, self.img.detach().clone(),
+                                                      target=r_feat[t].t().reshape(1, -1, fh, fw)) for t in range(T)])
+        if self.ACCUMULATE_LIKE_REFERENCE:
+            heat = torch.cumsum(heat, 0)
+        relevance_imgs = [heat[t:t + 1] for t in range(T)]
+        relevance_preceeding_words = [r_words[t, :t + 1] for t in range(T)]
+        self.save_linguistic_explanation(relevance_preceeding_words)
+        return relevance_imgs, relevance_preceeding_words
+
+    def explain_caption_words(self, img_filepath):
+        """reference :1183-1194: linguistic relevance only (head 0)."""
+        self.img_filepath = img_filepath
+        self.get_hidden_parameters(img_filepath)
+        T = self.caption_length
+        _, r_words = self._decoder_lrp(list(range(T)), 0)
+        return [r_words[t, :t + 1] for t in range(T)]

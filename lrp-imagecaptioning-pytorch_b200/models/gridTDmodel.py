@@ -376,13 +376,20 @@ class ExplainGridTDAttention(object):
     ACCUMULATE_LIKE_REFERENCE = True
 
     def __init__(self, args, word_map, model=None, precision=None):
+        self._common_init(args, word_map, model, precision,
+                          lambda: GridTDModel(args.embed_dim, args.hidden_dim, len(word_map), args.encoder))
+        m = self.model
+        self.adalstm_weight_i, self.adalstm_weight_h = m.AdaLSTM.lstm_cell.weight_ih, m.AdaLSTM.lstm_cell.weight_hh
+        self.adalstm_bias_i, self.adalstm_bias_h = m.AdaLSTM.lstm_cell.bias_ih, m.AdaLSTM.lstm_cell.bias_hh
+
+    def _common_init(self, args, word_map, model, precision, make_model):
         self.args = args
         self.word_map = word_map
         self.vocab_size = len(word_map)
         if model is not None:
             self.model = model
         else:
-            self.model = GridTDModel(args.embed_dim, args.hidden_dim, len(word_map), args.encoder)
+            self.model = make_model()
             checkpoint = torch.load(args.weight, map_location='cpu')
             self.model.load_state_dict(checkpoint['state_dict'])
             self.model.cuda()
@@ -397,8 +404,6 @@ class ExplainGridTDAttention(object):
         self.mean = [0.485, 0.456, 0.406]
         self.std = [0.229, 0.224, 0.225]
         m = self.model
-        self.adalstm_weight_i, self.adalstm_weight_h = m.AdaLSTM.lstm_cell.weight_ih, m.AdaLSTM.lstm_cell.weight_hh
-        self.adalstm_bias_i, self.adalstm_bias_h = m.AdaLSTM.lstm_cell.bias_ih, m.AdaLSTM.lstm_cell.bias_hh
         self.language_weight_i, self.language_weight_h = m.LanguageLSTM.weight_ih, m.LanguageLSTM.weight_hh
         self.language_bias_i, self.language_bias_h = m.LanguageLSTM.bias_ih, m.LanguageLSTM.bias_hh
         self.output_weight = m.fc.weight

@@ -90,7 +90,8 @@ def test_linear_epsilon(golden):
     want = O.linear_epsilon(x.double(), w.double(), None, r.double())
     got = ops.linear_epsilon(*_c(x, w, None, r))
     scale = want.abs().max()
-    assert_close(got / scale, want / scale, rtol=1e-4, atol=2e-6, what="linear eps big")
+    # 75-term sums with cancellation: fp32 accumulation error ~1e-5 of the largest element
+    assert_close(got / scale, want / scale, rtol=1e-4, atol=1e-5, what="linear eps big")
 
 
 def test_pools(golden):

@@ -142,7 +142,8 @@ def _engine_vs_oracle(cfg, seed, n, size, chunk):
     tgt = torch.randn(Q, C, fh, fw, generator=g) * feats[row_img.long()]       # relevance ~ a (.) something
     r_pix = tgt.flatten(2).transpose(1, 2).contiguous()                       # (Q, P, C)
     heat = eng.relevance(st, r_pix.to(DEV), row_img.to(DEV), chunk=chunk)
-    ref = O.sequential_lrp(layers, x[row_img.long()].double(), tgt.double())
+    layers64 = [tuple(v.double() if torch.is_tensor(v) else v for v in l) for l in layers]
+    ref = O.sequential_lrp(layers64, x[row_img.long()].double(), tgt.double())
     for q in range(Q):
         a, b = heat[q].cpu().double(), ref[q]
         l2 = float((a - b).norm() / b.norm())

@@ -70,3 +70,35 @@ def test_lrp_linear_eps_expression_matches_oracle():
     z = w @ x
     assert_close(m.lrp_linear_eps(r, x, z, w), O.lrp_linear_eps(r, x, z, w), what="lrp_linear_eps")
     assert_close(m.lrp_linear_eps(r, x, False, w), O.lrp_linear_eps(r, x, False, w), what="lrp_linear_eps recompute")
+
+
+@pytest.mark.parametrize("name", ["aoa_dec_512", "aoa_dec_bu"])
+def test_aoa_explainer_forward_matches_reference_fixture(golden, tmp_path, name):
+    from models import aoamodel as A
+    g = golden(name)
+    V, H, E, C = int(g["V"]), int(g["H"]), int(g["E"]), int(g["C"])
+    model = A.AOAModel(E, H, 8, V, "vgg16")
+    model.img_projector = torch.nn.Conv2d(C, H, 1)
+    model.encoder_raw_dim = C
+    sd = synth.aoa_decoder_state(int(g["seed"]), V, H, E, C)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("img_encoder.") for k in missing)
+    args = argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                              save_path=str(tmp_path), dataset="syn", weight="")
+    ex = A.ExplainAOAAttention(args, synth.word_map(V), model=model)
+    feat = g["feats"][0].flatten(1).t().unsqueeze(0).contiguous()
+    st = ex.explainer_forward(feat, torch.tensor([g["tokens"].tolist()]))
+    assert_close(st["pred"][0], g["predictions"], atol=5e-5, what="predictions")
+    assert_close(st["alpha"][0], g["alphas"].reshape(st["alpha"][0].shape), atol=1e-6, what="alphas")
+    assert_close(st["h"][0], g["ht"], atol=1e-5, what="ht")
+    assert_close(st["caoa"][0], g["context_aoa"], atol=1e-5, what="context_aoa")
+    # lrp_mha tensor expression vs the oracle's single-head rule
+    ost = O.aoa_explainer_forward(sd, g["feats"][0], g["tokens"].tolist(), 8)
+    t, hd = g["cases"].tolist()[0]
+    r_ctx = torch.randn(H, generator=torch.Generator().manual_seed(1))
+    got = ex.lrp_mha(ost["alpha"][t], ost["value"], ost["ctx"][t], r_ctx, hd)
+    dk = H // 8
+    sl = slice(hd * dk, (hd + 1) * dk)
+    want = torch.zeros_like(got)
+    want[:, sl] = ost["value"][:, sl] * ost["alpha"][t][hd][:, None] * (r_ctx[sl] / O.stab(ost["ctx"][t][sl]))[None, :]
+    assert_close(got, want, what="lrp_mha")
