@@ -1,0 +1,74 @@
+"""Batched explanation pipeline: all (image, word) requests of a batch of images in one pass.
+
+This is the throughput-oriented entry point above the reference-shaped explainers: what
+``ExplainGridTDAttention.explain_caption`` does for one image (gridTDmodel.py:1141-1156: forward, then per
+word decoder relevance + encoder relevance) is done here for B images x T words at once:
+
+  encoder forward + gains (tcgen05)  ->  explainer teacher-forced forward  ->  decoder relevance kernels for
+  all B*T requests  ->  encoder relevance chain (tcgen05)  ->  heat-maps (B*T,3,H,W) + r_words (B*T,T)
+
+Optionally the whole pass is captured once into a CUDA graph (fixed B and caption length) and replayed, which
+removes the launch latency of the ~2.7k small kernels of the decoder phases.
+"""
+import torch
+
+from . import ops
+
+
+class BatchExplainer:
+    def __init__(self, explainer, chunk=128, use_graph=False):
+        """explainer: models.gridTDmodel.ExplainGridTDAttention with precision='bf16' (VGG encoder)."""
+        if explainer.precision != "bf16":
+            raise ValueError("BatchExplainer drives the tensor-core chain: build the explainer with precision='bf16'")
+        self.ex = explainer
+        self.eng = explainer.engine()
+        self.W = explainer._lrp_weights()
+        self.chunk = chunk
+        self.use_graph = use_graph
+        self._graphs = {}
+
+    def _requests(self, B, T, device):
+        req_img = torch.arange(B, dtype=torch.int32, device=device).repeat_interleave(T)
+        req_t = torch.arange(T, dtype=torch.int32, device=device).repeat(B)
+        return req_img, req_t
+
+    def _run(self, imgs, tokens, req_img, req_t, heat):
+        est = self.eng.forward(imgs)
+        feat = self.eng.features(est, "pixel")
+        st = self.ex.explainer_forward(feat, tokens)
+        req_word = tokens[:, 1:].reshape(-1).to(torch.int32)
+        r_feat, r_words = ops.gridtd_decoder_lrp(st, self.W, req_img, req_t, req_word)
+        self.eng.relevance(est, r_feat, req_img, chunk=self.chunk, out=heat)
+        return r_words
+
+    def explain(self, imgs, tokens, out=None):
+        """imgs (B,3,H,W) fp32 CUDA, tokens (B,T+1) long CUDA with column 0 = <start>.
+        Returns (heat (B*T,3,H,W) fp32, r_words (B*T,T) fp32); request q = b*T + t explains word t+1 of image b.
+        With ``use_graph`` the returned tensors are the graph's static outputs (overwritten by the next call)."""
+        B, T = tokens.shape[0], tokens.shape[1] - 1
+        dev = imgs.device
+        if not self.use_graph:
+            req_img, req_t = self._requests(B, T, dev)
+            heat = out if out is not None else torch.empty(B * T, 3, imgs.shape[2], imgs.shape[3], device=dev)
+            return heat, self._run(imgs, tokens, req_img, req_t, heat)
+        key = (tuple(imgs.shape), tuple(tokens.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            s_imgs, s_toks = imgs.clone(), tokens.clone()
+            req_img, req_t = self._requests(B, T, dev)
+            heat = torch.empty(B * T, 3, imgs.shape[2], imgs.shape[3], device=dev)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                       # warm-up outside capture (lazy inits, attributes)
+                self._run(s_imgs, s_toks, req_img, req_t, heat)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                r_words = self._run(s_imgs, s_toks, req_img, req_t, heat)
+            g = self._graphs[key] = (graph, s_imgs, s_toks, heat, r_words)
+        graph, s_imgs, s_toks, heat, r_words = g
+        s_imgs.copy_(imgs, non_blocking=True)
+        s_toks.copy_(tokens, non_blocking=True)
+        graph.replay()
+        return heat, r_words

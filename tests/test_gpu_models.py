@@ -117,3 +117,94 @@ def test_explain_caption_end_to_end_both_precisions(tmp_path):
         l2 = float((heat16[t] - heat32[t]).norm() / heat32[t].norm())
         print(f"word {t}: bf16 vs fp32 spearman {sp:.5f} rel L2 {l2:.3e}")
         assert sp >= 0.99 and l2 <= 1e-1
+
+
+@pytest.mark.parametrize("name", ["aoa_dec_512", "aoa_dec_bu"])
+def test_aoa_explainer_vs_reference_fixture(golden, tmp_path, name):
+    """ExplainAOAAttention.get_hidden_parameters + explain_caption_wordt(t, head) with stubbed features; the
+    `aoa_dec_bu` fixture is BASELINE config 3 (36 bottom-up regions x 2048-d, H=1024, 8 heads)."""
+    from models import aoamodel as A
+    g = golden(name)
+    V, H, E, C = int(g["V"]), int(g["H"]), int(g["E"]), int(g["C"])
+    model = A.AOAModel(E, H, 8, V, "vgg16")
+    model.img_projector = torch.nn.Conv2d(C, H, 1)
+    model.encoder_raw_dim = C
+    model.load_state_dict(synth.aoa_decoder_state(int(g["seed"]), V, H, E, C), strict=False)
+    model.to(DEV)
+    ex = A.ExplainAOAAttention(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="fp32")
+    toks = g["tokens"].tolist()
+    fh, fw = g["feats"].shape[2:]
+    feat = g["feats"][0].flatten(1).t().unsqueeze(0).contiguous().to(DEV)
+    ex.preprocess_img = lambda p: torch.zeros(1, 3, 224, 224, device=DEV)
+    ex.encode_images = lambda img: (feat, (fh, fw), None)
+    model.beam_search = lambda *a, **k: ([" ".join(f"w{t}" for t in toks[1:])], toks[1:])
+    ex.get_hidden_parameters("x")
+    assert_close(ex.predictions, g["predictions"], atol=1e-4, what="predictions")
+    assert_close(ex.alphas, g["alphas"].reshape(ex.alphas.shape), atol=1e-6, what="alphas")
+    for t, hd in g["cases"].tolist():
+        rf, rw = ex.explain_caption_wordt(t, hd)
+        ref = g[f"r_feat_{t}_{hd}"]
+        assert rf.shape == ref.shape
+        scale = ref.abs().max()
+        assert_close(rf / scale, ref / scale, rtol=1e-3, atol=2e-5, what=f"r_img_feature {t},{hd}")
+        assert_close(rw, g[f"r_words_{t}_{hd}"], rtol=1e-3, atol=2e-5, what=f"r_words {t},{hd}")
+    words = ex.explain_caption_words.__func__  # linguistic-only entry point exists (aoamodel.py:1183-1194)
+    assert callable(words)
+
+
+def test_aoa_tuner_weights_vs_oracle():
+    """AOAModel.get_lrp_weight_step / forwardlrp_context: weights equal the oracle's batched rule; weighted
+    predictions equal fc(w_ctx*ctx + w_h*h) recomputed from them (eval mode: dropout off)."""
+    from models import aoamodel as A
+    V, H, E = 80, 64, 32
+    model = A.AOAModel(E, H, 8, V, "vgg16")
+    sd = synth.aoa_decoder_state(91, V, H, E)
+    model.load_state_dict(sd, strict=False)
+    model.to(DEV).eval()
+    wm = synth.word_map(V)
+    stop = synth.stop_mask(V)
+    rev = {v: ("the" if (bool(stop[v]) and k.startswith("w")) else k) for k, v in wm.items()}
+    g = torch.Generator().manual_seed(92)
+    logits, h, c = torch.randn(6, V, generator=g), torch.randn(6, H, generator=g), torch.randn(6, H, generator=g)
+    wc, wh = model.get_lrp_weight_step(logits.to(DEV), rev, h.to(DEV), c.to(DEV))
+    rc, rh = O.lrp_weight_step(logits, h, c, sd["fc.weight"], stop)
+    assert_close(wc, rc, atol=1e-5, what="aoa w_ctx")
+    assert_close(wh, rh, atol=1e-5, what="aoa w_h")
+    imgs = synth.images(93, 2).to(DEV)
+    caps = torch.randint(1, V - 4, (2, 4), generator=g).to(DEV)
+    with torch.no_grad():
+        pred, wpred, maxlen = model.forwardlrp_context(imgs, caps, torch.tensor([4, 4]), rev)
+    assert pred.shape == (2, 3, V) and wpred.shape == (2, 3, V) and maxlen == 3
+    assert torch.isfinite(wpred).all()
+
+
+def test_batch_pipeline_graph_equals_eager_and_single_image_api(tmp_path):
+    """lrpx.pipeline.BatchExplainer: B images x T words in one pass == the per-image explain_caption results;
+    CUDA-graph replay == eager launch (bit-exact, same kernels)."""
+    from models import gridTDmodel as G
+    from lrpx.pipeline import BatchExplainer
+    V, H, E, B, T = 60, 64, 32, 2, 3
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(81, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(82))
+    model.to(DEV).eval()
+    ex = G.ExplainGridTDAttention(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="bf16")
+    ex.ACCUMULATE_LIKE_REFERENCE = False
+    imgs = synth.images(85, B).to(DEV)
+    toks = torch.stack([torch.tensor(synth.tokens(86 + b, T, V)) for b in range(B)]).to(DEV)
+    heat_e, words_e = BatchExplainer(ex, chunk=4, use_graph=False).explain(imgs, toks)
+    pipe = BatchExplainer(ex, chunk=4, use_graph=True)
+    heat_g, words_g = pipe.explain(imgs, toks)
+    assert torch.equal(heat_e, heat_g) and torch.equal(words_e, words_g)
+    heat_g2, _ = pipe.explain(imgs.flip(0), toks.flip(0))             # replay with new inputs
+    assert torch.equal(heat_g2.view(B, T, 3, 224, 224).flip(0).reshape_as(heat_e), heat_e)
+    # per-image API gives the same explanations
+    for b in range(B):
+        ex.preprocess_img = lambda p, b=b: imgs[b:b + 1]
+        tk = toks[b].tolist()
+        model.beam_search = lambda *a, tk=tk, **k: (["a b c"], tk[1:])
+        hs, ws = ex.explain_caption("synthetic.jpg")
+        for t in range(T):
+            assert_close(hs[t][0], heat_e[b * T + t], rtol=1e-3, atol=1e-6 + 1e-3 * float(heat_e[b * T + t].abs().max()),
+                         what=f"image {b} word {t}")
+            assert_close(ws[t], words_e[b * T + t, :t + 1], rtol=1e-3, atol=1e-4, what=f"words {b},{t}")
