@@ -22,6 +22,7 @@
 #include "lrpx_common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace lrpx {
 
@@ -30,7 +31,7 @@ constexpr int TC_BK = 64;             // channels per K step (128 bytes of bf16)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 192;
 constexpr int TC_EPI_WARPS = 4;
-constexpr int TC_SMEM_BYTES = 200 * 1024;
+constexpr int TC_SMEM_BYTES = 220 * 1024;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KiB
 
 struct TcParams {
@@ -46,6 +47,15 @@ struct TcParams {
   int kc_per_tap;    // cin / 64
   int num_m_tiles, num_n_tiles;
   int stages;
+  // ---- slab mode (3x3 only): the A rows of all 9 taps of a tile are fetched once per channel block
+  int slab_mode;     // 0 = off (one A tile per tap), 1 = one contiguous slab, 3 = one slab per filter row
+  int mh;            // M halves per CTA tile (1 -> 128 rows, 2 -> 256 rows sharing every B tile)
+  int slab_rows;     // rows per slab
+  int box0_rows, box1_rows;   // TMA boxes that make up a slab (box1_rows == 0: single box)
+  int slab_pitch;    // bytes between the slabs of a stage (slab_mode 3), multiple of 1024
+  int a_stage_bytes; // bytes of one A stage, multiple of 1024
+  int a_stages, b_stages;
+  int b_resident;    // all B tiles of the layer stay in shared memory for the lifetime of the CTA
   int out_c;         // channel pitch of out / gain (elements per pixel row)
   int gain_mode;     // FWD_GAIN: 0 -> act/safe(z+), 1 -> 1/safe(z+)
   const float* bias;
@@ -118,6 +128,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
   return d;
+}
+// same, for a start address that is only 128-byte aligned (a row-shifted view into a slab): the swizzle phase of
+// the first row goes into the "matrix base offset" field, (addr >> 7) & 7
+__device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t saddr) {
+  return make_smem_desc(saddr) | ((uint64_t)((saddr >> 7) & 7) << 49);
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
@@ -306,6 +321,46 @@ __device__ __forceinline__ void epi_input(const TcParams& p, const RowInfo& r, c
   }
 }
 
+// One accumulator row per thread: TMEM -> registers -> epilogue math -> global memory.
+template <int EPI>
+__device__ __forceinline__ void run_epilogue(const TcParams& p, int row, uint32_t taddr, int n_tile) {
+  const RowInfo r = row_info(p, row);
+  const int n0 = n_tile * p.bn;
+  if (EPI == LRPX_TC_EPI_INPUT) {
+    uint32_t v[16];
+    TMEM_LD_X16(taddr, v);
+    tmem_ld_wait();
+    epi_input(p, r, v);
+  } else if (EPI == LRPX_TC_EPI_FWD_GAIN) {
+    for (int c = 0; c < p.half; c += 32) {
+      uint32_t vw[32], vp[32];
+      TMEM_LD_X32(taddr + c, vw);
+      TMEM_LD_X32(taddr + p.half + c, vp);
+      tmem_ld_wait();
+      epi_fwd_gain(p, r, n_tile * p.half + c, vw, vp);
+    }
+  } else {
+    for (int c = 0; c < p.bn; c += 32) {
+      uint32_t v[32];
+      TMEM_LD_X32(taddr + c, v);
+      tmem_ld_wait();
+      if (EPI == LRPX_TC_EPI_MUL) {
+        epi_mul(p, r, n0 + c, v);
+      } else if (EPI == LRPX_TC_EPI_MUL_UNPOOL) {
+        epi_mul_unpool(p, r, n0 + c, v);
+      } else {  // STORE_F32
+        if (r.in_range) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                 __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -409,43 +464,191 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
-      const int m0 = m_tile * TC_BM, n0 = n_tile * p.bn;
       mbar_wait(smem_u32(&tmem_full_bar[buf]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
-      const RowInfo r = row_info(p, m0 + quarter * 32 + lane);
-      if (EPI == LRPX_TC_EPI_INPUT) {
-        uint32_t v[16];
-        TMEM_LD_X16(taddr, v);
-        tmem_ld_wait();
-        epi_input(p, r, v);
-      } else if (EPI == LRPX_TC_EPI_FWD_GAIN) {
-        for (int c = 0; c < p.half; c += 32) {
-          uint32_t vw[32], vp[32];
-          TMEM_LD_X32(taddr + c, vw);
-          TMEM_LD_X32(taddr + p.half + c, vp);
-          tmem_ld_wait();
-          epi_fwd_gain(p, r, n_tile * p.half + c, vw, vp);
-        }
-      } else {
-        for (int c = 0; c < p.bn; c += 32) {
-          uint32_t v[32];
-          TMEM_LD_X32(taddr + c, v);
-          tmem_ld_wait();
-          if (EPI == LRPX_TC_EPI_MUL) {
-            epi_mul(p, r, n0 + c, v);
-          } else if (EPI == LRPX_TC_EPI_MUL_UNPOOL) {
-            epi_mul_unpool(p, r, n0 + c, v);
-          } else {  // STORE_F32
-            if (r.in_range) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c);
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                     __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+      run_epilogue<EPI>(p, m_tile * TC_BM + quarter * 32 + lane, taddr, n_tile);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ slab-mode kernel
+// 3x3 convolutions only.  For a tile of mh*128 consecutive PF rows and one block of 64 channels, the A rows of
+// ALL nine taps come from one contiguous run of rows (slab_mode 1: mh*128 + 2*(w+1) + 2 rows) or from three runs,
+// one per filter row (slab_mode 3: 3 x (mh*128 + 2) rows, used when the image is wide).  The slab is fetched
+// once; each tap's A operand is a row-shifted view of it: shared-memory descriptor start = slab + off*128 B with
+// the swizzle phase of that row in the descriptor's base-offset field.  Compared with one TMA tile per tap this
+// cuts the L2 -> SMEM traffic of A by 9x/(1.2 ... 3x), which is what bounds the 64/128-channel 224^2/112^2 layers.
+// B tiles stream through their own ring (kc-major, tap-minor) or, when the whole layer's B fits (<= 80 KB),
+// stay resident for the lifetime of the persistent CTA.  With mh == 2 every B tile feeds two 128-row MMAs.
+constexpr int TC_A_MAX_STAGES = 4;
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[TC_A_MAX_STAGES];
+  __shared__ __align__(8) uint64_t a_empty[TC_A_MAX_STAGES];
+  __shared__ __align__(8) uint64_t b_full[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t b_empty[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bres_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + (uint32_t)p.a_stages * p.a_stage_bytes;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tile_rows = p.mh * TC_BM;
+  const int n_slabs = p.slab_mode == 1 ? 1 : 3;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(smem_u32(&a_full[s]), 1);
+      mbar_init(smem_u32(&a_empty[s]), 1);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(smem_u32(&b_full[s]), 1);
+      mbar_init(smem_u32(&b_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bres_bar), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[b]), TC_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (one thread)
+    if (lane == 0) {
+      if (p.b_resident) {
+        const uint32_t bb = smem_u32(&bres_bar);
+        mbar_expect_tx(bb, (uint32_t)(p.taps * p.kc_per_tap) * b_bytes);
+        for (int tap = 0; tap < p.taps; ++tap)
+          for (int kc = 0; kc < p.kc_per_tap; ++kc)
+            tma_load_2d(b_base + (uint32_t)(tap * p.kc_per_tap + kc) * b_bytes, &tmB, bb, tap * p.cin + kc * TC_BK, 0);
+      }
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      const uint32_t a_tx = (uint32_t)n_slabs * p.slab_rows * (TC_BK * 2);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+        const int m0 = m_tile * tile_rows, n0 = n_tile * p.bn;
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(smem_u32(&a_empty[as]), aph ^ 1);
+          const uint32_t fb = smem_u32(&a_full[as]);
+          const uint32_t sa = a_base + (uint32_t)as * p.a_stage_bytes;
+          mbar_expect_tx(fb, a_tx);
+          for (int j = 0; j < n_slabs; ++j) {
+            const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
+            const uint32_t dst = sa + (uint32_t)j * p.slab_pitch;
+            tma_load_2d(dst, &tmA0, fb, kc * TC_BK, row0);
+            if (p.box1_rows) tma_load_2d(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kc * TC_BK, row0 + p.box0_rows);
+          }
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+          if (!p.b_resident) {
+            for (int tap = 0; tap < p.taps; ++tap) {
+              mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1);
+              const uint32_t bb = smem_u32(&b_full[bs]);
+              mbar_expect_tx(bb, b_bytes);
+              tma_load_2d(b_base + (uint32_t)bs * b_bytes, &tmB, bb, tap * p.cin + kc * TC_BK, n0);
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
             }
           }
         }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.bn);
+      int as = 0, bs = 0, it = 0;
+      uint32_t aph = 0, bph = 0;
+      if (p.b_resident) {
+        mbar_wait(smem_u32(&bres_bar), 0);
+        tc_fence_after();
+      }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&tmem_empty_bar[buf]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256;
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(smem_u32(&a_full[as]), aph);
+          tc_fence_after();
+          const uint32_t sa = a_base + (uint32_t)as * p.a_stage_bytes;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            uint32_t b_addr;
+            if (p.b_resident) {
+              b_addr = b_base + (uint32_t)(tap * p.kc_per_tap + kc) * b_bytes;
+            } else {
+              mbar_wait(smem_u32(&b_full[bs]), bph);
+              tc_fence_after();
+              b_addr = b_base + (uint32_t)bs * b_bytes;
+            }
+            const int dyi = tap / 3, dxi = tap - 3 * dyi;
+            const uint32_t a_addr = (p.slab_mode == 1) ? sa + (uint32_t)(dyi * p.wp1 + dxi) * (TC_BK * 2)
+                                                       : sa + (uint32_t)dyi * p.slab_pitch + (uint32_t)dxi * (TC_BK * 2);
+            const uint64_t bdesc = make_smem_desc(b_addr);
+            for (int h = 0; h < p.mh; ++h) {
+              const uint32_t ah = a_addr + (uint32_t)h * (TC_BM * TC_BK * 2);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                tc_mma_f16(d_tmem + h * p.bn, make_smem_desc_shifted(ah + 32 * k), bdesc + 2 * k, idesc,
+                           (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
+            if (!p.b_resident) {
+              tc_commit(smem_u32(&b_empty[bs]));
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+            }
+          }
+          tc_commit(smem_u32(&a_empty[as]));
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+        }
+        tc_commit(smem_u32(&tmem_full_bar[buf]));
+      }
+    }
+  } else {
+    // ================================ epilogue warps
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+      mbar_wait(smem_u32(&tmem_full_bar[buf]), acc_phase);
+      tc_fence_after();
+      for (int h = 0; h < p.mh; ++h) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + h * p.bn;
+        run_epilogue<EPI>(p, m_tile * tile_rows + h * TC_BM + quarter * 32 + lane, taddr, n_tile);
       }
       tc_fence_before();
       __syncwarp();
@@ -521,6 +724,60 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
   return LRPX_OK;
 }
 
+template <int EPI>
+static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const TcParams& p,
+                          int grid, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tc_conv_slab_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
+    return LRPX_E_CUDA;
+  }
+  tc_conv_slab_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma0, ma1, mb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("tc_conv_slab_kernel launch failed: %s", cudaGetErrorString(e));
+    return LRPX_E_CUDA;
+  }
+  return LRPX_OK;
+}
+
+// Picks the slab-mode configuration (see tc_conv_slab_kernel).  Returns false when nothing fits.
+static bool plan_slab(TcParams& p) {
+  const int budget = TC_SMEM_BYTES - 1024;
+  const int b_bytes = p.bn * TC_BK * 2;
+  const long long b_total = (long long)p.taps * p.kc_per_tap * b_bytes;
+  const bool resident = p.num_n_tiles == 1 && b_total <= 80 * 1024;
+  for (int mh = (p.bn <= 128 && !resident) ? 2 : 1; mh >= 1; --mh) {
+    const int rows1 = mh * TC_BM + 2 + 2 * p.wp1, rows3 = mh * TC_BM + 2;
+    const int mode = (rows1 <= 3 * rows3 && rows1 <= 512) ? 1 : 3;
+    const int slab_rows = mode == 1 ? rows1 : rows3;
+    const int slab_bytes = ((slab_rows * TC_BK * 2) + 1023) & ~1023;
+    const int a_stage = mode == 1 ? slab_bytes : 3 * slab_bytes;
+    for (int a_stages = 3; a_stages >= 2; --a_stages) {
+      const int left = budget - a_stages * a_stage;
+      int b_stages = 0;
+      if (resident) {
+        if (left < b_total) continue;
+      } else {
+        b_stages = left / b_bytes;
+        if (b_stages > TC_MAX_STAGES) b_stages = TC_MAX_STAGES;
+        if (b_stages < 3) continue;
+      }
+      p.slab_mode = mode; p.mh = mh; p.slab_rows = slab_rows;
+      p.box0_rows = slab_rows < 256 ? slab_rows : 256;
+      p.box1_rows = slab_rows - p.box0_rows;
+      p.slab_pitch = slab_bytes; p.a_stage_bytes = a_stage;
+      p.a_stages = a_stages; p.b_stages = b_stages; p.b_resident = resident ? 1 : 0;
+      return true;
+    }
+  }
+  return false;
+}
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -581,6 +838,32 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     p.out_c = a->ncol;
   }
   p.num_n_tiles = a->ncol / p.bn;
+  cudaStream_t st = as_stream(stream);
+  {
+    const char* env = getenv("LRPX_TC_SLAB");
+    const bool want_slab = a->ksize == 3 && !(env && env[0] == '0');
+    if (want_slab && plan_slab(p)) {
+      const int tile_rows = p.mh * TC_BM;
+      p.num_m_tiles = (p.m_total + tile_rows - 1) / tile_rows;
+      CUtensorMap ma0, ma1, mb;
+      int rc = make_map_2d(&ma0, a->a, (uint64_t)p.m_total, (uint64_t)a->cin, (uint32_t)p.box0_rows);
+      if (rc) return rc;
+      rc = make_map_2d(&ma1, a->a, (uint64_t)p.m_total, (uint64_t)a->cin, (uint32_t)(p.box1_rows ? p.box1_rows : 8));
+      if (rc) return rc;
+      rc = make_map_2d(&mb, a->wt, (uint64_t)a->ncol, (uint64_t)p.taps * a->cin, (uint32_t)p.bn);
+      if (rc) return rc;
+      int tiles = p.num_m_tiles * p.num_n_tiles;
+      int grid = tiles < sm_count() ? tiles : sm_count();
+      switch (epi) {
+        case LRPX_TC_EPI_FWD_GAIN: return launch_tc_slab<LRPX_TC_EPI_FWD_GAIN>(ma0, ma1, mb, p, grid, st);
+        case LRPX_TC_EPI_MUL: return launch_tc_slab<LRPX_TC_EPI_MUL>(ma0, ma1, mb, p, grid, st);
+        case LRPX_TC_EPI_MUL_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MUL_UNPOOL>(ma0, ma1, mb, p, grid, st);
+        case LRPX_TC_EPI_INPUT: return launch_tc_slab<LRPX_TC_EPI_INPUT>(ma0, ma1, mb, p, grid, st);
+        default: return launch_tc_slab<LRPX_TC_EPI_STORE_F32>(ma0, ma1, mb, p, grid, st);
+      }
+    }
+  }
+  p.slab_mode = 0; p.mh = 1;
   p.num_m_tiles = (p.m_total + TC_BM - 1) / TC_BM;
   const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;
   p.stages = (TC_SMEM_BYTES - 1024) / stage_bytes;
@@ -595,7 +878,6 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
 
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  cudaStream_t st = as_stream(stream);
   switch (epi) {
     case LRPX_TC_EPI_FWD_GAIN: return launch_tc<LRPX_TC_EPI_FWD_GAIN>(ma, mb, p, grid, st);
     case LRPX_TC_EPI_MUL: return launch_tc<LRPX_TC_EPI_MUL>(ma, mb, p, grid, st);

@@ -66,8 +66,9 @@ class BatchExplainer:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 r_words = self._run(s_imgs, s_toks, req_img, req_t, heat)
-            g = self._graphs[key] = (graph, s_imgs, s_toks, heat, r_words)
-        graph, s_imgs, s_toks, heat, r_words = g
+            # everything the captured kernels point at must outlive the graph (incl. the request index tensors)
+            g = self._graphs[key] = (graph, s_imgs, s_toks, heat, r_words, req_img, req_t)
+        graph, s_imgs, s_toks, heat, r_words = g[:5]
         s_imgs.copy_(imgs, non_blocking=True)
         s_toks.copy_(tokens, non_blocking=True)
         graph.replay()

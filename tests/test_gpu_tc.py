@@ -39,10 +39,16 @@ def _no_tf32():
     torch.backends.cuda.matmul.allow_tf32 = False
 
 
+@pytest.mark.parametrize("slab", ["1", "0"])
 @pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 8, 64, 64), (3, 10, 6, 128, 256), (2, 14, 14, 64, 512),
-                                            (5, 28, 28, 256, 128), (1, 4, 4, 512, 32)])
-def test_gemm_forward_layout(n, h, w, cin, cout):
+                                            (5, 28, 28, 256, 128), (1, 4, 4, 512, 32), (2, 56, 56, 128, 128),
+                                            (1, 112, 112, 64, 64), (1, 224, 224, 64, 64), (1, 224, 224, 64, 128)])
+def test_gemm_forward_layout(n, h, w, cin, cout, slab, monkeypatch):
+    """slab=1: row-shifted descriptor views into one A slab per channel block (single slab, two-box slab,
+    three-slab, B-resident and 256-row tile configurations are all hit by these shapes); slab=0: one TMA tile
+    per filter tap."""
     from lrpx import tc
+    monkeypatch.setenv("LRPX_TC_SLAB", slab)
     g = torch.Generator().manual_seed(n * 1000 + h + cin + cout)
     x = _bf(torch.randn(n, cin, h, w, generator=g)).to(DEV)
     wt = _bf(torch.randn(cout, cin, 3, 3, generator=g) * 0.1).to(DEV)
@@ -56,10 +62,12 @@ def test_gemm_forward_layout(n, h, w, cin, cout):
     assert_close(got, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()), what="tc conv forward")
 
 
+@pytest.mark.parametrize("slab", ["1", "0"])
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 6, 10, 64, 128), (1, 14, 14, 512, 512)])
-def test_gemm_relevance_layout(n, h, w, cin, cout):
+def test_gemm_relevance_layout(n, h, w, cin, cout, slab, monkeypatch):
     """mode-2 weights: acc = W+^T * s (the transposed convolution of utils.lrp_backward, utils.py:29)."""
     from lrpx import tc
+    monkeypatch.setenv("LRPX_TC_SLAB", slab)
     g = torch.Generator().manual_seed(h * 31 + cout)
     s = _bf(torch.randn(n, cout, h, w, generator=g)).to(DEV)
     wt = _bf(torch.randn(cout, cin, 3, 3, generator=g) * 0.1).to(DEV)
