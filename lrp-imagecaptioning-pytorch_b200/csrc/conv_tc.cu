@@ -56,6 +56,8 @@ struct TcParams {
   int a_stage_bytes; // bytes of one A stage, multiple of 1024
   int a_stages, b_stages;
   int b_resident;    // all B tiles of the layer stay in shared memory for the lifetime of the CTA
+  int desc_mode;     // experiment switch (env LRPX_TC_BASEOFF): 1 = base-offset field from the address, 0 = leave it 0
+  int debug_flags;   // env LRPX_TC_DEBUG: bit 0 = epilogue skips its global loads/stores (timing experiments only)
   int out_c;         // channel pitch of out / gain (elements per pixel row)
   int gain_mode;     // FWD_GAIN: 0 -> act/safe(z+), 1 -> 1/safe(z+)
   const float* bias;
@@ -324,7 +326,8 @@ __device__ __forceinline__ void epi_input(const TcParams& p, const RowInfo& r, c
 // One accumulator row per thread: TMEM -> registers -> epilogue math -> global memory.
 template <int EPI>
 __device__ __forceinline__ void run_epilogue(const TcParams& p, int row, uint32_t taddr, int n_tile) {
-  const RowInfo r = row_info(p, row);
+  RowInfo r = row_info(p, row);
+  if (p.debug_flags & 1) { r.in_range = false; r.valid = false; }
   const int n0 = n_tile * p.bn;
   if (EPI == LRPX_TC_EPI_INPUT) {
     uint32_t v[16];
@@ -622,7 +625,8 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               const uint32_t ah = a_addr + (uint32_t)h * (TC_BM * TC_BK * 2);
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k)
-                tc_mma_f16(d_tmem + h * p.bn, make_smem_desc_shifted(ah + 32 * k), bdesc + 2 * k, idesc,
+                tc_mma_f16(d_tmem + h * p.bn, p.desc_mode ? make_smem_desc_shifted(ah + 32 * k) : make_smem_desc(ah + 32 * k),
+                           bdesc + 2 * k, idesc,
                            (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
             }
             if (!p.b_resident) {
@@ -840,8 +844,15 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
   p.num_n_tiles = a->ncol / p.bn;
   cudaStream_t st = as_stream(stream);
   {
+    const char* e1 = getenv("LRPX_TC_BASEOFF");
+    p.desc_mode = (e1 && e1[0] == '0') ? 0 : 1;
+    const char* e2 = getenv("LRPX_TC_DEBUG");
+    p.debug_flags = e2 ? atoi(e2) : 0;
+  }
+  {
+    // slab mode is opt-in (LRPX_TC_SLAB=1) until its row-shifted descriptor views are validated on hardware
     const char* env = getenv("LRPX_TC_SLAB");
-    const bool want_slab = a->ksize == 3 && !(env && env[0] == '0');
+    const bool want_slab = a->ksize == 3 && env && env[0] == '1';
     if (want_slab && plan_slab(p)) {
       const int tile_rows = p.mh * TC_BM;
       p.num_m_tiles = (p.m_total + tile_rows - 1) / tile_rows;
