@@ -56,7 +56,9 @@ struct TcParams {
   int a_stage_bytes; // bytes of one A stage, multiple of 1024
   int a_stages, b_stages;
   int b_resident;    // all B tiles of the layer stay in shared memory for the lifetime of the CTA
-  int desc_mode;     // experiment switch (env LRPX_TC_BASEOFF): 1 = base-offset field from the address, 0 = leave it 0
+  int desc_mode;     // experiment switch (env LRPX_TC_BASEOFF=1): also fill the descriptor's base-offset field.
+                     // Measured on B200: the swizzle follows the ABSOLUTE smem address bits, so a row-shifted view
+                     // needs only the shifted start address (base offset 0); setting the field gives wrong products.
   int debug_flags;   // env LRPX_TC_DEBUG: bit 0 = epilogue skips its global loads/stores (timing experiments only)
   int out_c;         // channel pitch of out / gain (elements per pixel row)
   int gain_mode;     // FWD_GAIN: 0 -> act/safe(z+), 1 -> 1/safe(z+)
@@ -489,8 +491,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // 3x3 convolutions only.  For a tile of mh*128 consecutive PF rows and one block of 64 channels, the A rows of
 // ALL nine taps come from one contiguous run of rows (slab_mode 1: mh*128 + 2*(w+1) + 2 rows) or from three runs,
 // one per filter row (slab_mode 3: 3 x (mh*128 + 2) rows, used when the image is wide).  The slab is fetched
-// once; each tap's A operand is a row-shifted view of it: shared-memory descriptor start = slab + off*128 B with
-// the swizzle phase of that row in the descriptor's base-offset field.  Compared with one TMA tile per tap this
+// once; each tap's A operand is a row-shifted view of it: shared-memory descriptor start = slab + off*128 B (the
+// 128B swizzle is a function of the absolute shared-memory address, so TMA's layout and the MMA's view agree
+// without touching the descriptor's base-offset field — verified against a reference convolution on B200).  Compared with one TMA tile per tap this
 // cuts the L2 -> SMEM traffic of A by 9x/(1.2 ... 3x), which is what bounds the 64/128-channel 224^2/112^2 layers.
 // B tiles stream through their own ring (kc-major, tap-minor) or, when the whole layer's B fits (<= 80 KB),
 // stay resident for the lifetime of the persistent CTA.  With mh == 2 every B tile feeds two 128-row MMAs.
@@ -845,14 +848,13 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
   cudaStream_t st = as_stream(stream);
   {
     const char* e1 = getenv("LRPX_TC_BASEOFF");
-    p.desc_mode = (e1 && e1[0] == '0') ? 0 : 1;
+    p.desc_mode = (e1 && e1[0] == '1') ? 1 : 0;
     const char* e2 = getenv("LRPX_TC_DEBUG");
     p.debug_flags = e2 ? atoi(e2) : 0;
   }
   {
-    // slab mode is opt-in (LRPX_TC_SLAB=1) until its row-shifted descriptor views are validated on hardware
-    const char* env = getenv("LRPX_TC_SLAB");
-    const bool want_slab = a->ksize == 3 && env && env[0] == '1';
+    const char* env = getenv("LRPX_TC_SLAB");       // LRPX_TC_SLAB=0 falls back to one TMA tile per filter tap
+    const bool want_slab = a->ksize == 3 && !(env && env[0] == '0');
     if (want_slab && plan_slab(p)) {
       const int tile_rows = p.mh * TC_BM;
       p.num_m_tiles = (p.m_total + tile_rows - 1) / tile_rows;

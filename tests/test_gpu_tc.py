@@ -39,7 +39,7 @@ def _no_tf32():
     torch.backends.cuda.matmul.allow_tf32 = False
 
 
-@pytest.mark.parametrize("slab", ["0"])
+@pytest.mark.parametrize("slab", ["1", "0"])
 @pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 8, 64, 64), (3, 10, 6, 128, 256), (2, 14, 14, 64, 512),
                                             (5, 28, 28, 256, 128), (1, 4, 4, 512, 32), (2, 56, 56, 128, 128),
                                             (1, 112, 112, 64, 64), (1, 224, 224, 64, 64), (1, 224, 224, 64, 128)])
@@ -62,7 +62,7 @@ def test_gemm_forward_layout(n, h, w, cin, cout, slab, monkeypatch):
     assert_close(got, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()), what="tc conv forward")
 
 
-@pytest.mark.parametrize("slab", ["0"])
+@pytest.mark.parametrize("slab", ["1", "0"])
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 6, 10, 64, 128), (1, 14, 14, 512, 512)])
 def test_gemm_relevance_layout(n, h, w, cin, cout, slab, monkeypatch):
     """mode-2 weights: acc = W+^T * s (the transposed convolution of utils.lrp_backward, utils.py:29)."""
