@@ -29,7 +29,7 @@ namespace lrpx {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;             // channels per K step (128 bytes of bf16)
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;          // warps: 0 A/TMA producer, 1 MMA, 2-5 epilogue, 6 B producer (slab kernel)
 constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_SMEM_BYTES = 220 * 1024;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KiB
@@ -60,6 +60,7 @@ struct TcParams {
                      // Measured on B200: the swizzle follows the ABSOLUTE smem address bits, so a row-shifted view
                      // needs only the shifted start address (base offset 0); setting the field gives wrong products.
   int debug_flags;   // env LRPX_TC_DEBUG: bit 0 = epilogue skips its global loads/stores (timing experiments only)
+  int prefetch_tiles; // slab kernel: L2-prefetch the A slab and the gain rows this many of the CTA's tiles ahead
   int out_c;         // channel pitch of out / gain (elements per pixel row)
   int gain_mode;     // FWD_GAIN: 0 -> act/safe(z+), 1 -> 1/safe(z+)
   const float* bias;
@@ -108,6 +109,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -461,7 +468,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_commit(smem_u32(&tmem_full_bar[buf]));        // accumulator ready for the epilogue
       }
     }
-  } else {
+  } else if (warp >= 2 && warp < 2 + TC_EPI_WARPS) {
     // ================================ epilogue warps
     const int quarter = warp & 3;
     int it = 0;
@@ -552,21 +559,43 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ================================ TMA producer (one thread)
+    // ================================ A producer (one thread): slabs + L2 prefetch of the tiles ahead
     if (lane == 0) {
-      if (p.b_resident) {
-        const uint32_t bb = smem_u32(&bres_bar);
-        mbar_expect_tx(bb, (uint32_t)(p.taps * p.kc_per_tap) * b_bytes);
-        for (int tap = 0; tap < p.taps; ++tap)
-          for (int kc = 0; kc < p.kc_per_tap; ++kc)
-            tma_load_2d(b_base + (uint32_t)(tap * p.kc_per_tap + kc) * b_bytes, &tmB, bb, tap * p.cin + kc * TC_BK, 0);
-      }
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+      int as = 0;
+      uint32_t aph = 0;
       const uint32_t a_tx = (uint32_t)n_slabs * p.slab_rows * (TC_BK * 2);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      auto prefetch_tile = [&](int tile) {
+        if (tile >= num_tiles) return;
         const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
-        const int m0 = m_tile * tile_rows, n0 = n_tile * p.bn;
+        const int m0 = m_tile * tile_rows;
+        if (n_tile == 0) {      // the A rows are shared by the N tiles of a row block
+          for (int kc = 0; kc < p.kc_per_tap; ++kc)
+            for (int j = 0; j < n_slabs; ++j) {
+              const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
+              tma_prefetch_2d(&tmA0, kc * TC_BK, row0);
+              if (p.box1_rows) tma_prefetch_2d(&tmA1, kc * TC_BK, row0 + p.box0_rows);
+            }
+        }
+        if ((EPI == LRPX_TC_EPI_MUL || EPI == LRPX_TC_EPI_MUL_UNPOOL) && p.num_n_tiles == 1) {
+          // gain (and argmax) rows of the tile: contiguous per explanation block
+          int row = m0;
+          const int end = min(m0 + tile_rows, p.m_total);
+          while (row < end) {
+            const int e = row / p.blk, rem = row - e * p.blk;
+            const int cnt = min(end - row, p.blk - rem);
+            const int img = p.row_img ? p.row_img[e] : e;
+            const size_t off = ((size_t)img * p.blk + rem) * p.out_c;
+            bulk_prefetch_l2(p.gain + off, (uint32_t)cnt * p.out_c * 2);
+            if (EPI == LRPX_TC_EPI_MUL_UNPOOL) bulk_prefetch_l2(p.pool_idx + off, (uint32_t)cnt * p.out_c);
+            row += cnt;
+          }
+        }
+      };
+      for (int i = 1; i <= p.prefetch_tiles; ++i) prefetch_tile(blockIdx.x + i * gridDim.x);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int m0 = m_tile * tile_rows;
+        if (p.prefetch_tiles) prefetch_tile(tile + (p.prefetch_tiles + 1) * gridDim.x);
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
           mbar_wait(smem_u32(&a_empty[as]), aph ^ 1);
           const uint32_t fb = smem_u32(&a_full[as]);
@@ -579,7 +608,24 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             if (p.box1_rows) tma_load_2d(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kc * TC_BK, row0 + p.box0_rows);
           }
           if (++as == p.a_stages) { as = 0; aph ^= 1; }
-          if (!p.b_resident) {
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ================================ B producer (one thread)
+    if (lane == 0) {
+      if (p.b_resident) {
+        const uint32_t bb = smem_u32(&bres_bar);
+        mbar_expect_tx(bb, (uint32_t)(p.taps * p.kc_per_tap) * b_bytes);
+        for (int tap = 0; tap < p.taps; ++tap)
+          for (int kc = 0; kc < p.kc_per_tap; ++kc)
+            tma_load_2d(b_base + (uint32_t)(tap * p.kc_per_tap + kc) * b_bytes, &tmB, bb, tap * p.cin + kc * TC_BK, 0);
+      } else {
+        int bs = 0;
+        uint32_t bph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int n0 = (tile % p.num_n_tiles) * p.bn;
+          for (int kc = 0; kc < p.kc_per_tap; ++kc)
             for (int tap = 0; tap < p.taps; ++tap) {
               mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1);
               const uint32_t bb = smem_u32(&b_full[bs]);
@@ -587,7 +633,6 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               tma_load_2d(b_base + (uint32_t)bs * b_bytes, &tmB, bb, tap * p.cin + kc * TC_BK, n0);
               if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
             }
-          }
         }
       }
     }
@@ -643,7 +688,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         tc_commit(smem_u32(&tmem_full_bar[buf]));
       }
     }
-  } else {
+  } else if (warp >= 2 && warp < 2 + TC_EPI_WARPS) {
     // ================================ epilogue warps
     const int quarter = warp & 3;
     int it = 0;
@@ -851,6 +896,8 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     p.desc_mode = (e1 && e1[0] == '1') ? 1 : 0;
     const char* e2 = getenv("LRPX_TC_DEBUG");
     p.debug_flags = e2 ? atoi(e2) : 0;
+    const char* e3 = getenv("LRPX_TC_PREFETCH");
+    p.prefetch_tiles = e3 ? atoi(e3) : 2;
   }
   {
     const char* env = getenv("LRPX_TC_SLAB");       // LRPX_TC_SLAB=0 falls back to one TMA tile per filter tap
