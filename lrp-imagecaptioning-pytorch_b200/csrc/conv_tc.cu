@@ -600,12 +600,16 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           mbar_wait(smem_u32(&a_empty[as]), aph ^ 1);
           const uint32_t fb = smem_u32(&a_full[as]);
           const uint32_t sa = a_base + (uint32_t)as * p.a_stage_bytes;
-          mbar_expect_tx(fb, a_tx);
-          for (int j = 0; j < n_slabs; ++j) {
-            const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
-            const uint32_t dst = sa + (uint32_t)j * p.slab_pitch;
-            tma_load_2d(dst, &tmA0, fb, kc * TC_BK, row0);
-            if (p.box1_rows) tma_load_2d(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kc * TC_BK, row0 + p.box0_rows);
+          if (p.debug_flags & 4) {          // timing experiment: no A traffic at all
+            mbar_arrive(fb);
+          } else {
+            mbar_expect_tx(fb, a_tx);
+            for (int j = 0; j < n_slabs; ++j) {
+              const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
+              const uint32_t dst = sa + (uint32_t)j * p.slab_pitch;
+              tma_load_2d(dst, &tmA0, fb, kc * TC_BK, row0);
+              if (p.box1_rows) tma_load_2d(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kc * TC_BK, row0 + p.box0_rows);
+            }
           }
           if (++as == p.a_stages) { as = 0; aph ^= 1; }
         }
@@ -669,8 +673,8 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const uint32_t a_addr = (p.slab_mode == 1) ? sa + (uint32_t)(dyi * p.wp1 + dxi) * (TC_BK * 2)
                                                        : sa + (uint32_t)dyi * p.slab_pitch + (uint32_t)dxi * (TC_BK * 2);
             const uint64_t bdesc = make_smem_desc(b_addr);
-            for (int h = 0; h < p.mh; ++h) {
-              const uint32_t ah = a_addr + (uint32_t)h * (TC_BM * TC_BK * 2);
+            for (int h = 0; h < p.mh && !(p.debug_flags & 2); ++h) {
+              const uint32_t ah = ((p.debug_flags & 8) ? sa : a_addr) + (uint32_t)h * (TC_BM * TC_BK * 2);
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k)
                 tc_mma_f16(d_tmem + h * p.bn, p.desc_mode ? make_smem_desc_shifted(ah + 32 * k) : make_smem_desc(ah + 32 * k),
