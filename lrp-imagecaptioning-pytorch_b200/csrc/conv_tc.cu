@@ -56,11 +56,7 @@ struct TcParams {
   int a_stage_bytes; // bytes of one A stage, multiple of 1024
   int a_stages, b_stages;
   int b_resident;    // all B tiles of the layer stay in shared memory for the lifetime of the CTA
-  int desc_mode;     // experiment switch (env LRPX_TC_BASEOFF=1): also fill the descriptor's base-offset field.
-                     // Measured on B200: the swizzle follows the ABSOLUTE smem address bits, so a row-shifted view
-                     // needs only the shifted start address (base offset 0); setting the field gives wrong products.
   int debug_flags;   // env LRPX_TC_DEBUG: bit 0 = epilogue skips its global loads/stores (timing experiments only)
-  int prefetch_tiles; // slab kernel: L2-prefetch the A slab and the gain rows this many of the CTA's tiles ahead
   int out_c;         // channel pitch of out / gain (elements per pixel row)
   int gain_mode;     // FWD_GAIN: 0 -> act/safe(z+), 1 -> 1/safe(z+)
   const float* bias;
@@ -140,10 +136,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
   return d;
 }
-// same, for a start address that is only 128-byte aligned (a row-shifted view into a slab): the swizzle phase of
-// the first row goes into the "matrix base offset" field, (addr >> 7) & 7
-__device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t saddr) {
-  return make_smem_desc(saddr) | ((uint64_t)((saddr >> 7) & 7) << 49);
+// A row-shifted view into a slab (start address only 128-byte aligned) uses the SAME descriptor with the shifted
+// start address and base offset 0: measured on B200, the 128B swizzle is a function of the absolute shared-memory
+// address bits, so TMA's layout and the MMA's view agree; filling the "matrix base offset" field ((addr >> 7) & 7)
+// instead produces wrong products.
+// Split form for the MMA issue loops (one thread issues every MMA, so its instruction count per MMA bounds the
+// tensor pipe for small N): the high word is constant, the low word is (addr >> 4) | LBO and is advanced by adds.
+constexpr uint32_t TC_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(TC_DESC_HI));
+  return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
@@ -442,6 +446,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.bn);
+      const uint32_t stage16 = stage_bytes >> 4;
+      const uint32_t a_lo_base = desc_lo(smem_base), b_lo_base = desc_lo(smem_base + TC_A_BYTES);
+      const int stages = p.stages;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -454,16 +461,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES);
+          const uint32_t a_lo = a_lo_base + (uint32_t)stage * stage16, b_lo = b_lo_base + (uint32_t)stage * stage16;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_mma_f16(d_tmem, desc_pack(a_lo + 2 * k), desc_pack(b_lo + 2 * k), idesc, (k == 0) ? (kb != 0 ? 1u : 0u) : 1u);
           }
           tc_commit(smem_u32(&empty_bar[stage]));       // frees the smem stage once these MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         tc_commit(smem_u32(&tmem_full_bar[buf]));        // accumulator ready for the epilogue
       }
@@ -491,6 +496,72 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// MMA issue loop of the slab kernel.  Everything loop-invariant is hoisted and the 9 taps x 4 K-steps are unrolled
+// so that one MMA costs a handful of integer instructions (measured: ~200 cycles per MMA with the naive loop, which
+// capped the N<=64 layers at 1/6 of the tensor rate).
+template <bool BRES>
+__device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full,
+                                              uint64_t* b_empty, uint64_t* bres_bar, uint64_t* tmem_full_bar,
+                                              uint64_t* tmem_empty_bar, uint32_t a_base, uint32_t b_base,
+                                              uint32_t tmem_base, int num_tiles) {
+  const uint32_t idesc = make_idesc(p.bn);
+  const uint32_t b16 = ((uint32_t)p.bn * TC_BK * 2) >> 4;       // B tile size in 16-byte units
+  const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
+  const uint32_t a_lo_base = desc_lo(a_base), b_lo_base = desc_lo(b_base);
+  uint32_t tap_off[9];                                            // row-shifted view of each tap, 16-byte units
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int dyi = t / 3, dxi = t % 3;
+    tap_off[t] = (p.slab_mode == 1) ? (uint32_t)(dyi * p.wp1 + dxi) * 8u
+                                    : (uint32_t)dyi * ((uint32_t)p.slab_pitch >> 4) + (uint32_t)dxi * 8u;
+  }
+  const int mh = p.mh, kcpt = p.kc_per_tap, a_stages = p.a_stages, b_stages = p.b_stages;
+  const uint32_t bn = (uint32_t)p.bn;
+  int as = 0, bs = 0, it = 0;
+  uint32_t aph = 0, bph = 0;
+  if (BRES) {
+    mbar_wait(smem_u32(bres_bar), 0);
+    tc_fence_after();
+  }
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((it >> 1) & 1) ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + buf * 256;
+    for (int kc = 0; kc < kcpt; ++kc) {
+      mbar_wait(smem_u32(&a_full[as]), aph);
+      tc_fence_after();
+      const uint32_t a_lo0 = a_lo_base + (uint32_t)as * a_stage16;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        uint32_t b_lo;
+        if (BRES) {
+          b_lo = b_lo_base + (uint32_t)(tap * kcpt + kc) * b16;
+        } else {
+          mbar_wait(smem_u32(&b_full[bs]), bph);
+          tc_fence_after();
+          b_lo = b_lo_base + (uint32_t)bs * b16;
+        }
+        const uint32_t a_lo = a_lo0 + tap_off[tap];
+        for (int h = 0; h < mh; ++h) {
+          const uint32_t ah = a_lo + (uint32_t)h * ((TC_BM * TC_BK * 2) >> 4);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            tc_mma_f16(d_tmem + h * bn, desc_pack(ah + 2 * k), desc_pack(b_lo + 2 * k), idesc,
+                       (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
+        }
+        if (!BRES) {
+          tc_commit(smem_u32(&b_empty[bs]));
+          if (++bs == b_stages) { bs = 0; bph ^= 1; }
+        }
+      }
+      tc_commit(smem_u32(&a_empty[as]));
+      if (++as == a_stages) { as = 0; aph ^= 1; }
+    }
+    tc_commit(smem_u32(&tmem_full_bar[buf]));
   }
 }
 
@@ -559,57 +630,24 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ================================ A producer (one thread): slabs + L2 prefetch of the tiles ahead
+    // ================================ A producer (one thread)
     if (lane == 0) {
       int as = 0;
       uint32_t aph = 0;
       const uint32_t a_tx = (uint32_t)n_slabs * p.slab_rows * (TC_BK * 2);
-      auto prefetch_tile = [&](int tile) {
-        if (tile >= num_tiles) return;
-        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
-        const int m0 = m_tile * tile_rows;
-        if (n_tile == 0) {      // the A rows are shared by the N tiles of a row block
-          for (int kc = 0; kc < p.kc_per_tap; ++kc)
-            for (int j = 0; j < n_slabs; ++j) {
-              const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
-              tma_prefetch_2d(&tmA0, kc * TC_BK, row0);
-              if (p.box1_rows) tma_prefetch_2d(&tmA1, kc * TC_BK, row0 + p.box0_rows);
-            }
-        }
-        if ((EPI == LRPX_TC_EPI_MUL || EPI == LRPX_TC_EPI_MUL_UNPOOL) && p.num_n_tiles == 1) {
-          // gain (and argmax) rows of the tile: contiguous per explanation block
-          int row = m0;
-          const int end = min(m0 + tile_rows, p.m_total);
-          while (row < end) {
-            const int e = row / p.blk, rem = row - e * p.blk;
-            const int cnt = min(end - row, p.blk - rem);
-            const int img = p.row_img ? p.row_img[e] : e;
-            const size_t off = ((size_t)img * p.blk + rem) * p.out_c;
-            bulk_prefetch_l2(p.gain + off, (uint32_t)cnt * p.out_c * 2);
-            if (EPI == LRPX_TC_EPI_MUL_UNPOOL) bulk_prefetch_l2(p.pool_idx + off, (uint32_t)cnt * p.out_c);
-            row += cnt;
-          }
-        }
-      };
-      for (int i = 1; i <= p.prefetch_tiles; ++i) prefetch_tile(blockIdx.x + i * gridDim.x);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.num_n_tiles;
         const int m0 = m_tile * tile_rows;
-        if (p.prefetch_tiles) prefetch_tile(tile + (p.prefetch_tiles + 1) * gridDim.x);
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
           mbar_wait(smem_u32(&a_empty[as]), aph ^ 1);
           const uint32_t fb = smem_u32(&a_full[as]);
           const uint32_t sa = a_base + (uint32_t)as * p.a_stage_bytes;
-          if (p.debug_flags & 4) {          // timing experiment: no A traffic at all
-            mbar_arrive(fb);
-          } else {
-            mbar_expect_tx(fb, a_tx);
-            for (int j = 0; j < n_slabs; ++j) {
-              const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
-              const uint32_t dst = sa + (uint32_t)j * p.slab_pitch;
-              tma_load_2d(dst, &tmA0, fb, kc * TC_BK, row0);
-              if (p.box1_rows) tma_load_2d(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kc * TC_BK, row0 + p.box0_rows);
-            }
+          mbar_expect_tx(fb, a_tx);
+          for (int j = 0; j < n_slabs; ++j) {
+            const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
+            const uint32_t dst = sa + (uint32_t)j * p.slab_pitch;
+            tma_load_2d(dst, &tmA0, fb, kc * TC_BK, row0);
+            if (p.box1_rows) tma_load_2d(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kc * TC_BK, row0 + p.box0_rows);
           }
           if (++as == p.a_stages) { as = 0; aph ^= 1; }
         }
@@ -643,54 +681,10 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp == 1) {
     // ================================ MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.bn);
-      int as = 0, bs = 0, it = 0;
-      uint32_t aph = 0, bph = 0;
-      if (p.b_resident) {
-        mbar_wait(smem_u32(&bres_bar), 0);
-        tc_fence_after();
-      }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(smem_u32(&tmem_empty_bar[buf]), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 256;
-        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
-          mbar_wait(smem_u32(&a_full[as]), aph);
-          tc_fence_after();
-          const uint32_t sa = a_base + (uint32_t)as * p.a_stage_bytes;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            uint32_t b_addr;
-            if (p.b_resident) {
-              b_addr = b_base + (uint32_t)(tap * p.kc_per_tap + kc) * b_bytes;
-            } else {
-              mbar_wait(smem_u32(&b_full[bs]), bph);
-              tc_fence_after();
-              b_addr = b_base + (uint32_t)bs * b_bytes;
-            }
-            const int dyi = tap / 3, dxi = tap - 3 * dyi;
-            const uint32_t a_addr = (p.slab_mode == 1) ? sa + (uint32_t)(dyi * p.wp1 + dxi) * (TC_BK * 2)
-                                                       : sa + (uint32_t)dyi * p.slab_pitch + (uint32_t)dxi * (TC_BK * 2);
-            const uint64_t bdesc = make_smem_desc(b_addr);
-            for (int h = 0; h < p.mh && !(p.debug_flags & 2); ++h) {
-              const uint32_t ah = ((p.debug_flags & 8) ? sa : a_addr) + (uint32_t)h * (TC_BM * TC_BK * 2);
-#pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k)
-                tc_mma_f16(d_tmem + h * p.bn, p.desc_mode ? make_smem_desc_shifted(ah + 32 * k) : make_smem_desc(ah + 32 * k),
-                           bdesc + 2 * k, idesc,
-                           (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            }
-            if (!p.b_resident) {
-              tc_commit(smem_u32(&b_empty[bs]));
-              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
-            }
-          }
-          tc_commit(smem_u32(&a_empty[as]));
-          if (++as == p.a_stages) { as = 0; aph ^= 1; }
-        }
-        tc_commit(smem_u32(&tmem_full_bar[buf]));
-      }
+      if (p.b_resident) slab_mma_loop<true>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar,
+                                            a_base, b_base, tmem_base, num_tiles);
+      else slab_mma_loop<false>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar, a_base,
+                                b_base, tmem_base, num_tiles);
     }
   } else if (warp >= 2 && warp < 2 + TC_EPI_WARPS) {
     // ================================ epilogue warps
@@ -896,12 +890,9 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
   p.num_n_tiles = a->ncol / p.bn;
   cudaStream_t st = as_stream(stream);
   {
-    const char* e1 = getenv("LRPX_TC_BASEOFF");
-    p.desc_mode = (e1 && e1[0] == '1') ? 1 : 0;
     const char* e2 = getenv("LRPX_TC_DEBUG");
     p.debug_flags = e2 ? atoi(e2) : 0;
-    const char* e3 = getenv("LRPX_TC_PREFETCH");
-    p.prefetch_tiles = e3 ? atoi(e3) : 2;
+
   }
   {
     const char* env = getenv("LRPX_TC_SLAB");       // LRPX_TC_SLAB=0 falls back to one TMA tile per filter tap

@@ -11,11 +11,9 @@ sd = synth.vgg_state(1)
 eng = tc.TcVggEngine([sd[k] for k in sd if k.endswith("weight")], [sd[k] for k in sd if k.endswith("bias")], synth.VGG16_CFG, "cuda")
 eng.forward(torch.randn(1, 3, 224, 224, device="cuda"))
 chunk = int(os.environ.get("CHUNK", "128"))
-for name, env in [("tap", {"LRPX_TC_SLAB": "0"}), ("slab pf0", {"LRPX_TC_SLAB": "1", "LRPX_TC_PREFETCH": "0"}),
-                  ("slab pf2", {"LRPX_TC_SLAB": "1", "LRPX_TC_PREFETCH": "2"}),
-                  ("slab pf4", {"LRPX_TC_SLAB": "1", "LRPX_TC_PREFETCH": "4"}),
-                  ("slab pf4 skip_epi_io", {"LRPX_TC_SLAB": "1", "LRPX_TC_PREFETCH": "4", "LRPX_TC_DEBUG": "1"})]:
-    for k in ("LRPX_TC_DEBUG", "LRPX_TC_SLAB", "LRPX_TC_PREFETCH"):
+for name, env in [("tap", {"LRPX_TC_SLAB": "0"}), ("tap skip_epi_io", {"LRPX_TC_SLAB": "0", "LRPX_TC_DEBUG": "1"}),
+                  ("slab", {"LRPX_TC_SLAB": "1"}), ("slab skip_epi_io", {"LRPX_TC_SLAB": "1", "LRPX_TC_DEBUG": "1"})]:
+    for k in ("LRPX_TC_DEBUG", "LRPX_TC_SLAB"):
         os.environ.pop(k, None)
     os.environ.update(env)
     rows = bench.layer_table(eng, chunk, torch.device("cuda"), None)
