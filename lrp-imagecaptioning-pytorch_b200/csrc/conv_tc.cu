@@ -126,6 +126,26 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-converged variants: the WHOLE warp executes the instruction stream with uniform operands and one elected lane
+// issues (elect.sync predicate).  Keeping the issuing warp converged lets ptxas keep descriptors in uniform
+// registers instead of wrapping every UTCHMMA in an elect/branch loop (what a `if (lane == 0)` region compiles to).
+__device__ __forceinline__ void tc_mma_f16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -550,18 +570,18 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
           const uint32_t ah = a_lo + (uint32_t)h * ((TC_BM * TC_BK * 2) >> 4);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
-            tc_mma_f16(d_tmem + h * bn, desc_pack(ah + 2 * k), desc_pack(b_lo + 2 * k), idesc,
+            tc_mma_f16_elect(d_tmem + h * bn, desc_pack(ah + 2 * k), desc_pack(b_lo + 2 * k), idesc,
                        (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
         }
         if (!BRES) {
-          tc_commit(smem_u32(&b_empty[bs]));
+          tc_commit_elect(smem_u32(&b_empty[bs]));
           if (++bs == b_stages) { bs = 0; bph ^= 1; }
         }
       }
-      tc_commit(smem_u32(&a_empty[as]));
+      tc_commit_elect(smem_u32(&a_empty[as]));
       if (++as == a_stages) { as = 0; aph ^= 1; }
     }
-    tc_commit(smem_u32(&tmem_full_bar[buf]));
+    tc_commit_elect(smem_u32(&tmem_full_bar[buf]));
   }
 }
 
@@ -679,13 +699,12 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer (one thread)
-    if (lane == 0) {
-      if (p.b_resident) slab_mma_loop<true>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar,
-                                            a_base, b_base, tmem_base, num_tiles);
-      else slab_mma_loop<false>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar, a_base,
-                                b_base, tmem_base, num_tiles);
-    }
+    // ================================ MMA issuer (converged warp, one elected lane issues)
+    if (p.b_resident) slab_mma_loop<true>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar,
+                                          a_base, b_base, tmem_base, num_tiles);
+    else slab_mma_loop<false>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar, a_base,
+                              b_base, tmem_base, num_tiles);
+    __syncwarp();
   } else if (warp >= 2 && warp < 2 + TC_EPI_WARPS) {
     // ================================ epilogue warps
     const int quarter = warp & 3;
