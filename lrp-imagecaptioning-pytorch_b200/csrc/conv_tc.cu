@@ -359,6 +359,7 @@ __device__ __forceinline__ void epi_input(const TcParams& p, const RowInfo& r, c
 // One accumulator row per thread: TMEM -> registers -> epilogue math -> global memory.
 template <int EPI>
 __device__ __forceinline__ void run_epilogue(const TcParams& p, int row, uint32_t taddr, int n_tile) {
+  if (p.debug_flags & 16) return;      // timing experiment: epilogue only hands the accumulator back
   RowInfo r = row_info(p, row);
   if (p.debug_flags & 1) { r.in_range = false; r.valid = false; }
   const int n0 = n_tile * p.bn;
@@ -540,6 +541,7 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
   }
   const int mh = p.mh, kcpt = p.kc_per_tap, a_stages = p.a_stages, b_stages = p.b_stages;
   const uint32_t bn = (uint32_t)p.bn;
+  const bool skip_mma = (p.debug_flags & 2) != 0;     // timing experiment
   int as = 0, bs = 0, it = 0;
   uint32_t aph = 0, bph = 0;
   if (BRES) {
@@ -566,7 +568,7 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
           b_lo = b_lo_base + (uint32_t)bs * b16;
         }
         const uint32_t a_lo = a_lo0 + tap_off[tap];
-        for (int h = 0; h < mh; ++h) {
+        for (int h = 0; h < mh && !skip_mma; ++h) {
           const uint32_t ah = a_lo + (uint32_t)h * ((TC_BM * TC_BK * 2) >> 4);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
@@ -662,12 +664,16 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           mbar_wait(smem_u32(&a_empty[as]), aph ^ 1);
           const uint32_t fb = smem_u32(&a_full[as]);
           const uint32_t sa = a_base + (uint32_t)as * p.a_stage_bytes;
-          mbar_expect_tx(fb, a_tx);
-          for (int j = 0; j < n_slabs; ++j) {
-            const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
-            const uint32_t dst = sa + (uint32_t)j * p.slab_pitch;
-            tma_load_2d(dst, &tmA0, fb, kc * TC_BK, row0);
-            if (p.box1_rows) tma_load_2d(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kc * TC_BK, row0 + p.box0_rows);
+          if (p.debug_flags & 4) {          // timing experiment: no A traffic
+            mbar_arrive(fb);
+          } else {
+            mbar_expect_tx(fb, a_tx);
+            for (int j = 0; j < n_slabs; ++j) {
+              const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
+              const uint32_t dst = sa + (uint32_t)j * p.slab_pitch;
+              tma_load_2d(dst, &tmA0, fb, kc * TC_BK, row0);
+              if (p.box1_rows) tma_load_2d(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kc * TC_BK, row0 + p.box0_rows);
+            }
           }
           if (++as == p.a_stages) { as = 0; aph ^= 1; }
         }
