@@ -26,12 +26,15 @@ for li in [int(v) for v in os.environ.get("LAYERS", "1").split(",")]:
     else:
         out = torch.empty(tc.pf_rows(n, c.h, c.w), c.cin, device="cuda", dtype=torch.bfloat16)
         fn = lambda: tc.tc_conv(a, c.w_rel, n, c.h, c.w, c.cout, c.cin, 3, tc.EPI_MUL, out, gain=st.gain[li - 1], row_img=rimg)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
+    for _ in range(3):
         fn()
-    e1.record()
     torch.cuda.synchronize()
-    print(f"layer {li}: {e0.elapsed_time(e1) / reps:.4f} ms per launch (chunk {n})")
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    print(f"layer {li}: min {ts[0]:.4f} med {ts[len(ts) // 2]:.4f} max {ts[-1]:.4f} ms (chunk {n})")
     del a, out
