@@ -29,8 +29,9 @@ namespace lrpx {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;             // channels per K step (128 bytes of bf16)
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 224;          // warps: 0 A/TMA producer, 1 MMA, 2-5 epilogue, 6 B producer (slab kernel)
-constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_THREADS = 352;          // warps: 0 A/TMA producer, 1 MMA, 2-9 epilogue, 10 B producer (slab kernel)
+constexpr int TC_EPI_WARPS = 8;            // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int TC_BPROD_WARP = 2 + TC_EPI_WARPS;
 constexpr int TC_SMEM_BYTES = 220 * 1024;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KiB
 
@@ -164,11 +165,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // tensor pipe for small N): the high word is constant, the low word is (addr >> 4) | LBO and is advanced by adds.
 constexpr uint32_t TC_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
-__device__ __forceinline__ uint64_t desc_pack(uint32_t lo) {
-  uint64_t d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(TC_DESC_HI));
-  return d;
-}
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo) { return ((uint64_t)TC_DESC_HI << 32) | (uint64_t)lo; }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -233,61 +230,46 @@ __device__ __forceinline__ RowInfo row_info(const TcParams& p, int row) {
   return r;
 }
 
-// out[row][col..col+32) = bf16(acc * gain[img][rem][col..])
-__device__ __forceinline__ void epi_mul(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32]) {
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// out[row][col..col+32) = bf16(acc * gain[img][rem][col..]);  g = the 64 bytes of gain, loaded by the caller BEFORE it
+// waits on the accumulator so that the global-load latency overlaps the TMEM read
+__device__ __forceinline__ void epi_mul(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32],
+                                        const uint4 (&g)[4]) {
   if (!r.in_range) return;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * p.out_c + col;
-  uint4 o[4];
-  if (r.valid) {
-    int img = p.row_img ? p.row_img[r.e] : r.e;
-    const __nv_bfloat16* g = p.gain + ((size_t)img * p.blk + r.rem) * p.out_c + col;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 gv = ldg_nc_v4(g + 8 * q);
-      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-      uint32_t ow[4];
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t gw[4] = {g[q].x, g[q].y, g[q].z, g[q].w};
+    uint32_t ow[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float a0 = __uint_as_float(v[8 * q + 2 * k]) * bf16_lo(gw[k]);
-        float a1 = __uint_as_float(v[8 * q + 2 * k + 1]) * bf16_hi(gw[k]);
-        ow[k] = pack_bf16(a0, a1);
-      }
-      o[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    for (int k = 0; k < 4; ++k) {
+      float a0 = __uint_as_float(v[8 * q + 2 * k]) * bf16_lo(gw[k]);
+      float a1 = __uint_as_float(v[8 * q + 2 * k + 1]) * bf16_hi(gw[k]);
+      ow[k] = r.valid ? pack_bf16(a0, a1) : 0u;
     }
-  } else {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) o[q] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(out)[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(out)[q] = o[q];
 }
 
 // tile at pooled resolution; scatter to the 2x2 fine pixels chosen by pool_idx (others get 0)
-__device__ __forceinline__ void epi_mul_unpool(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32]) {
+__device__ __forceinline__ void epi_mul_unpool(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32],
+                                               const uint4 (&g)[4], const uint4 (&sidx)[2]) {
   if (!r.in_range) return;
   const int wf1 = 2 * p.w + 1;
   const size_t blk_f = (size_t)(2 * p.h + 1) * wf1;
   __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.e * blk_f * p.out_c + col;
   uint32_t prod[16];   // bf16x2 products
-  uint32_t sel[8];     // packed argmax bytes
-  if (r.valid) {
-    int img = p.row_img ? p.row_img[r.e] : r.e;
-    size_t go = ((size_t)img * p.blk + r.rem) * p.out_c + col;
-    const __nv_bfloat16* g = p.gain + go;
+  const uint32_t sel[8] = {sidx[0].x, sidx[0].y, sidx[0].z, sidx[0].w, sidx[1].x, sidx[1].y, sidx[1].z, sidx[1].w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 gv = ldg_nc_v4(g + 8 * q);
-      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t gw[4] = {g[q].x, g[q].y, g[q].z, g[q].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float a0 = __uint_as_float(v[8 * q + 2 * k]) * bf16_lo(gw[k]);
-        float a1 = __uint_as_float(v[8 * q + 2 * k + 1]) * bf16_hi(gw[k]);
-        prod[4 * q + k] = pack_bf16(a0, a1);
-      }
+    for (int k = 0; k < 4; ++k) {
+      float a0 = __uint_as_float(v[8 * q + 2 * k]) * bf16_lo(gw[k]);
+      float a1 = __uint_as_float(v[8 * q + 2 * k + 1]) * bf16_hi(gw[k]);
+      prod[4 * q + k] = pack_bf16(a0, a1);
     }
-    uint4 s0 = ldg_nc_v4(p.pool_idx + go), s1 = ldg_nc_v4(p.pool_idx + go + 16);
-    sel[0] = s0.x; sel[1] = s0.y; sel[2] = s0.z; sel[3] = s0.w;
-    sel[4] = s1.x; sel[5] = s1.y; sel[6] = s1.z; sel[7] = s1.w;
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -356,45 +338,104 @@ __device__ __forceinline__ void epi_input(const TcParams& p, const RowInfo& r, c
   }
 }
 
-// One accumulator row per thread: TMEM -> registers -> epilogue math -> global memory.
+// One accumulator row per thread, columns [c_begin, c_end) of the tile (two warps share a row's columns):
+// global loads of gain / argmax first, then TMEM -> registers, epilogue math, global stores.
+// pf_row >= 0: also L2-prefetch the gain row this thread will need for a later tile of the CTA.
 template <int EPI>
-__device__ __forceinline__ void run_epilogue(const TcParams& p, int row, uint32_t taddr, int n_tile) {
+__device__ __forceinline__ void run_epilogue(const TcParams& p, int row, uint32_t taddr, int n_tile, int c_begin,
+                                             int c_end, int pf_row) {
   if (p.debug_flags & 16) return;      // timing experiment: epilogue only hands the accumulator back
   RowInfo r = row_info(p, row);
   if (p.debug_flags & 1) { r.in_range = false; r.valid = false; }
   const int n0 = n_tile * p.bn;
   if (EPI == LRPX_TC_EPI_INPUT) {
+    if (c_begin != 0) return;
     uint32_t v[16];
     TMEM_LD_X16(taddr, v);
     tmem_ld_wait();
     epi_input(p, r, v);
   } else if (EPI == LRPX_TC_EPI_FWD_GAIN) {
-    for (int c = 0; c < p.half; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       uint32_t vw[32], vp[32];
       TMEM_LD_X32(taddr + c, vw);
       TMEM_LD_X32(taddr + p.half + c, vp);
       tmem_ld_wait();
       epi_fwd_gain(p, r, n_tile * p.half + c, vw, vp);
     }
-  } else {
-    for (int c = 0; c < p.bn; c += 32) {
+  } else if (EPI == LRPX_TC_EPI_STORE_F32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       uint32_t v[32];
       TMEM_LD_X32(taddr + c, v);
       tmem_ld_wait();
-      if (EPI == LRPX_TC_EPI_MUL) {
-        epi_mul(p, r, n0 + c, v);
-      } else if (EPI == LRPX_TC_EPI_MUL_UNPOOL) {
-        epi_mul_unpool(p, r, n0 + c, v);
-      } else {  // STORE_F32
-        if (r.in_range) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c);
+      if (r.in_range) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c);
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                 __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-        }
+        for (int q = 0; q < 8; ++q)
+          dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                               __uint_as_float(v[4 * q + 3]));
       }
     }
+  } else {   // MUL / MUL_UNPOOL
+    size_t goff = 0;
+    if (r.valid) {
+      const int img = p.row_img ? p.row_img[r.e] : r.e;
+      goff = ((size_t)img * p.blk + r.rem) * p.out_c + n0;
+    }
+    if (pf_row >= 0 && pf_row < p.m_total) {
+      const RowInfo q = row_info(p, pf_row);
+      if (q.valid) {
+        const int img = p.row_img ? p.row_img[q.e] : q.e;
+        const size_t po = ((size_t)img * p.blk + q.rem) * p.out_c + n0 + c_begin;
+        for (int c = 0; c < c_end - c_begin; c += 64) prefetch_l2(p.gain + po + c);      // 128-byte lines
+        if (EPI == LRPX_TC_EPI_MUL_UNPOOL) prefetch_l2(p.pool_idx + po);
+      }
+    }
+    for (int c = c_begin; c < c_end; c += 64) {          // two 32-column chunks per trip: their loads overlap
+      const bool two = c + 32 < c_end;
+      uint4 g0[4], g1[4], s0[2], s1[2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { g0[q] = make_uint4(0, 0, 0, 0); g1[q] = make_uint4(0, 0, 0, 0); }
+      s0[0] = s0[1] = s1[0] = s1[1] = make_uint4(0, 0, 0, 0);
+      if (r.valid) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g0[q] = ldg_nc_v4(p.gain + goff + c + 8 * q);
+        if (two) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) g1[q] = ldg_nc_v4(p.gain + goff + c + 32 + 8 * q);
+        }
+        if (EPI == LRPX_TC_EPI_MUL_UNPOOL) {
+          s0[0] = ldg_nc_v4(p.pool_idx + goff + c);
+          s0[1] = ldg_nc_v4(p.pool_idx + goff + c + 16);
+          if (two) {
+            s1[0] = ldg_nc_v4(p.pool_idx + goff + c + 32);
+            s1[1] = ldg_nc_v4(p.pool_idx + goff + c + 48);
+          }
+        }
+      }
+      uint32_t v0[32], v1[32];
+      TMEM_LD_X32(taddr + c, v0);
+      if (two) TMEM_LD_X32(taddr + c + 32, v1);
+      tmem_ld_wait();
+      if (EPI == LRPX_TC_EPI_MUL) {
+        epi_mul(p, r, n0 + c, v0, g0);
+        if (two) epi_mul(p, r, n0 + c + 32, v1, g1);
+      } else {
+        epi_mul_unpool(p, r, n0 + c, v0, g0, s0);
+        if (two) epi_mul_unpool(p, r, n0 + c + 32, v1, g1, s1);
+      }
+    }
+  }
+}
+
+// column range of the tile handled by an epilogue warp (eh = 0/1: which of the two warps of a TMEM lane quarter)
+__device__ __forceinline__ void epi_col_range(const TcParams& p, int epi, int eh, int& c_begin, int& c_end) {
+  const int ncols = (epi == LRPX_TC_EPI_FWD_GAIN) ? p.half : p.bn;
+  if (ncols >= 64) {
+    c_begin = eh * (ncols / 2);
+    c_end = c_begin + ncols / 2;
+  } else {            // too narrow to split: the first warp takes everything
+    c_begin = 0;
+    c_end = eh == 0 ? ncols : 0;
   }
 }
 
@@ -505,7 +546,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(smem_u32(&tmem_full_bar[buf]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
-      run_epilogue<EPI>(p, m_tile * TC_BM + quarter * 32 + lane, taddr, n_tile);
+      int c_begin, c_end;
+      epi_col_range(p, EPI, (warp - 2) >> 2, c_begin, c_end);
+      run_epilogue<EPI>(p, m_tile * TC_BM + quarter * 32 + lane, taddr, n_tile, c_begin, c_end, -1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
@@ -679,7 +722,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == TC_BPROD_WARP) {
     // ================================ B producer (one thread)
     if (lane == 0) {
       if (p.b_resident) {
@@ -721,9 +764,14 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
       mbar_wait(smem_u32(&tmem_full_bar[buf]), acc_phase);
       tc_fence_after();
+      int c_begin, c_end;
+      epi_col_range(p, EPI, (warp - 2) >> 2, c_begin, c_end);
+      const int tile_pf = tile + 2 * (int)gridDim.x;      // L2 prefetch distance: two of this CTA's tiles ahead
       for (int h = 0; h < p.mh; ++h) {
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + h * p.bn;
-        run_epilogue<EPI>(p, m_tile * tile_rows + h * TC_BM + quarter * 32 + lane, taddr, n_tile);
+        const int pf_row = (tile_pf < num_tiles && tile_pf % p.num_n_tiles == n_tile)
+                               ? (tile_pf / p.num_n_tiles) * tile_rows + h * TC_BM + quarter * 32 + lane : -1;
+        run_epilogue<EPI>(p, m_tile * tile_rows + h * TC_BM + quarter * 32 + lane, taddr, n_tile, c_begin, c_end, pf_row);
       }
       tc_fence_before();
       __syncwarp();
