@@ -199,6 +199,21 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                : "l"(p));
   return r;
 }
+// 256-bit global accesses (sm_100): one thread moves 32 contiguous bytes per instruction.  The epilogues are
+// row-per-thread (rows are >= 128 bytes apart), so every lane touches its own sector(s): wavefronts = bytes / 32.
+struct U8 { uint32_t w[8]; };
+__device__ __forceinline__ U8 ldg_nc_v8(const void* p) {
+  U8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_v8(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -235,61 +250,55 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // out[row][col..col+32) = bf16(acc * gain[img][rem][col..]);  g = the 64 bytes of gain, loaded by the caller BEFORE it
 // waits on the accumulator so that the global-load latency overlaps the TMEM read
 __device__ __forceinline__ void epi_mul(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32],
-                                        const uint4 (&g)[4]) {
+                                        const U8 (&g)[2]) {
   if (!r.in_range) return;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * p.out_c + col;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t gw[4] = {g[q].x, g[q].y, g[q].z, g[q].w};
-    uint32_t ow[4];
+  for (int q = 0; q < 2; ++q) {
+    uint32_t ow[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float a0 = __uint_as_float(v[8 * q + 2 * k]) * bf16_lo(gw[k]);
-      float a1 = __uint_as_float(v[8 * q + 2 * k + 1]) * bf16_hi(gw[k]);
+    for (int k = 0; k < 8; ++k) {
+      float a0 = __uint_as_float(v[16 * q + 2 * k]) * bf16_lo(g[q].w[k]);
+      float a1 = __uint_as_float(v[16 * q + 2 * k + 1]) * bf16_hi(g[q].w[k]);
       ow[k] = r.valid ? pack_bf16(a0, a1) : 0u;
     }
-    reinterpret_cast<uint4*>(out)[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    stg_v8(out + 16 * q, ow);
   }
 }
 
 // tile at pooled resolution; scatter to the 2x2 fine pixels chosen by pool_idx (others get 0)
 __device__ __forceinline__ void epi_mul_unpool(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32],
-                                               const uint4 (&g)[4], const uint4 (&sidx)[2]) {
+                                               const U8 (&g)[2], const U8& sidx) {
   if (!r.in_range) return;
   const int wf1 = 2 * p.w + 1;
   const size_t blk_f = (size_t)(2 * p.h + 1) * wf1;
   __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.e * blk_f * p.out_c + col;
-  uint32_t prod[16];   // bf16x2 products
-  const uint32_t sel[8] = {sidx[0].x, sidx[0].y, sidx[0].z, sidx[0].w, sidx[1].x, sidx[1].y, sidx[1].z, sidx[1].w};
+  uint32_t prod[16];   // bf16x2 products: prod[j] = channels 2j, 2j+1
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t gw[4] = {g[q].x, g[q].y, g[q].z, g[q].w};
+  for (int q = 0; q < 2; ++q)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float a0 = __uint_as_float(v[8 * q + 2 * k]) * bf16_lo(gw[k]);
-      float a1 = __uint_as_float(v[8 * q + 2 * k + 1]) * bf16_hi(gw[k]);
-      prod[4 * q + k] = pack_bf16(a0, a1);
+    for (int k = 0; k < 8; ++k) {
+      float a0 = __uint_as_float(v[16 * q + 2 * k]) * bf16_lo(g[q].w[k]);
+      float a1 = __uint_as_float(v[16 * q + 2 * k + 1]) * bf16_hi(g[q].w[k]);
+      prod[8 * q + k] = pack_bf16(a0, a1);
     }
-  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     int fr = 2 * r.a - 1 + (k >> 1), fc = 2 * r.b - 1 + (k & 1);
     if (fr < 0 || fc < 0) continue;
-    uint4* dst = reinterpret_cast<uint4*>(outb + ((size_t)fr * wf1 + fc) * p.out_c);
+    __nv_bfloat16* dst = outb + ((size_t)fr * wf1 + fc) * p.out_c;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t ow[4] = {0, 0, 0, 0};
-      if (r.valid) {
+    for (int q = 0; q < 2; ++q) {
+      uint32_t ow[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          // channels 8q+2j (low half) and 8q+2j+1 (high half); argmax bytes sit in sel[(8q+2j)/4]
-          uint32_t sw = sel[2 * q + (j >> 1)];
-          uint32_t b0 = (sw >> (16 * (j & 1))) & 0xFF, b1 = (sw >> (16 * (j & 1) + 8)) & 0xFF;
-          uint32_t pv = prod[4 * q + j];
-          ow[j] = (b0 == (uint32_t)k ? (pv & 0xFFFFu) : 0u) | (b1 == (uint32_t)k ? (pv & 0xFFFF0000u) : 0u);
-        }
+      for (int j = 0; j < 8; ++j) {
+        // channels 16q+2j (low half) and 16q+2j+1 (high half); their argmax bytes sit in word (16q+2j)/4 of sidx
+        const uint32_t sw = sidx.w[4 * q + (j >> 1)];
+        const uint32_t b0 = (sw >> (16 * (j & 1))) & 0xFF, b1 = (sw >> (16 * (j & 1) + 8)) & 0xFF;
+        const uint32_t pv = prod[8 * q + j];
+        ow[j] = !r.valid ? 0u : ((b0 == (uint32_t)k ? (pv & 0xFFFFu) : 0u) | (b1 == (uint32_t)k ? (pv & 0xFFFF0000u) : 0u));
       }
-      dst[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      stg_v8(dst + 16 * q, ow);
     }
   }
 }
@@ -301,25 +310,23 @@ __device__ __forceinline__ void epi_fwd_gain(const TcParams& p, const RowInfo& r
   __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * p.out_c + ch;
   __nv_bfloat16* gn = reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)r.row * p.out_c + ch;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t aw[4] = {0, 0, 0, 0}, gw[4] = {0, 0, 0, 0};
-    if (r.valid) {
+  for (int q = 0; q < 2; ++q) {
+    uint32_t aw[8], gw[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float z0 = __uint_as_float(vw[8 * q + 2 * k]), z1 = __uint_as_float(vw[8 * q + 2 * k + 1]);
-        if (p.bias) {
-          z0 += __ldg(p.bias + ch + 8 * q + 2 * k);
-          z1 += __ldg(p.bias + ch + 8 * q + 2 * k + 1);
-        }
-        float a0 = fmaxf(z0, 0.f), a1 = fmaxf(z1, 0.f);
-        float zp0 = __uint_as_float(vp[8 * q + 2 * k]), zp1 = __uint_as_float(vp[8 * q + 2 * k + 1]);
-        float g0 = safe_div(p.gain_mode ? 1.f : a0, zp0), g1 = safe_div(p.gain_mode ? 1.f : a1, zp1);
-        aw[k] = pack_bf16(a0, a1);
-        gw[k] = pack_bf16(g0, g1);
+    for (int k = 0; k < 8; ++k) {
+      float z0 = __uint_as_float(vw[16 * q + 2 * k]), z1 = __uint_as_float(vw[16 * q + 2 * k + 1]);
+      if (p.bias) {
+        z0 += __ldg(p.bias + ch + 16 * q + 2 * k);
+        z1 += __ldg(p.bias + ch + 16 * q + 2 * k + 1);
       }
+      float a0 = fmaxf(z0, 0.f), a1 = fmaxf(z1, 0.f);
+      float zp0 = __uint_as_float(vp[16 * q + 2 * k]), zp1 = __uint_as_float(vp[16 * q + 2 * k + 1]);
+      float g0 = safe_div(p.gain_mode ? 1.f : a0, zp0), g1 = safe_div(p.gain_mode ? 1.f : a1, zp1);
+      aw[k] = r.valid ? pack_bf16(a0, a1) : 0u;
+      gw[k] = r.valid ? pack_bf16(g0, g1) : 0u;
     }
-    reinterpret_cast<uint4*>(act)[q] = make_uint4(aw[0], aw[1], aw[2], aw[3]);
-    reinterpret_cast<uint4*>(gn)[q] = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+    stg_v8(act + 16 * q, aw);
+    stg_v8(gn + 16 * q, gw);
   }
 }
 
@@ -392,24 +399,19 @@ __device__ __forceinline__ void run_epilogue(const TcParams& p, int row, uint32_
     }
     for (int c = c_begin; c < c_end; c += 64) {          // two 32-column chunks per trip: their loads overlap
       const bool two = c + 32 < c_end;
-      uint4 g0[4], g1[4], s0[2], s1[2];
+      U8 g0[2], g1[2], s0, s1;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { g0[q] = make_uint4(0, 0, 0, 0); g1[q] = make_uint4(0, 0, 0, 0); }
-      s0[0] = s0[1] = s1[0] = s1[1] = make_uint4(0, 0, 0, 0);
+      for (int k = 0; k < 8; ++k) g0[0].w[k] = g0[1].w[k] = g1[0].w[k] = g1[1].w[k] = s0.w[k] = s1.w[k] = 0u;
       if (r.valid) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) g0[q] = ldg_nc_v4(p.gain + goff + c + 8 * q);
+        g0[0] = ldg_nc_v8(p.gain + goff + c);
+        g0[1] = ldg_nc_v8(p.gain + goff + c + 16);
         if (two) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) g1[q] = ldg_nc_v4(p.gain + goff + c + 32 + 8 * q);
+          g1[0] = ldg_nc_v8(p.gain + goff + c + 32);
+          g1[1] = ldg_nc_v8(p.gain + goff + c + 48);
         }
         if (EPI == LRPX_TC_EPI_MUL_UNPOOL) {
-          s0[0] = ldg_nc_v4(p.pool_idx + goff + c);
-          s0[1] = ldg_nc_v4(p.pool_idx + goff + c + 16);
-          if (two) {
-            s1[0] = ldg_nc_v4(p.pool_idx + goff + c + 32);
-            s1[1] = ldg_nc_v4(p.pool_idx + goff + c + 48);
-          }
+          s0 = ldg_nc_v8(p.pool_idx + goff + c);
+          if (two) s1 = ldg_nc_v8(p.pool_idx + goff + c + 32);
         }
       }
       uint32_t v0[32], v1[32];
