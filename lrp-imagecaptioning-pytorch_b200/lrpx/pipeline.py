@@ -26,46 +26,71 @@ class BatchExplainer:
         self.chunk = chunk
         self.use_graph = use_graph
         self._graphs = {}
+        self._copy_stream = None
 
     def _requests(self, B, T, device):
         req_img = torch.arange(B, dtype=torch.int32, device=device).repeat_interleave(T)
         req_t = torch.arange(T, dtype=torch.int32, device=device).repeat(B)
         return req_img, req_t
 
-    def _run(self, imgs, tokens, req_img, req_t, heat):
+    def _run(self, imgs, tokens, req_img, req_t, heat, host=None):
         est = self.eng.forward(imgs)
         feat = self.eng.features(est, "pixel")
         st = self.ex.explainer_forward(feat, tokens)
         req_word = tokens[:, 1:].reshape(-1).to(torch.int32)
         r_feat, r_words = ops.gridtd_decoder_lrp(st, self.W, req_img, req_t, req_word)
-        self.eng.relevance(est, r_feat, req_img, chunk=self.chunk, out=heat)
+        if host is None:
+            self.eng.relevance(est, r_feat, req_img, chunk=self.chunk, out=heat)
+            return r_words
+        # results go to pinned host buffers: the copy of chunk i runs on a side stream under the kernels of chunk i+1
+        host_heat, host_words = host
+        main = torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        side = self._copy_stream
+
+        def on_chunk(q0, q1):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                host_heat[q0:q1].copy_(heat[q0:q1], non_blocking=True)
+
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            host_words.copy_(r_words, non_blocking=True)
+        self.eng.relevance(est, r_feat, req_img, chunk=self.chunk, out=heat, on_chunk=on_chunk)
+        main.wait_stream(side)
         return r_words
 
-    def explain(self, imgs, tokens, out=None):
-        """imgs (B,3,H,W) fp32 CUDA, tokens (B,T+1) long CUDA with column 0 = <start>.
+    def explain(self, imgs, tokens, out=None, host_out=None):
+        """imgs (B,3,H,W) fp32 (CUDA, or pinned host memory), tokens (B,T+1) long with column 0 = <start>.
         Returns (heat (B*T,3,H,W) fp32, r_words (B*T,T) fp32); request q = b*T + t explains word t+1 of image b.
+        ``host_out=(heat_host, words_host)`` (pinned tensors) additionally delivers the results to the host, the
+        heat-map copy overlapped chunk by chunk with the relevance kernels.
         With ``use_graph`` the returned tensors are the graph's static outputs (overwritten by the next call)."""
         B, T = tokens.shape[0], tokens.shape[1] - 1
-        dev = imgs.device
+        dev = self.ex.device
         if not self.use_graph:
+            imgs, tokens = imgs.to(dev, non_blocking=True), tokens.to(dev, non_blocking=True)
             req_img, req_t = self._requests(B, T, dev)
             heat = out if out is not None else torch.empty(B * T, 3, imgs.shape[2], imgs.shape[3], device=dev)
-            return heat, self._run(imgs, tokens, req_img, req_t, heat)
-        key = (tuple(imgs.shape), tuple(tokens.shape))
+            return heat, self._run(imgs, tokens, req_img, req_t, heat, host_out)
+        key = (tuple(imgs.shape), tuple(tokens.shape), None if host_out is None else (host_out[0].data_ptr(), host_out[1].data_ptr()))
         g = self._graphs.get(key)
         if g is None:
-            s_imgs, s_toks = imgs.clone(), tokens.clone()
+            s_imgs, s_toks = imgs.to(dev).clone(), tokens.to(dev).clone()
             req_img, req_t = self._requests(B, T, dev)
             heat = torch.empty(B * T, 3, imgs.shape[2], imgs.shape[3], device=dev)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                       # warm-up outside capture (lazy inits, attributes)
-                self._run(s_imgs, s_toks, req_img, req_t, heat)
+                self._run(s_imgs, s_toks, req_img, req_t, heat, host_out)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                r_words = self._run(s_imgs, s_toks, req_img, req_t, heat)
+                r_words = self._run(s_imgs, s_toks, req_img, req_t, heat, host_out)
             # everything the captured kernels point at must outlive the graph (incl. the request index tensors)
             g = self._graphs[key] = (graph, s_imgs, s_toks, heat, r_words, req_img, req_t)
         graph, s_imgs, s_toks, heat, r_words = g[:5]

@@ -222,10 +222,11 @@ class TcVggEngine:
 
     # ------------------------------------------------------------------------------------------
     def relevance(self, st: VggState, r_feat: torch.Tensor, row_img: Optional[torch.Tensor] = None,
-                  chunk: int = 64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  chunk: int = 128, out: Optional[torch.Tensor] = None, on_chunk=None) -> torch.Tensor:
         """Image relevance for Q requests.  r_feat: fp32 (Q, h*w, C) pixel-major relevance of the encoder
         output (what the decoder kernels emit); row_img: int32 (Q,) image of each request (None = identity).
-        Returns fp32 (Q, 3, H, W)."""
+        Returns fp32 (Q, 3, H, W).  ``on_chunk(q0, q1)`` is called after the launches that produce out[q0:q1]
+        have been enqueued (used to overlap the device->host copy of finished heat-maps with the next chunk)."""
         _need_cuda(r_feat, "r_feat")
         r_feat = r_feat.detach().float().contiguous()
         Q = r_feat.shape[0]
@@ -267,6 +268,8 @@ class TcVggEngine:
                 s = dst
             c0 = self.convs[0]
             tc_conv(s, c0.w_rel, nq, c0.h, c0.w, c0.cout, 16, 3, EPI_INPUT, out[q0:q1], row_img=rimg, x=st.x)
+            if on_chunk is not None:
+                on_chunk(q0, q1)
         return out
 
     def flops_per_explanation(self) -> float:

@@ -196,6 +196,14 @@ def test_batch_pipeline_graph_equals_eager_and_single_image_api(tmp_path):
     pipe = BatchExplainer(ex, chunk=4, use_graph=True)
     heat_g, words_g = pipe.explain(imgs, toks)
     assert torch.equal(heat_e, heat_g) and torch.equal(words_e, words_g)
+    # host-buffer path (pinned in / pinned out, D2H overlapped chunk by chunk), eager and graph
+    for use_graph in (False, True):
+        hh = torch.empty(B * T, 3, 224, 224).pin_memory()
+        wh = torch.empty(B * T, T).pin_memory()
+        BatchExplainer(ex, chunk=4, use_graph=use_graph).explain(imgs.cpu().pin_memory(), toks.cpu().pin_memory(),
+                                                                  host_out=(hh, wh))
+        torch.cuda.synchronize()
+        assert torch.equal(hh, heat_e.cpu()) and torch.equal(wh, words_e.cpu())
     heat_g2, _ = pipe.explain(imgs.flip(0), toks.flip(0))             # replay with new inputs
     assert torch.equal(heat_g2.view(B, T, 3, 224, 224).flip(0).reshape_as(heat_e), heat_e)
     # per-image API gives the same explanations
