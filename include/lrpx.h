@@ -119,8 +119,13 @@ int lrpx_sum_f64(const float* x, size_t count, double* out, void* stream);
  * Saved-state tensors are those of get_hidden_parameters (gridTDmodel.py:933-1012), stacked over
  * B images and padded to T steps:   name[b][t][...]  row-major.
  * ------------------------------------------------------------------------------------------- */
+/* flags of the decoder entry points */
+#define LRPX_DEC_TC_GEMM 1   /* run the GEMMs on tcgen05 tensor cores as error-compensated bf16x3 (a_hi*w_hi + a_hi*w_lo +
+                                a_lo*w_hi, fp32 accumulate: ~2^-16 relative per product) instead of fp32 CUDA cores */
+
 typedef struct {
   int B, T, H, E, P, C, V, Q;
+  int flags, reserved_;    /* LRPX_DEC_* */
   /* per image */
   const float* feat;      /* (B,P,C)  encoder output, pixel-major (NHWC)      gridTDmodel.py:1029-1030 */
   const float* avg;       /* (B,C)                                                         :941       */
@@ -167,6 +172,7 @@ int lrpx_gridtd_decoder_lrp_f32(const lrpx_gridtd_args* args, void* workspace, s
 
 typedef struct {
   int B, T, H, E, P, C, V, Q, num_head;
+  int flags;               /* LRPX_DEC_* */
   const float* feat;      /* (B,P,C)                                   aoamodel.py:1079-1080 */
   const float* A_pre;     /* (B,P,H)                                              :1006      */
   const float* A;         /* (B,P,H)                                              :1005      */
@@ -264,6 +270,11 @@ typedef struct {
 } lrpx_tc_conv_args;
 
 int lrpx_tc_conv(const lrpx_tc_conv_args* args, void* stream);
+
+/* Plain tensor-core GEMM of the same kernel family (one filter tap):  out[m][n] = sum_k a[m][k] * wt[n][k]
+ *   a (m,k) bf16 row-major, wt (n,k) bf16 row-major, out (m,n) fp32.  k % 64 == 0, n % 32 == 0, n <= 256 or n % 256 == 0.
+ * Used by the decoder kernels for their error-compensated bf16x3 GEMMs (LRPX_DEC_TC_GEMM). */
+int lrpx_tc_gemm_bf16_f32(const void* a, const void* wt, float* out, int m, int n, int k, void* stream);
 
 /* First VGG layer forward on CUDA cores (cin = 3 is no tensor-core shape): from fp32 NCHW images
  *   act  = relu(conv(x, W) + b)                       -> PF bf16 (n, blk, cout)

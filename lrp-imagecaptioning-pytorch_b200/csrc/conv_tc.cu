@@ -920,7 +920,7 @@ using namespace lrpx;
 
 extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
   LRPX_CHECK_ARG(a, "null args");
-  LRPX_CHECK_ARG(a->n_img > 0 && a->h > 0 && a->w > 0, "bad image dimensions");
+  LRPX_CHECK_ARG(a->n_img > 0 && a->h >= 0 && a->w >= 0, "bad image dimensions");
   LRPX_CHECK_ARG(a->cin > 0 && a->cin % TC_BK == 0, "cin must be a multiple of 64");
   LRPX_CHECK_ARG(a->ksize == 1 || a->ksize == 3, "ksize must be 1 or 3");
   LRPX_CHECK_ARG(a->a && a->wt && a->out, "null pointer");
@@ -1015,4 +1015,14 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     case LRPX_TC_EPI_INPUT: return launch_tc<LRPX_TC_EPI_INPUT>(ma, mb, p, grid, st);
     default: return launch_tc<LRPX_TC_EPI_STORE_F32>(ma, mb, p, grid, st);
   }
+}
+
+extern "C" int lrpx_tc_gemm_bf16_f32(const void* a, const void* wt, float* out, int m, int n, int k, void* stream) {
+  LRPX_CHECK_ARG(a && wt && out && m > 0 && n > 0 && k > 0, "bad argument");
+  LRPX_CHECK_ARG(k % TC_BK == 0 && n % 32 == 0 && (n <= 256 || n % 256 == 0), "unsupported GEMM shape");
+  // one PF "block" of m rows (h = 0, w = m - 1): the STORE_F32 epilogue writes every in-range row
+  lrpx_tc_conv_args g{};
+  g.n_img = 1; g.h = 0; g.w = m - 1; g.cin = k; g.ncol = n; g.ksize = 1; g.epilogue = LRPX_TC_EPI_STORE_F32;
+  g.a = a; g.wt = wt; g.out = out;
+  return lrpx_tc_conv(&g, stream);
 }

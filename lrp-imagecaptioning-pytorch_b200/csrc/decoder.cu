@@ -110,6 +110,84 @@ static int sgemm(const float* A, const float* B, float* C, int M, int N, int K, 
   return LRPX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Error-compensated tensor-core GEMM (LRPX_DEC_TC_GEMM):  x = hi + lo with hi = bf16(x), lo = bf16(x - hi);
+//   a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi   (the dropped lo*lo term is ~2^-16 relative)
+// evaluated as ONE bf16 GEMM with the K dimension concatenated three times, fp32 accumulation in TMEM:
+//   A' = [a_hi | a_hi | a_lo]  (M x 3K),   W' = [w_hi | w_lo | w_hi]  (N x 3K, K-major = the transposed weight)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16(x);
+  lo = __float2bfloat16(x - __bfloat162float(hi));
+}
+// rows x K fp32 (row pitch lda) -> rows x 3K bf16 [hi | hi | lo]
+__global__ void split3_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int K,
+                                  int lda) {
+  long long total = rows * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / K;
+    int k = (int)(i - r * K);
+    __nv_bfloat16 hi, lo;
+    split_bf16(x[r * lda + k], hi, lo);
+    __nv_bfloat16* o = out + r * 3 * K;
+    o[k] = hi; o[K + k] = hi; o[2 * K + k] = lo;
+  }
+}
+// W (K x N fp32 row-major, i.e. [k][n]) -> N x 3K bf16 [hi | lo | hi] of W^T
+__global__ void split3_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int K, int N) {
+  long long total = (long long)K * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(i % N);
+    int k = (int)(i / N);
+    __nv_bfloat16 hi, lo;
+    split_bf16(w[i], hi, lo);
+    __nv_bfloat16* o = out + (size_t)n * 3 * K;
+    o[k] = hi; o[K + k] = lo; o[2 * K + k] = hi;
+  }
+}
+// GE_FEAT / GE_AOA_PROJ epilogues applied to a plain GEMM result in place
+template <int EPI>
+__global__ void gemm_epilogue_kernel(float* __restrict__ C, long long M, int N, GemmEpi e) {
+  long long total = M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long m = i / N;
+    int n = (int)(i - m * N);
+    int q = (int)(m / e.P), pp = (int)(m % e.P);
+    int b = e.req_img[q];
+    size_t o = ((size_t)b * e.P + pp) * N + n;
+    float add = e.add_q ? e.add_q[(size_t)q * N + n] : 0.f;
+    float v = e.x0[o] * (C[i] + add);
+    if (EPI == GE_AOA_PROJ) v = v / stab(e.x1[o]);
+    C[i] = v;
+  }
+}
+
+static inline int ew_grid(long long total) {
+  long long g = (total + 255) / 256, cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+static bool tc_shape_ok(int N, int K) { return K % 64 == 0 && N % 32 == 0 && (N <= 256 || N % 256 == 0); }
+
+// C[M,N] = A[M,K] @ W[K,N] (+ epilogue): tensor cores when `wt3` (prepared W') is given, CUDA cores otherwise
+template <int EPI>
+static int gemm_any(const float* A, const float* W, const __nv_bfloat16* wt3, __nv_bfloat16* a3, float* C, int M, int N,
+                    int K, const GemmEpi& e, cudaStream_t st) {
+  if (M == 0) return LRPX_OK;
+  if (!wt3) return sgemm<EPI>(A, W, C, M, N, K, e, st);
+  split3_act_kernel<<<ew_grid((long long)M * K), 256, 0, st>>>(A, a3, M, K, K);
+  int rc = lrpx_tc_gemm_bf16_f32(a3, wt3, C, M, N, 3 * K, st);
+  if (rc) return rc;
+  if (EPI != GE_STORE) gemm_epilogue_kernel<EPI><<<ew_grid((long long)M * N), 256, 0, st>>>(C, M, N, e);
+  return LRPX_OK;
+}
+static __nv_bfloat16* prep_weight3(const float* W, __nv_bfloat16* dst, int K, int N, cudaStream_t st) {
+  split3_weight_kernel<<<ew_grid((long long)K * N), 256, 0, st>>>(W, dst, K, N);
+  return dst;
+}
+
 // fc rule for the target word only (one-hot relevance): gridTDmodel.py:1033-1059
 //   r_sum = s_in * W_fc[word] * logit/stab(logit);  r_a = a * r_sum / stab(s_in), r_b likewise
 __device__ __forceinline__ void fc_split(float a, float b, float wrow, float coef, float& ra, float& rb) {
@@ -125,6 +203,8 @@ __device__ __forceinline__ void fc_split(float a, float b, float wrow, float coe
 // ------------------------------------------------------------------------------------------------
 struct GridWs {
   float *r_h2, *r_c2, *r_c1, *r_cth, *r_glob, *u, *v, *uctx, *coefavg, *wproj;
+  // LRPX_DEC_TC_GEMM: split activations (largest GEMM) and prepared weights, bf16
+  __nv_bfloat16 *a3, *w3_g2, *w3_g1, *w3_glob, *w3_proj;
 };
 
 __global__ void grid_init_kernel(lrpx_gridtd_args a, GridWs w) {
@@ -293,6 +373,16 @@ static size_t grid_carve(const lrpx_gridtd_args* a, float* base, GridWs* w) {
   t.uctx = take(Q * a->T * H);
   t.coefavg = take(Q * a->C);
   t.wproj = take(Q * a->P * H);
+  t.a3 = t.w3_g2 = t.w3_g1 = t.w3_glob = t.w3_proj = nullptr;
+  if (a->flags & LRPX_DEC_TC_GEMM) {
+    auto take16 = [&](size_t n) { return reinterpret_cast<__nv_bfloat16*>(take((n + 1) / 2)); };   // n bf16 elements
+    size_t rows_max = Q * a->P;
+    t.a3 = take16(rows_max * 3 * H > Q * 3 * E ? rows_max * 3 * H : Q * 3 * E);
+    t.w3_g2 = take16((size_t)3 * H * 3 * H);
+    t.w3_g1 = take16((size_t)(2 * H + 2 * E) * 3 * H);
+    t.w3_glob = take16((size_t)a->C * 3 * E);
+    t.w3_proj = take16((size_t)a->C * 3 * H);
+  }
   if (w) *w = t;
   return off * sizeof(float);
 }
@@ -302,6 +392,7 @@ static size_t grid_carve(const lrpx_gridtd_args* a, float* base, GridWs* w) {
 // ------------------------------------------------------------------------------------------------
 struct AoaWs {
   float *r_h, *r_glob, *u, *v, *uval, *addq, *wval, *w2;
+  __nv_bfloat16 *a3, *w3_aoa, *w3_g, *w3_v, *w3_proj;
 };
 
 __global__ void aoa_init_kernel(lrpx_aoa_args a, AoaWs w) {
@@ -406,6 +497,15 @@ static size_t aoa_carve(const lrpx_aoa_args* a, float* base, AoaWs* w) {
   t.uval = take(Q * H); t.addq = take(Q * H);
   t.wval = take(Q * a->P * H);
   t.w2 = take(Q * a->P * H);
+  t.a3 = t.w3_aoa = t.w3_g = t.w3_v = t.w3_proj = nullptr;
+  if (a->flags & LRPX_DEC_TC_GEMM) {
+    auto take16 = [&](size_t n) { return reinterpret_cast<__nv_bfloat16*>(take((n + 1) / 2)); };
+    t.a3 = take16(Q * a->P * 3 * H);
+    t.w3_aoa = take16(H * 3 * H);
+    t.w3_g = take16((size_t)(a->E + 2 * H) * 3 * H);
+    t.w3_v = take16(H * 3 * H);
+    t.w3_proj = take16((size_t)a->C * 3 * H);
+  }
   if (w) *w = t;
   return off * sizeof(float);
 }
@@ -515,21 +615,28 @@ int lrpx_gridtd_decoder_lrp_f32(const lrpx_gridtd_args* a, void* workspace, size
   const int Q = a->Q, H = a->H, E = a->E, T = a->T;
   int nt = H >= 256 ? 256 : 128;
   GemmEpi none{};
+  // tensor-core GEMMs where the shape allows it (per GEMM), CUDA cores otherwise
+  const bool tc = (a->flags & LRPX_DEC_TC_GEMM) != 0;
+  const __nv_bfloat16* w3_g2 = (tc && tc_shape_ok(3 * H, H)) ? prep_weight3(a->W_g2, w.w3_g2, H, 3 * H, st) : nullptr;
+  const __nv_bfloat16* w3_g1 =
+      (tc && tc_shape_ok(2 * H + 2 * E, H)) ? prep_weight3(a->W_g1, w.w3_g1, H, 2 * H + 2 * E, st) : nullptr;
+  const __nv_bfloat16* w3_glob = (tc && tc_shape_ok(a->C, E)) ? prep_weight3(a->W_glob, w.w3_glob, E, a->C, st) : nullptr;
+  const __nv_bfloat16* w3_proj = (tc && tc_shape_ok(a->C, H)) ? prep_weight3(a->W_proj, w.w3_proj, H, a->C, st) : nullptr;
   grid_init_kernel<<<Q, nt, 0, st>>>(*a, w);
   cudaMemsetAsync(w.uctx, 0, (size_t)Q * T * H * sizeof(float), st);
   for (int i = T - 1; i >= 0; --i) {
     grid_cell2_kernel<<<Q, nt, 0, st>>>(*a, w, i);
-    RUN(sgemm<GE_STORE>(w.u, a->W_g2, w.v, Q, 3 * H, H, none, st));
+    RUN(gemm_any<GE_STORE>(w.u, a->W_g2, w3_g2, w.a3, w.v, Q, 3 * H, H, none, st));
     grid_post2_kernel<<<Q, nt, 0, st>>>(*a, w, i);
-    RUN(sgemm<GE_STORE>(w.u, a->W_g1, w.v, Q, 2 * H + 2 * E, H, none, st));
+    RUN(gemm_any<GE_STORE>(w.u, a->W_g1, w3_g1, w.a3, w.v, Q, 2 * H + 2 * E, H, none, st));
     grid_post1_kernel<<<Q, 256, 0, st>>>(*a, w, i);
   }
   grid_glob_kernel<<<Q, 128, 0, st>>>(*a, w);
-  RUN(sgemm<GE_STORE>(w.u, a->W_glob, w.v, Q, a->C, E, none, st));
+  RUN(gemm_any<GE_STORE>(w.u, a->W_glob, w3_glob, w.a3, w.v, Q, a->C, E, none, st));
   grid_avg_kernel<<<Q, 128, 0, st>>>(*a, w);
   grid_attn_kernel<<<dim3(a->P, Q), nt, 0, st>>>(*a, w);
   GemmEpi fe{a->feat, nullptr, w.coefavg, a->req_img, a->P};
-  RUN(sgemm<GE_FEAT>(w.wproj, a->W_proj, a->r_feat, Q * a->P, a->C, H, fe, st));
+  RUN(gemm_any<GE_FEAT>(w.wproj, a->W_proj, w3_proj, w.a3, a->r_feat, Q * a->P, a->C, H, fe, st));
   words_norm_kernel<<<Q, 32, 0, st>>>(a->r_words, a->req_t, T);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;
@@ -558,19 +665,24 @@ int lrpx_aoa_decoder_lrp_f32(const lrpx_aoa_args* a, void* workspace, size_t wor
   const int Q = a->Q, H = a->H, E = a->E, T = a->T;
   int nt = H >= 256 ? 256 : 128;
   GemmEpi none{};
+  const bool tc = (a->flags & LRPX_DEC_TC_GEMM) != 0;
+  const __nv_bfloat16* w3_aoa = (tc && tc_shape_ok(H, H)) ? prep_weight3(a->W_aoa, w.w3_aoa, H, H, st) : nullptr;
+  const __nv_bfloat16* w3_g = (tc && tc_shape_ok(E + 2 * H, H)) ? prep_weight3(a->W_g, w.w3_g, H, E + 2 * H, st) : nullptr;
+  const __nv_bfloat16* w3_v = (tc && tc_shape_ok(H, H)) ? prep_weight3(a->W_v, w.w3_v, H, H, st) : nullptr;
+  const __nv_bfloat16* w3_proj = (tc && tc_shape_ok(a->C, H)) ? prep_weight3(a->W_proj, w.w3_proj, H, a->C, st) : nullptr;
   aoa_init_kernel<<<Q, nt, 0, st>>>(*a, w);
-  RUN(sgemm<GE_STORE>(w.u, a->W_aoa, w.v, Q, H, H, none, st));
+  RUN(gemm_any<GE_STORE>(w.u, a->W_aoa, w3_aoa, w.a3, w.v, Q, H, H, none, st));
   aoa_ctx_kernel<<<Q, nt, 0, st>>>(*a, w);
   for (int i = T - 1; i >= 0; --i) {
     aoa_cell_kernel<<<Q, nt, 0, st>>>(*a, w, i);
-    RUN(sgemm<GE_STORE>(w.u, a->W_g, w.v, Q, E + 2 * H, H, none, st));
+    RUN(gemm_any<GE_STORE>(w.u, a->W_g, w3_g, w.a3, w.v, Q, E + 2 * H, H, none, st));
     aoa_post_kernel<<<Q, 256, 0, st>>>(*a, w, i);
   }
   aoa_val_kernel<<<dim3(a->P, Q), nt, 0, st>>>(*a, w);
   GemmEpi pe{a->A, a->A_pre, w.addq, a->req_img, a->P};
-  RUN(sgemm<GE_AOA_PROJ>(w.wval, a->W_v, w.w2, Q * a->P, H, H, pe, st));
+  RUN(gemm_any<GE_AOA_PROJ>(w.wval, a->W_v, w3_v, w.a3, w.w2, Q * a->P, H, H, pe, st));
   GemmEpi fe{a->feat, nullptr, nullptr, a->req_img, a->P};
-  RUN(sgemm<GE_FEAT>(w.w2, a->W_proj, a->r_feat, Q * a->P, a->C, H, fe, st));
+  RUN(gemm_any<GE_FEAT>(w.w2, a->W_proj, w3_proj, w.a3, a->r_feat, Q * a->P, a->C, H, fe, st));
   words_norm_kernel<<<Q, 32, 0, st>>>(a->r_words, a->req_t, T);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;

@@ -27,7 +27,8 @@ _GRID_PTRS = ["feat", "avg", "A_pre", "A", "glob_pre", "x1", "x2", "h1", "c1", "
 
 
 class GridTDArgs(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("B", "T", "H", "E", "P", "C", "V", "Q")] + [(n, _P) for n in _GRID_PTRS]
+    _fields_ = [(n, C.c_int) for n in ("B", "T", "H", "E", "P", "C", "V", "Q", "flags", "reserved_")] + \
+               [(n, _P) for n in _GRID_PTRS]
 
 
 _AOA_PTRS = ["feat", "A_pre", "A", "glob", "value", "x", "h", "c", "g", "i", "ctx", "caoa", "caoa_lin", "alpha",
@@ -36,7 +37,7 @@ _AOA_PTRS = ["feat", "A_pre", "A", "glob", "value", "x", "h", "c", "g", "i", "ct
 
 
 class AoaArgs(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("B", "T", "H", "E", "P", "C", "V", "Q", "num_head")] + \
+    _fields_ = [(n, C.c_int) for n in ("B", "T", "H", "E", "P", "C", "V", "Q", "num_head", "flags")] + \
                [(n, _P) for n in _AOA_PTRS]
 
 
@@ -69,6 +70,7 @@ SYMBOLS = {
     "lrpx_aoa_decoder_lrp_f32": (_i, [C.POINTER(AoaArgs), _P, _sz, _P]),
     "lrpx_fc_lrp_weights_f32": (_i, [_P, _P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
     "lrpx_tc_conv": (_i, [C.POINTER(TcConvArgs), _P]),
+    "lrpx_tc_gemm_bf16_f32": (_i, [_P, _P, _P, _i, _i, _i, _P]),
     "lrpx_weight_prep_bf16": (_i, [_P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),
     "lrpx_tc_first_fwd": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "lrpx_tc_maxpool2_bf16": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),

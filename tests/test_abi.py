@@ -46,8 +46,8 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.ConvShape) == 13 * 4
     assert C.sizeof(_lib.PoolShape) == 10 * 4
     assert C.sizeof(_lib.TcConvArgs) == 8 * 4 + 9 * 8
-    assert C.sizeof(_lib.GridTDArgs) == 8 * 4 + len(_lib._GRID_PTRS) * 8
-    assert C.sizeof(_lib.AoaArgs) == 40 + len(_lib._AOA_PTRS) * 8      # 9 ints padded to 40 bytes
+    assert C.sizeof(_lib.GridTDArgs) == 10 * 4 + len(_lib._GRID_PTRS) * 8
+    assert C.sizeof(_lib.AoaArgs) == 40 + len(_lib._AOA_PTRS) * 8      # 10 ints
 
 
 def test_no_cpu_fallback():
