@@ -231,9 +231,13 @@ def _fill_args(struct, fields: dict, keep: list):
     return struct
 
 
-def gridtd_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, want_raw=False):
+DEC_TC_GEMM = 1
+
+
+def gridtd_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, want_raw=False, tc_gemm=False):
     """state: tensors of lrpx_gridtd_args (stacked over B images), weights: W_g1,W_g2,W_fc,W_glob,W_proj.
-    Returns r_feat (Q,P,C), r_words (Q,T)[, r_words_raw]."""
+    tc_gemm: run the GEMMs as error-compensated bf16x3 on the tensor cores (LRPX_DEC_TC_GEMM) instead of fp32
+    CUDA cores.  Returns r_feat (Q,P,C), r_words (Q,T)[, r_words_raw]."""
     dev = state["feat"].device
     B, P, Cc = state["feat"].shape
     T, H = state["g1"].shape[1], state["g1"].shape[2]
@@ -241,7 +245,7 @@ def gridtd_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, wan
     V = state["pred"].shape[2]
     Q = int(req_img.numel())
     keep = []
-    a = _lib.GridTDArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q)
+    a = _lib.GridTDArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q, flags=DEC_TC_GEMM if tc_gemm else 0)
     f = {k: _f32(state[k], k) for k in ["feat", "avg", "A_pre", "A", "glob_pre", "x1", "x2", "h1", "c1", "h2", "c2",
                                         "g1", "i1", "f1", "g2", "i2", "f2", "st", "ctx", "ctx_hat", "alpha", "beta",
                                         "pred"]}
@@ -260,7 +264,8 @@ def gridtd_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, wan
     return (r_feat, r_words, r_raw) if want_raw else (r_feat, r_words)
 
 
-def aoa_decoder_lrp(state: dict, weights: dict, num_head, req_img, req_t, req_word, req_head, want_raw=False):
+def aoa_decoder_lrp(state: dict, weights: dict, num_head, req_img, req_t, req_word, req_head, want_raw=False,
+                    tc_gemm=False):
     dev = state["feat"].device
     B, P, Cc = state["feat"].shape
     T, H = state["g"].shape[1], state["g"].shape[2]
@@ -268,7 +273,7 @@ def aoa_decoder_lrp(state: dict, weights: dict, num_head, req_img, req_t, req_wo
     V = state["pred"].shape[2]
     Q = int(req_img.numel())
     keep = []
-    a = _lib.AoaArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q, num_head=num_head)
+    a = _lib.AoaArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q, num_head=num_head, flags=DEC_TC_GEMM if tc_gemm else 0)
     f = {k: _f32(state[k], k) for k in ["feat", "A_pre", "A", "glob", "value", "x", "h", "c", "g", "i", "ctx", "caoa",
                                         "caoa_lin", "alpha", "pred"]}
     f.update({k: _f32(weights[k], k) for k in ["W_g", "W_fc", "W_aoa", "W_v", "W_proj"]})

@@ -16,7 +16,7 @@ from . import ops
 
 
 class BatchExplainer:
-    def __init__(self, explainer, chunk=128, use_graph=False):
+    def __init__(self, explainer, chunk=128, use_graph=False, tc_gemm=True):
         """explainer: models.gridTDmodel.ExplainGridTDAttention with precision='bf16' (VGG encoder)."""
         if explainer.precision != "bf16":
             raise ValueError("BatchExplainer drives the tensor-core chain: build the explainer with precision='bf16'")
@@ -25,6 +25,7 @@ class BatchExplainer:
         self.W = explainer._lrp_weights()
         self.chunk = chunk
         self.use_graph = use_graph
+        self.tc_gemm = tc_gemm            # decoder GEMMs as bf16x3 on tensor cores (fp32 CUDA cores when False)
         self._graphs = {}
         self._copy_stream = None
 
@@ -38,7 +39,7 @@ class BatchExplainer:
         feat = self.eng.features(est, "pixel")
         st = self.ex.explainer_forward(feat, tokens)
         req_word = tokens[:, 1:].reshape(-1).to(torch.int32)
-        r_feat, r_words = ops.gridtd_decoder_lrp(st, self.W, req_img, req_t, req_word)
+        r_feat, r_words = ops.gridtd_decoder_lrp(st, self.W, req_img, req_t, req_word, tc_gemm=self.tc_gemm)
         if host is None:
             self.eng.relevance(est, r_feat, req_img, chunk=self.chunk, out=heat)
             return r_words

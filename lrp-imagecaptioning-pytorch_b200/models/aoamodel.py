@@ -333,7 +333,8 @@ class ExplainAOAAttention(ExplainGridTDAttention):
         dev = self.device
         i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
         return ops.aoa_decoder_lrp(self._state, self._lrp_weights(), self.num_head, i32([0] * len(ts)), i32(list(ts)),
-                                   i32([toks[t + 1] for t in ts]), i32([head_idx] * len(ts)))
+                                   i32([toks[t + 1] for t in ts]), i32([head_idx] * len(ts)),
+                                   tc_gemm=(self.precision == 'bf16'))
 
     def lrp_mha(self, alpha, value, context, r_context, head_idx):
         """reference :812-862: relevance of the values of ONE head (others get 0, Q5).

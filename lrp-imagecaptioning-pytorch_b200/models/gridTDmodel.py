@@ -548,7 +548,8 @@ class ExplainGridTDAttention(object):
         req_t = torch.tensor(ts, dtype=torch.int32, device=dev)
         req_word = torch.tensor([toks[t + 1] for t in ts], dtype=torch.int32, device=dev)
         req_img = torch.zeros(len(ts), dtype=torch.int32, device=dev)
-        return ops.gridtd_decoder_lrp(self._state, self._lrp_weights(), req_img, req_t, req_word)
+        return ops.gridtd_decoder_lrp(self._state, self._lrp_weights(), req_img, req_t, req_word,
+                                      tc_gemm=(self.precision == 'bf16'))
 
     def explain_caption_wordt(self, t):
         """reference :1014-1135 -> (r_img_feature (1,C,h,w), r_words (t+1,))."""

@@ -18,8 +18,11 @@ def _ref_feat(r, C):
     return r[0].reshape(C, -1).t()
 
 
+@pytest.mark.parametrize("tc_gemm", [False, True])
 @pytest.mark.parametrize("name", ["gridtd_dec_small", "gridtd_dec_512"])
-def test_gridtd_vs_reference_fixture(golden, name):
+def test_gridtd_vs_reference_fixture(golden, name, tc_gemm):
+    """tc_gemm=True: the GEMMs run as error-compensated bf16x3 on the tensor cores (~2^-16 relative per product);
+    bar for that mode: scale-relative atol 1e-4 (fp32 CUDA-core mode: 1e-5)."""
     from lrpx import ops
     g = golden(name)
     V, H, E = int(g["V"]), int(g["H"]), int(g["E"])
@@ -32,12 +35,15 @@ def test_gridtd_vs_reference_fixture(golden, name):
     req_img = torch.zeros(len(ts), dtype=torch.int32)
     req_t = torch.tensor(ts, dtype=torch.int32)
     req_word = torch.tensor([toks[t + 1] for t in ts], dtype=torch.int32)
-    r_feat, r_words, raw = ops.gridtd_decoder_lrp(ks, W, req_img, req_t, req_word, want_raw=True)
+    r_feat, r_words, raw = ops.gridtd_decoder_lrp(ks, W, req_img, req_t, req_word, want_raw=True, tc_gemm=tc_gemm)
+    atol = 1e-4 if tc_gemm else 1e-5
     for q, t in enumerate(ts):
         ref = _ref_feat(g[f"r_feat_{t}"], 512)
         scale = ref.abs().max()
-        assert_close(r_feat[q] / scale, ref / scale, rtol=1e-3, atol=1e-5, what=f"{name} r_feat t={t}")
-        assert_close(r_words[q, :t + 1], g[f"r_words_{t}"], rtol=1e-3, atol=1e-5, what=f"{name} r_words t={t}")
+        print(f"{name} tc_gemm={tc_gemm} t={t}: max scale-relative error "
+              f"{float((r_feat[q].cpu() - ref).abs().max() / scale):.3e}")
+        assert_close(r_feat[q] / scale, ref / scale, rtol=1e-3, atol=atol, what=f"{name} r_feat t={t}")
+        assert_close(r_words[q, :t + 1], g[f"r_words_{t}"], rtol=1e-3, atol=atol, what=f"{name} r_words t={t}")
         assert float(r_words[q, t + 1:].abs().sum()) == 0.0
         # conservation report: relevance reaching the features + words vs the explained logit
         print(f"{name} t={t}: sum r_feat={float(r_feat[q].sum()):.6g} sum r_words_raw={float(raw[q].sum()):.6g} "
@@ -75,8 +81,9 @@ def test_gridtd_batched_requests_vs_oracle():
     assert rf0.shape[0] == 0 and rw0.shape[0] == 0
 
 
+@pytest.mark.parametrize("tc_gemm", [False, True])
 @pytest.mark.parametrize("name", ["aoa_dec_512", "aoa_dec_bu"])
-def test_aoa_vs_reference_fixture(golden, name):
+def test_aoa_vs_reference_fixture(golden, name, tc_gemm):
     from lrpx import ops
     g = golden(name)
     V, H, E, C = int(g["V"]), int(g["H"]), int(g["E"]), int(g["C"])
@@ -90,9 +97,12 @@ def test_aoa_vs_reference_fixture(golden, name):
     req_t = torch.tensor([c[0] for c in cases], dtype=torch.int32)
     req_head = torch.tensor([c[1] for c in cases], dtype=torch.int32)
     req_word = torch.tensor([toks[c[0] + 1] for c in cases], dtype=torch.int32)
-    r_feat, r_words = ops.aoa_decoder_lrp(ks, W, 8, req_img, req_t, req_word, req_head)
+    r_feat, r_words = ops.aoa_decoder_lrp(ks, W, 8, req_img, req_t, req_word, req_head, tc_gemm=tc_gemm)
+    atol = 1e-4 if tc_gemm else 1e-5
     for q, (t, hd) in enumerate(cases):
         ref = _ref_feat(g[f"r_feat_{t}_{hd}"], C)
         scale = ref.abs().max()
-        assert_close(r_feat[q] / scale, ref / scale, rtol=1e-3, atol=1e-5, what=f"{name} r_feat {t},{hd}")
-        assert_close(r_words[q, :t + 1], g[f"r_words_{t}_{hd}"], rtol=1e-3, atol=1e-5, what=f"{name} r_words {t},{hd}")
+        print(f"{name} tc_gemm={tc_gemm} ({t},{hd}): max scale-relative error "
+              f"{float((r_feat[q].cpu() - ref).abs().max() / scale):.3e}")
+        assert_close(r_feat[q] / scale, ref / scale, rtol=1e-3, atol=atol, what=f"{name} r_feat {t},{hd}")
+        assert_close(r_words[q, :t + 1], g[f"r_words_{t}_{hd}"], rtol=1e-3, atol=atol, what=f"{name} r_words {t},{hd}")
