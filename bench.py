@@ -207,7 +207,8 @@ def run_ours(args):
         est = eng.forward(imgs_d); marks[1].record()
         feat = eng.features(est, "pixel")
         st = ex.explainer_forward(feat, toks_d); marks[2].record()
-        r_feat, r_words = ops.gridtd_decoder_lrp(st, W, req_img, req_t, toks_d[:, 1:].reshape(-1).to(torch.int32))
+        r_feat, r_words = ops.gridtd_decoder_lrp(st, W, req_img, req_t, toks_d[:, 1:].reshape(-1).to(torch.int32),
+                                                 tc_gemm=True)
         marks[3].record()
         eng.relevance(est, r_feat, req_img, chunk=args.chunk, out=heat); marks[4].record()
         torch.cuda.synchronize()
@@ -235,9 +236,10 @@ def run_ours(args):
     step_eager_ms = sum(phase_ms.values())
 
     # launches of OUR kernels inside the timed region: one per C-ABI call, except the decoder call which
-    # enqueues 1 init + 1 memset-free zeroing + 5 per step + 5 tail kernels (csrc/decoder.cu)
+    # enqueues 4 weight splits + init + per step (3 element-wise + 2 x (split + tensor-core GEMM)) + 9 tail kernels
+    # (csrc/decoder.cu, LRPX_DEC_TC_GEMM path)
     launches = sum(v for k, v in calls.items() if k != "lrpx_gridtd_decoder_lrp_f32")
-    launches += calls.get("lrpx_gridtd_decoder_lrp_f32", 0) * (1 + 5 * T + 6)
+    launches += calls.get("lrpx_gridtd_decoder_lrp_f32", 0) * (5 + 7 * T + 9)
     launches *= args.steps          # the same kernels per step whether launched eagerly or replayed from the graph
 
     out = None
@@ -254,7 +256,7 @@ def run_ours(args):
                                    f"{B} images x {T} words per GPU per step, 224x224, V={args.vocab}, H=E=512",
                        "explanations_per_step_per_gpu": Q, "chunk": args.chunk, "cuda_graph": not args.no_graph, "parallelism": f"request-sharded x{world}",
                        "l2": "working set (gains 1.9 GB + chain buffers) far larger than the 126 MB L2; no flush needed",
-                       "decoder_relevance_dtype": "f32", "encoder_relevance_dtype": "bf16 operands, f32 accumulate"},
+                       "decoder_relevance_dtype": "f32 element-wise, GEMMs as error-compensated bf16x3 on tensor cores (f32 accumulate)", "encoder_relevance_dtype": "bf16 operands, f32 accumulate"},
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": imgs_h.numel() * 4 + toks_h.numel() * 8,
                     "d2h_bytes_per_step": heat_h.numel() * 4 + words_h.numel() * 4},
