@@ -29,9 +29,10 @@ namespace lrpx {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;             // channels per K step (128 bytes of bf16)
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 352;          // warps: 0 A/TMA producer, 1 MMA, 2-9 epilogue, 10 B producer (slab kernel)
+constexpr int TC_THREADS = 384;          // warps: 0 A/TMA producer, 1 MMA, 2-9 epilogue, 10 B producer, 11 second MMA issuer (slab kernel)
 constexpr int TC_EPI_WARPS = 8;            // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int TC_BPROD_WARP = 2 + TC_EPI_WARPS;
+constexpr int TC_MMA2_WARP = TC_BPROD_WARP + 1;
 constexpr int TC_SMEM_BYTES = 220 * 1024;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KiB
 
@@ -572,7 +573,9 @@ template <bool BRES>
 __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full,
                                               uint64_t* b_empty, uint64_t* bres_bar, uint64_t* tmem_full_bar,
                                               uint64_t* tmem_empty_bar, uint32_t a_base, uint32_t b_base,
-                                              uint32_t tmem_base, int num_tiles) {
+                                              uint32_t tmem_base, int num_tiles, int issuer) {
+  // Two issuer warps take the CTA's tiles alternately (issuer j owns TMEM buffer j): one thread needs ~75 cycles
+  // per MMA (descriptor moves to uniform registers + issue), which is more than an N <= 64 MMA occupies the pipe.
   const uint32_t idesc = make_idesc(p.bn);
   const uint32_t b16 = ((uint32_t)p.bn * TC_BK * 2) >> 4;       // B tile size in 16-byte units
   const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
@@ -587,13 +590,22 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
   const int mh = p.mh, kcpt = p.kc_per_tap, a_stages = p.a_stages, b_stages = p.b_stages;
   const uint32_t bn = (uint32_t)p.bn;
   const bool skip_mma = (p.debug_flags & 2) != 0;     // timing experiment
-  int as = 0, bs = 0, it = 0;
+  int as = 0, bs = 0, it = issuer;
   uint32_t aph = 0, bph = 0;
+  auto skip_tile = [&]() {          // advance the ring positions over a tile handled by the other issuer
+    as += kcpt;
+    while (as >= a_stages) { as -= a_stages; aph ^= 1; }
+    if (!BRES) {
+      bs += 9 * kcpt;
+      while (bs >= b_stages) { bs -= b_stages; bph ^= 1; }
+    }
+  };
   if (BRES) {
     mbar_wait(smem_u32(bres_bar), 0);
     tc_fence_after();
   }
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+  if (issuer == 1) skip_tile();
+  for (int tile = blockIdx.x + issuer * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
     const int buf = it & 1;
     mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((it >> 1) & 1) ^ 1);
     tc_fence_after();
@@ -629,6 +641,7 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
       if (++as == a_stages) { as = 0; aph ^= 1; }
     }
     tc_commit_elect(smem_u32(&tmem_full_bar[buf]));
+    skip_tile();
   }
 }
 
@@ -749,12 +762,13 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer (converged warp, one elected lane issues)
+  } else if (warp == 1 || warp == TC_MMA2_WARP) {
+    // ================================ MMA issuers (converged warps, one elected lane issues)
+    const int issuer = warp == 1 ? 0 : 1;
     if (p.b_resident) slab_mma_loop<true>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar,
-                                          a_base, b_base, tmem_base, num_tiles);
+                                          a_base, b_base, tmem_base, num_tiles, issuer);
     else slab_mma_loop<false>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar, a_base,
-                              b_base, tmem_base, num_tiles);
+                              b_base, tmem_base, num_tiles, issuer);
     __syncwarp();
   } else if (warp >= 2 && warp < 2 + TC_EPI_WARPS) {
     // ================================ epilogue warps

@@ -35,7 +35,7 @@ def launch_list(src, dst, cmd):
             if "lrpx::" in k:
                 ours += t
         f.write(f"\nlrpx kernels: {100 * ours / tot:.1f}% of device time; "
-                f"tc_conv_kernel (all epilogues): {100 * sum(t for k, (c, t) in agg.items() if 'tc_conv_kernel' in k) / tot:.1f}%\n")
+                f"tc_conv_*kernel (all epilogues, forward + chain + decoder GEMMs): {100 * sum(t for k, (c, t) in agg.items() if 'tc_conv' in k) / tot:.1f}%\n")
     print(open(dst).read())
 
 
