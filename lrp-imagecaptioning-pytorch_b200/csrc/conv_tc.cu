@@ -28,7 +28,7 @@ namespace lrpx {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;             // channels per K step (128 bytes of bf16)
-constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_THREADS = 384;          // warps: 0 A/TMA producer, 1 MMA, 2-9 epilogue, 10 B producer, 11 second MMA issuer (slab kernel)
 constexpr int TC_EPI_WARPS = 8;            // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int TC_BPROD_WARP = 2 + TC_EPI_WARPS;
@@ -54,8 +54,8 @@ struct TcParams {
   int mh;            // M halves per CTA tile (1 -> 128 rows, 2 -> 256 rows sharing every B tile)
   int slab_rows;     // rows per slab
   int box0_rows, box1_rows;   // TMA boxes that make up a slab (box1_rows == 0: single box)
-  int slab_pitch;    // bytes between the slabs of a stage (slab_mode 3), multiple of 1024
-  int a_stage_bytes; // bytes of one A stage, multiple of 1024
+  int a_stage_bytes; // bytes of one A stage (= one slab), multiple of 1024
+  int n_issuers;     // MMA issuer warps in use: 2 (one per M half) when mh == 2, else 1
   int a_stages, b_stages;
   int b_resident;    // all B tiles of the layer stay in shared memory for the lifetime of the CTA
   int debug_flags;   // env LRPX_TC_DEBUG: bit 0 = epilogue skips its global loads/stores (timing experiments only)
@@ -566,82 +566,91 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// MMA issue loop of the slab kernel.  Everything loop-invariant is hoisted and the 9 taps x 4 K-steps are unrolled
+// MMA issue loop of the slab kernel.  Everything loop-invariant is hoisted and the taps x 4 K-steps are unrolled
 // so that one MMA costs a handful of integer instructions (measured: ~200 cycles per MMA with the naive loop, which
-// capped the N<=64 layers at 1/6 of the tensor rate).
-template <bool BRES>
+// capped the N<=64 layers at 1/6 of the tensor rate; ~75 cycles with this loop and a converged issuing warp).
+//
+// Two issuer warps, in LOCKSTEP: with mh == 2 issuer j issues the MMAs of M half j (rows [128j, 128j+128) of the
+// tile, TMEM columns [j*bn, (j+1)*bn) of the tile's accumulator buffer).  Both walk every tile, every A stage and
+// every B tile in the same order; the a_empty / b_empty / tmem_full barriers count one tcgen05.commit per issuer,
+// so neither issuer can run more than one ring revolution ahead of the other (mbarrier parity waits are only
+// unambiguous one phase apart — giving the issuers alternate TILES on a shared ring is not safe).
+// With mh == 1 only issuer 0 works (N = 256 MMAs occupy the tensor pipe for 128 cycles, one thread keeps up).
+template <bool BRES, bool MODE3>
 __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full,
                                               uint64_t* b_empty, uint64_t* bres_bar, uint64_t* tmem_full_bar,
                                               uint64_t* tmem_empty_bar, uint32_t a_base, uint32_t b_base,
                                               uint32_t tmem_base, int num_tiles, int issuer) {
-  // Two issuer warps take the CTA's tiles alternately (issuer j owns TMEM buffer j): one thread needs ~75 cycles
-  // per MMA (descriptor moves to uniform registers + issue), which is more than an N <= 64 MMA occupies the pipe.
   const uint32_t idesc = make_idesc(p.bn);
   const uint32_t b16 = ((uint32_t)p.bn * TC_BK * 2) >> 4;       // B tile size in 16-byte units
   const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
-  const uint32_t a_lo_base = desc_lo(a_base), b_lo_base = desc_lo(b_base);
-  uint32_t tap_off[9];                                            // row-shifted view of each tap, 16-byte units
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int dyi = t / 3, dxi = t % 3;
-    tap_off[t] = (p.slab_mode == 1) ? (uint32_t)(dyi * p.wp1 + dxi) * 8u
-                                    : (uint32_t)dyi * ((uint32_t)p.slab_pitch >> 4) + (uint32_t)dxi * 8u;
-  }
-  const int mh = p.mh, kcpt = p.kc_per_tap, a_stages = p.a_stages, b_stages = p.b_stages;
+  const uint32_t row16 = (TC_BK * 2) >> 4;                        // one PF row of 64 channels, 16-byte units
+  const uint32_t dy16 = MODE3 ? 0u : (uint32_t)p.wp1 * row16;      // MODE3: each filter row has its own slab (stage)
+  const int kcpt = p.kc_per_tap, a_stages = p.a_stages, b_stages = p.b_stages;
   const uint32_t bn = (uint32_t)p.bn;
   const bool skip_mma = (p.debug_flags & 2) != 0;     // timing experiment
-  int as = 0, bs = 0, it = issuer;
+  // this issuer's M halves: [h0, h1)
+  const int h0 = p.n_issuers == 2 ? issuer : 0, h1 = p.n_issuers == 2 ? issuer + 1 : p.mh;
+  const uint32_t a_lo_base = desc_lo(a_base) + (uint32_t)h0 * ((TC_BM * TC_BK * 2) >> 4);
+  const uint32_t b_lo_base = desc_lo(b_base);
+  int as = 0, bs = 0, it = 0;
   uint32_t aph = 0, bph = 0;
-  auto skip_tile = [&]() {          // advance the ring positions over a tile handled by the other issuer
-    as += kcpt;
-    while (as >= a_stages) { as -= a_stages; aph ^= 1; }
-    if (!BRES) {
-      bs += 9 * kcpt;
-      while (bs >= b_stages) { bs -= b_stages; bph ^= 1; }
-    }
-  };
   if (BRES) {
     mbar_wait(smem_u32(bres_bar), 0);
     tc_fence_after();
   }
-  if (issuer == 1) skip_tile();
-  for (int tile = blockIdx.x + issuer * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
     mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((it >> 1) & 1) ^ 1);
     tc_fence_after();
-    const uint32_t d_tmem = tmem_base + buf * 256;
+    const uint32_t d_tmem = tmem_base + buf * 256 + (uint32_t)h0 * bn;
     for (int kc = 0; kc < kcpt; ++kc) {
-      mbar_wait(smem_u32(&a_full[as]), aph);
-      tc_fence_after();
-      const uint32_t a_lo0 = a_lo_base + (uint32_t)as * a_stage16;
+      if (!MODE3) {
+        mbar_wait(smem_u32(&a_full[as]), aph);
+        tc_fence_after();
+      }
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        uint32_t b_lo;
-        if (BRES) {
-          b_lo = b_lo_base + (uint32_t)(tap * kcpt + kc) * b16;
-        } else {
-          mbar_wait(smem_u32(&b_full[bs]), bph);
+      for (int dy = 0; dy < 3; ++dy) {
+        if (MODE3) {
+          mbar_wait(smem_u32(&a_full[as]), aph);
           tc_fence_after();
-          b_lo = b_lo_base + (uint32_t)bs * b16;
         }
-        const uint32_t a_lo = a_lo0 + tap_off[tap];
-        for (int h = 0; h < mh && !skip_mma; ++h) {
-          const uint32_t ah = a_lo + (uint32_t)h * ((TC_BM * TC_BK * 2) >> 4);
+        const uint32_t a_row = a_lo_base + (uint32_t)as * a_stage16 + (uint32_t)dy * dy16;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            tc_mma_f16_elect(d_tmem + h * bn, desc_pack(ah + 2 * k), desc_pack(b_lo + 2 * k), idesc,
-                       (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
+        for (int dx = 0; dx < 3; ++dx) {
+          const int tap = dy * 3 + dx;
+          uint32_t b_lo;
+          if (BRES) {
+            b_lo = b_lo_base + (uint32_t)(tap * kcpt + kc) * b16;
+          } else {
+            mbar_wait(smem_u32(&b_full[bs]), bph);
+            tc_fence_after();
+            b_lo = b_lo_base + (uint32_t)bs * b16;
+          }
+          const uint32_t a_lo = a_row + (uint32_t)dx * row16;
+          for (int h = h0; h < h1 && !skip_mma; ++h) {
+            const uint32_t ah = a_lo + (uint32_t)(h - h0) * ((TC_BM * TC_BK * 2) >> 4);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+              tc_mma_f16_elect(d_tmem + (uint32_t)(h - h0) * bn, desc_pack(ah + 2 * k), desc_pack(b_lo + 2 * k), idesc,
+                               (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
+          }
+          if (!BRES) {
+            tc_commit_elect(smem_u32(&b_empty[bs]));
+            if (++bs == b_stages) { bs = 0; bph ^= 1; }
+          }
         }
-        if (!BRES) {
-          tc_commit_elect(smem_u32(&b_empty[bs]));
-          if (++bs == b_stages) { bs = 0; bph ^= 1; }
+        if (MODE3) {
+          tc_commit_elect(smem_u32(&a_empty[as]));
+          if (++as == a_stages) { as = 0; aph ^= 1; }
         }
       }
-      tc_commit_elect(smem_u32(&a_empty[as]));
-      if (++as == a_stages) { as = 0; aph ^= 1; }
+      if (!MODE3) {
+        tc_commit_elect(smem_u32(&a_empty[as]));
+        if (++as == a_stages) { as = 0; aph ^= 1; }
+      }
     }
     tc_commit_elect(smem_u32(&tmem_full_bar[buf]));
-    skip_tile();
   }
 }
 
@@ -655,7 +664,7 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
 // cuts the L2 -> SMEM traffic of A by 9x/(1.2 ... 3x), which is what bounds the 64/128-channel 224^2/112^2 layers.
 // B tiles stream through their own ring (kc-major, tap-minor) or, when the whole layer's B fits (<= 80 KB),
 // stay resident for the lifetime of the persistent CTA.  With mh == 2 every B tile feeds two 128-row MMAs.
-constexpr int TC_A_MAX_STAGES = 4;
+constexpr int TC_A_MAX_STAGES = 6;
 
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -681,17 +690,18 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const int n_slabs = p.slab_mode == 1 ? 1 : 3;
 
   if (threadIdx.x == 0) {
+    // "empty" / "accumulator ready" barriers collect one tcgen05.commit per issuer warp
     for (int s = 0; s < p.a_stages; ++s) {
       mbar_init(smem_u32(&a_full[s]), 1);
-      mbar_init(smem_u32(&a_empty[s]), 1);
+      mbar_init(smem_u32(&a_empty[s]), p.n_issuers);
     }
     for (int s = 0; s < p.b_stages; ++s) {
       mbar_init(smem_u32(&b_full[s]), 1);
-      mbar_init(smem_u32(&b_empty[s]), 1);
+      mbar_init(smem_u32(&b_empty[s]), p.n_issuers);
     }
     mbar_init(smem_u32(&bres_bar), 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+      mbar_init(smem_u32(&tmem_full_bar[b]), p.n_issuers);
       mbar_init(smem_u32(&tmem_empty_bar[b]), TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -714,26 +724,25 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     if (lane == 0) {
       int as = 0;
       uint32_t aph = 0;
-      const uint32_t a_tx = (uint32_t)n_slabs * p.slab_rows * (TC_BK * 2);
+      const uint32_t a_tx = (uint32_t)p.slab_rows * (TC_BK * 2);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.num_n_tiles;
         const int m0 = m_tile * tile_rows;
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
-          mbar_wait(smem_u32(&a_empty[as]), aph ^ 1);
-          const uint32_t fb = smem_u32(&a_full[as]);
-          const uint32_t sa = a_base + (uint32_t)as * p.a_stage_bytes;
-          if (p.debug_flags & 4) {          // timing experiment: no A traffic
-            mbar_arrive(fb);
-          } else {
-            mbar_expect_tx(fb, a_tx);
-            for (int j = 0; j < n_slabs; ++j) {
+          for (int j = 0; j < n_slabs; ++j) {          // one ring stage per slab
+            mbar_wait(smem_u32(&a_empty[as]), aph ^ 1);
+            const uint32_t fb = smem_u32(&a_full[as]);
+            const uint32_t dst = a_base + (uint32_t)as * p.a_stage_bytes;
+            if (p.debug_flags & 4) {          // timing experiment: no A traffic
+              mbar_arrive(fb);
+            } else {
+              mbar_expect_tx(fb, a_tx);
               const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
-              const uint32_t dst = sa + (uint32_t)j * p.slab_pitch;
               tma_load_2d(dst, &tmA0, fb, kc * TC_BK, row0);
               if (p.box1_rows) tma_load_2d(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kc * TC_BK, row0 + p.box0_rows);
             }
+            if (++as == p.a_stages) { as = 0; aph ^= 1; }
           }
-          if (++as == p.a_stages) { as = 0; aph ^= 1; }
         }
       }
     }
@@ -765,10 +774,17 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp == 1 || warp == TC_MMA2_WARP) {
     // ================================ MMA issuers (converged warps, one elected lane issues)
     const int issuer = warp == 1 ? 0 : 1;
-    if (p.b_resident) slab_mma_loop<true>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar,
-                                          a_base, b_base, tmem_base, num_tiles, issuer);
-    else slab_mma_loop<false>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar, a_base,
-                              b_base, tmem_base, num_tiles, issuer);
+    if (issuer < p.n_issuers) {
+#define LRPX_SLAB_LOOP(BRES, MODE3)                                                                                  \
+  slab_mma_loop<BRES, MODE3>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar, a_base, \
+                             b_base, tmem_base, num_tiles, issuer)
+      if (p.b_resident) {
+        if (p.slab_mode == 3) LRPX_SLAB_LOOP(true, true); else LRPX_SLAB_LOOP(true, false);
+      } else {
+        if (p.slab_mode == 3) LRPX_SLAB_LOOP(false, true); else LRPX_SLAB_LOOP(false, false);
+      }
+#undef LRPX_SLAB_LOOP
+    }
     __syncwarp();
   } else if (warp >= 2 && warp < 2 + TC_EPI_WARPS) {
     // ================================ epilogue warps
@@ -885,32 +901,38 @@ static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const 
 }
 
 // Picks the slab-mode configuration (see tc_conv_slab_kernel).  Returns false when nothing fits.
+//   mh = 2 (256-row tiles, one issuer warp per half) whenever two accumulators of the tile fit one TMEM buffer
+//   (bn <= 128); slab_mode 1 when the single slab is the smaller fetch and fits two TMA boxes, else one slab per
+//   filter row; B resident when the whole layer's B fits next to >= 2 (mode 1) / 4 (mode 3) A stages.
 static bool plan_slab(TcParams& p) {
   const int budget = TC_SMEM_BYTES - 1024;
   const int b_bytes = p.bn * TC_BK * 2;
   const long long b_total = (long long)p.taps * p.kc_per_tap * b_bytes;
-  const bool resident = p.num_n_tiles == 1 && b_total <= 80 * 1024;
-  for (int mh = (p.bn <= 128 && !resident) ? 2 : 1; mh >= 1; --mh) {
+  for (int mh = p.bn <= 128 ? 2 : 1; mh >= 1; --mh) {
     const int rows1 = mh * TC_BM + 2 + 2 * p.wp1, rows3 = mh * TC_BM + 2;
     const int mode = (rows1 <= 3 * rows3 && rows1 <= 512) ? 1 : 3;
     const int slab_rows = mode == 1 ? rows1 : rows3;
     const int slab_bytes = ((slab_rows * TC_BK * 2) + 1023) & ~1023;
-    const int a_stage = mode == 1 ? slab_bytes : 3 * slab_bytes;
-    for (int a_stages = 3; a_stages >= 2; --a_stages) {
-      const int left = budget - a_stages * a_stage;
+    const int min_a = mode == 1 ? 2 : 4, max_a = mode == 1 ? 3 : TC_A_MAX_STAGES;
+    const bool want_res = p.num_n_tiles == 1 && b_total <= budget - (long long)min_a * slab_bytes;
+    for (int a_stages = max_a; a_stages >= min_a; --a_stages) {
+      const int left = budget - a_stages * slab_bytes;
       int b_stages = 0;
-      if (resident) {
+      if (want_res) {
         if (left < b_total) continue;
       } else {
         b_stages = left / b_bytes;
         if (b_stages > TC_MAX_STAGES) b_stages = TC_MAX_STAGES;
+        // the B ring has to cover the TMA latency: >= 4 tiles and >= 48 KB in flight unless A is at its minimum
         if (b_stages < 3) continue;
+        if (a_stages > min_a && (b_stages < 4 || b_stages * b_bytes < 48 * 1024)) continue;
       }
       p.slab_mode = mode; p.mh = mh; p.slab_rows = slab_rows;
+      p.n_issuers = mh == 2 ? 2 : 1;
       p.box0_rows = slab_rows < 256 ? slab_rows : 256;
       p.box1_rows = slab_rows - p.box0_rows;
-      p.slab_pitch = slab_bytes; p.a_stage_bytes = a_stage;
-      p.a_stages = a_stages; p.b_stages = b_stages; p.b_resident = resident ? 1 : 0;
+      p.a_stage_bytes = slab_bytes;
+      p.a_stages = a_stages; p.b_stages = b_stages; p.b_resident = want_res ? 1 : 0;
       return true;
     }
   }
@@ -1007,7 +1029,7 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       }
     }
   }
-  p.slab_mode = 0; p.mh = 1;
+  p.slab_mode = 0; p.mh = 1; p.n_issuers = 1;
   p.num_m_tiles = (p.m_total + TC_BM - 1) / TC_BM;
   const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;
   p.stages = (TC_SMEM_BYTES - 1024) / stage_bytes;

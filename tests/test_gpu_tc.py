@@ -42,7 +42,10 @@ def _no_tf32():
 @pytest.mark.parametrize("slab", ["1", "0"])
 @pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 8, 64, 64), (3, 10, 6, 128, 256), (2, 14, 14, 64, 512),
                                             (5, 28, 28, 256, 128), (1, 4, 4, 512, 32), (2, 56, 56, 128, 128),
-                                            (1, 112, 112, 64, 64), (1, 224, 224, 64, 64), (1, 224, 224, 64, 128)])
+                                            (1, 112, 112, 64, 64), (1, 224, 224, 64, 64), (1, 224, 224, 64, 128),
+                                            # >= 3 tiles per persistent CTA (ring phases wrap, both issuer warps busy):
+                                            (8, 112, 112, 128, 64), (2, 224, 224, 64, 64), (2, 224, 224, 64, 32),
+                                            (3, 224, 224, 64, 128), (40, 28, 28, 512, 256)])
 def test_gemm_forward_layout(n, h, w, cin, cout, slab, monkeypatch):
     """slab=1: row-shifted descriptor views into one A slab per channel block (single slab, two-box slab,
     three-slab, B-resident and 256-row tile configurations are all hit by these shapes); slab=0: one TMA tile
@@ -188,3 +191,11 @@ def test_engine_vgg16_224_vs_reference_fixture(golden):
     sp = spearman(a, b)
     print(f"vgg16 224: rel L2 {l2:.3e} spearman {sp:.5f} sumR {float(a.sum()):.6g} vs {float(b.sum()):.6g}")
     assert sp >= 0.99 and l2 <= 5e-2
+    # the same request 6 times in one chunk: every persistent CTA now walks several tiles per layer (accumulator
+    # double-buffering, ring wrap-around, both MMA issuer warps); each copy must reproduce the single-request result
+    # bit for bit (same arithmetic, different tile -> CTA assignment)
+    Q = 6
+    r6 = tgt.flatten(2).transpose(1, 2).contiguous().repeat(Q, 1, 1).to(DEV)
+    heat6 = eng.relevance(st, r6, torch.zeros(Q, dtype=torch.int32, device=DEV), chunk=Q)
+    for q in range(Q):
+        assert torch.equal(heat6[q], heat[0]), f"request {q} of the replicated chunk differs from the single request"
