@@ -29,8 +29,9 @@ namespace lrpx {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;             // channels per K step (128 bytes of bf16)
 constexpr int TC_MAX_STAGES = 12;
-constexpr int TC_THREADS = 384;          // warps: 0 A/TMA producer, 1 MMA, 2-9 epilogue, 10 B producer, 11 second MMA issuer (slab kernel)
-constexpr int TC_EPI_WARPS = 8;            // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int TC_EPI_WARPS = 16;           // four warps per TMEM lane quarter, sharing the tile's 32x32 units round-robin
+// warps: 0 A/TMA producer, 1 MMA, 2..17 epilogue, 18 B producer, 19 second MMA issuer (slab kernel)
+constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 4);
 constexpr int TC_BPROD_WARP = 2 + TC_EPI_WARPS;
 constexpr int TC_MMA2_WARP = TC_BPROD_WARP + 1;
 constexpr int TC_SMEM_BYTES = 220 * 1024;
@@ -41,6 +42,8 @@ struct TcParams {
   int blk;           // (h+1)*(w+1)
   int h, w;          // unpadded spatial size of A's images
   int wp1;           // w + 1
+  uint32_t blk_mul, wp1_mul;   // fast_div multipliers / shifts for blk and wp1
+  int blk_sh, wp1_sh;
   int cin;           // channels of A
   int ncol;          // GEMM N (rows of Wt)
   int bn;            // N tile
@@ -223,7 +226,11 @@ __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
 // ------------------------------------------------------------------------------------------ epilogues
-// One thread owns one accumulator row (= one PF pixel) and walks its columns in chunks of 32.
+// One thread owns one accumulator row (= one PF pixel).  The work of a tile is cut into UNITS of 32 rows (one TMEM
+// lane quarter of one M half) x 32 columns; the four epilogue warps of a lane quarter take the units round-robin.
+// (Measured on the 64-channel 224^2 layer with 8 warps and a row's whole column range per thread: the epilogue warps
+// were busy 100 % of the time at ~8 cycles per instruction and ~450 instructions per 32x64 block — the epilogue, not
+// the tensor pipe, set the tile time.  Hence 16 warps for latency hiding and the lean index arithmetic below.)
 struct RowInfo {
   int row;       // flat PF row
   int e;         // image / explanation block
@@ -233,14 +240,19 @@ struct RowInfo {
   bool valid;    // a real pixel
 };
 
+// n / d for n < 2^31 with the host-prepared multiplier m = ceil(2^sh / d), sh = 31 + ceil(log2 d)
+__device__ __forceinline__ int fast_div(int n, uint32_t m, int sh) {
+  return (int)(((uint64_t)(uint32_t)n * m) >> sh);
+}
+
 __device__ __forceinline__ RowInfo row_info(const TcParams& p, int row) {
   RowInfo r;
   r.row = row;
   r.in_range = row < p.m_total;
   int rr = r.in_range ? row : 0;
-  r.e = rr / p.blk;
+  r.e = fast_div(rr, p.blk_mul, p.blk_sh);
   r.rem = rr - r.e * p.blk;
-  r.a = r.rem / p.wp1;
+  r.a = fast_div(r.rem, p.wp1_mul, p.wp1_sh);
   r.b = r.rem - r.a * p.wp1;
   r.valid = r.in_range && r.a > 0 && r.b > 0;
   return r;
@@ -248,12 +260,22 @@ __device__ __forceinline__ RowInfo row_info(const TcParams& p, int row) {
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+__device__ __forceinline__ void stg_zero32(void* p) {
+  const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  stg_v8(p, z);
+}
+
 // out[row][col..col+32) = bf16(acc * gain[img][rem][col..]);  g = the 64 bytes of gain, loaded by the caller BEFORE it
 // waits on the accumulator so that the global-load latency overlaps the TMEM read
 __device__ __forceinline__ void epi_mul(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32],
                                         const U8 (&g)[2]) {
   if (!r.in_range) return;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * p.out_c + col;
+  if (!r.valid) {          // padding rows of the PF layout stay exactly zero
+    stg_zero32(out);
+    stg_zero32(out + 16);
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     uint32_t ow[8];
@@ -261,74 +283,73 @@ __device__ __forceinline__ void epi_mul(const TcParams& p, const RowInfo& r, int
     for (int k = 0; k < 8; ++k) {
       float a0 = __uint_as_float(v[16 * q + 2 * k]) * bf16_lo(g[q].w[k]);
       float a1 = __uint_as_float(v[16 * q + 2 * k + 1]) * bf16_hi(g[q].w[k]);
-      ow[k] = r.valid ? pack_bf16(a0, a1) : 0u;
+      ow[k] = pack_bf16(a0, a1);
     }
     stg_v8(out + 16 * q, ow);
   }
 }
 
-// tile at pooled resolution; scatter to the 2x2 fine pixels chosen by pool_idx (others get 0)
-__device__ __forceinline__ void epi_mul_unpool(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32],
-                                               const U8 (&g)[2], const U8& sidx) {
+// tile at pooled resolution; 16 columns starting at `col`: scatter to the 2x2 fine pixels chosen by the argmax bytes
+// (the other three get 0).  g = 16 gains (bf16), sidx = 16 argmax bytes.
+__device__ __forceinline__ void epi_mul_unpool16(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[16],
+                                                 const U8& g, const uint4& sidx) {
   if (!r.in_range) return;
   const int wf1 = 2 * p.w + 1;
   const size_t blk_f = (size_t)(2 * p.h + 1) * wf1;
   __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.e * blk_f * p.out_c + col;
-  uint32_t prod[16];   // bf16x2 products: prod[j] = channels 2j, 2j+1
+  uint32_t prod[8];   // bf16x2 products: prod[j] = channels 2j, 2j+1
 #pragma unroll
-  for (int q = 0; q < 2; ++q)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float a0 = __uint_as_float(v[16 * q + 2 * k]) * bf16_lo(g[q].w[k]);
-      float a1 = __uint_as_float(v[16 * q + 2 * k + 1]) * bf16_hi(g[q].w[k]);
-      prod[8 * q + k] = pack_bf16(a0, a1);
-    }
+  for (int k = 0; k < 8; ++k) {
+    float a0 = __uint_as_float(v[2 * k]) * bf16_lo(g.w[k]);
+    float a1 = __uint_as_float(v[2 * k + 1]) * bf16_hi(g.w[k]);
+    prod[k] = r.valid ? pack_bf16(a0, a1) : 0u;
+  }
+  const uint32_t sw[4] = {sidx.x, sidx.y, sidx.z, sidx.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     int fr = 2 * r.a - 1 + (k >> 1), fc = 2 * r.b - 1 + (k & 1);
     if (fr < 0 || fc < 0) continue;
     __nv_bfloat16* dst = outb + ((size_t)fr * wf1 + fc) * p.out_c;
+    uint32_t ow[8];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint32_t ow[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        // channels 16q+2j (low half) and 16q+2j+1 (high half); their argmax bytes sit in word (16q+2j)/4 of sidx
-        const uint32_t sw = sidx.w[4 * q + (j >> 1)];
-        const uint32_t b0 = (sw >> (16 * (j & 1))) & 0xFF, b1 = (sw >> (16 * (j & 1) + 8)) & 0xFF;
-        const uint32_t pv = prod[8 * q + j];
-        ow[j] = !r.valid ? 0u : ((b0 == (uint32_t)k ? (pv & 0xFFFFu) : 0u) | (b1 == (uint32_t)k ? (pv & 0xFFFF0000u) : 0u));
-      }
-      stg_v8(dst + 16 * q, ow);
+    for (int j = 0; j < 8; ++j) {
+      // channels 2j (low half) and 2j+1 (high half); their argmax bytes sit in word j/2 of sidx
+      const uint32_t w4 = sw[j >> 1];
+      const uint32_t b0 = (w4 >> (16 * (j & 1))) & 0xFF, b1 = (w4 >> (16 * (j & 1) + 8)) & 0xFF;
+      const uint32_t pv = prod[j];
+      ow[j] = (b0 == (uint32_t)k ? (pv & 0xFFFFu) : 0u) | (b1 == (uint32_t)k ? (pv & 0xFFFF0000u) : 0u);
     }
+    stg_v8(dst, ow);
   }
 }
 
-// forward + gain: vw = acc of W, vp = acc of W+ (same 32 output channels starting at `ch`)
-__device__ __forceinline__ void epi_fwd_gain(const TcParams& p, const RowInfo& r, int ch, const uint32_t (&vw)[32],
-                                             const uint32_t (&vp)[32]) {
+// forward + gain, 16 output channels starting at `ch`: vw = acc of W, vp = acc of W+
+__device__ __forceinline__ void epi_fwd_gain16(const TcParams& p, const RowInfo& r, int ch, const uint32_t (&vw)[16],
+                                               const uint32_t (&vp)[16]) {
   if (!r.in_range) return;
   __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * p.out_c + ch;
   __nv_bfloat16* gn = reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)r.row * p.out_c + ch;
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    uint32_t aw[8], gw[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float z0 = __uint_as_float(vw[16 * q + 2 * k]), z1 = __uint_as_float(vw[16 * q + 2 * k + 1]);
-      if (p.bias) {
-        z0 += __ldg(p.bias + ch + 16 * q + 2 * k);
-        z1 += __ldg(p.bias + ch + 16 * q + 2 * k + 1);
-      }
-      float a0 = fmaxf(z0, 0.f), a1 = fmaxf(z1, 0.f);
-      float zp0 = __uint_as_float(vp[16 * q + 2 * k]), zp1 = __uint_as_float(vp[16 * q + 2 * k + 1]);
-      float g0 = safe_div(p.gain_mode ? 1.f : a0, zp0), g1 = safe_div(p.gain_mode ? 1.f : a1, zp1);
-      aw[k] = r.valid ? pack_bf16(a0, a1) : 0u;
-      gw[k] = r.valid ? pack_bf16(g0, g1) : 0u;
-    }
-    stg_v8(act + 16 * q, aw);
-    stg_v8(gn + 16 * q, gw);
+  if (!r.valid) {
+    stg_zero32(act);
+    stg_zero32(gn);
+    return;
   }
+  uint32_t aw[8], gw[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float z0 = __uint_as_float(vw[2 * k]), z1 = __uint_as_float(vw[2 * k + 1]);
+    if (p.bias) {
+      z0 += __ldg(p.bias + ch + 2 * k);
+      z1 += __ldg(p.bias + ch + 2 * k + 1);
+    }
+    float a0 = fmaxf(z0, 0.f), a1 = fmaxf(z1, 0.f);
+    float zp0 = __uint_as_float(vp[2 * k]), zp1 = __uint_as_float(vp[2 * k + 1]);
+    float g0 = safe_div(p.gain_mode ? 1.f : a0, zp0), g1 = safe_div(p.gain_mode ? 1.f : a1, zp1);
+    aw[k] = pack_bf16(a0, a1);
+    gw[k] = pack_bf16(g0, g1);
+  }
+  stg_v8(act, aw);
+  stg_v8(gn, gw);
 }
 
 // first layer: acc columns 0..2 = W+^T s, 3..5 = W-^T s  ->  fp32 NCHW heat-map
@@ -346,99 +367,110 @@ __device__ __forceinline__ void epi_input(const TcParams& p, const RowInfo& r, c
   }
 }
 
-// One accumulator row per thread, columns [c_begin, c_end) of the tile (two warps share a row's columns):
-// global loads of gain / argmax first, then TMEM -> registers, epilogue math, global stores.
-// pf_row >= 0: also L2-prefetch the gain row this thread will need for a later tile of the CTA.
+// number of 32-column units per (lane quarter, M half) of a tile
+__device__ __forceinline__ int epi_units_per_half(const TcParams& p, int epi) {
+  if (epi == LRPX_TC_EPI_INPUT) return 1;
+  const int ncols = (epi == LRPX_TC_EPI_FWD_GAIN) ? p.half : p.bn;
+  return ncols >> 5;
+}
+
+// One unit: accumulator row `r` (this thread's), columns [c, c+32) of tile column block n_tile.
+// taddr = TMEM address of column 0 of this row's accumulator (lane quarter, buffer and M half already applied).
+// Global loads of gain / argmax are issued first, then TMEM -> registers, epilogue math, global stores.
 template <int EPI>
-__device__ __forceinline__ void run_epilogue(const TcParams& p, int row, uint32_t taddr, int n_tile, int c_begin,
-                                             int c_end, int pf_row) {
+__device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, uint32_t taddr, int n_tile, int c) {
   if (p.debug_flags & 16) return;      // timing experiment: epilogue only hands the accumulator back
-  RowInfo r = row_info(p, row);
+  RowInfo r = r0;
   if (p.debug_flags & 1) { r.in_range = false; r.valid = false; }
   const int n0 = n_tile * p.bn;
   if (EPI == LRPX_TC_EPI_INPUT) {
-    if (c_begin != 0) return;
     uint32_t v[16];
     TMEM_LD_X16(taddr, v);
     tmem_ld_wait();
     epi_input(p, r, v);
   } else if (EPI == LRPX_TC_EPI_FWD_GAIN) {
-    for (int c = c_begin; c < c_end; c += 32) {
-      uint32_t vw[32], vp[32];
-      TMEM_LD_X32(taddr + c, vw);
-      TMEM_LD_X32(taddr + p.half + c, vp);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint32_t vw[16], vp[16];
+      TMEM_LD_X16(taddr + c + 16 * q, vw);
+      TMEM_LD_X16(taddr + p.half + c + 16 * q, vp);
       tmem_ld_wait();
-      epi_fwd_gain(p, r, n_tile * p.half + c, vw, vp);
+      epi_fwd_gain16(p, r, n_tile * p.half + c + 16 * q, vw, vp);
     }
   } else if (EPI == LRPX_TC_EPI_STORE_F32) {
-    for (int c = c_begin; c < c_end; c += 32) {
-      uint32_t v[32];
-      TMEM_LD_X32(taddr + c, v);
-      tmem_ld_wait();
-      if (r.in_range) {
-        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c);
+    uint32_t v[32];
+    TMEM_LD_X32(taddr + c, v);
+    tmem_ld_wait();
+    if (r.in_range) {
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                               __uint_as_float(v[4 * q + 3]));
-      }
+      for (int q = 0; q < 8; ++q)
+        dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                             __uint_as_float(v[4 * q + 3]));
     }
   } else {   // MUL / MUL_UNPOOL
     size_t goff = 0;
     if (r.valid) {
       const int img = p.row_img ? p.row_img[r.e] : r.e;
-      goff = ((size_t)img * p.blk + r.rem) * p.out_c + n0;
+      goff = ((size_t)img * p.blk + r.rem) * p.out_c + n0 + c;
     }
-    if (pf_row >= 0 && pf_row < p.m_total) {
-      const RowInfo q = row_info(p, pf_row);
-      if (q.valid) {
-        const int img = p.row_img ? p.row_img[q.e] : q.e;
-        const size_t po = ((size_t)img * p.blk + q.rem) * p.out_c + n0 + c_begin;
-        for (int c = 0; c < c_end - c_begin; c += 64) prefetch_l2(p.gain + po + c);      // 128-byte lines
-        if (EPI == LRPX_TC_EPI_MUL_UNPOOL) prefetch_l2(p.pool_idx + po);
-      }
-    }
-    for (int c = c_begin; c < c_end; c += 64) {          // two 32-column chunks per trip: their loads overlap
-      const bool two = c + 32 < c_end;
-      U8 g0[2], g1[2], s0, s1;
+    U8 g[2];
+    uint4 s4[2];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g0[0].w[k] = g0[1].w[k] = g1[0].w[k] = g1[1].w[k] = s0.w[k] = s1.w[k] = 0u;
-      if (r.valid) {
-        g0[0] = ldg_nc_v8(p.gain + goff + c);
-        g0[1] = ldg_nc_v8(p.gain + goff + c + 16);
-        if (two) {
-          g1[0] = ldg_nc_v8(p.gain + goff + c + 32);
-          g1[1] = ldg_nc_v8(p.gain + goff + c + 48);
-        }
-        if (EPI == LRPX_TC_EPI_MUL_UNPOOL) {
-          s0 = ldg_nc_v8(p.pool_idx + goff + c);
-          if (two) s1 = ldg_nc_v8(p.pool_idx + goff + c + 32);
-        }
+    for (int k = 0; k < 8; ++k) g[0].w[k] = g[1].w[k] = 0u;
+    s4[0] = s4[1] = make_uint4(0u, 0u, 0u, 0u);
+    if (r.valid) {
+      g[0] = ldg_nc_v8(p.gain + goff);
+      g[1] = ldg_nc_v8(p.gain + goff + 16);
+      if (EPI == LRPX_TC_EPI_MUL_UNPOOL) {
+        s4[0] = ldg_nc_v4(p.pool_idx + goff);
+        s4[1] = ldg_nc_v4(p.pool_idx + goff + 16);
       }
-      uint32_t v0[32], v1[32];
-      TMEM_LD_X32(taddr + c, v0);
-      if (two) TMEM_LD_X32(taddr + c + 32, v1);
+    }
+    if (EPI == LRPX_TC_EPI_MUL) {
+      uint32_t v[32];
+      TMEM_LD_X32(taddr + c, v);
       tmem_ld_wait();
-      if (EPI == LRPX_TC_EPI_MUL) {
-        epi_mul(p, r, n0 + c, v0, g0);
-        if (two) epi_mul(p, r, n0 + c + 32, v1, g1);
-      } else {
-        epi_mul_unpool(p, r, n0 + c, v0, g0, s0);
-        if (two) epi_mul_unpool(p, r, n0 + c + 32, v1, g1, s1);
+      epi_mul(p, r, n0 + c, v, g);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t v[16];
+        TMEM_LD_X16(taddr + c + 16 * q, v);
+        tmem_ld_wait();
+        epi_mul_unpool16(p, r, n0 + c + 16 * q, v, g[q], s4[q]);
       }
     }
   }
 }
 
-// column range of the tile handled by an epilogue warp (eh = 0/1: which of the two warps of a TMEM lane quarter)
-__device__ __forceinline__ void epi_col_range(const TcParams& p, int epi, int eh, int& c_begin, int& c_end) {
-  const int ncols = (epi == LRPX_TC_EPI_FWD_GAIN) ? p.half : p.bn;
-  if (ncols >= 64) {
-    c_begin = eh * (ncols / 2);
-    c_end = c_begin + ncols / 2;
-  } else {            // too narrow to split: the first warp takes everything
-    c_begin = 0;
-    c_end = eh == 0 ? ncols : 0;
+// L2 prefetch of the gain (and argmax) bytes a unit will read, issued a couple of tiles ahead
+template <int EPI>
+__device__ __forceinline__ void epi_prefetch_unit(const TcParams& p, int row, int n_tile, int c) {
+  if (EPI != LRPX_TC_EPI_MUL && EPI != LRPX_TC_EPI_MUL_UNPOOL) return;
+  if (row >= p.m_total) return;
+  const RowInfo q = row_info(p, row);
+  if (!q.valid) return;
+  const int img = p.row_img ? p.row_img[q.e] : q.e;
+  const size_t po = ((size_t)img * p.blk + q.rem) * p.out_c + n_tile * p.bn + c;
+  prefetch_l2(p.gain + po);                                   // 32 columns of bf16 = 64 bytes: one line
+  if (EPI == LRPX_TC_EPI_MUL_UNPOOL) prefetch_l2(p.pool_idx + po);
+}
+
+// All units of one tile that belong to this epilogue warp.  sub = 0..3: which of the four warps of the lane quarter.
+template <int EPI>
+__device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_base /* tile row 0 + quarter*32 + lane */,
+                                                  uint32_t taddr_q /* lane quarter + buffer */, int n_tile, int sub,
+                                                  int mh, int pf_row_base /* same for the prefetched tile, or -1 */) {
+  const int uph = epi_units_per_half(p, EPI);
+  const int n_units = mh * uph;
+  int h_cached = -1;
+  RowInfo r{};
+  for (int u = sub; u < n_units; u += TC_EPI_WARPS / 4) {
+    const int h = u / uph, c = (u - h * uph) << 5;
+    if (h != h_cached) { r = row_info(p, row_base + h * TC_BM); h_cached = h; }
+    if (pf_row_base >= 0) epi_prefetch_unit<EPI>(p, pf_row_base + h * TC_BM, n_tile, c);
+    epi_unit<EPI>(p, r, taddr_q + (uint32_t)(h * p.bn), n_tile, c);
   }
 }
 
@@ -549,9 +581,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(smem_u32(&tmem_full_bar[buf]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
-      int c_begin, c_end;
-      epi_col_range(p, EPI, (warp - 2) >> 2, c_begin, c_end);
-      run_epilogue<EPI>(p, m_tile * TC_BM + quarter * 32 + lane, taddr, n_tile, c_begin, c_end, -1);
+      run_epilogue_tile<EPI>(p, m_tile * TC_BM + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, 1, -1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
@@ -796,15 +826,11 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
       mbar_wait(smem_u32(&tmem_full_bar[buf]), acc_phase);
       tc_fence_after();
-      int c_begin, c_end;
-      epi_col_range(p, EPI, (warp - 2) >> 2, c_begin, c_end);
       const int tile_pf = tile + 2 * (int)gridDim.x;      // L2 prefetch distance: two of this CTA's tiles ahead
-      for (int h = 0; h < p.mh; ++h) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + h * p.bn;
-        const int pf_row = (tile_pf < num_tiles && tile_pf % p.num_n_tiles == n_tile)
-                               ? (tile_pf / p.num_n_tiles) * tile_rows + h * TC_BM + quarter * 32 + lane : -1;
-        run_epilogue<EPI>(p, m_tile * tile_rows + h * TC_BM + quarter * 32 + lane, taddr, n_tile, c_begin, c_end, pf_row);
-      }
+      const int pf_row = (tile_pf < num_tiles && tile_pf % p.num_n_tiles == n_tile)
+                             ? (tile_pf / p.num_n_tiles) * tile_rows + quarter * 32 + lane : -1;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
+      run_epilogue_tile<EPI>(p, m_tile * tile_rows + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh, pf_row);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
@@ -965,6 +991,16 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
   TcParams p{};
   p.h = a->h; p.w = a->w; p.wp1 = a->w + 1;
   p.blk = (a->h + 1) * (a->w + 1);
+  {
+    auto magic = [](int d, uint32_t& mul, int& sh) {      // n / d == (n * mul) >> sh for 0 <= n < 2^31
+      int s = 0;
+      while ((1LL << s) < d) ++s;
+      sh = 31 + s;
+      mul = (uint32_t)((((unsigned long long)1 << sh) + (unsigned long long)d - 1) / (unsigned long long)d);
+    };
+    magic(p.blk, p.blk_mul, p.blk_sh);
+    magic(p.wp1, p.wp1_mul, p.wp1_sh);
+  }
   long long m_total = (long long)a->n_img * p.blk;
   LRPX_CHECK_ARG(m_total < (1LL << 31) - 4096, "too many pixel rows for one call");
   p.m_total = (int)m_total;

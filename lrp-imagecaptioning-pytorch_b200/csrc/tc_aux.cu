@@ -38,17 +38,22 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* _
 
 // ---------------------------------------------------------------- first layer (cin = 3), CUDA cores
 // lane = 4 pixels x 8 channel groups of 8 channels: a warp writes 4 contiguous 128-byte PF rows (cout = 64).
+// Shared memory holds W, W+ and W- (transposed, [27][cout]) so that one (tap, channel pair) costs three packed
+// fma.rn.f32x2: z += w*x, z+ += w+*x+, z+ += w-*x-  (lrp_modules.py:81-84 for the mixed-sign input).
 template <int CG>   // channel groups per pixel = cout / 8
 __global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, uint4* __restrict__ act,
                                                         uint4* __restrict__ gain, int n, int h, int wd) {
-  extern __shared__ float ws[];        // [27][cout] transposed weights, then bias[cout]
-  const int cout = CG * 8;
+  extern __shared__ __align__(16) float ws[];        // [3][27][cout] (w, w+, w-), then bias[cout]
+  constexpr int cout = CG * 8;
   for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
     int k = i / cout, co = i % cout;
-    ws[i] = w[co * 27 + k];            // k = (ci, r, s) of (cout,3,3,3)
+    float v = w[co * 27 + k];            // k = (ci, r, s) of (cout,3,3,3)
+    ws[i] = v;
+    ws[27 * cout + i] = fmaxf(v, 0.f);
+    ws[2 * 27 * cout + i] = fminf(v, 0.f);
   }
-  for (int i = threadIdx.x; i < cout; i += blockDim.x) ws[27 * cout + i] = bias ? bias[i] : 0.f;
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) ws[3 * 27 * cout + i] = bias ? bias[i] : 0.f;
   __syncthreads();
   const int wp1 = wd + 1, blk = (h + 1) * wp1;
   const long long total = (long long)n * blk * CG;
@@ -61,9 +66,12 @@ __global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict_
     uint4 oa = make_uint4(0, 0, 0, 0), og = make_uint4(0, 0, 0, 0);
     if (a > 0 && b > 0) {
       int y = a - 1, xx = b - 1;
-      float z[8], zp[8];
+      float2 z[4], zp[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { z[j] = ws[27 * cout + cg * 8 + j]; zp[j] = 0.f; }
+      for (int j = 0; j < 4; ++j) {
+        z[j] = make_float2(ws[3 * 27 * cout + cg * 8 + 2 * j], ws[3 * 27 * cout + cg * 8 + 2 * j + 1]);
+        zp[j] = make_float2(0.f, 0.f);
+      }
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
@@ -73,23 +81,30 @@ __global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict_
             int yy = y + r - 1, xs = xx + s - 1;
             float xv = 0.f;
             if (yy >= 0 && yy < h && xs >= 0 && xs < wd) xv = __ldg(x + (((size_t)img * 3 + ci) * h + yy) * wd + xs);
-            float xp = fmaxf(xv, 0.f), xn = fminf(xv, 0.f);
-            const float4* wr = reinterpret_cast<const float4*>(ws + ((ci * 3 + r) * 3 + s) * cout + cg * 8);
-            float4 w0 = wr[0], w1 = wr[1];
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const float2 x2 = make_float2(xv, xv);
+            const float2 xp2 = make_float2(fmaxf(xv, 0.f), fmaxf(xv, 0.f));
+            const float2 xn2 = make_float2(fminf(xv, 0.f), fminf(xv, 0.f));
+            const int k = (ci * 3 + r) * 3 + s;
+            const float4* w4 = reinterpret_cast<const float4*>(ws + k * cout + cg * 8);
+            const float4* p4 = reinterpret_cast<const float4*>(ws + (27 + k) * cout + cg * 8);
+            const float4* n4 = reinterpret_cast<const float4*>(ws + (54 + k) * cout + cg * 8);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              z[j] = fmaf(wv[j], xv, z[j]);
-              zp[j] = fmaf(fmaxf(wv[j], 0.f), xp, zp[j]);
-              zp[j] = fmaf(fminf(wv[j], 0.f), xn, zp[j]);
+            for (int q = 0; q < 2; ++q) {
+              const float4 wv = w4[q], pv = p4[q], nv = n4[q];
+              z[2 * q] = __ffma2_rn(make_float2(wv.x, wv.y), x2, z[2 * q]);
+              z[2 * q + 1] = __ffma2_rn(make_float2(wv.z, wv.w), x2, z[2 * q + 1]);
+              zp[2 * q] = __ffma2_rn(make_float2(pv.x, pv.y), xp2, zp[2 * q]);
+              zp[2 * q + 1] = __ffma2_rn(make_float2(pv.z, pv.w), xp2, zp[2 * q + 1]);
+              zp[2 * q] = __ffma2_rn(make_float2(nv.x, nv.y), xn2, zp[2 * q]);
+              zp[2 * q + 1] = __ffma2_rn(make_float2(nv.z, nv.w), xn2, zp[2 * q + 1]);
             }
           }
       uint32_t pa[4], pg[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float a0 = fmaxf(z[2 * j], 0.f), a1 = fmaxf(z[2 * j + 1], 0.f);
+        float a0 = fmaxf(z[j].x, 0.f), a1 = fmaxf(z[j].y, 0.f);
         __nv_bfloat162 ta = __floats2bfloat162_rn(a0, a1);
-        __nv_bfloat162 tg = __floats2bfloat162_rn(safe_div(a0, zp[2 * j]), safe_div(a1, zp[2 * j + 1]));
+        __nv_bfloat162 tg = __floats2bfloat162_rn(safe_div(a0, zp[j].x), safe_div(a1, zp[j].y));
         pa[j] = *reinterpret_cast<uint32_t*>(&ta);
         pg[j] = *reinterpret_cast<uint32_t*>(&tg);
       }
@@ -254,7 +269,7 @@ int lrpx_tc_first_fwd(const float* x, const float* w, const float* bias, void* a
   LRPX_CHECK_ARG(x && w && act && gain && n > 0 && h > 0 && wd > 0, "bad argument");
   LRPX_CHECK_ARG(cout == 64 || cout == 32 || cout == 16 || cout == 8, "cout must be 8, 16, 32 or 64");
   long long total = (long long)n * (h + 1) * (wd + 1) * (cout / 8);
-  size_t smem = (size_t)(27 * cout + cout) * sizeof(float);
+  size_t smem = (size_t)(3 * 27 * cout + cout) * sizeof(float);
   cudaStream_t st = as_stream(stream);
   int grid = grid_for(total);
   switch (cout) {
