@@ -131,25 +131,21 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Warp-converged variants: the WHOLE warp executes the instruction stream with uniform operands and one elected lane
-// issues (elect.sync predicate).  Keeping the issuing warp converged lets ptxas keep descriptors in uniform
-// registers instead of wrapping every UTCHMMA in an elect/branch loop (what a `if (lane == 0)` region compiles to).
-__device__ __forceinline__ void tc_mma_f16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                 uint32_t accumulate) {
+// elect.sync as a C++ predicate.  ptxas recognises `if (elect_one()) { ... }` as a single-thread region whose
+// values are warp-uniform: descriptors then live in uniform registers and are advanced with UIADD3, and a
+// tcgen05.mma / UTMALDG costs ~3 SASS instructions.  (Measured alternatives on B200: an `if (lane == 0)` region wraps
+// every UTCHMMA in an ELECT/branch loop, ~200 cycles per MMA; elect.sync predicates inside the asm statement cost
+// VOTEU + 6 R2UR.BROADCAST per MMA, ~50 cycles per MMA plus ~500 per ring stage.)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0, laneid = 0;
   asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
-      : "memory");
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -519,7 +515,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ================================ TMA producer (one thread)
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -541,7 +537,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (one thread)
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(p.bn);
       const uint32_t stage16 = stage_bytes >> 4;
       const uint32_t a_lo_base = desc_lo(smem_base), b_lo_base = desc_lo(smem_base + TC_A_BYTES);
@@ -606,11 +602,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // so neither issuer can run more than one ring revolution ahead of the other (mbarrier parity waits are only
 // unambiguous one phase apart — giving the issuers alternate TILES on a shared ring is not safe).
 // With mh == 1 only issuer 0 works (N = 256 MMAs occupy the tensor pipe for 128 cycles, one thread keeps up).
-template <bool BRES, bool MODE3>
+template <bool BRES, bool MODE3, int ISSUER>
 __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full,
                                               uint64_t* b_empty, uint64_t* bres_bar, uint64_t* tmem_full_bar,
                                               uint64_t* tmem_empty_bar, uint32_t a_base, uint32_t b_base,
-                                              uint32_t tmem_base, int num_tiles, int issuer) {
+                                              uint32_t tmem_base, int num_tiles) {
+  // ISSUER is a template parameter (not a value derived from threadIdx) so that ptxas can prove every descriptor
+  // warp-uniform and keep it in uniform registers
+  constexpr int issuer = ISSUER;
   const uint32_t idesc = make_idesc(p.bn);
   const uint32_t b16 = ((uint32_t)p.bn * TC_BK * 2) >> 4;       // B tile size in 16-byte units
   const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
@@ -662,25 +661,25 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
             const uint32_t ah = a_lo + (uint32_t)(h - h0) * ((TC_BM * TC_BK * 2) >> 4);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)
-              tc_mma_f16_elect(d_tmem + (uint32_t)(h - h0) * bn, desc_pack(ah + 2 * k), desc_pack(b_lo + 2 * k), idesc,
+              tc_mma_f16(d_tmem + (uint32_t)(h - h0) * bn, desc_pack(ah + 2 * k), desc_pack(b_lo + 2 * k), idesc,
                                (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
           }
           if (!BRES) {
-            tc_commit_elect(smem_u32(&b_empty[bs]));
+            tc_commit(smem_u32(&b_empty[bs]));
             if (++bs == b_stages) { bs = 0; bph ^= 1; }
           }
         }
         if (MODE3) {
-          tc_commit_elect(smem_u32(&a_empty[as]));
+          tc_commit(smem_u32(&a_empty[as]));
           if (++as == a_stages) { as = 0; aph ^= 1; }
         }
       }
       if (!MODE3) {
-        tc_commit_elect(smem_u32(&a_empty[as]));
+        tc_commit(smem_u32(&a_empty[as]));
         if (++as == a_stages) { as = 0; aph ^= 1; }
       }
     }
-    tc_commit_elect(smem_u32(&tmem_full_bar[buf]));
+    tc_commit(smem_u32(&tmem_full_bar[buf]));
   }
 }
 
@@ -751,7 +750,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
   if (warp == 0) {
     // ================================ A producer (one thread)
-    if (lane == 0) {
+    if (elect_one()) {
       int as = 0;
       uint32_t aph = 0;
       const uint32_t a_tx = (uint32_t)p.slab_rows * (TC_BK * 2);
@@ -778,7 +777,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
   } else if (warp == TC_BPROD_WARP) {
     // ================================ B producer (one thread)
-    if (lane == 0) {
+    if (elect_one()) {
       if (p.b_resident) {
         const uint32_t bb = smem_u32(&bres_bar);
         mbar_expect_tx(bb, (uint32_t)(p.taps * p.kc_per_tap) * b_bytes);
@@ -802,12 +801,18 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
     }
   } else if (warp == 1 || warp == TC_MMA2_WARP) {
-    // ================================ MMA issuers (converged warps, one elected lane issues)
+    // ================================ MMA issuers (one elected thread per issuer warp)
     const int issuer = warp == 1 ? 0 : 1;
-    if (issuer < p.n_issuers) {
-#define LRPX_SLAB_LOOP(BRES, MODE3)                                                                                  \
-  slab_mma_loop<BRES, MODE3>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar, a_base, \
-                             b_base, tmem_base, num_tiles, issuer)
+    if (issuer < p.n_issuers && elect_one()) {
+#define LRPX_SLAB_LOOP(BRES, MODE3)                                                                                   \
+  do {                                                                                                                \
+    if (issuer == 0)                                                                                                  \
+      slab_mma_loop<BRES, MODE3, 0>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar,    \
+                                    a_base, b_base, tmem_base, num_tiles);                                            \
+    else                                                                                                              \
+      slab_mma_loop<BRES, MODE3, 1>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar,    \
+                                    a_base, b_base, tmem_base, num_tiles);                                            \
+  } while (0)
       if (p.b_resident) {
         if (p.slab_mode == 3) LRPX_SLAB_LOOP(true, true); else LRPX_SLAB_LOOP(true, false);
       } else {
@@ -934,7 +939,10 @@ static bool plan_slab(TcParams& p) {
   const int budget = TC_SMEM_BYTES - 1024;
   const int b_bytes = p.bn * TC_BK * 2;
   const long long b_total = (long long)p.taps * p.kc_per_tap * b_bytes;
-  for (int mh = p.bn <= 128 ? 2 : 1; mh >= 1; --mh) {
+  const char* env_mh = getenv("LRPX_TC_MH");             // experiment switches (timing probes only)
+  const char* env_iss = getenv("LRPX_TC_ISSUERS");
+  const int mh_max = (env_mh && env_mh[0] == '1') ? 1 : 2;
+  for (int mh = p.bn <= 128 ? mh_max : 1; mh >= 1; --mh) {
     const int rows1 = mh * TC_BM + 2 + 2 * p.wp1, rows3 = mh * TC_BM + 2;
     const int mode = (rows1 <= 3 * rows3 && rows1 <= 512) ? 1 : 3;
     const int slab_rows = mode == 1 ? rows1 : rows3;
@@ -954,7 +962,7 @@ static bool plan_slab(TcParams& p) {
         if (a_stages > min_a && (b_stages < 4 || b_stages * b_bytes < 48 * 1024)) continue;
       }
       p.slab_mode = mode; p.mh = mh; p.slab_rows = slab_rows;
-      p.n_issuers = mh == 2 ? 2 : 1;
+      p.n_issuers = (mh == 2 && !(env_iss && env_iss[0] == '1')) ? 2 : 1;
       p.box0_rows = slab_rows < 256 ? slab_rows : 256;
       p.box1_rows = slab_rows - p.box0_rows;
       p.a_stage_bytes = slab_bytes;

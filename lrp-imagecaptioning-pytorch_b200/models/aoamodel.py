@@ -248,6 +248,41 @@ class AOAModel(nn.Module):
         return seq, seq_logprobs, max_length
 
 
+class AOAModelBU(AOAModel):
+    """reference :1779-2400 — the AoA decoder on bottom-up region features (B, 36, 2048): ``Linear(2048, hidden)``
+    projector (:1797), global feature = mean of the projected regions (:1845).  ``beam_search`` (:2059-2135, default
+    length 30), ``get_lrp_weight_step`` (:2235-2264), ``forwardlrp_context`` (:2266-2310) and ``sample_lrp``
+    (:2312-2400) are the parent's code over ``_encode``."""
+
+    def __init__(self, embed_dim, hidden_dim, num_head, vocab_size, encoder_type):
+        nn.Module.__init__(self)
+        self.embed_dim, self.hidden_dim, self.vocab_size = embed_dim, hidden_dim, vocab_size
+        self.encoder_type, self.num_head = encoder_type, num_head
+        if hidden_dim % num_head != 0:
+            raise TypeError("the number of head should be dividable by the hidden dim")
+        self.dropout = nn.Dropout(0.3)
+        self.encoder_raw_dim = 2048
+        self.img_projector = nn.Linear(self.encoder_raw_dim, self.hidden_dim)
+        self.embedding = nn.Embedding(vocab_size, embed_dim)
+        self.LanguageLSTM = nn.LSTMCell(hidden_dim + embed_dim, hidden_dim)
+        self.decoder_k_proj = nn.Linear(hidden_dim, hidden_dim)
+        self.decoder_v_proj = nn.Linear(hidden_dim, hidden_dim)
+        self.decoder_multihead_attention = MultiHeadedDotAttention(num_head=num_head, hidden_dim=hidden_dim,
+                                                                   project_k_v_flag=False, norm_q=False, aoa=False)
+        self.decoder_aoa_linear_gate = nn.Linear(hidden_dim, hidden_dim)
+        self.decoder_aoa_linear = nn.Linear(hidden_dim, hidden_dim)
+        self.fc = nn.Linear(hidden_dim, vocab_size)
+        self.relu = nn.ReLU()
+        self._stop_cache = {}
+
+    def _encode(self, images_features):
+        proj = self.relu(self.img_projector(images_features)).contiguous()     # (bs, regions, hidden)
+        return images_features, proj, torch.mean(proj, dim=1)
+
+    def beam_search(self, images_features, word_map, beam_size=3, max_cap_length=30):
+        return AOAModel.beam_search(self, images_features, word_map, beam_size, max_cap_length)
+
+
 class ExplainAOAAttention(ExplainGridTDAttention):
     """reference :748-1254."""
 

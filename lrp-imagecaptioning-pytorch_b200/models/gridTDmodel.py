@@ -365,6 +365,39 @@ class GridTDModel(nn.Module):
         return seq, seq_logprobs, max_length
 
 
+class GridTDModelBU(GridTDModel):
+    """reference :1863-2478 — the same decoder on bottom-up region features (B, 36, 2048) instead of images: the
+    projector is a ``Linear(2048, hidden)`` over the regions, the global feature is the mean of the PROJECTED regions
+    through ``Linear(hidden, embed)`` (:1878-1879, :1911-1916).  ``forward`` / ``beam_search`` / ``get_lrp_weight_step``
+    (:2314-2343) / ``forwardlrp_context`` (:2345-2397) / ``sample_lrp`` (:2399-2478) are the parent's code over
+    ``_encode``; state_dict keys match the reference's (there is no ``img_encoder``)."""
+
+    def __init__(self, embed_dim, hidden_dim, vocab_size, encoder_type, n_region=36):
+        nn.Module.__init__(self)
+        self.embed_dim = embed_dim
+        self.hidden_dim = hidden_dim
+        self.vocab_size = vocab_size
+        self.encoder_type = encoder_type
+        self.dropout = nn.Dropout(0.5)
+        self.encoder_raw_dim = 2048
+        self.img_projector = nn.Linear(self.encoder_raw_dim, self.hidden_dim)
+        self.global_img_feature_proj = nn.Linear(self.hidden_dim, self.embed_dim)
+        self.LanguageLSTM = nn.LSTMCell(2 * hidden_dim, hidden_dim)
+        self.AdaLSTM = AdaptiveLSTMCell(embed_dim * 2 + hidden_dim, hidden_dim)
+        self.AdaAttention = AdaptiveAttention(self.hidden_dim, n_region)
+        self.embedding = nn.Embedding(vocab_size, embed_dim)
+        self.fc = nn.Linear(hidden_dim, vocab_size)
+        self.relu = nn.ReLU()
+        self._stop_cache = {}
+
+    def _encode(self, images_features):
+        proj = self.relu(self.img_projector(images_features))                 # (bs, regions, hidden)
+        global_img_feature = self.relu(self.global_img_feature_proj(torch.mean(proj, dim=1)))
+        if global_img_feature.dim() == 1:
+            global_img_feature = global_img_feature.unsqueeze(0)
+        return images_features, proj.contiguous().transpose(1, 2), global_img_feature     # (bs, hidden, regions)
+
+
 # ----------------------------------------------------------------------------------------------------
 class ExplainGridTDAttention(object):
     """reference :705-1211.  ``precision``: 'bf16' = tcgen05 encoder chain (VGG encoders), 'fp32' = the fp32

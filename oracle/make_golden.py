@@ -298,13 +298,52 @@ def golden_tune(ns):
          predictions=pred, weighted_predictions=wpred, max_length=int(maxlen))
 
 
+END_BIAS = float(os.environ.get("END_BIAS", "0.17"))   # added to the <end> logit bias of the BU fixtures
+
+
+def golden_tune_bu(ns):
+    """Bottom-up twins (gridTDmodel.py:1863-2478, aoamodel.py:1779-2400) on 36 x 2048 region features:
+    forwardlrp_context, sample_lrp (greedy) and beam_search(beam_size=3) of the reference itself.  The <end> logit
+    gets a positive bias so that beams do finish (complete / incomplete bookkeeping, bit-exact beam indices)."""
+    V, H, E, B, L = 60, 64, 32, 3, 6
+    stop = synth.stop_mask(V)
+    wm, rev = _rev_word_map(V, stop)
+    feats = synth.bu_features(83, B)
+    g = torch.Generator().manual_seed(84)
+    caps = torch.randint(1, V - 4, (B, L), generator=g)
+    caps[:, 0] = V - 2
+    caplens = torch.tensor([L, L - 1, L])
+    out = dict(V=V, H=H, E=E, end_bias=END_BIAS, seeds=np.array([81, 82, 83, 84]), caps=caps, caplens=caplens, stop=stop)
+    for tag, make, state in (("gridtd", lambda: ns.gridTDmodel.GridTDModelBU(E, H, V, "bu"), synth.gridtd_bu_state(81, V, H, E)),
+                             ("aoa", lambda: ns.aoamodel.AOAModelBU(E, H, 8, V, "bu"), synth.aoa_bu_state(82, V, H, E))):
+        with quiet():
+            m = make()
+        state["fc.bias"][V - 1] += END_BIAS
+        m.load_state_dict(state, strict=True)
+        m.eval()
+        with torch.no_grad():
+            pred, wpred, maxlen = m.forwardlrp_context(feats, caps, caplens, rev)
+            seq, seq_lp, _ = m.sample_lrp(feats, rev, wm, caplens, {"sample_method": "greedy"})
+            beams = []
+            for b in range(B):
+                for bs in (1, 3):
+                    _, sen_idx = m.beam_search(feats[b:b + 1], wm, beam_size=bs)
+                    beams.append(np.array(sen_idx + [-1] * (40 - len(sen_idx)), dtype=np.int64))
+        out.update({f"{tag}_predictions": pred, f"{tag}_weighted_predictions": wpred, f"{tag}_max_length": int(maxlen),
+                    f"{tag}_seq": seq, f"{tag}_seq_logprobs": seq_lp, f"{tag}_beams": np.stack(beams)})
+    save("tune_bu", **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     os.makedirs("/tmp/lrpx_ref", exist_ok=True)
     ns = ref_shim.load_reference()
     torch.manual_seed(0)
+    only = set(sys.argv[1:])          # optional: names of the generators to (re)run
     for fn in (golden_rules, golden_sequential_small, golden_vgg16, golden_resnet, golden_gridtd_decoder,
-               golden_aoa_decoder, golden_lrp_weights, golden_tune):
+               golden_aoa_decoder, golden_lrp_weights, golden_tune, golden_tune_bu):
+        if only and fn.__name__ not in only:
+            continue
         print(fn.__name__)
         fn(ns)
 

@@ -95,6 +95,29 @@ def aoa_decoder_state(seed: int, V: int, H: int, E: int, C: int = 512):
     return sd
 
 
+def gridtd_bu_state(seed: int, V: int, H: int, E: int, n_region: int = 36, C: int = 2048):
+    """GridTDModelBU (gridTDmodel.py:1868-1886): Linear projector over C-d regions, global projection hidden -> embed."""
+    sd = gridtd_decoder_state(seed, V, H, E, C=C, n_pixel=n_region)
+    sd["img_projector.weight"] = sd["img_projector.weight"].reshape(H, C).clone()
+    g = _gen(seed + 100003)
+    for k in ("global_img_feature_proj.weight", "global_img_feature_proj.bias"):
+        del sd[k]
+    _linear(g, sd, "global_img_feature_proj", E, H)
+    return sd
+
+
+def aoa_bu_state(seed: int, V: int, H: int, E: int, C: int = 2048):
+    """AOAModelBU (aoamodel.py:1783-1806): Linear projector over C-d regions."""
+    sd = aoa_decoder_state(seed, V, H, E, C=C)
+    sd["img_projector.weight"] = sd["img_projector.weight"].reshape(H, C).clone()
+    return sd
+
+
+def bu_features(seed: int, n: int, n_region: int = 36, C: int = 2048):
+    """Synthetic bottom-up region features, rand(n, 36, 2048)."""
+    return torch.rand(n, n_region, C, generator=_gen(seed))
+
+
 def resnet_state(seed: int, layers: Sequence[int] = (1, 1, 1, 1), randomize_bn: bool = True):
     """Bottleneck ResNet up to layer4 (resnet.py:143-239), incl. the unused fc head."""
     g = _gen(seed)

@@ -216,3 +216,27 @@ def test_batch_pipeline_graph_equals_eager_and_single_image_api(tmp_path):
             assert_close(hs[t][0], heat_e[b * T + t], rtol=1e-3, atol=1e-6 + 1e-3 * float(heat_e[b * T + t].abs().max()),
                          what=f"image {b} word {t}")
             assert_close(ws[t], words_e[b * T + t, :t + 1], rtol=1e-3, atol=1e-4, what=f"words {b},{t}")
+
+
+def test_bu_twins_forwardlrp_and_sample_lrp_vs_reference_fixture(golden):
+    """GridTDModelBU / AOAModelBU (36 x 2048 bottom-up features): forwardlrp_context predictions and LRP-weighted
+    predictions vs the reference's own outputs; greedy sample_lrp word indices bit-exact."""
+    from test_models_cpu import _bu_models
+    g = golden("tune_bu")
+    models, V, s = _bu_models(g)
+    wm = synth.word_map(V)
+    rev = {v: k for k, v in wm.items()}
+    for i in range(V):
+        if bool(g["stop"][i]) and rev[i].startswith("w"):
+            rev[i] = "the"
+    feats = synth.bu_features(s[2], 3).to(DEV)
+    for tag, m in models.items():
+        m.to(DEV)
+        with torch.no_grad():
+            pred, wpred, maxlen = m.forwardlrp_context(feats, g["caps"].to(DEV), g["caplens"], rev)
+            seq, seq_lp, _ = m.sample_lrp(feats, rev, wm, g["caplens"], {"sample_method": "greedy"})
+        assert maxlen == int(g[f"{tag}_max_length"])
+        assert_close(pred, g[f"{tag}_predictions"], rtol=1e-4, atol=1e-5, what=f"{tag} BU predictions")
+        assert_close(wpred, g[f"{tag}_weighted_predictions"], rtol=1e-4, atol=1e-5, what=f"{tag} BU weighted predictions")
+        assert torch.equal(seq.cpu(), g[f"{tag}_seq"]), (tag, seq.cpu(), g[f"{tag}_seq"])
+        assert_close(seq_lp, g[f"{tag}_seq_logprobs"], rtol=1e-4, atol=1e-5, what=f"{tag} BU sample log-probs")

@@ -102,3 +102,35 @@ def test_aoa_explainer_forward_matches_reference_fixture(golden, tmp_path, name)
     want = torch.zeros_like(got)
     want[:, sl] = ost["value"][:, sl] * ost["alpha"][t][hd][:, None] * (r_ctx[sl] / O.stab(ost["ctx"][t][sl]))[None, :]
     assert_close(got, want, what="lrp_mha")
+
+
+def _bu_models(g):
+    """The bottom-up twins with the fixture's synthetic weights (incl. its <end> bias)."""
+    from models import gridTDmodel as G, aoamodel as A
+    V, H, E = int(g["V"]), int(g["H"]), int(g["E"])
+    s = g["seeds"].tolist()
+    out = {}
+    for tag, m, sd in (("gridtd", G.GridTDModelBU(E, H, V, "bu"), synth.gridtd_bu_state(s[0], V, H, E)),
+                       ("aoa", A.AOAModelBU(E, H, 8, V, "bu"), synth.aoa_bu_state(s[1], V, H, E))):
+        sd["fc.bias"][V - 1] += float(g["end_bias"])
+        m.load_state_dict(sd, strict=True)          # key-for-key the reference's state_dict layout
+        out[tag] = m.eval()
+    return out, V, s
+
+
+def test_bu_beam_search_indices_bit_exact_vs_reference(golden):
+    """AOAModelBU / GridTDModelBU.beam_search on 36 x 2048 region features (BASELINE config 3: beam size 3): the
+    word indices must equal the reference's own output bit for bit (finished and unfinished beams both occur)."""
+    g = golden("tune_bu")
+    models, V, s = _bu_models(g)
+    wm = synth.word_map(V)
+    feats = synth.bu_features(s[2], 3)
+    for tag, m in models.items():
+        ref = g[f"{tag}_beams"]
+        row = 0
+        for b in range(3):
+            for bs in (1, 3):
+                _, sen_idx = m.beam_search(feats[b:b + 1], wm, beam_size=bs)
+                want = [int(v) for v in ref[row] if int(v) >= 0]
+                assert sen_idx == want, (tag, b, bs, sen_idx, want)
+                row += 1
