@@ -213,6 +213,45 @@ int lrpx_fc_lrp_weights_f32(const float* logits, const float* h, const float* ct
                             int B, int V, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Explainer forward (the producer of the saved state above): fused element-wise steps of
+ * ExplainGridTDAttention.get_hidden_parameters (gridTDmodel.py:933-1012).  Row strides ("ld_*", in
+ * elements) let the kernels write straight into the (B, T, .) saved-state tensors and into the
+ * staging rows of the next GEMM.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, H;
+  const float* z;         long long ldz;        /* (B, >=4H) gate pre-activations, order i,f,g,o (:777-783) */
+  const float* c_prev;    long long ld_cprev;   /* (B,H) */
+  const float* gate_pre;  long long ld_gate_pre;/* optional (B,H): x_gate(x) + h_gate(h_old), :982          */
+  float *h, *c;           long long ld_state;   /* new state rows                                           */
+  float *g, *i, *f, *s;   long long ld_gate;    /* pre-tanh candidate, input/forget gates, sentinel (if gate_pre) */
+  float* h_copy0;         long long ld_copy0;   /* optional copies of h (inputs of the next GEMMs)          */
+  float* h_copy1;         long long ld_copy1;
+  float* h_copy2;         long long ld_copy2;
+  float* s_copy;          long long ld_s_copy;
+} lrpx_lstm_cell_args;
+
+int lrpx_lstm_cell_f32(const lrpx_lstm_cell_args* args, void* stream);
+
+/* AdaptiveAttention.forward (gridTDmodel.py:61-103), one block per image:
+ *   z[p] = w_h . tanh(img_proj[b,p,:] + hproj[b,p]) (sic, needs P == K);  alpha = softmax z;  ctx = sum_p alpha[p] A[b,p,:]
+ *   zs = w_h . tanh(sproj[b,:] + hproj[b,:]);  beta = softmax([z; zs])[-1];  ctx_hat = beta*s + (1-beta)*ctx */
+typedef struct {
+  int B, P, K, H;                              /* K = n_pixel of the attention projections */
+  const float* A;                              /* (B,P,H) projected features, pixel-major  */
+  const float* img_proj;                       /* (B,P,K) W_v_proj(A)                      */
+  const float* hs_proj;   long long ld_hs;     /* (B,2K): [W_g_proj(h) | W_s_proj(s)+bias]  */
+  const float* w_h;                            /* (K)                                      */
+  const float* s;         long long ld_s;      /* (B,H) sentinel                           */
+  float *ctx, *ctx_hat;   long long ld_out;
+  float* alpha;           long long ld_alpha;  /* (B,P) rows */
+  float* beta;            long long ld_beta;   /* (B) */
+  float* ctx_hat_copy;    long long ld_copy;   /* optional */
+} lrpx_ada_attention_args;
+
+int lrpx_adaptive_attention_f32(const lrpx_ada_attention_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Tensor-core path (tcgen05 + TMA, bf16 operands / fp32 accumulate in TMEM).
  *
  * Layout "PF" (padded-flat NHWC bf16): an image of h x w pixels and C channels is a block of

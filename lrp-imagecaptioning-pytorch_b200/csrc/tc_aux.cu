@@ -37,82 +37,111 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* _
 }
 
 // ---------------------------------------------------------------- first layer (cin = 3), CUDA cores
-// lane = 4 pixels x 8 channel groups of 8 channels: a warp writes 4 contiguous 128-byte PF rows (cout = 64).
-// Shared memory holds W, W+ and W- (transposed, [27][cout]) so that one (tap, channel pair) costs three packed
-// fma.rn.f32x2: z += w*x, z+ += w+*x+, z+ += w-*x-  (lrp_modules.py:81-84 for the mixed-sign input).
+// One thread = FF_PX consecutive PF rows x 8 output channels; a warp = 4 row groups x 8 channel groups (cout = 64), so
+// every store instruction writes 4 full 128-byte PF rows.  Shared memory holds W, W+ and W- in the order
+// [array][tap][quad][channel group][4] — the 8 channel groups of a warp read 128 contiguous bytes per LDS.128, and a
+// weight fetched once feeds FF_PX pixels (with one pixel per thread and a [tap][cout] layout the kernel was bound by
+// shared-memory bandwidth: 2-way bank conflicts on every LDS.128, 3.7 ms for 64 images).  One (tap, channel pair)
+// costs three packed fma.rn.f32x2: z += w*x, z+ += w+*x+, z+ += w-*x-  (lrp_modules.py:81-84, mixed-sign input).
+constexpr int FF_PX = 4;
 template <int CG>   // channel groups per pixel = cout / 8
 __global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, uint4* __restrict__ act,
                                                         uint4* __restrict__ gain, int n, int h, int wd) {
-  extern __shared__ __align__(16) float ws[];        // [3][27][cout] (w, w+, w-), then bias[cout]
+  extern __shared__ __align__(16) float ws[];        // [3][27][2][CG][4] (w, w+, w-), then bias[cout]
   constexpr int cout = CG * 8;
   for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
-    int k = i / cout, co = i % cout;
-    float v = w[co * 27 + k];            // k = (ci, r, s) of (cout,3,3,3)
-    ws[i] = v;
-    ws[27 * cout + i] = fmaxf(v, 0.f);
-    ws[2 * 27 * cout + i] = fminf(v, 0.f);
+    const int k = i / cout, co = i % cout;           // k = (ci, r, s) of (cout,3,3,3)
+    const int cg = co >> 3, q = (co >> 2) & 1, e = co & 3;
+    const float v = w[co * 27 + k];
+    const int o = ((k * 2 + q) * CG + cg) * 4 + e;
+    ws[o] = v;
+    ws[27 * cout + o] = fmaxf(v, 0.f);
+    ws[2 * 27 * cout + o] = fminf(v, 0.f);
   }
   for (int i = threadIdx.x; i < cout; i += blockDim.x) ws[3 * 27 * cout + i] = bias ? bias[i] : 0.f;
   __syncthreads();
   const int wp1 = wd + 1, blk = (h + 1) * wp1;
-  const long long total = (long long)n * blk * CG;
+  const long long rows = (long long)n * blk;
+  const long long groups = (rows + FF_PX - 1) / FF_PX;
+  const long long total = groups * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long prow = i / CG;
-    int img = (int)(prow / blk), rem = (int)(prow % blk);
-    int a = rem / wp1, b = rem % wp1;
-    uint4 oa = make_uint4(0, 0, 0, 0), og = make_uint4(0, 0, 0, 0);
-    if (a > 0 && b > 0) {
-      int y = a - 1, xx = b - 1;
-      float2 z[4], zp[4];
+    const int cg = (int)(i % CG);
+    const long long prow0 = (i / CG) * FF_PX;
+    const float* xb[FF_PX];      // image base of each pixel (nullptr: padding row or past the end)
+    int py[FF_PX], pxx[FF_PX];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        z[j] = make_float2(ws[3 * 27 * cout + cg * 8 + 2 * j], ws[3 * 27 * cout + cg * 8 + 2 * j + 1]);
-        zp[j] = make_float2(0.f, 0.f);
+    for (int j = 0; j < FF_PX; ++j) {
+      const long long prow = prow0 + j;
+      const int img = (int)(prow / blk), rem = (int)(prow % blk);
+      const int a = rem / wp1, b = rem % wp1;
+      const bool valid = prow < rows && a > 0 && b > 0;
+      xb[j] = valid ? x + (size_t)img * 3 * h * wd : nullptr;
+      py[j] = a - 1;
+      pxx[j] = b - 1;
+    }
+    float2 z[FF_PX][4], zp[FF_PX][4];
+#pragma unroll
+    for (int j = 0; j < FF_PX; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        z[j][c] = make_float2(ws[3 * 27 * cout + cg * 8 + 2 * c], ws[3 * 27 * cout + cg * 8 + 2 * c + 1]);
+        zp[j][c] = make_float2(0.f, 0.f);
       }
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci)
+    for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            int yy = y + r - 1, xs = xx + s - 1;
+        for (int s = 0; s < 3; ++s) {
+          const int k = (ci * 3 + r) * 3 + s;
+          float4 wv[2], pv[2], nv[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            wv[q] = *reinterpret_cast<const float4*>(ws + ((k * 2 + q) * CG + cg) * 4);
+            pv[q] = *reinterpret_cast<const float4*>(ws + 27 * cout + ((k * 2 + q) * CG + cg) * 4);
+            nv[q] = *reinterpret_cast<const float4*>(ws + 2 * 27 * cout + ((k * 2 + q) * CG + cg) * 4);
+          }
+#pragma unroll
+          for (int j = 0; j < FF_PX; ++j) {
+            const int yy = py[j] + r - 1, xs = pxx[j] + s - 1;
             float xv = 0.f;
-            if (yy >= 0 && yy < h && xs >= 0 && xs < wd) xv = __ldg(x + (((size_t)img * 3 + ci) * h + yy) * wd + xs);
+            if (xb[j] && yy >= 0 && yy < h && xs >= 0 && xs < wd) xv = __ldg(xb[j] + ((size_t)ci * h + yy) * wd + xs);
             const float2 x2 = make_float2(xv, xv);
             const float2 xp2 = make_float2(fmaxf(xv, 0.f), fmaxf(xv, 0.f));
             const float2 xn2 = make_float2(fminf(xv, 0.f), fminf(xv, 0.f));
-            const int k = (ci * 3 + r) * 3 + s;
-            const float4* w4 = reinterpret_cast<const float4*>(ws + k * cout + cg * 8);
-            const float4* p4 = reinterpret_cast<const float4*>(ws + (27 + k) * cout + cg * 8);
-            const float4* n4 = reinterpret_cast<const float4*>(ws + (54 + k) * cout + cg * 8);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const float4 wv = w4[q], pv = p4[q], nv = n4[q];
-              z[2 * q] = __ffma2_rn(make_float2(wv.x, wv.y), x2, z[2 * q]);
-              z[2 * q + 1] = __ffma2_rn(make_float2(wv.z, wv.w), x2, z[2 * q + 1]);
-              zp[2 * q] = __ffma2_rn(make_float2(pv.x, pv.y), xp2, zp[2 * q]);
-              zp[2 * q + 1] = __ffma2_rn(make_float2(pv.z, pv.w), xp2, zp[2 * q + 1]);
-              zp[2 * q] = __ffma2_rn(make_float2(nv.x, nv.y), xn2, zp[2 * q]);
-              zp[2 * q + 1] = __ffma2_rn(make_float2(nv.z, nv.w), xn2, zp[2 * q + 1]);
+              z[j][2 * q] = __ffma2_rn(make_float2(wv[q].x, wv[q].y), x2, z[j][2 * q]);
+              z[j][2 * q + 1] = __ffma2_rn(make_float2(wv[q].z, wv[q].w), x2, z[j][2 * q + 1]);
+              zp[j][2 * q] = __ffma2_rn(make_float2(pv[q].x, pv[q].y), xp2, zp[j][2 * q]);
+              zp[j][2 * q + 1] = __ffma2_rn(make_float2(pv[q].z, pv[q].w), xp2, zp[j][2 * q + 1]);
+              zp[j][2 * q] = __ffma2_rn(make_float2(nv[q].x, nv[q].y), xn2, zp[j][2 * q]);
+              zp[j][2 * q + 1] = __ffma2_rn(make_float2(nv[q].z, nv[q].w), xn2, zp[j][2 * q + 1]);
             }
           }
-      uint32_t pa[4], pg[4];
+        }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a0 = fmaxf(z[j].x, 0.f), a1 = fmaxf(z[j].y, 0.f);
-        __nv_bfloat162 ta = __floats2bfloat162_rn(a0, a1);
-        __nv_bfloat162 tg = __floats2bfloat162_rn(safe_div(a0, zp[j].x), safe_div(a1, zp[j].y));
-        pa[j] = *reinterpret_cast<uint32_t*>(&ta);
-        pg[j] = *reinterpret_cast<uint32_t*>(&tg);
+    for (int j = 0; j < FF_PX; ++j) {
+      if (prow0 + j >= rows) break;
+      uint4 oa = make_uint4(0, 0, 0, 0), og = make_uint4(0, 0, 0, 0);
+      if (xb[j]) {
+        uint32_t pa[4], pg[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float a0 = fmaxf(z[j][c].x, 0.f), a1 = fmaxf(z[j][c].y, 0.f);
+          __nv_bfloat162 ta = __floats2bfloat162_rn(a0, a1);
+          __nv_bfloat162 tg = __floats2bfloat162_rn(safe_div(a0, zp[j][c].x), safe_div(a1, zp[j][c].y));
+          pa[c] = *reinterpret_cast<uint32_t*>(&ta);
+          pg[c] = *reinterpret_cast<uint32_t*>(&tg);
+        }
+        oa = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+        og = make_uint4(pg[0], pg[1], pg[2], pg[3]);
       }
-      oa = make_uint4(pa[0], pa[1], pa[2], pa[3]);
-      og = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+      act[(prow0 + j) * CG + cg] = oa;
+      gain[(prow0 + j) * CG + cg] = og;
     }
-    act[i] = oa;
-    gain[i] = og;
   }
 }
 
@@ -268,7 +297,7 @@ int lrpx_tc_first_fwd(const float* x, const float* w, const float* bias, void* a
                       int cout, void* stream) {
   LRPX_CHECK_ARG(x && w && act && gain && n > 0 && h > 0 && wd > 0, "bad argument");
   LRPX_CHECK_ARG(cout == 64 || cout == 32 || cout == 16 || cout == 8, "cout must be 8, 16, 32 or 64");
-  long long total = (long long)n * (h + 1) * (wd + 1) * (cout / 8);
+  long long total = ((long long)n * (h + 1) * (wd + 1) + FF_PX - 1) / FF_PX * (cout / 8);
   size_t smem = (size_t)(3 * 27 * cout + cout) * sizeof(float);
   cudaStream_t st = as_stream(stream);
   int grid = grid_for(total);

@@ -46,6 +46,23 @@ class TcConvArgs(C.Structure):
                [(n, _P) for n in ("a", "wt", "bias", "gain", "row_img", "pool_idx", "x", "out", "out2")]
 
 
+_LL = C.c_longlong
+
+
+class LstmCellArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("z", _P), ("ldz", _LL), ("c_prev", _P), ("ld_cprev", _LL),
+                ("gate_pre", _P), ("ld_gate_pre", _LL), ("h", _P), ("c", _P), ("ld_state", _LL), ("g", _P), ("i", _P),
+                ("f", _P), ("s", _P), ("ld_gate", _LL), ("h_copy0", _P), ("ld_copy0", _LL), ("h_copy1", _P),
+                ("ld_copy1", _LL), ("h_copy2", _P), ("ld_copy2", _LL), ("s_copy", _P), ("ld_s_copy", _LL)]
+
+
+class AdaAttentionArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("P", C.c_int), ("K", C.c_int), ("H", C.c_int), ("A", _P), ("img_proj", _P),
+                ("hs_proj", _P), ("ld_hs", _LL), ("w_h", _P), ("s", _P), ("ld_s", _LL), ("ctx", _P), ("ctx_hat", _P),
+                ("ld_out", _LL), ("alpha", _P), ("ld_alpha", _LL), ("beta", _P), ("ld_beta", _LL),
+                ("ctx_hat_copy", _P), ("ld_copy", _LL)]
+
+
 # every symbol include/lrpx.h declares: name -> (restype, argtypes)
 _i, _f, _sz = C.c_int, C.c_float, C.c_size_t
 SYMBOLS = {
@@ -69,6 +86,8 @@ SYMBOLS = {
     "lrpx_aoa_decoder_workspace_bytes": (_sz, [C.POINTER(AoaArgs)]),
     "lrpx_aoa_decoder_lrp_f32": (_i, [C.POINTER(AoaArgs), _P, _sz, _P]),
     "lrpx_fc_lrp_weights_f32": (_i, [_P, _P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
+    "lrpx_lstm_cell_f32": (_i, [C.POINTER(LstmCellArgs), _P]),
+    "lrpx_adaptive_attention_f32": (_i, [C.POINTER(AdaAttentionArgs), _P]),
     "lrpx_tc_conv": (_i, [C.POINTER(TcConvArgs), _P]),
     "lrpx_tc_gemm_bf16_f32": (_i, [_P, _P, _P, _i, _i, _i, _P]),
     "lrpx_weight_prep_bf16": (_i, [_P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),

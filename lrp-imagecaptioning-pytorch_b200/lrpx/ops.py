@@ -288,3 +288,57 @@ def aoa_decoder_lrp(state: dict, weights: dict, num_head, req_img, req_t, req_wo
     ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
     check(lib().lrpx_aoa_decoder_lrp_f32(C.byref(a), _ptr(ws), nbytes, _stream()), "lrpx_aoa_decoder_lrp_f32")
     return (r_feat, r_words, r_raw) if want_raw else (r_feat, r_words)
+
+
+# ------------------------------------------------------------------------------------------ explainer forward
+def _ld(t):
+    """row stride (elements) of a 2-D view whose last dimension is contiguous"""
+    if t.stride(-1) != 1:
+        raise _lib.LrpxError("last dimension must be contiguous")
+    return t.stride(0)
+
+
+def lstm_cell(z, c_prev, h, c, g, i, f, gate_pre=None, s=None, h_copy0=None, h_copy1=None, h_copy2=None, s_copy=None):
+    """lrpx_lstm_cell_f32: all arguments are 2-D fp32 CUDA views (B, H) (z: (B, >=4H)) with contiguous rows; outputs
+    are written in place.  h/c share one row stride, g/i/f/s share one."""
+    B, H = c_prev.shape
+    for t in (z, c_prev, h, c, g, i, f):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise _lib.LrpxError("lstm_cell needs fp32 CUDA tensors: lrpx has no CPU fallback")
+    if _ld(h) != _ld(c) or not (_ld(g) == _ld(i) == _ld(f)) or (s is not None and _ld(s) != _ld(g)):
+        raise _lib.LrpxError("h/c and g/i/f/s must share their row strides")
+    a = _lib.LstmCellArgs(B=B, H=H)
+    a.z, a.ldz = z.data_ptr(), _ld(z)
+    a.c_prev, a.ld_cprev = c_prev.data_ptr(), _ld(c_prev)
+    if gate_pre is not None:
+        a.gate_pre, a.ld_gate_pre = gate_pre.data_ptr(), _ld(gate_pre)
+        a.s = s.data_ptr()
+    a.h, a.c, a.ld_state = h.data_ptr(), c.data_ptr(), _ld(h)
+    a.g, a.i, a.f, a.ld_gate = g.data_ptr(), i.data_ptr(), f.data_ptr(), _ld(g)
+    for name, ldn, t in (("h_copy0", "ld_copy0", h_copy0), ("h_copy1", "ld_copy1", h_copy1), ("h_copy2", "ld_copy2", h_copy2),
+                         ("s_copy", "ld_s_copy", s_copy)):
+        if t is not None:
+            setattr(a, name, t.data_ptr())
+            setattr(a, ldn, _ld(t))
+    check(lib().lrpx_lstm_cell_f32(C.byref(a), _stream()), "lrpx_lstm_cell_f32")
+
+
+def adaptive_attention(A, img_proj, hs_proj, w_h, s, ctx, ctx_hat, alpha, beta, ctx_hat_copy=None):
+    """lrpx_adaptive_attention_f32 (AdaptiveAttention.forward, gridTDmodel.py:61-103); outputs written in place.
+    A (B,P,H), img_proj (B,P,K) contiguous; hs_proj (B,2K); s/ctx/ctx_hat (B,H) row views; alpha (B,P); beta (B,)."""
+    B, P, H = A.shape
+    K = img_proj.shape[2]
+    if not (A.is_cuda and A.is_contiguous() and img_proj.is_contiguous() and w_h.is_contiguous()):
+        raise _lib.LrpxError("adaptive_attention needs contiguous CUDA tensors")
+    if _ld(ctx) != _ld(ctx_hat):
+        raise _lib.LrpxError("ctx / ctx_hat must share their row stride")
+    a = _lib.AdaAttentionArgs(B=B, P=P, K=K, H=H)
+    a.A, a.img_proj, a.w_h = A.data_ptr(), img_proj.data_ptr(), w_h.data_ptr()
+    a.hs_proj, a.ld_hs = hs_proj.data_ptr(), _ld(hs_proj)
+    a.s, a.ld_s = s.data_ptr(), _ld(s)
+    a.ctx, a.ctx_hat, a.ld_out = ctx.data_ptr(), ctx_hat.data_ptr(), _ld(ctx)
+    a.alpha, a.ld_alpha = alpha.data_ptr(), _ld(alpha)
+    a.beta, a.ld_beta = beta.data_ptr(), beta.stride(0)
+    if ctx_hat_copy is not None:
+        a.ctx_hat_copy, a.ld_copy = ctx_hat_copy.data_ptr(), _ld(ctx_hat_copy)
+    check(lib().lrpx_adaptive_attention_f32(C.byref(a), _stream()), "lrpx_adaptive_attention_f32")

@@ -503,7 +503,80 @@ class ExplainGridTDAttention(object):
 
         feat: (B,P,C) pixel-major encoder output; tokens: (B,L) long, column 0 = <start>.  Returns the saved
         state in the kernels' layout (lrpx_gridtd_args), T = L-1 steps.  ``quirk_double_bias_ih`` reproduces the
-        explainer's language LSTM adding bias_ih twice (:789, Q3)."""
+        explainer's language LSTM adding bias_ih twice (:789, Q3).
+
+        On a CUDA device a time step is 3 library GEMMs over concatenated inputs + 3 fused kernels
+        (``lrpx_lstm_cell_f32`` x2, ``lrpx_adaptive_attention_f32``) writing straight into the saved-state tensors;
+        everything that does not depend on the recurrent state (embeddings, the input-side halves of the gate
+        pre-activations, the vocabulary projection) is one batched GEMM over all T steps.  On the CPU (host-logic
+        tests only) the same arithmetic runs as plain tensor ops."""
+        if not feat.is_cuda:
+            return self._explainer_forward_ops(feat, tokens, quirk_double_bias_ih)
+        m = self.model
+        B, P, C = feat.shape
+        H, E = m.hidden_dim, m.embed_dim
+        T = tokens.shape[1] - 1
+        dev = feat.device
+        att = m.AdaAttention
+        K = att.num_pixel
+        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            feat = feat.contiguous()
+            avg = feat.mean(1)
+            Wp = m.img_projector.weight.reshape(H, C)
+            A_pre = torch.addmm(m.img_projector.bias, feat.view(B * P, C), Wp.t()).view(B, P, H)
+            A = A_pre.clamp(min=0)
+            glob_pre = m.global_img_feature_proj(avg)
+            glob = glob_pre.clamp(min=0)
+            img_proj = att.W_v_proj(A).contiguous()                                  # (B,P,K)
+            cell, L = m.AdaLSTM.lstm_cell, m.LanguageLSTM
+            lb2 = L.bias_ih if quirk_double_bias_ih else L.bias_hh
+            # ---- weights of the concatenated GEMMs (x1 = [h2, glob, emb], :975-983)
+            xg, hg = m.AdaLSTM.x_gate, m.AdaLSTM.h_gate
+            W1_rec = torch.cat((torch.cat((cell.weight_ih[:, :H], cell.weight_hh), 1),           # [h2 | h1] -> 4H
+                                torch.cat((xg.weight[:, :H], hg.weight), 1)), 0).t().contiguous()  # ... -> gate (H)
+            W1_in = torch.cat((cell.weight_ih[:, H:], xg.weight[:, H:]), 0).t().contiguous()       # [glob | emb] -> 5H
+            b1 = torch.cat((cell.bias_ih + cell.bias_hh, xg.bias + hg.bias))
+            W2 = torch.cat((L.weight_ih, L.weight_hh), 1).t().contiguous()                          # [ctx_hat | h1 | h2] -> 4H
+            b2 = L.bias_ih + lb2
+            Wa = torch.zeros(2 * H, 2 * K, device=dev)                                              # [h1 | s] -> [W_g h1 | W_s s]
+            Wa[:H, :K] = att.W_g_proj.weight.t()
+            Wa[H:, K:] = att.W_s_proj.weight.t()
+            ba = torch.cat((torch.zeros(K, device=dev), att.W_s_proj.bias))
+            w_h = att.w_h.weight.reshape(-1).contiguous()
+            # ---- state-independent halves for all T steps at once
+            emb = m.embedding(tokens[:, :T])                                                     # (B,T,E)
+            xin = torch.cat((glob.unsqueeze(1).expand(B, T, E), emb), -1)                        # (B,T,2E)
+            pre1 = torch.addmm(b1, xin.transpose(0, 1).reshape(T * B, 2 * E), W1_in).view(T, B, 5 * H)
+            # ---- saved state
+            h1, c1, h2, c2 = (torch.zeros(B, T + 1, H, device=dev) for _ in range(4))
+            g1, i1, f1, g2, i2, f2, st, ctx, ctx_hat = (new(B, T, H) for _ in range(9))
+            alpha, beta = new(B, T, P), new(B, T)
+            # ---- staging rows of the GEMMs
+            hcat = torch.zeros(B, 2 * H, device=dev)          # [h2_t | h1_t]
+            hs = new(B, 2 * H)                                # [h1_{t+1} | s_t]
+            x2c = torch.zeros(B, 3 * H, device=dev)           # [ctx_hat_t | h1_{t+1} | h2_t]
+            for t in range(T):
+                z1 = torch.addmm(pre1[t], hcat, W1_rec)                                           # (B,5H)
+                ops.lstm_cell(z1, c1[:, t], h1[:, t + 1], c1[:, t + 1], g1[:, t], i1[:, t], f1[:, t],
+                              gate_pre=z1[:, 4 * H:], s=st[:, t], h_copy0=hcat[:, H:], h_copy1=x2c[:, H:2 * H],
+                              h_copy2=hs[:, :H], s_copy=hs[:, H:])
+                hsp = torch.addmm(ba, hs, Wa)                                                     # (B,2K)
+                ops.adaptive_attention(A, img_proj, hsp, w_h, st[:, t], ctx[:, t], ctx_hat[:, t], alpha[:, t],
+                                       beta[:, t], ctx_hat_copy=x2c[:, :H])
+                z2 = torch.addmm(b2, x2c, W2)                                                     # (B,4H)
+                ops.lstm_cell(z2, c2[:, t], h2[:, t + 1], c2[:, t + 1], g2[:, t], i2[:, t], f2[:, t],
+                              h_copy0=hcat[:, :H], h_copy1=x2c[:, 2 * H:])
+            pred = torch.addmm(m.fc.bias, (ctx_hat + h2[:, 1:]).view(B * T, H), m.fc.weight.t()).view(B, T, -1)
+            x1 = torch.cat((h2[:, :T], xin), -1)
+            x2 = torch.cat((ctx_hat, h1[:, 1:]), -1)
+            st_ = dict(x1=x1, x2=x2, g1=g1, i1=i1, f1=f1, g2=g2, i2=i2, f2=f2, st=st, ctx=ctx, ctx_hat=ctx_hat,
+                       alpha=alpha, beta=beta, pred=pred, h1=h1, c1=c1, h2=h2, c2=c2, feat=feat, avg=avg,
+                       A_pre=A_pre.contiguous(), A=A.contiguous(), glob_pre=glob_pre)
+        return st_
+
+    def _explainer_forward_ops(self, feat, tokens, quirk_double_bias_ih=True):
+        """Plain tensor-op form of ``explainer_forward`` (host-logic tests on the CPU; reference :941-1012)."""
         m = self.model
         B, P, C = feat.shape
         H, E = m.hidden_dim, m.embed_dim

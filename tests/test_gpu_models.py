@@ -240,3 +240,22 @@ def test_bu_twins_forwardlrp_and_sample_lrp_vs_reference_fixture(golden):
         assert_close(wpred, g[f"{tag}_weighted_predictions"], rtol=1e-4, atol=1e-5, what=f"{tag} BU weighted predictions")
         assert torch.equal(seq.cpu(), g[f"{tag}_seq"]), (tag, seq.cpu(), g[f"{tag}_seq"])
         assert_close(seq_lp, g[f"{tag}_seq_logprobs"], rtol=1e-4, atol=1e-5, what=f"{tag} BU sample log-probs")
+
+
+@pytest.mark.parametrize("B,T,P,H,E,V", [(3, 5, 16, 64, 32, 50), (2, 4, 196, 512, 512, 300)])
+def test_fused_explainer_forward_equals_tensor_op_form(tmp_path, B, T, P, H, E, V):
+    """lrpx_lstm_cell_f32 / lrpx_adaptive_attention_f32 + concatenated GEMMs vs the step-by-step tensor-op form of
+    the reference's get_hidden_parameters (gridTDmodel.py:941-1012): every saved-state tensor, fp32 bar."""
+    from models import gridTDmodel as G
+    model = G.GridTDModel(E, H, V, "vgg16", n_pixel=P)
+    model.load_state_dict(synth.gridtd_decoder_state(5, V, H, E, n_pixel=P), strict=False)
+    ex = G.ExplainGridTDAttention(_args(E, H, tmp_path), synth.word_map(V), model=model.to(DEV))
+    g = torch.Generator().manual_seed(6)
+    feat = torch.rand(B, P, 512, generator=g).to(DEV)
+    toks = torch.randint(1, V - 4, (B, T + 1), generator=g).to(DEV)
+    fused = ex.explainer_forward(feat, toks)
+    plain = ex._explainer_forward_ops(feat, toks)
+    assert set(fused) == set(plain)
+    for k in sorted(plain):
+        assert fused[k].shape == plain[k].shape, k
+        assert_close(fused[k], plain[k], rtol=1e-4, atol=2e-6, what=f"explainer forward state '{k}'")
