@@ -322,6 +322,12 @@ int lrpx_tc_gemm_bf16_f32(const void* a, const void* wt, float* out, int m, int 
 int lrpx_tc_first_fwd(const float* x, const float* w, const float* bias, void* act, void* gain, int n, int h, int wd,
                       int cout, void* stream);
 
+/* First VGG layer on the tensor cores: sign-split im2col of the fp32 NCHW images (n,3,h,w) into PF bf16 rows of 64
+ * columns [x+ over the 27 (ci,r,s) taps | x- over the 27 taps | 10 zeros].  lrpx_tc_conv(ksize 1, cin 64,
+ * LRPX_TC_EPI_FWD_GAIN) with weight rows [w | w | 0] (z) and [w+ | w- | 0] (z+) then yields act and gain of
+ * the mixed-sign first layer (lrp_modules.py:81-84). */
+int lrpx_tc_im2col3_split_bf16(const float* x, void* dst, int n, int h, int w, void* stream);
+
 /* One-time weight preparation (replaces the per-call PosNetConv/NegNetConv clones,
  * lrp_modules.py:59-76): from fp32 (cout,cin,kh,kw) build bf16 GEMM operands.
  *   mode 0: forward      Wt[co][(r,s,ci)]            = W[co][ci][r][s]

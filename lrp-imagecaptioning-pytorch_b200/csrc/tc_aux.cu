@@ -275,11 +275,64 @@ __global__ void nchw_to_pf_kernel(const float* __restrict__ src, __nv_bfloat16* 
   }
 }
 
+// ---------------------------------------------------------------- first layer as a tensor-core GEMM: sign-split im2col
+// PF row of pixel (y,x) <- 64 bf16: [x+ over the 27 (ci,r,s) taps | x- over the 27 taps | 10 zeros], so that the
+// first conv is a 1x1 "convolution" with K = 64 for lrpx_tc_conv(EPI_FWD_GAIN): rows [w | w | 0] give z = W*x and
+// rows [w+ | w- | 0] give z+ = W+*x+ + W-*x- (lrp_modules.py:81-84).
+__global__ void im2col3_split_kernel(const float* __restrict__ x, uint32_t* __restrict__ dst, int n, int h, int w) {
+  // one thread per PF row: 27 coalesced loads (consecutive lanes = consecutive pixels), all tap arithmetic static
+  const int wp1 = w + 1, blk = (h + 1) * wp1;
+  const long long total = (long long)n * blk;
+  for (long long prow = blockIdx.x * (long long)blockDim.x + threadIdx.x; prow < total;
+       prow += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(prow / blk), rem = (int)(prow % blk);
+    const int a = rem / wp1, b = rem % wp1;
+    uint32_t o[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = 0u;
+    if (a > 0 && b > 0) {
+      const float* xi = x + (size_t)img * 3 * h * w;
+      float v[28];
+      v[27] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        const int ci = k / 9, r = (k % 9) / 3, s = k % 3;
+        const int yy = a - 1 + r - 1, xs = b - 1 + s - 1;
+        v[k] = (yy >= 0 && yy < h && xs >= 0 && xs < w) ? __ldg(xi + ((size_t)ci * h + yy) * w + xs) : 0.f;
+      }
+      // columns 0..26 = x+, 27..53 = x-, 54..63 = 0
+#pragma unroll
+      for (int j = 0; j < 27; ++j) {
+        const int e0 = 2 * j, e1 = 2 * j + 1;
+        const float f0 = e0 < 27 ? fmaxf(v[e0], 0.f) : fminf(v[e0 - 27], 0.f);
+        const float f1 = e1 < 27 ? fmaxf(v[e1], 0.f) : fminf(v[e1 - 27], 0.f);
+        __nv_bfloat162 t = __floats2bfloat162_rn(f0, f1);
+        o[j] = *reinterpret_cast<uint32_t*>(&t);
+      }
+    }
+    uint32_t* d = dst + prow * 32;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(d + 8 * q), "r"(o[8 * q]),
+                   "r"(o[8 * q + 1]), "r"(o[8 * q + 2]), "r"(o[8 * q + 3]), "r"(o[8 * q + 4]), "r"(o[8 * q + 5]),
+                   "r"(o[8 * q + 6]), "r"(o[8 * q + 7])
+                   : "memory");
+  }
+}
+
 }  // namespace lrpx
 
 using namespace lrpx;
 
 extern "C" {
+
+int lrpx_tc_im2col3_split_bf16(const float* x, void* dst, int n, int h, int w, void* stream) {
+  LRPX_CHECK_ARG(x && dst && n > 0 && h > 0 && w > 0, "bad argument");
+  long long total = (long long)n * (h + 1) * (w + 1);
+  im2col3_split_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, (uint32_t*)dst, n, h, w);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
 
 int lrpx_weight_prep_bf16(const float* w, void* wt, int cout, int cin, int kh, int kw, int mode, int rows_pad,
                           int chan_pad, void* stream) {

@@ -92,6 +92,7 @@ SYMBOLS = {
     "lrpx_tc_gemm_bf16_f32": (_i, [_P, _P, _P, _i, _i, _i, _P]),
     "lrpx_weight_prep_bf16": (_i, [_P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),
     "lrpx_tc_first_fwd": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
+    "lrpx_tc_im2col3_split_bf16": (_i, [_P, _P, _i, _i, _i, _P]),
     "lrpx_tc_maxpool2_bf16": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "lrpx_tc_scale_rows": (_i, [_P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "lrpx_tc_pf_to_dense_f32": (_i, [_P, _P, _i, _i, _i, _i, _i, _P]),

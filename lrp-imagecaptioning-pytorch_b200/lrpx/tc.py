@@ -168,6 +168,13 @@ class TcVggEngine:
                 weight_prep(w, 2, out=c.w_rel[0:3])
                 weight_prep(w, 3, out=c.w_rel[3:6])
                 c.w_dual = None
+                if c.cout % 32 == 0:
+                    # forward on the tensor cores over the sign-split im2col (lrpx_tc_im2col3_split_bf16):
+                    # rows [w | w | 0] -> z, rows [w+ | w- | 0] -> z+   (K = 27 + 27 + 10 zero columns)
+                    w27 = w.reshape(c.cout, 27)
+                    pad = w27.new_zeros(c.cout, 10)
+                    c.w_dual = torch.cat((torch.cat((w27, w27, pad), 1),
+                                          torch.cat((w27.clamp(min=0), w27.clamp(max=0), pad), 1)), 0).to(torch.bfloat16).contiguous()
             else:
                 if c.cin % 64 or c.cout % 32:
                     raise _lib.LrpxError("conv channels must be multiples of 64 (in) / 32 (out) on the tensor-core path")
@@ -197,7 +204,12 @@ class TcVggEngine:
             out = torch.empty(rows, c.cout, device=dev, dtype=torch.bfloat16)
             gain = torch.empty(rows, c.cout, device=dev, dtype=torch.bfloat16)
             last = li == len(self.convs) - 1
-            if li == 0:
+            if li == 0 and c.w_dual is not None:
+                cols = torch.empty(rows, 64, device=dev, dtype=torch.bfloat16)
+                check(lib().lrpx_tc_im2col3_split_bf16(_ptr(x), _ptr(cols), n, h, w, _stream()),
+                      "lrpx_tc_im2col3_split_bf16")
+                tc_conv(cols, c.w_dual, n, h, w, 64, 2 * c.cout, 1, EPI_FWD_GAIN, out, out2=gain, bias=c.bias)
+            elif li == 0:      # narrow first layer (cout 8 / 16): CUDA cores
                 check(lib().lrpx_tc_first_fwd(_ptr(x), _ptr(c.w_f32), _ptr(c.bias), _ptr(out), _ptr(gain), n, h, w,
                                               c.cout, _stream()), "lrpx_tc_first_fwd")
             else:
