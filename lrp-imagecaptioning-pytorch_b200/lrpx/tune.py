@@ -1,0 +1,89 @@
+"""lrp_tune training step (reference train.py:211-233, ``train_lrp``), data-parallel over GPUs.
+
+    predictions, weighted_predictions, L = model.forwardlrp_context(imgs, caps, caplens, rev_word_map)
+    loss = CE(predictions, caps[:, 1:L+1]) + CE(weighted_predictions, caps[:, 1:L+1])       (ignore <pad>)
+    optimizer.zero_grad(); loss.backward(); clip_gradient(optimizer, grad_clip); optimizer.step()
+
+The LRP weights inside ``forwardlrp_context`` are per-sample constants (``lrpx_fc_lrp_weights_f32``, computed under
+no_grad), so sharding the batch across ranks needs no exchange on the forward path; the only collective is the
+gradient all-reduce, done by torch's DistributedDataParallel (NCCL over NVLink on the GPU box, gloo in the CPU
+tests), bucketed and overlapped with the backward pass.  Each rank feeds its own slice of the global batch.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+def clip_gradient(optimizer, grad_clip):
+    """models/modelutils.py:102-112 — element-wise clamp of every gradient."""
+    for group in optimizer.param_groups:
+        for param in group['params']:
+            if param.grad is not None:
+                param.grad.data.clamp_(-grad_clip, grad_clip)
+
+
+class _TuneForward(nn.Module):
+    """``forward`` = ``model.forwardlrp_context`` so that DistributedDataParallel sees the call."""
+
+    def __init__(self, model, rev_word_map):
+        super().__init__()
+        self.model = model
+        self.rev_word_map = rev_word_map
+
+    def forward(self, imgs, caps, caplens):
+        pred, wpred, max_length = self.model.forwardlrp_context(imgs, caps, caplens, self.rev_word_map)
+        return pred, wpred, torch.tensor(max_length)
+
+
+class LrpTuneStep:
+    """One ``train_lrp`` iteration per call.  ``model`` is any module with the reference's
+    ``forwardlrp_context(imgs, caps, caplens, rev_word_map) -> (predictions, weighted_predictions, max_length)``
+    (GridTDModel / AOAModel and their BU twins).  With an initialised process group the gradients are averaged
+    over the ranks by DistributedDataParallel."""
+
+    def __init__(self, model, word_map, optimizer=None, lr=1e-4, grad_clip=None, fix_encoder=True):
+        self.model = model
+        self.word_map = word_map
+        self.rev_word_map = {v: k for k, v in word_map.items()}
+        if fix_encoder:                                     # train.py:100-104 ("Training with fixed CNN")
+            for name, p in model.named_parameters():
+                if 'img_encoder' in name:
+                    p.requires_grad = False
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.optimizer = optimizer or torch.optim.Adam(params=params, lr=lr, betas=(0.8, 0.999))     # train.py:107-109
+        self.grad_clip = grad_clip
+        self.criterion = nn.CrossEntropyLoss(ignore_index=word_map['<pad>'])                        # train.py:124
+        fwd = _TuneForward(model, self.rev_word_map)
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self.distributed:
+            dev = next(model.parameters()).device
+            ids = [dev.index] if dev.type == "cuda" else None
+            fwd = nn.parallel.DistributedDataParallel(fwd, device_ids=ids, broadcast_buffers=False)
+        self.fwd = fwd
+
+    @staticmethod
+    def shard(batch, rank, world):
+        """This rank's contiguous slice of a global batch (tensors with the batch on dim 0)."""
+        n = batch[0].shape[0]
+        per = (n + world - 1) // world
+        lo, hi = rank * per, min(n, (rank + 1) * per)
+        return tuple(t[lo:hi] for t in batch)
+
+    def losses(self, imgs, caps, caplens):
+        self.model.train()
+        pred, wpred, max_length = self.fwd(imgs, caps, caplens)
+        max_length = int(max_length)
+        targets = caps[:, 1:max_length + 1].contiguous().view(-1)
+        loss_standard = self.criterion(pred.contiguous().view(-1, pred.size(2)), targets)
+        loss_lrp = self.criterion(wpred.contiguous().view(-1, wpred.size(2)), targets)
+        return loss_lrp + loss_standard, loss_standard, loss_lrp
+
+    def step(self, imgs, caps, caplens):
+        """-> (loss, loss_standard, loss_lrp) as detached tensors (no host sync here)."""
+        loss, ls, ll = self.losses(imgs, caps, caplens)
+        self.optimizer.zero_grad()
+        loss.backward()                                     # DDP all-reduces the gradient buckets here
+        if self.grad_clip:
+            clip_gradient(self.optimizer, self.grad_clip)
+        self.optimizer.step()
+        return loss.detach(), ls.detach(), ll.detach()

@@ -259,3 +259,28 @@ def test_fused_explainer_forward_equals_tensor_op_form(tmp_path, B, T, P, H, E, 
     for k in sorted(plain):
         assert fused[k].shape == plain[k].shape, k
         assert_close(fused[k], plain[k], rtol=1e-4, atol=2e-6, what=f"explainer forward state '{k}'")
+
+
+def test_lrp_tune_step_on_the_real_model():
+    """lrpx.tune.LrpTuneStep (train.py:211-233) on GridTDModelBU: the loss is CE(pred) + CE(weighted pred) of
+    forwardlrp_context, the decoder parameters move, the LRP weights carry no gradient."""
+    from models import gridTDmodel as G
+    from lrpx import tune
+    V, H, E, B, L = 60, 64, 32, 4, 6
+    model = G.GridTDModelBU(E, H, V, "bu")
+    model.load_state_dict(synth.gridtd_bu_state(81, V, H, E), strict=True)
+    model.to(DEV)
+    wm = synth.word_map(V)
+    st = tune.LrpTuneStep(model, wm, lr=1e-3, grad_clip=5.0)
+    g = torch.Generator().manual_seed(1)
+    feats = synth.bu_features(2, B).to(DEV)
+    caps = torch.randint(1, V - 4, (B, L), generator=g)
+    caps[:, 0] = V - 2
+    caps, caplens = caps.to(DEV), torch.full((B,), L)
+    before = {k: v.detach().clone() for k, v in model.named_parameters()}
+    loss0, ls, ll = st.step(feats, caps, caplens)
+    assert torch.isfinite(loss0) and abs(float(loss0) - float(ls) - float(ll)) < 1e-5
+    moved = [k for k, v in model.named_parameters() if not torch.equal(before[k], v.detach())]
+    assert "fc.weight" in moved and "LanguageLSTM.weight_hh" in moved
+    losses = [float(st.step(feats, caps, caplens)[0]) for _ in range(5)]
+    assert losses[-1] < float(loss0), (float(loss0), losses)
