@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
                     help="run 1 warm-up + 1 step and exit (the command line captured under ncu for profiles/)")
-    ap.add_argument("--cpu-words", type=int, default=3, help="words of the bounded CPU sample")
+    ap.add_argument("--cpu-words", type=int, default=19, help="words per image of the bounded CPU sample")
+    ap.add_argument("--cpu-images", type=int, default=4, help="images of the bounded CPU sample (about 10-30 s of host work)")
     return ap.parse_args()
 
 
@@ -222,6 +223,9 @@ def run_ours(args):
     for _ in range(2):
         eager.explain(imgs_d, toks_d, out=heat)
     phase_ms, calls = breakdown()
+    for _ in range(2):                       # per-phase minimum of three instrumented steps
+        again, _ = breakdown()
+        phase_ms = {k: min(v, again[k]) for k, v in phase_ms.items()}
     del eager
     for _ in range(max(args.warmup, 3)):
         step(imgs_d, toks_d)
@@ -264,7 +268,11 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "tc_conv_kernel<MUL|MUL_UNPOOL|INPUT> (encoder relevance chain)",
                          "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+                         "frac": achieved / pk["tf_sustained"], "traffic": chain_traffic(args.chunk),
+                         "traffic_note": "dram read+write bytes of the 13 chain launches of one chunk (ncu --set full, "
+                                         "profiles/r1_chain_full.md); algorithmic FLOPs per chunk = chunk x "
+                                         "algorithmic_gflop_per_explanation",
+                         "peak_source": pk["src"] + " sustained bf16",
                          "share_of_step": phase_ms["encoder_relevance_chain"] / step_eager_ms,
                          "algorithmic_gflop_per_explanation": eng.flops_per_explanation() / 1e9},
         }
@@ -279,6 +287,17 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def chain_traffic(chunk):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the relevance-chain launches of one chunk, from the committed
+    ncu --set full capture (profiles/r1_chain_full.json, written by scripts/ncu_summary.py); None if absent or if
+    the capture was taken with another chunk size."""
+    path = os.path.join(ROOT, "profiles", "r1_chain_full.json")
+    if not os.path.exists(path) or chunk != 128:
+        return None
+    d = json.load(open(path))
+    return d["dram_bytes_read"] + d["dram_bytes_write"]
 
 
 def layer_table(eng, chunk, dev, pk):
@@ -335,40 +354,53 @@ def cpu_baseline(args, steps):
     p = synth.gridtd_decoder_state(1000, V, H, E)
     vsd = synth.vgg_state(2000)
     layers = O.vgg_layers_from_state(vsd)
-    img = synth.images(3000, 1)
+    nimg = max(1, args.cpu_images)
+    imgs = synth.images(3000, nimg)
     toks = synth.tokens(3001, args.words, V)
     nwords = max(1, min(args.cpu_words, args.words))
     best = None
     for _ in range(max(1, steps)):
         t0 = time.perf_counter()
-        feats = O.sequential_forward(layers, img)[-1]
-        st = O.gridtd_explainer_forward(p, feats[0], toks)
-        for t in range(args.words - nwords, args.words):
-            rf, rw, _ = O.gridtd_explain_wordt(p, st, t)
-            O.sequential_lrp(layers, img, rf.t().reshape(1, 512, 14, 14))
+        for b in range(nimg):
+            img = imgs[b:b + 1]
+            feats = O.sequential_forward(layers, img)[-1]
+            st = O.gridtd_explainer_forward(p, feats[0], toks)
+            for t in range(args.words - nwords, args.words):
+                rf, rw, _ = O.gridtd_explain_wordt(p, st, t)
+                O.sequential_lrp(layers, img, rf.t().reshape(1, 512, 14, 14))
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": nwords / best, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 image (forward once) x {nwords} words (decoder + VGG16 encoder relevance), fp32 torch-CPU, "
-                      f"{best:.2f} s"}
+    return {"value": nimg * nwords / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{nimg} images (forward once each) x {nwords} words (decoder + VGG16 encoder relevance, the "
+                      f"reference's per-word formulation), fp32 torch-CPU, {best:.2f} s"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    # keep the whole run within a few minutes whatever --steps / --warmup are: time one image, then size the
+    # per-step sample (whole images of `cpu_words` words) for a ~180 s total
+    probe = argparse.Namespace(**vars(args))
+    probe.cpu_images = 1
+    t0 = time.perf_counter()
+    cpu_baseline(probe, steps=1)
+    per_image = time.perf_counter() - t0
+    n_steps = max(1, args.warmup + args.steps)
+    args.cpu_images = max(1, min(args.cpu_images, int(180.0 / n_steps / max(per_image, 1e-3))))
     t_all = []
     for i in range(args.warmup + args.steps):
         r = cpu_baseline(args, steps=1)
         if i >= args.warmup:
             t_all.append(r)
     v = sum(x["value"] for x in t_all) / len(t_all)
-    nwords = max(1, min(args.cpu_words, args.words))
+    nwords = max(1, min(args.cpu_words, args.words)) * max(1, args.cpu_images)
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * nwords / v, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "gridTD VGG16 LRP alpha1beta0 image+linguistic explanations, 224x224, "
-                                  f"V={args.vocab}, H=E=512; bounded sample per step: 1 image x {nwords} words"},
+                                  f"V={args.vocab}, H=E=512; bounded sample per step: {max(1, args.cpu_images)} images x "
+                                  f"{max(1, min(args.cpu_words, args.words))} words"},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": t_all[0]["cores"], "kind": "port",
                             "sample": t_all[0]["sample"]},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -55,9 +55,20 @@ def full(src, dst, cmd):
     with open(dst, "w") as f:
         f.write(f"# ncu --set full capture (tc_conv_kernel)\n\ncommand: `{cmd}`\n\n| # | kernel | " +
                 " | ".join(f"{c} [{units[idx[c]]}]" for c in cols) + " |\n|" + "---|" * (len(cols) + 2) + "\n")
+        tot_r = tot_w = tot_t = 0.0
         for i, r in enumerate(rows[2:]):
             name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "")
             f.write(f"| {i} | `{name}` | " + " | ".join(r[idx[c]] for c in cols) + " |\n")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot_r += float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
+            tot_w += float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
+            tot_t += float(r[idx["gpu__time_duration.sum"]]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}[units[idx["gpu__time_duration.sum"]]]
+        f.write(f"\nall {len(rows) - 2} launches: dram read {tot_r / 1e6:.1f} MB + write {tot_w / 1e6:.1f} MB = "
+                f"{(tot_r + tot_w) / 1e6:.1f} MB in {tot_t:.1f} us\n")
+    # machine-readable copy for bench.py's roofline.traffic
+    import json
+    json.dump({"launches": len(rows) - 2, "dram_bytes_read": tot_r, "dram_bytes_write": tot_w, "gpu_time_us": tot_t,
+               "command": cmd, "source": dst}, open(dst.replace(".md", ".json"), "w"), indent=1)
     print(open(dst).read())
 
 
