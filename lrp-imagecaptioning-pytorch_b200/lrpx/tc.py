@@ -254,22 +254,29 @@ class TcVggEngine:
         H, W = self.convs[0].h, self.convs[0].w
         if out is None:
             out = torch.empty(Q, 3, H, W, device=dev, dtype=torch.float32)
-        # ping-pong s buffers sized for the largest layer of a chunk
+        # Stage 1: the low-resolution layers run over ALL requests in one launch per layer (their tile counts per
+        # chunk are only ~3 waves of the persistent grid, so chunked launches lose up to a quarter of the machine to
+        # wave quantisation); stage 2: the remaining layers chunk by chunk, ping-ponging two buffers sized for the
+        # largest layer of a chunk, so that finished heat-maps can leave for the host while the next chunk runs.
         chunk = max(1, min(chunk, Q))
-        max_elems = max(pf_rows(chunk, c.h, c.w) * c.cout for c in self.convs)
-        buf = [torch.empty(max_elems, device=dev, dtype=torch.bfloat16) for _ in range(2)]
         L = len(self.convs)
-        for q0 in range(0, Q, chunk):
-            q1 = min(Q, q0 + chunk)
-            nq = q1 - q0
-            rimg = row_img[q0:q1]
-            cur = 0
-            s = buf[cur]
-            check(lib().lrpx_tc_scale_rows(_ptr(r_feat[q0:q1]), _ptr(st.rz_last), _ptr(rimg), _ptr(s), nq, fh, fw,
-                                           st.feat_c, _stream()), "lrpx_tc_scale_rows")
+        budget = 2 << 30                      # bytes per stage-1 buffer
+        n_wide = 0                            # layers L-1 .. L-n_wide handled in stage 1 (their INPUT and OUTPUT fit)
+        if Q > chunk:
             for li in range(L - 1, 0, -1):
                 c, below = self.convs[li], self.convs[li - 1]
-                dst = buf[cur ^ 1]
+                oh, ow = (2 * c.h, 2 * c.w) if below.pool_after else (c.h, c.w)
+                need = max(pf_rows(Q, c.h, c.w) * c.cout, pf_rows(Q, oh, ow) * c.cin) * 2
+                if need > budget:
+                    break
+                n_wide += 1
+        split = L - n_wide                    # stage 1 = layers L-1 .. split, stage 2 = layers split-1 .. 0
+
+        def run_layers(s, nq, rimg, lo, hi, bufs, cur):
+            """layers hi-1 .. lo (lo >= 1) on nq requests; returns (tensor holding the result, index of its buffer)"""
+            for li in range(hi - 1, lo - 1, -1):
+                c, below = self.convs[li], self.convs[li - 1]
+                dst = bufs[cur ^ 1]
                 if below.pool_after:
                     tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL_UNPOOL, dst, gain=st.gain[li - 1],
                             row_img=rimg, pool_idx=st.idx[li - 1])
@@ -278,6 +285,34 @@ class TcVggEngine:
                             row_img=rimg)
                 cur ^= 1
                 s = dst
+            return s, cur
+
+        s_all = None
+        if n_wide > 0:
+            elems = 0
+            for li in range(L - 1, split - 1, -1):
+                c, below = self.convs[li], self.convs[li - 1]
+                oh, ow = (2 * c.h, 2 * c.w) if below.pool_after else (c.h, c.w)
+                elems = max(elems, pf_rows(Q, c.h, c.w) * c.cout, pf_rows(Q, oh, ow) * c.cin)
+            wide = [torch.empty(elems, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+            check(lib().lrpx_tc_scale_rows(_ptr(r_feat), _ptr(st.rz_last), _ptr(row_img), _ptr(wide[0]), Q, fh, fw,
+                                           st.feat_c, _stream()), "lrpx_tc_scale_rows")
+            s_all, _ = run_layers(wide[0], Q, row_img, split, L, wide, 0)
+        top = self.convs[split - 1]           # first layer of stage 2: its input is (h, w, cout) of that layer
+        max_elems = max(pf_rows(chunk, c.h, c.w) * c.cout for c in self.convs[:split])
+        buf = [torch.empty(max_elems, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+        for q0 in range(0, Q, chunk):
+            q1 = min(Q, q0 + chunk)
+            nq = q1 - q0
+            rimg = row_img[q0:q1]
+            if s_all is not None:
+                per = pf_rows(1, top.h, top.w) * top.cout
+                s, cur = s_all[q0 * per:q1 * per], 1      # reads the stage-1 result in place, writes into buf[0]
+            else:
+                s, cur = buf[0], 0
+                check(lib().lrpx_tc_scale_rows(_ptr(r_feat[q0:q1]), _ptr(st.rz_last), _ptr(rimg), _ptr(s), nq, fh, fw,
+                                               st.feat_c, _stream()), "lrpx_tc_scale_rows")
+            s, cur = run_layers(s, nq, rimg, 1, split, buf, cur)
             c0 = self.convs[0]
             tc_conv(s, c0.w_rel, nq, c0.h, c0.w, c0.cout, 16, 3, EPI_INPUT, out[q0:q1], row_img=rimg, x=st.x)
             if on_chunk is not None:
