@@ -287,6 +287,12 @@ enum {
   LRPX_TC_EPI_INPUT = 4,
   /* out_f32[p][n] = acc[p][n] (debug / tests of the GEMM machinery) */
   LRPX_TC_EPI_STORE_F32 = 5,
+  /* decoder projector rule (gridTDmodel.py:1121-1128, aoamodel.py:1141-1150), blocks = requests, rows = pixels:
+   *   out_f32[q][p][n] = x[img(q)][p][n] * (acc[q*P+p][n] + bias[q][n])
+   * x = fp32 (n_x, P, ncol) encoder features, bias = fp32 (n_img, ncol) per-request addend or NULL */
+  LRPX_TC_EPI_FEAT = 6,
+  /* as FEAT, divided by stab(x1[img(q)][p][n])  (z + 0.01*sign z, 0 -> 0.01; the value-projection rule) */
+  LRPX_TC_EPI_FEAT_DIV = 7,
 };
 
 typedef struct {
@@ -303,9 +309,10 @@ typedef struct {
   const void* gain;     /* bf16 PF (n_gain_img, blk, ncol), MUL / MUL_UNPOOL                      */
   const int32_t* row_img; /* (n_img) block of `gain`/`pool_idx`/`x` used by each block of A; NULL = identity */
   const uint8_t* pool_idx;/* PF (n_gain_img, blk, ncol) argmax bytes, MUL_UNPOOL                  */
-  const float* x;       /* fp32 NCHW (n_x, 3, h, w) input images, INPUT                           */
+  const float* x;       /* fp32 NCHW (n_x, 3, h, w) input images, INPUT; fp32 (n_x, blk, ncol), FEAT  */
   void* out;
   void* out2;
+  const float* x1;      /* FEAT_DIV: fp32 (n_x, blk, ncol)                                        */
 } lrpx_tc_conv_args;
 
 int lrpx_tc_conv(const lrpx_tc_conv_args* args, void* stream);

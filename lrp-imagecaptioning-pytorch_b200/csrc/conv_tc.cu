@@ -69,6 +69,7 @@ struct TcParams {
   const int32_t* row_img;
   const uint8_t* pool_idx;
   const float* x;
+  const float* x1;
   void* out;
   void* out2;
 };
@@ -416,6 +417,46 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
       for (int q = 0; q < 8; ++q)
         dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
                              __uint_as_float(v[4 * q + 3]));
+    }
+  } else if (EPI == LRPX_TC_EPI_FEAT || EPI == LRPX_TC_EPI_FEAT_DIV) {
+    // rows = (request q = r.e, pixel p = r.rem); x / x1 are indexed by the request's image
+    const int img = p.row_img ? p.row_img[r.e] : r.e;
+    const size_t xo = ((size_t)img * p.blk + r.rem) * p.out_c + n0 + c;
+    const size_t bo = (size_t)r.e * p.out_c + n0 + c;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      U8 xv[2], bv[2], dv[2];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bv[0].w[k] = bv[1].w[k] = 0u;
+      if (r.in_range) {
+        xv[0] = ldg_nc_v8(p.x + xo + 16 * q);
+        xv[1] = ldg_nc_v8(p.x + xo + 16 * q + 8);
+        if (p.bias) {
+          bv[0] = ldg_nc_v8(p.bias + bo + 16 * q);
+          bv[1] = ldg_nc_v8(p.bias + bo + 16 * q + 8);
+        }
+        if (EPI == LRPX_TC_EPI_FEAT_DIV) {
+          dv[0] = ldg_nc_v8(p.x1 + xo + 16 * q);
+          dv[1] = ldg_nc_v8(p.x1 + xo + 16 * q + 8);
+        }
+      }
+      uint32_t v[16];
+      TMEM_LD_X16(taddr + c + 16 * q, v);
+      tmem_ld_wait();
+      if (r.in_range) {
+        float* dst = reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c + 16 * q;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t ow[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float val = __uint_as_float(xv[hh].w[k]) * (__uint_as_float(v[8 * hh + k]) + __uint_as_float(bv[hh].w[k]));
+            if (EPI == LRPX_TC_EPI_FEAT_DIV) val = val / stab(__uint_as_float(dv[hh].w[k]));
+            ow[k] = __float_as_uint(val);
+          }
+          stg_v8(dst + 8 * hh, ow);
+        }
+      }
     }
   } else {   // MUL / MUL_UNPOOL
     size_t goff = 0;
@@ -1030,7 +1071,7 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
   p.taps = a->ksize * a->ksize;
   p.kc_per_tap = a->cin / TC_BK;
   p.bias = a->bias; p.gain = reinterpret_cast<const __nv_bfloat16*>(a->gain);
-  p.row_img = a->row_img; p.pool_idx = a->pool_idx; p.x = a->x; p.out = a->out; p.out2 = a->out2;
+  p.row_img = a->row_img; p.pool_idx = a->pool_idx; p.x = a->x; p.x1 = a->x1; p.out = a->out; p.out2 = a->out2;
   p.gain_mode = a->gain_mode;
 
   if (epi == LRPX_TC_EPI_FWD_GAIN) {
@@ -1047,10 +1088,14 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     p.bn = 16;
     p.out_c = 3;
   } else {
-    LRPX_CHECK_ARG(epi == LRPX_TC_EPI_MUL || epi == LRPX_TC_EPI_MUL_UNPOOL || epi == LRPX_TC_EPI_STORE_F32,
+    LRPX_CHECK_ARG(epi == LRPX_TC_EPI_MUL || epi == LRPX_TC_EPI_MUL_UNPOOL || epi == LRPX_TC_EPI_STORE_F32 ||
+                       epi == LRPX_TC_EPI_FEAT || epi == LRPX_TC_EPI_FEAT_DIV,
                    "unknown epilogue");
     LRPX_CHECK_ARG(a->ncol % 32 == 0, "ncol must be a multiple of 32 for this epilogue");
-    if (epi != LRPX_TC_EPI_STORE_F32) LRPX_CHECK_ARG(a->gain, "gain required");
+    if (epi == LRPX_TC_EPI_FEAT || epi == LRPX_TC_EPI_FEAT_DIV) {
+      LRPX_CHECK_ARG(a->x && a->ksize == 1, "FEAT epilogues: x required, ksize 1");
+      LRPX_CHECK_ARG(epi == LRPX_TC_EPI_FEAT || a->x1, "FEAT_DIV needs x1");
+    } else if (epi != LRPX_TC_EPI_STORE_F32) LRPX_CHECK_ARG(a->gain, "gain required");
     if (epi == LRPX_TC_EPI_MUL_UNPOOL) LRPX_CHECK_ARG(a->pool_idx, "pool_idx required");
     p.bn = a->ncol <= 256 ? a->ncol : 256;
     LRPX_CHECK_ARG(a->ncol % p.bn == 0, "ncol must be <= 256 or a multiple of 256");
@@ -1107,6 +1152,8 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     case LRPX_TC_EPI_MUL: return launch_tc<LRPX_TC_EPI_MUL>(ma, mb, p, grid, st);
     case LRPX_TC_EPI_MUL_UNPOOL: return launch_tc<LRPX_TC_EPI_MUL_UNPOOL>(ma, mb, p, grid, st);
     case LRPX_TC_EPI_INPUT: return launch_tc<LRPX_TC_EPI_INPUT>(ma, mb, p, grid, st);
+    case LRPX_TC_EPI_FEAT: return launch_tc<LRPX_TC_EPI_FEAT>(ma, mb, p, grid, st);
+    case LRPX_TC_EPI_FEAT_DIV: return launch_tc<LRPX_TC_EPI_FEAT_DIV>(ma, mb, p, grid, st);
     default: return launch_tc<LRPX_TC_EPI_STORE_F32>(ma, mb, p, grid, st);
   }
 }

@@ -172,16 +172,21 @@ static inline int ew_grid(long long total) {
 static bool tc_shape_ok(int N, int K) { return K % 64 == 0 && N % 32 == 0 && (N <= 256 || N % 256 == 0); }
 
 // C[M,N] = A[M,K] @ W[K,N] (+ epilogue): tensor cores when `wt3` (prepared W') is given, CUDA cores otherwise
+// a3_ready: the producer kernel already wrote the split operand [hi | hi | lo] into a3 (no fp32 A exists then)
 template <int EPI>
 static int gemm_any(const float* A, const float* W, const __nv_bfloat16* wt3, __nv_bfloat16* a3, float* C, int M, int N,
-                    int K, const GemmEpi& e, cudaStream_t st) {
+                    int K, const GemmEpi& e, cudaStream_t st, bool a3_ready = false) {
   if (M == 0) return LRPX_OK;
   if (!wt3) return sgemm<EPI>(A, W, C, M, N, K, e, st);
-  split3_act_kernel<<<ew_grid((long long)M * K), 256, 0, st>>>(A, a3, M, K, K);
-  int rc = lrpx_tc_gemm_bf16_f32(a3, wt3, C, M, N, 3 * K, st);
-  if (rc) return rc;
-  if (EPI != GE_STORE) gemm_epilogue_kernel<EPI><<<ew_grid((long long)M * N), 256, 0, st>>>(C, M, N, e);
-  return LRPX_OK;
+  if (!a3_ready) split3_act_kernel<<<ew_grid((long long)M * K), 256, 0, st>>>(A, a3, M, K, K);
+  if (EPI == GE_STORE) return lrpx_tc_gemm_bf16_f32(a3, wt3, C, M, N, 3 * K, st);
+  // projector rules fused into the GEMM's epilogue: rows are (request, pixel) = one PF "block" of P rows per request
+  lrpx_tc_conv_args g{};
+  g.n_img = M / e.P; g.h = 0; g.w = e.P - 1; g.cin = 3 * K; g.ncol = N; g.ksize = 1;
+  g.epilogue = EPI == GE_FEAT ? LRPX_TC_EPI_FEAT : LRPX_TC_EPI_FEAT_DIV;
+  g.a = a3; g.wt = wt3; g.out = C;
+  g.x = e.x0; g.x1 = e.x1; g.bias = e.add_q; g.row_img = e.req_img;
+  return lrpx_tc_conv(&g, st);
 }
 static __nv_bfloat16* prep_weight3(const float* W, __nv_bfloat16* dst, int K, int N, cudaStream_t st) {
   split3_weight_kernel<<<ew_grid((long long)K * N), 256, 0, st>>>(W, dst, K, N);
@@ -339,6 +344,42 @@ __global__ void grid_attn_kernel(lrpx_gridtd_args a, GridWs w) {
     float acc = 0.f;
     for (int i = t; i >= 0; --i) acc += al[(size_t)i * a.P] * w.uctx[((size_t)q * a.T + i) * a.H + h] * a.A[o0 + h];
     w.wproj[((size_t)q * a.P + p) * a.H + h] = acc / stab(a.A_pre[o0 + h]);
+  }
+}
+// Same rule, one block per request and one thread per hidden unit: the thread keeps its (t+1) values of uctx in
+// registers and walks the pixels, so uctx is read once per request instead of once per (request, pixel), and the
+// result can leave directly as the split bf16 operand [hi | hi | lo] of the tensor-core projector GEMM.
+constexpr int ATT_MAX_T = 32;
+template <bool SPLIT>
+__global__ void __launch_bounds__(512) grid_attn_rows_kernel(lrpx_gridtd_args a, GridWs w) {
+  extern __shared__ float al_s[];          // alpha[b][0..t][:]  ((t+1) x P)
+  const int q = blockIdx.x;
+  const int b = a.req_img[q], t = a.req_t[q];
+  const int H = a.H, P = a.P;
+  for (int k = threadIdx.x; k < (t + 1) * P; k += blockDim.x) al_s[k] = a.alpha[(size_t)b * a.T * P + k];
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float u[ATT_MAX_T];
+#pragma unroll
+    for (int i = 0; i < ATT_MAX_T; ++i) u[i] = i <= t ? w.uctx[((size_t)q * a.T + i) * H + h] : 0.f;
+    for (int p = 0; p < P; ++p) {
+      const size_t o0 = ((size_t)b * P + p) * H + h;
+      const float Av = a.A[o0];
+      float acc = 0.f;
+#pragma unroll
+      for (int i = ATT_MAX_T - 1; i >= 0; --i)       // same summation order as the reference loop: i = t .. 0
+        if (i <= t) acc += al_s[i * P + p] * u[i] * Av;
+      const float r = acc / stab(a.A_pre[o0]);
+      const size_t row = (size_t)q * P + p;
+      if (SPLIT) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(r, hi, lo);
+        __nv_bfloat16* o = w.a3 + row * 3 * H;
+        o[h] = hi; o[H + h] = hi; o[2 * H + h] = lo;
+      } else {
+        w.wproj[row * H + h] = r;
+      }
+    }
   }
 }
 // r_words / max|r_words|   (:1129-1132)
@@ -634,9 +675,17 @@ int lrpx_gridtd_decoder_lrp_f32(const lrpx_gridtd_args* a, void* workspace, size
   grid_glob_kernel<<<Q, 128, 0, st>>>(*a, w);
   RUN(gemm_any<GE_STORE>(w.u, a->W_glob, w3_glob, w.a3, w.v, Q, a->C, E, none, st));
   grid_avg_kernel<<<Q, 128, 0, st>>>(*a, w);
-  grid_attn_kernel<<<dim3(a->P, Q), nt, 0, st>>>(*a, w);
   GemmEpi fe{a->feat, nullptr, w.coefavg, a->req_img, a->P};
-  RUN(gemm_any<GE_FEAT>(w.wproj, a->W_proj, w3_proj, w.a3, a->r_feat, Q * a->P, a->C, H, fe, st));
+  const size_t att_smem = (size_t)T * a->P * sizeof(float);
+  if (T <= ATT_MAX_T && att_smem <= 48 * 1024) {
+    const int at = H >= 512 ? 512 : (H >= 256 ? 256 : 128);
+    if (w3_proj) grid_attn_rows_kernel<true><<<Q, at, att_smem, st>>>(*a, w);
+    else grid_attn_rows_kernel<false><<<Q, at, att_smem, st>>>(*a, w);
+    RUN(gemm_any<GE_FEAT>(w.wproj, a->W_proj, w3_proj, w.a3, a->r_feat, Q * a->P, a->C, H, fe, st, w3_proj != nullptr));
+  } else {
+    grid_attn_kernel<<<dim3(a->P, Q), nt, 0, st>>>(*a, w);
+    RUN(gemm_any<GE_FEAT>(w.wproj, a->W_proj, w3_proj, w.a3, a->r_feat, Q * a->P, a->C, H, fe, st));
+  }
   words_norm_kernel<<<Q, 32, 0, st>>>(a->r_words, a->req_t, T);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;

@@ -43,7 +43,7 @@ class AoaArgs(C.Structure):
 
 class TcConvArgs(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n_img", "h", "w", "cin", "ncol", "ksize", "epilogue", "gain_mode")] + \
-               [(n, _P) for n in ("a", "wt", "bias", "gain", "row_img", "pool_idx", "x", "out", "out2")]
+               [(n, _P) for n in ("a", "wt", "bias", "gain", "row_img", "pool_idx", "x", "out", "out2", "x1")]
 
 
 _LL = C.c_longlong
