@@ -995,34 +995,43 @@ static bool plan_slab(TcParams& p) {
   const long long b_total = (long long)p.taps * p.kc_per_tap * b_bytes;
   const char* env_mh = getenv("LRPX_TC_MH");             // experiment switches (timing probes only)
   const char* env_iss = getenv("LRPX_TC_ISSUERS");
+  const char* env_res = getenv("LRPX_TC_RES3");           // "0": do not trade slab mode 1 for a resident B
   const int mh_max = (env_mh && env_mh[0] == '1') ? 1 : 2;
+  auto commit = [&](int mode, int mh, int slab_rows, int slab_bytes, int a_stages, int b_stages, bool res) {
+    p.slab_mode = mode; p.mh = mh; p.slab_rows = slab_rows;
+    p.n_issuers = (mh == 2 && !(env_iss && env_iss[0] == '1')) ? 2 : 1;
+    p.box0_rows = slab_rows < 256 ? slab_rows : 256;
+    p.box1_rows = slab_rows - p.box0_rows;
+    p.a_stage_bytes = slab_bytes;
+    p.a_stages = a_stages; p.b_stages = b_stages; p.b_resident = res ? 1 : 0;
+    return true;
+  };
   for (int mh = p.bn <= 128 ? mh_max : 1; mh >= 1; --mh) {
     const int rows1 = mh * TC_BM + 2 + 2 * p.wp1, rows3 = mh * TC_BM + 2;
-    const int mode = (rows1 <= 3 * rows3 && rows1 <= 512) ? 1 : 3;
-    const int slab_rows = mode == 1 ? rows1 : rows3;
-    const int slab_bytes = ((slab_rows * TC_BK * 2) + 1023) & ~1023;
+    const int bytes1 = ((rows1 * TC_BK * 2) + 1023) & ~1023, bytes3 = ((rows3 * TC_BK * 2) + 1023) & ~1023;
+    const bool mode1_ok = rows1 <= 3 * rows3 && rows1 <= 512;
+    // (1) resident B: streaming B costs more shared-memory ingest (and one barrier round trip per tap) than the
+    //     A slabs do, so it is worth fewer A stages and even the larger per-filter-row slabs of mode 3
+    if (p.num_n_tiles == 1) {
+      if (mode1_ok)
+        for (int a_stages = 3; a_stages >= 2; --a_stages)
+          if ((long long)a_stages * bytes1 + b_total <= budget) return commit(1, mh, rows1, bytes1, a_stages, 0, true);
+      if (!mode1_ok || !(env_res && env_res[0] == '0'))
+        for (int a_stages = TC_A_MAX_STAGES; a_stages >= 2; --a_stages)
+          if ((long long)a_stages * bytes3 + b_total <= budget) return commit(3, mh, rows3, bytes3, a_stages, 0, true);
+    }
+    // (2) B streamed through its own ring
+    const int mode = mode1_ok ? 1 : 3;
+    const int slab_rows = mode == 1 ? rows1 : rows3, slab_bytes = mode == 1 ? bytes1 : bytes3;
     const int min_a = mode == 1 ? 2 : 4, max_a = mode == 1 ? 3 : TC_A_MAX_STAGES;
-    // resident B is worth giving up A stages for: streaming B costs more shared-memory ingest than the A slabs do
-    const bool want_res = p.num_n_tiles == 1 && b_total <= budget - 2LL * slab_bytes;
-    for (int a_stages = max_a; a_stages >= (want_res ? 2 : min_a); --a_stages) {
+    for (int a_stages = max_a; a_stages >= min_a; --a_stages) {
       const int left = budget - a_stages * slab_bytes;
-      int b_stages = 0;
-      if (want_res) {
-        if (left < b_total) continue;
-      } else {
-        b_stages = left / b_bytes;
-        if (b_stages > TC_MAX_STAGES) b_stages = TC_MAX_STAGES;
-        // the B ring has to cover the TMA latency: >= 4 tiles and >= 48 KB in flight unless A is at its minimum
-        if (b_stages < 3) continue;
-        if (a_stages > min_a && (b_stages < 4 || b_stages * b_bytes < 48 * 1024)) continue;
-      }
-      p.slab_mode = mode; p.mh = mh; p.slab_rows = slab_rows;
-      p.n_issuers = (mh == 2 && !(env_iss && env_iss[0] == '1')) ? 2 : 1;
-      p.box0_rows = slab_rows < 256 ? slab_rows : 256;
-      p.box1_rows = slab_rows - p.box0_rows;
-      p.a_stage_bytes = slab_bytes;
-      p.a_stages = a_stages; p.b_stages = b_stages; p.b_resident = want_res ? 1 : 0;
-      return true;
+      int b_stages = left / b_bytes;
+      if (b_stages > TC_MAX_STAGES) b_stages = TC_MAX_STAGES;
+      // the B ring has to cover the TMA latency: >= 4 tiles and >= 48 KB in flight unless A is at its minimum
+      if (b_stages < 3) continue;
+      if (a_stages > min_a && (b_stages < 4 || b_stages * b_bytes < 48 * 1024)) continue;
+      return commit(mode, mh, slab_rows, slab_bytes, a_stages, b_stages, false);
     }
   }
   return false;
