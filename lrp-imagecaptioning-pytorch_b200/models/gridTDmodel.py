@@ -508,10 +508,11 @@ class ExplainGridTDAttention(object):
         On a CUDA device a time step is 3 library GEMMs over concatenated inputs + 3 fused kernels
         (``lrpx_lstm_cell_f32`` x2, ``lrpx_adaptive_attention_f32``) writing straight into the saved-state tensors;
         everything that does not depend on the recurrent state (embeddings, the input-side halves of the gate
-        pre-activations, the vocabulary projection) is one batched GEMM over all T steps.  On the CPU (host-logic
-        tests only) the same arithmetic runs as plain tensor ops."""
+        pre-activations, the vocabulary projection) is one batched GEMM over all T steps.  CUDA only: there is no
+        CPU form in the product (tests/helpers.py holds the step-by-step tensor-op restatement the kernels are
+        checked against)."""
         if not feat.is_cuda:
-            return self._explainer_forward_ops(feat, tokens, quirk_double_bias_ih)
+            raise ops._lib.LrpxError("explainer_forward needs CUDA tensors: lrpx has no CPU fallback")
         m = self.model
         B, P, C = feat.shape
         H, E = m.hidden_dim, m.embed_dim
@@ -574,46 +575,6 @@ class ExplainGridTDAttention(object):
                        alpha=alpha, beta=beta, pred=pred, h1=h1, c1=c1, h2=h2, c2=c2, feat=feat, avg=avg,
                        A_pre=A_pre.contiguous(), A=A.contiguous(), glob_pre=glob_pre)
         return st_
-
-    def _explainer_forward_ops(self, feat, tokens, quirk_double_bias_ih=True):
-        """Plain tensor-op form of ``explainer_forward`` (host-logic tests on the CPU; reference :941-1012)."""
-        m = self.model
-        B, P, C = feat.shape
-        H, E = m.hidden_dim, m.embed_dim
-        T = tokens.shape[1] - 1
-        with torch.no_grad():
-            avg = feat.mean(1)
-            Wp = m.img_projector.weight.reshape(H, C)
-            A_pre = feat @ Wp.t() + m.img_projector.bias
-            A = A_pre.clamp(min=0)
-            glob_pre = m.global_img_feature_proj(avg)
-            glob = glob_pre.clamp(min=0)
-            att = m.AdaAttention
-            img_proj = att.W_v_proj(A)
-            zeros = feat.new_zeros(B, H)
-            h1, c1, h2, c2 = [zeros], [zeros], [zeros], [zeros]
-            keys = ["x1", "x2", "g1", "i1", "f1", "g2", "i2", "f2", "st", "ctx", "ctx_hat", "alpha", "beta", "pred"]
-            seq = {k: [] for k in keys}
-            cell, L = m.AdaLSTM.lstm_cell, m.LanguageLSTM
-            lb2 = L.bias_ih if quirk_double_bias_ih else L.bias_hh
-            for t in range(T):
-                emb = m.embedding(tokens[:, t])
-                x1 = torch.cat((h2[t], glob, emb), dim=-1)
-                h1n, c1n, g1, i1, f1 = _lstm_forward(x1, h1[t], c1[t], cell.weight_ih, cell.weight_hh, cell.bias_ih,
-                                                     cell.bias_hh)
-                s = torch.sigmoid(m.AdaLSTM.x_gate(x1) + m.AdaLSTM.h_gate(h1[t])) * torch.tanh(c1n)   # OLD h1 (:982)
-                ctx_hat, ctx, alpha, beta = att.attend(A, img_proj, h1n, s)
-                x2 = torch.cat((ctx_hat, h1n), dim=-1)
-                h2n, c2n, g2, i2, f2 = _lstm_forward(x2, h2[t], c2[t], L.weight_ih, L.weight_hh, L.bias_ih, lb2)
-                pred = m.fc(ctx_hat + h2n)
-                for k, v in zip(keys, [x1, x2, g1, i1, f1, g2, i2, f2, s, ctx, ctx_hat, alpha, beta.squeeze(-1), pred]):
-                    seq[k].append(v)
-                h1.append(h1n); c1.append(c1n); h2.append(h2n); c2.append(c2n)
-            st = {k: torch.stack(v, 1).contiguous() for k, v in seq.items()}
-            for k, v in (("h1", h1), ("c1", c1), ("h2", h2), ("c2", c2)):
-                st[k] = torch.stack(v, 1).contiguous()
-            st.update(feat=feat.contiguous(), avg=avg, A_pre=A_pre.contiguous(), A=A.contiguous(), glob_pre=glob_pre)
-        return st
 
     def teacherforce_forward(self, img, beam_caption_encode):
         """reference :892-931 -> logits (len(beam_caption_encode), vocab)."""

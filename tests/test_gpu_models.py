@@ -254,7 +254,8 @@ def test_fused_explainer_forward_equals_tensor_op_form(tmp_path, B, T, P, H, E, 
     feat = torch.rand(B, P, 512, generator=g).to(DEV)
     toks = torch.randint(1, V - 4, (B, T + 1), generator=g).to(DEV)
     fused = ex.explainer_forward(feat, toks)
-    plain = ex._explainer_forward_ops(feat, toks)
+    import helpers
+    plain = helpers.gridtd_explainer_forward_ops(ex.model, feat, toks)
     assert set(fused) == set(plain)
     for k in sorted(plain):
         assert fused[k].shape == plain[k].shape, k

@@ -24,11 +24,18 @@ def _explainer(g, tmp_path):
 
 @pytest.mark.parametrize("name", ["gridtd_dec_small", "gridtd_dec_512"])
 def test_explainer_forward_matches_reference_fixture(golden, tmp_path, name):
+    """The tensor-op restatement in tests/helpers.py (the checker of the fused CUDA explainer forward, see
+    tests/test_gpu_models.py) against the reference's own get_hidden_parameters outputs; the product method
+    itself refuses CPU tensors."""
+    import helpers
+    from lrpx._lib import LrpxError
     g = golden(name)
     ex, sd = _explainer(g, tmp_path)
     feat = g["feats"][0].flatten(1).t().unsqueeze(0).contiguous()          # (1,P,C)
     toks = torch.tensor([g["tokens"].tolist()])
-    st = ex.explainer_forward(feat, toks)
+    with pytest.raises(LrpxError):
+        ex.explainer_forward(feat, toks)
+    st = helpers.gridtd_explainer_forward_ops(ex.model, feat, toks)
     assert_close(st["pred"][0], g["predictions"], atol=3e-5, what="predictions")
     assert_close(st["alpha"][0], g["alphas"].reshape(st["alpha"][0].shape), atol=1e-6, what="alphas")
     assert_close(st["beta"][0], g["betas"].reshape(-1), atol=1e-6, what="betas")
