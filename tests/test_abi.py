@@ -40,14 +40,34 @@ def test_version_and_error_reporting():
         _lib.check(-1, "x")
 
 
-def test_struct_layout_matches_header():
-    """The ctypes mirrors must have the C struct sizes (x86-64 SysV: ints then 8-byte pointers)."""
+def test_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors must have the C layout of include/lrpx.h: sizes and the offset of every field, taken from
+    a C program compiled with gcc against the header itself."""
+    import shutil
+    import subprocess
     from lrpx import _lib
-    assert C.sizeof(_lib.ConvShape) == 13 * 4
-    assert C.sizeof(_lib.PoolShape) == 10 * 4
-    assert C.sizeof(_lib.TcConvArgs) == 8 * 4 + 9 * 8
-    assert C.sizeof(_lib.GridTDArgs) == 10 * 4 + len(_lib._GRID_PTRS) * 8
-    assert C.sizeof(_lib.AoaArgs) == 40 + len(_lib._AOA_PTRS) * 8      # 10 ints
+    pairs = [("lrpx_conv_shape", _lib.ConvShape), ("lrpx_pool_shape", _lib.PoolShape),
+             ("lrpx_tc_conv_args", _lib.TcConvArgs), ("lrpx_gridtd_args", _lib.GridTDArgs),
+             ("lrpx_aoa_args", _lib.AoaArgs), ("lrpx_lstm_cell_args", _lib.LstmCellArgs),
+             ("lrpx_ada_attention_args", _lib.AdaAttentionArgs)]
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "lrpx.h"', 'int main(void) {']
+    for cname, ct in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in pairs:
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
 
 
 def test_no_cpu_fallback():
