@@ -1,0 +1,95 @@
+"""GPU, BASELINE.json full size (config 2: gridTD / VGG16, 64 images x 19 words = 1216 explanations, 224x224,
+V = 10000, H = E = 512): the oracle cannot run this in seconds, so the checks are the size-independent properties the
+rules offer — linearity of the relevance chain in its input relevance, independence of a request from the batch it
+is computed in (bit-exact), relevance conservation from the decoder's output to the heat-map, word relevances
+normalised to max |r| = 1 — plus equality of the CUDA-graph replay with the eager launches."""
+import argparse
+import os
+import sys
+
+import pytest
+import torch
+
+import synth
+from conftest import ROOT
+
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def full():
+    import bench
+    from lrpx import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    args = argparse.Namespace(images=64, words=19, vocab=10000, chunk=128)
+    model, ex, imgs, toks = bench.build_problem(args, torch.device(DEV), seed=0)
+    imgs, toks = imgs.to(DEV), toks.to(DEV)
+    eng, W = ex.engine(), ex._lrp_weights()
+    B, T = 64, 19
+    req_img = torch.arange(B, dtype=torch.int32, device=DEV).repeat_interleave(T)
+    req_t = torch.arange(T, dtype=torch.int32, device=DEV).repeat(B)
+    est = eng.forward(imgs)
+    st = ex.explainer_forward(eng.features(est, "pixel"), toks)
+    r_feat, r_words = ops.gridtd_decoder_lrp(st, W, req_img, req_t, toks[:, 1:].reshape(-1).to(torch.int32), tc_gemm=True)
+    heat = eng.relevance(est, r_feat, req_img, chunk=128)
+    torch.cuda.synchronize()
+    return dict(ex=ex, eng=eng, est=est, imgs=imgs, toks=toks, req_img=req_img, req_t=req_t, r_feat=r_feat,
+                r_words=r_words, heat=heat, B=B, T=T)
+
+
+def test_outputs_finite_and_words_normalised(full):
+    assert torch.isfinite(full["heat"]).all() and torch.isfinite(full["r_words"]).all()
+    assert float(full["heat"].abs().max()) > 0
+    # gridTDmodel.py:1129-1132: r_words / max|r_words| over the words 0..t of each request
+    T = full["T"]
+    mask = torch.arange(T, device=DEV)[None, :] <= full["req_t"][:, None]
+    m = (full["r_words"].abs() * mask).amax(1)
+    assert torch.allclose(m, torch.ones_like(m), atol=1e-6), (float(m.min()), float(m.max()))
+    assert float((full["r_words"] * ~mask).abs().max()) == 0.0
+
+
+def test_conservation_decoder_output_to_heatmap(full):
+    """alpha=1/beta=0 without bias conserves relevance layer by layer (lrp_modules.py:81-84,134): the heat-map of a
+    request sums to the relevance the decoder handed to the encoder output, up to bf16 rounding of the chain and the
+    relevance dropped where z+ == 0.  Reported per request; bar: 1e-3 of sum |R| (measured: 7e-5)."""
+    rin = full["heat"].double().flatten(1).sum(1)
+    rout = full["r_feat"].double().flatten(1).sum(1)
+    scale = full["r_feat"].double().flatten(1).abs().sum(1)
+    rel = ((rin - rout).abs() / scale)
+    print(f"conservation |sum R_in - sum R_out| / sum|R_out|: median {float(rel.median()):.3e} max {float(rel.max()):.3e}")
+    assert float(rel.max()) < 1e-3
+
+
+def test_chain_is_linear_in_the_relevance(full):
+    eng, est = full["eng"], full["est"]
+    q = slice(300, 428)                                     # one chunk's worth of requests
+    r1, rimg = full["r_feat"][q], full["req_img"][q]
+    g = torch.Generator(device=DEV).manual_seed(1)
+    r2 = r1[torch.randperm(128, device=DEV, generator=g)] * 0.5
+    h1 = eng.relevance(est, r1, rimg, chunk=128)
+    h2 = eng.relevance(est, r2, rimg, chunk=128)
+    h12 = eng.relevance(est, 2.0 * r1 - 3.0 * r2, rimg, chunk=128)
+    ref = 2.0 * h1.double() - 3.0 * h2.double()
+    err = float((h12.double() - ref).norm() / ref.norm())
+    print(f"linearity rel L2 {err:.3e}")
+    assert err < 5e-3                                        # bf16 storage of s between the 13 layers (measured 5e-4)
+    assert torch.equal(h1, full["heat"][q])                  # same requests in another batch composition: bit-exact
+
+
+def test_request_is_independent_of_its_batch(full):
+    eng, est = full["eng"], full["est"]
+    for q in (0, 517, 1215):
+        alone = eng.relevance(est, full["r_feat"][q:q + 1], full["req_img"][q:q + 1], chunk=1)
+        assert torch.equal(alone[0], full["heat"][q]), q
+
+
+def test_graph_replay_equals_eager_at_full_size(full):
+    from lrpx.pipeline import BatchExplainer
+    pipe = BatchExplainer(full["ex"], chunk=128, use_graph=True)
+    heat, words = pipe.explain(full["imgs"], full["toks"])
+    heat, words = pipe.explain(full["imgs"], full["toks"])      # second call = pure replay
+    torch.cuda.synchronize()
+    assert torch.equal(heat, full["heat"])
+    assert torch.equal(words, full["r_words"])
