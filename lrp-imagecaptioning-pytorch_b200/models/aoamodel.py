@@ -412,6 +412,26 @@ class ExplainAOAAttention(ExplainGridTDAttention):
         self.save_linguistic_explanation(relevance_preceeding_words)
         return relevance_imgs, relevance_preceeding_words
 
+    def explain_region_features(self, images_features, head_idx, beam_size=3, t_list=None):
+        """BASELINE config 3: the AoA decoder on bottom-up region features (1, 36, 2048) with ``AOAModelBU`` —
+        beam search (reference :2059-2135), the explainer's teacher-forced forward (:999-1062) and the decoder
+        relevance (:1064-1156) down to the region features, where the explanation ends (there is no CNN).
+        The reference has no ``Explain*BU`` class; this is ``explain_caption`` without
+        ``explain_cnn``.  -> (list of (1, regions, 2048) relevances, list of (t+1,) word relevances), one per word."""
+        feats = images_features.to(self.device).float()
+        assert feats.dim() == 3 and feats.size(0) == 1
+        self.beam_caption, self.beam_caption_encode = self.model.beam_search(feats, self.word_map, beam_size=beam_size)
+        self.beam_caption_encode = [self.word_map['<start>']] + self.beam_caption_encode
+        toks = torch.tensor([self.beam_caption_encode], dtype=torch.long, device=self.device)
+        st = self.explainer_forward(feats, toks)
+        self._state, self._enc_state, self._feat_hw = st, None, (feats.shape[1], 1)
+        self.caption_length = len(self.beam_caption_encode) - 1
+        self.num_pixels = feats.shape[1]
+        self.predictions, self.alphas = st["pred"][0], st["alpha"][0]
+        ts = list(range(self.caption_length)) if t_list is None else list(t_list)
+        r_feat, r_words = self._decoder_lrp(ts, head_idx)
+        return [r_feat[k:k + 1] for k in range(len(ts))], [r_words[k, :t + 1] for k, t in enumerate(ts)]
+
     def explain_caption_words(self, img_filepath):
         """reference :1183-1194: linguistic relevance only (head 0)."""
         self.img_filepath = img_filepath

@@ -430,9 +430,11 @@ class ExplainGridTDAttention(object):
         # the forward passes are torch tensor ops; every relevance call below goes to liblrpx.so, which raises
         # on non-CUDA tensors (there is no CPU fallback)
         self.device = next(self.model.parameters()).device
-        is_vgg = isinstance(self.model.img_encoder.encoder, nn.Sequential)
+        # bottom-up twins (GridTDModelBU / AOAModelBU) have no CNN: the explanation ends at the region features
+        self.has_encoder = hasattr(self.model, 'img_encoder')
+        is_vgg = self.has_encoder and isinstance(self.model.img_encoder.encoder, nn.Sequential)
         self.precision = precision or ('bf16' if is_vgg else 'fp32')
-        if self.precision == 'bf16' and not is_vgg:
+        if self.precision == 'bf16' and not is_vgg and self.has_encoder:
             raise NotImplementedError("the tensor-core chain supports VGG-style encoders; use precision='fp32'")
         self.mean = [0.485, 0.456, 0.406]
         self.std = [0.229, 0.224, 0.225]

@@ -285,3 +285,61 @@ def test_lrp_tune_step_on_the_real_model():
     assert "fc.weight" in moved and "LanguageLSTM.weight_hh" in moved
     losses = [float(st.step(feats, caps, caplens)[0]) for _ in range(5)]
     assert losses[-1] < float(loss0), (float(loss0), losses)
+
+
+def _aoa_bu_explainer(V, H, E, seed, tmp_path, end_bias=0.0):
+    from models import aoamodel as A
+    model = A.AOAModelBU(E, H, 8, V, "bu")
+    sd = synth.aoa_bu_state(seed, V, H, E)
+    sd["fc.bias"][V - 1] += end_bias
+    model.load_state_dict(sd, strict=True)
+    ex = A.ExplainAOAAttention(_args(E, H, tmp_path), synth.word_map(V), model=model.to(DEV))
+    return ex, sd
+
+
+def test_config3_aoa_bu_region_features_vs_oracle(tmp_path):
+    """BASELINE config 3 at a size the oracle walks in seconds: AOAModelBU on 36 x 2048 region features, beam size 3,
+    relevance of the region features and of the preceding words for every word and two heads vs the oracle's
+    restatement of aoamodel.py:1064-1156 on the same beam-searched caption."""
+    V, H, E = 80, 64, 32
+    ex, sd = _aoa_bu_explainer(V, H, E, 103, tmp_path)      # a seed whose beam search ends with <end> after 9 words
+    feats = synth.bu_features(96, 1)
+    for head in (0, 5):
+        r_feats, r_words = ex.explain_region_features(feats, head)
+        toks = ex.beam_caption_encode
+        assert len(toks) >= 3
+        ost = O.aoa_explainer_forward(sd, feats[0].t().reshape(2048, 36, 1), toks, 8)
+        for t in range(len(toks) - 1):
+            rf, rw, _ = O.aoa_explain_wordt(sd, ost, t, head)
+            scale = float(rf.abs().max())
+            assert_close(r_feats[t][0] / scale, rf / scale, rtol=1e-3, atol=1e-5, what=f"head {head} word {t} r_feat")
+            assert_close(r_words[t], rw, rtol=1e-3, atol=1e-5, what=f"head {head} word {t} r_words")
+
+
+def test_config3_aoa_bu_full_size_properties(tmp_path):
+    """BASELINE config 3 at full size (36 regions x 2048, H = 1024, 8 heads, V = 10000, beam size 3): finite
+    outputs, word relevances normalised to max |r| = 1, a request's result independent of the other requests in
+    the launch (bit-exact), and the error-compensated tensor-core GEMMs within 1e-4 (scale-relative) of the fp32
+    CUDA-core GEMMs."""
+    from lrpx import ops
+    V, H, E = 10000, 1024, 1024
+    ex, sd = _aoa_bu_explainer(V, H, E, 97, tmp_path)
+    feats = synth.bu_features(98, 1)
+    r_feats, r_words = ex.explain_region_features(feats, 3)
+    T = ex.caption_length
+    assert T >= 10 and all(torch.isfinite(r).all() for r in r_feats)
+    for t in range(T):
+        assert abs(float(r_words[t].abs().max()) - 1.0) < 1e-6
+    st, W = ex._state, ex._lrp_weights()
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    toks = ex.beam_caption_encode
+    ts = list(range(T))
+    args = (st, W, 8, i32([0] * T), i32(ts), i32([toks[t + 1] for t in ts]), i32([3] * T))
+    f32_feat, f32_words = ops.aoa_decoder_lrp(*args, tc_gemm=False)
+    tc_feat, tc_words = ops.aoa_decoder_lrp(*args, tc_gemm=True)
+    for t in range(T):
+        scale = float(f32_feat[t].abs().max())
+        assert float((tc_feat[t] - f32_feat[t]).abs().max()) <= 1e-4 * scale, t
+        assert torch.equal(f32_feat[t:t + 1], r_feats[t])               # the API call used the fp32 GEMMs (precision fp32)
+    one = ops.aoa_decoder_lrp(st, W, 8, i32([0]), i32([T - 1]), i32([toks[T]]), i32([3]), tc_gemm=False)[0]
+    assert torch.equal(one[0], f32_feat[T - 1])
