@@ -93,3 +93,39 @@ def test_graph_replay_equals_eager_at_full_size(full):
     torch.cuda.synchronize()
     assert torch.equal(heat, full["heat"])
     assert torch.equal(words, full["r_words"])
+
+
+def test_config5_tuner_weights_and_step_at_full_size():
+    """BASELINE config 5 (lrp_tune, batch 128 per GPU, V = 10000, H = E = 512, 224x224 images): the batched tuner
+    kernel vs the oracle's restatement of get_lrp_weight_step (gridTDmodel.py:549-578) on the full-size logits,
+    bit-exact argmax; then one whole train_lrp iteration (train.py:211-233) on the full model: finite losses,
+    LRP weights in [0, 2], decoder parameters updated, encoder fixed."""
+    import lrp_oracle as O
+    from lrpx import ops, tune
+    from models import gridTDmodel as G
+    V, H, E, B, L = 10000, 512, 512, 128, 21
+    g = torch.Generator().manual_seed(5)
+    logits, h, c = torch.randn(B, V, generator=g), torch.randn(B, H, generator=g), torch.randn(B, H, generator=g)
+    W_fc = torch.randn(V, H, generator=g) * 0.05
+    stop = synth.stop_mask(V)
+    w_ctx, w_h, am = ops.fc_lrp_weights(logits.to(DEV), h.to(DEV), c.to(DEV), W_fc.to(DEV), stop.to(DEV))
+    rc, rh = O.lrp_weight_step(logits, h, c, W_fc, stop)
+    assert torch.equal(am.cpu().long(), logits.argmax(-1))
+    assert float((w_ctx.cpu() - rc).abs().max()) < 1e-5 and float((w_h.cpu() - rh).abs().max()) < 1e-5
+    assert float(w_ctx.min()) >= 0.0 and float(w_ctx.max()) <= 2.0
+    # one full-size training iteration
+    torch.manual_seed(0)
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(1000, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(2000))
+    model.to(DEV)
+    st = tune.LrpTuneStep(model, synth.word_map(V), lr=1e-4, grad_clip=5.0)
+    imgs = torch.randn(B, 3, 224, 224, generator=g).to(DEV)
+    caps = torch.randint(1, V - 4, (B, L), generator=g)
+    caps[:, 0] = V - 2
+    enc_before = model.img_encoder.encoder[0].weight.detach().clone()
+    fc_before = model.fc.weight.detach().clone()
+    loss, ls, ll = st.step(imgs, caps.to(DEV), torch.full((B,), L))
+    assert torch.isfinite(loss) and torch.isfinite(ls) and torch.isfinite(ll)
+    assert torch.equal(enc_before, model.img_encoder.encoder[0].weight.detach())
+    assert not torch.equal(fc_before, model.fc.weight.detach())
