@@ -266,7 +266,7 @@ __device__ __forceinline__ void stg_zero32(void* p) {
 // waits on the accumulator so that the global-load latency overlaps the TMEM read
 __device__ __forceinline__ void epi_mul(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32],
                                         const U8 (&g)[2]) {
-  if (!r.in_range) return;
+  if (!r.in_range || (p.debug_flags & 64)) return;      // 64: timing experiment without the stores
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * p.out_c + col;
   if (!r.valid) {          // padding rows of the PF layout stay exactly zero
     stg_zero32(out);
@@ -387,9 +387,22 @@ __device__ __forceinline__ int epi_units_per_half(const TcParams& p, int epi) {
 // One unit: accumulator row `r` (this thread's), columns [c, c+32) of tile column block n_tile.
 // taddr = TMEM address of column 0 of this row's accumulator (lane quarter, buffer and M half already applied).
 // Global loads of gain / argmax are issued first, then TMEM -> registers, epilogue math, global stores.
+// release_bar != 0 (the warp's LAST unit of the tile): the accumulator buffer is handed back to the MMA issuers as
+// soon as this warp's last TMEM read has landed in registers, i.e. before the epilogue math and the global stores —
+// the stores are the slow part of the epilogue (measured: 8-22 % of a layer's time) and must not sit on the
+// TMEM hand-over path.
+__device__ __forceinline__ void epi_release(uint32_t release_bar) {
+  if (release_bar) {
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(release_bar);
+  }
+}
+
 template <int EPI>
-__device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, uint32_t taddr, int n_tile, int c) {
-  if (p.debug_flags & 16) return;      // timing experiment: epilogue only hands the accumulator back
+__device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, uint32_t taddr, int n_tile, int c,
+                                         uint32_t release_bar) {
+  if (p.debug_flags & 16) { epi_release(release_bar); return; }      // timing experiment: only hands the accumulator back
   RowInfo r = r0;
   if (p.debug_flags & 1) { r.in_range = false; r.valid = false; }
   const int n0 = n_tile * p.bn;
@@ -397,6 +410,7 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
     uint32_t v[16];
     TMEM_LD_X16(taddr, v);
     tmem_ld_wait();
+    epi_release(release_bar);
     epi_input(p, r, v);
   } else if (EPI == LRPX_TC_EPI_FWD_GAIN) {
 #pragma unroll
@@ -405,12 +419,14 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
       TMEM_LD_X16(taddr + c + 16 * q, vw);
       TMEM_LD_X16(taddr + p.half + c + 16 * q, vp);
       tmem_ld_wait();
+      if (q == 1) epi_release(release_bar);
       epi_fwd_gain16(p, r, n_tile * p.half + c + 16 * q, vw, vp);
     }
   } else if (EPI == LRPX_TC_EPI_STORE_F32) {
     uint32_t v[32];
     TMEM_LD_X32(taddr + c, v);
     tmem_ld_wait();
+    epi_release(release_bar);
     if (r.in_range) {
       float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c);
 #pragma unroll
@@ -443,6 +459,7 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
       uint32_t v[16];
       TMEM_LD_X16(taddr + c + 16 * q, v);
       tmem_ld_wait();
+      if (q == 1) epi_release(release_bar);
       if (r.in_range) {
         float* dst = reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c + 16 * q;
 #pragma unroll
@@ -469,7 +486,7 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
 #pragma unroll
     for (int k = 0; k < 8; ++k) g[0].w[k] = g[1].w[k] = 0u;
     s4[0] = s4[1] = make_uint4(0u, 0u, 0u, 0u);
-    if (r.valid) {
+    if (r.valid && !(p.debug_flags & 32)) {      // 32: timing experiment without the gain loads
       g[0] = ldg_nc_v8(p.gain + goff);
       g[1] = ldg_nc_v8(p.gain + goff + 16);
       if (EPI == LRPX_TC_EPI_MUL_UNPOOL) {
@@ -481,6 +498,7 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
       uint32_t v[32];
       TMEM_LD_X32(taddr + c, v);
       tmem_ld_wait();
+      epi_release(release_bar);
       epi_mul(p, r, n0 + c, v, g);
     } else {
 #pragma unroll
@@ -488,6 +506,7 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
         uint32_t v[16];
         TMEM_LD_X16(taddr + c + 16 * q, v);
         tmem_ld_wait();
+        if (q == 1) epi_release(release_bar);
         epi_mul_unpool16(p, r, n0 + c + 16 * q, v, g[q], s4[q]);
       }
     }
@@ -511,16 +530,22 @@ __device__ __forceinline__ void epi_prefetch_unit(const TcParams& p, int row, in
 template <int EPI>
 __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_base /* tile row 0 + quarter*32 + lane */,
                                                   uint32_t taddr_q /* lane quarter + buffer */, int n_tile, int sub,
-                                                  int mh, int pf_row_base /* same for the prefetched tile, or -1 */) {
+                                                  int mh, int pf_row_base /* same for the prefetched tile, or -1 */,
+                                                  uint32_t release_bar /* tmem_empty barrier of the tile's buffer */) {
   const int uph = epi_units_per_half(p, EPI);
   const int n_units = mh * uph;
+  constexpr int step = TC_EPI_WARPS / 4;
+  if (sub >= n_units) {                 // nothing to read for this warp: hand the buffer back at once
+    epi_release(release_bar);
+    return;
+  }
   int h_cached = -1;
   RowInfo r{};
-  for (int u = sub; u < n_units; u += TC_EPI_WARPS / 4) {
+  for (int u = sub; u < n_units; u += step) {
     const int h = u / uph, c = (u - h * uph) << 5;
     if (h != h_cached) { r = row_info(p, row_base + h * TC_BM); h_cached = h; }
     if (pf_row_base >= 0) epi_prefetch_unit<EPI>(p, pf_row_base + h * TC_BM, n_tile, c);
-    epi_unit<EPI>(p, r, taddr_q + (uint32_t)(h * p.bn), n_tile, c);
+    epi_unit<EPI>(p, r, taddr_q + (uint32_t)(h * p.bn), n_tile, c, (u + step >= n_units) ? release_bar : 0u);
   }
 }
 
@@ -631,10 +656,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(smem_u32(&tmem_full_bar[buf]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
-      run_epilogue_tile<EPI>(p, m_tile * TC_BM + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, 1, -1);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+      run_epilogue_tile<EPI>(p, m_tile * TC_BM + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, 1, -1,
+                             smem_u32(&tmem_empty_bar[buf]));
     }
   }
 
@@ -889,10 +912,8 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int pf_row = (tile_pf < num_tiles && tile_pf % p.num_n_tiles == n_tile)
                              ? (tile_pf / p.num_n_tiles) * tile_rows + quarter * 32 + lane : -1;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
-      run_epilogue_tile<EPI>(p, m_tile * tile_rows + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh, pf_row);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+      run_epilogue_tile<EPI>(p, m_tile * tile_rows + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh, pf_row,
+                             smem_u32(&tmem_empty_bar[buf]));
     }
   }
 
