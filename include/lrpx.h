@@ -233,6 +233,29 @@ typedef struct {
 
 int lrpx_lstm_cell_f32(const lrpx_lstm_cell_args* args, void* stream);
 
+/* One LSTM time step as ONE kernel: skinny fp32 GEMM (B <= a few hundred rows) + the cell update of
+ * lrpx_lstm_cell_f32 in its epilogue.     z[b][g*H + j] = add[b][g*H + j] + sum_k x[b][k] * W[k][g*H + j]
+ * G = 4 (gates i,f,g,o) or 5 (+ the sentinel gate pre-activation, gridTDmodel.py:982).  Each CTA owns 4 hidden
+ * units with all their G gate columns, so the cell update needs no second pass.  `wp` is W re-laid out once by
+ * lrpx_lstm_prep_weights_f32 as [H/4][G][4][K] (each CTA's 4*G weight rows contiguous, k fastest). */
+int lrpx_lstm_prep_weights_f32(const float* w /* (K, G*H) row-major */, float* wp, int K, int G, int H, void* stream);
+
+typedef struct {
+  int B, H, K, G;
+  const float* x;         long long ldx;        /* (B,K) concatenated recurrent inputs                       */
+  const float* wp;                              /* prepared weights                                          */
+  const float* add;       long long ld_add;     /* (B,G*H) addend rows, or one (G*H) row with ld_add = 0     */
+  const float* c_prev;    long long ld_cprev;
+  float *h, *c;           long long ld_state;
+  float *g, *i, *f, *s;   long long ld_gate;    /* s: sentinel, required when G == 5                         */
+  float* h_copy0;         long long ld_copy0;
+  float* h_copy1;         long long ld_copy1;
+  float* h_copy2;         long long ld_copy2;
+  float* s_copy;          long long ld_s_copy;
+} lrpx_lstm_step_args;
+
+int lrpx_lstm_step_f32(const lrpx_lstm_step_args* args, void* stream);
+
 /* AdaptiveAttention.forward (gridTDmodel.py:61-103), one block per image:
  *   z[p] = w_h . tanh(img_proj[b,p,:] + hproj[b,p]) (sic, needs P == K);  alpha = softmax z;  ctx = sum_p alpha[p] A[b,p,:]
  *   zs = w_h . tanh(sproj[b,:] + hproj[b,:]);  beta = softmax([z; zs])[-1];  ctx_hat = beta*s + (1-beta)*ctx */
@@ -240,13 +263,16 @@ typedef struct {
   int B, P, K, H;                              /* K = n_pixel of the attention projections */
   const float* A;                              /* (B,P,H) projected features, pixel-major  */
   const float* img_proj;                       /* (B,P,K) W_v_proj(A)                      */
-  const float* hs_proj;   long long ld_hs;     /* (B,2K): [W_g_proj(h) | W_s_proj(s)+bias]  */
+  const float* hs_proj;   long long ld_hs;     /* (B,2K): [W_g_proj(h) | W_s_proj(s)+bias], or NULL: computed in the
+                                                  kernel from h, s and the projection weights below            */
   const float* w_h;                            /* (K)                                      */
   const float* s;         long long ld_s;      /* (B,H) sentinel                           */
   float *ctx, *ctx_hat;   long long ld_out;
   float* alpha;           long long ld_alpha;  /* (B,P) rows */
   float* beta;            long long ld_beta;   /* (B) */
   float* ctx_hat_copy;    long long ld_copy;   /* optional */
+  const float* h;         long long ld_h;      /* (B,H) hidden state (hs_proj == NULL)      */
+  const float *W_g, *W_s, *b_s;                /* (K,H), (K,H), (K) projection weights      */
 } lrpx_ada_attention_args;
 
 int lrpx_adaptive_attention_f32(const lrpx_ada_attention_args* args, void* stream);

@@ -56,11 +56,19 @@ class LstmCellArgs(C.Structure):
                 ("ld_copy1", _LL), ("h_copy2", _P), ("ld_copy2", _LL), ("s_copy", _P), ("ld_s_copy", _LL)]
 
 
+class LstmStepArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("K", C.c_int), ("G", C.c_int), ("x", _P), ("ldx", _LL), ("wp", _P),
+                ("add", _P), ("ld_add", _LL), ("c_prev", _P), ("ld_cprev", _LL), ("h", _P), ("c", _P),
+                ("ld_state", _LL), ("g", _P), ("i", _P), ("f", _P), ("s", _P), ("ld_gate", _LL), ("h_copy0", _P),
+                ("ld_copy0", _LL), ("h_copy1", _P), ("ld_copy1", _LL), ("h_copy2", _P), ("ld_copy2", _LL),
+                ("s_copy", _P), ("ld_s_copy", _LL)]
+
+
 class AdaAttentionArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("P", C.c_int), ("K", C.c_int), ("H", C.c_int), ("A", _P), ("img_proj", _P),
                 ("hs_proj", _P), ("ld_hs", _LL), ("w_h", _P), ("s", _P), ("ld_s", _LL), ("ctx", _P), ("ctx_hat", _P),
                 ("ld_out", _LL), ("alpha", _P), ("ld_alpha", _LL), ("beta", _P), ("ld_beta", _LL),
-                ("ctx_hat_copy", _P), ("ld_copy", _LL)]
+                ("ctx_hat_copy", _P), ("ld_copy", _LL), ("h", _P), ("ld_h", _LL), ("W_g", _P), ("W_s", _P), ("b_s", _P)]
 
 
 # every symbol include/lrpx.h declares: name -> (restype, argtypes)
@@ -88,6 +96,8 @@ SYMBOLS = {
     "lrpx_fc_lrp_weights_f32": (_i, [_P, _P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
     "lrpx_lstm_cell_f32": (_i, [C.POINTER(LstmCellArgs), _P]),
     "lrpx_adaptive_attention_f32": (_i, [C.POINTER(AdaAttentionArgs), _P]),
+    "lrpx_lstm_prep_weights_f32": (_i, [_P, _P, _i, _i, _i, _P]),
+    "lrpx_lstm_step_f32": (_i, [C.POINTER(LstmStepArgs), _P]),
     "lrpx_tc_conv": (_i, [C.POINTER(TcConvArgs), _P]),
     "lrpx_tc_gemm_bf16_f32": (_i, [_P, _P, _P, _i, _i, _i, _P]),
     "lrpx_weight_prep_bf16": (_i, [_P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),

@@ -323,9 +323,46 @@ def lstm_cell(z, c_prev, h, c, g, i, f, gate_pre=None, s=None, h_copy0=None, h_c
     check(lib().lrpx_lstm_cell_f32(C.byref(a), _stream()), "lrpx_lstm_cell_f32")
 
 
-def adaptive_attention(A, img_proj, hs_proj, w_h, s, ctx, ctx_hat, alpha, beta, ctx_hat_copy=None):
+def lstm_prep_weights(w, G):
+    """lrpx_lstm_prep_weights_f32: (K, G*H) fp32 row-major -> the [H/4][G][4][K] layout lrpx_lstm_step_f32 reads."""
+    w = _f32(w, "w")
+    K, GH = w.shape
+    out = torch.empty(GH * K, device=w.device, dtype=torch.float32)
+    check(lib().lrpx_lstm_prep_weights_f32(_ptr(w), _ptr(out), K, G, GH // G, _stream()), "lrpx_lstm_prep_weights_f32")
+    return out
+
+
+def lstm_step(x, wp, add, G, c_prev, h, c, g, i, f, s=None, h_copy0=None, h_copy1=None, h_copy2=None, s_copy=None):
+    """lrpx_lstm_step_f32: z = add + x @ W (skinny fp32 GEMM) and the LSTM cell rule in one kernel.  x (B,K) row
+    view, wp from lstm_prep_weights, add (B,G*H) rows or a (G*H,) vector; the other arguments as in lstm_cell."""
+    B, H = c_prev.shape
+    for t in (x, wp, add, c_prev, h, c, g, i, f):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise _lib.LrpxError("lstm_step needs fp32 CUDA tensors: lrpx has no CPU fallback")
+    if _ld(h) != _ld(c) or not (_ld(g) == _ld(i) == _ld(f)) or (s is not None and _ld(s) != _ld(g)):
+        raise _lib.LrpxError("h/c and g/i/f/s must share their row strides")
+    a = _lib.LstmStepArgs(B=B, H=H, K=x.shape[1], G=G)
+    a.x, a.ldx, a.wp = x.data_ptr(), _ld(x), wp.data_ptr()
+    a.add, a.ld_add = add.data_ptr(), (0 if add.dim() == 1 else _ld(add))
+    a.c_prev, a.ld_cprev = c_prev.data_ptr(), _ld(c_prev)
+    a.h, a.c, a.ld_state = h.data_ptr(), c.data_ptr(), _ld(h)
+    a.g, a.i, a.f, a.ld_gate = g.data_ptr(), i.data_ptr(), f.data_ptr(), _ld(g)
+    if s is not None:
+        a.s = s.data_ptr()
+    for name, ldn, t in (("h_copy0", "ld_copy0", h_copy0), ("h_copy1", "ld_copy1", h_copy1), ("h_copy2", "ld_copy2", h_copy2),
+                         ("s_copy", "ld_s_copy", s_copy)):
+        if t is not None:
+            setattr(a, name, t.data_ptr())
+            setattr(a, ldn, _ld(t))
+    check(lib().lrpx_lstm_step_f32(C.byref(a), _stream()), "lrpx_lstm_step_f32")
+
+
+def adaptive_attention(A, img_proj, hs_proj, w_h, s, ctx, ctx_hat, alpha, beta, ctx_hat_copy=None, h=None, W_g=None,
+                       W_s=None, b_s=None):
     """lrpx_adaptive_attention_f32 (AdaptiveAttention.forward, gridTDmodel.py:61-103); outputs written in place.
-    A (B,P,H), img_proj (B,P,K) contiguous; hs_proj (B,2K); s/ctx/ctx_hat (B,H) row views; alpha (B,P); beta (B,)."""
+    A (B,P,H), img_proj (B,P,K) contiguous; hs_proj (B,2K) or None (then h (B,H) and the projection weights W_g, W_s
+    (K,H), b_s (K) are given and the projections are computed in the kernel); s/ctx/ctx_hat (B,H) row views;
+    alpha (B,P); beta (B,)."""
     B, P, H = A.shape
     K = img_proj.shape[2]
     if not (A.is_cuda and A.is_contiguous() and img_proj.is_contiguous() and w_h.is_contiguous()):
@@ -334,7 +371,14 @@ def adaptive_attention(A, img_proj, hs_proj, w_h, s, ctx, ctx_hat, alpha, beta, 
         raise _lib.LrpxError("ctx / ctx_hat must share their row stride")
     a = _lib.AdaAttentionArgs(B=B, P=P, K=K, H=H)
     a.A, a.img_proj, a.w_h = A.data_ptr(), img_proj.data_ptr(), w_h.data_ptr()
-    a.hs_proj, a.ld_hs = hs_proj.data_ptr(), _ld(hs_proj)
+    if hs_proj is not None:
+        a.hs_proj, a.ld_hs = hs_proj.data_ptr(), _ld(hs_proj)
+    else:
+        for t in (W_g, W_s, b_s):
+            if t is None or not t.is_contiguous() or t.dtype != torch.float32:
+                raise _lib.LrpxError("W_g, W_s, b_s must be contiguous fp32 tensors when hs_proj is None")
+        a.h, a.ld_h = h.data_ptr(), _ld(h)
+        a.W_g, a.W_s, a.b_s = W_g.data_ptr(), W_s.data_ptr(), b_s.data_ptr()
     a.s, a.ld_s = s.data_ptr(), _ld(s)
     a.ctx, a.ctx_hat, a.ld_out = ctx.data_ptr(), ctx_hat.data_ptr(), _ld(ctx)
     a.alpha, a.ld_alpha = alpha.data_ptr(), _ld(alpha)

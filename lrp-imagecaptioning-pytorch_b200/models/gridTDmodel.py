@@ -500,6 +500,28 @@ class ExplainGridTDAttention(object):
         B, C, h, w = fmap.shape
         return fmap.flatten(2).transpose(1, 2).contiguous(), (h, w), None
 
+    def _explainer_weights(self, quirk_double_bias_ih=True):
+        """Concatenated / re-laid-out weights of the fused explainer forward, cached until a parameter changes
+        (the cache key holds every source tensor's data pointer and in-place version counter)."""
+        m = self.model
+        cell, L, xg, hg = m.AdaLSTM.lstm_cell, m.LanguageLSTM, m.AdaLSTM.x_gate, m.AdaLSTM.h_gate
+        src = [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, xg.weight, xg.bias, hg.weight, hg.bias,
+               L.weight_ih, L.weight_hh, L.bias_ih, L.bias_hh]
+        key = (quirk_double_bias_ih,) + tuple((t.data_ptr(), t._version) for t in src)
+        if getattr(self, "_expl_w_key", None) != key:
+            H = m.hidden_dim
+            with torch.no_grad():
+                # x1 = [h2, glob, emb] (:975): recurrent part [h2 | h1] -> (4H gates | sentinel gate), input part [glob | emb]
+                W1_rec = torch.cat((torch.cat((cell.weight_ih[:, :H], cell.weight_hh), 1),
+                                    torch.cat((xg.weight[:, :H], hg.weight), 1)), 0).t().contiguous()      # (2H, 5H)
+                W1_in = torch.cat((cell.weight_ih[:, H:], xg.weight[:, H:]), 0).t().contiguous()           # (2E, 5H)
+                b1 = torch.cat((cell.bias_ih + cell.bias_hh, xg.bias + hg.bias)).contiguous()
+                W2 = torch.cat((L.weight_ih, L.weight_hh), 1).t().contiguous()                             # (3H, 4H)
+                b2 = (L.bias_ih + (L.bias_ih if quirk_double_bias_ih else L.bias_hh)).contiguous()        # Q3 (:789)
+                self._expl_w = (ops.lstm_prep_weights(W1_rec, 5), W1_in, b1, ops.lstm_prep_weights(W2, 4), b2)
+            self._expl_w_key = key
+        return self._expl_w
+
     def explainer_forward(self, feat, tokens, quirk_double_bias_ih=True):
         """The explainer's teacher-forced forward (reference :941-1012) batched over images.
 
@@ -507,8 +529,9 @@ class ExplainGridTDAttention(object):
         state in the kernels' layout (lrpx_gridtd_args), T = L-1 steps.  ``quirk_double_bias_ih`` reproduces the
         explainer's language LSTM adding bias_ih twice (:789, Q3).
 
-        On a CUDA device a time step is 3 library GEMMs over concatenated inputs + 3 fused kernels
-        (``lrpx_lstm_cell_f32`` x2, ``lrpx_adaptive_attention_f32``) writing straight into the saved-state tensors;
+        A time step is three kernels writing straight into the saved-state tensors: ``lrpx_lstm_step_f32`` (skinny
+        GEMM over the concatenated recurrent inputs + cell rule) for the AdaLSTM, ``lrpx_adaptive_attention_f32``
+        (both attention projections + attention + sentinel mix), ``lrpx_lstm_step_f32`` for the language LSTM;
         everything that does not depend on the recurrent state (embeddings, the input-side halves of the gate
         pre-activations, the vocabulary projection) is one batched GEMM over all T steps.  CUDA only: there is no
         CPU form in the product (tests/helpers.py holds the step-by-step tensor-op restatement the kernels are
@@ -533,16 +556,10 @@ class ExplainGridTDAttention(object):
             glob = glob_pre.clamp(min=0)
             img_proj = att.W_v_proj(A).contiguous()                                  # (B,P,K)
             cell, L = m.AdaLSTM.lstm_cell, m.LanguageLSTM
-            lb2 = L.bias_ih if quirk_double_bias_ih else L.bias_hh
-            # ---- weights of the concatenated GEMMs (x1 = [h2, glob, emb], :975-983)
-            xg, hg = m.AdaLSTM.x_gate, m.AdaLSTM.h_gate
-            W1_rec = torch.cat((torch.cat((cell.weight_ih[:, :H], cell.weight_hh), 1),           # [h2 | h1] -> 4H
-                                torch.cat((xg.weight[:, :H], hg.weight), 1)), 0).t().contiguous()  # ... -> gate (H)
-            W1_in = torch.cat((cell.weight_ih[:, H:], xg.weight[:, H:]), 0).t().contiguous()       # [glob | emb] -> 5H
-            b1 = torch.cat((cell.bias_ih + cell.bias_hh, xg.bias + hg.bias))
-            W2 = torch.cat((L.weight_ih, L.weight_hh), 1).t().contiguous()                          # [ctx_hat | h1 | h2] -> 4H
-            b2 = L.bias_ih + lb2
-            Wa = torch.zeros(2 * H, 2 * K, device=dev)                                              # [h1 | s] -> [W_g h1 | W_s s]
+            W1p, W1_in, b1, W2p, b2 = self._explainer_weights(quirk_double_bias_ih)
+            # both attention projections as ONE library GEMM per step: [h1 | s] @ blockdiag(W_g^T, W_s^T) + [0 | b_s]
+            # (computing them inside the attention kernel re-reads 0.8 MB of weights per image and step: measured slower)
+            Wa = torch.zeros(2 * H, 2 * K, device=dev)
             Wa[:H, :K] = att.W_g_proj.weight.t()
             Wa[H:, K:] = att.W_s_proj.weight.t()
             ba = torch.cat((torch.zeros(K, device=dev), att.W_s_proj.bias))
@@ -555,21 +572,23 @@ class ExplainGridTDAttention(object):
             h1, c1, h2, c2 = (torch.zeros(B, T + 1, H, device=dev) for _ in range(4))
             g1, i1, f1, g2, i2, f2, st, ctx, ctx_hat = (new(B, T, H) for _ in range(9))
             alpha, beta = new(B, T, P), new(B, T)
-            # ---- staging rows of the GEMMs
-            hcat = torch.zeros(B, 2 * H, device=dev)          # [h2_t | h1_t]
+            # ---- staging rows of the recurrent GEMMs, ping-ponged over the steps: a step kernel reads ALL columns of
+            # its input rows in every CTA while its CTAs write the new state, so the new state goes to the other copy
+            hcat = torch.zeros(2, B, 2 * H, device=dev)       # [h2_t | h1_t]
+            x2c = torch.zeros(2, B, 3 * H, device=dev)        # [ctx_hat_t | h1_{t+1} | h2_t]
             hs = new(B, 2 * H)                                # [h1_{t+1} | s_t]
-            x2c = torch.zeros(B, 3 * H, device=dev)           # [ctx_hat_t | h1_{t+1} | h2_t]
             for t in range(T):
-                z1 = torch.addmm(pre1[t], hcat, W1_rec)                                           # (B,5H)
-                ops.lstm_cell(z1, c1[:, t], h1[:, t + 1], c1[:, t + 1], g1[:, t], i1[:, t], f1[:, t],
-                              gate_pre=z1[:, 4 * H:], s=st[:, t], h_copy0=hcat[:, H:], h_copy1=x2c[:, H:2 * H],
+                p, q = t & 1, (t & 1) ^ 1
+                # AdaLSTM: 4 gates + sentinel gate from [h2_t | h1_t] (+ the input-side halves in pre1[t])   :975-983
+                ops.lstm_step(hcat[p], W1p, pre1[t], 5, c1[:, t], h1[:, t + 1], c1[:, t + 1], g1[:, t], i1[:, t],
+                              f1[:, t], s=st[:, t], h_copy0=hcat[q][:, H:], h_copy1=x2c[p][:, H:2 * H],
                               h_copy2=hs[:, :H], s_copy=hs[:, H:])
                 hsp = torch.addmm(ba, hs, Wa)                                                     # (B,2K)
                 ops.adaptive_attention(A, img_proj, hsp, w_h, st[:, t], ctx[:, t], ctx_hat[:, t], alpha[:, t],
-                                       beta[:, t], ctx_hat_copy=x2c[:, :H])
-                z2 = torch.addmm(b2, x2c, W2)                                                     # (B,4H)
-                ops.lstm_cell(z2, c2[:, t], h2[:, t + 1], c2[:, t + 1], g2[:, t], i2[:, t], f2[:, t],
-                              h_copy0=hcat[:, :H], h_copy1=x2c[:, 2 * H:])
+                                       beta[:, t], ctx_hat_copy=x2c[p][:, :H])
+                # LanguageLSTM from [ctx_hat_t | h1_{t+1} | h2_t]                                             :984-990
+                ops.lstm_step(x2c[p], W2p, b2, 4, c2[:, t], h2[:, t + 1], c2[:, t + 1], g2[:, t], i2[:, t], f2[:, t],
+                              h_copy0=hcat[q][:, :H], h_copy1=x2c[q][:, 2 * H:])
             pred = torch.addmm(m.fc.bias, (ctx_hat + h2[:, 1:]).view(B * T, H), m.fc.weight.t()).view(B, T, -1)
             x1 = torch.cat((h2[:, :T], xin), -1)
             x2 = torch.cat((ctx_hat, h1[:, 1:]), -1)
