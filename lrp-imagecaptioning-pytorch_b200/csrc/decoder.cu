@@ -346,38 +346,59 @@ __global__ void grid_attn_kernel(lrpx_gridtd_args a, GridWs w) {
     w.wproj[((size_t)q * a.P + p) * a.H + h] = acc / stab(a.A_pre[o0 + h]);
   }
 }
-// Same rule, one block per request and one thread per hidden unit: the thread keeps its (t+1) values of uctx in
-// registers and walks the pixels, so uctx is read once per request instead of once per (request, pixel), and the
-// result can leave directly as the split bf16 operand [hi | hi | lo] of the tensor-core projector GEMM.
-constexpr int ATT_MAX_T = 32;
+// Same rule, one block per request and one thread per hidden unit.  The request's alpha rows ((t+1) x P) and uctx
+// rows ((t+1) x H) sit in shared memory; a thread walks the pixels four at a time: per step i one LDS (uctx) + one
+// LDS.128 (four alphas, broadcast) feed four FMAs, i = t..0 like the reference loop, then
+// wproj = A * acc / stab(A_pre).  (The per-(request, pixel) form above re-reads uctx 196 times and spends ~4
+// instructions per multiply-add: 1.4 ms per 1216 requests; this form is bound by its 0.7 GB of output.)
+// SPLIT: the result leaves directly as the split bf16 operand [hi | hi | lo] of the tensor-core projector GEMM.
 template <bool SPLIT>
 __global__ void __launch_bounds__(512) grid_attn_rows_kernel(lrpx_gridtd_args a, GridWs w) {
-  extern __shared__ float al_s[];          // alpha[b][0..t][:]  ((t+1) x P)
+  extern __shared__ __align__(16) float att_s[];          // alpha[(t+1)][P4] | uctx[(t+1)][H]
   const int q = blockIdx.x;
   const int b = a.req_img[q], t = a.req_t[q];
-  const int H = a.H, P = a.P;
-  for (int k = threadIdx.x; k < (t + 1) * P; k += blockDim.x) al_s[k] = a.alpha[(size_t)b * a.T * P + k];
+  const int H = a.H, P = a.P, P4 = (P + 3) & ~3;
+  float* al_s = att_s;
+  float* u_s = att_s + (size_t)(t + 1) * P4;
+  for (int k = threadIdx.x; k < (t + 1) * P4; k += blockDim.x) {
+    const int i = k / P4, p = k - i * P4;
+    al_s[k] = p < P ? a.alpha[((size_t)b * a.T + i) * P + p] : 0.f;
+  }
+  for (int k = threadIdx.x; k < (t + 1) * H; k += blockDim.x) u_s[k] = w.uctx[(size_t)q * a.T * H + k];
   __syncthreads();
   for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    float u[ATT_MAX_T];
+    for (int p0 = 0; p0 < P; p0 += 4) {
+      float Av[4], Ap[4];
 #pragma unroll
-    for (int i = 0; i < ATT_MAX_T; ++i) u[i] = i <= t ? w.uctx[((size_t)q * a.T + i) * H + h] : 0.f;
-    for (int p = 0; p < P; ++p) {
-      const size_t o0 = ((size_t)b * P + p) * H + h;
-      const float Av = a.A[o0];
-      float acc = 0.f;
+      for (int k = 0; k < 4; ++k) {
+        const bool ok = p0 + k < P;
+        const size_t o0 = ((size_t)b * P + (ok ? p0 + k : 0)) * H + h;
+        Av[k] = ok ? __ldg(a.A + o0) : 0.f;
+        Ap[k] = ok ? __ldg(a.A_pre + o0) : 1.f;
+      }
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = t; i >= 0; --i) {
+        const float uv = u_s[i * H + h];
+        const float4 a4 = *reinterpret_cast<const float4*>(al_s + i * P4 + p0);
+        acc[0] = fmaf(a4.x, uv, acc[0]);
+        acc[1] = fmaf(a4.y, uv, acc[1]);
+        acc[2] = fmaf(a4.z, uv, acc[2]);
+        acc[3] = fmaf(a4.w, uv, acc[3]);
+      }
 #pragma unroll
-      for (int i = ATT_MAX_T - 1; i >= 0; --i)       // same summation order as the reference loop: i = t .. 0
-        if (i <= t) acc += al_s[i * P + p] * u[i] * Av;
-      const float r = acc / stab(a.A_pre[o0]);
-      const size_t row = (size_t)q * P + p;
-      if (SPLIT) {
-        __nv_bfloat16 hi, lo;
-        split_bf16(r, hi, lo);
-        __nv_bfloat16* o = w.a3 + row * 3 * H;
-        o[h] = hi; o[H + h] = hi; o[2 * H + h] = lo;
-      } else {
-        w.wproj[row * H + h] = r;
+      for (int k = 0; k < 4; ++k) {
+        if (p0 + k >= P) break;
+        const size_t row = (size_t)q * P + p0 + k;
+        if (SPLIT) {
+          // the quotient is split into bf16 hi + lo (16 mantissa bits): the 2-ulp division is far below that
+          const float r = __fdividef(acc[k] * Av[k], stab(Ap[k]));
+          __nv_bfloat16 hi, lo;
+          split_bf16(r, hi, lo);
+          __nv_bfloat16* o = w.a3 + row * 3 * H;
+          o[h] = hi; o[H + h] = hi; o[2 * H + h] = lo;
+        } else {
+          w.wproj[row * H + h] = acc[k] * Av[k] / stab(Ap[k]);
+        }
       }
     }
   }
@@ -676,9 +697,15 @@ int lrpx_gridtd_decoder_lrp_f32(const lrpx_gridtd_args* a, void* workspace, size
   RUN(gemm_any<GE_STORE>(w.u, a->W_glob, w3_glob, w.a3, w.v, Q, a->C, E, none, st));
   grid_avg_kernel<<<Q, 128, 0, st>>>(*a, w);
   GemmEpi fe{a->feat, nullptr, w.coefavg, a->req_img, a->P};
-  const size_t att_smem = (size_t)T * a->P * sizeof(float);
-  if (T <= ATT_MAX_T && att_smem <= 48 * 1024) {
+  const size_t att_smem = (size_t)T * (((a->P + 3) & ~3) + H) * sizeof(float);
+  if (att_smem <= 160 * 1024) {
     const int at = H >= 512 ? 512 : (H >= 256 ? 256 : 128);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(grid_attn_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      cudaFuncSetAttribute(grid_attn_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      attr_done = true;
+    }
     if (w3_proj) grid_attn_rows_kernel<true><<<Q, at, att_smem, st>>>(*a, w);
     else grid_attn_rows_kernel<false><<<Q, at, att_smem, st>>>(*a, w);
     RUN(gemm_any<GE_FEAT>(w.wproj, a->W_proj, w3_proj, w.a3, a->r_feat, Q * a->P, a->C, H, fe, st, w3_proj != nullptr));
