@@ -214,7 +214,7 @@ def run_ours(args):
         marks[3].record()
         eng.relevance(est, r_feat, req_img, chunk=args.chunk, out=heat); marks[4].record()
         torch.cuda.synchronize()
-        names = ["encoder_forward_gains", "explainer_forward_torch", "decoder_relevance", "encoder_relevance_chain"]
+        names = ["encoder_forward_gains", "explainer_forward", "decoder_relevance", "encoder_relevance_chain"]
         calls = {k: _lib.CALLS[k] - calls0.get(k, 0) for k in _lib.CALLS}
         return {n: round(marks[i].elapsed_time(marks[i + 1]), 3) for i, n in enumerate(names)}, calls
 
@@ -241,10 +241,11 @@ def run_ours(args):
     step_eager_ms = sum(phase_ms.values())
 
     # launches of OUR kernels inside the timed region: one per C-ABI call, except the decoder call which
-    # enqueues 4 weight splits + init + per step (3 element-wise + 2 x (split + tensor-core GEMM)) + 9 tail kernels
-    # (csrc/decoder.cu, LRPX_DEC_TC_GEMM path)
+    # enqueues 4 weight splits + init + per step (3 element-wise + 2 x (split + tensor-core GEMM)) + 7 tail kernels
+    # (glob, split + GEMM, avg, attention rows, projector GEMM with fused epilogue, word norm; csrc/decoder.cu,
+    # LRPX_DEC_TC_GEMM path)
     launches = sum(v for k, v in calls.items() if k != "lrpx_gridtd_decoder_lrp_f32")
-    launches += calls.get("lrpx_gridtd_decoder_lrp_f32", 0) * (5 + 7 * T + 9)
+    launches += calls.get("lrpx_gridtd_decoder_lrp_f32", 0) * (5 + 7 * T + 7)
     launches *= args.steps          # the same kernels per step whether launched eagerly or replayed from the graph
 
     out = None
