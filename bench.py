@@ -272,9 +272,10 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "tc_conv_kernel<MUL|MUL_UNPOOL|INPUT> (encoder relevance chain)",
                          "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tf_sustained"], "traffic": chain_traffic(args.chunk),
-                         "traffic_note": "dram read+write bytes of the 13 chain launches of one chunk (ncu --set full, "
-                                         "profiles/r1_chain_full.md); algorithmic FLOPs per chunk = chunk x "
-                                         "algorithmic_gflop_per_explanation",
+                         "traffic_note": "dram read+write bytes of the 13 chain layers per chunk of explanations (ncu --set "
+                                         "full of the 8 low-resolution launches over 1216 requests + the 5 launches "
+                                         "of one 128-request chunk, profiles/r1_chain_full.md); algorithmic FLOPs per "
+                                         "chunk = chunk x algorithmic_gflop_per_explanation",
                          "peak_source": pk["src"] + " sustained bf16",
                          "share_of_step": phase_ms["encoder_relevance_chain"] / step_eager_ms,
                          "algorithmic_gflop_per_explanation": eng.flops_per_explanation() / 1e9},
@@ -307,14 +308,16 @@ def bind_to_gpu_numa_node(index):
 
 
 def chain_traffic(chunk):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the relevance-chain launches of one chunk, from the committed
-    ncu --set full capture (profiles/r1_chain_full.json, written by scripts/ncu_summary.py); None if absent or if
-    the capture was taken with another chunk size."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the relevance-chain launches, per `chunk` explanations, from the
+    committed ncu --set full capture of all chain launches of one step (profiles/r1_chain_full.json, written by
+    scripts/ncu_summary.py); None if absent."""
     path = os.path.join(ROOT, "profiles", "r1_chain_full.json")
-    if not os.path.exists(path) or chunk != 128:
+    if not os.path.exists(path):
         return None
     d = json.load(open(path))
-    return d["dram_bytes_read"] + d["dram_bytes_write"]
+    if not d.get("dram_bytes_per_explanation"):
+        return None
+    return d["dram_bytes_per_explanation"] * chunk
 
 
 def layer_table(eng, chunk, dev, pk):

@@ -56,6 +56,13 @@ def full(src, dst, cmd):
         f.write(f"# ncu --set full capture (tc_conv_kernel)\n\ncommand: `{cmd}`\n\n| # | kernel | " +
                 " | ".join(f"{c} [{units[idx[c]]}]" for c in cols) + " |\n|" + "---|" * (len(cols) + 2) + "\n")
         tot_r = tot_w = tot_t = 0.0
+        # explanations covered by each captured launch, e.g. "1216x8,128x5" (8 launches over 1216 requests, then 5 over 128)
+        per_launch = []
+        if len(sys.argv) > 5:
+            for part in sys.argv[5].split(","):
+                n, _, c = part.partition("x")
+                per_launch += [int(n)] * int(c or 1)
+        bytes_per_expl = 0.0
         for i, r in enumerate(rows[2:]):
             name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "")
             f.write(f"| {i} | `{name}` | " + " | ".join(r[idx[c]] for c in cols) + " |\n")
@@ -63,12 +70,16 @@ def full(src, dst, cmd):
             tot_r += float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
             tot_w += float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
             tot_t += float(r[idx["gpu__time_duration.sum"]]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}[units[idx["gpu__time_duration.sum"]]]
+            if i < len(per_launch):
+                bytes_per_expl += (float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]] +
+                                   float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]) / per_launch[i]
         f.write(f"\nall {len(rows) - 2} launches: dram read {tot_r / 1e6:.1f} MB + write {tot_w / 1e6:.1f} MB = "
                 f"{(tot_r + tot_w) / 1e6:.1f} MB in {tot_t:.1f} us\n")
     # machine-readable copy for bench.py's roofline.traffic
     import json
     json.dump({"launches": len(rows) - 2, "dram_bytes_read": tot_r, "dram_bytes_write": tot_w, "gpu_time_us": tot_t,
-               "command": cmd, "source": dst}, open(dst.replace(".md", ".json"), "w"), indent=1)
+               "explanations_per_launch": per_launch, "dram_bytes_per_explanation": bytes_per_expl, "command": cmd,
+               "source": dst}, open(dst.replace(".md", ".json"), "w"), indent=1)
     print(open(dst).read())
 
 
