@@ -301,8 +301,13 @@ class TcVggEngine:
         top = self.convs[split - 1]           # first layer of stage 2: its input is (h, w, cout) of that layer
         max_elems = max(pf_rows(chunk, c.h, c.w) * c.cout for c in self.convs[:split])
         buf = [torch.empty(max_elems, device=dev, dtype=torch.bfloat16) for _ in range(2)]
-        for q0 in range(0, Q, chunk):
-            q1 = min(Q, q0 + chunk)
+        bounds = list(range(0, Q, chunk)) + [Q]
+        if on_chunk is not None and bounds[-1] - bounds[-2] > 32:
+            # results are being delivered chunk by chunk (device->host copy under the next chunk's kernels): the copy
+            # of the LAST chunk has nothing to hide under, so finish with a short one
+            last = bounds[-1] - bounds[-2]
+            bounds.insert(-1, bounds[-1] - max(16, last // 4))
+        for q0, q1 in zip(bounds[:-1], bounds[1:]):
             nq = q1 - q0
             rimg = row_img[q0:q1]
             if s_all is not None:
