@@ -238,7 +238,30 @@ class TcVggEngine:
         """Image relevance for Q requests.  r_feat: fp32 (Q, h*w, C) pixel-major relevance of the encoder
         output (what the decoder kernels emit); row_img: int32 (Q,) image of each request (None = identity).
         Returns fp32 (Q, 3, H, W).  ``on_chunk(q0, q1)`` is called after the launches that produce out[q0:q1]
-        have been enqueued (used to overlap the device->host copy of finished heat-maps with the next chunk)."""
+        have been enqueued (used to overlap the device->host copy of finished heat-maps with the next chunk).
+        = ``relevance_tail(relevance_head(...))``."""
+        head = self.relevance_head(st, r_feat, row_img, chunk)
+        return self.relevance_tail(st, head, out=out, on_chunk=on_chunk)
+
+    def _run_layers(self, st, s, nq, rimg, lo, hi, bufs, cur):
+        """layers hi-1 .. lo (lo >= 1) on nq requests; returns (tensor holding the result, index of its buffer)"""
+        for li in range(hi - 1, lo - 1, -1):
+            c, below = self.convs[li], self.convs[li - 1]
+            dst = bufs[cur ^ 1]
+            if below.pool_after:
+                tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL_UNPOOL, dst, gain=st.gain[li - 1],
+                        row_img=rimg, pool_idx=st.idx[li - 1])
+            else:
+                tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL, dst, gain=st.gain[li - 1], row_img=rimg)
+            cur ^= 1
+            s = dst
+        return s, cur
+
+    def relevance_head(self, st: VggState, r_feat: torch.Tensor, row_img: Optional[torch.Tensor] = None,
+                       chunk: int = 128) -> dict:
+        """Stage 1 of ``relevance``: the low-resolution layers over ALL requests in one launch per layer (their tile
+        counts per chunk are only ~3 waves of the persistent grid, so chunked launches lose up to a quarter of the
+        machine to wave quantisation).  Returns the hand-over for ``relevance_tail``."""
         _need_cuda(r_feat, "r_feat")
         r_feat = r_feat.detach().float().contiguous()
         Q = r_feat.shape[0]
@@ -251,13 +274,6 @@ class TcVggEngine:
                 raise _lib.LrpxError("row_img is required when the number of requests differs from the images")
             row_img = torch.arange(Q, device=dev, dtype=torch.int32)
         row_img = row_img.to(device=dev, dtype=torch.int32).contiguous()
-        H, W = self.convs[0].h, self.convs[0].w
-        if out is None:
-            out = torch.empty(Q, 3, H, W, device=dev, dtype=torch.float32)
-        # Stage 1: the low-resolution layers run over ALL requests in one launch per layer (their tile counts per
-        # chunk are only ~3 waves of the persistent grid, so chunked launches lose up to a quarter of the machine to
-        # wave quantisation); stage 2: the remaining layers chunk by chunk, ping-ponging two buffers sized for the
-        # largest layer of a chunk, so that finished heat-maps can leave for the host while the next chunk runs.
         chunk = max(1, min(chunk, Q))
         L = len(self.convs)
         budget = 2 << 30                      # bytes per stage-1 buffer
@@ -271,22 +287,6 @@ class TcVggEngine:
                     break
                 n_wide += 1
         split = L - n_wide                    # stage 1 = layers L-1 .. split, stage 2 = layers split-1 .. 0
-
-        def run_layers(s, nq, rimg, lo, hi, bufs, cur):
-            """layers hi-1 .. lo (lo >= 1) on nq requests; returns (tensor holding the result, index of its buffer)"""
-            for li in range(hi - 1, lo - 1, -1):
-                c, below = self.convs[li], self.convs[li - 1]
-                dst = bufs[cur ^ 1]
-                if below.pool_after:
-                    tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL_UNPOOL, dst, gain=st.gain[li - 1],
-                            row_img=rimg, pool_idx=st.idx[li - 1])
-                else:
-                    tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL, dst, gain=st.gain[li - 1],
-                            row_img=rimg)
-                cur ^= 1
-                s = dst
-            return s, cur
-
         s_all = None
         if n_wide > 0:
             elems = 0
@@ -297,7 +297,18 @@ class TcVggEngine:
             wide = [torch.empty(elems, device=dev, dtype=torch.bfloat16) for _ in range(2)]
             check(lib().lrpx_tc_scale_rows(_ptr(r_feat), _ptr(st.rz_last), _ptr(row_img), _ptr(wide[0]), Q, fh, fw,
                                            st.feat_c, _stream()), "lrpx_tc_scale_rows")
-            s_all, _ = run_layers(wide[0], Q, row_img, split, L, wide, 0)
+            s_all, _ = self._run_layers(st, wide[0], Q, row_img, split, L, wide, 0)
+        return dict(Q=Q, chunk=chunk, split=split, s_all=s_all, r_feat=r_feat, row_img=row_img)
+
+    def relevance_tail(self, st: VggState, head: dict, out: Optional[torch.Tensor] = None, on_chunk=None) -> torch.Tensor:
+        """Stage 2 of ``relevance``: the high-resolution layers chunk by chunk, ping-ponging two buffers sized for the
+        largest layer of a chunk, so that finished heat-maps can leave for the host while the next chunk runs."""
+        Q, chunk, split, s_all, r_feat, row_img = (head[k] for k in ("Q", "chunk", "split", "s_all", "r_feat", "row_img"))
+        dev = r_feat.device
+        fh, fw = st.feat_hw
+        H, W = self.convs[0].h, self.convs[0].w
+        if out is None:
+            out = torch.empty(Q, 3, H, W, device=dev, dtype=torch.float32)
         top = self.convs[split - 1]           # first layer of stage 2: its input is (h, w, cout) of that layer
         max_elems = max(pf_rows(chunk, c.h, c.w) * c.cout for c in self.convs[:split])
         buf = [torch.empty(max_elems, device=dev, dtype=torch.bfloat16) for _ in range(2)]
@@ -317,7 +328,7 @@ class TcVggEngine:
                 s, cur = buf[0], 0
                 check(lib().lrpx_tc_scale_rows(_ptr(r_feat[q0:q1]), _ptr(st.rz_last), _ptr(rimg), _ptr(s), nq, fh, fw,
                                                st.feat_c, _stream()), "lrpx_tc_scale_rows")
-            s, cur = run_layers(s, nq, rimg, 1, split, buf, cur)
+            s, cur = self._run_layers(st, s, nq, rimg, 1, split, buf, cur)
             c0 = self.convs[0]
             tc_conv(s, c0.w_rel, nq, c0.h, c0.w, c0.cout, 16, 3, EPI_INPUT, out[q0:q1], row_img=rimg, x=st.x)
             if on_chunk is not None:
