@@ -29,16 +29,25 @@ class BatchExplainer:
         self._graphs = {}
         self._copy_stream = None
 
-    def _requests(self, B, T, device):
-        req_img = torch.arange(B, dtype=torch.int32, device=device).repeat_interleave(T)
-        req_t = torch.arange(T, dtype=torch.int32, device=device).repeat(B)
+    def _requests(self, B, T, device, words_per_image=None):
+        """(image, word) requests in image-major order; ``words_per_image[b]`` <= T limits image b to its own caption
+        length (ragged batches: shorter captions are padded in ``tokens``, their padding words are not explained)."""
+        if words_per_image is None:
+            req_img = torch.arange(B, dtype=torch.int32, device=device).repeat_interleave(T)
+            req_t = torch.arange(T, dtype=torch.int32, device=device).repeat(B)
+            return req_img, req_t
+        n = [int(v) for v in words_per_image]
+        if len(n) != B or any(v < 0 or v > T for v in n):
+            raise ValueError("words_per_image must hold B values in [0, T]")
+        req_img = torch.tensor([b for b in range(B) for _ in range(n[b])], dtype=torch.int32, device=device)
+        req_t = torch.tensor([t for b in range(B) for t in range(n[b])], dtype=torch.int32, device=device)
         return req_img, req_t
 
     def _run(self, imgs, tokens, req_img, req_t, heat, host=None):
         est = self.eng.forward(imgs)
         feat = self.eng.features(est, "pixel")
         st = self.ex.explainer_forward(feat, tokens)
-        req_word = tokens[:, 1:].reshape(-1).to(torch.int32)
+        req_word = tokens[req_img.long(), req_t.long() + 1].to(torch.int32)       # the word each request explains
         r_feat, r_words = ops.gridtd_decoder_lrp(st, self.W, req_img, req_t, req_word, tc_gemm=self.tc_gemm)
         if host is None:
             self.eng.relevance(est, r_feat, req_img, chunk=self.chunk, out=heat)
@@ -64,25 +73,32 @@ class BatchExplainer:
         main.wait_stream(side)
         return r_words
 
-    def explain(self, imgs, tokens, out=None, host_out=None):
+    def explain(self, imgs, tokens, out=None, host_out=None, words_per_image=None):
         """imgs (B,3,H,W) fp32 (CUDA, or pinned host memory), tokens (B,T+1) long with column 0 = <start>.
-        Returns (heat (B*T,3,H,W) fp32, r_words (B*T,T) fp32); request q = b*T + t explains word t+1 of image b.
+        Returns (heat (Q,3,H,W) fp32, r_words (Q,T) fp32); with ``words_per_image=None`` Q = B*T and request
+        q = b*T + t explains word t+1 of image b; with ragged captions (``words_per_image[b]`` words for image b,
+        ``tokens`` padded to T+1) the requests are the valid (b, t) pairs in the same image-major order.
         ``host_out=(heat_host, words_host)`` (pinned tensors) additionally delivers the results to the host, the
         heat-map copy overlapped chunk by chunk with the relevance kernels.
         With ``use_graph`` the returned tensors are the graph's static outputs (overwritten by the next call)."""
         B, T = tokens.shape[0], tokens.shape[1] - 1
         dev = self.ex.device
+        wpi = None if words_per_image is None else tuple(int(v) for v in words_per_image)
+        Q = B * T if wpi is None else sum(wpi)
+        if Q == 0:                                               # nothing to explain
+            return (torch.empty(0, 3, imgs.shape[2], imgs.shape[3], device=dev), torch.empty(0, T, device=dev))
         if not self.use_graph:
             imgs, tokens = imgs.to(dev, non_blocking=True), tokens.to(dev, non_blocking=True)
-            req_img, req_t = self._requests(B, T, dev)
-            heat = out if out is not None else torch.empty(B * T, 3, imgs.shape[2], imgs.shape[3], device=dev)
+            req_img, req_t = self._requests(B, T, dev, wpi)
+            heat = out if out is not None else torch.empty(Q, 3, imgs.shape[2], imgs.shape[3], device=dev)
             return heat, self._run(imgs, tokens, req_img, req_t, heat, host_out)
-        key = (tuple(imgs.shape), tuple(tokens.shape), None if host_out is None else (host_out[0].data_ptr(), host_out[1].data_ptr()))
+        key = (tuple(imgs.shape), tuple(tokens.shape), wpi,
+               None if host_out is None else (host_out[0].data_ptr(), host_out[1].data_ptr()))
         g = self._graphs.get(key)
         if g is None:
             s_imgs, s_toks = imgs.to(dev).clone(), tokens.to(dev).clone()
-            req_img, req_t = self._requests(B, T, dev)
-            heat = torch.empty(B * T, 3, imgs.shape[2], imgs.shape[3], device=dev)
+            req_img, req_t = self._requests(B, T, dev, wpi)
+            heat = torch.empty(Q, 3, imgs.shape[2], imgs.shape[3], device=dev)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                       # warm-up outside capture (lazy inits, attributes)

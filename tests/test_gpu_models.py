@@ -343,3 +343,29 @@ def test_config3_aoa_bu_full_size_properties(tmp_path):
         assert torch.equal(f32_feat[t:t + 1], r_feats[t])               # the API call used the fp32 GEMMs (precision fp32)
     one = ops.aoa_decoder_lrp(st, W, 8, i32([0]), i32([T - 1]), i32([toks[T]]), i32([3]), tc_gemm=False)[0]
     assert torch.equal(one[0], f32_feat[T - 1])
+
+
+def test_batch_pipeline_ragged_captions_and_empty_batch(tmp_path):
+    """Ragged input: images with captions of different lengths (tokens padded) explain only their own words, in
+    image-major order, with the same results as the full rectangular batch restricted to those requests; an
+    all-empty batch returns empty tensors."""
+    from models import gridTDmodel as G
+    from lrpx.pipeline import BatchExplainer
+    V, H, E, B, T = 60, 64, 32, 3, 4
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(181, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(182))
+    ex = G.ExplainGridTDAttention(_args(E, H, tmp_path), synth.word_map(V), model=model.to(DEV).eval(), precision="bf16")
+    imgs = synth.images(185, B).to(DEV)
+    toks = torch.stack([torch.tensor(synth.tokens(186 + b, T, V)) for b in range(B)]).to(DEV)
+    full_heat, full_words = BatchExplainer(ex, chunk=5, use_graph=False).explain(imgs, toks)
+    lens = [4, 0, 2]
+    keep = [b * T + t for b in range(B) for t in range(lens[b])]
+    for use_graph in (False, True):
+        heat, words = BatchExplainer(ex, chunk=5, use_graph=use_graph).explain(imgs, toks, words_per_image=lens)
+        assert heat.shape[0] == sum(lens) and words.shape == (sum(lens), T)
+        assert torch.equal(heat, full_heat[keep]) and torch.equal(words, full_words[keep])
+    heat0, words0 = BatchExplainer(ex, chunk=5).explain(imgs, toks, words_per_image=[0, 0, 0])
+    assert heat0.shape == (0, 3, 224, 224) and words0.shape == (0, T)
+    with pytest.raises(ValueError):
+        BatchExplainer(ex).explain(imgs, toks, words_per_image=[5, 0, 0])
