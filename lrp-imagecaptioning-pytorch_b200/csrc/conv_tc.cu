@@ -59,6 +59,7 @@ struct TcParams {
   int box0_rows, box1_rows;   // TMA boxes that make up a slab (box1_rows == 0: single box)
   int a_stage_bytes; // bytes of one A stage (= one slab), multiple of 1024
   int n_issuers;     // MMA issuer warps in use: 2 (one per M half) when mh == 2, else 1
+  int store_off;     // EPI_MUL: byte offset (from the aligned smem base) of the TMA-store staging area, 0 = plain stores
   int a_stages, b_stages;
   int b_resident;    // all B tiles of the layer stay in shared memory for the lifetime of the CTA
   int debug_flags;   // env LRPX_TC_DEBUG: bit 0 = epilogue skips its global loads/stores (timing experiments only)
@@ -111,6 +112,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// smem -> global tile store (bulk async group); the box is clipped at the tensor's bounds
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
@@ -286,6 +298,37 @@ __device__ __forceinline__ void epi_mul(const TcParams& p, const RowInfo& r, int
   }
 }
 
+// Same arithmetic, but the 32 x 32 result block leaves through shared memory and two TMA tile stores (16 columns
+// each, SWIZZLE_32B staging: 16-byte chunk index ^= (row >> 2) & 1, conflict-free for the row-per-lane writes).
+// Row-per-thread st.global costs one L1 wavefront per lane per instruction; with the stores switched off a layer ran
+// 8-22 % faster, although the bytes are few — the TMA path takes them off the LSU / L1.
+__device__ __forceinline__ void epi_mul_tma(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[32],
+                                            const U8 (&g)[2], uint32_t stage, const CUtensorMap* tmo) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t sw = (uint32_t)(lane >> 2) & 1u;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t ow[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a0 = __uint_as_float(v[16 * q + 2 * k]) * bf16_lo(g[q].w[k]);
+      float a1 = __uint_as_float(v[16 * q + 2 * k + 1]) * bf16_hi(g[q].w[k]);
+      ow[k] = r.valid ? pack_bf16(a0, a1) : 0u;          // padding rows of the PF layout stay exactly zero
+    }
+    if (lane == 0) bulk_wait_read0();                    // the previous store has finished reading the staging block
+    __syncwarp();
+    const uint32_t row_addr = stage + (uint32_t)lane * 32u;
+    sts_v4(row_addr + ((0u ^ sw) << 4), ow[0], ow[1], ow[2], ow[3]);
+    sts_v4(row_addr + ((1u ^ sw) << 4), ow[4], ow[5], ow[6], ow[7]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmo, stage, col + 16 * q, r.row - lane);
+      bulk_commit();
+    }
+  }
+}
+
 // tile at pooled resolution; 16 columns starting at `col`: scatter to the 2x2 fine pixels chosen by the argmax bytes
 // (the other three get 0).  g = 16 gains (bf16), sidx = 16 argmax bytes.
 __device__ __forceinline__ void epi_mul_unpool16(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[16],
@@ -401,7 +444,7 @@ __device__ __forceinline__ void epi_release(uint32_t release_bar) {
 
 template <int EPI>
 __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, uint32_t taddr, int n_tile, int c,
-                                         uint32_t release_bar) {
+                                         uint32_t release_bar, uint32_t stage = 0, const CUtensorMap* tmo = nullptr) {
   if (p.debug_flags & 16) { epi_release(release_bar); return; }      // timing experiment: only hands the accumulator back
   RowInfo r = r0;
   if (p.debug_flags & 1) { r.in_range = false; r.valid = false; }
@@ -499,7 +542,8 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
       TMEM_LD_X32(taddr + c, v);
       tmem_ld_wait();
       epi_release(release_bar);
-      epi_mul(p, r, n0 + c, v, g);
+      if (stage && !(p.debug_flags & 64)) epi_mul_tma(p, r, n0 + c, v, g, stage, tmo);
+      else epi_mul(p, r, n0 + c, v, g);
     } else {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -531,7 +575,8 @@ template <int EPI>
 __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_base /* tile row 0 + quarter*32 + lane */,
                                                   uint32_t taddr_q /* lane quarter + buffer */, int n_tile, int sub,
                                                   int mh, int pf_row_base /* same for the prefetched tile, or -1 */,
-                                                  uint32_t release_bar /* tmem_empty barrier of the tile's buffer */) {
+                                                  uint32_t release_bar /* tmem_empty barrier of the tile's buffer */,
+                                                  uint32_t stage = 0, const CUtensorMap* tmo = nullptr) {
   const int uph = epi_units_per_half(p, EPI);
   const int n_units = mh * uph;
   constexpr int step = TC_EPI_WARPS / 4;
@@ -545,7 +590,7 @@ __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_bas
     const int h = u / uph, c = (u - h * uph) << 5;
     if (h != h_cached) { r = row_info(p, row_base + h * TC_BM); h_cached = h; }
     if (pf_row_base >= 0) epi_prefetch_unit<EPI>(p, pf_row_base + h * TC_BM, n_tile, c);
-    epi_unit<EPI>(p, r, taddr_q + (uint32_t)(h * p.bn), n_tile, c, (u + step >= n_units) ? release_bar : 0u);
+    epi_unit<EPI>(p, r, taddr_q + (uint32_t)(h * p.bn), n_tile, c, (u + step >= n_units) ? release_bar : 0u, stage, tmo);
   }
 }
 
@@ -775,7 +820,7 @@ constexpr int TC_A_MAX_STAGES = 6;
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                    const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[TC_A_MAX_STAGES];
   __shared__ __align__(8) uint64_t a_empty[TC_A_MAX_STAGES];
@@ -912,8 +957,13 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int pf_row = (tile_pf < num_tiles && tile_pf % p.num_n_tiles == n_tile)
                              ? (tile_pf / p.num_n_tiles) * tile_rows + quarter * 32 + lane : -1;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
+      const uint32_t stage = (EPI == LRPX_TC_EPI_MUL && p.store_off) ? smem_base + (uint32_t)p.store_off + (uint32_t)(warp - 2) * 1024u : 0u;
       run_epilogue_tile<EPI>(p, m_tile * tile_rows + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh, pf_row,
-                             smem_u32(&tmem_empty_bar[buf]));
+                             smem_u32(&tmem_empty_bar[buf]), stage, &tmO);
+    }
+    if (EPI == LRPX_TC_EPI_MUL && p.store_off) {      // the staging block must outlive the last tile store's read
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
     }
   }
 
@@ -965,6 +1015,28 @@ static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
   return LRPX_OK;
 }
 
+// output tensor of the MUL epilogue: 2-D bf16 (rows x cols), box = (16 cols, 32 rows), SWIZZLE_32B
+static int make_map_out(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return LRPX_E_CUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed (%d) rows=%llu cols=%llu", (int)r, (unsigned long long)rows,
+              (unsigned long long)cols);
+    return LRPX_E_CUDA;
+  }
+  return LRPX_OK;
+}
+
 template <int EPI>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid, cudaStream_t st) {
   static std::once_flag once;
@@ -986,8 +1058,8 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
 }
 
 template <int EPI>
-static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const TcParams& p,
-                          int grid, cudaStream_t st) {
+static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mo,
+                          const TcParams& p, int grid, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -997,7 +1069,7 @@ static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const 
     set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
     return LRPX_E_CUDA;
   }
-  tc_conv_slab_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma0, ma1, mb, p);
+  tc_conv_slab_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma0, ma1, mb, mo, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("tc_conv_slab_kernel launch failed: %s", cudaGetErrorString(e));
@@ -1010,8 +1082,8 @@ static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const 
 //   mh = 2 (256-row tiles, one issuer warp per half) whenever two accumulators of the tile fit one TMEM buffer
 //   (bn <= 128); slab_mode 1 when the single slab is the smaller fetch and fits two TMA boxes, else one slab per
 //   filter row; B resident when the whole layer's B fits next to >= 2 (mode 1) / 4 (mode 3) A stages.
-static bool plan_slab(TcParams& p) {
-  const int budget = TC_SMEM_BYTES - 1024;
+static bool plan_slab(TcParams& p, int reserve) {
+  const int budget = TC_SMEM_BYTES - 1024 - reserve;
   const int b_bytes = p.bn * TC_BK * 2;
   const long long b_total = (long long)p.taps * p.kc_per_tap * b_bytes;
   const char* env_mh = getenv("LRPX_TC_MH");             // experiment switches (timing probes only)
@@ -1141,10 +1213,23 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
   {
     const char* env = getenv("LRPX_TC_SLAB");       // LRPX_TC_SLAB=0 falls back to one TMA tile per filter tap
     const bool want_slab = a->ksize == 3 && !(env && env[0] == '0');
-    if (want_slab && plan_slab(p)) {
+    // EPI_MUL: results leave through a 16 KB staging area (1 KB per epilogue warp) and TMA tile stores
+    const char* env_ts = getenv("LRPX_TC_TMASTORE");
+    const bool tma_store = epi == LRPX_TC_EPI_MUL && !(env_ts && env_ts[0] == '0');
+    const int reserve = tma_store ? TC_EPI_WARPS * 1024 : 0;
+    if (want_slab && plan_slab(p, reserve)) {
       const int tile_rows = p.mh * TC_BM;
       p.num_m_tiles = (p.m_total + tile_rows - 1) / tile_rows;
-      CUtensorMap ma0, ma1, mb;
+      CUtensorMap ma0, ma1, mb, mo;
+      mo = CUtensorMap{};
+      p.store_off = 0;
+      if (tma_store) {
+        const long long b_region = p.b_resident ? (long long)p.taps * p.kc_per_tap * p.bn * TC_BK * 2
+                                                : (long long)p.b_stages * p.bn * TC_BK * 2;
+        p.store_off = (int)((p.a_stages * (long long)p.a_stage_bytes + b_region + 1023) & ~1023LL);
+        int rco = make_map_out(&mo, a->out, (uint64_t)p.m_total, (uint64_t)p.out_c);
+        if (rco) return rco;
+      }
       int rc = make_map_2d(&ma0, a->a, (uint64_t)p.m_total, (uint64_t)a->cin, (uint32_t)p.box0_rows);
       if (rc) return rc;
       rc = make_map_2d(&ma1, a->a, (uint64_t)p.m_total, (uint64_t)a->cin, (uint32_t)(p.box1_rows ? p.box1_rows : 8));
@@ -1154,11 +1239,11 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       int tiles = p.num_m_tiles * p.num_n_tiles;
       int grid = tiles < sm_count() ? tiles : sm_count();
       switch (epi) {
-        case LRPX_TC_EPI_FWD_GAIN: return launch_tc_slab<LRPX_TC_EPI_FWD_GAIN>(ma0, ma1, mb, p, grid, st);
-        case LRPX_TC_EPI_MUL: return launch_tc_slab<LRPX_TC_EPI_MUL>(ma0, ma1, mb, p, grid, st);
-        case LRPX_TC_EPI_MUL_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MUL_UNPOOL>(ma0, ma1, mb, p, grid, st);
-        case LRPX_TC_EPI_INPUT: return launch_tc_slab<LRPX_TC_EPI_INPUT>(ma0, ma1, mb, p, grid, st);
-        default: return launch_tc_slab<LRPX_TC_EPI_STORE_F32>(ma0, ma1, mb, p, grid, st);
+        case LRPX_TC_EPI_FWD_GAIN: return launch_tc_slab<LRPX_TC_EPI_FWD_GAIN>(ma0, ma1, mb, mo, p, grid, st);
+        case LRPX_TC_EPI_MUL: return launch_tc_slab<LRPX_TC_EPI_MUL>(ma0, ma1, mb, mo, p, grid, st);
+        case LRPX_TC_EPI_MUL_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MUL_UNPOOL>(ma0, ma1, mb, mo, p, grid, st);
+        case LRPX_TC_EPI_INPUT: return launch_tc_slab<LRPX_TC_EPI_INPUT>(ma0, ma1, mb, mo, p, grid, st);
+        default: return launch_tc_slab<LRPX_TC_EPI_STORE_F32>(ma0, ma1, mb, mo, p, grid, st);
       }
     }
   }
