@@ -239,9 +239,28 @@ class TcVggEngine:
         output (what the decoder kernels emit); row_img: int32 (Q,) image of each request (None = identity).
         Returns fp32 (Q, 3, H, W).  ``on_chunk(q0, q1)`` is called after the launches that produce out[q0:q1]
         have been enqueued (used to overlap the device->host copy of finished heat-maps with the next chunk).
-        = ``relevance_tail(relevance_head(...))``."""
-        head = self.relevance_head(st, r_feat, row_img, chunk)
-        return self.relevance_tail(st, head, out=out, on_chunk=on_chunk)
+        = ``relevance_tail(relevance_head(...))`` per group of at most ``GROUP`` requests (the stage-1 buffers of a
+        group stay within their memory budget however many requests a call brings)."""
+        Q = r_feat.shape[0]
+        if Q <= self.GROUP:
+            head = self.relevance_head(st, r_feat, row_img, chunk)
+            return self.relevance_tail(st, head, out=out, on_chunk=on_chunk)
+        _need_cuda(r_feat, "r_feat")
+        if row_img is None:
+            if Q != st.n:
+                raise _lib.LrpxError("row_img is required when the number of requests differs from the images")
+            row_img = torch.arange(Q, device=r_feat.device, dtype=torch.int32)
+        if out is None:
+            out = torch.empty(Q, 3, self.convs[0].h, self.convs[0].w, device=r_feat.device, dtype=torch.float32)
+        group = max(chunk, self.GROUP // max(1, chunk) * chunk)
+        for g0 in range(0, Q, group):
+            g1 = min(Q, g0 + group)
+            head = self.relevance_head(st, r_feat[g0:g1], row_img[g0:g1], chunk)
+            cb = None if on_chunk is None else (lambda q0, q1, g0=g0: on_chunk(g0 + q0, g0 + q1))
+            self.relevance_tail(st, head, out=out[g0:g1], on_chunk=cb)
+        return out
+
+    GROUP = 2048          # requests per stage-1 group
 
     def _run_layers(self, st, s, nq, rimg, lo, hi, bufs, cur):
         """layers hi-1 .. lo (lo >= 1) on nq requests; returns (tensor holding the result, index of its buffer)"""

@@ -199,3 +199,25 @@ def test_engine_vgg16_224_vs_reference_fixture(golden):
     heat6 = eng.relevance(st, r6, torch.zeros(Q, dtype=torch.int32, device=DEV), chunk=Q)
     for q in range(Q):
         assert torch.equal(heat6[q], heat[0]), f"request {q} of the replicated chunk differs from the single request"
+
+
+def test_relevance_groups_and_chunks_do_not_change_results():
+    """TcVggEngine.relevance over many requests: the stage-1 grouping (GROUP), the chunk size and the chunk-wise
+    callback must not change a single bit of any request's heat-map, and the callback must cover every request once."""
+    from lrpx import tc
+    cfg = [64, 64, "M", 128, "M", 128, 128]
+    sd = synth.vgg_state(7, cfg)
+    eng = tc.TcVggEngine([sd[k] for k in sd if k.endswith("weight")], [sd[k] for k in sd if k.endswith("bias")], cfg, DEV)
+    g = torch.Generator().manual_seed(8)
+    n, Q = 3, 11
+    st = eng.forward(torch.randn(n, 3, 32, 32, generator=g).to(DEV))
+    row_img = (torch.arange(Q, dtype=torch.int32) % n).to(DEV)
+    r = torch.randn(Q, 64, 128, generator=g).to(DEV)
+    ref = eng.relevance(st, r, row_img, chunk=Q)                 # one chunk, no stage 1
+    for group, chunk in ((4, 2), (6, 3), (2048, 4), (5, 5)):
+        eng.GROUP = group
+        seen = []
+        got = eng.relevance(st, r, row_img, chunk=chunk, on_chunk=lambda q0, q1: seen.append((q0, q1)))
+        assert torch.equal(got, ref), (group, chunk)
+        assert seen[0][0] == 0 and seen[-1][1] == Q and all(a[1] == b[0] for a, b in zip(seen, seen[1:])), seen
+    eng.GROUP = 2048
