@@ -369,3 +369,31 @@ def test_batch_pipeline_ragged_captions_and_empty_batch(tmp_path):
     assert heat0.shape == (0, 3, 224, 224) and words0.shape == (0, T)
     with pytest.raises(ValueError):
         BatchExplainer(ex).explain(imgs, toks, words_per_image=[5, 0, 0])
+
+
+def test_batch_pipeline_aoa_equals_single_image_api(tmp_path):
+    """lrpx.pipeline.BatchExplainer with an ExplainAOAAttention (VGG16 encoder, bf16 chain): B images x T words for one
+    attention head in one pass == ExplainAOAAttention.explain_caption(img, head) per image; graph replay == eager."""
+    from models import aoamodel as A
+    from lrpx.pipeline import BatchExplainer
+    V, H, E, B, T, head = 60, 64, 32, 2, 3, 5
+    model = A.AOAModel(E, H, 8, V, "vgg16")
+    model.load_state_dict(synth.aoa_decoder_state(191, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(192))
+    model.to(DEV).eval()
+    ex = A.ExplainAOAAttention(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="bf16")
+    ex.ACCUMULATE_LIKE_REFERENCE = False
+    imgs = synth.images(195, B).to(DEV)
+    toks = torch.stack([torch.tensor(synth.tokens(196 + b, T, V)) for b in range(B)]).to(DEV)
+    heat_e, words_e = BatchExplainer(ex, chunk=4, use_graph=False, head_idx=head).explain(imgs, toks)
+    heat_g, words_g = BatchExplainer(ex, chunk=4, use_graph=True, head_idx=head).explain(imgs, toks)
+    assert torch.equal(heat_e, heat_g) and torch.equal(words_e, words_g)
+    for b in range(B):
+        ex.preprocess_img = lambda p, b=b: imgs[b:b + 1]
+        tk = toks[b].tolist()
+        model.beam_search = lambda *a, tk=tk, **k: (["a b c"], tk[1:])
+        hs, ws = ex.explain_caption("synthetic.jpg", head)
+        for t in range(T):
+            assert_close(hs[t][0], heat_e[b * T + t], rtol=1e-3, atol=1e-6 + 1e-3 * float(heat_e[b * T + t].abs().max()),
+                         what=f"aoa image {b} word {t}")
+            assert_close(ws[t], words_e[b * T + t, :t + 1], rtol=1e-3, atol=1e-4, what=f"aoa words {b},{t}")
