@@ -59,6 +59,8 @@ struct TcParams {
   int box0_rows, box1_rows;   // TMA boxes that make up a slab (box1_rows == 0: single box)
   int a_stage_bytes; // bytes of one A stage (= one slab), multiple of 1024
   int n_issuers;     // MMA issuer warps in use: 2 (one per M half) when mh == 2, else 1
+  int cluster;       // 2: CTA pairs (thread-block clusters) share every streamed B tile through TMA multicast; else 1
+  int tiles_sched;   // tiles the persistent loop walks (cluster mode pads the M tiles to an even count)
   int store_off;     // EPI_MUL: byte offset (from the aligned smem base) of the TMA-store staging area, 0 = plain stores
   int a_stages, b_stages;
   int b_resident;    // all B tiles of the layer stay in shared memory for the lifetime of the CTA
@@ -139,6 +141,29 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// multicast tile load: the box lands at the same shared-memory offset in every CTA of `mask` and signals the mbarrier
+// at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
@@ -730,6 +755,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// tile index -> (M tile, N tile).  Cluster mode: the two CTAs of a pair (tile 2P, 2P+1) get the SAME column block and
+// neighbouring M tiles, so they consume the same B tiles in the same order; m_tile may be one past the end (a padding
+// tile: its A rows are zero-filled by TMA and its results are clipped by the row bound).
+__device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& m_tile, int& n_tile) {
+  if (p.cluster == 2) {
+    const int pr = tile >> 1;
+    n_tile = pr % p.num_n_tiles;
+    m_tile = (pr / p.num_n_tiles) * 2 + (tile & 1);
+  } else {
+    n_tile = tile % p.num_n_tiles;
+    m_tile = tile / p.num_n_tiles;
+  }
+}
+
 // MMA issue loop of the slab kernel.  Everything loop-invariant is hoisted and the taps x 4 K-steps are unrolled
 // so that one MMA costs a handful of integer instructions (measured: ~200 cycles per MMA with the naive loop, which
 // capped the N<=64 layers at 1/6 of the tensor rate; ~75 cycles with this loop and a converged issuing warp).
@@ -803,7 +842,8 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
                                (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
           }
           if (!BRES) {
-            tc_commit(smem_u32(&b_empty[bs]));
+            if (p.cluster == 2) tc_commit_mc(smem_u32(&b_empty[bs]), (uint16_t)3);      // frees the stage in both CTAs
+            else tc_commit(smem_u32(&b_empty[bs]));
             if (++bs == b_stages) { bs = 0; bph ^= 1; }
           }
         }
@@ -836,7 +876,8 @@ constexpr int TC_A_MAX_STAGES = 6;
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const TcParams p) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
+                    const __grid_constant__ CUtensorMap tmO, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[TC_A_MAX_STAGES];
   __shared__ __align__(8) uint64_t a_empty[TC_A_MAX_STAGES];
@@ -852,7 +893,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)p.a_stages * p.a_stage_bytes;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.tiles_sched;
   const int tile_rows = p.mh * TC_BM;
   const int n_slabs = p.slab_mode == 1 ? 1 : 3;
 
@@ -864,7 +905,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     for (int s = 0; s < p.b_stages; ++s) {
       mbar_init(smem_u32(&b_full[s]), 1);
-      mbar_init(smem_u32(&b_empty[s]), p.n_issuers);
+      mbar_init(smem_u32(&b_empty[s]), p.n_issuers * p.cluster);      // cluster: both CTAs' issuers release a B stage
     }
     mbar_init(smem_u32(&bres_bar), 1);
     for (int b = 0; b < 2; ++b) {
@@ -884,6 +925,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.cluster == 2) cluster_sync_all();      // the peer's barriers exist before any multicast traffic or remote arrive
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
@@ -893,7 +935,8 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       uint32_t aph = 0;
       const uint32_t a_tx = (uint32_t)p.slab_rows * (TC_BK * 2);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
+        int m_tile, n_tile_unused;
+        tile_coords(p, tile, m_tile, n_tile_unused);
         const int m0 = m_tile * tile_rows;
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
           for (int j = 0; j < n_slabs; ++j) {          // one ring stage per slab
@@ -925,14 +968,24 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       } else {
         int bs = 0;
         uint32_t bph = 0;
+        // cluster mode: this CTA fetches HALF of every B tile (rows [rank*bn/2, +bn/2)) and multicasts it into both
+        // CTAs of the pair; a stage is free once the issuers of BOTH CTAs have committed it (b_empty counts them all)
+        const uint32_t rank = p.cluster == 2 ? cluster_ctarank() : 0u;
+        const uint32_t half_bytes = b_bytes >> 1;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int n0 = (tile % p.num_n_tiles) * p.bn;
+          int m_tile_unused, n_tile;
+          tile_coords(p, tile, m_tile_unused, n_tile);
+          const int n0 = n_tile * p.bn;
           for (int kc = 0; kc < p.kc_per_tap; ++kc)
             for (int tap = 0; tap < p.taps; ++tap) {
               mbar_wait_relaxed(smem_u32(&b_empty[bs]), bph ^ 1);
               const uint32_t bb = smem_u32(&b_full[bs]);
               mbar_expect_tx(bb, b_bytes);
-              tma_load_2d(b_base + (uint32_t)bs * b_bytes, &tmB, bb, tap * p.cin + kc * TC_BK, n0);
+              if (p.cluster == 2)
+                tma_load_2d_mc(b_base + (uint32_t)bs * b_bytes + rank * half_bytes, &tmBh, bb, tap * p.cin + kc * TC_BK,
+                               n0 + (int)rank * (p.bn >> 1), (uint16_t)3);
+              else
+                tma_load_2d(b_base + (uint32_t)bs * b_bytes, &tmB, bb, tap * p.cin + kc * TC_BK, n0);
               if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
             }
         }
@@ -966,12 +1019,14 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+      int m_tile, n_tile;
+      tile_coords(p, tile, m_tile, n_tile);
       mbar_wait_relaxed(smem_u32(&tmem_full_bar[buf]), acc_phase);
       tc_fence_after();
       const int tile_pf = tile + 2 * (int)gridDim.x;      // L2 prefetch distance: two of this CTA's tiles ahead
-      const int pf_row = (tile_pf < num_tiles && tile_pf % p.num_n_tiles == n_tile)
-                             ? (tile_pf / p.num_n_tiles) * tile_rows + quarter * 32 + lane : -1;
+      int m_pf = 0, n_pf = -1;
+      if (tile_pf < num_tiles) tile_coords(p, tile_pf, m_pf, n_pf);
+      const int pf_row = (n_pf == n_tile) ? m_pf * tile_rows + quarter * 32 + lane : -1;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
       const uint32_t stage = (EPI == LRPX_TC_EPI_MUL && p.store_off) ? smem_base + (uint32_t)p.store_off + (uint32_t)(warp - 2) * 1024u : 0u;
       run_epilogue_tile<EPI>(p, m_tile * tile_rows + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh, pf_row,
@@ -985,6 +1040,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster == 2) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -1074,8 +1130,8 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
 }
 
 template <int EPI>
-static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mo,
-                          const TcParams& p, int grid, cudaStream_t st) {
+static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mbh,
+                          const CUtensorMap& mo, const TcParams& p, int grid, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -1085,7 +1141,44 @@ static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const 
     set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
     return LRPX_E_CUDA;
   }
-  tc_conv_slab_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma0, ma1, mb, mo, p);
+  if (p.cluster == 2) {
+    // GPCs with an odd number of SMs cannot host a pair on their last SM: a persistent grid must not exceed the
+    // number of clusters that are co-resident, or the left-over pair would run after everyone else
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(2 * 148);
+      q.blockDim = dim3(TC_THREADS);
+      q.dynamicSmemBytes = TC_SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, tc_conv_slab_kernel<EPI>, &q) != cudaSuccess || n <= 0) n = 64;
+      max_clusters = n;
+    }
+    if (grid > 2 * max_clusters) grid = 2 * max_clusters;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, tc_conv_slab_kernel<EPI>, ma0, ma1, mb, mbh, mo, p);
+    if (le != cudaSuccess) {
+      set_error("tc_conv_slab_kernel cluster launch failed: %s", cudaGetErrorString(le));
+      return LRPX_E_CUDA;
+    }
+    return LRPX_OK;
+  }
+  tc_conv_slab_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma0, ma1, mb, mbh, mo, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("tc_conv_slab_kernel launch failed: %s", cudaGetErrorString(e));
@@ -1252,18 +1345,32 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       if (rc) return rc;
       rc = make_map_2d(&mb, a->wt, (uint64_t)a->ncol, (uint64_t)p.taps * a->cin, (uint32_t)p.bn);
       if (rc) return rc;
-      int tiles = p.num_m_tiles * p.num_n_tiles;
+      // CTA pairs sharing the streamed B tiles through TMA multicast (halves the L2 -> SM weight traffic, which is
+      // what bounds the 256/512-channel layers: ~12 TB/s of B re-fetches at 128-row tiles)
+      const char* env_cl = getenv("LRPX_TC_CLUSTER");             // LRPX_TC_CLUSTER=0: one CTA per cluster
+      const bool want_cluster = !(env_cl && env_cl[0] == '0');
+      CUtensorMap mbh = mb;
+      p.cluster = 1;
+      p.tiles_sched = p.num_m_tiles * p.num_n_tiles;
+      if (want_cluster && !p.b_resident && p.bn >= 16 && sm_count() >= 2) {
+        p.cluster = 2;
+        p.tiles_sched = p.num_n_tiles * 2 * ((p.num_m_tiles + 1) / 2);
+        rc = make_map_2d(&mbh, a->wt, (uint64_t)a->ncol, (uint64_t)p.taps * a->cin, (uint32_t)(p.bn / 2));
+        if (rc) return rc;
+      }
+      int tiles = p.tiles_sched;
       int grid = tiles < sm_count() ? tiles : sm_count();
+      if (p.cluster == 2) grid &= ~1;
       switch (epi) {
-        case LRPX_TC_EPI_FWD_GAIN: return launch_tc_slab<LRPX_TC_EPI_FWD_GAIN>(ma0, ma1, mb, mo, p, grid, st);
-        case LRPX_TC_EPI_MUL: return launch_tc_slab<LRPX_TC_EPI_MUL>(ma0, ma1, mb, mo, p, grid, st);
-        case LRPX_TC_EPI_MUL_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MUL_UNPOOL>(ma0, ma1, mb, mo, p, grid, st);
-        case LRPX_TC_EPI_INPUT: return launch_tc_slab<LRPX_TC_EPI_INPUT>(ma0, ma1, mb, mo, p, grid, st);
-        default: return launch_tc_slab<LRPX_TC_EPI_STORE_F32>(ma0, ma1, mb, mo, p, grid, st);
+        case LRPX_TC_EPI_FWD_GAIN: return launch_tc_slab<LRPX_TC_EPI_FWD_GAIN>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        case LRPX_TC_EPI_MUL: return launch_tc_slab<LRPX_TC_EPI_MUL>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        case LRPX_TC_EPI_MUL_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MUL_UNPOOL>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        case LRPX_TC_EPI_INPUT: return launch_tc_slab<LRPX_TC_EPI_INPUT>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        default: return launch_tc_slab<LRPX_TC_EPI_STORE_F32>(ma0, ma1, mb, mbh, mo, p, grid, st);
       }
     }
   }
-  p.slab_mode = 0; p.mh = 1; p.n_issuers = 1;
+  p.slab_mode = 0; p.mh = 1; p.n_issuers = 1; p.cluster = 1;
   p.num_m_tiles = (p.m_total + TC_BM - 1) / TC_BM;
   const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;
   p.stages = (TC_SMEM_BYTES - 1024) / stage_bytes;
