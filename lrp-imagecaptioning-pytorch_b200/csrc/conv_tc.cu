@@ -14,11 +14,16 @@
 // no im2col, every TMA box is a plain 2-D tile, out-of-range rows are zero-filled by TMA.
 //
 // GEMM:  acc[p][n] = sum_{tap, c} A[p + off(tap)][c] * Wt[n][tap*cin + c]      (both operands K-major)
-//   tile 128 (pixels) x BN (<=256) per CTA iteration, K step 64 channels (one 128-byte swizzle row),
+//   tile 128 or 256 (pixels) x BN (<=256) per CTA iteration, K step 64 channels (one 128-byte swizzle row),
 //   tcgen05.mma.cta_group::1.kind::f16  M=128, N=BN, K=16 (4 per K step), accumulators double-buffered in
 //   TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
-// Warp roles: warp 0 = TMA producer (one thread), warp 1 = TMEM allocator + MMA issuer (one thread),
-//             warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Two kernels:
+//   tc_conv_kernel       one TMA tile per filter tap (1x1 convolutions / plain GEMMs: first-layer forward, decoder GEMMs)
+//   tc_conv_slab_kernel  3x3: the A rows of all taps fetched once per channel block ("slab"), taps = row-shifted
+//                        descriptor views; B streamed (TMA-multicast to a CTA pair) or resident; two lockstep MMA issuers
+// Warp roles (20 warps): 0 = A producer, 1 = TMEM allocator + MMA issuer, 2..17 = epilogue (TMEM lane quarter =
+//   warp_idx % 4, four warps per quarter share the tile's 32x32 units), 18 = B producer, 19 = second MMA issuer.
+// DESIGN.md section 4.1 has the measurements behind each of these choices.
 #include "lrpx_common.cuh"
 #include <cuda.h>
 #include <mutex>
