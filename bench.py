@@ -241,11 +241,12 @@ def run_ours(args):
     step_eager_ms = sum(phase_ms.values())
 
     # launches of OUR kernels inside the timed region: one per C-ABI call, except the decoder call which
-    # enqueues 4 weight splits + init + per step (3 element-wise + 2 x (split + tensor-core GEMM)) + 7 tail kernels
+    # enqueues 4 weight splits + init + per step (3 element-wise kernels that also write the split GEMM operand + 2
+    # tensor-core GEMMs) + 7 tail kernels
     # (glob, split + GEMM, avg, attention rows, projector GEMM with fused epilogue, word norm; csrc/decoder.cu,
     # LRPX_DEC_TC_GEMM path)
     launches = sum(v for k, v in calls.items() if k != "lrpx_gridtd_decoder_lrp_f32")
-    launches += calls.get("lrpx_gridtd_decoder_lrp_f32", 0) * (5 + 7 * T + 7)
+    launches += calls.get("lrpx_gridtd_decoder_lrp_f32", 0) * (5 + 5 * T + 7)
     launches *= args.steps          # the same kernels per step whether launched eagerly or replayed from the graph
 
     out = None

@@ -120,6 +120,17 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16(x);
   lo = __float2bfloat16(x - __bfloat162float(hi));
 }
+// a producer kernel writes its GEMM operand both as fp32 (CUDA-core GEMM) and, when `a3` is given, directly as the
+// split row [hi | hi | lo] of the tensor-core GEMM (saves the separate split pass over the operand)
+__device__ __forceinline__ void put_operand(float* u, __nv_bfloat16* a3, size_t row, int K, int k, float x) {
+  u[row * K + k] = x;
+  if (a3) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(x, hi, lo);
+    __nv_bfloat16* o = a3 + row * 3 * K;
+    o[k] = hi; o[K + k] = hi; o[2 * K + k] = lo;
+  }
+}
 // rows x K fp32 (row pitch lda) -> rows x 3K bf16 [hi | hi | lo]
 __global__ void split3_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int K,
                                   int lda) {
@@ -210,6 +221,7 @@ struct GridWs {
   float *r_h2, *r_c2, *r_c1, *r_cth, *r_glob, *u, *v, *uctx, *coefavg, *wproj;
   // LRPX_DEC_TC_GEMM: split activations (largest GEMM) and prepared weights, bf16
   __nv_bfloat16 *a3, *w3_g2, *w3_g1, *w3_glob, *w3_proj;
+  __nv_bfloat16* a3u;      // split form of u written by the step kernels themselves (null: CUDA-core GEMMs)
 };
 
 __global__ void grid_init_kernel(lrpx_gridtd_args a, GridWs w) {
@@ -245,13 +257,13 @@ __global__ void grid_cell2_kernel(lrpx_gridtd_args a, GridWs w, int i) {
          bi0 = ((size_t)b * (a.T + 1) + i) * a.H;
   for (int j = threadIdx.x; j < a.H; j += blockDim.x) {
     size_t o = (size_t)q * a.H + j;
-    if (!active) { w.u[o] = 0.f; continue; }
+    if (!active) { put_operand(w.u, w.a3u, q, a.H, j, 0.f); continue; }
     float rc2 = w.r_c2[o] + w.r_h2[o];
     float d = stab(a.c2[bi1 + j]);
     float g = a.g2[bi + j];
     float r_g = a.i2[bi + j] * tanhf(g) * rc2 / d;
     w.r_c2[o] = a.f2[bi + j] * a.c2[bi0 + j] * rc2 / d;
-    w.u[o] = r_g / stab(g);
+    put_operand(w.u, w.a3u, q, a.H, j, r_g / stab(g));
   }
 }
 
@@ -268,7 +280,7 @@ __global__ void grid_post2_kernel(lrpx_gridtd_args a, GridWs w, int i) {
   float beta = a.beta[(size_t)b * a.T + i];
   for (int j = threadIdx.x; j < H; j += blockDim.x) {
     size_t o = (size_t)q * H + j;
-    if (!active) { w.u[o] = 0.f; continue; }
+    if (!active) { put_operand(w.u, w.a3u, q, H, j, 0.f); continue; }
     float rx_ctx = x2[j] * vq[j];                 // xh2[:H]   = ctx_hat_i
     float rx_h1 = x2[H + j] * vq[H + j];          // xh2[H:2H] = h1_{i+1}
     float rx_h2 = a.h2[bi0 + j] * vq[2 * H + j];  // xh2[2H:]  = h2_i
@@ -284,7 +296,7 @@ __global__ void grid_post2_kernel(lrpx_gridtd_args a, GridWs w, int i) {
     float g = a.g1[bi + j];
     float r_g = a.i1[bi + j] * tanhf(g) * rc1 / d;
     w.r_c1[o] = a.f1[bi + j] * a.c1[bi0 + j] * rc1 / d;
-    w.u[o] = r_g / stab(g);
+    put_operand(w.u, w.a3u, q, H, j, r_g / stab(g));
     w.r_h2[o] = rx_h2;
   }
 }
@@ -436,6 +448,7 @@ static size_t grid_carve(const lrpx_gridtd_args* a, float* base, GridWs* w) {
   t.coefavg = take(Q * a->C);
   t.wproj = take(Q * a->P * H);
   t.a3 = t.w3_g2 = t.w3_g1 = t.w3_glob = t.w3_proj = nullptr;
+  t.a3u = nullptr;
   if (a->flags & LRPX_DEC_TC_GEMM) {
     auto take16 = [&](size_t n) { return reinterpret_cast<__nv_bfloat16*>(take((n + 1) / 2)); };   // n bf16 elements
     size_t rows_max = Q * a->P;
@@ -444,6 +457,7 @@ static size_t grid_carve(const lrpx_gridtd_args* a, float* base, GridWs* w) {
     t.w3_g1 = take16((size_t)(2 * H + 2 * E) * 3 * H);
     t.w3_glob = take16((size_t)a->C * 3 * E);
     t.w3_proj = take16((size_t)a->C * 3 * H);
+    t.a3u = take16(Q * 3 * H);
   }
   if (w) *w = t;
   return off * sizeof(float);
@@ -684,13 +698,17 @@ int lrpx_gridtd_decoder_lrp_f32(const lrpx_gridtd_args* a, void* workspace, size
       (tc && tc_shape_ok(2 * H + 2 * E, H)) ? prep_weight3(a->W_g1, w.w3_g1, H, 2 * H + 2 * E, st) : nullptr;
   const __nv_bfloat16* w3_glob = (tc && tc_shape_ok(a->C, E)) ? prep_weight3(a->W_glob, w.w3_glob, E, a->C, st) : nullptr;
   const __nv_bfloat16* w3_proj = (tc && tc_shape_ok(a->C, H)) ? prep_weight3(a->W_proj, w.w3_proj, H, a->C, st) : nullptr;
+  // the step kernels write the split operand themselves when both step GEMMs run on the tensor cores
+  const bool fused_split = w3_g2 && w3_g1;
+  if (!fused_split) w.a3u = nullptr;
+  __nv_bfloat16* a3_step = fused_split ? w.a3u : w.a3;
   grid_init_kernel<<<Q, nt, 0, st>>>(*a, w);
   cudaMemsetAsync(w.uctx, 0, (size_t)Q * T * H * sizeof(float), st);
   for (int i = T - 1; i >= 0; --i) {
     grid_cell2_kernel<<<Q, nt, 0, st>>>(*a, w, i);
-    RUN(gemm_any<GE_STORE>(w.u, a->W_g2, w3_g2, w.a3, w.v, Q, 3 * H, H, none, st));
+    RUN(gemm_any<GE_STORE>(w.u, a->W_g2, w3_g2, a3_step, w.v, Q, 3 * H, H, none, st, fused_split));
     grid_post2_kernel<<<Q, nt, 0, st>>>(*a, w, i);
-    RUN(gemm_any<GE_STORE>(w.u, a->W_g1, w3_g1, w.a3, w.v, Q, 2 * H + 2 * E, H, none, st));
+    RUN(gemm_any<GE_STORE>(w.u, a->W_g1, w3_g1, a3_step, w.v, Q, 2 * H + 2 * E, H, none, st, fused_split));
     grid_post1_kernel<<<Q, 256, 0, st>>>(*a, w, i);
   }
   grid_glob_kernel<<<Q, 128, 0, st>>>(*a, w);
