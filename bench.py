@@ -334,7 +334,10 @@ def layer_table(eng, chunk, dev, pk):
         a = torch.randn(tc.pf_rows(n, c.h, c.w), c.cout, device=dev).to(torch.bfloat16)
         if li == 0:
             out = torch.empty(n, 3, c.h, c.w, device=dev)
-            fn = lambda: tc.tc_conv(a, c.w_rel, n, c.h, c.w, c.cout, 16, 3, tc.EPI_INPUT, out, row_img=rimg, x=st.x)
+            if c.w_rel3 is not None:          # the engine's own choice: filter columns folded into N
+                fn = lambda: tc.tc_conv(a, c.w_rel3, n, c.h, c.w, c.cout, 24, 3, tc.EPI_INPUT3, out, row_img=rimg, x=st.x)
+            else:
+                fn = lambda: tc.tc_conv(a, c.w_rel, n, c.h, c.w, c.cout, 16, 3, tc.EPI_INPUT, out, row_img=rimg, x=st.x)
             flops = 2.0 * n * c.h * c.w * c.cin * c.cout * 9
         else:
             below = eng.convs[li - 1]

@@ -319,6 +319,10 @@ enum {
   LRPX_TC_EPI_FEAT = 6,
   /* as FEAT, divided by stab(x1[img(q)][p][n])  (z + 0.01*sign z, 0 -> 0.01; the value-projection rule) */
   LRPX_TC_EPI_FEAT_DIV = 7,
+  /* first layer with the three filter columns folded into N: ncol = 24, Wt row dx*8 + c (c = 0..2: W+^T, 3..5: W-^T,
+   * 6..7: zero) holds, K-ordered (filter row dy, channel), the weights of filter tap (dy, dx); the kernel adds the
+   * three column-shifted partial sums in its epilogue.  Same output as LRPX_TC_EPI_INPUT (3x3 only). */
+  LRPX_TC_EPI_INPUT3 = 8,
 };
 
 typedef struct {

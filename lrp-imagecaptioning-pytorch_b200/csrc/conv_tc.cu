@@ -64,6 +64,9 @@ struct TcParams {
   int box0_rows, box1_rows;   // TMA boxes that make up a slab (box1_rows == 0: single box)
   int a_stage_bytes; // bytes of one A stage (= one slab), multiple of 1024
   int n_issuers;     // MMA issuer warps in use: 2 (one per M half) when mh == 2, else 1
+  int fold;          // EPI_INPUT3: the three filter columns are folded into N (see epi_input3); 0 otherwise
+  int half_rows;     // row distance between the M halves of a tile (128; 126 with fold: the halves overlap by two rows)
+  int tile_out_rows; // output rows per tile (mh*128; 252 with fold)
   int cluster;       // 2: CTA pairs (thread-block clusters) share every streamed B tile through TMA multicast; else 1
   int tiles_sched;   // tiles the persistent loop walks (cluster mode pads the M tiles to an even count)
   int store_off;     // EPI_MUL: byte offset (from the aligned smem base) of the TMA-store staging area, 0 = plain stores
@@ -249,6 +252,11 @@ __device__ __forceinline__ uint32_t make_idesc(int bn) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])    \
       : "r"(taddr)                                                                                              \
       : "memory")
+#define TMEM_LD_X8(taddr, v)                                                                                    \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                  \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])  \
+               : "r"(taddr)                                                                                      \
+               : "memory")
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
@@ -303,7 +311,7 @@ __device__ __forceinline__ int fast_div(int n, uint32_t m, int sh) {
 __device__ __forceinline__ RowInfo row_info(const TcParams& p, int row) {
   RowInfo r;
   r.row = row;
-  r.in_range = row < p.m_total;
+  r.in_range = row >= 0 && row < p.m_total;
   int rr = r.in_range ? row : 0;
   r.e = fast_div(rr, p.blk_mul, p.blk_sh);
   r.rem = rr - r.e * p.blk;
@@ -466,16 +474,6 @@ __device__ __forceinline__ void epi_input(const TcParams& p, const RowInfo& r, c
   }
 }
 
-// number of 32-column units per (lane quarter, M half) of a tile
-__device__ __forceinline__ int epi_units_per_half(const TcParams& p, int epi) {
-  if (epi == LRPX_TC_EPI_INPUT) return 1;
-  const int ncols = (epi == LRPX_TC_EPI_FWD_GAIN) ? p.half : p.bn;
-  return ncols >> 5;
-}
-
-// One unit: accumulator row `r` (this thread's), columns [c, c+32) of tile column block n_tile.
-// taddr = TMEM address of column 0 of this row's accumulator (lane quarter, buffer and M half already applied).
-// Global loads of gain / argmax are issued first, then TMEM -> registers, epilogue math, global stores.
 // release_bar != 0 (the warp's LAST unit of the tile): the accumulator buffer is handed back to the MMA issuers as
 // soon as this warp's last TMEM read has landed in registers, i.e. before the epilogue math and the global stores —
 // the stores are the slow part of the epilogue (measured: 8-22 % of a layer's time) and must not sit on the
@@ -488,14 +486,83 @@ __device__ __forceinline__ void epi_release(uint32_t release_bar) {
   }
 }
 
+// First layer with the three filter COLUMNS folded into N (LRPX_TC_EPI_INPUT3).  The N = 16 form issues 36 MMAs per 128
+// rows and every one of them is bound by its 4 KB A read from shared memory (~46 cycles instead of 8): the layer runs at
+// 1/6 of what its bytes allow.  Here one MMA chain per filter ROW (A view shifted by (dy-1)(w+1) rows, no column shift)
+// produces P'[q][dx*8 + c] = sum_{dy,ch} s[q + (dy-1)(w+1)][ch] W[c][dy,dx][ch]  (c < 3: W+, 3..5: W-), 12 MMAs per 128
+// rows, and the column shift moves to the epilogue:  acc[p][c] = P'[p-1][0,c] + P'[p][1,c] + P'[p+1][2,c].
+// Neighbouring rows are neighbouring TMEM lanes = neighbouring threads: warp shuffles, plus a 48-byte exchange through
+// shared memory at the three warp boundaries of a 128-row block.  The first and last row of a block have no neighbour,
+// so the M halves of a tile start 126 rows apart and a tile yields 252 output rows.
+__device__ __forceinline__ void epi_input3(const TcParams& p, const RowInfo& r, uint32_t taddr, uint32_t release_bar,
+                                           float* scratch /* [4 quarters][2][8] of this (buffer, half) */, int quarter,
+                                           int bar_id) {
+  const int lane = threadIdx.x & 31;
+  uint32_t v[24];
+  TMEM_LD_X16(taddr, v);
+  {
+    uint32_t (&v8)[8] = *reinterpret_cast<uint32_t (*)[8]>(&v[16]);
+    TMEM_LD_X8(taddr + 16, v8);
+  }
+  tmem_ld_wait();
+  epi_release(release_bar);
+  float up[6], dn[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    up[c] = __shfl_up_sync(0xffffffffu, __uint_as_float(v[c]), 1);          // P'[q-1][dx = 0]
+    dn[c] = __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + c]), 1);   // P'[q+1][dx = 2]
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) scratch[(quarter * 2 + 0) * 8 + c] = __uint_as_float(v[16 + c]);
+  if (lane == 31)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) scratch[(quarter * 2 + 1) * 8 + c] = __uint_as_float(v[c]);
+  // the four quarter warps of this M half meet on their own named barrier (immediate ids: ptxas counts them)
+  if (bar_id == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+  if (lane == 0 && quarter > 0)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) up[c] = scratch[((quarter - 1) * 2 + 1) * 8 + c];
+  if (lane == 31 && quarter < 3)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) dn[c] = scratch[((quarter + 1) * 2 + 0) * 8 + c];
+  const bool edge = (quarter == 0 && lane == 0) || (quarter == 3 && lane == 31);
+  if (!r.valid || edge || (p.debug_flags & 1)) return;
+  const int img = p.row_img ? p.row_img[r.e] : r.e;
+  const size_t hw = (size_t)p.h * p.w;
+  const size_t pix = (size_t)(r.a - 1) * p.w + (r.b - 1);
+  float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float xv = __ldg(p.x + ((size_t)img * 3 + c) * hw + pix);
+    const float cp = up[c] + __uint_as_float(v[8 + c]) + dn[c];
+    const float cn = up[3 + c] + __uint_as_float(v[8 + 3 + c]) + dn[3 + c];
+    out[((size_t)r.e * 3 + c) * hw + pix] = fmaxf(xv, 0.f) * cp + fminf(xv, 0.f) * cn;
+  }
+}
+
+// number of 32-column units per (lane quarter, M half) of a tile
+__device__ __forceinline__ int epi_units_per_half(const TcParams& p, int epi) {
+  if (epi == LRPX_TC_EPI_INPUT || epi == LRPX_TC_EPI_INPUT3) return 1;
+  const int ncols = (epi == LRPX_TC_EPI_FWD_GAIN) ? p.half : p.bn;
+  return ncols >> 5;
+}
+
+// One unit: accumulator row `r` (this thread's), columns [c, c+32) of tile column block n_tile.
+// taddr = TMEM address of column 0 of this row's accumulator (lane quarter, buffer and M half already applied).
+// Global loads of gain / argmax are issued first, then TMEM -> registers, epilogue math, global stores.
 template <int EPI>
 __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, uint32_t taddr, int n_tile, int c,
-                                         uint32_t release_bar, uint32_t stage = 0, const CUtensorMap* tmo = nullptr) {
+                                         uint32_t release_bar, uint32_t stage = 0, const CUtensorMap* tmo = nullptr,
+                                         float* scratch = nullptr, int quarter = 0, int bar_id = 0) {
   if (p.debug_flags & 16) { epi_release(release_bar); return; }      // timing experiment: only hands the accumulator back
   RowInfo r = r0;
   if (p.debug_flags & 1) { r.in_range = false; r.valid = false; }
   const int n0 = n_tile * p.bn;
-  if (EPI == LRPX_TC_EPI_INPUT) {
+  if (EPI == LRPX_TC_EPI_INPUT3) {
+    epi_input3(p, r0, taddr, release_bar, scratch, quarter, bar_id);
+  } else if (EPI == LRPX_TC_EPI_INPUT) {
     uint32_t v[16];
     TMEM_LD_X16(taddr, v);
     tmem_ld_wait();
@@ -607,7 +674,7 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
 template <int EPI>
 __device__ __forceinline__ void epi_prefetch_unit(const TcParams& p, int row, int n_tile, int c) {
   if (EPI != LRPX_TC_EPI_MUL && EPI != LRPX_TC_EPI_MUL_UNPOOL) return;
-  if (row >= p.m_total) return;
+  if (row >= p.m_total || (p.debug_flags & 128)) return;      // 128: timing experiment without the L2 prefetch
   const RowInfo q = row_info(p, row);
   if (!q.valid) return;
   const int img = p.row_img ? p.row_img[q.e] : q.e;
@@ -622,7 +689,8 @@ __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_bas
                                                   uint32_t taddr_q /* lane quarter + buffer */, int n_tile, int sub,
                                                   int mh, int pf_row_base /* same for the prefetched tile, or -1 */,
                                                   uint32_t release_bar /* tmem_empty barrier of the tile's buffer */,
-                                                  uint32_t stage = 0, const CUtensorMap* tmo = nullptr) {
+                                                  uint32_t stage = 0, const CUtensorMap* tmo = nullptr,
+                                                  float* scratch = nullptr /* INPUT3: [2 halves][4][2][8] */, int quarter = 0) {
   const int uph = epi_units_per_half(p, EPI);
   const int n_units = mh * uph;
   constexpr int step = TC_EPI_WARPS / 4;
@@ -634,9 +702,11 @@ __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_bas
   RowInfo r{};
   for (int u = sub; u < n_units; u += step) {
     const int h = u / uph, c = (u - h * uph) << 5;
-    if (h != h_cached) { r = row_info(p, row_base + h * TC_BM); h_cached = h; }
+    const int hr = (EPI == LRPX_TC_EPI_INPUT3) ? p.half_rows : TC_BM;
+    if (h != h_cached) { r = row_info(p, row_base + h * hr); h_cached = h; }
     if (pf_row_base >= 0) epi_prefetch_unit<EPI>(p, pf_row_base + h * TC_BM, n_tile, c);
-    epi_unit<EPI>(p, r, taddr_q + (uint32_t)(h * p.bn), n_tile, c, (u + step >= n_units) ? release_bar : 0u, stage, tmo);
+    epi_unit<EPI>(p, r, taddr_q + (uint32_t)(h * p.bn), n_tile, c, (u + step >= n_units) ? release_bar : 0u, stage, tmo,
+                  scratch ? scratch + h * 64 : nullptr, quarter, 1 + h);
   }
 }
 
@@ -802,7 +872,9 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
   const bool skip_mma = (p.debug_flags & 2) != 0;     // timing experiment
   // this issuer's M halves: [h0, h1)
   const int h0 = p.n_issuers == 2 ? issuer : 0, h1 = p.n_issuers == 2 ? issuer + 1 : p.mh;
-  const uint32_t a_lo_base = desc_lo(a_base) + (uint32_t)h0 * ((TC_BM * TC_BK * 2) >> 4);
+  const uint32_t half16 = (uint32_t)p.half_rows * row16;           // M halves: 128 rows apart (126 with fold)
+  const int ndx = p.fold ? 1 : 3;                                   // fold: the filter columns live in N, one chain per filter row
+  const uint32_t a_lo_base = desc_lo(a_base) + (uint32_t)h0 * half16;
   const uint32_t b_lo_base = desc_lo(b_base);
   int as = 0, bs = 0, it = 0;
   uint32_t aph = 0, bph = 0;
@@ -829,10 +901,11 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
         const uint32_t a_row = a_lo_base + (uint32_t)as * a_stage16 + (uint32_t)dy * dy16;
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
+          if (dx >= ndx) break;
           const int tap = dy * 3 + dx;
           uint32_t b_lo;
           if (BRES) {
-            b_lo = b_lo_base + (uint32_t)(tap * kcpt + kc) * b16;
+            b_lo = b_lo_base + (uint32_t)((p.fold ? dy : tap) * kcpt + kc) * b16;
           } else {
             mbar_wait(smem_u32(&b_full[bs]), bph);
             tc_fence_after();
@@ -840,7 +913,7 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
           }
           const uint32_t a_lo = a_row + (uint32_t)dx * row16;
           for (int h = h0; h < h1 && !skip_mma; ++h) {
-            const uint32_t ah = a_lo + (uint32_t)(h - h0) * ((TC_BM * TC_BK * 2) >> 4);
+            const uint32_t ah = a_lo + (uint32_t)(h - h0) * half16;
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)
               tc_mma_f16(d_tmem + (uint32_t)(h - h0) * bn, desc_pack(ah + 2 * k), desc_pack(b_lo + 2 * k), idesc,
@@ -892,6 +965,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float in3_scratch[2][2][64];      // EPI_INPUT3: [accumulator buffer][M half][quarter][2][8]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -899,7 +973,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)p.a_stages * p.a_stage_bytes;
   const int num_tiles = p.tiles_sched;
-  const int tile_rows = p.mh * TC_BM;
+  const int tile_rows = p.tile_out_rows;       // output rows per tile; with fold the computed rows start one row earlier
   const int n_slabs = p.slab_mode == 1 ? 1 : 3;
 
   if (threadIdx.x == 0) {
@@ -942,7 +1016,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_tile, n_tile_unused;
         tile_coords(p, tile, m_tile, n_tile_unused);
-        const int m0 = m_tile * tile_rows;
+        const int m0 = m_tile * tile_rows;             // fold: P' rows start at m0 - 1, which is where the slabs start anyway
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
           for (int j = 0; j < n_slabs; ++j) {          // one ring stage per slab
             mbar_wait_relaxed(smem_u32(&a_empty[as]), aph ^ 1);
@@ -1034,8 +1108,9 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int pf_row = (n_pf == n_tile) ? m_pf * tile_rows + quarter * 32 + lane : -1;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
       const uint32_t stage = (EPI == LRPX_TC_EPI_MUL && p.store_off) ? smem_base + (uint32_t)p.store_off + (uint32_t)(warp - 2) * 1024u : 0u;
-      run_epilogue_tile<EPI>(p, m_tile * tile_rows + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh, pf_row,
-                             smem_u32(&tmem_empty_bar[buf]), stage, &tmO);
+      run_epilogue_tile<EPI>(p, m_tile * tile_rows - p.fold + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh,
+                             pf_row, smem_u32(&tmem_empty_bar[buf]), stage, &tmO,
+                             EPI == LRPX_TC_EPI_INPUT3 ? &in3_scratch[buf][0][0] : nullptr, quarter);
     }
     if (EPI == LRPX_TC_EPI_MUL && p.store_off) {      // the staging block must outlive the last tile store's read
       if (lane == 0) bulk_wait_read0();
@@ -1265,7 +1340,8 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
   LRPX_CHECK_ARG(a->cin > 0 && a->cin % TC_BK == 0, "cin must be a multiple of 64");
   LRPX_CHECK_ARG(a->ksize == 1 || a->ksize == 3, "ksize must be 1 or 3");
   LRPX_CHECK_ARG(a->a && a->wt && a->out, "null pointer");
-  LRPX_CHECK_ARG(a->ncol > 0 && a->ncol % 16 == 0, "ncol must be a multiple of 16");
+  LRPX_CHECK_ARG(a->ncol > 0 && (a->ncol % 16 == 0 || (a->epilogue == LRPX_TC_EPI_INPUT3 && a->ncol == 24)),
+                 "ncol must be a multiple of 16");
   const int epi = a->epilogue;
   TcParams p{};
   p.h = a->h; p.w = a->w; p.wp1 = a->w + 1;
@@ -1299,6 +1375,12 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     LRPX_CHECK_ARG(cout % p.half == 0, "FWD_GAIN: output channels must be <128 or a multiple of 128");
     p.bn = 2 * p.half;
     p.out_c = cout;
+  } else if (epi == LRPX_TC_EPI_INPUT3) {
+    LRPX_CHECK_ARG(a->ncol == 24 && a->x && a->ksize == 3, "INPUT3 epilogue: ncol must be 24, x set, 3x3");
+    p.bn = 24;
+    p.out_c = 3;
+    p.taps = 3;           // B tiles per channel block: one per filter row (the filter columns live in N)
+    p.fold = 1;
   } else if (epi == LRPX_TC_EPI_INPUT) {
     LRPX_CHECK_ARG(a->ncol == 16 && a->x, "INPUT epilogue: ncol must be 16 (3 W+ cols, 3 W- cols, padding) and x set");
     p.bn = 16;
@@ -1332,7 +1414,9 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     const bool tma_store = epi == LRPX_TC_EPI_MUL && !(env_ts && env_ts[0] == '0');
     const int reserve = tma_store ? TC_EPI_WARPS * 1024 : 0;
     if (want_slab && plan_slab(p, reserve)) {
-      const int tile_rows = p.mh * TC_BM;
+      p.half_rows = p.fold ? TC_BM - 2 : TC_BM;
+      p.tile_out_rows = p.mh * p.half_rows;
+      const int tile_rows = p.tile_out_rows;
       p.num_m_tiles = (p.m_total + tile_rows - 1) / tile_rows;
       CUtensorMap ma0, ma1, mb, mo;
       mo = CUtensorMap{};
@@ -1371,11 +1455,13 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
         case LRPX_TC_EPI_MUL: return launch_tc_slab<LRPX_TC_EPI_MUL>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_MUL_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MUL_UNPOOL>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_INPUT: return launch_tc_slab<LRPX_TC_EPI_INPUT>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        case LRPX_TC_EPI_INPUT3: return launch_tc_slab<LRPX_TC_EPI_INPUT3>(ma0, ma1, mb, mbh, mo, p, grid, st);
         default: return launch_tc_slab<LRPX_TC_EPI_STORE_F32>(ma0, ma1, mb, mbh, mo, p, grid, st);
       }
     }
   }
-  p.slab_mode = 0; p.mh = 1; p.n_issuers = 1; p.cluster = 1;
+  LRPX_CHECK_ARG(epi != LRPX_TC_EPI_INPUT3, "INPUT3 needs the slab kernel (3x3, LRPX_TC_SLAB != 0)");
+  p.slab_mode = 0; p.mh = 1; p.n_issuers = 1; p.cluster = 1; p.half_rows = TC_BM; p.tile_out_rows = TC_BM;
   p.num_m_tiles = (p.m_total + TC_BM - 1) / TC_BM;
   const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;
   p.stages = (TC_SMEM_BYTES - 1024) / stage_bytes;

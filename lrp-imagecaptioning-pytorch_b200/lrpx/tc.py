@@ -15,6 +15,7 @@ What it replaces in the reference, for an encoder made of conv3x3(pad 1) + ReLU 
   (lrp_modules.py:186-191) folded into the epilogue through the saved 2-bit argmax.
 """
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -23,6 +24,7 @@ from . import _lib
 from ._lib import TcConvArgs, check, lib
 
 EPI_FWD_GAIN, EPI_MUL, EPI_MUL_UNPOOL, EPI_INPUT, EPI_STORE_F32 = 1, 2, 3, 4, 5
+EPI_INPUT3 = 8
 
 
 def _ptr(t):
@@ -117,7 +119,7 @@ def maxpool2(act, gain, n, h, w, c, want_idx=True):
 
 
 class _Conv:
-    __slots__ = ("cin", "cout", "h", "w", "pool_after", "w_f32", "bias", "w_dual", "w_rel")
+    __slots__ = ("cin", "cout", "h", "w", "pool_after", "w_f32", "bias", "w_dual", "w_rel", "w_rel3")
 
 
 class VggState:
@@ -168,6 +170,12 @@ class TcVggEngine:
                 weight_prep(w, 2, out=c.w_rel[0:3])
                 weight_prep(w, 3, out=c.w_rel[3:6])
                 c.w_dual = None
+                # LRPX_TC_EPI_INPUT3: filter columns folded into N — row dx*8 + r holds, K-ordered (dy, channel), the
+                # weights of tap (dy, dx) of w_rel's row r
+                c.w_rel3 = None
+                if c.cout % 64 == 0 and os.environ.get("LRPX_TC_INPUT3", "1") != "0":
+                    t = c.w_rel[0:8].reshape(8, 3, 3, c.cout)                      # (r, dy, dx, ch)
+                    c.w_rel3 = t.permute(2, 0, 1, 3).reshape(24, 3 * c.cout).contiguous()
                 if c.cout % 32 == 0:
                     # forward on the tensor cores over the sign-split im2col (lrpx_tc_im2col3_split_bf16):
                     # rows [w | w | 0] -> z, rows [w+ | w- | 0] -> z+   (K = 27 + 27 + 10 zero columns)
@@ -349,7 +357,10 @@ class TcVggEngine:
                                                st.feat_c, _stream()), "lrpx_tc_scale_rows")
             s, cur = self._run_layers(st, s, nq, rimg, 1, split, buf, cur)
             c0 = self.convs[0]
-            tc_conv(s, c0.w_rel, nq, c0.h, c0.w, c0.cout, 16, 3, EPI_INPUT, out[q0:q1], row_img=rimg, x=st.x)
+            if c0.w_rel3 is not None:
+                tc_conv(s, c0.w_rel3, nq, c0.h, c0.w, c0.cout, 24, 3, EPI_INPUT3, out[q0:q1], row_img=rimg, x=st.x)
+            else:
+                tc_conv(s, c0.w_rel, nq, c0.h, c0.w, c0.cout, 16, 3, EPI_INPUT, out[q0:q1], row_img=rimg, x=st.x)
             if on_chunk is not None:
                 on_chunk(q0, q1)
         return out

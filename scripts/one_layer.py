@@ -18,7 +18,10 @@ for li in [int(v) for v in os.environ.get("LAYERS", "1").split(",")]:
     a = torch.randn(tc.pf_rows(n, c.h, c.w), c.cout, device="cuda").to(torch.bfloat16)
     if li == 0:
         out = torch.empty(n, 3, c.h, c.w, device="cuda")
-        fn = lambda: tc.tc_conv(a, c.w_rel, n, c.h, c.w, c.cout, 16, 3, tc.EPI_INPUT, out, row_img=rimg, x=st.x)
+        if c.w_rel3 is not None:
+            fn = lambda: tc.tc_conv(a, c.w_rel3, n, c.h, c.w, c.cout, 24, 3, tc.EPI_INPUT3, out, row_img=rimg, x=st.x)
+        else:
+            fn = lambda: tc.tc_conv(a, c.w_rel, n, c.h, c.w, c.cout, 16, 3, tc.EPI_INPUT, out, row_img=rimg, x=st.x)
     elif eng.convs[li - 1].pool_after:
         out = torch.empty(tc.pf_rows(n, 2 * c.h, 2 * c.w), c.cin, device="cuda", dtype=torch.bfloat16)
         fn = lambda: tc.tc_conv(a, c.w_rel, n, c.h, c.w, c.cout, c.cin, 3, tc.EPI_MUL_UNPOOL, out, gain=st.gain[li - 1],

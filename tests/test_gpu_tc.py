@@ -221,3 +221,35 @@ def test_relevance_groups_and_chunks_do_not_change_results():
         assert torch.equal(got, ref), (group, chunk)
         assert seen[0][0] == 0 and seen[-1][1] == Q and all(a[1] == b[0] for a, b in zip(seen, seen[1:])), seen
     eng.GROUP = 2048
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 8, 8), (3, 12, 20), (2, 56, 56), (5, 224, 224)])
+def test_first_layer_folded_columns_equals_plain_form(n, h, w):
+    """LRPX_TC_EPI_INPUT3 (filter columns folded into N, column shift in the epilogue, 126-row M halves) vs
+    LRPX_TC_EPI_INPUT (one MMA chain per filter tap) on the same operands: same bf16 products, fp32 accumulation in
+    another order -> equal within 1e-5 of the largest element; every pixel of every request is written."""
+    from lrpx import tc
+    g = torch.Generator().manual_seed(h * 7 + w)
+    cout = 64
+    wt = torch.randn(cout, 3, 3, 3, generator=g) * 0.2
+    sd = {"0.weight": wt, "0.bias": torch.zeros(cout)}
+    eng = tc.TcVggEngine([wt], [torch.zeros(cout)], [cout], DEV)
+    c0 = eng.convs[0]
+    assert c0.w_rel3 is not None
+    x = torch.randn(n, 3, h, w, generator=g).to(DEV)
+    s = _bf(torch.randn(n, cout, h, w, generator=g)).to(DEV)
+    a = tc.nchw_to_pf(s)
+    rimg = torch.arange(n, dtype=torch.int32, device=DEV)
+    out16 = torch.full((n, 3, h, w), float("nan"), device=DEV)
+    out24 = torch.full((n, 3, h, w), float("nan"), device=DEV)
+    tc.tc_conv(a, c0.w_rel, n, h, w, cout, 16, 3, tc.EPI_INPUT, out16, row_img=rimg, x=x)
+    tc.tc_conv(a, c0.w_rel3, n, h, w, cout, 24, 3, tc.EPI_INPUT3, out24, row_img=rimg, x=x)
+    assert torch.isfinite(out24).all()
+    scale = float(out16.abs().max())
+    assert float((out24 - out16).abs().max()) <= 1e-5 * scale
+    # and against the rule itself: R = x+ (W+^T * s) + x- (W-^T * s)   (lrp_modules.py:81-84, utils.py:26-30)
+    wb = _bf(wt).to(DEV)
+    cp = torch.nn.grad.conv2d_input((n, 3, h, w), wb.clamp(min=0), s, 1, 1)
+    cn = torch.nn.grad.conv2d_input((n, 3, h, w), wb.clamp(max=0), s, 1, 1)
+    ref = x.clamp(min=0) * cp + x.clamp(max=0) * cn
+    assert_close(out24, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()), what="folded first layer vs rule")
