@@ -498,6 +498,16 @@ __device__ __forceinline__ void epi_input3(const TcParams& p, const RowInfo& r, 
                                            float* scratch /* [4 quarters][2][8] of this (buffer, half) */, int quarter,
                                            int bar_id) {
   const int lane = threadIdx.x & 31;
+  const bool edge = (quarter == 0 && lane == 0) || (quarter == 3 && lane == 31);
+  const bool writes = r.valid && !edge && !(p.debug_flags & 1);
+  // the three input values of this pixel: issued before the accumulator read so that their L2 latency hides under it
+  const int img = p.row_img ? p.row_img[r.e] : r.e;
+  const size_t hw = (size_t)p.h * p.w;
+  const size_t pix = writes ? (size_t)(r.a - 1) * p.w + (r.b - 1) : 0;
+  float xin[3] = {0.f, 0.f, 0.f};
+  if (writes)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) xin[c] = __ldg(p.x + ((size_t)img * 3 + c) * hw + pix);
   uint32_t v[24];
   TMEM_LD_X16(taddr, v);
   {
@@ -520,22 +530,20 @@ __device__ __forceinline__ void epi_input3(const TcParams& p, const RowInfo& r, 
     for (int c = 0; c < 6; ++c) scratch[(quarter * 2 + 1) * 8 + c] = __uint_as_float(v[c]);
   // the four quarter warps of this M half meet on their own named barrier (immediate ids: ptxas counts them)
   if (bar_id == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
-  else asm volatile("bar.sync 2, 128;" ::: "memory");
+  else if (bar_id == 2) asm volatile("bar.sync 2, 128;" ::: "memory");
+  else if (bar_id == 3) asm volatile("bar.sync 3, 128;" ::: "memory");
+  else asm volatile("bar.sync 4, 128;" ::: "memory");
   if (lane == 0 && quarter > 0)
 #pragma unroll
     for (int c = 0; c < 6; ++c) up[c] = scratch[((quarter - 1) * 2 + 1) * 8 + c];
   if (lane == 31 && quarter < 3)
 #pragma unroll
     for (int c = 0; c < 6; ++c) dn[c] = scratch[((quarter + 1) * 2 + 0) * 8 + c];
-  const bool edge = (quarter == 0 && lane == 0) || (quarter == 3 && lane == 31);
-  if (!r.valid || edge || (p.debug_flags & 1)) return;
-  const int img = p.row_img ? p.row_img[r.e] : r.e;
-  const size_t hw = (size_t)p.h * p.w;
-  const size_t pix = (size_t)(r.a - 1) * p.w + (r.b - 1);
+  if (!writes) return;
   float* out = reinterpret_cast<float*>(p.out);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float xv = __ldg(p.x + ((size_t)img * 3 + c) * hw + pix);
+    const float xv = xin[c];
     const float cp = up[c] + __uint_as_float(v[8 + c]) + dn[c];
     const float cn = up[3 + c] + __uint_as_float(v[8 + 3 + c]) + dn[3 + c];
     out[((size_t)r.e * 3 + c) * hw + pix] = fmaxf(xv, 0.f) * cp + fminf(xv, 0.f) * cn;
@@ -690,10 +698,20 @@ __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_bas
                                                   int mh, int pf_row_base /* same for the prefetched tile, or -1 */,
                                                   uint32_t release_bar /* tmem_empty barrier of the tile's buffer */,
                                                   uint32_t stage = 0, const CUtensorMap* tmo = nullptr,
-                                                  float* scratch = nullptr /* INPUT3: [2 halves][4][2][8] */, int quarter = 0) {
+                                                  float* scratch = nullptr /* INPUT3: [2 halves][4][2][8] */, int quarter = 0,
+                                                  int it = 0 /* this CTA's tile counter */) {
   const int uph = epi_units_per_half(p, EPI);
   const int n_units = mh * uph;
   constexpr int step = TC_EPI_WARPS / 4;
+  // First-layer epilogues have only mh (<= 2) units per lane quarter, and a tile's MMAs are short: the tile time is the
+  // LATENCY of one epilogue pass.  Warps 0,1 of a quarter therefore take the even tiles and warps 2,3 the odd ones, so
+  // the passes of the two accumulator buffers overlap.
+  int set = 0;
+  if ((EPI == LRPX_TC_EPI_INPUT || EPI == LRPX_TC_EPI_INPUT3) && n_units <= 2) {
+    set = it & 1;
+    sub = set ? sub - 2 : sub;
+    if (sub < 0 || sub >= 2) sub = n_units;          // not this warp's tile
+  }
   if (sub >= n_units) {                 // nothing to read for this warp: hand the buffer back at once
     epi_release(release_bar);
     return;
@@ -706,7 +724,7 @@ __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_bas
     if (h != h_cached) { r = row_info(p, row_base + h * hr); h_cached = h; }
     if (pf_row_base >= 0) epi_prefetch_unit<EPI>(p, pf_row_base + h * TC_BM, n_tile, c);
     epi_unit<EPI>(p, r, taddr_q + (uint32_t)(h * p.bn), n_tile, c, (u + step >= n_units) ? release_bar : 0u, stage, tmo,
-                  scratch ? scratch + h * 64 : nullptr, quarter, 1 + h);
+                  scratch ? scratch + h * 64 : nullptr, quarter, 1 + 2 * set + h);
   }
 }
 
@@ -1110,7 +1128,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const uint32_t stage = (EPI == LRPX_TC_EPI_MUL && p.store_off) ? smem_base + (uint32_t)p.store_off + (uint32_t)(warp - 2) * 1024u : 0u;
       run_epilogue_tile<EPI>(p, m_tile * tile_rows - p.fold + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh,
                              pf_row, smem_u32(&tmem_empty_bar[buf]), stage, &tmO,
-                             EPI == LRPX_TC_EPI_INPUT3 ? &in3_scratch[buf][0][0] : nullptr, quarter);
+                             EPI == LRPX_TC_EPI_INPUT3 ? &in3_scratch[buf][0][0] : nullptr, quarter, it);
     }
     if (EPI == LRPX_TC_EPI_MUL && p.store_off) {      // the staging block must outlive the last tile store's read
       if (lane == 0) bulk_wait_read0();

@@ -71,7 +71,17 @@ def test_conv_forward_and_epsilon():
     assert_close(ops.conv_forward(*_c(x, w, b), 2, 1), ref, atol=1e-5, what="conv forward")
     assert_close(ops.conv_forward(*_c(x, w, b), 2, 1, relu=True), ref.clamp(min=0), atol=1e-5, what="conv+relu")
     r = torch.randn_like(ref)
+    # s = r / (z + eps*sign z) amplifies the fp32 rounding of z by 1/|z| (this seed has min |z| = 0.014, where the
+    # torch-CPU fp32 oracle itself is 8e-6 of the scale away from fp64): keep the comparison at the 1e-4 bar on the
+    # well-conditioned outputs and cover the small-|z| ones at the conditioning-scaled bar below
+    small = ref.abs() < 0.25
+    r_all = r.clone()
+    r = r.masked_fill(small, 0.0)
     for ib in (True, False):
+        want = O.conv_epsilon_unpinned(x.double(), w.double(), b.double(), r_all.double(), 2, 1, ignore_bias=ib)
+        got = ops.conv_epsilon(*_c(x, w, b, r_all), 2, 1, ignore_bias=ib)
+        scale = want.abs().max()
+        assert_close(got / scale, want / scale, rtol=1e-4, atol=1e-4, what=f"conv epsilon (all outputs) ib={ib}")
         want = O.conv_epsilon_unpinned(x.double(), w.double(), b.double(), r.double(), 2, 1, ignore_bias=ib)
         got = ops.conv_epsilon(*_c(x, w, b, r), 2, 1, ignore_bias=ib)
         scale = want.abs().max()
