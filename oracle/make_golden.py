@@ -250,6 +250,36 @@ def golden_aoa_decoder(ns):
         save(tag, **out)
 
 
+def golden_adaptive_decoder(ns):
+    """ExplainAdaptiveAttention (adaptiveattention.py:491-848): saved state + explain_caption_wordt."""
+    for tag, (V, H, T, seed, ts) in {"adaptive_dec_512": (1000, 512, 10, 61, [0, 6, 9]),
+                                     "adaptive_dec_small": (300, 64, 6, 62, [4])}.items():
+        E = H                               # the explainer's x_t buffer is embed_dim + hidden_dim wide (:636)
+        wm = synth.word_map(V)
+        with quiet():
+            model = ns.adaptiveattention.AdaptiveAttentionCaptioningModel(E, H, V, "vgg16")
+        model.load_state_dict(synth.adaptive_decoder_state(seed, V, H, E), strict=False)
+        feats = _features(seed + 1, 512, 14, 14)
+        model.img_encoder = _StubEncoder(feats)
+        toks = synth.tokens(seed + 2, T, V)
+        model.beam_search = lambda *a, **k: ([" ".join(f"w{t}" for t in toks[1:])], toks[1:])
+        args = argparse.Namespace(embed_dim=E, hidden_dim=H, encoder="vgg16", height=224, width=224,
+                                  save_path="/tmp/lrpx_ref", dataset="syn", weight="")
+        ex = ns.adaptiveattention.ExplainAdaptiveAttention(args, wm, model=model)
+        ex.preprocess_img = lambda p: torch.zeros(1, 3, 224, 224)
+        with torch.no_grad(), quiet():
+            ex.get_hidden_parameters("x")
+        out = dict(V=V, H=H, E=E, T=T, seed=seed, tokens=np.array(toks), ts=np.array(ts), feats=feats,
+                   predictions=ex.predictions, alphas=ex.alphas, betas=ex.betas, ht=ex.ht, ct=ex.ct, st=ex.st,
+                   context_hat=ex.context_hat)
+        for t in ts:
+            with torch.no_grad(), quiet():
+                rf, rw = ex.explain_caption_wordt(t)
+            out[f"r_feat_{t}"] = rf
+            out[f"r_words_{t}"] = rw
+        save(tag, **out)
+
+
 def _rev_word_map(V, stop):
     wm = synth.word_map(V)
     rev = {v: k for k, v in wm.items()}
@@ -341,7 +371,7 @@ def main():
     torch.manual_seed(0)
     only = set(sys.argv[1:])          # optional: names of the generators to (re)run
     for fn in (golden_rules, golden_sequential_small, golden_vgg16, golden_resnet, golden_gridtd_decoder,
-               golden_aoa_decoder, golden_lrp_weights, golden_tune, golden_tune_bu):
+               golden_aoa_decoder, golden_adaptive_decoder, golden_lrp_weights, golden_tune, golden_tune_bu):
         if only and fn.__name__ not in only:
             continue
         print(fn.__name__)

@@ -123,10 +123,12 @@ def load_reference(cpu: bool = True):
 
         ref_grid = _load_patched("models.gridTDmodel", "models/gridTDmodel.py")
         ref_aoa = _load_patched("models.aoamodel", "models/aoamodel.py")
+        ref_ada = _load_patched("models.adaptiveattention", "models/adaptiveattention.py")
     finally:
         sys.path.remove(REFERENCE_ROOT)
     ns = types.SimpleNamespace(utils=ref_utils, lrp_modules=ref_lrp_modules, lrp_wrapper=ref_lrp_wrapper,
-                               vgg=ref_vgg, resnet=ref_resnet, gridTDmodel=ref_grid, aoamodel=ref_aoa)
+                               vgg=ref_vgg, resnet=ref_resnet, gridTDmodel=ref_grid, aoamodel=ref_aoa,
+                               adaptiveattention=ref_ada)
     _loaded["ns"] = ns
     # leave the reference's modules registered under private names only
     for k in [k for k in sys.modules if k.split(".")[0] in ("LRPtools", "models")]:

@@ -77,6 +77,27 @@ def gridtd_decoder_state(seed: int, V: int, H: int, E: int, C: int = 512, n_pixe
     return sd
 
 
+def adaptive_decoder_state(seed: int, V: int, H: int, E: int, C: int = 512, n_pixel: int = 196):
+    """Everything in AdaptiveAttentionCaptioningModel except img_encoder.* (adaptiveattention.py:103-121);
+    the explainer's saved x_t is sized embed_dim + hidden_dim (:636), so E must equal H."""
+    g = _gen(seed)
+    sd = {}
+    b = 1.0 / math.sqrt(C)
+    sd["img_projector.weight"] = _uniform(g, (H, C, 1, 1), b)
+    sd["img_projector.bias"] = _uniform(g, (H,), b)
+    _linear(g, sd, "global_img_feature_proj", E, C)
+    _lstm(g, sd, "AdaLSTM.lstm_cell", 2 * E, H)
+    _linear(g, sd, "AdaLSTM.x_gate", H, 2 * E)
+    _linear(g, sd, "AdaLSTM.h_gate", H, H)
+    _linear(g, sd, "AdaAttention.W_v_proj", n_pixel, H)
+    _linear(g, sd, "AdaAttention.W_s_proj", n_pixel, H)
+    _linear(g, sd, "AdaAttention.W_g_proj", n_pixel, H, bias=False)
+    _linear(g, sd, "AdaAttention.w_h", 1, n_pixel, bias=False)
+    sd["embedding.weight"] = torch.randn(V, E, generator=g)
+    _linear(g, sd, "fc", V, H)
+    return sd
+
+
 def aoa_decoder_state(seed: int, V: int, H: int, E: int, C: int = 512):
     """Everything in AOAModel except img_encoder.* (aoamodel.py:111-139)."""
     g = _gen(seed)
