@@ -205,6 +205,48 @@ typedef struct {
 size_t lrpx_aoa_decoder_workspace_bytes(const lrpx_aoa_args* args);
 int lrpx_aoa_decoder_lrp_f32(const lrpx_aoa_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ExplainAdaptiveAttention.explain_caption_wordt (models/adaptiveattention.py:679-771): the single-LSTM adaptive
+ * attention decoder.  Saved state = get_hidden_parameters (:626-677), stacked over B images, padded to T steps. */
+typedef struct {
+  int B, T, H, E, P, C, V, Q;
+  int flags, reserved_;    /* LRPX_DEC_* */
+  /* per image */
+  const float* feat;      /* (B,P,C)  encoder output, pixel-major                            adaptiveattention.py:748-749 */
+  const float* avg;       /* (B,C)    mean feature = forward_input of the global rule                       :744       */
+  const float* z_proj;    /* (B,P,H)  feat @ W_proj^T WITHOUT bias (forward_output=False)                   :762       */
+  const float* A;         /* (B,P,H)  relu(z_proj + bias)                                                   :633       */
+  const float* z_glob;    /* (B,E)    avg @ W_glob^T WITHOUT bias (forward_output=False)                    :745       */
+  /* per image and step */
+  const float* x;         /* (B,T,2E) [emb | glob]                                                          :649,:663  */
+  const float* h;         /* (B,T+1,H) row 0 = zeros                                                        :667       */
+  const float* c;         /* (B,T+1,H) */
+  const float* g;         /* (B,T,H) pre-tanh cell candidate                                                :669       */
+  const float* i;         /* (B,T,H) sigmoid(input gate) */
+  const float* f;         /* (B,T,H) */
+  const float* st;        /* (B,T,H) sentinel                                                               :672       */
+  const float* ctx;       /* (B,T,H) */
+  const float* ctx_hat;   /* (B,T,H) */
+  const float* alpha;     /* (B,T,P) */
+  const float* beta;      /* (B,T)   */
+  const float* pred;      /* (B,T,V) logits                                                                 :664       */
+  /* weights */
+  const float* W_g;       /* (H, 2E+H) = [W_ih | W_hh] rows of gate g of AdaLSTM                            :685-687   */
+  const float* W_fc;      /* (V, H)                                                                         :523       */
+  const float* W_glob;    /* (E, C)                                                                         :746       */
+  const float* W_proj;    /* (H, C)                                                                         :763       */
+  /* requests */
+  const int32_t* req_img;   /* (Q) */
+  const int32_t* req_t;     /* (Q) 0 <= t_q < T */
+  const int32_t* req_word;  /* (Q) tokens[b_q][t_q+1]                                                       :682       */
+  /* outputs */
+  float* r_feat;            /* (Q,P,C)                                                                      :768       */
+  float* r_words;           /* (Q,T)  normalised, entries > t_q are 0                                       :764-767   */
+  float* r_words_raw;       /* (Q,T)  may be NULL */
+} lrpx_adaptive_args;
+
+size_t lrpx_adaptive_decoder_workspace_bytes(const lrpx_adaptive_args* args);
+int lrpx_adaptive_decoder_lrp_f32(const lrpx_adaptive_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
 /* lrp_tune weights, batched (gridTDmodel.py:549-578, aoamodel.py:597-626, utils.py:55-64):
  *   w = argmax logits[b]; if is_stop[w] -> weights 1; else r = fc-row eps rule, split to h / ctx,
  *   weights = r / max|r| + 1.   No host synchronisation; is_stop is a device byte mask (V). */

@@ -587,6 +587,166 @@ static size_t aoa_carve(const lrpx_aoa_args* a, float* base, AoaWs* w) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Adaptive attention (single AdaLSTM): ExplainAdaptiveAttention.explain_caption_wordt, adaptiveattention.py:679-771
+// ------------------------------------------------------------------------------------------------
+struct AdaWs {
+  float *r_h, *r_c, *r_glob, *u, *v, *uctx, *coefavg, *wproj;
+  __nv_bfloat16 *a3, *w3_g, *w3_glob, *w3_proj;
+  __nv_bfloat16* a3u;      // split form of u written by the cell kernel itself (null: CUDA-core GEMM)
+};
+
+// fc rule on the target row, split into h / ctx_hat, ctx_hat into context / sentinel (:700-724)
+__global__ void ada_init_kernel(lrpx_adaptive_args a, AdaWs w) {
+  int q = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q], word = a.req_word[q];
+  float logit = a.pred[((size_t)b * a.T + t) * a.V + word];
+  float coef = logit / stab(logit);
+  const float* h = a.h + ((size_t)b * (a.T + 1) + t + 1) * a.H;
+  size_t bi = ((size_t)b * a.T + t) * a.H;
+  const float* wr = a.W_fc + (size_t)word * a.H;
+  float beta = a.beta[(size_t)b * a.T + t];
+  for (int j = threadIdx.x; j < a.H; j += blockDim.x) {
+    float rh, rcth;
+    float cth = a.ctx_hat[bi + j];
+    fc_split(h[j], cth, wr[j], coef, rh, rcth);
+    float dct = stab(cth);
+    float cx = a.ctx[bi + j];
+    float r_ctx = (1.f - beta) * cx * rcth / dct;
+    size_t o = (size_t)q * a.H + j;
+    w.r_h[o] = rh;
+    w.r_c[o] = beta * a.st[bi + j] * rcth / dct;          // r_ct[t+1] = r_st (:724)
+    w.uctx[o] = r_ctx / stab(cx);
+  }
+  for (int j = threadIdx.x; j < a.E; j += blockDim.x) w.r_glob[(size_t)q * a.E + j] = 0.f;
+  for (int j = threadIdx.x; j < a.T; j += blockDim.x) {
+    a.r_words[(size_t)q * a.T + j] = 0.f;
+    if (a.r_words_raw) a.r_words_raw[(size_t)q * a.T + j] = 0.f;
+  }
+}
+
+// cell rule (:726-734) -> u = r_g / stab(tanh g)   (the reference passes tanh(gt) as forward_output, :737)
+__global__ void ada_cell_kernel(lrpx_adaptive_args a, AdaWs w, int i) {
+  int q = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q];
+  bool active = i <= t;
+  size_t bi = ((size_t)b * a.T + i) * a.H, bi1 = ((size_t)b * (a.T + 1) + i + 1) * a.H,
+         bi0 = ((size_t)b * (a.T + 1) + i) * a.H;
+  for (int j = threadIdx.x; j < a.H; j += blockDim.x) {
+    size_t o = (size_t)q * a.H + j;
+    if (!active) { put_operand(w.u, w.a3u, q, a.H, j, 0.f); continue; }
+    float rc = w.r_c[o] + w.r_h[o];
+    float d = stab(a.c[bi1 + j]);
+    float tg = tanhf(a.g[bi + j]);
+    float r_g = a.i[bi + j] * tg * rc / d;
+    w.r_c[o] = a.f[bi + j] * a.c[bi0 + j] * rc / d;
+    put_operand(w.u, w.a3u, q, a.H, j, r_g / stab(tg));
+  }
+}
+
+// after v = u @ W_g : slices of xht = [emb | glob | h_i] (:739-742)
+__global__ void ada_post_kernel(lrpx_adaptive_args a, AdaWs w, int i) {
+  int q = blockIdx.x;
+  int b = a.req_img[q], t = a.req_t[q];
+  if (i > t) return;
+  const int H = a.H, E = a.E;
+  const float* x = a.x + ((size_t)b * a.T + i) * 2 * E;
+  const float* hp = a.h + ((size_t)b * (a.T + 1) + i) * H;
+  const float* vq = w.v + (size_t)q * (2 * E + H);
+  float wsum = 0.f;
+  for (int k = threadIdx.x; k < 2 * E + H; k += blockDim.x) {
+    if (k < E) wsum += x[k] * vq[k];
+    else if (k < 2 * E) { if (i == t) w.r_glob[(size_t)q * E + (k - E)] = x[k] * vq[k]; }   // only the explained step (:740)
+    else w.r_h[(size_t)q * H + (k - 2 * E)] = hp[k - 2 * E] * vq[k];
+  }
+  for (int o = 16; o; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  __shared__ float sm[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < (blockDim.x + 31) / 32; ++k) s += sm[k];
+    float* dst = a.r_words_raw ? a.r_words_raw : a.r_words;
+    dst[(size_t)q * a.T + i] = s;
+    if (a.r_words_raw) a.r_words[(size_t)q * a.T + i] = s;
+  }
+}
+
+// u_g = r_glob / stab(avg @ W_glob^T)   (:743-746, forward_output=False: no bias)
+__global__ void ada_glob_kernel(lrpx_adaptive_args a, AdaWs w) {
+  int q = blockIdx.x, b = a.req_img[q];
+  for (int j = threadIdx.x; j < a.E; j += blockDim.x)
+    w.u[(size_t)q * a.E + j] = w.r_glob[(size_t)q * a.E + j] / stab(a.z_glob[(size_t)b * a.E + j]);
+}
+// coefavg = avg * v / stab(avg) / P  (mean rule :752-755 applied to r_avg = avg * v)
+__global__ void ada_avg_kernel(lrpx_adaptive_args a, AdaWs w) {
+  int q = blockIdx.x, b = a.req_img[q];
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float av = a.avg[(size_t)b * a.C + c];
+    float r_avg = av * w.v[(size_t)q * a.C + c];
+    w.coefavg[(size_t)q * a.C + c] = r_avg / stab(av) / (float)a.P;
+  }
+}
+// attention weighted-sum rule at the explained step only (:756-759), already divided for the projector rule (:760-763):
+//   wproj[q][p][h] = A[p][h] * alpha_t[p] * uctx[h] / stab(z_proj[p][h]);  block = (request, pixel group of 8)
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) ada_attn_kernel(lrpx_adaptive_args a, AdaWs w) {
+  const int H = a.H, P = a.P;
+  const int ng = (P + 7) / 8;
+  const int q = blockIdx.x / ng;
+  const int b = a.req_img[q], t = a.req_t[q];
+  const int p0 = (blockIdx.x - q * ng) * 8, p1 = min(P, p0 + 8);
+  const float* al = a.alpha + ((size_t)b * a.T + t) * P;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const float uv = w.uctx[(size_t)q * H + h];
+    for (int p = p0; p < p1; ++p) {
+      const size_t o0 = ((size_t)b * P + p) * H + h;
+      const size_t row = (size_t)q * P + p;
+      const float num = __ldg(a.A + o0) * al[p] * uv, den = stab(__ldg(a.z_proj + o0));
+      if (SPLIT) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(__fdividef(num, den), hi, lo);       // bf16 hi + lo keeps 16 mantissa bits: above the 2-ulp division
+        __nv_bfloat16* o = w.a3 + row * 3 * H;
+        o[h] = hi; o[H + h] = hi; o[2 * H + h] = lo;
+      } else {
+        w.wproj[row * H + h] = num / den;
+      }
+    }
+  }
+}
+
+static size_t ada_carve(const lrpx_adaptive_args* a, float* base, AdaWs* w) {
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    float* p = base ? base + off : nullptr;
+    off += align_up(n);
+    return p;
+  };
+  size_t Q = a->Q, H = a->H, E = a->E;
+  size_t nmax = 2 * E + H > (size_t)a->C ? 2 * E + H : (size_t)a->C;
+  AdaWs t;
+  t.r_h = take(Q * H); t.r_c = take(Q * H);
+  t.r_glob = take(Q * E);
+  t.u = take(Q * (H > E ? H : E));
+  t.v = take(Q * nmax);
+  t.uctx = take(Q * H);
+  t.coefavg = take(Q * a->C);
+  t.wproj = take(Q * a->P * H);
+  t.a3 = t.w3_g = t.w3_glob = t.w3_proj = t.a3u = nullptr;
+  if (a->flags & LRPX_DEC_TC_GEMM) {
+    auto take16 = [&](size_t n) { return reinterpret_cast<__nv_bfloat16*>(take((n + 1) / 2)); };   // n bf16 elements
+    size_t rows_max = Q * a->P;
+    t.a3 = take16(rows_max * 3 * H > Q * 3 * E ? rows_max * 3 * H : Q * 3 * E);
+    t.w3_g = take16((size_t)(2 * E + H) * 3 * H);
+    t.w3_glob = take16((size_t)a->C * 3 * E);
+    t.w3_proj = take16((size_t)a->C * 3 * H);
+    t.a3u = take16(Q * 3 * H);
+  }
+  if (w) *w = t;
+  return off * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
 // lrp_tune weights: one block per sample
 // ------------------------------------------------------------------------------------------------
 __global__ void fc_lrp_weights_kernel(const float* __restrict__ logits, const float* __restrict__ h,
@@ -777,6 +937,51 @@ int lrpx_aoa_decoder_lrp_f32(const lrpx_aoa_args* a, void* workspace, size_t wor
   RUN(gemm_any<GE_AOA_PROJ>(w.wval, a->W_v, w3_v, w.a3, w.w2, Q * a->P, H, H, pe, st));
   GemmEpi fe{a->feat, nullptr, nullptr, a->req_img, a->P};
   RUN(gemm_any<GE_FEAT>(w.w2, a->W_proj, w3_proj, w.a3, a->r_feat, Q * a->P, a->C, H, fe, st));
+  words_norm_kernel<<<Q, 32, 0, st>>>(a->r_words, a->req_t, T);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+size_t lrpx_adaptive_decoder_workspace_bytes(const lrpx_adaptive_args* a) {
+  if (!a) return 0;
+  return ada_carve(a, nullptr, nullptr);
+}
+
+int lrpx_adaptive_decoder_lrp_f32(const lrpx_adaptive_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  LRPX_CHECK_ARG(a, "null args");
+  LRPX_CHECK_ARG(a->B > 0 && a->T > 0 && a->H > 0 && a->E > 0 && a->P > 0 && a->C > 0 && a->V > 0 && a->Q >= 0,
+                 "bad dimensions");
+  if (a->Q == 0) return LRPX_OK;
+  LRPX_CHECK_ARG(a->feat && a->avg && a->z_proj && a->A && a->z_glob && a->x && a->h && a->c && a->g && a->i && a->f &&
+                     a->st && a->ctx && a->ctx_hat && a->alpha && a->beta && a->pred && a->W_g && a->W_fc && a->W_glob &&
+                     a->W_proj && a->req_img && a->req_t && a->req_word && a->r_feat && a->r_words,
+                 "null pointer in args");
+  AdaWs w;
+  size_t need = ada_carve(a, (float*)workspace, &w);
+  LRPX_CHECK_ARG(workspace && workspace_bytes >= need, "workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int Q = a->Q, H = a->H, E = a->E, T = a->T;
+  int nt = H >= 256 ? 256 : 128;
+  GemmEpi none{};
+  const bool tc = (a->flags & LRPX_DEC_TC_GEMM) != 0;
+  const __nv_bfloat16* w3_g = (tc && tc_shape_ok(2 * E + H, H)) ? prep_weight3(a->W_g, w.w3_g, H, 2 * E + H, st) : nullptr;
+  const __nv_bfloat16* w3_glob = (tc && tc_shape_ok(a->C, E)) ? prep_weight3(a->W_glob, w.w3_glob, E, a->C, st) : nullptr;
+  const __nv_bfloat16* w3_proj = (tc && tc_shape_ok(a->C, H)) ? prep_weight3(a->W_proj, w.w3_proj, H, a->C, st) : nullptr;
+  if (!w3_g) w.a3u = nullptr;
+  ada_init_kernel<<<Q, nt, 0, st>>>(*a, w);
+  for (int i = T - 1; i >= 0; --i) {
+    ada_cell_kernel<<<Q, nt, 0, st>>>(*a, w, i);
+    RUN(gemm_any<GE_STORE>(w.u, a->W_g, w3_g, w.a3u, w.v, Q, 2 * E + H, H, none, st, w3_g != nullptr));
+    ada_post_kernel<<<Q, 256, 0, st>>>(*a, w, i);
+  }
+  ada_glob_kernel<<<Q, 128, 0, st>>>(*a, w);
+  RUN(gemm_any<GE_STORE>(w.u, a->W_glob, w3_glob, w.a3, w.v, Q, a->C, E, none, st));
+  ada_avg_kernel<<<Q, 128, 0, st>>>(*a, w);
+  GemmEpi fe{a->feat, nullptr, w.coefavg, a->req_img, a->P};
+  const unsigned ag = (unsigned)((a->P + 7) / 8) * (unsigned)Q;
+  if (w3_proj) ada_attn_kernel<true><<<ag, nt, 0, st>>>(*a, w);
+  else ada_attn_kernel<false><<<ag, nt, 0, st>>>(*a, w);
+  RUN(gemm_any<GE_FEAT>(w.wproj, a->W_proj, w3_proj, w.a3, a->r_feat, Q * a->P, a->C, H, fe, st, w3_proj != nullptr));
   words_norm_kernel<<<Q, 32, 0, st>>>(a->r_words, a->req_t, T);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;

@@ -41,6 +41,16 @@ class AoaArgs(C.Structure):
                [(n, _P) for n in _AOA_PTRS]
 
 
+_ADA_PTRS = ["feat", "avg", "z_proj", "A", "z_glob", "x", "h", "c", "g", "i", "f", "st", "ctx", "ctx_hat", "alpha", "beta",
+             "pred", "W_g", "W_fc", "W_glob", "W_proj", "req_img", "req_t", "req_word", "r_feat", "r_words",
+             "r_words_raw"]
+
+
+class AdaptiveArgs(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("B", "T", "H", "E", "P", "C", "V", "Q", "flags", "reserved_")] + \
+               [(n, _P) for n in _ADA_PTRS]
+
+
 class TcConvArgs(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n_img", "h", "w", "cin", "ncol", "ksize", "epilogue", "gain_mode")] + \
                [(n, _P) for n in ("a", "wt", "bias", "gain", "row_img", "pool_idx", "x", "out", "out2", "x1")]
@@ -93,6 +103,8 @@ SYMBOLS = {
     "lrpx_gridtd_decoder_lrp_f32": (_i, [C.POINTER(GridTDArgs), _P, _sz, _P]),
     "lrpx_aoa_decoder_workspace_bytes": (_sz, [C.POINTER(AoaArgs)]),
     "lrpx_aoa_decoder_lrp_f32": (_i, [C.POINTER(AoaArgs), _P, _sz, _P]),
+    "lrpx_adaptive_decoder_workspace_bytes": (_sz, [C.POINTER(AdaptiveArgs)]),
+    "lrpx_adaptive_decoder_lrp_f32": (_i, [C.POINTER(AdaptiveArgs), _P, _sz, _P]),
     "lrpx_fc_lrp_weights_f32": (_i, [_P, _P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
     "lrpx_lstm_cell_f32": (_i, [C.POINTER(LstmCellArgs), _P]),
     "lrpx_adaptive_attention_f32": (_i, [C.POINTER(AdaAttentionArgs), _P]),

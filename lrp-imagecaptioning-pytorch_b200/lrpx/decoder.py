@@ -1,5 +1,5 @@
 """Packing helpers between the explainers' saved state (get_hidden_parameters, gridTDmodel.py:933-1012 /
-aoamodel.py:990-1062) and the batched decoder-relevance kernels (lrpx_gridtd_args / lrpx_aoa_args)."""
+aoamodel.py:990-1062 / adaptiveattention.py:626-677) and the batched decoder-relevance kernels (lrpx_gridtd_args / lrpx_aoa_args / lrpx_adaptive_args)."""
 from typing import Dict, List, Sequence
 
 import torch
@@ -11,6 +11,9 @@ GRIDTD_STEP1_KEYS = ["h1", "c1", "h2", "c2"]
 AOA_IMAGE_KEYS = ["feat", "A_pre", "A", "glob", "value"]
 AOA_STEP_KEYS = ["x", "g", "i", "ctx", "caoa", "caoa_lin", "alpha", "pred"]
 AOA_STEP1_KEYS = ["h", "c"]
+ADAPTIVE_IMAGE_KEYS = ["feat", "avg", "z_proj", "A", "z_glob"]
+ADAPTIVE_STEP_KEYS = ["x", "g", "i", "f", "st", "ctx", "ctx_hat", "alpha", "beta", "pred"]
+ADAPTIVE_STEP1_KEYS = ["h", "c"]
 
 
 def _gate_rows(w_ih, w_hh):
@@ -36,6 +39,17 @@ def aoa_weights(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         "W_fc": sd["fc.weight"].contiguous(),
         "W_aoa": sd["decoder_aoa_linear.weight"].contiguous(),
         "W_v": sd["decoder_v_proj.weight"].contiguous(),
+        "W_proj": sd["img_projector.weight"].reshape(H, -1).contiguous(),
+    }
+
+
+def adaptive_weights(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """adaptiveattention.py:685-687 (gate-g rows of the AdaLSTM), :523, :746, :763."""
+    H = sd["fc.weight"].shape[1]
+    return {
+        "W_g": _gate_rows(sd["AdaLSTM.lstm_cell.weight_ih"], sd["AdaLSTM.lstm_cell.weight_hh"]),
+        "W_fc": sd["fc.weight"].contiguous(),
+        "W_glob": sd["global_img_feature_proj.weight"].contiguous(),
         "W_proj": sd["img_projector.weight"].reshape(H, -1).contiguous(),
     }
 

@@ -290,6 +290,34 @@ def aoa_decoder_lrp(state: dict, weights: dict, num_head, req_img, req_t, req_wo
     return (r_feat, r_words, r_raw) if want_raw else (r_feat, r_words)
 
 
+def adaptive_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, want_raw=False, tc_gemm=False):
+    """ExplainAdaptiveAttention.explain_caption_wordt (adaptiveattention.py:679-771) batched over requests.
+    state: tensors of lrpx_adaptive_args (stacked over B images), weights: W_g, W_fc, W_glob, W_proj.
+    Returns r_feat (Q,P,C), r_words (Q,T)[, r_words_raw]."""
+    dev = state["feat"].device
+    B, P, Cc = state["feat"].shape
+    T, H = state["g"].shape[1], state["g"].shape[2]
+    E = state["z_glob"].shape[1]
+    V = state["pred"].shape[2]
+    Q = int(req_img.numel())
+    keep = []
+    a = _lib.AdaptiveArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q, flags=DEC_TC_GEMM if tc_gemm else 0)
+    f = {k: _f32(state[k], k) for k in ["feat", "avg", "z_proj", "A", "z_glob", "x", "h", "c", "g", "i", "f", "st",
+                                        "ctx", "ctx_hat", "alpha", "beta", "pred"]}
+    f.update({k: _f32(weights[k], k) for k in ["W_g", "W_fc", "W_glob", "W_proj"]})
+    for k, v in (("req_img", req_img), ("req_t", req_t), ("req_word", req_word)):
+        f[k] = v.to(device=dev, dtype=torch.int32).contiguous()
+    r_feat = torch.empty(Q, P, Cc, device=dev, dtype=torch.float32)
+    r_words = torch.zeros(Q, T, device=dev, dtype=torch.float32)
+    r_raw = torch.zeros(Q, T, device=dev, dtype=torch.float32) if want_raw else None
+    f.update(r_feat=r_feat, r_words=r_words, r_words_raw=r_raw)
+    _fill_args(a, f, keep)
+    nbytes = lib().lrpx_adaptive_decoder_workspace_bytes(C.byref(a))
+    ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
+    check(lib().lrpx_adaptive_decoder_lrp_f32(C.byref(a), _ptr(ws), nbytes, _stream()), "lrpx_adaptive_decoder_lrp_f32")
+    return (r_feat, r_words, r_raw) if want_raw else (r_feat, r_words)
+
+
 # ------------------------------------------------------------------------------------------ explainer forward
 def _ld(t):
     """row stride (elements) of a 2-D view whose last dimension is contiguous"""

@@ -439,8 +439,9 @@ class ExplainGridTDAttention(object):
         self.mean = [0.485, 0.456, 0.406]
         self.std = [0.229, 0.224, 0.225]
         m = self.model
-        self.language_weight_i, self.language_weight_h = m.LanguageLSTM.weight_ih, m.LanguageLSTM.weight_hh
-        self.language_bias_i, self.language_bias_h = m.LanguageLSTM.bias_ih, m.LanguageLSTM.bias_hh
+        if hasattr(m, 'LanguageLSTM'):       # the single-LSTM adaptive attention model has none
+            self.language_weight_i, self.language_weight_h = m.LanguageLSTM.weight_ih, m.LanguageLSTM.weight_hh
+            self.language_bias_i, self.language_bias_h = m.LanguageLSTM.bias_ih, m.LanguageLSTM.bias_hh
         self.output_weight = m.fc.weight
         self.visualizatioin_save_path = os.path.join(args.save_path, args.dataset + 'explanation')
         os.makedirs(self.visualizatioin_save_path, exist_ok=True)

@@ -277,6 +277,24 @@ def golden_adaptive_decoder(ns):
                 rf, rw = ex.explain_caption_wordt(t)
             out[f"r_feat_{t}"] = rf
             out[f"r_words_{t}"] = rw
+        if tag == "adaptive_dec_small":
+            # the model's own beam_search / greedy_search (adaptiveattention.py:370-489) on three feature maps, with the
+            # <end> logit raised so that finished and unfinished beams both occur
+            del model.beam_search
+            end_bias = 0.4
+            with torch.no_grad():
+                model.fc.bias[V - 1] += end_bias
+            beams, greedy = [], []
+            for b in range(3):
+                model.img_encoder = _StubEncoder(_features(seed + 10 + b, 512, 14, 14))
+                for bs in (1, 3):
+                    with torch.no_grad(), quiet():
+                        _, sen_idx = model.beam_search(torch.zeros(1, 3, 224, 224), wm, beam_size=bs)
+                    beams.append(np.array(sen_idx + [-1] * (40 - len(sen_idx)), dtype=np.int64))
+                with torch.no_grad(), quiet():
+                    _, seqs = model.greedy_search(torch.zeros(1, 3, 224, 224), wm, max_cap_length=12)
+                greedy.append(np.array(seqs[0], dtype=np.int64))
+            out.update(end_bias=end_bias, beams=np.stack(beams), greedy=np.stack(greedy))
         save(tag, **out)
 
 

@@ -21,6 +21,13 @@ def aoa_kernel_state(oracle_states, device):
     return D.stack_states(conv, D.AOA_IMAGE_KEYS, D.AOA_STEP_KEYS, D.AOA_STEP1_KEYS, device)
 
 
+def adaptive_kernel_state(oracle_states, device):
+    """oracle.adaptive_explainer_forward dicts (one per image) -> stacked kernel state (lrpx_adaptive_args)."""
+    keys = D.ADAPTIVE_IMAGE_KEYS + D.ADAPTIVE_STEP_KEYS + D.ADAPTIVE_STEP1_KEYS
+    conv = [{k: st[_GRID_RENAME.get(k, k)] for k in keys} for st in oracle_states]
+    return D.stack_states(conv, D.ADAPTIVE_IMAGE_KEYS, D.ADAPTIVE_STEP_KEYS, D.ADAPTIVE_STEP1_KEYS, device)
+
+
 def to_dev(d, device):
     return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in d.items()}
 

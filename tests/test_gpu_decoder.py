@@ -106,3 +106,64 @@ def test_aoa_vs_reference_fixture(golden, name, tc_gemm):
               f"{float((r_feat[q].cpu() - ref).abs().max() / scale):.3e}")
         assert_close(r_feat[q] / scale, ref / scale, rtol=1e-3, atol=atol, what=f"{name} r_feat {t},{hd}")
         assert_close(r_words[q, :t + 1], g[f"r_words_{t}_{hd}"], rtol=1e-3, atol=atol, what=f"{name} r_words {t},{hd}")
+
+
+@pytest.mark.parametrize("tc_gemm", [False, True])
+@pytest.mark.parametrize("name", ["adaptive_dec_small", "adaptive_dec_512"])
+def test_adaptive_vs_reference_fixture(golden, name, tc_gemm):
+    """lrpx_adaptive_decoder_lrp_f32 vs ExplainAdaptiveAttention.explain_caption_wordt run by the
+    reference (adaptiveattention.py:679-771).  Same bars as the gridTD kernel."""
+    from lrpx import ops
+    g = golden(name)
+    V, H, E = int(g["V"]), int(g["H"]), int(g["E"])
+    p = synth.adaptive_decoder_state(int(g["seed"]), V, H, E)
+    toks = g["tokens"].tolist()
+    st = O.adaptive_explainer_forward(p, g["feats"][0], toks)
+    ks = helpers.adaptive_kernel_state([st], DEV)
+    W = helpers.to_dev(D.adaptive_weights(p), DEV)
+    ts = g["ts"].tolist()
+    req_img = torch.zeros(len(ts), dtype=torch.int32)
+    req_t = torch.tensor(ts, dtype=torch.int32)
+    req_word = torch.tensor([toks[t + 1] for t in ts], dtype=torch.int32)
+    r_feat, r_words, raw = ops.adaptive_decoder_lrp(ks, W, req_img, req_t, req_word, want_raw=True, tc_gemm=tc_gemm)
+    atol = 1e-4 if tc_gemm else 1e-5
+    for q, t in enumerate(ts):
+        ref = _ref_feat(g[f"r_feat_{t}"], 512)
+        scale = ref.abs().max()
+        print(f"{name} tc_gemm={tc_gemm} t={t}: max scale-relative error "
+              f"{float((r_feat[q].cpu() - ref).abs().max() / scale):.3e}")
+        assert_close(r_feat[q] / scale, ref / scale, rtol=1e-3, atol=atol, what=f"{name} r_feat t={t}")
+        assert_close(r_words[q, :t + 1], g[f"r_words_{t}"], rtol=1e-3, atol=atol, what=f"{name} r_words t={t}")
+        assert float(r_words[q, t + 1:].abs().sum()) == 0.0
+        print(f"{name} t={t}: sum r_feat={float(r_feat[q].sum()):.6g} sum r_words_raw={float(raw[q].sum()):.6g} "
+              f"logit={float(st['pred'][t][toks[t + 1]]):.6g}")
+
+
+def test_adaptive_batched_requests_vs_oracle():
+    """Several images with ragged caption lengths, requests in arbitrary order (duplicates, t=0), empty batch."""
+    from lrpx import ops
+    V, H, E = 120, 64, 64
+    p = synth.adaptive_decoder_state(8, V, H, E, C=96, n_pixel=16)
+    states, toks = [], []
+    for b, T in enumerate([5, 3, 1]):
+        f = torch.randn(96, 4, 4, generator=torch.Generator().manual_seed(300 + b)).clamp(min=0)
+        tk = synth.tokens(400 + b, T, V)
+        toks.append(tk)
+        states.append(O.adaptive_explainer_forward(p, f, tk))
+    ks = helpers.adaptive_kernel_state(states, DEV)
+    W = helpers.to_dev(D.adaptive_weights(p), DEV)
+    reqs = [(0, 4), (1, 0), (2, 0), (0, 0), (1, 2), (0, 4), (0, 2)]
+    req_img = torch.tensor([r[0] for r in reqs], dtype=torch.int32)
+    req_t = torch.tensor([r[1] for r in reqs], dtype=torch.int32)
+    req_word = torch.tensor([toks[b][t + 1] for b, t in reqs], dtype=torch.int32)
+    r_feat, r_words = ops.adaptive_decoder_lrp(ks, W, req_img, req_t, req_word)
+    pd = {k: v.double() for k, v in p.items()}
+    for q, (b, t) in enumerate(reqs):
+        rf, rw, _ = O.adaptive_explain_wordt(pd, {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v)
+                                                  for k, v in states[b].items()}, t)
+        scale = rf.abs().max()
+        assert_close(r_feat[q] / scale, rf / scale, rtol=1e-3, atol=2e-5, what=f"req {q} r_feat")
+        assert_close(r_words[q, :t + 1], rw, rtol=1e-3, atol=2e-5, what=f"req {q} r_words")
+    e = torch.zeros(0, dtype=torch.int32)
+    rf0, rw0 = ops.adaptive_decoder_lrp(ks, W, e, e, e)
+    assert rf0.shape[0] == 0 and rw0.shape[0] == 0

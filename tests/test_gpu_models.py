@@ -397,3 +397,83 @@ def test_batch_pipeline_aoa_equals_single_image_api(tmp_path):
             assert_close(hs[t][0], heat_e[b * T + t], rtol=1e-3, atol=1e-6 + 1e-3 * float(heat_e[b * T + t].abs().max()),
                          what=f"aoa image {b} word {t}")
             assert_close(ws[t], words_e[b * T + t, :t + 1], rtol=1e-3, atol=1e-4, what=f"aoa words {b},{t}")
+
+
+def test_adaptive_explainer_vs_reference_fixture(golden, tmp_path):
+    """ExplainAdaptiveAttention.get_hidden_parameters + explain_caption_wordt with the encoder stubbed by
+    the fixture's features — the saved state comes from the fused step kernels, the relevance from
+    lrpx_adaptive_decoder_lrp_f32; both against the reference's own outputs (adaptiveattention.py:626-771)."""
+    from models import adaptiveattention as AA
+    g = golden("adaptive_dec_512")
+    V, H, E = int(g["V"]), int(g["H"]), int(g["E"])
+    model = AA.AdaptiveAttentionCaptioningModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.adaptive_decoder_state(int(g["seed"]), V, H, E), strict=False)
+    model.to(DEV)
+    ex = AA.ExplainAdaptiveAttention(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="fp32")
+    toks = g["tokens"].tolist()
+    feat = g["feats"][0].flatten(1).t().unsqueeze(0).contiguous().to(DEV)
+    ex.preprocess_img = lambda p: torch.zeros(1, 3, 224, 224, device=DEV)
+    ex.encode_images = lambda img: (feat, (14, 14), None)
+    model.beam_search = lambda *a, **k: ([" ".join(f"w{t}" for t in toks[1:])], toks[1:])
+    ex.get_hidden_parameters("x")
+    assert ex.caption_length == int(g["T"])
+    assert_close(ex.predictions, g["predictions"], atol=5e-5, what="predictions")
+    assert_close(ex.alphas, g["alphas"], atol=1e-6, what="alphas")
+    assert_close(ex.betas, g["betas"].reshape(-1), atol=1e-6, what="betas")
+    assert_close(ex.ht, g["ht"], atol=2e-6, what="ht")
+    assert_close(ex.ct, g["ct"], atol=2e-6, what="ct")
+    assert_close(ex.st, g["st"], atol=2e-6, what="st")
+    assert_close(ex.context_hat, g["context_hat"], atol=2e-6, what="context_hat")
+    for t in g["ts"].tolist():
+        rf, rw = ex.explain_caption_wordt(t)
+        ref = g[f"r_feat_{t}"]
+        assert rf.shape == ref.shape
+        scale = ref.abs().max()
+        assert_close(rf / scale, ref / scale, rtol=1e-3, atol=2e-5, what=f"r_img_feature t={t}")
+        assert_close(rw, g[f"r_words_{t}"], rtol=1e-3, atol=2e-5, what=f"r_words t={t}")
+
+
+def test_adaptive_explain_caption_end_to_end(tmp_path):
+    """Drop-in call on a 224x224 image through the VGG16 encoder: beam search of the mirror model, explainer forward,
+    decoder relevance, encoder relevance.  fp32 rule path: heat-maps and linguistic relevance against the CPU oracle at
+    the fp32 bar; bf16 tensor-core chain against the fp32 path: Spearman >= 0.99, relative L2 <= 1e-1 per word."""
+    from models import adaptiveattention as AA
+    V, H, E = 60, 64, 64
+    model = AA.AdaptiveAttentionCaptioningModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.adaptive_decoder_state(91, V, H, E), strict=False)
+    vsd = synth.vgg_state(92)
+    model.img_encoder.encoder.load_state_dict(vsd)
+    model.to(DEV).eval()
+    img = synth.images(93, 1)
+    wm = synth.word_map(V)
+    # the mirror's own searches on the device
+    _, sen_idx = model.beam_search(img.to(DEV), wm, beam_size=3, max_cap_length=20)
+    assert 1 <= len(sen_idx) <= 20
+    sents, seqs = model.greedy_search(img.to(DEV), wm, max_cap_length=5)
+    assert len(sents) == 1 and seqs[0][0] == wm['<start>']
+    toks = [wm['<start>']] + sen_idx[:4]
+    T = len(toks) - 1
+    model.beam_search = lambda *a, **k: ([" ".join(f"w{t}" for t in toks[1:])], toks[1:])
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        ex = AA.ExplainAdaptiveAttention(_args(E, H, tmp_path), wm, model=model, precision=prec)
+        ex.ACCUMULATE_LIKE_REFERENCE = False
+        ex.preprocess_img = lambda p: img.to(DEV)
+        outs[prec] = ex.explain_caption("synthetic.jpg")
+    heat32, words32 = outs["fp32"]
+    heat16, words16 = outs["bf16"]
+    assert len(heat32) == T and heat32[0].shape == (1, 3, 224, 224)
+    layers = O.vgg_layers_from_state(vsd)
+    feats = O.sequential_forward(layers, img)[-1]
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    st = O.adaptive_explainer_forward(sd, feats[0], toks)
+    for t in range(T):
+        rf, rw, _ = O.adaptive_explain_wordt(sd, st, t)
+        ref = O.sequential_lrp(layers, img, rf.t().reshape(1, 512, 14, 14))
+        scale = ref.abs().max()
+        assert_close(heat32[t] / scale, ref / scale, rtol=2e-3, atol=2e-4, what=f"fp32 heat-map t={t}")
+        assert_close(words32[t], rw, rtol=1e-3, atol=1e-4, what=f"r_words t={t}")
+        sp = spearman(heat16[t], heat32[t])
+        l2 = float((heat16[t] - heat32[t]).norm() / heat32[t].norm())
+        print(f"adaptive word {t}: bf16 vs fp32 spearman {sp:.5f} rel L2 {l2:.3e}")
+        assert sp >= 0.99 and l2 <= 1e-1

@@ -141,3 +141,53 @@ def test_bu_beam_search_indices_bit_exact_vs_reference(golden):
                 want = [int(v) for v in ref[row] if int(v) >= 0]
                 assert sen_idx == want, (tag, b, bs, sen_idx, want)
                 row += 1
+
+
+def test_adaptive_model_state_dict_and_search_bit_exact_vs_reference(golden):
+    """the AdaptiveAttentionCaptioningModel mirror loads the reference's state_dict layout key for key,
+    and its beam_search (beam sizes 1 and 3) / greedy_search reproduce the reference's word indices bit for bit
+    (adaptiveattention.py:370-489; finished and unfinished beams both occur in the fixture)."""
+    from models import adaptiveattention as AA
+    g = golden("adaptive_dec_small")
+    V, H, E, seed = int(g["V"]), int(g["H"]), int(g["E"]), int(g["seed"])
+    m = AA.AdaptiveAttentionCaptioningModel(E, H, V, "vgg16")
+    sd = synth.adaptive_decoder_state(seed, V, H, E)
+    assert set(k for k in m.state_dict() if not k.startswith("img_encoder.")) == set(sd.keys())
+    sd["fc.bias"][V - 1] += float(g["end_bias"])
+    m.load_state_dict(sd, strict=False)
+    m.eval()
+    wm = synth.word_map(V)
+
+    class Stub(torch.nn.Module):
+        def __init__(self, f):
+            super().__init__()
+            self.f = f
+
+        def forward(self, img):
+            return self.f, self.f.mean((2, 3)).squeeze()
+
+    row = 0
+    for b in range(3):
+        gen = torch.Generator().manual_seed(seed + 10 + b)
+        m.img_encoder = Stub(torch.randn(1, 512, 14, 14, generator=gen).clamp(min=0))
+        for bs in (1, 3):
+            _, sen_idx = m.beam_search(torch.zeros(1, 3, 224, 224), wm, beam_size=bs)
+            want = [int(v) for v in g["beams"][row] if int(v) >= 0]
+            assert sen_idx == want, (b, bs, sen_idx, want)
+            row += 1
+        _, seqs = m.greedy_search(torch.zeros(1, 3, 224, 224), wm, max_cap_length=12)
+        assert seqs[0] == g["greedy"][b].tolist(), (b, seqs[0], g["greedy"][b].tolist())
+
+
+def test_adaptive_explainer_refuses_cpu(tmp_path):
+    from models import adaptiveattention as AA
+    from lrpx._lib import LrpxError
+    V, H = 50, 32
+    m = AA.AdaptiveAttentionCaptioningModel(H, H, V, "vgg16")
+    args = argparse.Namespace(embed_dim=H, hidden_dim=H, encoder="vgg16", height=224, width=224,
+                              save_path=str(tmp_path), dataset="syn", weight="")
+    ex = AA.ExplainAdaptiveAttention(args, synth.word_map(V), model=m)
+    with pytest.raises(LrpxError):
+        ex.explainer_forward(torch.zeros(1, 196, 512), torch.zeros(1, 4, dtype=torch.long))
+    with pytest.raises(ValueError):
+        AA.ExplainAdaptiveAttention(args, synth.word_map(V), model=AA.AdaptiveAttentionCaptioningModel(16, H, V, "vgg16"))
