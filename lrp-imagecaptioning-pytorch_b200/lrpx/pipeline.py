@@ -17,8 +17,8 @@ from . import ops
 
 class BatchExplainer:
     def __init__(self, explainer, chunk=128, use_graph=False, tc_gemm=True, head_idx=0):
-        """explainer: models.gridTDmodel.ExplainGridTDAttention or models.aoamodel.ExplainAOAAttention with
-        precision='bf16' (VGG encoder); ``head_idx``: the attention head an AoA explanation follows
+        """explainer: models.gridTDmodel.ExplainGridTDAttention, models.aoamodel.ExplainAOAAttention or
+        models.adaptiveattention.ExplainAdaptiveAttention with precision='bf16' (VGG encoder); ``head_idx``: the attention head an AoA explanation follows
         (aoamodel.py:1165, ``explain_caption(img, head_idx)``)."""
         if explainer.precision != "bf16":
             raise ValueError("BatchExplainer drives the tensor-core chain: build the explainer with precision='bf16'")
@@ -29,6 +29,7 @@ class BatchExplainer:
         self.use_graph = use_graph
         self.tc_gemm = tc_gemm            # decoder GEMMs as bf16x3 on tensor cores (fp32 CUDA cores when False)
         self.is_aoa = hasattr(explainer, "num_head") and hasattr(explainer.model, "decoder_multihead_attention")
+        self.is_adaptive = not self.is_aoa and not hasattr(explainer.model, "LanguageLSTM")   # single-LSTM decoder
         self.head_idx = int(head_idx)
         self._graphs = {}
         self._copy_stream = None
@@ -55,6 +56,8 @@ class BatchExplainer:
         if self.is_aoa:
             r_feat, r_words = ops.aoa_decoder_lrp(st, self.W, self.ex.num_head, req_img, req_t, req_word,
                                                   torch.full_like(req_t, self.head_idx), tc_gemm=self.tc_gemm)
+        elif self.is_adaptive:
+            r_feat, r_words = ops.adaptive_decoder_lrp(st, self.W, req_img, req_t, req_word, tc_gemm=self.tc_gemm)
         else:
             r_feat, r_words = ops.gridtd_decoder_lrp(st, self.W, req_img, req_t, req_word, tc_gemm=self.tc_gemm)
         if host is None:

@@ -477,3 +477,31 @@ def test_adaptive_explain_caption_end_to_end(tmp_path):
         l2 = float((heat16[t] - heat32[t]).norm() / heat32[t].norm())
         print(f"adaptive word {t}: bf16 vs fp32 spearman {sp:.5f} rel L2 {l2:.3e}")
         assert sp >= 0.99 and l2 <= 1e-1
+
+
+def test_batch_pipeline_adaptive_equals_single_image_api(tmp_path):
+    """BatchExplainer with an ExplainAdaptiveAttention: B images x T words in one pass == explain_caption per image;
+    graph replay == eager."""
+    from models import adaptiveattention as AA
+    from lrpx.pipeline import BatchExplainer
+    V, H, E, B, T = 60, 64, 64, 2, 3
+    model = AA.AdaptiveAttentionCaptioningModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.adaptive_decoder_state(291, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(292))
+    model.to(DEV).eval()
+    ex = AA.ExplainAdaptiveAttention(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="bf16")
+    ex.ACCUMULATE_LIKE_REFERENCE = False
+    imgs = synth.images(295, B).to(DEV)
+    toks = torch.stack([torch.tensor(synth.tokens(296 + b, T, V)) for b in range(B)]).to(DEV)
+    heat_e, words_e = BatchExplainer(ex, chunk=4, use_graph=False).explain(imgs, toks)
+    heat_g, words_g = BatchExplainer(ex, chunk=4, use_graph=True).explain(imgs, toks)
+    assert torch.equal(heat_e, heat_g) and torch.equal(words_e, words_g)
+    for b in range(B):
+        ex.preprocess_img = lambda p, b=b: imgs[b:b + 1]
+        tk = toks[b].tolist()
+        model.beam_search = lambda *a, tk=tk, **k: (["a b c"], tk[1:])
+        hs, ws = ex.explain_caption("synthetic.jpg")
+        for t in range(T):
+            assert_close(hs[t][0], heat_e[b * T + t], rtol=1e-3, atol=1e-6 + 1e-3 * float(heat_e[b * T + t].abs().max()),
+                         what=f"adaptive image {b} word {t}")
+            assert_close(ws[t], words_e[b * T + t, :t + 1], rtol=1e-3, atol=1e-4, what=f"adaptive words {b},{t}")
