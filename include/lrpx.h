@@ -255,6 +255,50 @@ int lrpx_fc_lrp_weights_f32(const float* logits, const float* h, const float* ct
                             int B, int V, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Beam search bookkeeping on the device: one step of GridTDModel.beam_search
+ * (models/gridTDmodel.py:400-478; same loop in aoamodel.py:405-485 and adaptiveattention.py:370-447) for B images
+ * with k beam slots each.  Slots [0, n_alive[b]) of image b are its unfinished beams in the reference's order.
+ * A step takes the logits of the B*k rows and
+ *   - adds log_softmax(logits[r]) to the running score of every alive row (row 0 only at step 0, :436-439),
+ *   - selects the n_alive best (row, word) pairs in descending order, ties to the lower flat index (:440),
+ *   - moves pairs ending in end_id to the completed list (sequence incl. <end>, score; :449-452),
+ *   - compacts the others into the new alive slots: seqs, scores, prev_words, and src_row[b*k+j] = the global row
+ *     whose recurrent state slot j continues (:455-462) — dead slots point at themselves.
+ * No host synchronisation; the caller reads seqs / comp_* once after the last step (:463-468).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, k, V, L;          /* k <= 8 slots per image, L = max_cap_length steps (L + 1 <= 64 tokens per sequence) */
+  int step, end_id;        /* 0 <= step < L */
+  const float* logits;     /* (B*k, V) */
+  float* scores;           /* (B,k)     running log-probabilities, zero before step 0 */
+  int32_t* n_alive;        /* (B)       k before step 0 */
+  int32_t* seqs;           /* (B,k,L+1) alive sequences, column 0 = <start> */
+  int32_t* comp_seqs;      /* (B,k,L+1) completed sequences in completion order */
+  int32_t* comp_len;       /* (B,k)     their token counts */
+  float* comp_scores;      /* (B,k) */
+  int32_t* n_comp;         /* (B)       0 before step 0 */
+  int64_t* prev_words;     /* (B*k)     input words of the next step (int64: an embedding index) */
+  int32_t* src_row;        /* (B*k) */
+} lrpx_beam_args;
+
+int lrpx_beam_step(const lrpx_beam_args* args, void* stream);
+
+/* dst[e][row][0:width[e]] = src[e][src_row[row]][0:width[e]] for every pair e (state[beam_idx], gridTDmodel.py:459);
+ * dst and src of a pair must be different buffers. */
+#define LRPX_BEAM_GATHER_MAX 8
+typedef struct {
+  int n_rows, n_pairs;
+  const int32_t* src_row;
+  float* dst[LRPX_BEAM_GATHER_MAX];
+  const float* src[LRPX_BEAM_GATHER_MAX];
+  long long ld_dst[LRPX_BEAM_GATHER_MAX];
+  long long ld_src[LRPX_BEAM_GATHER_MAX];
+  int width[LRPX_BEAM_GATHER_MAX];
+} lrpx_beam_gather_args;
+
+int lrpx_beam_gather_f32(const lrpx_beam_gather_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Explainer forward (the producer of the saved state above): fused element-wise steps of
  * ExplainGridTDAttention.get_hidden_parameters (gridTDmodel.py:933-1012).  Row strides ("ld_*", in
  * elements) let the kernels write straight into the (B, T, .) saved-state tensors and into the

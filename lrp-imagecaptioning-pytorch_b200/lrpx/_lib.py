@@ -81,6 +81,21 @@ class AdaAttentionArgs(C.Structure):
                 ("ctx_hat_copy", _P), ("ld_copy", _LL), ("h", _P), ("ld_h", _LL), ("W_g", _P), ("W_s", _P), ("b_s", _P)]
 
 
+class BeamArgs(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("B", "k", "V", "L", "step", "end_id")] + \
+               [(n, _P) for n in ("logits", "scores", "n_alive", "seqs", "comp_seqs", "comp_len", "comp_scores", "n_comp",
+                                  "prev_words", "src_row")]
+
+
+BEAM_GATHER_MAX = 8
+
+
+class BeamGatherArgs(C.Structure):
+    _fields_ = [("n_rows", C.c_int), ("n_pairs", C.c_int), ("src_row", _P), ("dst", _P * BEAM_GATHER_MAX),
+                ("src", _P * BEAM_GATHER_MAX), ("ld_dst", _LL * BEAM_GATHER_MAX), ("ld_src", _LL * BEAM_GATHER_MAX),
+                ("width", C.c_int * BEAM_GATHER_MAX)]
+
+
 # every symbol include/lrpx.h declares: name -> (restype, argtypes)
 _i, _f, _sz = C.c_int, C.c_float, C.c_size_t
 SYMBOLS = {
@@ -106,6 +121,8 @@ SYMBOLS = {
     "lrpx_adaptive_decoder_workspace_bytes": (_sz, [C.POINTER(AdaptiveArgs)]),
     "lrpx_adaptive_decoder_lrp_f32": (_i, [C.POINTER(AdaptiveArgs), _P, _sz, _P]),
     "lrpx_fc_lrp_weights_f32": (_i, [_P, _P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
+    "lrpx_beam_step": (_i, [C.POINTER(BeamArgs), _P]),
+    "lrpx_beam_gather_f32": (_i, [C.POINTER(BeamGatherArgs), _P]),
     "lrpx_lstm_cell_f32": (_i, [C.POINTER(LstmCellArgs), _P]),
     "lrpx_adaptive_attention_f32": (_i, [C.POINTER(AdaAttentionArgs), _P]),
     "lrpx_lstm_prep_weights_f32": (_i, [_P, _P, _i, _i, _i, _P]),

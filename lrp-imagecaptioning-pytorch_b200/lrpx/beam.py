@@ -1,0 +1,148 @@
+"""Beam search of the gridTD decoder on the device.
+
+``GridTDModel.beam_search`` (reference models/gridTDmodel.py:400-478) runs ~25 tensor ops per step and reads the
+top-k result back to python lists every step.  Here a step is a fixed sequence of kernels with no host round trip:
+
+  embedding gather + input-side GEMM -> ``lrpx_lstm_step_f32`` (AdaLSTM + sentinel gate) -> attention projections
+  (library GEMM) -> ``lrpx_adaptive_attention_f32`` -> ``lrpx_lstm_step_f32`` (language LSTM) -> vocabulary GEMM ->
+  ``lrpx_beam_step`` (log-softmax, top-k over the alive beams, <end> handling, compaction) ->
+  ``lrpx_beam_gather_f32`` (recurrent state of the surviving beams)
+
+over B images x k beam slots, the whole ``max_cap_length``-step loop captured once into a CUDA graph.  The result is
+read back once.  Word indices equal the reference's (tests: the reference's own beam-search fixtures, bit for bit).
+"""
+import torch
+
+from . import ops
+
+
+class GridTDBeamSearch:
+    def __init__(self, model, use_graph=True):
+        """model: models.gridTDmodel.GridTDModel or GridTDModelBU on a CUDA device (eval mode: dropout is identity)."""
+        self.model = model
+        self.use_graph = use_graph
+        self._w_key = None
+        self._plans = {}
+
+    # ------------------------------------------------------------------ weights in the step kernels' layout
+    def _weights(self):
+        m = self.model
+        cell, L, xg, hg, att = m.AdaLSTM.lstm_cell, m.LanguageLSTM, m.AdaLSTM.x_gate, m.AdaLSTM.h_gate, m.AdaAttention
+        src = [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, xg.weight, xg.bias, hg.weight, hg.bias,
+               L.weight_ih, L.weight_hh, L.bias_ih, L.bias_hh, att.W_g_proj.weight, att.W_s_proj.weight,
+               att.W_s_proj.bias, att.w_h.weight]
+        key = tuple((t.data_ptr(), t._version) for t in src)
+        if self._w_key != key:
+            H, E, K = m.hidden_dim, m.embed_dim, att.num_pixel
+            dev = cell.weight_ih.device
+            with torch.no_grad():
+                # x1 = [h2 | glob | emb] (:431): recurrent rows [h2 | h1] -> (4H gates | sentinel gate)
+                W1_rec = torch.cat((torch.cat((cell.weight_ih[:, :H], cell.weight_hh), 1),
+                                    torch.cat((xg.weight[:, :H], hg.weight), 1)), 0).t().contiguous()      # (2H, 5H)
+                W1_in = torch.cat((cell.weight_ih[:, H:], xg.weight[:, H:]), 0).t().contiguous()           # (2E, 5H)
+                b1 = torch.cat((cell.bias_ih + cell.bias_hh, xg.bias + hg.bias)).contiguous()
+                W2 = torch.cat((L.weight_ih, L.weight_hh), 1).t().contiguous()                             # (3H, 4H)
+                Wa = torch.zeros(2 * H, 2 * K, device=dev)
+                Wa[:H, :K] = att.W_g_proj.weight.t()
+                Wa[H:, K:] = att.W_s_proj.weight.t()
+                self._w = dict(W1p=ops.lstm_prep_weights(W1_rec, 5), W1_glob=W1_in[:E].contiguous(),
+                               W1_emb=W1_in[E:].contiguous(), b1=b1, W2p=ops.lstm_prep_weights(W2, 4),
+                               b2=(L.bias_ih + L.bias_hh).contiguous(), Wa=Wa,
+                               ba=torch.cat((torch.zeros(K, device=dev), att.W_s_proj.bias)),
+                               w_h=att.w_h.weight.reshape(-1).contiguous())
+            self._w_key = key
+            self._plans = {}
+        return self._w
+
+    # ------------------------------------------------------------------ one plan per (B, k, L)
+    def _plan(self, B, k, L, P, start_id, end_id):
+        key = (B, k, L, P, start_id, end_id)
+        pl = self._plans.get(key)
+        if pl is not None:
+            return pl
+        m, w = self.model, self._weights()
+        H, E, V = m.hidden_dim, m.embed_dim, m.vocab_size
+        K = m.AdaAttention.num_pixel
+        dev = m.fc.weight.device
+        R = B * k
+        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        i32 = lambda *s: torch.zeros(*s, device=dev, dtype=torch.int32)
+        t = dict(A=f(R, P, H), img_proj=f(R, P, K), preg=f(R, 5 * H),                      # per-call inputs
+                 hcat=f(R, 2 * H), x2c=f(R, 3 * H), hs=f(R, 2 * H), c1=f(R, H), c2=f(R, H),
+                 h1n=f(R, H), c1n=f(R, H), h2n=f(R, H), c2n=f(R, H), g=f(R, H), i=f(R, H), f=f(R, H), st=f(R, H),
+                 ctx=f(R, H), ctx_hat=f(R, H), alpha=f(R, P), beta=f(R), emb=f(R, E), pre1=f(R, 5 * H), hsp=f(R, 2 * K),
+                 xo=f(R, H), logits=f(R, V), scores=f(B, k), comp_scores=f(B, k), n_alive=i32(B), n_comp=i32(B),
+                 seqs=i32(B, k, L + 1), comp_seqs=i32(B, k, L + 1), comp_len=i32(B, k), src_row=i32(R),
+                 prev=torch.zeros(R, device=dev, dtype=torch.int64))
+        fcW_t = m.fc.weight.t()
+
+        def run():
+            for name in ("hcat", "x2c", "c1", "c2", "scores", "comp_scores", "n_comp", "comp_len", "seqs", "comp_seqs"):
+                t[name].zero_()
+            t["n_alive"].fill_(k)
+            t["prev"].fill_(start_id)
+            t["seqs"][:, :, 0] = start_id
+            for step in range(L):
+                torch.index_select(m.embedding.weight, 0, t["prev"], out=t["emb"])
+                torch.addmm(t["preg"], t["emb"], w["W1_emb"], out=t["pre1"])
+                ops.lstm_step(t["hcat"], w["W1p"], t["pre1"], 5, t["c1"], t["h1n"], t["c1n"], t["g"], t["i"], t["f"],
+                              s=t["st"], h_copy1=t["x2c"][:, H:2 * H], h_copy2=t["hs"][:, :H], s_copy=t["hs"][:, H:])
+                torch.addmm(w["ba"], t["hs"], w["Wa"], out=t["hsp"])
+                ops.adaptive_attention(t["A"], t["img_proj"], t["hsp"], w["w_h"], t["st"], t["ctx"], t["ctx_hat"],
+                                       t["alpha"], t["beta"], ctx_hat_copy=t["x2c"][:, :H])
+                ops.lstm_step(t["x2c"], w["W2p"], w["b2"], 4, t["c2"], t["h2n"], t["c2n"], t["g"], t["i"], t["f"])
+                torch.add(t["ctx_hat"], t["h2n"], out=t["xo"])
+                torch.addmm(m.fc.bias, t["xo"], fcW_t, out=t["logits"])
+                ops.beam_step(t["logits"], t["scores"], t["n_alive"], t["seqs"], t["comp_seqs"], t["comp_len"],
+                              t["comp_scores"], t["n_comp"], t["prev"], t["src_row"], step, end_id)
+                ops.beam_gather(t["src_row"], [(t["hcat"][:, :H], t["h2n"]), (t["hcat"][:, H:], t["h1n"]),
+                                               (t["x2c"][:, 2 * H:], t["h2n"]), (t["c1"], t["c1n"]), (t["c2"], t["c2n"])])
+
+        graph = None
+        if self.use_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():     # warm-up outside capture (lazy library initialisation)
+                run()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph), torch.no_grad():
+                run()
+        pl = self._plans[key] = (t, run, graph)
+        return pl
+
+    # ------------------------------------------------------------------ search
+    def search(self, image_feature_proj, global_img_feature, word_map, beam_size=3, max_cap_length=20):
+        """image_feature_proj (B, hidden, P) and global_img_feature (B, embed) as ``GridTDModel._encode`` returns them.
+        -> list of B token lists ``sen_idx`` (special tokens removed, reference :466-468)."""
+        if not image_feature_proj.is_cuda:
+            raise ops._lib.LrpxError("GridTDBeamSearch needs CUDA tensors: lrpx has no CPU fallback")
+        m, w = self.model, self._weights()
+        B, H, P = image_feature_proj.shape
+        k, L = int(beam_size), int(max_cap_length)
+        start_id, end_id = word_map['<start>'], word_map['<end>']
+        t, run, graph = self._plan(B, k, L, P, start_id, end_id)
+        with torch.no_grad():
+            A = image_feature_proj.transpose(1, 2)                                     # (B,P,H)
+            t["A"].view(B, k, P, H).copy_(A.unsqueeze(1).expand(B, k, P, H))
+            t["img_proj"].view(B, k, P, -1).copy_(m.AdaAttention.W_v_proj(A).unsqueeze(1).expand(B, k, P, -1))
+            preg = torch.addmm(w["b1"], global_img_feature.float(), w["W1_glob"])      # (B,5H)
+            t["preg"].view(B, k, -1).copy_(preg.unsqueeze(1).expand(B, k, -1))
+            if graph is not None:
+                graph.replay()
+            else:
+                run()
+            n_comp, comp_len, comp_scores = t["n_comp"].tolist(), t["comp_len"].tolist(), t["comp_scores"].tolist()
+            comp_seqs, seqs = t["comp_seqs"].tolist(), t["seqs"][:, 0].tolist()
+        special = {word_map['<start>'], word_map['<end>'], word_map['<unk>'], word_map['<pad>']}
+        out = []
+        for b in range(B):
+            if n_comp[b] > 0:                                   # best completed sequence, first one on ties (:463-465)
+                sc = comp_scores[b][:n_comp[b]]
+                j = sc.index(max(sc))
+                seq = comp_seqs[b][j][:comp_len[b][j]]
+            else:
+                seq = seqs[b][:min(L + 1, 20)]                  # seqs[0][:20] (:467)
+            out.append([wd for wd in seq if wd not in special])
+        return out

@@ -414,3 +414,35 @@ def adaptive_attention(A, img_proj, hs_proj, w_h, s, ctx, ctx_hat, alpha, beta, 
     if ctx_hat_copy is not None:
         a.ctx_hat_copy, a.ld_copy = ctx_hat_copy.data_ptr(), _ld(ctx_hat_copy)
     check(lib().lrpx_adaptive_attention_f32(C.byref(a), _stream()), "lrpx_adaptive_attention_f32")
+
+
+# ------------------------------------------------------------------------------------------ device beam search
+def beam_step(logits, scores, n_alive, seqs, comp_seqs, comp_len, comp_scores, n_comp, prev_words, src_row, step, end_id):
+    """lrpx_beam_step: one step of the reference's beam search bookkeeping (gridTDmodel.py:436-462) for B images x k
+    slots, in place on the device state tensors (see include/lrpx.h)."""
+    B, k, W = seqs.shape
+    for t, dt in ((logits, torch.float32), (scores, torch.float32), (comp_scores, torch.float32), (n_alive, torch.int32),
+                  (seqs, torch.int32), (comp_seqs, torch.int32), (comp_len, torch.int32), (n_comp, torch.int32),
+                  (prev_words, torch.int64), (src_row, torch.int32)):
+        if not t.is_cuda or t.dtype != dt or not t.is_contiguous():
+            raise _lib.LrpxError("beam_step needs contiguous CUDA tensors of the documented dtypes: lrpx has no CPU fallback")
+    a = _lib.BeamArgs(B=B, k=k, V=logits.shape[1], L=W - 1, step=int(step), end_id=int(end_id))
+    for name, t in (("logits", logits), ("scores", scores), ("n_alive", n_alive), ("seqs", seqs), ("comp_seqs", comp_seqs),
+                    ("comp_len", comp_len), ("comp_scores", comp_scores), ("n_comp", n_comp), ("prev_words", prev_words),
+                    ("src_row", src_row)):
+        setattr(a, name, t.data_ptr())
+    check(lib().lrpx_beam_step(C.byref(a), _stream()), "lrpx_beam_step")
+
+
+def beam_gather(src_row, pairs):
+    """lrpx_beam_gather_f32: dst[row] = src[src_row[row]] for every (dst, src) pair of 2-D fp32 row views."""
+    if len(pairs) > _lib.BEAM_GATHER_MAX:
+        raise _lib.LrpxError("too many pairs")
+    g = _lib.BeamGatherArgs(n_rows=int(src_row.numel()), n_pairs=len(pairs))
+    g.src_row = src_row.data_ptr()
+    for e, (dst, src) in enumerate(pairs):
+        if not (dst.is_cuda and src.is_cuda and dst.dtype == src.dtype == torch.float32 and dst.shape[1] == src.shape[1]):
+            raise _lib.LrpxError("beam_gather needs fp32 CUDA row views of equal width")
+        g.dst[e], g.src[e] = dst.data_ptr(), src.data_ptr()
+        g.ld_dst[e], g.ld_src[e], g.width[e] = _ld(dst), _ld(src), dst.shape[1]
+    check(lib().lrpx_beam_gather_f32(C.byref(g), _stream()), "lrpx_beam_gather_f32")

@@ -264,6 +264,21 @@ class GridTDModel(nn.Module):
             sentence = self.remove_bad_endings([' '.join(rev_word_map[w] for w in sen_idx)])
             return sentence, sen_idx
 
+    def beam_search_device(self, imgs, word_map, beam_size=3, max_cap_length=20):
+        """``beam_search`` with the whole step loop on the device (lrpx.beam.GridTDBeamSearch: fused step kernels +
+        ``lrpx_beam_step`` bookkeeping, one CUDA graph, one read-back) and for B >= 1 images at once.  Same word
+        indices as ``beam_search``.  -> (sentence, sen_idx) for one image, a list of such pairs for a batch."""
+        from lrpx.beam import GridTDBeamSearch
+        self.eval()
+        if getattr(self, "_beam", None) is None:
+            self._beam = GridTDBeamSearch(self)
+        with torch.no_grad():
+            _, image_feature_proj, global_img_feature = self._encode(imgs)
+        rev_word_map = {v: k for k, v in word_map.items()}
+        out = [(self.remove_bad_endings([' '.join(rev_word_map[w] for w in idx)]), idx)
+               for idx in self._beam.search(image_feature_proj, global_img_feature, word_map, beam_size, max_cap_length)]
+        return out[0] if len(out) == 1 else out
+
     def sample_next_word(self, logprobs, sample_method, temperature):
         if sample_method == 'greedy':
             sampleLogprobs, it = torch.max(logprobs.data, 1)
@@ -590,7 +605,7 @@ class ExplainGridTDAttention(object):
                 # LanguageLSTM from [ctx_hat_t | h1_{t+1} | h2_t]                                             :984-990
                 ops.lstm_step(x2c[p], W2p, b2, 4, c2[:, t], h2[:, t + 1], c2[:, t + 1], g2[:, t], i2[:, t], f2[:, t],
                               h_copy0=hcat[q][:, :H], h_copy1=x2c[q][:, 2 * H:])
-            pred = torch.addmm(m.fc.bias, (ctx_hat + h2[:, 1:]).view(B * T, H), m.fc.weight.t()).view(B, T, -1)
+            pred = torch.addmm(m.fc.bias, (ctx_hat + h2[:, 1:]).view(B * T, H), m.fc.weight.t()).view(B, T, m.vocab_size)
             x1 = torch.cat((h2[:, :T], xin), -1)
             x2 = torch.cat((ctx_hat, h1[:, 1:]), -1)
             st_ = dict(x1=x1, x2=x2, g1=g1, i1=i1, f1=f1, g2=g2, i2=i2, f2=f2, st=st, ctx=ctx, ctx_hat=ctx_hat,
@@ -605,16 +620,38 @@ class ExplainGridTDAttention(object):
         return self.explainer_forward(feat, toks)["pred"][0]
 
     # ------------------------------------------------------------------ reference entry points
+    # with the tensor-core encoder the caption search runs on the device too and shares the encoder pass of the
+    # explanation (the reference's host loop encodes the image a second time); set False for the host loop
+    DEVICE_BEAM_SEARCH = True
+
     def get_hidden_parameters(self, img_filepath):
         self.img = self.preprocess_img(img_filepath)
-        self.beam_caption, self.beam_caption_encode = self.model.beam_search(self.img, self.word_map, beam_size=2,
-                                                                             max_cap_length=50)
+        m = self.model
+        enc = None
+        if (self.DEVICE_BEAM_SEARCH and self.precision == 'bf16' and self.has_encoder and self.img.is_cuda
+                and 'beam_search' not in m.__dict__ and isinstance(m, GridTDModel)):
+            from lrpx.beam import GridTDBeamSearch
+            if getattr(self, "_beam", None) is None:
+                self._beam = GridTDBeamSearch(m)
+            enc = self.encode_images(self.img)
+            feat = enc[0]                                                              # (1,P,C)
+            with torch.no_grad():
+                Wp = m.img_projector.weight.reshape(m.hidden_dim, -1)
+                proj = torch.addmm(m.img_projector.bias, feat[0], Wp.t()).clamp(min=0).t().unsqueeze(0)      # (1,H,P)
+                glob = m.global_img_feature_proj(feat.mean(1)).clamp(min=0)
+            idx = self._beam.search(proj, glob, self.word_map, beam_size=2, max_cap_length=50)[0]
+            rev = {v: k for k, v in self.word_map.items()}
+            self.beam_caption = m.remove_bad_endings([' '.join(rev[w] for w in idx)])
+            self.beam_caption_encode = idx
+        else:
+            self.beam_caption, self.beam_caption_encode = m.beam_search(self.img, self.word_map, beam_size=2,
+                                                                        max_cap_length=50)
         self.beam_caption_encode = [self.word_map['<start>']] + self.beam_caption_encode
         print(f'the predicted caption of {img_filepath} is "{self.beam_caption[0]}"')
-        self._set_state(self.img, self.beam_caption_encode)
+        self._set_state(self.img, self.beam_caption_encode, enc)
 
-    def _set_state(self, img, tokens):
-        feat, (fh, fw), est = self.encode_images(img)
+    def _set_state(self, img, tokens, enc=None):
+        feat, (fh, fw), est = enc if enc is not None else self.encode_images(img)
         toks = torch.tensor([tokens], dtype=torch.long, device=self.device)
         st = self.explainer_forward(feat, toks)
         self._state, self._enc_state, self._feat_hw = st, est, (fh, fw)
