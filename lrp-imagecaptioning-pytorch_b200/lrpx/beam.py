@@ -8,8 +8,9 @@ top-k result back to python lists every step.  Here a step is a fixed sequence o
   ``lrpx_beam_step`` (log-softmax, top-k over the alive beams, <end> handling, compaction) ->
   ``lrpx_beam_gather_f32`` (recurrent state of the surviving beams)
 
-over B images x k beam slots, the whole ``max_cap_length``-step loop captured once into a CUDA graph.  The result is
-read back once.  Word indices equal the reference's (tests: the reference's own beam-search fixtures, bit for bit).
+over B images x k beam slots, captured into CUDA graphs of ten steps each; between two graphs the host reads the alive
+counts once to stop early, and the result is read back once at the end.  Word indices equal the reference's (tests:
+the reference's own beam-search fixtures, bit for bit).
 """
 import torch
 
@@ -17,6 +18,8 @@ from . import ops
 
 
 class GridTDBeamSearch:
+    SEGMENT = 10          # steps per CUDA graph / between two looks at the alive counts
+
     def __init__(self, model, use_graph=True):
         """model: models.gridTDmodel.GridTDModel or GridTDModelBU on a CUDA device (eval mode: dropout is identity)."""
         self.model = model
@@ -76,13 +79,14 @@ class GridTDBeamSearch:
                  prev=torch.zeros(R, device=dev, dtype=torch.int64))
         fcW_t = m.fc.weight.t()
 
-        def run():
-            for name in ("hcat", "x2c", "c1", "c2", "scores", "comp_scores", "n_comp", "comp_len", "seqs", "comp_seqs"):
-                t[name].zero_()
-            t["n_alive"].fill_(k)
-            t["prev"].fill_(start_id)
-            t["seqs"][:, :, 0] = start_id
-            for step in range(L):
+        def run(s0, s1):
+            if s0 == 0:
+                for name in ("hcat", "x2c", "c1", "c2", "scores", "comp_scores", "n_comp", "comp_len", "seqs", "comp_seqs"):
+                    t[name].zero_()
+                t["n_alive"].fill_(k)
+                t["prev"].fill_(start_id)
+                t["seqs"][:, :, 0] = start_id
+            for step in range(s0, s1):
                 torch.index_select(m.embedding.weight, 0, t["prev"], out=t["emb"])
                 torch.addmm(t["preg"], t["emb"], w["W1_emb"], out=t["pre1"])
                 ops.lstm_step(t["hcat"], w["W1p"], t["pre1"], 5, t["c1"], t["h1n"], t["c1n"], t["g"], t["i"], t["f"],
@@ -98,18 +102,24 @@ class GridTDBeamSearch:
                 ops.beam_gather(t["src_row"], [(t["hcat"][:, :H], t["h2n"]), (t["hcat"][:, H:], t["h1n"]),
                                                (t["x2c"][:, 2 * H:], t["h2n"]), (t["c1"], t["c1n"]), (t["c2"], t["c2n"])])
 
-        graph = None
+        # the loop runs in segments of SEGMENT steps; between two segments the host looks at n_alive once and stops when
+        # every beam of every image has ended (the reference's `if unfinished_num == 0: break`, :453-454)
+        segs = [(s0, min(L, s0 + self.SEGMENT)) for s0 in range(0, L, self.SEGMENT)]
+        graphs = None
         if self.use_graph:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side), torch.no_grad():     # warm-up outside capture (lazy library initialisation)
-                run()
+                run(0, min(L, 2))
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph), torch.no_grad():
-                run()
-        pl = self._plans[key] = (t, run, graph)
+            graphs = []
+            for s0, s1 in segs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g), torch.no_grad():
+                    run(s0, s1)
+                graphs.append(g)
+        pl = self._plans[key] = (t, run, segs, graphs)
         return pl
 
     # ------------------------------------------------------------------ search
@@ -122,17 +132,20 @@ class GridTDBeamSearch:
         B, H, P = image_feature_proj.shape
         k, L = int(beam_size), int(max_cap_length)
         start_id, end_id = word_map['<start>'], word_map['<end>']
-        t, run, graph = self._plan(B, k, L, P, start_id, end_id)
+        t, run, segs, graphs = self._plan(B, k, L, P, start_id, end_id)
         with torch.no_grad():
             A = image_feature_proj.transpose(1, 2)                                     # (B,P,H)
             t["A"].view(B, k, P, H).copy_(A.unsqueeze(1).expand(B, k, P, H))
             t["img_proj"].view(B, k, P, -1).copy_(m.AdaAttention.W_v_proj(A).unsqueeze(1).expand(B, k, P, -1))
             preg = torch.addmm(w["b1"], global_img_feature.float(), w["W1_glob"])      # (B,5H)
             t["preg"].view(B, k, -1).copy_(preg.unsqueeze(1).expand(B, k, -1))
-            if graph is not None:
-                graph.replay()
-            else:
-                run()
+            for n, (s0, s1) in enumerate(segs):
+                if n and not bool(t["n_alive"].any()):           # one small read-back per segment
+                    break
+                if graphs is not None:
+                    graphs[n].replay()
+                else:
+                    run(s0, s1)
             n_comp, comp_len, comp_scores = t["n_comp"].tolist(), t["comp_len"].tolist(), t["comp_scores"].tolist()
             comp_seqs, seqs = t["comp_seqs"].tolist(), t["seqs"][:, 0].tolist()
         special = {word_map['<start>'], word_map['<end>'], word_map['<unk>'], word_map['<pad>']}

@@ -18,8 +18,8 @@ from . import ops
 class BatchExplainer:
     def __init__(self, explainer, chunk=128, use_graph=False, tc_gemm=True, head_idx=0):
         """explainer: models.gridTDmodel.ExplainGridTDAttention, models.aoamodel.ExplainAOAAttention or
-        models.adaptiveattention.ExplainAdaptiveAttention with precision='bf16' (VGG encoder); ``head_idx``: the attention head an AoA explanation follows
-        (aoamodel.py:1165, ``explain_caption(img, head_idx)``)."""
+        models.adaptiveattention.ExplainAdaptiveAttention with precision='bf16' (VGG encoder); ``head_idx``: the
+        attention head an AoA explanation follows (aoamodel.py:1165, ``explain_caption(img, head_idx)``)."""
         if explainer.precision != "bf16":
             raise ValueError("BatchExplainer drives the tensor-core chain: build the explainer with precision='bf16'")
         self.ex = explainer
