@@ -186,6 +186,20 @@ class AOAModel(nn.Module):
             sen_idx = [w for w in seq if w not in special]
             return self.remove_bad_endings([' '.join(rev_word_map[w] for w in sen_idx)]), sen_idx
 
+    def beam_search_device(self, imgs, word_map, beam_size=3, max_cap_length=20):
+        """``beam_search`` with the step loop on the device (lrpx.beam.AoaBeamSearch) for B >= 1 images at once; same
+        word indices.  -> (sentence, sen_idx) for one image, a list of such pairs for a batch."""
+        from lrpx.beam import AoaBeamSearch
+        self.eval()
+        if getattr(self, "_beam", None) is None:
+            self._beam = AoaBeamSearch(self)
+        with torch.no_grad():
+            _, proj, glob = self._encode(imgs)
+        rev_word_map = {v: k for k, v in word_map.items()}
+        out = [(self.remove_bad_endings([' '.join(rev_word_map[w] for w in idx)]), idx)
+               for idx in self._beam.search(proj, glob, word_map, beam_size, max_cap_length)]
+        return out[0] if len(out) == 1 else out
+
     # ------------------------------------------------------------------ lrp_tune
     def get_lrp_weight_step(self, predictions_t, rev_word_map, ht_, context_aoa):
         """reference :597-626 -> (weight_of_context_aoa, weight_of_ht); one batched kernel."""
@@ -281,6 +295,9 @@ class AOAModelBU(AOAModel):
 
     def beam_search(self, images_features, word_map, beam_size=3, max_cap_length=30):
         return AOAModel.beam_search(self, images_features, word_map, beam_size, max_cap_length)
+
+    def beam_search_device(self, images_features, word_map, beam_size=3, max_cap_length=30):
+        return AOAModel.beam_search_device(self, images_features, word_map, beam_size, max_cap_length)
 
 
 class ExplainAOAAttention(ExplainGridTDAttention):
@@ -420,7 +437,10 @@ class ExplainAOAAttention(ExplainGridTDAttention):
         ``explain_cnn``.  -> (list of (1, regions, 2048) relevances, list of (t+1,) word relevances), one per word."""
         feats = images_features.to(self.device).float()
         assert feats.dim() == 3 and feats.size(0) == 1
-        self.beam_caption, self.beam_caption_encode = self.model.beam_search(feats, self.word_map, beam_size=beam_size)
+        # the caption search runs on the device (same word indices) unless the model's beam_search was replaced
+        search = (self.model.beam_search_device if self.DEVICE_BEAM_SEARCH and 'beam_search' not in self.model.__dict__
+                  else self.model.beam_search)
+        self.beam_caption, self.beam_caption_encode = search(feats, self.word_map, beam_size=beam_size)
         self.beam_caption_encode = [self.word_map['<start>']] + self.beam_caption_encode
         toks = torch.tensor([self.beam_caption_encode], dtype=torch.long, device=self.device)
         st = self.explainer_forward(feats, toks)

@@ -308,6 +308,8 @@ def test_config3_aoa_bu_region_features_vs_oracle(tmp_path):
         r_feats, r_words = ex.explain_region_features(feats, head)
         toks = ex.beam_caption_encode
         assert len(toks) >= 3
+        # the caption came from the device search (lrpx.beam.AoaBeamSearch): same words as the host loop
+        assert ex.model.beam_search(feats.to(DEV), ex.word_map, beam_size=3)[1] == toks[1:]
         ost = O.aoa_explainer_forward(sd, feats[0].t().reshape(2048, 36, 1), toks, 8)
         for t in range(len(toks) - 1):
             rf, rw, _ = O.aoa_explain_wordt(sd, ost, t, head)
