@@ -270,7 +270,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": heat_h.numel() * 4 + words_h.numel() * 4},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "tc_conv_kernel<MUL|MUL_UNPOOL|INPUT> (encoder relevance chain)",
+            "roofline": {"bound": "tensor", "kernel": "tc_conv_slab_kernel<MUL|MUL_UNPOOL|INPUT3> (encoder relevance chain)",
                          "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tf_sustained"], "traffic": chain_traffic(args.chunk),
                          "traffic_note": "dram read+write bytes of the 13 chain layers per chunk of explanations (ncu --set "

@@ -983,7 +983,11 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float in3_scratch[2][2][64];      // EPI_INPUT3: [accumulator buffer][M half][quarter][2][8]
+  // EPI_INPUT3: [accumulator buffer][tile parity of the warp set][M half][quarter][2][8].  A warp writes its boundary
+  // rows BEFORE the named barrier of a tile and reads its neighbours' right after it; with two copies alternating per
+  // tile a slot is rewritten only after the barrier of the tile in between, which every reader of the old value has
+  // passed its reads to reach.
+  __shared__ float in3_scratch[2][2][2][64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1128,7 +1132,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const uint32_t stage = (EPI == LRPX_TC_EPI_MUL && p.store_off) ? smem_base + (uint32_t)p.store_off + (uint32_t)(warp - 2) * 1024u : 0u;
       run_epilogue_tile<EPI>(p, m_tile * tile_rows - p.fold + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh,
                              pf_row, smem_u32(&tmem_empty_bar[buf]), stage, &tmO,
-                             EPI == LRPX_TC_EPI_INPUT3 ? &in3_scratch[buf][0][0] : nullptr, quarter, it);
+                             EPI == LRPX_TC_EPI_INPUT3 ? &in3_scratch[buf][(it >> 1) & 1][0][0] : nullptr, quarter, it);
     }
     if (EPI == LRPX_TC_EPI_MUL && p.store_off) {      // the staging block must outlive the last tile store's read
       if (lane == 0) bulk_wait_read0();

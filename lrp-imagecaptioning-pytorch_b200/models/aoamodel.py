@@ -452,6 +452,30 @@ class ExplainAOAAttention(ExplainGridTDAttention):
         r_feat, r_words = self._decoder_lrp(ts, head_idx)
         return [r_feat[k:k + 1] for k in range(len(ts))], [r_words[k, :t + 1] for k, t in enumerate(ts)]
 
+    def explain_region_features_batch(self, images_features, head_idx, beam_size=3, tokens=None):
+        """BASELINE config 3 for B feature sets at once: one batched device beam search (``beam_search_device``), one
+        batched explainer forward over the padded captions, ONE decoder-relevance launch sequence over all (image, word)
+        requests.  ``tokens`` ((B, L) long, column 0 = <start>, 0-padded) skips the search.
+        -> (r_feat (Q, regions, 2048), r_words (Q, T), req_img (Q,), req_t (Q,), captions: list of B token lists)."""
+        feats = images_features.to(self.device).float().contiguous()
+        B = feats.shape[0]
+        if tokens is None:
+            found = self.model.beam_search_device(feats, self.word_map, beam_size=beam_size)
+            caps = [found[1]] if B == 1 else [c[1] for c in found]
+        else:
+            caps = [[int(w) for w in row[1:] if int(w) != 0] for row in tokens.tolist()]
+        T = max(1, max(len(c) for c in caps))
+        start = self.word_map['<start>']
+        toks = torch.tensor([[start] + c + [0] * (T - len(c)) for c in caps], dtype=torch.long, device=self.device)
+        st = self.explainer_forward(feats, toks)
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=self.device)
+        req_img = i32([b for b in range(B) for _ in caps[b]])
+        req_t = i32([t for b in range(B) for t in range(len(caps[b]))])
+        req_word = i32([w for c in caps for w in c])
+        r_feat, r_words = ops.aoa_decoder_lrp(st, self._lrp_weights(), self.num_head, req_img, req_t, req_word,
+                                              torch.full_like(req_t, int(head_idx)), tc_gemm=(self.precision == 'bf16'))
+        return r_feat, r_words, req_img, req_t, caps
+
     def explain_caption_words(self, img_filepath):
         """reference :1183-1194: linguistic relevance only (head 0)."""
         self.img_filepath = img_filepath

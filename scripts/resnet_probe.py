@@ -10,7 +10,7 @@ dev = "cuda"
 for name, net, cshape in (("resnet101", resnet.resnet101(), (2048, 7, 7)), ("vgg16 features[0:-1]", vgg.vgg16(pretrained=False).features[0:-1], (512, 14, 14))):
     net = net.to(dev).eval()
     lrp_wrapper.add_lrp(net)
-    for n in (1, 8):
+    for n in [int(v) for v in os.environ.get("BATCHES", "1,8").split(",")]:
         x = torch.randn(n, 3, 224, 224, device=dev); tgt = torch.randn(n, *cshape, device=dev)
         for _ in range(2): net.compute_lrp(x.clone(), target=tgt)
         torch.cuda.synchronize(); t0 = time.perf_counter()

@@ -507,3 +507,26 @@ def test_batch_pipeline_adaptive_equals_single_image_api(tmp_path):
             assert_close(hs[t][0], heat_e[b * T + t], rtol=1e-3, atol=1e-6 + 1e-3 * float(heat_e[b * T + t].abs().max()),
                          what=f"adaptive image {b} word {t}")
             assert_close(ws[t], words_e[b * T + t, :t + 1], rtol=1e-3, atol=1e-4, what=f"adaptive words {b},{t}")
+
+
+def test_config3_batched_region_features_equals_per_image_api(tmp_path):
+    """explain_region_features_batch (batched device beam search + one decoder-relevance pass over all requests of B
+    feature sets with ragged captions) == explain_region_features per image."""
+    V, H, E, B, head = 80, 64, 32, 3, 2
+    ex, sd = _aoa_bu_explainer(V, H, E, 103, tmp_path, end_bias=0.15)
+    feats = synth.bu_features(96, B)
+    r_feat, r_words, req_img, req_t, caps = ex.explain_region_features_batch(feats, head)
+    print("caption lengths", [len(c) for c in caps])
+    assert r_feat.shape[0] == sum(len(c) for c in caps) and max(len(c) for c in caps) >= 2
+    q = 0
+    for b in range(B):
+        if not caps[b]:                       # <end> as the first word: nothing to explain for this image
+            continue
+        rf, rw = ex.explain_region_features(feats[b:b + 1], head)
+        assert ex.beam_caption_encode[1:] == caps[b]
+        for t in range(len(caps[b])):
+            assert int(req_img[q]) == b and int(req_t[q]) == t
+            scale = float(rf[t].abs().max())
+            assert_close(r_feat[q] / scale, rf[t][0] / scale, rtol=1e-3, atol=1e-5, what=f"image {b} word {t} r_feat")
+            assert_close(r_words[q, :t + 1], rw[t], rtol=1e-3, atol=1e-5, what=f"image {b} word {t} r_words")
+            q += 1
