@@ -271,3 +271,67 @@ class AoaBeamSearch(_DeviceBeamSearch):
             raise ops._lib.LrpxError("AoaBeamSearch needs CUDA tensors: lrpx has no CPU fallback")
         B, P, H = image_feature_proj.shape
         return self._search(B, P, image_feature_proj, global_img_feature, word_map, beam_size, max_cap_length)
+
+
+class AdaptiveBeamSearch(_DeviceBeamSearch):
+    """model: models.adaptiveattention.AdaptiveAttentionCaptioningModel on a CUDA device.  A step
+    (adaptiveattention.py:128-135): AdaLSTM over [emb | glob] with the sentinel gate from the old hidden state
+    (``lrpx_lstm_step_f32``, five gates), adaptive attention (``lrpx_adaptive_attention_f32``), fc(ctx_hat + h)."""
+
+    def _weight_sources(self):
+        m = self.model
+        cell, xg, hg, att = m.AdaLSTM.lstm_cell, m.AdaLSTM.x_gate, m.AdaLSTM.h_gate, m.AdaAttention
+        return [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, xg.weight, xg.bias, hg.weight, hg.bias,
+                att.W_g_proj.weight, att.W_s_proj.weight, att.W_s_proj.bias, att.w_h.weight]
+
+    def _build_weights(self):
+        m = self.model
+        cell, xg, hg, att = m.AdaLSTM.lstm_cell, m.AdaLSTM.x_gate, m.AdaLSTM.h_gate, m.AdaAttention
+        H, E, K = m.hidden_dim, m.embed_dim, att.num_pixel
+        dev = cell.weight_ih.device
+        W_rec = torch.cat((cell.weight_hh, hg.weight), 0).t().contiguous()             # (H, 5H)
+        W_in = torch.cat((cell.weight_ih, xg.weight), 0).t().contiguous()              # (2E, 5H): rows [emb ; glob]
+        Wa = torch.zeros(2 * H, 2 * K, device=dev)
+        Wa[:H, :K] = att.W_g_proj.weight.t()
+        Wa[H:, K:] = att.W_s_proj.weight.t()
+        return dict(Wp=ops.lstm_prep_weights(W_rec, 5), W_emb=W_in[:E].contiguous(), W1_glob=W_in[E:].contiguous(),
+                    b1=torch.cat((cell.bias_ih + cell.bias_hh, xg.bias + hg.bias)).contiguous(), Wa=Wa,
+                    ba=torch.cat((torch.zeros(K, device=dev), att.W_s_proj.bias)),
+                    w_h=att.w_h.weight.reshape(-1).contiguous(), fcW_t=m.fc.weight.t())
+
+    def _alloc(self, R, P, f):
+        m = self.model
+        H, E, K = m.hidden_dim, m.embed_dim, m.AdaAttention.num_pixel
+        return dict(A=f(R, P, H), img_proj=f(R, P, K), preg=f(R, 5 * H),                   # per-call inputs
+                    hin=f(R, H), c=f(R, H), hs=f(R, 2 * H), hn=f(R, H), cn=f(R, H), g=f(R, H), i=f(R, H), f=f(R, H), st=f(R, H),
+                    ctx=f(R, H), ctx_hat=f(R, H), alpha=f(R, P), beta=f(R), emb=f(R, E), pre=f(R, 5 * H),
+                    hsp=f(R, 2 * K), xo=f(R, H))
+
+    def _recurrent(self, t):
+        return [t["hin"], t["c"]]
+
+    def _pairs(self, t):
+        return [(t["hin"], t["hn"]), (t["c"], t["cn"])]
+
+    def _step(self, t, w):
+        m = self.model
+        H = m.hidden_dim
+        torch.index_select(m.embedding.weight, 0, t["prev"], out=t["emb"])
+        torch.addmm(t["preg"], t["emb"], w["W_emb"], out=t["pre"])
+        ops.lstm_step(t["hin"], w["Wp"], t["pre"], 5, t["c"], t["hn"], t["cn"], t["g"], t["i"], t["f"],
+                      s=t["st"], h_copy2=t["hs"][:, :H], s_copy=t["hs"][:, H:])
+        torch.addmm(w["ba"], t["hs"], w["Wa"], out=t["hsp"])
+        ops.adaptive_attention(t["A"], t["img_proj"], t["hsp"], w["w_h"], t["st"], t["ctx"], t["ctx_hat"],
+                               t["alpha"], t["beta"])
+        torch.add(t["ctx_hat"], t["hn"], out=t["xo"])
+        torch.addmm(m.fc.bias, t["xo"], w["fcW_t"], out=t["logits"])
+
+    _prepare = GridTDBeamSearch._prepare
+
+    def search(self, image_feature_proj, global_img_feature, word_map, beam_size=3, max_cap_length=20):
+        """image_feature_proj (B, hidden, P) and global_img_feature (B, embed) as the model's ``_encode`` returns them."""
+        if not image_feature_proj.is_cuda:
+            raise ops._lib.LrpxError("AdaptiveBeamSearch needs CUDA tensors: lrpx has no CPU fallback")
+        B, H, P = image_feature_proj.shape
+        return self._search(B, P, image_feature_proj.transpose(1, 2), global_img_feature, word_map, beam_size,
+                            max_cap_length)

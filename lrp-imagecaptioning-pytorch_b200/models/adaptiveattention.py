@@ -139,6 +139,20 @@ class AdaptiveAttentionCaptioningModel(nn.Module):
             sen_idx = [w for w in seq if w not in special]
             return [' '.join(rev_word_map[w] for w in sen_idx)], sen_idx
 
+    def beam_search_device(self, imgs, word_map, beam_size=3, max_cap_length=20):
+        """``beam_search`` with the step loop on the device (lrpx.beam.AdaptiveBeamSearch) for B >= 1 images at once;
+        same word indices.  -> (sentence, sen_idx) for one image, a list of such pairs for a batch."""
+        from lrpx.beam import AdaptiveBeamSearch
+        self.eval()
+        if getattr(self, "_beam", None) is None:
+            self._beam = AdaptiveBeamSearch(self)
+        with torch.no_grad():
+            _, image_feature_proj, global_img_feature = self._encode(imgs)
+        rev_word_map = {v: k for k, v in word_map.items()}
+        out = [([' '.join(rev_word_map[w] for w in idx)], idx)
+               for idx in self._beam.search(image_feature_proj, global_img_feature, word_map, beam_size, max_cap_length)]
+        return out[0] if len(out) == 1 else out
+
     def greedy_search(self, imgs, word_map, max_cap_length=20):
         """reference :449-489 -> (sentences, token lists incl. <start>; finished rows continue with <pad>=0)."""
         self.eval()
@@ -266,16 +280,18 @@ class ExplainAdaptiveAttention(ExplainGridTDAttention):
         """reference :567-624: the same saved state for the beam-size-1 caption."""
         self._caption_state(img_filepath, beam_size=1)
 
+    _BEAM = "AdaptiveBeamSearch"
+    _REMOVE_BAD_ENDINGS = False           # this model's beam search keeps the sentence as it is (:444-446)
+
     def _caption_state(self, img_filepath, beam_size):
         self.img = self.preprocess_img(img_filepath)
-        self.beam_caption, self.beam_caption_encode = self.model.beam_search(self.img, self.word_map,
-                                                                             beam_size=beam_size, max_cap_length=20)
-        self.beam_caption_encode = [self.word_map['<start>']] + self.beam_caption_encode
-        print(f'the predicted caption of {img_filepath} is "{self.beam_caption[0]}"')
-        self._set_state(self.img, self.beam_caption_encode)
+        enc = self._find_caption(img_filepath, beam_size=beam_size, max_cap_length=20)
+        self._set_state(self.img, self.beam_caption_encode, enc)
 
-    def _set_state(self, img, tokens):
-        feat, (fh, fw), est = self.encode_images(img)
+    def _set_state(self, img, tokens, enc=None):
+        if self._empty_caption(tokens):
+            return
+        feat, (fh, fw), est = enc if enc is not None else self.encode_images(img)
         toks = torch.tensor([tokens], dtype=torch.long, device=self.device)
         st = self.explainer_forward(feat, toks)
         self._state, self._enc_state, self._feat_hw = st, est, (fh, fw)

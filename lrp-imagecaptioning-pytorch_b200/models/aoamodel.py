@@ -357,16 +357,23 @@ class ExplainAOAAttention(ExplainGridTDAttention):
                       value=value.contiguous())
         return st
 
+    _BEAM = "AoaBeamSearch"
+
+    def _search_inputs(self, feat):
+        m = self.model
+        Wp = m.img_projector.weight.reshape(m.hidden_dim, -1)
+        proj = torch.addmm(m.img_projector.bias, feat[0], Wp.t()).clamp(min=0).unsqueeze(0)          # (1,P,H)
+        return proj, proj.mean(1)
+
     def get_hidden_parameters(self, img_filepath):
         self.img = self.preprocess_img(img_filepath)
-        self.beam_caption, self.beam_caption_encode = self.model.beam_search(self.img, self.word_map, beam_size=3,
-                                                                             max_cap_length=20)
-        self.beam_caption_encode = [self.word_map['<start>']] + self.beam_caption_encode
-        print(f'the predicted caption of {img_filepath} is "{self.beam_caption[0]}"')
-        self._set_state(self.img, self.beam_caption_encode)
+        enc = self._find_caption(img_filepath, beam_size=3, max_cap_length=20)
+        self._set_state(self.img, self.beam_caption_encode, enc)
 
-    def _set_state(self, img, tokens):
-        feat, (fh, fw), est = self.encode_images(img)
+    def _set_state(self, img, tokens, enc=None):
+        if self._empty_caption(tokens):
+            return
+        feat, (fh, fw), est = enc if enc is not None else self.encode_images(img)
         toks = torch.tensor([tokens], dtype=torch.long, device=self.device)
         st = self.explainer_forward(feat, toks)
         self._state, self._enc_state, self._feat_hw = st, est, (fh, fw)
@@ -413,6 +420,8 @@ class ExplainAOAAttention(ExplainGridTDAttention):
         self.img_filepath = img_filepath
         self.get_hidden_parameters(img_filepath)
         T = self.caption_length
+        if T == 0:
+            return [], []
         r_feat, r_words = self._decoder_lrp(list(range(T)), head_idx)
         if self.precision == 'bf16':
             heat = self.engine().relevance(self._enc_state, r_feat, torch.zeros(T, dtype=torch.int32, device=self.device))

@@ -623,34 +623,58 @@ class ExplainGridTDAttention(object):
     # with the tensor-core encoder the caption search runs on the device too and shares the encoder pass of the
     # explanation (the reference's host loop encodes the image a second time); set False for the host loop
     DEVICE_BEAM_SEARCH = True
+    _BEAM = "GridTDBeamSearch"            # class in lrpx.beam
+    _REMOVE_BAD_ENDINGS = True
 
-    def get_hidden_parameters(self, img_filepath):
-        self.img = self.preprocess_img(img_filepath)
+    def _search_inputs(self, feat):
+        """(1,P,C) encoder features -> what the model's ``_encode`` hands to its beam search."""
+        m = self.model
+        Wp = m.img_projector.weight.reshape(m.hidden_dim, -1)
+        proj = torch.addmm(m.img_projector.bias, feat[0], Wp.t()).clamp(min=0).t().unsqueeze(0)      # (1,H,P)
+        return proj, m.global_img_feature_proj(feat.mean(1)).clamp(min=0)
+
+    def _find_caption(self, img_filepath, beam_size, max_cap_length):
+        """Sets ``beam_caption`` / ``beam_caption_encode`` (with <start>) from the model's beam search; returns the
+        encoder pass when it was already needed for the search (device search), else None."""
         m = self.model
         enc = None
         if (self.DEVICE_BEAM_SEARCH and self.precision == 'bf16' and self.has_encoder and self.img.is_cuda
-                and 'beam_search' not in m.__dict__ and isinstance(m, GridTDModel)):
-            from lrpx.beam import GridTDBeamSearch
+                and 'beam_search' not in m.__dict__):
+            from lrpx import beam
             if getattr(self, "_beam", None) is None:
-                self._beam = GridTDBeamSearch(m)
+                self._beam = getattr(beam, self._BEAM)(m)
             enc = self.encode_images(self.img)
-            feat = enc[0]                                                              # (1,P,C)
             with torch.no_grad():
-                Wp = m.img_projector.weight.reshape(m.hidden_dim, -1)
-                proj = torch.addmm(m.img_projector.bias, feat[0], Wp.t()).clamp(min=0).t().unsqueeze(0)      # (1,H,P)
-                glob = m.global_img_feature_proj(feat.mean(1)).clamp(min=0)
-            idx = self._beam.search(proj, glob, self.word_map, beam_size=2, max_cap_length=50)[0]
+                proj, glob = self._search_inputs(enc[0])
+            idx = self._beam.search(proj, glob, self.word_map, beam_size=beam_size, max_cap_length=max_cap_length)[0]
             rev = {v: k for k, v in self.word_map.items()}
-            self.beam_caption = m.remove_bad_endings([' '.join(rev[w] for w in idx)])
+            sentence = [' '.join(rev[w] for w in idx)]
+            self.beam_caption = m.remove_bad_endings(sentence) if self._REMOVE_BAD_ENDINGS else sentence
             self.beam_caption_encode = idx
         else:
-            self.beam_caption, self.beam_caption_encode = m.beam_search(self.img, self.word_map, beam_size=2,
-                                                                        max_cap_length=50)
+            self.beam_caption, self.beam_caption_encode = m.beam_search(self.img, self.word_map, beam_size=beam_size,
+                                                                        max_cap_length=max_cap_length)
         self.beam_caption_encode = [self.word_map['<start>']] + self.beam_caption_encode
         print(f'the predicted caption of {img_filepath} is "{self.beam_caption[0]}"')
+        return enc
+
+    def get_hidden_parameters(self, img_filepath):
+        self.img = self.preprocess_img(img_filepath)
+        enc = self._find_caption(img_filepath, beam_size=2, max_cap_length=50)
         self._set_state(self.img, self.beam_caption_encode, enc)
 
+    def _empty_caption(self, tokens):
+        """The search returned no word (<end> or only special tokens first): like the reference, nothing is explained
+        (caption_length 0, explain_caption returns two empty lists)."""
+        if len(tokens) > 1:
+            return False
+        self._state, self._enc_state, self.caption_length = None, None, 0
+        self.predictions = torch.zeros(0, self.vocab_size, device=self.device)
+        return True
+
     def _set_state(self, img, tokens, enc=None):
+        if self._empty_caption(tokens):
+            return
         feat, (fh, fw), est = enc if enc is not None else self.encode_images(img)
         toks = torch.tensor([tokens], dtype=torch.long, device=self.device)
         st = self.explainer_forward(feat, toks)
@@ -701,6 +725,8 @@ class ExplainGridTDAttention(object):
         self.img_filepath = img_filepath
         self.get_hidden_parameters(img_filepath)
         T = self.caption_length
+        if T == 0:
+            return [], []
         r_feat, r_words = self._decoder_lrp(list(range(T)))
         if self.precision == 'bf16':
             rows = torch.zeros(T, dtype=torch.int32, device=self.device)
