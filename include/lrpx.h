@@ -299,6 +299,24 @@ typedef struct {
 int lrpx_beam_gather_f32(const lrpx_beam_gather_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Patch ablation: EvaluationExperiments.block_image (evaluation.py:57-80) batched over Q requests.
+ * spatial relevance = channel mean of the request's heat-map (:128-129); the k patches (patch x patch pixels) with the
+ * largest relevance sums are blanked: mask = 0 there, 1 elsewhere (:73-80); masked = mask * images[req_img[q]] (:130).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int Q, C, H, W;          /* heat-maps (Q,C,H,W) */
+  int patch, k;            /* evaluation.py:55-56: patch_size 8, num_delete_patches 20 */
+  int img_c, reserved_;    /* channels of `images` */
+  const float* heat;
+  const float* images;     /* (B,img_c,H,W) or NULL */
+  const int32_t* req_img;  /* (Q) image of each request, NULL = identity */
+  float* mask;             /* (Q,H,W) or NULL */
+  float* masked;           /* (Q,img_c,H,W) or NULL */
+} lrpx_block_image_args;
+
+int lrpx_block_image_f32(const lrpx_block_image_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Explainer forward (the producer of the saved state above): fused element-wise steps of
  * ExplainGridTDAttention.get_hidden_parameters (gridTDmodel.py:933-1012).  Row strides ("ld_*", in
  * elements) let the kernels write straight into the (B, T, .) saved-state tensors and into the

@@ -96,6 +96,11 @@ class BeamGatherArgs(C.Structure):
                 ("width", C.c_int * BEAM_GATHER_MAX)]
 
 
+class BlockImageArgs(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("Q", "C", "H", "W", "patch", "k", "img_c", "reserved_")] + \
+               [(n, _P) for n in ("heat", "images", "req_img", "mask", "masked")]
+
+
 # every symbol include/lrpx.h declares: name -> (restype, argtypes)
 _i, _f, _sz = C.c_int, C.c_float, C.c_size_t
 SYMBOLS = {
@@ -123,6 +128,7 @@ SYMBOLS = {
     "lrpx_fc_lrp_weights_f32": (_i, [_P, _P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
     "lrpx_beam_step": (_i, [C.POINTER(BeamArgs), _P]),
     "lrpx_beam_gather_f32": (_i, [C.POINTER(BeamGatherArgs), _P]),
+    "lrpx_block_image_f32": (_i, [C.POINTER(BlockImageArgs), _P]),
     "lrpx_lstm_cell_f32": (_i, [C.POINTER(LstmCellArgs), _P]),
     "lrpx_adaptive_attention_f32": (_i, [C.POINTER(AdaAttentionArgs), _P]),
     "lrpx_lstm_prep_weights_f32": (_i, [_P, _P, _i, _i, _i, _P]),

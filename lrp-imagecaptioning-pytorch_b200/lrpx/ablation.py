@@ -1,0 +1,115 @@
+"""Ablation experiments of the reference's evaluation.py, batched over (image, word) requests.
+
+``EvaluationExperiments.ablation_experiment`` (evaluation.py:82-290) walks one image at a time and, per explained word,
+
+* image ablation (:120-150): blanks the 20 most relevant 8x8 patches of the image (``block_image`` :57-80), captions
+  the modified image again with beam search, and records whether the word disappears or — if it is still there — how
+  much its softmax score drops under teacher forcing of the new prefix;
+* word ablation (:234-262): deletes the 3 most relevant preceding words and records the score drop of the word under
+  teacher forcing of the shortened prefix.
+
+Here every stage runs once for ALL requests: ``lrpx_block_image_f32`` writes the masked images, the tensor-core encoder
+and the device beam search (lrpx.beam) caption them in chunks, and one batched explainer forward per experiment yields
+the teacher-forced scores.  The word filters of the reference (object-word list, stop words, t >= 1 / t >= 6) are the
+caller's choice of requests.
+"""
+import torch
+
+from . import ops
+
+
+class AblationExperiments:
+    def __init__(self, explainer, num_delete_patches=20, patch_size=8, num_delete_words=3, chunk=128):
+        """explainer: ExplainGridTDAttention / ExplainAOAAttention / ExplainAdaptiveAttention with precision='bf16'
+        (VGG encoder on the tensor-core engine).  Defaults: evaluation.py:55-56, :241."""
+        if explainer.precision != "bf16":
+            raise ValueError("AblationExperiments drives the tensor-core encoder: build the explainer with precision='bf16'")
+        self.ex = explainer
+        self.num_delete_patches = int(num_delete_patches)
+        self.patch_size = int(patch_size)
+        self.num_delete_words = int(num_delete_words)
+        self.chunk = int(chunk)
+
+    # ------------------------------------------------------------------ evaluation.py:57-80
+    def block_image(self, relevance):
+        """relevance (H, W) -> mask (H, W), the reference's signature (one map)."""
+        return ops.block_image(relevance.reshape(1, 1, *relevance.shape), self.num_delete_patches, self.patch_size)[0]
+
+    def _searcher(self):
+        from . import beam
+        ex = self.ex
+        if getattr(ex, "_beam", None) is None:
+            ex._beam = getattr(beam, ex._BEAM)(ex.model)
+        return ex._beam
+
+    def _teacher_forced_scores(self, feat, prefixes, words):
+        """softmax score of ``words[i]`` as the next word after ``prefixes[i]`` (token lists starting with <start>) for
+        the images with features ``feat`` (n,P,C): evaluation.py:139-142 (teacherforce_forward + softmax of the last row)."""
+        dev = feat.device
+        L = max(len(p) for p in prefixes)
+        toks = torch.tensor([p + [0] * (L + 1 - len(p)) for p in prefixes], dtype=torch.long, device=dev)
+        pred = self.ex.explainer_forward(feat, toks)["pred"]                          # (n, L, V)
+        last = torch.tensor([len(p) - 1 for p in prefixes], device=dev)
+        rows = pred[torch.arange(len(prefixes), device=dev), last]
+        return torch.softmax(rows, dim=-1).gather(1, torch.as_tensor(words, device=dev).view(-1, 1))[:, 0]
+
+    # ------------------------------------------------------------------ evaluation.py:120-150
+    def image_ablation(self, imgs, tokens, heat, req_img, req_t, pred, beam_size=3, max_cap_length=20):
+        """imgs (B,3,H,W), tokens (B,T+1) with column 0 = <start>, heat (Q,3,H,W) relevance of request q = (req_img[q],
+        req_t[q]), pred (B,T,V) the explainer's logits.  -> dict: ``disappear`` (Q,) bool — the word is not in the new
+        caption (:147-149); ``score_diff`` (Q,) original minus new softmax score, NaN where the word disappeared
+        (:143-146); ``captions``: the Q new captions (token lists)."""
+        ex = self.ex
+        dev = ex.device
+        eng = ex.engine()
+        Q = heat.shape[0]
+        req_img_l, req_t_l = req_img.tolist(), req_t.tolist()
+        words = [int(tokens[b, t + 1]) for b, t in zip(req_img_l, req_t_l)]
+        with torch.no_grad():
+            _, masked = ops.block_image(heat, self.num_delete_patches, self.patch_size, images=imgs, req_img=req_img,
+                                        want_mask=False)
+            orig = torch.softmax(pred[req_img.long(), req_t.long()], dim=-1).gather(
+                1, torch.tensor(words, device=dev).view(-1, 1))[:, 0]
+            searcher = self._searcher()
+            caps, feats = [], []
+            for q0 in range(0, Q, self.chunk):
+                est = eng.forward(masked[q0:q0 + self.chunk])
+                feat = eng.features(est, "pixel").clone()
+                del est
+                proj, glob = ex._search_inputs(feat)
+                caps += searcher.search(proj, glob, ex.word_map, beam_size=beam_size, max_cap_length=max_cap_length)
+                feats.append(feat)
+            feat = torch.cat(feats)
+            disappear = torch.tensor([w not in c for w, c in zip(words, caps)], device=dev)
+            score_diff = torch.full((Q,), float("nan"), device=dev)
+            keep = [q for q in range(Q) if words[q] in caps[q]]
+            if keep:
+                start = ex.word_map['<start>']
+                prefixes = [[start] + caps[q][:caps[q].index(words[q])] for q in keep]
+                idx = torch.tensor(keep, device=dev)
+                new = self._teacher_forced_scores(feat[idx], prefixes, [words[q] for q in keep])
+                score_diff[idx] = orig[idx] - new
+        return dict(disappear=disappear, score_diff=score_diff, captions=caps, masked=masked)
+
+    # ------------------------------------------------------------------ evaluation.py:234-262
+    def word_ablation(self, feat, tokens, r_words, req_img, req_t, pred):
+        """feat (B,P,C) encoder features, r_words (Q,T) linguistic relevance of each request (entry 0 = <start>).
+        Deletes the ``num_delete_words`` most relevant preceding words (never <start>, :241-246) and returns the score
+        drop of the explained word (Q,) under teacher forcing of the shortened prefix.  Requests need
+        t >= num_delete_words (the reference uses t >= 6)."""
+        dev = feat.device
+        req_img_l, req_t_l = req_img.tolist(), req_t.tolist()
+        if any(t < self.num_delete_words for t in req_t_l):
+            raise ValueError("word ablation needs at least num_delete_words preceding words per request")
+        toks = tokens.tolist()
+        words = [toks[b][t + 1] for b, t in zip(req_img_l, req_t_l)]
+        prefixes = []
+        for q, (b, t) in enumerate(zip(req_img_l, req_t_l)):
+            top = torch.topk(r_words[q, 1:t + 1], k=self.num_delete_words).indices.tolist()       # :241
+            drop = {i + 1 for i in top}
+            prefixes.append([w for i, w in enumerate(toks[b][:t + 1]) if i not in drop])          # np.delete (:246)
+        with torch.no_grad():
+            orig = torch.softmax(pred[req_img.long(), req_t.long()], dim=-1).gather(
+                1, torch.tensor(words, device=dev).view(-1, 1))[:, 0]
+            new = self._teacher_forced_scores(feat[req_img.long()], prefixes, words)
+        return orig - new

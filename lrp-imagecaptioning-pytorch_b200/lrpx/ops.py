@@ -446,3 +446,28 @@ def beam_gather(src_row, pairs):
         g.dst[e], g.src[e] = dst.data_ptr(), src.data_ptr()
         g.ld_dst[e], g.ld_src[e], g.width[e] = _ld(dst), _ld(src), dst.shape[1]
     check(lib().lrpx_beam_gather_f32(C.byref(g), _stream()), "lrpx_beam_gather_f32")
+
+
+# ------------------------------------------------------------------------------------------ patch ablation
+def block_image(heat, k=20, patch=8, images=None, req_img=None, want_mask=True):
+    """lrpx_block_image_f32 (EvaluationExperiments.block_image, evaluation.py:57-80, batched): heat (Q,C,H,W) ->
+    mask (Q,H,W) with zeros on the k most relevant patch x patch patches [and masked = mask * images[req_img]]."""
+    heat = _f32(heat, "heat")
+    Q, Cc, H, W = heat.shape
+    a = _lib.BlockImageArgs(Q=Q, C=Cc, H=H, W=W, patch=int(patch), k=int(k))
+    a.heat = heat.data_ptr()
+    keep = [heat]
+    mask = masked = None
+    if want_mask:
+        mask = torch.empty(Q, H, W, device=heat.device, dtype=torch.float32)
+        a.mask = mask.data_ptr()
+    if images is not None:
+        images = _f32(images, "images")
+        a.images, a.img_c = images.data_ptr(), images.shape[1]
+        if req_img is not None:
+            req_img = req_img.to(device=heat.device, dtype=torch.int32).contiguous()
+            a.req_img = req_img.data_ptr()
+        masked = torch.empty(Q, images.shape[1], H, W, device=heat.device, dtype=torch.float32)
+        a.masked = masked.data_ptr()
+    check(lib().lrpx_block_image_f32(C.byref(a), _stream()), "lrpx_block_image_f32")
+    return (mask, masked) if images is not None else mask

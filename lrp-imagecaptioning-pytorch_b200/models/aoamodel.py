@@ -361,8 +361,9 @@ class ExplainAOAAttention(ExplainGridTDAttention):
 
     def _search_inputs(self, feat):
         m = self.model
+        B, P, C = feat.shape
         Wp = m.img_projector.weight.reshape(m.hidden_dim, -1)
-        proj = torch.addmm(m.img_projector.bias, feat[0], Wp.t()).clamp(min=0).unsqueeze(0)          # (1,P,H)
+        proj = torch.addmm(m.img_projector.bias, feat.reshape(B * P, C), Wp.t()).clamp(min=0).view(B, P, -1)   # (B,P,H)
         return proj, proj.mean(1)
 
     def get_hidden_parameters(self, img_filepath):

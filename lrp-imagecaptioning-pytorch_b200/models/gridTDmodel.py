@@ -627,11 +627,12 @@ class ExplainGridTDAttention(object):
     _REMOVE_BAD_ENDINGS = True
 
     def _search_inputs(self, feat):
-        """(1,P,C) encoder features -> what the model's ``_encode`` hands to its beam search."""
+        """(B,P,C) encoder features -> what the model's ``_encode`` hands to its beam search."""
         m = self.model
+        B, P, C = feat.shape
         Wp = m.img_projector.weight.reshape(m.hidden_dim, -1)
-        proj = torch.addmm(m.img_projector.bias, feat[0], Wp.t()).clamp(min=0).t().unsqueeze(0)      # (1,H,P)
-        return proj, m.global_img_feature_proj(feat.mean(1)).clamp(min=0)
+        proj = torch.addmm(m.img_projector.bias, feat.reshape(B * P, C), Wp.t()).clamp(min=0).view(B, P, -1)
+        return proj.transpose(1, 2), m.global_img_feature_proj(feat.mean(1)).clamp(min=0)           # (B,H,P), (B,E)
 
     def _find_caption(self, img_filepath, beam_size, max_cap_length):
         """Sets ``beam_caption`` / ``beam_caption_encode`` (with <start>) from the model's beam search; returns the

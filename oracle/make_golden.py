@@ -298,6 +298,30 @@ def golden_adaptive_decoder(ns):
         save(tag, **out)
 
 
+def golden_block_image(ns):
+    """EvaluationExperiments.block_image (evaluation.py:57-80): the mask that removes the num_delete_patches most
+    relevant 8x8 patches, run by the reference on seeded relevance maps (heat-map-like: channel mean of random maps)."""
+    ev = ref_shim.load_reference_evaluation()
+
+    class _Ex:                                            # the two attributes EvaluationExperiments.__init__ touches
+        model = nn.Identity()
+        word_map = {"<start>": 0}
+
+    exp = ev.EvaluationExperiments(_Ex())
+    heat, small = synth.block_image_inputs(71)          # regenerated from the seed by the tests, not stored
+    out = dict(seed=np.array(71), k=np.array(exp.num_delete_patches), patch=np.array(exp.patch_size))
+    masks = []
+    for q in range(heat.shape[0]):
+        with quiet():
+            masks.append(exp.block_image(torch.mean(heat[q:q + 1], dim=(0, 1))))          # evaluation.py:128-129
+    out["masks"] = torch.stack(masks).to(torch.uint8)
+    exp.num_delete_patches = 5
+    with quiet():
+        out["small_masks"] = torch.stack([exp.block_image(torch.mean(small[q:q + 1], dim=(0, 1)))
+                                          for q in range(3)]).to(torch.uint8)
+    save("block_image", **out)
+
+
 def _rev_word_map(V, stop):
     wm = synth.word_map(V)
     rev = {v: k for k, v in wm.items()}
@@ -389,7 +413,7 @@ def main():
     torch.manual_seed(0)
     only = set(sys.argv[1:])          # optional: names of the generators to (re)run
     for fn in (golden_rules, golden_sequential_small, golden_vgg16, golden_resnet, golden_gridtd_decoder,
-               golden_aoa_decoder, golden_adaptive_decoder, golden_lrp_weights, golden_tune, golden_tune_bu):
+               golden_aoa_decoder, golden_adaptive_decoder, golden_block_image, golden_lrp_weights, golden_tune, golden_tune_bu):
         if only and fn.__name__ not in only:
             continue
         print(fn.__name__)

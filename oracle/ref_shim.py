@@ -46,7 +46,7 @@ def _stub(name, **attrs):
 def install_stubs():
     if "matplotlib" not in sys.modules:
         mpl = _stub("matplotlib")
-        plt = _stub("matplotlib.pyplot")
+        plt = _stub("matplotlib.pyplot", imshow=lambda *a, **k: None, show=lambda *a, **k: None)   # display only
         mpl.pyplot = plt
     if "skimage" not in sys.modules:
         sk = _stub("skimage")
@@ -71,6 +71,32 @@ def install_stubs():
 
 
 _loaded = {}
+
+
+def load_reference_evaluation():
+    """evaluation.py of the reference (EvaluationExperiments: block_image, ablation loops), imported with the reference's
+    own models / LRPtools visible under their public names for the duration of the import."""
+    if "evaluation" in _loaded:
+        return _loaded["evaluation"]
+    load_reference()
+    saved = {k: sys.modules[k] for k in list(sys.modules) if k.split(".")[0] in ("LRPtools", "models", "config")}
+    for k in saved:
+        del sys.modules[k]
+    for k in [k for k in sys.modules if k.startswith("_lrpx_ref_.")]:
+        sys.modules[k[len("_lrpx_ref_."):]] = sys.modules[k]
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        path = os.path.join(REFERENCE_ROOT, "evaluation.py")
+        mod = types.ModuleType("_lrpx_ref_evaluation")
+        mod.__file__ = path
+        exec(compile(open(path).read(), path, "exec"), mod.__dict__)
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        for k in [k for k in sys.modules if k.split(".")[0] in ("LRPtools", "models", "config")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    _loaded["evaluation"] = mod
+    return mod
 
 
 def load_reference(cpu: bool = True):

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,driver_version,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-for f in ${TESTS:-rules decoder encoder tc models beam fullsize}; do
+for f in ${TESTS:-rules decoder encoder tc models beam ablation fullsize}; do
   timeout 900 python -m pytest tests/test_gpu_$f.py -q -m gpu --tb=short -s > gpurun_out/test_$f.log 2>&1
   echo "test_gpu_$f exit $?" | tee -a gpurun_out/summary.txt
   grep -v "mbarrier wait timed out" gpurun_out/test_$f.log | tail -n 3

@@ -196,3 +196,13 @@ def tokens(seed: int, T: int, V: int) -> List[int]:
     """[<start>] + T random content words."""
     t = torch.randint(1, V - 4, (T,), generator=_gen(seed)).tolist()
     return [V - 2] + t
+
+
+def block_image_inputs(seed: int = 71):
+    """Seeded heat-map-like inputs of the block_image fixture (oracle/make_golden.py golden_block_image)."""
+    g = _gen(seed)
+    heat = torch.randn(6, 3, 224, 224, generator=g) * torch.rand(6, 1, 224, 224, generator=g)
+    heat[4, :, 8:16, 8:16] = 0                             # a patch of exact zeros
+    heat[5] = heat[5].abs()                                # non-negative map
+    small = torch.randn(3, 3, 32, 48, generator=g)
+    return heat, small

@@ -1,0 +1,117 @@
+"""GPU: patch-ablation masks (lrpx_block_image_f32) against masks produced by the reference's own
+EvaluationExperiments.block_image (fixture block_image), and the batched ablation experiments (lrpx.ablation) against
+the per-request walk of evaluation.py:120-150 / :234-262 done with the mirror's host functions."""
+import argparse
+
+import pytest
+import torch
+
+import lrp_oracle as O
+import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def test_block_image_masks_bit_exact_vs_reference(golden):
+    from lrpx import ops
+    g = golden("block_image")
+    heat, small = synth.block_image_inputs(int(g["seed"]))
+    k, patch = int(g["k"]), int(g["patch"])
+    mask = ops.block_image(heat.to(DEV), k, patch)
+    assert torch.equal(mask.cpu().to(torch.uint8), g["masks"])
+    assert torch.equal(ops.block_image(small.to(DEV), 5, patch).cpu().to(torch.uint8), g["small_masks"])
+    # masked images: mask * image of the request's image (evaluation.py:130), requests in arbitrary order
+    imgs = synth.images(5, 3).to(DEV)
+    req = torch.tensor([2, 0, 0, 1, 2, 1], dtype=torch.int32)
+    m2, masked = ops.block_image(heat.to(DEV), k, patch, images=imgs, req_img=req)
+    assert torch.equal(m2, mask)
+    assert torch.equal(masked, mask.unsqueeze(1) * imgs[req.long().to(DEV)])
+    # edge cases: k = 0 keeps everything, k = all patches blanks everything, empty batch
+    assert bool((ops.block_image(small.to(DEV), 0, patch) == 1).all())
+    assert bool((ops.block_image(small.to(DEV), 24, patch) == 0).all())
+    assert ops.block_image(small[:0].to(DEV), 5, patch).shape == (0, 32, 48)
+    from lrpx._lib import LrpxError
+    with pytest.raises(LrpxError):
+        ops.block_image(small.to(DEV), 25, patch)                  # more patches than there are (evaluation.py:65)
+    with pytest.raises(LrpxError):
+        ops.block_image(small[:, :, :30].contiguous().to(DEV), 5, patch)   # H not a multiple of the patch size (:59)
+
+
+def test_batched_ablation_equals_per_request_walk(tmp_path):
+    """B images x T words on GridTDModel + VGG16 (bf16 chain): explain, then the image ablation and the word ablation
+    for all requests at once == one request at a time with the mirror's host-side beam_search / teacherforce_forward
+    over the same (tensor-core) features and the oracle's block_image."""
+    from models import gridTDmodel as G
+    from lrpx.pipeline import BatchExplainer
+    from lrpx.ablation import AblationExperiments
+    V, H, E, B, T = 60, 64, 32, 2, 5
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(501, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(502))
+    model.to(DEV).eval()
+    wm = synth.word_map(V)
+    args = argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                              save_path=str(tmp_path), dataset="syn", weight="")
+    ex = G.ExplainGridTDAttention(args, wm, model=model, precision="bf16")
+    imgs = synth.images(503, B).to(DEV)
+    toks = torch.stack([torch.tensor(synth.tokens(504 + b, T, V)) for b in range(B)]).to(DEV)
+    heat, r_words = BatchExplainer(ex, chunk=8).explain(imgs, toks)
+    req_img = torch.arange(B, dtype=torch.int32, device=DEV).repeat_interleave(T)
+    req_t = torch.arange(T, dtype=torch.int32, device=DEV).repeat(B)
+    eng = ex.engine()
+    feat = eng.features(eng.forward(imgs), "pixel").clone()
+    pred = ex.explainer_forward(feat, toks)["pred"]
+    ab = AblationExperiments(ex, chunk=4)
+    out = ab.image_ablation(imgs, toks, heat, req_img, req_t, pred)
+    # ---- per-request walk (evaluation.py:120-150)
+    n_gone = 0
+    for q in range(B * T):
+        b, t = q // T, q % T
+        word = int(toks[b, t + 1])
+        mask = O.block_image(heat[q:q + 1].mean((0, 1)).cpu(), 20, 8).to(DEV)
+        assert torch.equal(ab.block_image(heat[q:q + 1].mean((0, 1))), mask)
+        image_modified = mask * imgs[b:b + 1]
+        assert torch.equal(out["masked"][q:q + 1], image_modified)
+        fmap = eng.features(eng.forward(image_modified), "pixel")[0].t().reshape(1, 512, 14, 14).clone()
+
+        class Stub(torch.nn.Module):
+            encoder = torch.nn.Identity()
+
+            def forward(self, im):
+                return fmap, fmap.mean((2, 3)).squeeze()
+
+        real = model.img_encoder
+        model.img_encoder = Stub()
+        _, new_idx = model.beam_search(image_modified, wm)
+        model.img_encoder = real
+        assert out["captions"][q] == new_idx, (q, out["captions"][q], new_idx)
+        if word in new_idx:
+            prefix = [wm['<start>']] + new_idx[:new_idx.index(word)]
+            new_scores = ex.teacherforce_forward(image_modified, prefix)
+            want = torch.softmax(pred[b, t], -1)[word] - torch.softmax(new_scores[-1], -1)[word]
+            assert not bool(out["disappear"][q])
+            assert abs(float(out["score_diff"][q]) - float(want)) <= 1e-3 * abs(float(want)) + 1e-6, (q, out["score_diff"][q], want)
+        else:
+            n_gone += 1
+            assert bool(out["disappear"][q]) and bool(torch.isnan(out["score_diff"][q]))
+    print(f"image ablation: {n_gone} of {B * T} words disappeared")
+    # ---- word ablation (evaluation.py:234-262) for the requests with t >= 3
+    sel = [q for q in range(B * T) if q % T >= 3]
+    idx = torch.tensor(sel, device=DEV)
+    diff = ab.word_ablation(feat, toks, r_words[idx], req_img[idx], req_t[idx], pred)
+    for n, q in enumerate(sel):
+        b, t = q // T, q % T
+        word = int(toks[b, t + 1])
+        top = torch.topk(r_words[q, 1:t + 1], k=3).indices.cpu().numpy()
+        import numpy as np
+        deleted = list(np.delete(np.array(toks[b, :t + 1].tolist()), top + 1))
+        new_scores = ex.teacherforce_forward(imgs[b:b + 1], [int(v) for v in deleted])
+        want = torch.softmax(pred[b, t], -1)[word] - torch.softmax(new_scores[-1], -1)[word]
+        assert abs(float(diff[n]) - float(want)) <= 1e-3 * abs(float(want)) + 1e-6, (q, diff[n], want)
