@@ -283,7 +283,7 @@ def run_ours(args):
         }
         out["breakdown_ms"] = phase_ms
         try:
-            out["roofline"]["layers"] = layer_table(eng, args.chunk, dev, pk)
+            out["roofline"]["layers"] = layer_table(eng, args.chunk, dev, pk, requests=args.images * args.words)
         except Exception as e:  # never lose the bench line to the per-layer microbenchmark
             out["roofline"]["layers_error"] = repr(e)
         if not args.no_cpu_baseline and world == 1:
@@ -321,16 +321,28 @@ def chain_traffic(chunk):
     return d["dram_bytes_per_explanation"] * chunk
 
 
-def layer_table(eng, chunk, dev, pk):
-    """Per-layer achieved TFLOP/s of the relevance-chain launches (CUDA events, 5 launches each, chunk blocks)."""
+def layer_table(eng, chunk, dev, pk, requests=None):
+    """Per-layer achieved TFLOP/s of the relevance-chain launches (CUDA events, 5 launches each) at the launch sizes the
+    engine uses: the low-resolution layers over all `requests` of a step in one launch (TcVggEngine.relevance_head),
+    the others per chunk; `ms` is per chunk of explanations either way."""
     from lrpx import tc
     rows = []
-    n = chunk
-    x = torch.randn(n, 3, eng.convs[0].h, eng.convs[0].w, device=dev)
+    x = torch.randn(1, 3, eng.convs[0].h, eng.convs[0].w, device=dev)
     st = eng.forward(x[:1])
-    rimg = torch.zeros(n, dtype=torch.int32, device=dev)
-    for li in range(len(eng.convs) - 1, -1, -1):
+    L = len(eng.convs)
+    Q = requests or chunk
+    n_wide = 0                                  # the engine's own rule (relevance_head): 2 GB per stage-1 buffer
+    if Q > chunk:
+        for li in range(L - 1, 0, -1):
+            c, below = eng.convs[li], eng.convs[li - 1]
+            oh, ow = (2 * c.h, 2 * c.w) if below.pool_after else (c.h, c.w)
+            if max(tc.pf_rows(Q, c.h, c.w) * c.cout, tc.pf_rows(Q, oh, ow) * c.cin) * 2 > (2 << 30):
+                break
+            n_wide += 1
+    for li in range(L - 1, -1, -1):
         c = eng.convs[li]
+        n = Q if li >= L - n_wide else chunk
+        rimg = torch.zeros(n, dtype=torch.int32, device=dev)
         a = torch.randn(tc.pf_rows(n, c.h, c.w), c.cout, device=dev).to(torch.bfloat16)
         if li == 0:
             out = torch.empty(n, 3, c.h, c.w, device=dev)
@@ -359,8 +371,8 @@ def layer_table(eng, chunk, dev, pk):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-        rows.append({"layer": li, "hw": c.h, "k": 9 * c.cout, "n": c.cin if li else 6, "ms": round(ms, 4),
-                     "tflops": round(flops / (ms * 1e-3) / 1e12, 1)})
+        rows.append({"layer": li, "hw": c.h, "k": 9 * c.cout, "n": c.cin if li else 6, "launch_requests": n,
+                     "ms": round(ms * chunk / n, 4), "tflops": round(flops / (ms * 1e-3) / 1e12, 1)})
         del a, out
     return rows
 
