@@ -87,3 +87,58 @@ class LrpTuneStep:
             clip_gradient(self.optimizer, self.grad_clip)
         self.optimizer.step()
         return loss.detach(), ls.detach(), ll.detach()
+
+
+class RewardCriterion(nn.Module):
+    """models/modelutils.py:31-46 — policy-gradient loss of the self-critical tuner: -logprob * reward, masked to the
+    sampled words up to and including the first <pad>/<end> position (mask shifted by one step)."""
+
+    def forward(self, input, seq, reward):
+        input = input.contiguous().view(-1)
+        reward = reward.contiguous().view(-1)
+        mask = (seq.detach() > 0).float()
+        mask = torch.cat([mask.new_ones(mask.size(0), 1), mask[:, :-1]], 1).contiguous().view(-1)
+        return torch.sum(-input * reward * mask) / torch.sum(mask)
+
+
+class LrpCiderTuneStep:
+    """One ``trainciderlrp`` iteration per call (reference train.py:252-272): greedy baseline with ``model.sample``,
+    sampled captions with ``model.sample_lrp`` (the LRP weights of every step come from ``lrpx_fc_lrp_weights_f32``),
+    self-critical reward, RewardCriterion, gradient clamp, optimizer step.
+
+    ``reward_fn(greedy_seq, all_caps, sampled_seq, word_map) -> (B, L) array / tensor`` is the caller's scorer — the
+    reference's ``get_self_critical_reward`` (modelutils.py:200-238) runs the CIDEr / BLEU scorers of pycocoevalcap on
+    the host, which are outside this path (SURVEY.md §8 out of scope)."""
+
+    def __init__(self, model, word_map, reward_fn, optimizer=None, lr=1e-5, grad_clip=None, fix_encoder=True):
+        self.model = model
+        self.word_map = word_map
+        self.rev_word_map = {v: k for k, v in word_map.items()}
+        self.reward_fn = reward_fn
+        if fix_encoder:
+            for name, p in model.named_parameters():
+                if 'img_encoder' in name:
+                    p.requires_grad = False
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.optimizer = optimizer or torch.optim.Adam(params=params, lr=lr, betas=(0.8, 0.999))
+        self.grad_clip = grad_clip
+        self.criterion = RewardCriterion()
+
+    def step(self, imgs, all_caps, caplens):
+        """-> (loss, mean reward) as detached tensors."""
+        m = self.model
+        m.eval()
+        with torch.no_grad():
+            greedy_res, _, _ = m.sample(imgs, self.word_map, caplens)                                  # train.py:259-261
+        m.train()
+        gen_result, sample_logprobs, _ = m.sample_lrp(imgs, self.rev_word_map, self.word_map, caplens,
+                                                      opt={'sample_method': 'sample'})                 # :263
+        reward = torch.as_tensor(self.reward_fn(greedy_res, all_caps, gen_result, self.word_map),
+                                 dtype=torch.float32, device=sample_logprobs.device)                   # :264-265
+        loss = self.criterion(sample_logprobs, gen_result.data, reward)
+        self.optimizer.zero_grad()
+        loss.backward()
+        if self.grad_clip:
+            clip_gradient(self.optimizer, self.grad_clip)
+        self.optimizer.step()
+        return loss.detach(), reward[:, 0].mean().detach()

@@ -186,6 +186,32 @@ class AOAModel(nn.Module):
             sen_idx = [w for w in seq if w not in special]
             return self.remove_bad_endings([' '.join(rev_word_map[w] for w in sen_idx)]), sen_idx
 
+    def sample(self, images, word_map, caption_lengths, opt={}):
+        """reference aoamodel.py:206-245 -> (seq, seq_logprobs, max_length), see GridTDModel.sample."""
+        batch_size = images.size(0)
+        sample_method = opt.get('sample_method', 'greedy')
+        temperature = opt.get('temperature', 1.0)
+        max_length = int(max(caption_lengths)) - 1
+        _, proj, glob = self._encode(images)
+        state = self.init_hidden_state(proj)
+        dev = proj.device
+        seq = torch.zeros(batch_size, max_length, dtype=torch.long, device=dev)
+        seq_logprobs = torch.zeros(batch_size, max_length, device=dev)
+        it = torch.full((batch_size,), word_map['<start>'], dtype=torch.long, device=dev)
+        unfinished = None
+        for t in range(max_length):
+            xt = torch.cat((self.embedding(it), glob), dim=-1)
+            score, _, _, state = self.predict_next_word(proj, xt, state)
+            it, sample_logprobs = self.sample_next_word(torch.log_softmax(score, dim=-1), sample_method, temperature)
+            finished = it == word_map['<end>']
+            unfinished = ~finished if unfinished is None else unfinished & ~finished
+            it = it * unfinished.type_as(it)
+            seq[:, t] = it
+            seq_logprobs[:, t] = sample_logprobs.view(-1)
+            if int(unfinished.sum()) == 0:
+                break
+        return seq, seq_logprobs, max_length
+
     def beam_search_device(self, imgs, word_map, beam_size=3, max_cap_length=20):
         """``beam_search`` with the step loop on the device (lrpx.beam.AoaBeamSearch) for B >= 1 images at once; same
         word indices.  -> (sentence, sen_idx) for one image, a list of such pairs for a batch."""

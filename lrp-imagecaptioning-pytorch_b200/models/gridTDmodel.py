@@ -264,6 +264,34 @@ class GridTDModel(nn.Module):
             sentence = self.remove_bad_endings([' '.join(rev_word_map[w] for w in sen_idx)])
             return sentence, sen_idx
 
+    def sample(self, images, word_map, caption_lengths, opt={}):
+        """reference :200-242 -> (seq, seq_logprobs, max_length): greedy or multinomial sampling without the LRP
+        weights (the greedy baseline of the self-critical reward in ``trainciderlrp``, train.py:259-261)."""
+        batch_size = images.size(0)
+        sample_method = opt.get('sample_method', 'greedy')
+        temperature = opt.get('temperature', 1.0)
+        max_length = int(max(caption_lengths)) - 1
+        _, image_feature_proj, global_img_feature = self._encode(images)
+        state = self.init_hidden_state(image_feature_proj) + self.init_hidden_state(image_feature_proj)
+        dev = image_feature_proj.device
+        seq = torch.zeros(batch_size, max_length, dtype=torch.long, device=dev)
+        seq_logprobs = torch.zeros(batch_size, max_length, device=dev)
+        it = torch.full((batch_size,), word_map['<start>'], dtype=torch.long, device=dev)
+        unfinished = None
+        for t in range(max_length):
+            xt = torch.cat((state[2], global_img_feature, self.embedding(it)), dim=-1)
+            predict_score_t, _, _, state = self.predict_next_word(image_feature_proj, xt, state)
+            it, sample_logprobs = self.sample_next_word(torch.log_softmax(predict_score_t, dim=-1), sample_method,
+                                                        temperature)
+            finished = it == word_map['<end>']
+            unfinished = ~finished if unfinished is None else unfinished & ~finished
+            it = it * unfinished.type_as(it)
+            seq[:, t] = it
+            seq_logprobs[:, t] = sample_logprobs.view(-1)
+            if int(unfinished.sum()) == 0:
+                break
+        return seq, seq_logprobs, max_length
+
     def beam_search_device(self, imgs, word_map, beam_size=3, max_cap_length=20):
         """``beam_search`` with the whole step loop on the device (lrpx.beam.GridTDBeamSearch: fused step kernels +
         ``lrpx_beam_step`` bookkeeping, one CUDA graph, one read-back) and for B >= 1 images at once.  Same word

@@ -366,8 +366,10 @@ def golden_tune(ns):
     caplens = torch.tensor([L, L - 1])
     with torch.no_grad():
         pred, wpred, maxlen = gm.forwardlrp_context(imgs, caps, caplens, rev)
+        # the greedy baseline of trainciderlrp (train.py:259-261): GridTDModel.sample (:200-242)
+        seq, seq_lp, _ = gm.sample(imgs, wm, torch.tensor([9, 9]))
     save("tune_gridtd", V=V, H=H, E=E, seeds=np.array([71, 72, 73, 74]), caps=caps, caplens=caplens, stop=stop,
-         predictions=pred, weighted_predictions=wpred, max_length=int(maxlen))
+         predictions=pred, weighted_predictions=wpred, max_length=int(maxlen), sample_seq=seq, sample_logprobs=seq_lp)
 
 
 END_BIAS = float(os.environ.get("END_BIAS", "0.17"))   # added to the <end> logit bias of the BU fixtures

@@ -530,3 +530,32 @@ def test_config3_batched_region_features_equals_per_image_api(tmp_path):
             assert_close(r_feat[q] / scale, rf[t][0] / scale, rtol=1e-3, atol=1e-5, what=f"image {b} word {t} r_feat")
             assert_close(r_words[q, :t + 1], rw[t], rtol=1e-3, atol=1e-5, what=f"image {b} word {t} r_words")
             q += 1
+
+
+def test_lrp_cider_tune_step_on_the_real_model():
+    """One trainciderlrp iteration (train.py:252-272) on GridTDModel + VGG16: greedy baseline, sample_lrp with the
+    batched LRP-weight kernel inside, a caller-supplied reward, RewardCriterion, clamp, optimizer step."""
+    from models import gridTDmodel as G
+    from lrpx.tune import LrpCiderTuneStep
+    V, H, E, B = 60, 32, 32, 3
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(601, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(602))
+    model.to(DEV)
+    wm = synth.word_map(V)
+    seen = {}
+
+    def reward_fn(greedy, all_caps, sampled, word_map):
+        seen["shapes"] = (tuple(greedy.shape), tuple(sampled.shape))
+        # toy self-critical reward: +1 for every sampled word that differs from the greedy one, per image
+        r = (sampled != greedy).float().mean(1, keepdim=True) - 0.5
+        return r.expand(-1, sampled.shape[1]).cpu().numpy()
+
+    step = LrpCiderTuneStep(model, wm, reward_fn, lr=1e-3, grad_clip=0.1)
+    before = {k: v.detach().clone() for k, v in model.named_parameters()}
+    torch.manual_seed(0)
+    loss, rew = step.step(synth.images(603, B).to(DEV), None, torch.tensor([7, 7, 7]))
+    assert seen["shapes"] == ((B, 6), (B, 6)) and torch.isfinite(loss) and torch.isfinite(rew)
+    changed = [k for k, v in model.named_parameters() if not torch.equal(before[k], v.detach())]
+    assert any(k.startswith("fc.") for k in changed) and not any("img_encoder" in k for k in changed)
+    assert all(p.grad is None or float(p.grad.abs().max()) <= 0.1 + 1e-9 for p in model.parameters())

@@ -191,3 +191,28 @@ def test_adaptive_explainer_refuses_cpu(tmp_path):
         ex.explainer_forward(torch.zeros(1, 196, 512), torch.zeros(1, 4, dtype=torch.long))
     with pytest.raises(ValueError):
         AA.ExplainAdaptiveAttention(args, synth.word_map(V), model=AA.AdaptiveAttentionCaptioningModel(16, H, V, "vgg16"))
+
+
+def test_sample_greedy_matches_reference_and_reward_criterion(golden):
+    """GridTDModel.sample (the greedy baseline of trainciderlrp, train.py:259-261) on the full VGG16 model against the
+    reference's own output; RewardCriterion (modelutils.py:31-46) against its formula."""
+    from models import gridTDmodel as G
+    from lrpx.tune import RewardCriterion
+    g = golden("tune_gridtd")
+    V, H, E = int(g["V"]), int(g["H"]), int(g["E"])
+    s = g["seeds"].tolist()
+    m = G.GridTDModel(E, H, V, "vgg16")
+    m.load_state_dict(synth.gridtd_decoder_state(s[0], V, H, E), strict=False)
+    m.img_encoder.encoder.load_state_dict(synth.vgg_state(s[1]))
+    m.eval()
+    with torch.no_grad():
+        seq, lp, L = m.sample(synth.images(s[2], 2), synth.word_map(V), torch.tensor([9, 9]))
+    assert L == 8 and torch.equal(seq, g["sample_seq"])
+    assert_close(lp, g["sample_logprobs"], atol=1e-4, what="sample logprobs")
+    gen = torch.Generator().manual_seed(5)
+    logp = -torch.rand(3, 6, generator=gen)
+    seqs = torch.tensor([[4, 7, 0, 0, 0, 0], [3, 3, 3, 3, 3, 3], [0, 0, 0, 0, 0, 0]])
+    reward = torch.randn(3, 1, generator=gen).expand(3, 6)
+    mask = torch.tensor([[1., 1, 1, 0, 0, 0], [1, 1, 1, 1, 1, 1], [1, 0, 0, 0, 0, 0]])
+    want = (-logp * reward * mask).sum() / mask.sum()
+    assert_close(RewardCriterion()(logp, seqs, reward), want, what="reward criterion")
