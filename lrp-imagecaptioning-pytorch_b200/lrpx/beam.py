@@ -34,7 +34,11 @@ class _DeviceBeamSearch:
     # _alloc(R, P, f) -> dict of step tensors; _step(t, w) -> logits tensor name is t["logits"]; _pairs(t) -> gather
     # pairs; _prepare(t, B, k, feats, glob, w)
     def _weights(self):
-        key = tuple((t.data_ptr(), t._version) for t in self._weight_sources())
+        # the captured graphs hold raw pointers: every tensor a step reads belongs to the key, so that a model moved or
+        # re-loaded after the first search gets fresh plans
+        m = self.model
+        key = tuple((t.data_ptr(), t._version) for t in self._weight_sources()) + \
+            tuple(t.data_ptr() for t in (m.embedding.weight, m.fc.weight, m.fc.bias))      # read in place: pointer only
         if self._w_key != key:
             with torch.no_grad():
                 self._w = self._build_weights()

@@ -108,7 +108,7 @@ class LrpCiderTuneStep:
 
     ``reward_fn(greedy_seq, all_caps, sampled_seq, word_map) -> (B, L) array / tensor`` is the caller's scorer — the
     reference's ``get_self_critical_reward`` (modelutils.py:200-238) runs the CIDEr / BLEU scorers of pycocoevalcap on
-    the host, which are outside this path (SURVEY.md §8 out of scope)."""
+    the host, which are outside this path (SURVEY.md §8 out of scope).  Single process, like the reference's loop."""
 
     def __init__(self, model, word_map, reward_fn, optimizer=None, lr=1e-5, grad_clip=None, fix_encoder=True):
         self.model = model
