@@ -147,19 +147,22 @@ __global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict_
 
 // ---------------------------------------------------------------- 2x2/2 max-pool on PF, 8 channels / thread
 // Scan order (0,0),(0,1),(1,0),(1,1); strict '>' so the first maximum wins, NaN wins (max_pool2d_with_indices).
+// IDX = the type of the flat element index: unsigned 32-bit whenever the tensor allows it (64-bit divisions cost
+// ~100 instructions each and there are three per element; with them the kernel ran at 0.6 of the copy bandwidth)
+template <typename IDX>
 __global__ void maxpool2_pf_kernel(const uint4* __restrict__ act, const uint4* __restrict__ gain,
                                    uint4* __restrict__ pooled, uint2* __restrict__ idx, uint4* __restrict__ gpool,
                                    int n, int h, int w, int c8) {
   const int oh = h / 2, ow = w / 2;
   const int wp1 = w + 1, owp1 = ow + 1;
-  const long long blk_f = (long long)(h + 1) * wp1, blk_p = (long long)(oh + 1) * owp1;
-  const long long total = (long long)n * blk_p * c8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int cc = (int)(i % c8);
-    long long prow = i / c8;
-    int img = (int)(prow / blk_p), rem = (int)(prow % blk_p);
-    int a = rem / owp1, b = rem % owp1;
+  const IDX blk_f = (IDX)(h + 1) * wp1, blk_p = (IDX)(oh + 1) * owp1;
+  const IDX total = (IDX)n * blk_p * c8;
+  for (IDX i = blockIdx.x * (IDX)blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
+    const IDX prow = i / (IDX)c8;
+    int cc = (int)(i - prow * c8);
+    const IDX img_ = prow / blk_p;
+    int img = (int)img_, rem = (int)(prow - img_ * blk_p);
+    int a = rem / owp1, b = rem - a * owp1;
     uint4 outv = make_uint4(0, 0, 0, 0), outg = make_uint4(0, 0, 0, 0);
     uint2 pk = make_uint2(0, 0);
     if (a > 0 && b > 0) {
@@ -172,33 +175,39 @@ __global__ void maxpool2_pf_kernel(const uint4* __restrict__ act, const uint4* _
         v[k] = act[off[k]];
         g[k] = gain ? gain[off[k]] : make_uint4(0, 0, 0, 0);
       }
-      const unsigned short* vb[4] = {(const unsigned short*)&v[0], (const unsigned short*)&v[1],
-                                     (const unsigned short*)&v[2], (const unsigned short*)&v[3]};
-      const unsigned short* gb[4] = {(const unsigned short*)&g[0], (const unsigned short*)&g[1],
-                                     (const unsigned short*)&g[2], (const unsigned short*)&g[3]};
-      unsigned short ov[8], og[8];
-      unsigned char bi[8];
+      // everything below indexes registers with compile-time constants only: a run-time index into v[] / g[] (e.g.
+      // v[best_k]) would move both arrays to local memory — measured: 0.6 of the copy bandwidth with that form
+      const uint32_t vw[4][4] = {{v[0].x, v[0].y, v[0].z, v[0].w}, {v[1].x, v[1].y, v[1].z, v[1].w},
+                                 {v[2].x, v[2].y, v[2].z, v[2].w}, {v[3].x, v[3].y, v[3].z, v[3].w}};
+      const uint32_t gw[4][4] = {{g[0].x, g[0].y, g[0].z, g[0].w}, {g[1].x, g[1].y, g[1].z, g[1].w},
+                                 {g[2].x, g[2].y, g[2].z, g[2].w}, {g[3].x, g[3].y, g[3].z, g[3].w}};
+      uint32_t ovw[4], ogw[4], biw[2] = {0u, 0u};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float best = -INFINITY;
-        int bk = 0;
+      for (int wd = 0; wd < 4; ++wd) {                 // word wd holds channels 2*wd (low half) and 2*wd+1 (high half)
+        uint32_t o_v = 0u, o_g = 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float f = __uint_as_float((uint32_t)vb[k][e] << 16);
-          if (f > best || f != f) { best = f; bk = k; }
+        for (int hf = 0; hf < 2; ++hf) {
+          const int sh = 16 * hf;
+          float best = -INFINITY;
+          uint32_t bv = 0u, bg = 0u, bk = 0u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t bits = (vw[k][wd] >> sh) & 0xFFFFu;
+            const float f = __uint_as_float(bits << 16);
+            if (f > best || f != f) { best = f; bv = bits; bg = (gw[k][wd] >> sh) & 0xFFFFu; bk = (uint32_t)k; }
+          }
+          o_v |= bv << sh;
+          o_g |= bg << sh;
+          const int e = 2 * wd + hf;
+          biw[e >> 2] |= bk << (8 * (e & 3));
         }
-        bi[e] = (unsigned char)bk;
-        ov[e] = vb[bk][e];
-        og[e] = gb[bk][e];
+        ovw[wd] = o_v;
+        ogw[wd] = o_g;
       }
-#define PK16(a, b) ((uint32_t)(a) | ((uint32_t)(b) << 16))
-#define PK8(a, b, c, d) ((uint32_t)(a) | ((uint32_t)(b) << 8) | ((uint32_t)(c) << 16) | ((uint32_t)(d) << 24))
-      outv = make_uint4(PK16(ov[0], ov[1]), PK16(ov[2], ov[3]), PK16(ov[4], ov[5]), PK16(ov[6], ov[7]));
-      outg = make_uint4(PK16(og[0], og[1]), PK16(og[2], og[3]), PK16(og[4], og[5]), PK16(og[6], og[7]));
-      pk.x = PK8(bi[0], bi[1], bi[2], bi[3]);
-      pk.y = PK8(bi[4], bi[5], bi[6], bi[7]);
-#undef PK16
-#undef PK8
+      outv = make_uint4(ovw[0], ovw[1], ovw[2], ovw[3]);
+      outg = make_uint4(ogw[0], ogw[1], ogw[2], ogw[3]);
+      pk.x = biw[0];
+      pk.y = biw[1];
     }
     pooled[i] = outv;
     if (idx) idx[i] = pk;
@@ -370,9 +379,14 @@ int lrpx_tc_maxpool2_bf16(const void* act, const void* gain_fine, void* pooled, 
                  "bad argument (h, w even and c % 8 == 0 required)");
   LRPX_CHECK_ARG((gain_fine == nullptr) == (gain_pooled == nullptr), "gain_fine and gain_pooled go together");
   long long total = (long long)n * (h / 2 + 1) * (w / 2 + 1) * (c / 8);
-  maxpool2_pf_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)act, (const uint4*)gain_fine,
-                                                                    (uint4*)pooled, (uint2*)idx, (uint4*)gain_pooled, n,
-                                                                    h, w, c / 8);
+  // 32-bit indices when both the pooled element count and the fine uint4 offsets fit
+  const long long fine = (long long)n * (h + 1) * (w + 1) * (c / 8);
+  if (fine + 2LL * 148 * 64 * 256 < 0xFFFFFFFFLL)
+    maxpool2_pf_kernel<uint32_t><<<grid_for(total), 256, 0, as_stream(stream)>>>(
+        (const uint4*)act, (const uint4*)gain_fine, (uint4*)pooled, (uint2*)idx, (uint4*)gain_pooled, n, h, w, c / 8);
+  else
+    maxpool2_pf_kernel<long long><<<grid_for(total), 256, 0, as_stream(stream)>>>(
+        (const uint4*)act, (const uint4*)gain_fine, (uint4*)pooled, (uint2*)idx, (uint4*)gain_pooled, n, h, w, c / 8);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;
 }

@@ -9,6 +9,7 @@ PCMD="python bench.py --profile-step --no-graph"
 timeout 900 $PCMD > gpurun_out/plain.log 2>&1 &&
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches.csv $PCMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list exit $?"
+[ -n "$SKIP_FULL" ] && exit 0          # launch list only
 timeout 900 $PCMD > gpurun_out/plain2.log 2>&1 &&
 timeout 1800 ncu --set full --clock-control none -k regex:tc_conv_slab -s ${NCU_SKIP:-82} -c ${NCU_COUNT:-13} -o gpurun_out/prof_chain $PCMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
