@@ -378,6 +378,63 @@ __global__ void __launch_bounds__(512) grid_attn_rows_kernel(lrpx_gridtd_args a,
   }
   for (int k = threadIdx.x; k < (t + 1) * H; k += blockDim.x) u_s[k] = w.uctx[(size_t)q * a.T * H + k];
   __syncthreads();
+  if ((H & 3) == 0) {
+    // four hidden units per thread: per step one LDS.128 of uctx and one of the alphas feed 16 FMAs, A / A_pre come in
+    // 16-byte loads and the results leave as 8- or 16-byte stores (one unit per thread meant 2-byte stores of the split
+    // operand: 0.26 of the copy bandwidth in profiles/r1_hbm_kernels.md)
+    for (int h4 = threadIdx.x * 4; h4 < H; h4 += blockDim.x * 4) {
+      for (int p0 = 0; p0 < P; p0 += 4) {
+        float4 Av[4], Ap[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool ok = p0 + k < P;
+          const size_t o0 = ((size_t)b * P + (ok ? p0 + k : 0)) * H + h4;
+          Av[k] = ok ? __ldg(reinterpret_cast<const float4*>(a.A + o0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          Ap[k] = ok ? __ldg(reinterpret_cast<const float4*>(a.A_pre + o0)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+        for (int i = t; i >= 0; --i) {
+          const float4 uv = *reinterpret_cast<const float4*>(u_s + i * H + h4);
+          const float4 a4 = *reinterpret_cast<const float4*>(al_s + i * P4 + p0);
+          const float al[4] = {a4.x, a4.y, a4.z, a4.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[k][j] = fmaf(al[k], uu[j], acc[k][j]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (p0 + k >= P) break;
+          const size_t row = (size_t)q * P + p0 + k;
+          const float av[4] = {Av[k].x, Av[k].y, Av[k].z, Av[k].w}, ap[4] = {Ap[k].x, Ap[k].y, Ap[k].z, Ap[k].w};
+          if (SPLIT) {
+            uint32_t hi2[2], lo2[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(__fdividef(acc[k][2 * j] * av[2 * j], stab(ap[2 * j])), h0, l0);
+              split_bf16(__fdividef(acc[k][2 * j + 1] * av[2 * j + 1], stab(ap[2 * j + 1])), h1, l1);
+              hi2[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              lo2[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            __nv_bfloat16* o = w.a3 + row * 3 * H + h4;
+            *reinterpret_cast<uint2*>(o) = make_uint2(hi2[0], hi2[1]);
+            *reinterpret_cast<uint2*>(o + H) = make_uint2(hi2[0], hi2[1]);
+            *reinterpret_cast<uint2*>(o + 2 * H) = make_uint2(lo2[0], lo2[1]);
+          } else {
+            *reinterpret_cast<float4*>(w.wproj + row * H + h4) =
+                make_float4(acc[k][0] * av[0] / stab(ap[0]), acc[k][1] * av[1] / stab(ap[1]),
+                            acc[k][2] * av[2] / stab(ap[2]), acc[k][3] * av[3] / stab(ap[3]));
+          }
+        }
+      }
+    }
+    return;
+  }
   for (int h = threadIdx.x; h < H; h += blockDim.x) {
     for (int p0 = 0; p0 < P; p0 += 4) {
       float Av[4], Ap[4];
@@ -877,7 +934,8 @@ int lrpx_gridtd_decoder_lrp_f32(const lrpx_gridtd_args* a, void* workspace, size
   GemmEpi fe{a->feat, nullptr, w.coefavg, a->req_img, a->P};
   const size_t att_smem = (size_t)T * (((a->P + 3) & ~3) + H) * sizeof(float);
   if (att_smem <= 160 * 1024) {
-    const int at = H >= 512 ? 512 : (H >= 256 ? 256 : 128);
+    int at = H >= 512 ? 512 : (H >= 256 ? 256 : 128);
+    if ((H & 3) == 0) at = H / 4 >= 512 ? 512 : ((H / 4 + 31) & ~31);        // four hidden units per thread
     static bool attr_done = false;
     if (!attr_done) {
       cudaFuncSetAttribute(grid_attn_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

@@ -22,3 +22,9 @@ print("MARK")
 for _ in range(3):
     ops.gridtd_decoder_lrp(st, W, req_img, req_t, req_word, tc_gemm=True)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    ops.gridtd_decoder_lrp(st, W, req_img, req_t, req_word, tc_gemm=True)
+e1.record(); torch.cuda.synchronize()
+print(f"gridtd_decoder_lrp, 1216 requests, eager launches: {e0.elapsed_time(e1) / 10:.3f} ms")
