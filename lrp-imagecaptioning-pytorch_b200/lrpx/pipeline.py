@@ -122,7 +122,34 @@ class BatchExplainer:
             # everything the captured kernels point at must outlive the graph (incl. the request index tensors)
             g = self._graphs[key] = (graph, s_imgs, s_toks, heat, r_words, req_img, req_t)
         graph, s_imgs, s_toks, heat, r_words = g[:5]
-        s_imgs.copy_(imgs, non_blocking=True)
+        if imgs.is_cuda:
+            s_imgs.copy_(imgs, non_blocking=True)
+        else:
+            self._stage_host_images(imgs, s_imgs)
         s_toks.copy_(tokens, non_blocking=True)
         graph.replay()
         return heat, r_words
+
+    def _stage_host_images(self, imgs, s_imgs):
+        """Host images reach the graph's static input through one of two device staging buffers: the host->device copy
+        runs on a side stream as soon as the call is made — i.e. under the kernels of the PREVIOUS step, which are still
+        executing when the host has run ahead — and the main stream only pays a device-to-device copy.  A staging buffer
+        is reused two calls later, after the event behind its last device-to-device copy."""
+        key = tuple(s_imgs.shape)
+        st = getattr(self, "_stage", None)
+        if st is None or st["key"] != key:
+            st = self._stage = dict(key=key, bufs=[torch.empty_like(s_imgs) for _ in range(2)],
+                                    done=[None, None], n=0, stream=torch.cuda.Stream())
+        k = st["n"] & 1
+        st["n"] += 1
+        main, side = torch.cuda.current_stream(), st["stream"]
+        if st["done"][k] is not None:
+            side.wait_event(st["done"][k])                  # the buffer's previous contents have been consumed
+        with torch.cuda.stream(side):
+            st["bufs"][k].copy_(imgs, non_blocking=True)
+            arrived = torch.cuda.Event()
+            arrived.record(side)
+        main.wait_event(arrived)
+        s_imgs.copy_(st["bufs"][k], non_blocking=True)
+        st["done"][k] = torch.cuda.Event()
+        st["done"][k].record(main)

@@ -559,3 +559,36 @@ def test_lrp_cider_tune_step_on_the_real_model():
     changed = [k for k, v in model.named_parameters() if not torch.equal(before[k], v.detach())]
     assert any(k.startswith("fc.") for k in changed) and not any("img_encoder" in k for k in changed)
     assert all(p.grad is None or float(p.grad.abs().max()) <= 0.1 + 1e-9 for p in model.parameters())
+
+
+def test_batch_pipeline_host_buffers_back_to_back(tmp_path):
+    """The end-to-end form of BatchExplainer.explain (pinned host images in, pinned host heat-maps out, graph replay,
+    host->device copies staged under the previous step): consecutive calls with DIFFERENT inputs, issued without
+    synchronising in between, each deliver their own results."""
+    from models import gridTDmodel as G
+    from lrpx.pipeline import BatchExplainer
+    V, H, E, B, T = 60, 64, 32, 2, 3
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(701, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(702))
+    model.to(DEV).eval()
+    ex = G.ExplainGridTDAttention(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="bf16")
+    toks = torch.stack([torch.tensor(synth.tokens(704 + b, T, V)) for b in range(B)])
+    inputs = [synth.images(710 + n, B).pin_memory() for n in range(4)]
+    eager = BatchExplainer(ex, chunk=4, use_graph=False)
+    want = [tuple(t.clone() for t in eager.explain(x.to(DEV), toks.to(DEV))) for x in inputs]
+    pipe = BatchExplainer(ex, chunk=4, use_graph=True)
+    outs = [(torch.empty(B * T, 3, 224, 224).pin_memory(), torch.empty(B * T, T).pin_memory()) for _ in inputs]
+    toks_h = toks.pin_memory()
+    for x, o in zip(inputs, outs):                       # first round: builds one graph per output buffer pair
+        pipe.explain(x, toks_h, host_out=o)
+    torch.cuda.synchronize()
+    for n, ((heat, words), (wh, ww)) in enumerate(zip(outs, want)):
+        assert torch.equal(heat, wh.cpu()), n
+        assert torch.equal(words, ww.cpu()), n
+    for x, o in zip(reversed(inputs), outs):             # second round: replays only, no synchronisation in between
+        pipe.explain(x, toks_h, host_out=o)
+    torch.cuda.synchronize()
+    for n, ((heat, words), (wh, ww)) in enumerate(zip(outs, reversed(want))):
+        assert torch.equal(heat, wh.cpu()), n
+        assert torch.equal(words, ww.cpu()), n
