@@ -316,6 +316,26 @@ typedef struct {
 
 int lrpx_block_image_f32(const lrpx_block_image_args* args, void* stream);
 
+/* Bounding-box correctness of an explanation (EvaluationExperiments._calculate_overlaped_pixels + _project_maxabs,
+ * evaluation.py:310-342, as bbox_experiment applies them, :398-431), batched over Q requests:
+ *   m = maxabs-normalised mean over the channels of max(sign * heat, 0); for every threshold: m[m <= thr] = 0;
+ *   ratio = min(1, sum(m inside the box) / sum(m)), 0 when sum(m) == 0.        Boxes are (x0, y0, x1, y1), ends exclusive. */
+typedef struct {
+  int Q, C, H, W;
+  int n_thr, max_boxes;    /* max_boxes <= 8 */
+  float sign;              /* +1, or -1 for the 'neg' explanation types (:398-401) */
+  int inplace_quirk;       /* 1: like the reference, whose thresholding mutates the map (:324-326), every (box, threshold)
+                              pair in bbox_experiment's loop order (:419-431) sees the largest threshold applied before
+                              it; 0: every pair is evaluated on the fresh map */
+  const float* heat;       /* (Q,C,H,W) */
+  const float* thresholds; /* (n_thr)   evaluation.py:425 uses 0, 0.1, ..., 0.9 */
+  const int32_t* boxes;    /* (Q,max_boxes,4) */
+  const int32_t* n_boxes;  /* (Q) boxes in use per request, NULL = max_boxes */
+  float* ratio;            /* (Q,max_boxes,n_thr); unused box slots are set to 0 */
+} lrpx_bbox_args;
+
+int lrpx_bbox_ratio_f32(const lrpx_bbox_args* args, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Explainer forward (the producer of the saved state above): fused element-wise steps of
  * ExplainGridTDAttention.get_hidden_parameters (gridTDmodel.py:933-1012).  Row strides ("ld_*", in

@@ -100,6 +100,84 @@ __global__ void __launch_bounds__(ABL_THREADS) block_image_kernel(lrpx_block_ima
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bounding-box correctness (evaluation.py:310-335, :403-405, :425-431), batched over requests: the share of the
+// (thresholded) positive relevance that falls inside a box.  One block per request; the normalised map lives in shared
+// memory, so the heat-map is read from HBM once (algorithmic bytes = the heat-map).
+// ------------------------------------------------------------------------------------------------
+constexpr int BBOX_MAX_BOXES = 8;
+
+__device__ __forceinline__ float abl_block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = 0.f;
+  for (int w = 0; w < ABL_THREADS / 32; ++w) v += red[w];
+  return v;
+}
+
+__global__ void __launch_bounds__(ABL_THREADS) bbox_ratio_kernel(lrpx_bbox_args a) {
+  extern __shared__ float s_map[];                 // [H*W] max-abs-normalised positive relevance
+  __shared__ float s_red[ABL_THREADS / 32];
+  const int q = blockIdx.x, hw = a.H * a.W;
+  const float* heat = a.heat + (size_t)q * a.C * hw;
+  // np.mean(np.maximum(sign * relevance, 0), axis=(0, 1))   (:398-404)
+  float mx = 0.f;
+  for (int p = threadIdx.x; p < hw; p += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < a.C; ++c) acc += fmaxf(a.sign * heat[(size_t)c * hw + p], 0.f);
+    acc /= (float)a.C;
+    s_map[p] = acc;
+    mx = fmaxf(mx, acc);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = s_red[0];
+  for (int w = 1; w < ABL_THREADS / 32; ++w) mx = fmaxf(mx, s_red[w]);
+  __syncthreads();
+  // _project_maxabs (:337-342): all zeros when the map is zero
+  for (int p = threadIdx.x; p < hw; p += blockDim.x) s_map[p] = mx > 0.f ? s_map[p] / mx : 0.f;
+  __syncthreads();
+  const int nb = min(a.n_boxes ? a.n_boxes[q] : a.max_boxes, a.max_boxes);
+  __shared__ int bx[BBOX_MAX_BOXES][4];
+  if (threadIdx.x < BBOX_MAX_BOXES * 4)
+    bx[threadIdx.x >> 2][threadIdx.x & 3] =
+        (int)(threadIdx.x >> 2) < nb ? a.boxes[((size_t)q * a.max_boxes + (threadIdx.x >> 2)) * 4 + (threadIdx.x & 3)] : 0;
+  __syncthreads();
+  // Loop order of bbox_experiment (:419-431): boxes outer, thresholds inner.  _calculate_overlaped_pixels zeroes the
+  // map IN PLACE (:324-326), so with `inplace_quirk` every later (box, threshold) pair sees the map already cut at the
+  // largest threshold applied before it — the effective threshold is the running maximum in loop order.
+  float eff = -INFINITY;
+  for (int jb = 0; jb < nb; ++jb) {
+    const int x0 = bx[jb][0], y0 = bx[jb][1], x1 = bx[jb][2], y1 = bx[jb][3];
+    for (int t = 0; t < a.n_thr; ++t) {
+      const float thr = a.thresholds[t];
+      eff = a.inplace_quirk ? fmaxf(eff, thr) : thr;
+      float tot = 0.f, cor = 0.f;
+      for (int p = threadIdx.x; p < hw; p += blockDim.x) {
+        const float m = s_map[p];
+        const float v = m <= eff ? 0.f : m;                        // relevance[relevance <= threshold] = 0 (:324-326)
+        const int y = p / a.W, x = p - y * a.W;
+        tot += v;
+        if (x >= x0 && x < x1 && y >= y0 && y < y1) cor += v;       // bbox_mask[y0:y1, x0:x1] = 1 (:321-322)
+      }
+      tot = abl_block_sum(tot, s_red);
+      cor = abl_block_sum(cor, s_red);
+      if (threadIdx.x == 0) {
+        const float r = tot == 0.f ? 0.f : cor / tot;               // :327-334
+        a.ratio[((size_t)q * a.max_boxes + jb) * a.n_thr + t] = r > 1.f ? 1.f : r;
+      }
+    }
+  }
+  // unused box slots (contiguous behind the used ones) report 0
+  for (int k = threadIdx.x; k < (a.max_boxes - nb) * a.n_thr; k += blockDim.x)
+    a.ratio[((size_t)q * a.max_boxes + nb) * a.n_thr + k] = 0.f;
+}
+
 }  // namespace lrpx
 
 using namespace lrpx;
@@ -115,6 +193,25 @@ extern "C" int lrpx_block_image_f32(const lrpx_block_image_args* a, void* stream
   LRPX_CHECK_ARG(a->heat && (a->mask || a->masked), "null pointer");
   LRPX_CHECK_ARG(!a->masked || (a->images && a->img_c > 0), "masked output needs the images");
   block_image_kernel<<<a->Q, ABL_THREADS, (size_t)np * (1 + a->C) * sizeof(float), as_stream(stream)>>>(*a);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+extern "C" int lrpx_bbox_ratio_f32(const lrpx_bbox_args* a, void* stream) {
+  LRPX_CHECK_ARG(a, "null args");
+  LRPX_CHECK_ARG(a->Q >= 0 && a->C > 0 && a->H > 0 && a->W > 0 && a->n_thr > 0 && a->n_thr <= ABL_THREADS &&
+                     a->max_boxes > 0 && a->max_boxes <= BBOX_MAX_BOXES,
+                 "bad shape (at most 8 boxes per request)");
+  const size_t smem = (size_t)a->H * a->W * sizeof(float);
+  LRPX_CHECK_ARG(smem <= 200 * 1024, "H * W too large for the shared-memory map (at most 51200 pixels)");
+  if (a->Q == 0) return LRPX_OK;
+  LRPX_CHECK_ARG(a->heat && a->thresholds && a->boxes && a->ratio, "null pointer");
+  cudaError_t e = cudaFuncSetAttribute(bbox_ratio_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) {
+    set_error("lrpx_bbox_ratio_f32: %s", cudaGetErrorString(e));
+    return LRPX_E_CUDA;
+  }
+  bbox_ratio_kernel<<<a->Q, ABL_THREADS, smem, as_stream(stream)>>>(*a);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;
 }

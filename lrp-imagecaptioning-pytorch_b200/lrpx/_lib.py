@@ -101,6 +101,11 @@ class BlockImageArgs(C.Structure):
                [(n, _P) for n in ("heat", "images", "req_img", "mask", "masked")]
 
 
+class BboxArgs(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("Q", "C", "H", "W", "n_thr", "max_boxes")] + [("sign", C.c_float), ("inplace_quirk", C.c_int)] + \
+               [(n, _P) for n in ("heat", "thresholds", "boxes", "n_boxes", "ratio")]
+
+
 # every symbol include/lrpx.h declares: name -> (restype, argtypes)
 _i, _f, _sz = C.c_int, C.c_float, C.c_size_t
 SYMBOLS = {
@@ -129,6 +134,7 @@ SYMBOLS = {
     "lrpx_beam_step": (_i, [C.POINTER(BeamArgs), _P]),
     "lrpx_beam_gather_f32": (_i, [C.POINTER(BeamGatherArgs), _P]),
     "lrpx_block_image_f32": (_i, [C.POINTER(BlockImageArgs), _P]),
+    "lrpx_bbox_ratio_f32": (_i, [C.POINTER(BboxArgs), _P]),
     "lrpx_lstm_cell_f32": (_i, [C.POINTER(LstmCellArgs), _P]),
     "lrpx_adaptive_attention_f32": (_i, [C.POINTER(AdaAttentionArgs), _P]),
     "lrpx_lstm_prep_weights_f32": (_i, [_P, _P, _i, _i, _i, _P]),

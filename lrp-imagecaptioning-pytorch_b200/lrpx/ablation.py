@@ -10,7 +10,8 @@
 
 Here every stage runs once for ALL requests: ``lrpx_block_image_f32`` writes the masked images, the tensor-core encoder
 and the device beam search (lrpx.beam) caption them in chunks, and one batched explainer forward per experiment yields
-the teacher-forced scores.  The word filters of the reference (object-word list, stop words, t >= 1 / t >= 6) are the
+the teacher-forced scores; ``lrpx_bbox_ratio_f32`` scores every heat-map against its bounding boxes
+(``bbox_experiment``, :344-447).  The word filters of the reference (object-word list, stop words, t >= 1 / t >= 6) are the
 caller's choice of requests.
 """
 import torch
@@ -90,6 +91,17 @@ class AblationExperiments:
                 new = self._teacher_forced_scores(feat[idx], prefixes, [words[q] for q in keep])
                 score_diff[idx] = orig[idx] - new
         return dict(disappear=disappear, score_diff=score_diff, captions=caps, masked=masked)
+
+    # ------------------------------------------------------------------ evaluation.py:344-447
+    def bbox_correctness(self, heat, boxes, n_boxes=None, thresholds=(0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9),
+                         negative=False, inplace_quirk=True):
+        """The pointing-game style score of ``bbox_experiment``: heat (Q,3,H,W), boxes (Q,nb,4) int (x0,y0,x1,y1) already
+        scaled to the network's input size (:420-424) -> (Q, n_thr): per threshold the best share over the request's
+        boxes of the positive relevance that lies inside a box (the reference keeps the maximum over the boxes of a
+        category, :428-429).  ``inplace_quirk`` reproduces the reference's in-place thresholding (see ops.bbox_ratio)."""
+        ratio = ops.bbox_ratio(heat, boxes, n_boxes=n_boxes, thresholds=thresholds, negative=negative,
+                               inplace_quirk=inplace_quirk)
+        return ratio.max(1).values
 
     # ------------------------------------------------------------------ evaluation.py:234-262
     def word_ablation(self, feat, tokens, r_words, req_img, req_t, pred):

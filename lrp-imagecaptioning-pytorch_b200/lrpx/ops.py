@@ -471,3 +471,25 @@ def block_image(heat, k=20, patch=8, images=None, req_img=None, want_mask=True):
         a.masked = masked.data_ptr()
     check(lib().lrpx_block_image_f32(C.byref(a), _stream()), "lrpx_block_image_f32")
     return (mask, masked) if images is not None else mask
+
+
+def bbox_ratio(heat, boxes, n_boxes=None, thresholds=(0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9), negative=False,
+               inplace_quirk=True):
+    """lrpx_bbox_ratio_f32 (evaluation.py:310-342 as applied by bbox_experiment :398-431): heat (Q,C,H,W), boxes
+    (Q,nb,4) int (x0,y0,x1,y1), n_boxes (Q,) or None -> ratio (Q,nb,n_thr): share of the thresholded, max-abs normalised
+    positive (``negative``: negative) relevance inside each box.  ``inplace_quirk`` (default, = the reference): the
+    reference thresholds its map in place, so after the first box every pair sees the largest threshold used so far."""
+    heat = _f32(heat, "heat")
+    dev = heat.device
+    Q, Cc, H, W = heat.shape
+    boxes = boxes.to(device=dev, dtype=torch.int32).contiguous()
+    thr = torch.tensor(list(thresholds), dtype=torch.float32, device=dev)
+    a = _lib.BboxArgs(Q=Q, C=Cc, H=H, W=W, n_thr=int(thr.numel()), max_boxes=int(boxes.shape[1]),
+                      sign=-1.0 if negative else 1.0, inplace_quirk=1 if inplace_quirk else 0)
+    ratio = torch.empty(Q, boxes.shape[1], thr.numel(), device=dev, dtype=torch.float32)
+    a.heat, a.thresholds, a.boxes, a.ratio = heat.data_ptr(), thr.data_ptr(), boxes.data_ptr(), ratio.data_ptr()
+    if n_boxes is not None:
+        n_boxes = n_boxes.to(device=dev, dtype=torch.int32).contiguous()
+        a.n_boxes = n_boxes.data_ptr()
+    check(lib().lrpx_bbox_ratio_f32(C.byref(a), _stream()), "lrpx_bbox_ratio_f32")
+    return ratio

@@ -319,6 +319,22 @@ def golden_block_image(ns):
     with quiet():
         out["small_masks"] = torch.stack([exp.block_image(torch.mean(small[q:q + 1], dim=(0, 1)))
                                           for q in range(3)]).to(torch.uint8)
+    # bounding-box correctness: _project_maxabs + _calculate_overlaped_pixels as bbox_experiment applies them
+    # (evaluation.py:403-405, :425-431) on the same heat-maps, three boxes each, ten thresholds
+    boxes = synth.bbox_inputs(72, heat.shape[0])
+    thresholds = [0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9]
+    ratios = np.zeros((heat.shape[0], boxes.shape[1], len(thresholds)))
+    ratios_neg = np.zeros_like(ratios)
+    for q in range(heat.shape[0]):
+        for neg, dst in ((False, ratios), (True, ratios_neg)):
+            rel = heat[q:q + 1].numpy().copy()
+            if neg:
+                rel = -1 * rel                                                      # :398-401
+            rel = exp._project_maxabs(np.mean(np.maximum(rel, 0), axis=(0, 1)))    # :403-405
+            for j, box in enumerate(boxes[q].tolist()):
+                for t, thr in enumerate(thresholds):
+                    dst[q, j, t] = exp._calculate_overlaped_pixels(box, rel, thr)   # mutates rel like the reference loop
+    out.update(bbox_seed=np.array(72), thresholds=np.array(thresholds), ratios=ratios, ratios_neg=ratios_neg)
     save("block_image", **out)
 
 

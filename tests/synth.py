@@ -206,3 +206,13 @@ def block_image_inputs(seed: int = 71):
     heat[5] = heat[5].abs()                                # non-negative map
     small = torch.randn(3, 3, 32, 48, generator=g)
     return heat, small
+
+
+def bbox_inputs(seed: int, n: int, n_boxes: int = 3, size: int = 224) -> torch.Tensor:
+    """(n, n_boxes, 4) int boxes (x0, y0, x1, y1) inside a size x size image; the last box of image 0 is empty."""
+    g = _gen(seed)
+    lo = torch.randint(0, size - 40, (n, n_boxes, 2), generator=g)
+    ext = torch.randint(8, 120, (n, n_boxes, 2), generator=g)
+    b = torch.cat([lo, (lo + ext).clamp(max=size)], -1)
+    b[0, -1, 2] = b[0, -1, 0]
+    return b

@@ -50,7 +50,7 @@ def test_struct_layout_matches_header(tmp_path):
              ("lrpx_tc_conv_args", _lib.TcConvArgs), ("lrpx_gridtd_args", _lib.GridTDArgs),
              ("lrpx_aoa_args", _lib.AoaArgs), ("lrpx_adaptive_args", _lib.AdaptiveArgs),
              ("lrpx_beam_args", _lib.BeamArgs), ("lrpx_beam_gather_args", _lib.BeamGatherArgs),
-             ("lrpx_block_image_args", _lib.BlockImageArgs),
+             ("lrpx_block_image_args", _lib.BlockImageArgs), ("lrpx_bbox_args", _lib.BboxArgs),
              ("lrpx_lstm_cell_args", _lib.LstmCellArgs),
              ("lrpx_ada_attention_args", _lib.AdaAttentionArgs)]
     gcc = shutil.which("gcc")

@@ -44,6 +44,33 @@ def test_block_image_masks_bit_exact_vs_reference(golden):
         ops.block_image(small[:, :, :30].contiguous().to(DEV), 5, patch)   # H not a multiple of the patch size (:59)
 
 
+def test_bbox_ratio_vs_reference(golden):
+    """lrpx_bbox_ratio_f32 against the values the reference's _project_maxabs / _calculate_overlaped_pixels returned
+    (fixture block_image), positive and negative relevance, ragged box counts."""
+    from lrpx import ops
+    g = golden("block_image")
+    heat, _ = synth.block_image_inputs(int(g["seed"]))
+    boxes = synth.bbox_inputs(int(g["bbox_seed"]), heat.shape[0])
+    thr = g["thresholds"].tolist()
+    got = ops.bbox_ratio(heat.to(DEV), boxes, thresholds=thr)
+    neg = ops.bbox_ratio(heat.to(DEV), boxes, thresholds=thr, negative=True)
+    assert float((got.cpu().double() - g["ratios"]).abs().max()) <= 1e-5
+    assert float((neg.cpu().double() - g["ratios_neg"]).abs().max()) <= 1e-5
+    assert float(got[0, -1].abs().max()) == 0.0                       # the empty box
+    nb = torch.tensor([3, 1, 2, 0, 3, 2], dtype=torch.int32)
+    rag = ops.bbox_ratio(heat.to(DEV), boxes, n_boxes=nb, thresholds=thr)
+    for q in range(6):
+        assert torch.equal(rag[q, :int(nb[q])], got[q, :int(nb[q])]) and float(rag[q, int(nb[q]):].abs().sum()) == 0.0
+    # every pair on the fresh map (inplace_quirk=False): box 0 as in the reference, the others vs the oracle
+    fresh = ops.bbox_ratio(heat.to(DEV), boxes, thresholds=thr, inplace_quirk=False)
+    for q in range(6):
+        want = O.bbox_ratio(heat[q:q + 1].double(), boxes[q].tolist(), thr, inplace_quirk=False)
+        assert float((fresh[q].cpu().double() - want).abs().max()) <= 1e-5
+    assert torch.equal(fresh[:, 0], got[:, 0])
+    zero = ops.bbox_ratio(torch.zeros(1, 3, 224, 224, device=DEV), boxes[:1], thresholds=thr)
+    assert float(zero.abs().max()) == 0.0                              # total relevance 0 -> 0 (:328-329)
+
+
 def test_batched_ablation_equals_per_request_walk(tmp_path):
     """B images x T words on GridTDModel + VGG16 (bf16 chain): explain, then the image ablation and the word ablation
     for all requests at once == one request at a time with the mirror's host-side beam_search / teacherforce_forward
