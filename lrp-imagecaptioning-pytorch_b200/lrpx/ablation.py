@@ -103,6 +103,22 @@ class AblationExperiments:
                                inplace_quirk=inplace_quirk)
         return ratio.max(1).values
 
+    # ------------------------------------------------------------------ evaluation.py:449-547
+    @staticmethod
+    def tpfp_statistics(heat, n_quantiles=100):
+        """The per-word statistics ``tpfp_experiment`` records for true-/false-positive words (:503-513): of the channel
+        mean of each heat-map (Q,3,H,W) -> dict of (Q,) tensors ``mean``, ``mean_abs``, ``mean_pos`` (sum of the positive
+        part / number of positive pixels, 0 if none), ``max`` and ``quantile`` (Q, n_quantiles) at i/100 (numpy's default
+        linear interpolation).  Device tensor ops (one sort per request); whether a word counts as TP or FP — membership
+        in the reference captions' vocabulary, :469-470 — is the caller's bookkeeping."""
+        m = heat.float().mean(1).flatten(1)                                        # np.mean(axis=(0,1)) -> (H*W)
+        npos = (m > 0).sum(1)
+        pos = m.clamp(min=0).sum(1)
+        q = torch.arange(n_quantiles, device=m.device, dtype=m.dtype) / 100.0
+        return dict(mean=m.mean(1), mean_abs=m.abs().mean(1),
+                    mean_pos=torch.where(npos > 0, pos / npos.clamp(min=1), torch.zeros_like(pos)),
+                    max=m.max(1).values, quantile=torch.quantile(m, q, dim=1).t().contiguous())
+
     # ------------------------------------------------------------------ evaluation.py:234-262
     def word_ablation(self, feat, tokens, r_words, req_img, req_t, pred):
         """feat (B,P,C) encoder features, r_words (Q,T) linguistic relevance of each request (entry 0 = <start>).

@@ -71,6 +71,22 @@ def test_bbox_ratio_vs_reference(golden):
     assert float(zero.abs().max()) == 0.0                              # total relevance 0 -> 0 (:328-329)
 
 
+def test_tpfp_statistics_vs_numpy():
+    """evaluation.py:503-513 per request with numpy (the reference's own calls) vs the batched device form."""
+    import numpy as np
+    from lrpx.ablation import AblationExperiments
+    heat, _ = synth.block_image_inputs(71)
+    heat[3] = -heat[3].abs()                                            # a map without positive pixels: mean_pos = 0
+    st = AblationExperiments.tpfp_statistics(heat.to(DEV))
+    qp = [i / 100 for i in range(0, 100)]
+    for q in range(heat.shape[0]):
+        r = np.mean(heat[q:q + 1].numpy(), axis=(0, 1))
+        mean_pos = 0 if np.sum(r > 0) == 0 else np.sum(np.maximum(r, 0)) / np.sum(r > 0)
+        for key, want in (("mean", np.mean(r)), ("mean_abs", np.mean(np.abs(r))), ("mean_pos", mean_pos), ("max", np.max(r))):
+            assert abs(float(st[key][q]) - float(want)) <= 1e-5 * abs(float(want)) + 1e-7, (q, key)
+        assert np.allclose(st["quantile"][q].cpu().numpy(), np.quantile(r, qp), rtol=1e-5, atol=1e-7), q
+
+
 def test_batched_ablation_equals_per_request_walk(tmp_path):
     """B images x T words on GridTDModel + VGG16 (bf16 chain): explain, then the image ablation and the word ablation
     for all requests at once == one request at a time with the mirror's host-side beam_search / teacherforce_forward
