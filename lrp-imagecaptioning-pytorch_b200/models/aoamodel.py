@@ -341,45 +341,68 @@ class ExplainAOAAttention(ExplainGridTDAttention):
             self._weights = _dec.aoa_weights({k: v.detach() for k, v in self.model.state_dict().items()})
         return self._weights
 
+    def _explainer_weights(self, quirk_double_bias_ih=True):
+        """Recurrent weights in the step kernel's layout, input-side weights and summed biases; cached until a
+        parameter changes."""
+        L = self.model.LanguageLSTM
+        src = [L.weight_ih, L.weight_hh, L.bias_ih, L.bias_hh]
+        key = (quirk_double_bias_ih,) + tuple((t.data_ptr(), t._version) for t in src)
+        if getattr(self, "_expl_w_key", None) != key:
+            with torch.no_grad():
+                lb2 = L.bias_ih if quirk_double_bias_ih else L.bias_hh                    # Q3 (:873)
+                self._expl_w = (ops.lstm_prep_weights(L.weight_hh.t().contiguous(), 4), L.weight_ih.t().contiguous(),
+                                (L.bias_ih + lb2).contiguous())
+            self._expl_w_key = key
+        return self._expl_w
+
     def explainer_forward(self, feat, tokens, quirk_double_bias_ih=True):
         """The explainer's teacher-forced forward (reference :999-1062) batched over images; returns the saved
-        state in the layout of lrpx_aoa_args.  Q3: the LSTM adds bias_ih twice (:873)."""
+        state in the layout of lrpx_aoa_args.  Q3: the LSTM adds bias_ih twice (:873).
+
+        The AoA decoder feeds nothing of the attention back into its LSTM (x_t = [emb_t | glob], :1030), so only the
+        recurrence is sequential: T launches of ``lrpx_lstm_step_f32`` writing h, c, g, i, f straight into the (B,T,.)
+        state tensors (the input-side half of the gates is one GEMM over all steps), then query projection, 8-head
+        attention, AoA gate / linear and the vocabulary projection ONCE over all B*T positions.  CUDA only
+        (tests/helpers.py holds the step-by-step tensor-op restatement this is checked against)."""
+        if not feat.is_cuda:
+            raise ops._lib.LrpxError("explainer_forward needs CUDA tensors: lrpx has no CPU fallback")
         m = self.model
         B, P, C = feat.shape
-        H = m.hidden_dim
+        H, E = m.hidden_dim, m.embed_dim
         T = tokens.shape[1] - 1
         nh, dk = m.num_head, H // m.num_head
+        dev = feat.device
         with torch.no_grad():
+            feat = feat.contiguous()
             Wp = m.img_projector.weight.reshape(H, C)
-            A_pre = feat @ Wp.t() + m.img_projector.bias
+            A_pre = torch.addmm(m.img_projector.bias, feat.view(B * P, C), Wp.t()).view(B, P, H)
             A = A_pre.clamp(min=0)
             glob = A.mean(1)
             key, value = m.decoder_k_proj(A), m.decoder_v_proj(A)
-            kh = key.view(B, P, nh, dk).transpose(1, 2)
-            vh = value.view(B, P, nh, dk).transpose(1, 2)
+            kT = key.view(B, P, nh, dk).permute(0, 2, 3, 1)                      # (B,nh,dk,P)
+            vh = value.view(B, P, nh, dk).transpose(1, 2)                        # (B,nh,P,dk)
             mha = m.decoder_multihead_attention
-            L = m.LanguageLSTM
-            lb2 = L.bias_ih if quirk_double_bias_ih else L.bias_hh
-            zeros = feat.new_zeros(B, H)
-            h, c = [zeros], [zeros]
-            keys = ["x", "g", "i", "f", "ctx", "caoa", "caoa_lin", "caoa_gate", "alpha", "pred"]
-            seq = {k: [] for k in keys}
+            Wp_hh, W_in, b = self._explainer_weights(quirk_double_bias_ih)
+            x = torch.cat((m.embedding(tokens[:, :T]), glob.unsqueeze(1).expand(B, T, H)), -1).contiguous()   # (B,T,E+H)
+            pre = torch.addmm(b, x.transpose(0, 1).reshape(T * B, E + H), W_in).view(T, B, 4 * H)
+            h, c = torch.zeros(B, T + 1, H, device=dev), torch.zeros(B, T + 1, H, device=dev)
+            g, i, f = (torch.empty(B, T, H, device=dev) for _ in range(3))
+            hin = torch.zeros(2, B, H, device=dev)           # the step kernel's input rows, ping-ponged over the steps
             for t in range(T):
-                x = torch.cat((m.embedding(tokens[:, t]), glob), dim=-1)
-                hn, cn, g, i, f = _lstm_forward(x, h[t], c[t], L.weight_ih, L.weight_hh, L.bias_ih, lb2)
-                q = mha.q_proj(hn).view(B, nh, 1, dk)
-                alpha = torch.softmax(torch.matmul(q, kh.transpose(-2, -1)) / math.sqrt(dk), dim=-1)   # (B,nh,1,P)
-                ctx = torch.matmul(alpha, vh).transpose(1, 2).reshape(B, H)
-                gate = m.decoder_aoa_linear_gate(hn)
-                lin = m.decoder_aoa_linear(ctx)
-                caoa = torch.sigmoid(gate) * lin
-                pred = m.fc(caoa + hn)
-                for k, v in zip(keys, [x, g, i, f, ctx, caoa, lin, gate, alpha.squeeze(2), pred]):
-                    seq[k].append(v)
-                h.append(hn); c.append(cn)
-            st = {k: torch.stack(v, 1).contiguous() for k, v in seq.items()}
-            st["h"], st["c"] = torch.stack(h, 1).contiguous(), torch.stack(c, 1).contiguous()
-            st.update(feat=feat.contiguous(), A_pre=A_pre.contiguous(), A=A.contiguous(), glob=glob, key=key,
+                p, q = t & 1, (t & 1) ^ 1
+                ops.lstm_step(hin[p], Wp_hh, pre[t], 4, c[:, t], h[:, t + 1], c[:, t + 1], g[:, t], i[:, t], f[:, t],
+                              h_copy0=hin[q])
+            hn = h[:, 1:]                                                         # (B,T,H)
+            qv = mha.q_proj(hn).view(B, T, nh, dk).transpose(1, 2)                # (B,nh,T,dk)
+            alpha = torch.softmax(torch.matmul(qv, kT) / math.sqrt(dk), dim=-1)   # (B,nh,T,P)
+            ctx = torch.matmul(alpha, vh).transpose(1, 2).reshape(B, T, H)
+            gate = m.decoder_aoa_linear_gate(hn)
+            lin = m.decoder_aoa_linear(ctx)
+            caoa = torch.sigmoid(gate) * lin
+            pred = torch.addmm(m.fc.bias, (caoa + hn).reshape(B * T, H), m.fc.weight.t()).view(B, T, m.vocab_size)
+            st = dict(x=x, g=g, i=i, f=f, ctx=ctx.contiguous(), caoa=caoa.contiguous(), caoa_lin=lin.contiguous(),
+                      caoa_gate=gate.contiguous(), alpha=alpha.transpose(1, 2).contiguous(), pred=pred, h=h, c=c,
+                      feat=feat, A_pre=A_pre.contiguous(), A=A.contiguous(), glob=glob, key=key,
                       value=value.contiguous())
         return st
 

@@ -74,3 +74,49 @@ def gridtd_explainer_forward_ops(model, feat, tokens, quirk_double_bias_ih=True)
             st[k] = torch.stack(v, 1).contiguous()
         st.update(feat=feat.contiguous(), avg=avg, A_pre=A_pre.contiguous(), A=A.contiguous(), glob_pre=glob_pre)
     return st
+
+
+def aoa_explainer_forward_ops(model, feat, tokens, quirk_double_bias_ih=True):
+    """Step-by-step tensor-op restatement of ExplainAOAAttention.get_hidden_parameters (reference aoamodel.py:999-1062)
+    on an AOAModel mirror: the checker of the product's explainer forward (LSTM step kernel + batched attention); runs
+    on any device."""
+    import math
+    from models.gridTDmodel import _lstm_forward
+    m = model
+    B, P, C = feat.shape
+    H = m.hidden_dim
+    T = tokens.shape[1] - 1
+    nh, dk = m.num_head, H // m.num_head
+    with torch.no_grad():
+        Wp = m.img_projector.weight.reshape(H, C)
+        A_pre = feat @ Wp.t() + m.img_projector.bias
+        A = A_pre.clamp(min=0)
+        glob = A.mean(1)
+        key, value = m.decoder_k_proj(A), m.decoder_v_proj(A)
+        kh = key.view(B, P, nh, dk).transpose(1, 2)
+        vh = value.view(B, P, nh, dk).transpose(1, 2)
+        mha = m.decoder_multihead_attention
+        L = m.LanguageLSTM
+        lb2 = L.bias_ih if quirk_double_bias_ih else L.bias_hh
+        zeros = feat.new_zeros(B, H)
+        h, c = [zeros], [zeros]
+        keys = ["x", "g", "i", "f", "ctx", "caoa", "caoa_lin", "caoa_gate", "alpha", "pred"]
+        seq = {k: [] for k in keys}
+        for t in range(T):
+            x = torch.cat((m.embedding(tokens[:, t]), glob), dim=-1)
+            hn, cn, g, i, f = _lstm_forward(x, h[t], c[t], L.weight_ih, L.weight_hh, L.bias_ih, lb2)
+            q = mha.q_proj(hn).view(B, nh, 1, dk)
+            alpha = torch.softmax(torch.matmul(q, kh.transpose(-2, -1)) / math.sqrt(dk), dim=-1)   # (B,nh,1,P)
+            ctx = torch.matmul(alpha, vh).transpose(1, 2).reshape(B, H)
+            gate = m.decoder_aoa_linear_gate(hn)
+            lin = m.decoder_aoa_linear(ctx)
+            caoa = torch.sigmoid(gate) * lin
+            pred = m.fc(caoa + hn)
+            for k, v in zip(keys, [x, g, i, f, ctx, caoa, lin, gate, alpha.squeeze(2), pred]):
+                seq[k].append(v)
+            h.append(hn); c.append(cn)
+        st = {k: torch.stack(v, 1).contiguous() for k, v in seq.items()}
+        st["h"], st["c"] = torch.stack(h, 1).contiguous(), torch.stack(c, 1).contiguous()
+        st.update(feat=feat.contiguous(), A_pre=A_pre.contiguous(), A=A.contiguous(), glob=glob, key=key,
+                  value=value.contiguous())
+    return st

@@ -592,3 +592,26 @@ def test_batch_pipeline_host_buffers_back_to_back(tmp_path):
     for n, ((heat, words), (wh, ww)) in enumerate(zip(outs, reversed(want))):
         assert torch.equal(heat, wh.cpu()), n
         assert torch.equal(words, ww.cpu()), n
+
+
+@pytest.mark.parametrize("B,T,P,H,E,V,C", [(3, 5, 16, 64, 32, 50, 64), (2, 4, 36, 1024, 512, 300, 2048)])
+def test_aoa_explainer_forward_equals_tensor_op_form(tmp_path, B, T, P, H, E, V, C):
+    """ExplainAOAAttention.explainer_forward (LSTM step kernel for the recurrence, attention / AoA gate / vocabulary
+    projection once over all B*T positions) vs the step-by-step tensor-op restatement of aoamodel.py:999-1062."""
+    import helpers
+    from models import aoamodel as A
+    model = A.AOAModel(E, H, 8, V, "vgg16")
+    model.img_projector = torch.nn.Conv2d(C, H, 1)
+    model.encoder_raw_dim = C
+    model.load_state_dict(synth.aoa_decoder_state(801, V, H, E, C), strict=False)
+    model.to(DEV).eval()
+    ex = A.ExplainAOAAttention(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="fp32")
+    g = torch.Generator().manual_seed(802)
+    feat = torch.rand(B, P, C, generator=g).to(DEV)
+    toks = torch.randint(1, V - 4, (B, T + 1), generator=g).to(DEV)
+    got = ex.explainer_forward(feat, toks)
+    want = helpers.aoa_explainer_forward_ops(model, feat, toks)
+    assert set(want) <= set(got)
+    for k, v in want.items():
+        assert got[k].shape == v.shape, k
+        assert_close(got[k], v, rtol=1e-4, atol=2e-5, what=k)

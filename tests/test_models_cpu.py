@@ -94,7 +94,11 @@ def test_aoa_explainer_forward_matches_reference_fixture(golden, tmp_path, name)
                               save_path=str(tmp_path), dataset="syn", weight="")
     ex = A.ExplainAOAAttention(args, synth.word_map(V), model=model)
     feat = g["feats"][0].flatten(1).t().unsqueeze(0).contiguous()
-    st = ex.explainer_forward(feat, torch.tensor([g["tokens"].tolist()]))
+    import helpers
+    from lrpx._lib import LrpxError
+    with pytest.raises(LrpxError):                       # the product's forward is CUDA only
+        ex.explainer_forward(feat, torch.tensor([g["tokens"].tolist()]))
+    st = helpers.aoa_explainer_forward_ops(ex.model, feat, torch.tensor([g["tokens"].tolist()]))
     assert_close(st["pred"][0], g["predictions"], atol=5e-5, what="predictions")
     assert_close(st["alpha"][0], g["alphas"].reshape(st["alpha"][0].shape), atol=1e-6, what="alphas")
     assert_close(st["h"][0], g["ht"], atol=1e-5, what="ht")
