@@ -129,3 +129,39 @@ def test_config5_tuner_weights_and_step_at_full_size():
     assert torch.isfinite(loss) and torch.isfinite(ls) and torch.isfinite(ll)
     assert torch.equal(enc_before, model.img_encoder.encoder[0].weight.detach())
     assert not torch.equal(fc_before, model.fc.weight.detach())
+
+
+def test_adaptive_decoder_full_size_properties(tmp_path):
+    """ExplainAdaptiveAttention at the bench size (64 images x 19 words, V = 10000, H = E = 512, P = 196, C = 512), where
+    the oracle would need minutes: finite outputs, word relevances normalised to max |r| = 1, a request's result
+    independent of the launch it is computed in (bit-exact), bf16x3 tensor-core GEMMs within 1e-4 (scale-relative) of the
+    fp32 CUDA-core GEMMs (measured 8e-6)."""
+    from lrpx import ops
+    from models import adaptiveattention as AA
+    V, H, E, B, T, P, C = 10000, 512, 512, 64, 19, 196, 512
+    model = AA.AdaptiveAttentionCaptioningModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.adaptive_decoder_state(901, V, H, E), strict=False)
+    model.to(DEV).eval()
+    ns = argparse.Namespace(embed_dim=E, hidden_dim=H, encoder="vgg16", height=224, width=224, save_path=str(tmp_path),
+                            dataset="syn", weight="")
+    ex = AA.ExplainAdaptiveAttention(ns, synth.word_map(V), model=model, precision="fp32")
+    g = torch.Generator().manual_seed(902)
+    feat = torch.rand(B, P, C, generator=g).to(DEV)
+    toks = torch.randint(1, V - 4, (B, T + 1), generator=g).to(DEV)
+    st, W = ex.explainer_forward(feat, toks), ex._lrp_weights()
+    req_img = torch.arange(B, dtype=torch.int32, device=DEV).repeat_interleave(T)
+    req_t = torch.arange(T, dtype=torch.int32, device=DEV).repeat(B)
+    req_word = toks[:, 1:].reshape(-1).to(torch.int32)
+    f32_feat, f32_words = ops.adaptive_decoder_lrp(st, W, req_img, req_t, req_word, tc_gemm=False)
+    tc_feat, tc_words = ops.adaptive_decoder_lrp(st, W, req_img, req_t, req_word, tc_gemm=True)
+    assert torch.isfinite(f32_feat).all() and torch.isfinite(tc_feat).all()
+    mask = torch.arange(T, device=DEV)[None, :] <= req_t[:, None]
+    m = (f32_words.abs() * mask).amax(1)
+    assert torch.allclose(m, torch.ones_like(m), atol=1e-6) and float((f32_words * ~mask).abs().max()) == 0.0
+    scale = f32_feat.abs().flatten(1).amax(1)
+    err = ((tc_feat - f32_feat).abs().flatten(1).amax(1) / scale).max()
+    print(f"adaptive full size: bf16x3 vs fp32 GEMMs max scale-relative error {float(err):.3e}")
+    assert float(err) <= 1e-4
+    for q in (0, 611, 1215):
+        one = ops.adaptive_decoder_lrp(st, W, req_img[q:q + 1], req_t[q:q + 1], req_word[q:q + 1], tc_gemm=False)
+        assert torch.equal(one[0][0], f32_feat[q]) and torch.equal(one[1][0], f32_words[q]), q
