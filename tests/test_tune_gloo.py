@@ -95,3 +95,59 @@ def test_two_ranks_equal_single_process_gloo():
     ref_params, _ = _single_process_reference(V, steps)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, V, steps, ref_params), nprocs=2, join=True)
+
+
+class _StubSampler(nn.Module):
+    """Pure-torch stand-in with the reference's sample / sample_lrp contract (train.py:259-263)."""
+
+    def __init__(self, V, H=10):
+        super().__init__()
+        self.img = nn.Linear(6, H)
+        self.fc = nn.Linear(H, V)
+
+    def _roll(self, imgs, L, greedy):
+        h = torch.tanh(self.img(imgs))
+        logp = torch.log_softmax(self.fc(h), -1)
+        seq, lps = [], []
+        for t in range(L):
+            it = logp.argmax(-1) if greedy else torch.multinomial(logp.exp(), 1)[:, 0]
+            seq.append(it)
+            lps.append(logp.gather(1, it[:, None])[:, 0])
+        return torch.stack(seq, 1), torch.stack(lps, 1), L
+
+    def sample(self, imgs, word_map, caplens, opt={}):
+        return self._roll(imgs, int(max(caplens)) - 1, True)
+
+    def sample_lrp(self, imgs, rev_word_map, word_map, caplens, opt={}):
+        assert opt.get('sample_method') == 'sample'
+        return self._roll(imgs, int(max(caplens)) - 1, False)
+
+
+def test_cider_tune_step_host_logic():
+    """lrpx.tune.LrpCiderTuneStep (train.py:252-272): greedy baseline under no_grad / eval, sampled captions in train
+    mode, reward handed to RewardCriterion, clamp, step; RewardCriterion's mask (modelutils.py:40-41)."""
+    V = 30
+    torch.manual_seed(0)
+    m = _StubSampler(V)
+    seen = {}
+
+    def reward_fn(greedy, all_caps, sampled, word_map):
+        seen["greedy_requires_grad"] = greedy.requires_grad
+        seen["all_caps"] = all_caps
+        return (sampled != greedy).float().numpy() - 0.25
+
+    st = tune.LrpCiderTuneStep(m, synth.word_map(V), reward_fn, lr=1e-2, grad_clip=0.05)
+    before = [p.detach().clone() for p in m.parameters()]
+    imgs, caps, caplens = _data(V)
+    loss, rew = st.step(imgs, "refs", caplens)
+    assert seen["all_caps"] == "refs" and seen["greedy_requires_grad"] is False and m.training
+    assert torch.isfinite(loss) and -0.25 <= float(rew) <= 0.75
+    assert all(p.grad is None or float(p.grad.abs().max()) <= 0.05 + 1e-9 for p in m.parameters())
+    assert any(not torch.equal(b, p.detach()) for b, p in zip(before, m.parameters()))
+    crit = tune.RewardCriterion()
+    logp = torch.tensor([[-1.0, -2.0, -3.0], [-0.5, -0.5, -0.5]])
+    seq = torch.tensor([[5, 0, 0], [4, 4, 4]])
+    reward = torch.tensor([[2.0, 2.0, 2.0], [1.0, 1.0, 1.0]])
+    # mask = [1, seq>0 shifted right]: row 0 -> [1,1,0], row 1 -> [1,1,1]
+    want = (1.0 * 2 + 2.0 * 2 + 0.5 + 0.5 + 0.5) / 5
+    assert abs(float(crit(logp, seq, reward)) - want) < 1e-6
