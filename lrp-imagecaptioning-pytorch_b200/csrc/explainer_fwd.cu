@@ -46,7 +46,8 @@ __global__ void lstm_cell_kernel(lrpx_lstm_cell_args a) {
 // the prepared layout) x a tile of 64 batch rows; the K-slices' partial sums meet in shared memory and slice 0 applies
 // the cell rule.  fp32 throughout (the saved state feeds the fp32 decoder relevance).
 // ------------------------------------------------------------------------------------------------
-constexpr int LS_U = 4, LS_KC = 64, LS_ROWS = 64, LS_PITCH = LS_KC + 4, LS_SLICES = 8, LS_RPT = 8, LS_STAGES = 4;
+constexpr int LS_U = 4, LS_ROWS = 64, LS_SLICES = 8, LS_RPT = 8;
+// K chunk / ring depth are template parameters of the step kernel (see lrpx_lstm_step_f32)
 
 __global__ void lstm_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int K, int G, int H) {
   const long long total = (long long)K * G * H;
@@ -69,8 +70,9 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, b
 // unit: per 4 k it reads 8 + G float4 from shared memory for 32*G FMAs.  K chunks of 64 go through a 4-stage cp.async
 // ring: a CTA only moves ~0.35 MB, so what has to be covered is the L2 latency (measured: one chunk of look-ahead left
 // the kernel at 22 us, no faster than the library GEMM it replaces).
-template <int G>
+template <int G, int LS_KC, int LS_STAGES>
 __global__ void __launch_bounds__(256) lstm_step_kernel(lrpx_lstm_step_args a) {
+  constexpr int LS_PITCH = LS_KC + 4;
   extern __shared__ __align__(16) float ls_smem[];
   constexpr int XS = LS_ROWS * LS_PITCH, WS = G * LS_U * LS_PITCH;
   float* xs = ls_smem;                               // [LS_STAGES][LS_ROWS][LS_PITCH]
@@ -383,15 +385,27 @@ extern "C" int lrpx_lstm_step_f32(const lrpx_lstm_step_args* a, void* stream) {
   LRPX_CHECK_ARG(a->ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(a->x) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(a->wp) & 15) == 0,
                  "x rows and wp must be 16-byte aligned");
-  const size_t smem = (size_t)(LS_STAGES * (LS_ROWS * LS_PITCH + a->G * LS_U * LS_PITCH) + LS_SLICES * 32 * LS_RPT * a->G) * sizeof(float);
-  static bool attr_done[2] = {false, false};
   cudaStream_t st = as_stream(stream);
-  if (a->G == 5) {
-    if (!attr_done[1]) { cudaFuncSetAttribute(lstm_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done[1] = true; }
-    lstm_step_kernel<5><<<a->H / LS_U, 256, smem, st>>>(*a);
+  // K chunk x ring depth: 256 x 2 by default — measured for the explainer's two shapes (K = 1024 / 5 gates, K = 1536 /
+  // 4 gates, 64 rows): 64 x 4: 19.0 / 23.4 us, 128 x 3: 17.0 / 21.3 us, 256 x 2: 15.5 / 20.5 us (fewer block-wide
+  // barriers, one 87 KB chunk of look-ahead).  LRPX_LSTM_KC = 64 | 128 select the other variants.
+  static const int kc = [] { const char* e = getenv("LRPX_LSTM_KC"); const int v = e ? atoi(e) : 256;
+                             return (v == 64 || v == 128) ? v : 256; }();
+  auto launch = [&](auto kernel, int KC, int STAGES, bool* done) {
+    const size_t smem = (size_t)(STAGES * (LS_ROWS * (KC + 4) + a->G * LS_U * (KC + 4)) + LS_SLICES * 32 * LS_RPT * a->G) * sizeof(float);
+    if (!*done) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); *done = true; }
+    kernel<<<a->H / LS_U, 256, smem, st>>>(*a);
+  };
+  static bool attr_done[6] = {false, false, false, false, false, false};
+  if (kc == 128) {
+    if (a->G == 5) launch(lstm_step_kernel<5, 128, 3>, 128, 3, &attr_done[0]);
+    else launch(lstm_step_kernel<4, 128, 3>, 128, 3, &attr_done[1]);
+  } else if (kc == 256) {
+    if (a->G == 5) launch(lstm_step_kernel<5, 256, 2>, 256, 2, &attr_done[4]);
+    else launch(lstm_step_kernel<4, 256, 2>, 256, 2, &attr_done[5]);
   } else {
-    if (!attr_done[0]) { cudaFuncSetAttribute(lstm_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done[0] = true; }
-    lstm_step_kernel<4><<<a->H / LS_U, 256, smem, st>>>(*a);
+    if (a->G == 5) launch(lstm_step_kernel<5, 64, 4>, 64, 4, &attr_done[2]);
+    else launch(lstm_step_kernel<4, 64, 4>, 64, 4, &attr_done[3]);
   }
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;
