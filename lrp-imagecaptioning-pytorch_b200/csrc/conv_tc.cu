@@ -1419,6 +1419,13 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     if (epi == LRPX_TC_EPI_MUL_UNPOOL) LRPX_CHECK_ARG(a->pool_idx, "pool_idx required");
     p.bn = a->ncol <= 256 ? a->ncol : 256;
     LRPX_CHECK_ARG(a->ncol % p.bn == 0, "ncol must be <= 256 or a multiple of 256");
+    // plain GEMMs with few rows (the decoder's per-step GEMMs: 1216 x 1536 x 1536): 256-column tiles give fewer tiles
+    // than SMs; 128-column tiles fill the machine (LRPX_TC_GEMM_BN=256 keeps the wide tiles)
+    if (a->ksize == 1 && epi == LRPX_TC_EPI_STORE_F32 && p.bn == 256) {
+      const char* env_bn = getenv("LRPX_TC_GEMM_BN");
+      const long long m_tiles = ((long long)a->n_img * (a->h + 1) * (a->w + 1) + TC_BM - 1) / TC_BM;
+      if (!(env_bn && atoi(env_bn) == 256) && m_tiles * (a->ncol / 256) < sm_count()) p.bn = 128;
+    }
     p.out_c = a->ncol;
   }
   p.num_n_tiles = a->ncol / p.bn;
