@@ -78,3 +78,27 @@ def test_no_cpu_fallback():
     from lrpx import ops, _lib
     with pytest.raises(_lib.LrpxError):
         ops.relu_mask(torch.zeros(4), torch.zeros(4))
+
+
+def test_argument_validation_of_the_widened_entry_points():
+    """SURVEY §8 f1-f3 entry points: bad arguments are rejected with LRPX_E_INVALID and a message before any CUDA call."""
+    from lrpx import _lib
+    lib = _lib.lib()
+    assert lib.lrpx_adaptive_decoder_lrp_f32(None, None, 0, None) == -1
+    a = _lib.AdaptiveArgs(B=1, T=2, H=8, E=8, P=4, C=8, V=10, Q=1)
+    assert lib.lrpx_adaptive_decoder_lrp_f32(C.byref(a), None, 0, None) == -1 and b"null pointer" in lib.lrpx_last_error()
+    assert lib.lrpx_adaptive_decoder_workspace_bytes(C.byref(a)) > 0
+    b = _lib.BeamArgs(B=1, k=9, V=100, L=20, step=0, end_id=99)
+    assert lib.lrpx_beam_step(C.byref(b), None) == -1 and b"k <= 8" in lib.lrpx_last_error()
+    b = _lib.BeamArgs(B=1, k=3, V=100, L=70, step=0, end_id=99)
+    assert lib.lrpx_beam_step(C.byref(b), None) == -1
+    g = _lib.BeamGatherArgs(n_rows=1, n_pairs=0)
+    assert lib.lrpx_beam_gather_f32(C.byref(g), None) == -1
+    m = _lib.BlockImageArgs(Q=1, C=3, H=30, W=32, patch=8, k=2)
+    assert lib.lrpx_block_image_f32(C.byref(m), None) == -1 and b"multiples of the patch size" in lib.lrpx_last_error()
+    m = _lib.BlockImageArgs(Q=1, C=3, H=32, W=32, patch=8, k=17)
+    assert lib.lrpx_block_image_f32(C.byref(m), None) == -1 and b"patch count" in lib.lrpx_last_error()
+    x = _lib.BboxArgs(Q=1, C=3, H=32, W=32, n_thr=10, max_boxes=9, sign=1.0)
+    assert lib.lrpx_bbox_ratio_f32(C.byref(x), None) == -1 and b"8 boxes" in lib.lrpx_last_error()
+    x = _lib.BboxArgs(Q=1, C=3, H=512, W=512, n_thr=10, max_boxes=2, sign=1.0)
+    assert lib.lrpx_bbox_ratio_f32(C.byref(x), None) == -1 and b"too large" in lib.lrpx_last_error()
