@@ -279,7 +279,10 @@ def run_ours(args):
                                          "chunk = chunk x algorithmic_gflop_per_explanation",
                          "peak_source": pk["src"] + " sustained bf16",
                          "share_of_step": phase_ms["encoder_relevance_chain"] / step_eager_ms,
-                         "algorithmic_gflop_per_explanation": eng.flops_per_explanation() / 1e9},
+                         "algorithmic_gflop_per_explanation": eng.flops_per_explanation() / 1e9,
+                         # SURVEY 8(d) counts the reference's formulation (z+ recomputed per word: two contractions per
+                         # layer = 2 x the figure above); `achieved` counts only the FLOPs this chain executes
+                         "reference_formulation_gflop_per_explanation": 2.0 * eng.flops_per_explanation() / 1e9},
         }
         out["breakdown_ms"] = phase_ms
         try:
