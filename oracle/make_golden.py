@@ -294,7 +294,14 @@ def golden_adaptive_decoder(ns):
                 with torch.no_grad(), quiet():
                     _, seqs = model.greedy_search(torch.zeros(1, 3, 224, 224), wm, max_cap_length=12)
                 greedy.append(np.array(seqs[0], dtype=np.int64))
-            out.update(end_bias=end_bias, beams=np.stack(beams), greedy=np.stack(greedy))
+            # the model's teacher-forced training forward (adaptiveattention.py:137-190) on two of the feature maps
+            fb = torch.cat([_features(seed + 10 + b, 512, 14, 14) for b in range(2)])
+            model.img_encoder = _StubEncoder(fb)
+            caps = torch.tensor([toks[:5], toks[1:6]])
+            with torch.no_grad():
+                fpred, falpha, fbeta, _, fmax = model(torch.zeros(2, 3, 224, 224), caps, torch.tensor([5, 4]), None)
+            out.update(end_bias=end_bias, beams=np.stack(beams), greedy=np.stack(greedy), fwd_caps=caps,
+                       fwd_predictions=fpred, fwd_alphas=falpha, fwd_betas=fbeta, fwd_max_length=np.array(int(fmax)))
         save(tag, **out)
 
 

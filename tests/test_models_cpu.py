@@ -220,3 +220,30 @@ def test_sample_greedy_matches_reference_and_reward_criterion(golden):
     mask = torch.tensor([[1., 1, 1, 0, 0, 0], [1, 1, 1, 1, 1, 1], [1, 0, 0, 0, 0, 0]])
     want = (-logp * reward * mask).sum() / mask.sum()
     assert_close(RewardCriterion()(logp, seqs, reward), want, what="reward criterion")
+
+
+def test_adaptive_model_forward_matches_reference(golden):
+    """AdaptiveAttentionCaptioningModel.forward (teacher forcing, adaptiveattention.py:137-190) against the reference's
+    own predictions / alphas / betas on two stubbed feature maps."""
+    from models import adaptiveattention as AA
+    g = golden("adaptive_dec_small")
+    V, H, E, seed = int(g["V"]), int(g["H"]), int(g["E"]), int(g["seed"])
+    m = AA.AdaptiveAttentionCaptioningModel(E, H, V, "vgg16")
+    sd = synth.adaptive_decoder_state(seed, V, H, E)
+    sd["fc.bias"][V - 1] += float(g["end_bias"])
+    m.load_state_dict(sd, strict=False)
+    m.eval()
+    fb = torch.cat([torch.randn(1, 512, 14, 14, generator=torch.Generator().manual_seed(seed + 10 + b)).clamp(min=0)
+                    for b in range(2)])
+
+    class Stub(torch.nn.Module):
+        def forward(self, img):
+            return fb, fb.mean((2, 3)).squeeze()
+
+    m.img_encoder = Stub()
+    with torch.no_grad():
+        pred, alphas, betas, _, L = m(torch.zeros(2, 3, 224, 224), g["fwd_caps"], torch.tensor([5, 4]), None)
+    assert L == int(g["fwd_max_length"])
+    assert_close(pred, g["fwd_predictions"], atol=2e-5, what="forward predictions")
+    assert_close(alphas, g["fwd_alphas"], atol=1e-6, what="forward alphas")
+    assert_close(betas, g["fwd_betas"], atol=1e-6, what="forward betas")
