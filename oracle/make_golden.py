@@ -426,8 +426,13 @@ def golden_tune_bu(ns):
                 for bs in (1, 3):
                     _, sen_idx = m.beam_search(feats[b:b + 1], wm, beam_size=bs)
                     beams.append(np.array(sen_idx + [-1] * (40 - len(sen_idx)), dtype=np.int64))
+            # plain teacher-forced forward and greedy sample of the twins (gridTDmodel.py:1899-1955,:1956-1998 /
+            # aoamodel.py:1826-1881,:1883-1925)
+            fwd = m(feats, caps, caplens, None)
+            sseq, sseq_lp, _ = m.sample(feats, wm, caplens)
         out.update({f"{tag}_predictions": pred, f"{tag}_weighted_predictions": wpred, f"{tag}_max_length": int(maxlen),
-                    f"{tag}_seq": seq, f"{tag}_seq_logprobs": seq_lp, f"{tag}_beams": np.stack(beams)})
+                    f"{tag}_seq": seq, f"{tag}_seq_logprobs": seq_lp, f"{tag}_beams": np.stack(beams),
+                    f"{tag}_fwd_predictions": fwd[0], f"{tag}_sample_seq": sseq, f"{tag}_sample_logprobs": sseq_lp})
     save("tune_bu", **out)
 
 

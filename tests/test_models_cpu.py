@@ -247,3 +247,19 @@ def test_adaptive_model_forward_matches_reference(golden):
     assert_close(pred, g["fwd_predictions"], atol=2e-5, what="forward predictions")
     assert_close(alphas, g["fwd_alphas"], atol=1e-6, what="forward alphas")
     assert_close(betas, g["fwd_betas"], atol=1e-6, what="forward betas")
+
+
+def test_bu_twins_forward_and_greedy_sample_vs_reference(golden):
+    """GridTDModelBU / AOAModelBU: the plain teacher-forced ``forward`` and the greedy ``sample`` (the self-critical
+    baseline of trainciderlrp) against the reference's own outputs — logits to 2e-5, sampled words bit-exact."""
+    g = golden("tune_bu")
+    models, V, s = _bu_models(g)
+    wm = synth.word_map(V)
+    feats = synth.bu_features(s[2], 3)
+    for tag, m in models.items():
+        with torch.no_grad():
+            pred = m(feats, g["caps"], g["caplens"], None)[0]
+            seq, lp, _ = m.sample(feats, wm, g["caplens"])
+        assert_close(pred, g[f"{tag}_fwd_predictions"], atol=2e-5, what=f"{tag} forward")
+        assert torch.equal(seq, g[f"{tag}_sample_seq"]), tag
+        assert_close(lp, g[f"{tag}_sample_logprobs"], atol=1e-4, what=f"{tag} sample logprobs")
