@@ -263,3 +263,21 @@ def test_bu_twins_forward_and_greedy_sample_vs_reference(golden):
         assert_close(pred, g[f"{tag}_fwd_predictions"], atol=2e-5, what=f"{tag} forward")
         assert torch.equal(seq, g[f"{tag}_sample_seq"]), tag
         assert_close(lp, g[f"{tag}_sample_logprobs"], atol=1e-4, what=f"{tag} sample logprobs")
+
+
+def test_encoder_mirrors_forward_vs_reference_fixtures(golden):
+    """models.resnet.ResNet and models.vgg (features[0:-1]) mirrors: forward on the fixtures' inputs equals the
+    reference's encoder output (state_dict-compatible modules, plain torch forward)."""
+    from models import resnet, vgg
+    g = golden("resnet_2111")
+    r = resnet.ResNet(resnet.Bottleneck, g["layers"].tolist())
+    r.load_state_dict(synth.resnet_state(int(g["seed"]), tuple(g["layers"].tolist())))
+    r.eval()
+    with torch.no_grad():
+        assert_close(r(g["x"]), g["feats"], atol=2e-5, what="resnet mirror forward")
+    g = golden("vgg16_64")
+    enc = vgg.vgg16(pretrained=False).features[0:-1]
+    enc.load_state_dict(synth.vgg_state(int(g["seed"])))
+    enc.eval()
+    with torch.no_grad():
+        assert_close(enc(g["x"]), g["feats"], atol=2e-5, what="vgg mirror forward")
