@@ -104,6 +104,9 @@ __global__ void __launch_bounds__(BEAM_THREADS) beam_step_kernel(lrpx_beam_args 
       }
     }
     best = block_best(best, s_red);
+    // no candidate left (NaN scores compare false everywhere): keep the index inside [0, rows*V) so that the
+    // bookkeeping below never leaves its arrays; the score stays -inf
+    if (best.i < 0 || best.i >= rows * V) best.i = 0;
     if (threadIdx.x == 0) s_sel[j] = best;
     prev = best;
   }

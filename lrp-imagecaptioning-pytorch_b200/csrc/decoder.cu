@@ -815,17 +815,23 @@ __global__ void fc_lrp_weights_kernel(const float* __restrict__ logits, const fl
   __shared__ float s_val[32];
   __shared__ int s_idx[32];
   __shared__ float s_m[2][32];
-  // argmax, first index wins on ties (torch.argmax, gridTDmodel.py:555)
+  // argmax, first index wins on ties (torch.argmax, gridTDmodel.py:555); NaN counts as the maximum (torch's order:
+  // a diverged tuning run with NaN logits returns the first NaN's index there and must not index out of bounds here)
+  auto better = [](float v, int j, float bv, int bi) {
+    const bool vn = v != v, bn = bv != bv;
+    if (vn || bn) return vn && (!bn || j < bi);
+    return v > bv || (v == bv && j < bi);
+  };
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   for (int j = threadIdx.x; j < V; j += blockDim.x) {
     float v = lg[j];
-    if (v > bv || (v == bv && j < bi)) { bv = v; bi = j; }
+    if (better(v, j, bv, bi)) { bv = v; bi = j; }
   }
   for (int o = 16; o; o >>= 1) {
     float ov = __shfl_xor_sync(0xffffffffu, bv, o);
     int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
   }
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) / 32;
   if (lane == 0) { s_val[wid] = bv; s_idx[wid] = bi; }
@@ -836,9 +842,9 @@ __global__ void fc_lrp_weights_kernel(const float* __restrict__ logits, const fl
     for (int o = 16; o; o >>= 1) {
       float ov = __shfl_xor_sync(0xffffffffu, bv, o);
       int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
     }
-    if (lane == 0) { s_val[0] = bv; s_idx[0] = bi; }
+    if (lane == 0) { s_val[0] = bv; s_idx[0] = (bi >= 0 && bi < V) ? bi : 0; }
   }
   __syncthreads();
   int word = s_idx[0];

@@ -35,14 +35,17 @@ def build(force=False, verbose=False):
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     os.makedirs(os.path.join(HERE, "_obj"), exist_ok=True)
     procs = []
+    header = os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "lrpx.h")
+    shared_deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [header]
     for s in SOURCES:
         src = os.path.join(CSRC, s)
         if not os.path.exists(src):
             continue
         obj = os.path.join(HERE, "_obj", s.replace(".cu", ".o"))
         objs.append(obj)
+        # every object depends on its source, the shared csrc headers AND the public ABI header (struct layouts)
         if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(
-                os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")) or f == s):
+                os.path.getmtime(d) for d in shared_deps + [src]):
             continue
         cmd = [nvcc] + flags + ["-c", src, "-o", obj]
         if verbose:
@@ -54,10 +57,14 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed for {s}:\n{out}")
         if verbose and out.strip():
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("link failed:\n" + r.stdout.decode())
+    os.replace(tmp, LIB)          # a reader never sees a half-written library
     return LIB
 
 

@@ -4,6 +4,7 @@ torch is used only for device memory and streams; all arithmetic happens in libl
 Every function requires CUDA tensors and raises otherwise (no CPU fallback).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -234,6 +235,26 @@ def _fill_args(struct, fields: dict, keep: list):
 DEC_TC_GEMM = 1
 
 
+def _check_requests(B, T, V, req_img, req_t, req_word, req_head=None, num_head=0):
+    """The decoder kernels index saved state with the request tuples: reject out-of-range requests here (one small
+    reduction + read-back; skipped while a CUDA graph is being captured and with LRPX_VALIDATE=0)."""
+    if os.environ.get("LRPX_VALIDATE", "1") == "0":
+        return
+    n = int(req_img.numel())
+    if not (int(req_t.numel()) == n and int(req_word.numel()) == n and (req_head is None or int(req_head.numel()) == n)):
+        raise _lib.LrpxError("decoder lrp: req_img / req_t / req_word (/ req_head) must have the same length")
+    if n == 0 or (req_img.is_cuda and torch.cuda.is_current_stream_capturing()):
+        return
+    lim = [(req_img, B, "req_img"), (req_t, T, "req_t"), (req_word, V, "req_word")]
+    if req_head is not None:
+        lim.append((req_head, num_head, "req_head"))
+    dev = req_img.device
+    stats = torch.stack([torch.stack((v.to(dev).min(), v.to(dev).max())) for v, _, _ in lim]).tolist()
+    for (lo, hi), (_, bound, name) in zip(stats, lim):
+        if lo < 0 or hi >= bound:
+            raise _lib.LrpxError(f"decoder lrp: {name} out of range [0, {bound}): min {int(lo)}, max {int(hi)}")
+
+
 def gridtd_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, want_raw=False, tc_gemm=False):
     """state: tensors of lrpx_gridtd_args (stacked over B images), weights: W_g1,W_g2,W_fc,W_glob,W_proj.
     tc_gemm: run the GEMMs as error-compensated bf16x3 on the tensor cores (LRPX_DEC_TC_GEMM) instead of fp32
@@ -244,6 +265,7 @@ def gridtd_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, wan
     E = state["glob_pre"].shape[1]
     V = state["pred"].shape[2]
     Q = int(req_img.numel())
+    _check_requests(B, T, V, req_img, req_t, req_word)
     keep = []
     a = _lib.GridTDArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q, flags=DEC_TC_GEMM if tc_gemm else 0)
     f = {k: _f32(state[k], k) for k in ["feat", "avg", "A_pre", "A", "glob_pre", "x1", "x2", "h1", "c1", "h2", "c2",
@@ -272,6 +294,7 @@ def aoa_decoder_lrp(state: dict, weights: dict, num_head, req_img, req_t, req_wo
     E = state["x"].shape[2] - H
     V = state["pred"].shape[2]
     Q = int(req_img.numel())
+    _check_requests(B, T, V, req_img, req_t, req_word, req_head, num_head)
     keep = []
     a = _lib.AoaArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q, num_head=num_head, flags=DEC_TC_GEMM if tc_gemm else 0)
     f = {k: _f32(state[k], k) for k in ["feat", "A_pre", "A", "glob", "value", "x", "h", "c", "g", "i", "ctx", "caoa",
@@ -300,6 +323,7 @@ def adaptive_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, w
     E = state["z_glob"].shape[1]
     V = state["pred"].shape[2]
     Q = int(req_img.numel())
+    _check_requests(B, T, V, req_img, req_t, req_word)
     keep = []
     a = _lib.AdaptiveArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q, flags=DEC_TC_GEMM if tc_gemm else 0)
     f = {k: _f32(state[k], k) for k in ["feat", "avg", "z_proj", "A", "z_glob", "x", "h", "c", "g", "i", "f", "st",

@@ -63,10 +63,16 @@ class LrpTuneStep:
 
     @staticmethod
     def shard(batch, rank, world):
-        """This rank's contiguous slice of a global batch (tensors with the batch on dim 0)."""
+        """This rank's contiguous slice of a global batch (tensors with the batch on dim 0).  Balanced like
+        ``shard.image_range`` (slices differ by at most one sample); every rank must get at least one sample — an
+        empty slice would leave that rank out of DistributedDataParallel's gradient all-reduce and hang the others."""
         n = batch[0].shape[0]
-        per = (n + world - 1) // world
-        lo, hi = rank * per, min(n, (rank + 1) * per)
+        if n < world:
+            raise ValueError(f"LrpTuneStep.shard: a batch of {n} samples cannot feed {world} ranks "
+                             "(drop or pad the last short batch of the epoch)")
+        base, extra = divmod(n, world)
+        lo = rank * base + min(rank, extra)
+        hi = lo + base + (1 if rank < extra else 0)
         return tuple(t[lo:hi] for t in batch)
 
     def losses(self, imgs, caps, caplens):
@@ -74,8 +80,22 @@ class LrpTuneStep:
         pred, wpred, max_length = self.fwd(imgs, caps, caplens)
         max_length = int(max_length)
         targets = caps[:, 1:max_length + 1].contiguous().view(-1)
-        loss_standard = self.criterion(pred.contiguous().view(-1, pred.size(2)), targets)
-        loss_lrp = self.criterion(wpred.contiguous().view(-1, wpred.size(2)), targets)
+        if not self.distributed:
+            loss_standard = self.criterion(pred.contiguous().view(-1, pred.size(2)), targets)
+            loss_lrp = self.criterion(wpred.contiguous().view(-1, wpred.size(2)), targets)
+            return loss_lrp + loss_standard, loss_standard, loss_lrp
+        # The reference's loss is the mean over the non-<pad> tokens of the WHOLE batch (train.py:223-226).  Ranks
+        # hold different token counts (ragged captions, slices differing by one sample), so the plain average of
+        # per-rank means DistributedDataParallel would produce is a different number: each rank contributes
+        # world * (sum of its token losses) / (global token count), whose rank average is the global token mean.
+        pad = self.criterion.ignore_index
+        n_tok = (targets != pad).sum().to(torch.float32)
+        total = n_tok.detach().clone()
+        dist.all_reduce(total)                              # one scalar; the gradient all-reduce stays DDP's
+        scale = dist.get_world_size() / total.clamp(min=1.0)
+        ce = nn.functional.cross_entropy
+        loss_standard = ce(pred.contiguous().view(-1, pred.size(2)), targets, ignore_index=pad, reduction="sum") * scale
+        loss_lrp = ce(wpred.contiguous().view(-1, wpred.size(2)), targets, ignore_index=pad, reduction="sum") * scale
         return loss_lrp + loss_standard, loss_standard, loss_lrp
 
     def step(self, imgs, caps, caplens):

@@ -201,12 +201,14 @@ class GridTDModel(nn.Module):
         return predictions, alphas, betas, last_scores, max_length
 
     def remove_bad_endings(self, sentences):
+        """reference :284-300: trailing function words are stripped; a sentence made of nothing else is kept as it
+        is (the reference's ``bad_sentence`` branch)."""
         out = []
         for s in sentences:
             words = s.split(' ')
             while words and words[-1] in BAD_ENDINGS:
                 words = words[:-1]
-            out.append(' '.join(words))
+            out.append(' '.join(words) if words else s)
         return out
 
     def beam_search(self, imgs, word_map, beam_size=3, max_cap_length=20):
@@ -308,12 +310,21 @@ class GridTDModel(nn.Module):
         return out[0] if len(out) == 1 else out
 
     def sample_next_word(self, logprobs, sample_method, temperature):
+        """reference :244-282.  'greedy'; 'gumbel' (arg-max of the Gumbel-perturbed scores, log-probability gathered
+        from the unscaled input); anything else samples from softmax(logprobs / temperature) and gathers from the
+        SCALED log-probabilities — the reference's top-k / nucleus branch is dead code (`sample_method.startswith ==
+        'top'` compares a bound method with a string, :260), so 'top*' behaves like plain sampling there too."""
         if sample_method == 'greedy':
-            sampleLogprobs, it = torch.max(logprobs.data, 1)
+            sampleLogprobs, it = torch.max(logprobs.detach(), 1)
             return it.view(-1).long(), sampleLogprobs
-        prob = torch.exp(logprobs.data / temperature) if temperature != 1.0 else torch.exp(logprobs.data)
-        it = torch.multinomial(prob, 1)
-        return it.view(-1).long(), logprobs.gather(1, it)
+        if sample_method == 'gumbel':
+            u = torch.rand(logprobs.shape, device=logprobs.device)
+            y = logprobs + (-torch.log(-torch.log(u + 1e-20) + 1e-20))
+            it = torch.log_softmax(y / temperature, dim=-1).detach().argmax(1)
+            return it, logprobs.gather(1, it.unsqueeze(1))
+        logprobs = logprobs / temperature
+        it = torch.distributions.Categorical(logits=logprobs.detach()).sample()
+        return it, logprobs.gather(1, it.unsqueeze(1))
 
     # ------------------------------------------------------------------ lrp_tune
     def lrp_linear_eps(self, r_out, forward_input, forward_output, weight):

@@ -38,24 +38,30 @@ class _StubCaptioner(nn.Module):
         return torch.stack(preds, 1), torch.stack(wpreds, 1), max_length
 
 
-def _data(V, B=8, L=5):
+def _data(V, B=8, L=5, ragged=False):
     g = torch.Generator().manual_seed(3)
     imgs = torch.randn(B, 6, generator=g)
     caps = torch.randint(1, V - 4, (B, L), generator=g)
     caps[:, 0] = V - 2
-    return imgs, caps, torch.full((B,), L)
+    caplens = torch.full((B,), L)
+    if ragged:                                  # caption b has 2 + (b % (L-1)) tokens, <pad> = 0 after them
+        caplens = torch.tensor([2 + (b % (L - 1)) for b in range(B)])
+        for b in range(B):
+            caps[b, int(caplens[b]):] = 0
+    return imgs, caps, caplens
 
 
-def _single_process_reference(V, steps):
+def _single_process_reference(V, steps, **kw):
     torch.manual_seed(0)
     m = _StubCaptioner(V)
     st = tune.LrpTuneStep(m, synth.word_map(V), lr=1e-2, grad_clip=0.05)
     for _ in range(steps):
-        loss, ls, ll = st.step(*_data(V))
+        loss, ls, ll = st.step(*_data(V, **kw))
     return [p.detach().clone() for p in m.parameters()], float(loss)
 
 
-def _worker(rank, world, port, V, steps, ref_params):
+def _worker(rank, world, port, V, steps, ref_params, kw=None):
+    kw = kw or {}
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -65,7 +71,7 @@ def _worker(rank, world, port, V, steps, ref_params):
         st = tune.LrpTuneStep(m, synth.word_map(V), lr=1e-2, grad_clip=0.05)
         assert st.distributed
         for _ in range(steps):
-            st.step(*tune.LrpTuneStep.shard(_data(V), rank, world))
+            st.step(*tune.LrpTuneStep.shard(_data(V, **kw), rank, world))
         for p, r in zip(m.parameters(), ref_params):
             assert torch.allclose(p.detach(), r, rtol=1e-5, atol=1e-6), float((p.detach() - r).abs().max())
     finally:
@@ -95,6 +101,26 @@ def test_two_ranks_equal_single_process_gloo():
     ref_params, _ = _single_process_reference(V, steps)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, V, steps, ref_params), nprocs=2, join=True)
+
+
+def test_two_ranks_uneven_ragged_batch_equal_single_process_gloo():
+    """5 samples over 2 ranks (3 + 2) with ragged captions: the token-weighted loss makes the averaged gradients equal
+    to the single-process step on the whole batch (the reference's mean over all non-<pad> tokens)."""
+    V, steps = 30, 3
+    kw = dict(B=5, ragged=True)
+    ref_params, _ = _single_process_reference(V, steps, **kw)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, V, steps, ref_params, kw), nprocs=2, join=True)
+
+
+def test_shard_is_balanced_and_refuses_empty_ranks():
+    import pytest
+    b = (torch.arange(5),)
+    sizes = [tune.LrpTuneStep.shard(b, r, 4)[0].shape[0] for r in range(4)]
+    assert sizes == [2, 1, 1, 1]
+    assert torch.equal(torch.cat([tune.LrpTuneStep.shard(b, r, 4)[0] for r in range(4)]), b[0])
+    with pytest.raises(ValueError):
+        tune.LrpTuneStep.shard((torch.arange(3),), 0, 4)
 
 
 class _StubSampler(nn.Module):
