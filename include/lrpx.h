@@ -113,6 +113,21 @@ int lrpx_normalize_relevance_f32(const float* x, float* y, int rows, int cols, f
 /* sum of a buffer in double precision (conservation reports: sum R_in vs sum R_out); out is 1 double */
 int lrpx_sum_f64(const float* x, size_t count, double* out, void* stream);
 
+/* The explainers' NAMED vector rules (the batched decoder kernels below fuse the same arithmetic; these serve the
+ * reference's own method names as CUDA entry points):
+ * lrp_linear_eps (gridTDmodel.py:744-765 / :522-547, aoamodel.py:532-557,785-810):
+ *   r_in[j] = x[j] * sum_k W[k][j] * r_out[k] / stab(z[k]),  stab(z) = z + 0.01*sign(z), 0 -> 0.01;
+ *   z == NULL means forward_output=False in the reference: z = W x is recomputed (without bias).
+ *   W is (n_out, n_in) row-major.  workspace: lrpx_lrp_linear_eps_workspace_bytes(n_out, n_in) bytes. */
+size_t lrpx_lrp_linear_eps_workspace_bytes(int n_out, int n_in);
+int lrpx_lrp_linear_eps_f32(const float* r_out, const float* x, const float* z, const float* W, float* r_in, int n_out,
+                            int n_in, void* workspace, size_t workspace_bytes, void* stream);
+/* lrp_mha (aoamodel.py:812-862): value relevance of ONE head,
+ *   r_value[p][c] = value[p][c] * alpha[head][p] * r_context[c] / stab(context[c]) for c in head's d_k slice, else 0
+ *   alpha (num_head, P), value / r_value (P, H), r_context / context (H). */
+int lrpx_lrp_mha_f32(const float* alpha, const float* value, const float* r_context, const float* context, float* r_value,
+                     int P, int H, int num_head, int head_idx, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Decoder relevance, fp32 (models/gridTDmodel.py:1014-1135, models/aoamodel.py:812-862,1064-1156),
  * batched over Q explanation requests (image b_q, target word t_q).
@@ -445,8 +460,29 @@ enum {
   LRPX_TC_EPI_FEAT_DIV = 7,
   /* first layer with the three filter columns folded into N: ncol = 24, Wt row dx*8 + c (c = 0..2: W+^T, 3..5: W-^T,
    * 6..7: zero) holds, K-ordered (filter row dy, channel), the weights of filter tap (dy, dx); the kernel adds the
-   * three column-shifted partial sums in its epilogue.  Same output as LRPX_TC_EPI_INPUT (3x3 only). */
+   * three column-shifted partial sums in its epilogue.  Same output as LRPX_TC_EPI_INPUT (3x3 only).
+   * gain_mode selects the delivery format of the heat-map: 0 = fp32 (n, 3, h, w), 1 = channel mean fp32 (n, h, w)
+   * (evaluation.py:134,411,503 reduce every heat-map with torch.mean(relevance, dim=(0,1)) first), 2 = fp16 (n, 3, h, w). */
   LRPX_TC_EPI_INPUT3 = 8,
+  /* General relevance epilogue (any alpha/beta, the epsilon rule, bf16 or fp32-accurate storage):
+   *   for group j < groups:  v_j = acc[p][n] * gain_j[img(p)][rem(p)][n]
+   *   split == 0: out[p][j*ncol + n] = bf16(v_j)                      gains are bf16 PF (rows, ncol)
+   *   split == 1: out[p][j*ncol + n] = hi(v_j), out[p][(groups+j)*ncol + n] = lo(v_j) with v = hi + lo, both bf16
+   *               (16 significant bits); gains are fp32 PF (rows, ncol)
+   * The row written is the A operand of the layer below: groups = 2 carries [alpha*R/z+ | -beta*R/z-] so that
+   * alpha*R(pos-net) - beta*R(neg-net) (lrp_modules.py:129-150) is ONE contraction over K = [W+^T | W-^T]. */
+  LRPX_TC_EPI_MULX = 9,
+  /* MULX at pooled resolution with the max-pool winner-take-all scatter of MUL_UNPOOL */
+  LRPX_TC_EPI_MULX_UNPOOL = 10,
+  /* General forward + gains.  Wt holds per tile of `half` output channels n_acc row blocks: W, then W+ (n_acc >= 2),
+   * then W- (n_acc == 3);  z = acc_W + bias, act = relu(z);  num = act (gain_mode 0) or 1 (gain_mode 1)
+   *   rule 0 (alpha-beta): gain0 = alpha * num / safe(acc_W+ [+ bias if zbias]),
+   *                        gain1 = -beta * num / safe(acc_W- [+ bias if zbias])                      (n_acc == 3)
+   *   rule 1 (epsilon, lrp_modules.py:9-24 on the unfolded conv): gain0 = num' / stab(acc_W [+ bias if zbias]),
+   *                        num' = num with exact zeros replaced by -1e-6 (Q9), stab(z) = z + 0.01 sign z, 0 -> 0.01
+   * out = act (bf16 PF, or hi|lo split with 2*cout channels per row when split), out2 = gain0, out3 = gain1
+   * (bf16, or fp32 when split). */
+  LRPX_TC_EPI_FWDX = 11,
 };
 
 typedef struct {
@@ -456,7 +492,7 @@ typedef struct {
   int ncol;             /* rows of Wt == GEMM N                                                   */
   int ksize;            /* 1 or 3                                                                 */
   int epilogue;         /* LRPX_TC_EPI_*                                                          */
-  int gain_mode;        /* FWD_GAIN only                                                          */
+  int gain_mode;        /* FWD_GAIN / FWDX: 0 act/z, 1 1/z;  INPUT3: delivery format (see above)   */
   const void* a;        /* bf16 PF (n_img, (h+1)*(w+1), cin)                                      */
   const void* wt;       /* bf16 (ncol, ksize*ksize*cin), K ordered (tap, channel)                 */
   const float* bias;    /* FWD_GAIN: (cout) or NULL                                               */
@@ -467,6 +503,20 @@ typedef struct {
   void* out;
   void* out2;
   const float* x1;      /* FEAT_DIV: fp32 (n_x, blk, ncol)                                        */
+  /* ---- general modes (MULX / MULX_UNPOOL / FWDX; zero for the epilogues above) */
+  const void* gain2;    /* MULX*: gain of group 1                                                 */
+  void* out3;           /* FWDX: gain of group 1                                                  */
+  int a_phys;           /* channels per row of A in memory when they differ from `cin` (0 = cin): with
+                         * a_phys < cin the K blocks beyond a_phys wrap around (block kc reads A block
+                         * kc - a_phys/64), so a hi|lo split row [hi | lo] serves the error-compensated
+                         * product a*w ~ hi*w_hi + lo*w_hi + hi*w_lo as K = [hi | lo | hi] x [w_hi | w_hi | w_lo]
+                         * without storing hi twice                                                */
+  int groups;           /* MULX*: 1 or 2 gain groups                                              */
+  int split;            /* 0: bf16 rows / bf16 gains; 1: hi|lo split rows / fp32 gains            */
+  int n_acc;            /* FWDX: 1, 2 or 3 accumulators per output channel                        */
+  int rule;             /* FWDX: 0 alpha-beta, 1 epsilon                                          */
+  int zbias;            /* FWDX: the bias enters the rule's divisor (ignore_bias = False)         */
+  float alpha, beta;    /* FWDX                                                                   */
 } lrpx_tc_conv_args;
 
 int lrpx_tc_conv(const lrpx_tc_conv_args* args, void* stream);
@@ -512,6 +562,18 @@ int lrpx_tc_scale_rows(const float* r, const void* rz, const int32_t* row_img, v
 int lrpx_tc_pf_to_dense_f32(const void* src, float* dst, int n, int h, int w, int c, int layout, void* stream);
 /* dense fp32 NCHW (n, c, h, w) -> PF bf16 (n, blk, c_pad), channels >= c zero-filled */
 int lrpx_tc_nchw_to_pf_bf16(const float* src, void* dst, int n, int c, int h, int w, int c_pad, void* stream);
+
+/* ---- companions of the general modes (groups = 1 | 2 gain groups; split = 0: bf16, 1: hi|lo rows + fp32 gains) */
+/* lrpx_tc_im2col3_split_bf16 with hi|lo rows: 128 columns [hi of the 64 | lo of the 64] */
+int lrpx_tc_im2col3_split_x(const float* x, void* dst, int n, int h, int w, int split, void* stream);
+/* lrpx_tc_maxpool2_bf16 for split rows (the winner is the largest hi+lo) and up to two gain tensors */
+int lrpx_tc_maxpool2_x(const void* act, const void* gain0_fine, const void* gain1_fine, void* pooled, uint8_t* idx,
+                       void* gain0_pooled, void* gain1_pooled, int n, int h, int w, int c, int split, void* stream);
+/* lrpx_tc_scale_rows for the general chain: out row = [r*rz0 | r*rz1] (groups), bf16 or hi|lo split */
+int lrpx_tc_scale_rows_x(const float* r, const void* rz0, const void* rz1, const int32_t* row_img, void* out,
+                         int n_expl, int h, int w, int c, int groups, int split, void* stream);
+/* lrpx_tc_pf_to_dense_f32 for hi|lo rows of 2*c channels (value = hi + lo) */
+int lrpx_tc_pf_split_to_dense_f32(const void* src, float* dst, int n, int h, int w, int c, int layout, void* stream);
 
 #ifdef __cplusplus
 }

@@ -181,6 +181,64 @@ class _ResNetPlan:
         return R
 
 
+def _tc_cfg(model):
+    """The VGG-style layer list the tensor-core engine (lrpx.tc.TcVggEngine) runs: conv3x3/s1/p1 -> ReLU
+    [-> max-pool 2x2/s2] blocks ending with a ReLU (models/vgg.py:62-83, gridTDmodel.py:32-35).  -> (convs, cfg) or
+    None when the Sequential is anything else (those models stay on the fp32 rule kernels)."""
+    if not isinstance(model, nn.Sequential):
+        return None
+    leaves = _flatten_sequential(model)
+    convs, cfg, i = [], [], 0
+    pair = lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+    while i < len(leaves):
+        m = leaves[i]
+        if not (isinstance(m, nn.Conv2d) and pair(m.kernel_size) == (3, 3) and pair(m.stride) == (1, 1)
+                and pair(m.padding) == (1, 1) and pair(m.dilation) == (1, 1) and m.groups == 1
+                and m.padding_mode == 'zeros'):
+            return None
+        if i + 1 >= len(leaves) or type(leaves[i + 1]) != nn.ReLU:
+            return None
+        convs.append(m)
+        cfg.append(m.out_channels)
+        i += 2
+        if i < len(leaves) and isinstance(leaves[i], nn.MaxPool2d):
+            p = leaves[i]
+            if not (pair(p.kernel_size) == (2, 2) and pair(p.stride if p.stride is not None else p.kernel_size) == (2, 2)
+                    and pair(p.padding) == (0, 0) and pair(p.dilation) == (1, 1) and not p.ceil_mode):
+                return None
+            cfg.append("M")
+            i += 1
+    if not convs or cfg[-1] == "M" or convs[0].in_channels != 3 or convs[0].out_channels not in (8, 16, 32, 64):
+        return None
+    if any(c.in_channels % 64 or c.out_channels % 32 for c in convs[1:]):
+        return None
+    return convs, cfg
+
+
+class _TcPlan:
+    """Tensor-core route of ``compute_lrp`` for VGG-style encoders: ONE TcVggEngine per (precision, alpha, beta),
+    rebuilt when a weight tensor changes (data pointer / in-place version)."""
+
+    def __init__(self, convs, cfg):
+        self.convs, self.cfg = convs, cfg
+        self._eng = {}
+
+    def engine(self, precision, lrp_params):
+        from lrpx import tc
+        alpha, beta = float(lrp_params.get("alpha", 1.)), float(lrp_params.get("beta", 0.))
+        ignore_bias = bool(lrp_params.get("ignore_bias", True))
+        ws = [c.weight for c in self.convs]
+        bs = [c.bias for c in self.convs]
+        stamp = tuple((t.data_ptr(), t._version) for t in ws + [b for b in bs if b is not None])
+        key = (precision, alpha, beta, ignore_bias)
+        hit = self._eng.get(key)
+        if hit is None or hit[0] != stamp:
+            eng = tc.TcVggEngine(ws, bs, self.cfg, ws[0].device, precision=precision, alpha=alpha, beta=beta,
+                                 ignore_bias=ignore_bias)
+            hit = self._eng[key] = (stamp, eng)
+        return hit[1]
+
+
 def _build_plan(model):
     if isinstance(model, nn.Sequential):
         return _SequentialPlan(model)
@@ -198,12 +256,24 @@ def add_lrp(model):
             module.lrp_method = _method_for(module)
             module.lrp_params = preset.lrp_params
     model._lrpx_plan = _build_plan(model)
+    tcp = _tc_cfg(model)
+    model._lrpx_tc = _TcPlan(*tcp) if tcp is not None else None
     model.compute_lrp = lambda sample, **kwargs: compute_lrp(model, sample, **kwargs)
 
 
+# Arithmetic of ``compute_lrp`` when the caller does not say (a keyword the reference does not have):
+#   'fp32' — the reference's fp32 bar (rtol 1e-4 / atol 1e-6, scale-relative).  VGG-style encoders run the tcgen05
+#            chain with error-compensated bf16x3 operands and fp32 gains / inter-layer storage; every other
+#            topology runs the fp32 CUDA-core rule kernels.
+#   'bf16' — the tcgen05 chain with bf16 operands and storage (Spearman >= 0.99 / rel-L2 <= 5e-2 vs the reference).
+#   'simt' — the fp32 CUDA-core rule kernels whatever the topology (the rule-by-rule walker).
+DEFAULT_PRECISION = os.environ.get("LRPX_PRECISION", "fp32")
+
+
 def compute_lrp(model, sample, target=None, return_output=False, rectify_logits=False, explain_diff=False,
-                conservation_trace=None):
+                conservation_trace=None, precision=None):
     """reference :63-87.  ``rectify_logits`` / ``explain_diff`` are accepted and ignored, as there.
+    ``precision``: see DEFAULT_PRECISION above.
 
     Like the reference, the result is accumulated into ``sample.grad`` (the reference never zeroes it, so a
     second call on the same tensor returns the running sum — Q1).  Set LRPX_NO_GRAD_ACCUMULATION=1 to get the
@@ -215,13 +285,41 @@ def compute_lrp(model, sample, target=None, return_output=False, rectify_logits=
         raise RuntimeError("lrpx: compute_lrp needs a CUDA tensor (there is no CPU fallback)")
     if target is None:
         raise RuntimeError("grad can be implicitly created only for scalar outputs")   # what .backward(None) raises
+    precision = precision or DEFAULT_PRECISION
+    if precision not in ("fp32", "bf16", "simt"):
+        raise ValueError(f"compute_lrp: unknown precision {precision!r}")
+    tcp = getattr(model, "_lrpx_tc", None)
+    use_tc = tcp is not None and precision in ("fp32", "bf16") and conservation_trace is None and sample.dim() == 4
+    if use_tc:
+        params = tcp.convs[0].lrp_params
+        use_tc = all(c.lrp_method == "alpha_beta" and c.lrp_params == params for c in tcp.convs)
+        general = not (precision == "bf16" and params.get("alpha", 1.) == 1. and params.get("beta", 0.) == 0.
+                       and params.get("ignore_bias", True))
+        if general and tcp.convs[0].out_channels % 64:
+            use_tc = False                    # the general kernels need a 64-channel first layer: CUDA-core walker
+    if precision == "bf16" and not use_tc:
+        raise NotImplementedError("compute_lrp(precision='bf16'): the tensor-core chain covers VGG-style encoders "
+                                  "(conv3x3/ReLU/max-pool 2x2) under the alpha-beta rule only")
     with torch.no_grad():
         x = sample.detach()
-        logits = model._lrpx_plan.forward(x)
-        if tuple(target.shape) != tuple(logits.shape):
-            raise RuntimeError(f"Mismatch in shape: grad_output[0] has a shape of {tuple(target.shape)} and "
-                               f"output[0] has a shape of {tuple(logits.shape)}.")
-        R = model._lrpx_plan.backward(target.detach().float(), conservation_trace)
+        if use_tc:
+            # forward ONCE per call (the reference does the same, :70) + one contraction per layer per request
+            eng = tcp.engine(precision, params)
+            est = eng.forward(x)
+            fh, fw = est.feat_hw
+            want = (x.shape[0], est.feat_c, fh, fw)
+            if tuple(target.shape) != want:
+                raise RuntimeError(f"Mismatch in shape: grad_output[0] has a shape of {tuple(target.shape)} and "
+                                   f"output[0] has a shape of {want}.")
+            r_pix = target.detach().float().flatten(2).transpose(1, 2).contiguous()
+            R = eng.relevance(est, r_pix)
+            logits = eng.features(est, "nchw") if return_output else None
+        else:
+            logits = model._lrpx_plan.forward(x)
+            if tuple(target.shape) != tuple(logits.shape):
+                raise RuntimeError(f"Mismatch in shape: grad_output[0] has a shape of {tuple(target.shape)} and "
+                                   f"output[0] has a shape of {tuple(logits.shape)}.")
+            R = model._lrpx_plan.backward(target.detach().float(), conservation_trace)
     if os.environ.get("LRPX_NO_GRAD_ACCUMULATION", "0") == "1":
         output = R
     else:

@@ -26,6 +26,7 @@
 // DESIGN.md section 4.1 has the measurements behind each of these choices.
 #include "lrpx_common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include <stdlib.h>
 
@@ -75,6 +76,17 @@ struct TcParams {
   int debug_flags;   // env LRPX_TC_DEBUG: bit 0 = epilogue skips its global loads/stores (timing experiments only)
   int out_c;         // channel pitch of out / gain (elements per pixel row)
   int gain_mode;     // FWD_GAIN: 0 -> act/safe(z+), 1 -> 1/safe(z+)
+  // ---- general modes (MULX / MULX_UNPOOL / FWDX)
+  int a_wrap;        // physical 64-channel blocks per A row; K block kc >= a_wrap reads block kc - a_wrap (0 = no wrap)
+  int groups;        // MULX*: gain groups (1 | 2)
+  int split;         // 0: bf16 rows, bf16 gains; 1: hi|lo split rows, fp32 gains
+  int n_acc;         // FWDX: accumulators per output channel (W [, W+ [, W-]])
+  int rule;          // FWDX: 0 alpha-beta, 1 epsilon
+  int zbias;         // FWDX: bias enters the divisor
+  int cout;          // FWDX: output channels (row pitch of the gains; act pitch = cout * (1 + split))
+  float alpha, beta;
+  const void* gain2;
+  void* out3;
   const float* bias;
   const __nv_bfloat16* gain;
   const int32_t* row_img;
@@ -540,20 +552,205 @@ __device__ __forceinline__ void epi_input3(const TcParams& p, const RowInfo& r, 
 #pragma unroll
     for (int c = 0; c < 6; ++c) dn[c] = scratch[((quarter + 1) * 2 + 0) * 8 + c];
   if (!writes) return;
-  float* out = reinterpret_cast<float*>(p.out);
+  float res[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float xv = xin[c];
     const float cp = up[c] + __uint_as_float(v[8 + c]) + dn[c];
     const float cn = up[3 + c] + __uint_as_float(v[8 + 3 + c]) + dn[3 + c];
-    out[((size_t)r.e * 3 + c) * hw + pix] = fmaxf(xv, 0.f) * cp + fminf(xv, 0.f) * cn;
+    res[c] = fmaxf(xv, 0.f) * cp + fminf(xv, 0.f) * cn;
+  }
+  // delivery format (gain_mode): 0 = fp32 (Q,3,h,w), the reference's return value; 1 = channel mean fp32 (Q,h,w) — what
+  // every consumer in evaluation.py reduces a heat-map to first (:134,:411,:503: torch.mean(relevance, dim=(0,1)));
+  // 2 = fp16 (Q,3,h,w)
+  if (p.gain_mode == 1) {
+    reinterpret_cast<float*>(p.out)[(size_t)r.e * hw + pix] = ((res[0] + res[1]) + res[2]) / 3.f;
+  } else if (p.gain_mode == 2) {
+    __half* out = reinterpret_cast<__half*>(p.out);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[((size_t)r.e * 3 + c) * hw + pix] = __float2half_rn(res[c]);
+  } else {
+    float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[((size_t)r.e * 3 + c) * hw + pix] = res[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ general epilogues
+// value pair -> bf16x2 of the high parts and bf16x2 of the residuals (v = hi + lo to 16 significant bits)
+__device__ __forceinline__ void split_pack(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16(v0, v1);
+  lo = pack_bf16(v0 - bf16_lo(hi), v1 - bf16_hi(hi));
+}
+// 16 gains starting at element offset `off`: bf16 (32 bytes) or fp32 (64 bytes)
+__device__ __forceinline__ void load_gain16(const void* base, size_t off, bool f32, float (&g)[16]) {
+  if (f32) {
+    const U8 a = ldg_nc_v8(reinterpret_cast<const float*>(base) + off);
+    const U8 b = ldg_nc_v8(reinterpret_cast<const float*>(base) + off + 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { g[k] = __uint_as_float(a.w[k]); g[8 + k] = __uint_as_float(b.w[k]); }
+  } else {
+    const U8 a = ldg_nc_v8(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { g[2 * k] = bf16_lo(a.w[k]); g[2 * k + 1] = bf16_hi(a.w[k]); }
+  }
+}
+
+// MULX / MULX_UNPOOL: 32 accumulator columns [c, c+32) of this thread's row as two halves of 16.
+//   group j:  v = acc * gain_j  ->  out[row][j*N + n] (hi)  and, when split, out[row][(G+j)*N + n] (lo)
+// UNPOOL: the row is a pooled pixel; the products go to the winner of its 2x2 fine block, zeros to the other three.
+template <bool UNPOOL>
+__device__ __forceinline__ void epi_mulx(const TcParams& p, const RowInfo& r, uint32_t taddr, int n0, int c,
+                                         uint32_t release_bar) {
+  const int N = p.ncol, G = p.groups;
+  const bool sp = p.split != 0;
+  const int img = (r.valid && p.row_img) ? p.row_img[r.e] : r.e;
+  const size_t gbase = ((size_t)img * p.blk + r.rem) * (size_t)N;
+  __nv_bfloat16* const out = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll 1
+  for (int q = 0; q < 2; ++q) {
+    const int col = n0 + c + 16 * q;
+    float g[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) g[k] = 0.f;
+    uint4 sidx = make_uint4(0u, 0u, 0u, 0u);
+    if (r.valid) {
+      load_gain16(p.gain, gbase + col, sp, g);
+      if (UNPOOL) sidx = ldg_nc_v4(p.pool_idx + gbase + col);
+    }
+    uint32_t v[16];
+    TMEM_LD_X16(taddr + c + 16 * q, v);
+    tmem_ld_wait();
+    if (q == 1) epi_release(release_bar);
+    if (!r.in_range) continue;
+#pragma unroll 1
+    for (int j = 0; j < G; ++j) {
+      if (j == 1 && r.valid) load_gain16(p.gain2, gbase + col, sp, g);
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float a0 = r.valid ? __uint_as_float(v[2 * k]) * g[2 * k] : 0.f;
+        const float a1 = r.valid ? __uint_as_float(v[2 * k + 1]) * g[2 * k + 1] : 0.f;
+        split_pack(a0, a1, hi[k], lo[k]);
+      }
+      if (!UNPOOL) {
+        __nv_bfloat16* dst = out + (size_t)r.row * p.out_c + col;
+        stg_v8(dst + (size_t)j * N, hi);
+        if (sp) stg_v8(dst + (size_t)(G + j) * N, lo);
+      } else {
+        const int wf1 = 2 * p.w + 1;
+        const size_t blk_f = (size_t)(2 * p.h + 1) * wf1;
+        __nv_bfloat16* const outb = out + (size_t)r.e * blk_f * p.out_c + col;
+        const uint32_t sw[4] = {sidx.x, sidx.y, sidx.z, sidx.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int fr = 2 * r.a - 1 + (k >> 1), fc = 2 * r.b - 1 + (k & 1);
+          if (fr < 0 || fc < 0) continue;
+          __nv_bfloat16* dst = outb + ((size_t)fr * wf1 + fc) * p.out_c;
+          uint32_t oh[8], ol[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const uint32_t w4 = sw[m >> 1];
+            const uint32_t b0 = (w4 >> (16 * (m & 1))) & 0xFF, b1 = (w4 >> (16 * (m & 1) + 8)) & 0xFF;
+            const uint32_t mask = (b0 == (uint32_t)k ? 0xFFFFu : 0u) | (b1 == (uint32_t)k ? 0xFFFF0000u : 0u);
+            oh[m] = hi[m] & mask;
+            ol[m] = lo[m] & mask;
+          }
+          stg_v8(dst + (size_t)j * N, oh);
+          if (sp) stg_v8(dst + (size_t)(G + j) * N, ol);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void stg_f32x16(float* dst, const float (&v)[16]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __float_as_uint(v[8 * h + k]);
+    stg_v8(dst + 8 * h, w);
+  }
+}
+
+// FWDX: 32 output channels [c, c+32) of tile column block n_tile (see LRPX_TC_EPI_FWDX in lrpx.h)
+__device__ __forceinline__ void epi_fwdx(const TcParams& p, const RowInfo& r, uint32_t taddr, int n_tile, int c,
+                                         uint32_t release_bar) {
+  const bool sp = p.split != 0;
+  const int cout = p.cout;
+#pragma unroll 1
+  for (int q = 0; q < 2; ++q) {
+    const int ch = n_tile * p.half + c + 16 * q;
+    uint32_t vw[16], vp[16], vn[16];
+    TMEM_LD_X16(taddr + c + 16 * q, vw);
+    if (p.n_acc >= 2) TMEM_LD_X16(taddr + p.half + c + 16 * q, vp);
+    if (p.n_acc >= 3) TMEM_LD_X16(taddr + 2 * p.half + c + 16 * q, vn);
+    tmem_ld_wait();
+    if (q == 1) epi_release(release_bar);
+    if (!r.in_range) continue;
+    float bv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) bv[k] = 0.f;
+    if (p.bias) {
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + ch) + k4);
+        bv[4 * k4] = t.x; bv[4 * k4 + 1] = t.y; bv[4 * k4 + 2] = t.z; bv[4 * k4 + 3] = t.w;
+      }
+    }
+    float act[16], g0[16], g1[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float zw = __uint_as_float(vw[k]);
+      const float a = r.valid ? fmaxf(zw + bv[k], 0.f) : 0.f;
+      act[k] = a;
+      const float num = p.gain_mode ? 1.f : a;
+      float q0 = 0.f, q1 = 0.f;
+      if (p.rule == 0) {
+        float zp = __uint_as_float(vp[k]) + (p.zbias ? bv[k] : 0.f);
+        zp += (zp == 0.f ? LRPX_Z_EPSILON : 0.f);                   // safe_divide, utils.py:16-18
+        q0 = p.alpha * num / zp;
+        if (p.n_acc >= 3) {
+          float zn = __uint_as_float(vn[k]) + (p.zbias ? bv[k] : 0.f);
+          zn += (zn == 0.f ? LRPX_Z_EPSILON : 0.f);
+          q1 = -p.beta * num / zn;
+        }
+      } else {
+        const float zr = zw + (p.zbias ? bv[k] : 0.f);
+        const float nq = (num == 0.f) ? -1e-6f : num;               // zeros of the input count as -1e-6 (Q9)
+        q0 = p.zbias ? nq / zr : nq / stab(zr);                     // the bias branch is unstabilised (lrp_modules.py:20-21)
+      }
+      g0[k] = r.valid ? q0 : 0.f;
+      g1[k] = r.valid ? q1 : 0.f;
+    }
+    // activations: bf16 row, or hi | lo halves of a 2*cout row
+    {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) split_pack(act[2 * k], act[2 * k + 1], hi[k], lo[k]);
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * (size_t)(cout * (sp ? 2 : 1)) + ch;
+      stg_v8(dst, hi);
+      if (sp) stg_v8(dst + cout, lo);
+    }
+    const size_t go = (size_t)r.row * cout + ch;
+    if (sp) {
+      stg_f32x16(reinterpret_cast<float*>(p.out2) + go, g0);
+      if (p.out3) stg_f32x16(reinterpret_cast<float*>(p.out3) + go, g1);
+    } else {
+      uint32_t w0[8], w1[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { w0[k] = pack_bf16(g0[2 * k], g0[2 * k + 1]); w1[k] = pack_bf16(g1[2 * k], g1[2 * k + 1]); }
+      stg_v8(reinterpret_cast<__nv_bfloat16*>(p.out2) + go, w0);
+      if (p.out3) stg_v8(reinterpret_cast<__nv_bfloat16*>(p.out3) + go, w1);
+    }
   }
 }
 
 // number of 32-column units per (lane quarter, M half) of a tile
 __device__ __forceinline__ int epi_units_per_half(const TcParams& p, int epi) {
   if (epi == LRPX_TC_EPI_INPUT || epi == LRPX_TC_EPI_INPUT3) return 1;
-  const int ncols = (epi == LRPX_TC_EPI_FWD_GAIN) ? p.half : p.bn;
+  const int ncols = (epi == LRPX_TC_EPI_FWD_GAIN || epi == LRPX_TC_EPI_FWDX) ? p.half : p.bn;
   return ncols >> 5;
 }
 
@@ -570,6 +767,12 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
   const int n0 = n_tile * p.bn;
   if (EPI == LRPX_TC_EPI_INPUT3) {
     epi_input3(p, r0, taddr, release_bar, scratch, quarter, bar_id);
+  } else if (EPI == LRPX_TC_EPI_MULX) {
+    epi_mulx<false>(p, r, taddr, n0, c, release_bar);
+  } else if (EPI == LRPX_TC_EPI_MULX_UNPOOL) {
+    epi_mulx<true>(p, r, taddr, n0, c, release_bar);
+  } else if (EPI == LRPX_TC_EPI_FWDX) {
+    epi_fwdx(p, r, taddr, n_tile, c, release_bar);
   } else if (EPI == LRPX_TC_EPI_INPUT) {
     uint32_t v[16];
     TMEM_LD_X16(taddr, v);
@@ -786,7 +989,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t fb = smem_u32(&full_bar[stage]);
             const uint32_t sa = smem_base + stage * stage_bytes;
             mbar_expect_tx(fb, stage_bytes);
-            tma_load_2d(sa, &tmA, fb, kc * TC_BK, m0 + off);
+            const int kca = (p.a_wrap && kc >= p.a_wrap) ? kc - p.a_wrap : kc;      // hi | lo | hi view of a split row
+            tma_load_2d(sa, &tmA, fb, kca * TC_BK, m0 + off);
             tma_load_2d(sa + TC_A_BYTES, &tmB, fb, tap * p.cin + kc * TC_BK, n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -1049,8 +1253,9 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             } else {
               mbar_expect_tx(fb, a_tx);
               const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
-              tma_load_2d(dst, &tmA0, fb, kc * TC_BK, row0);
-              if (p.box1_rows) tma_load_2d(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kc * TC_BK, row0 + p.box0_rows);
+              const int kca = (p.a_wrap && kc >= p.a_wrap) ? kc - p.a_wrap : kc;    // hi | lo | hi view of a split row
+              tma_load_2d(dst, &tmA0, fb, kca * TC_BK, row0);
+              if (p.box1_rows) tma_load_2d(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kca * TC_BK, row0 + p.box0_rows);
             }
             if (++as == p.a_stages) { as = 0; aph ^= 1; }
           }
@@ -1387,8 +1592,35 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
   p.bias = a->bias; p.gain = reinterpret_cast<const __nv_bfloat16*>(a->gain);
   p.row_img = a->row_img; p.pool_idx = a->pool_idx; p.x = a->x; p.x1 = a->x1; p.out = a->out; p.out2 = a->out2;
   p.gain_mode = a->gain_mode;
+  // ---- general modes
+  const int a_phys = a->a_phys > 0 ? a->a_phys : a->cin;
+  LRPX_CHECK_ARG(a_phys % TC_BK == 0 && a_phys <= a->cin && (a_phys == a->cin || a->cin <= 2 * a_phys),
+                 "a_phys must be a multiple of 64 with cin/2 <= a_phys <= cin");
+  p.a_wrap = a_phys < a->cin ? a_phys / TC_BK : 0;
+  p.groups = a->groups > 0 ? a->groups : 1;
+  p.split = a->split; p.n_acc = a->n_acc; p.rule = a->rule; p.zbias = a->zbias;
+  p.alpha = a->alpha; p.beta = a->beta; p.gain2 = a->gain2; p.out3 = a->out3;
 
-  if (epi == LRPX_TC_EPI_FWD_GAIN) {
+  if (epi == LRPX_TC_EPI_FWDX) {
+    LRPX_CHECK_ARG(a->out2 && a->n_acc >= 1 && a->n_acc <= 3 && a->ncol % a->n_acc == 0, "FWDX: out2 and n_acc in 1..3");
+    LRPX_CHECK_ARG((a->rule == 0 && a->n_acc >= 2) || (a->rule == 1 && a->n_acc == 1), "FWDX: alpha-beta needs W and W+ (n_acc >= 2), epsilon n_acc == 1");
+    LRPX_CHECK_ARG(a->out3 == nullptr || a->n_acc == 3, "FWDX: out3 (gain of the neg-net) needs n_acc == 3");
+    const int cout = a->ncol / a->n_acc;
+    LRPX_CHECK_ARG(cout % 32 == 0, "FWDX: output channels must be a multiple of 32");
+    const int cap = a->n_acc == 3 ? 64 : (a->n_acc == 2 ? 128 : 256);      // n_acc * half <= 256 TMEM columns per buffer
+    p.half = cout < cap ? cout : cap;
+    LRPX_CHECK_ARG(cout % p.half == 0, "FWDX: output channels must divide into tiles of 64 / 128 / 256");
+    p.bn = a->n_acc * p.half;
+    p.cout = cout;
+    p.out_c = cout;
+  } else if (epi == LRPX_TC_EPI_MULX || epi == LRPX_TC_EPI_MULX_UNPOOL) {
+    LRPX_CHECK_ARG(a->gain && (p.groups == 1 || (p.groups == 2 && a->gain2)), "MULX: gain (and gain2 for two groups) required");
+    LRPX_CHECK_ARG(epi != LRPX_TC_EPI_MULX_UNPOOL || a->pool_idx, "pool_idx required");
+    LRPX_CHECK_ARG(a->ncol % 32 == 0, "ncol must be a multiple of 32 for this epilogue");
+    p.bn = a->ncol <= 256 ? a->ncol : 256;
+    LRPX_CHECK_ARG(a->ncol % p.bn == 0, "ncol must be <= 256 or a multiple of 256");
+    p.out_c = a->ncol * p.groups * (p.split ? 2 : 1);
+  } else if (epi == LRPX_TC_EPI_FWD_GAIN) {
     // Wt holds, per tile of `half` output channels, the W rows followed by the W+ rows: ncol = 2 * cout
     LRPX_CHECK_ARG(a->out2, "FWD_GAIN needs out2 (gain)");
     int cout = a->ncol / 2;
@@ -1457,9 +1689,9 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
         int rco = make_map_out(&mo, a->out, (uint64_t)p.m_total, (uint64_t)p.out_c);
         if (rco) return rco;
       }
-      int rc = make_map_2d(&ma0, a->a, (uint64_t)p.m_total, (uint64_t)a->cin, (uint32_t)p.box0_rows);
+      int rc = make_map_2d(&ma0, a->a, (uint64_t)p.m_total, (uint64_t)a_phys, (uint32_t)p.box0_rows);
       if (rc) return rc;
-      rc = make_map_2d(&ma1, a->a, (uint64_t)p.m_total, (uint64_t)a->cin, (uint32_t)(p.box1_rows ? p.box1_rows : 8));
+      rc = make_map_2d(&ma1, a->a, (uint64_t)p.m_total, (uint64_t)a_phys, (uint32_t)(p.box1_rows ? p.box1_rows : 8));
       if (rc) return rc;
       rc = make_map_2d(&mb, a->wt, (uint64_t)a->ncol, (uint64_t)p.taps * a->cin, (uint32_t)p.bn);
       if (rc) return rc;
@@ -1485,6 +1717,9 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
         case LRPX_TC_EPI_MUL_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MUL_UNPOOL>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_INPUT: return launch_tc_slab<LRPX_TC_EPI_INPUT>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_INPUT3: return launch_tc_slab<LRPX_TC_EPI_INPUT3>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        case LRPX_TC_EPI_MULX: return launch_tc_slab<LRPX_TC_EPI_MULX>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        case LRPX_TC_EPI_MULX_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MULX_UNPOOL>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        case LRPX_TC_EPI_FWDX: return launch_tc_slab<LRPX_TC_EPI_FWDX>(ma0, ma1, mb, mbh, mo, p, grid, st);
         default: return launch_tc_slab<LRPX_TC_EPI_STORE_F32>(ma0, ma1, mb, mbh, mo, p, grid, st);
       }
     }
@@ -1498,7 +1733,7 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
   LRPX_CHECK_ARG(p.stages >= 2, "tile does not fit in shared memory");
 
   CUtensorMap ma, mb;
-  int rc = make_map_2d(&ma, a->a, (uint64_t)p.m_total, (uint64_t)a->cin, TC_BM);
+  int rc = make_map_2d(&ma, a->a, (uint64_t)p.m_total, (uint64_t)a_phys, TC_BM);
   if (rc) return rc;
   rc = make_map_2d(&mb, a->wt, (uint64_t)a->ncol, (uint64_t)p.taps * a->cin, (uint32_t)p.bn);
   if (rc) return rc;
@@ -1512,6 +1747,9 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     case LRPX_TC_EPI_INPUT: return launch_tc<LRPX_TC_EPI_INPUT>(ma, mb, p, grid, st);
     case LRPX_TC_EPI_FEAT: return launch_tc<LRPX_TC_EPI_FEAT>(ma, mb, p, grid, st);
     case LRPX_TC_EPI_FEAT_DIV: return launch_tc<LRPX_TC_EPI_FEAT_DIV>(ma, mb, p, grid, st);
+    case LRPX_TC_EPI_MULX: return launch_tc<LRPX_TC_EPI_MULX>(ma, mb, p, grid, st);
+    case LRPX_TC_EPI_MULX_UNPOOL: return launch_tc<LRPX_TC_EPI_MULX_UNPOOL>(ma, mb, p, grid, st);
+    case LRPX_TC_EPI_FWDX: return launch_tc<LRPX_TC_EPI_FWDX>(ma, mb, p, grid, st);
     default: return launch_tc<LRPX_TC_EPI_STORE_F32>(ma, mb, p, grid, st);
   }
 }

@@ -176,6 +176,63 @@ __global__ void sum_f64_kernel(const float* __restrict__ x, size_t n, double* ou
   }
 }
 
+
+// ---------------------------------------------------------------- named vector rules of the explainers
+// lrp_linear_eps (gridTDmodel.py:744-765, aoamodel.py:785-810): R_in[j] = x_j * sum_k W[k][j] * r_k / stab(z_k),
+// stab(z) = z + 0.01 sign z (0 -> 0.01); z = W x when the caller passes forward_output=False.
+// (1) one warp per output row: t_k = r_k / stab(z_k), z_k recomputed when z == nullptr
+__global__ void lin_eps_t_kernel(const float* __restrict__ r, const float* __restrict__ x, const float* __restrict__ z,
+                                 const float* __restrict__ W, float* __restrict__ t, int n_out, int n_in) {
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (k >= n_out) return;
+  float zk;
+  if (z) {
+    zk = z[k];
+  } else {
+    float acc = 0.f;
+    for (int j = lane; j < n_in; j += 32) acc = fmaf(W[(size_t)k * n_in + j], x[j], acc);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    zk = acc;
+  }
+  if (lane == 0) t[k] = r[k] / stab(zk);
+}
+// (2) column sums over a slice of the rows (coalesced along j), deterministic: part[s][j] = sum_{k in slice s} W[k][j] t_k
+__global__ void lin_eps_part_kernel(const float* __restrict__ W, const float* __restrict__ t, float* __restrict__ part,
+                                    int n_out, int n_in, int rows_per_slice) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  if (j >= n_in) return;
+  const int k0 = s * rows_per_slice, k1 = min(n_out, k0 + rows_per_slice);
+  float acc = 0.f;
+  for (int k = k0; k < k1; ++k) acc = fmaf(W[(size_t)k * n_in + j], t[k], acc);
+  part[(size_t)s * n_in + j] = acc;
+}
+__global__ void lin_eps_final_kernel(const float* __restrict__ part, const float* __restrict__ x, float* __restrict__ out,
+                                     int n_in, int slices) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_in) return;
+  float acc = 0.f;
+  for (int s = 0; s < slices; ++s) acc += part[(size_t)s * n_in + j];
+  out[j] = x[j] * acc;
+}
+static inline int lin_eps_slices(int n_out) {
+  int s = (n_out + 63) / 64;
+  return s < 1 ? 1 : (s > 128 ? 128 : s);
+}
+
+// lrp_mha (aoamodel.py:812-862): r_val[p][head*dk + d] = v[p][..] * alpha[head][p] * r_ctx[..] / stab(ctx[..]); other heads 0
+__global__ void lrp_mha_kernel(const float* __restrict__ alpha, const float* __restrict__ value,
+                               const float* __restrict__ r_ctx, const float* __restrict__ ctx, float* __restrict__ out,
+                               int P, int H, int num_head, int head) {
+  const int dk = H / num_head;
+  const long long total = (long long)P * H;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i / H), c = (int)(i % H);
+    float v = 0.f;
+    if (c / dk == head) v = value[i] * alpha[(size_t)head * P + p] * r_ctx[c] / stab(ctx[c]);
+    out[i] = v;
+  }
+}
+
 static inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   long long cap = 148LL * 16;
@@ -276,6 +333,38 @@ int lrpx_sum_f64(const float* x, size_t count, double* out, void* stream) {
   cudaMemsetAsync(out, 0, sizeof(double), as_stream(stream));
   if (count == 0) return LRPX_OK;
   sum_f64_kernel<<<grid_for((long long)count), 256, 0, as_stream(stream)>>>(x, count, out);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+size_t lrpx_lrp_linear_eps_workspace_bytes(int n_out, int n_in) {
+  if (n_out <= 0 || n_in <= 0) return 0;
+  return ((size_t)n_out + (size_t)lin_eps_slices(n_out) * n_in) * sizeof(float);
+}
+
+int lrpx_lrp_linear_eps_f32(const float* r_out, const float* x, const float* z, const float* W, float* r_in, int n_out,
+                            int n_in, void* workspace, size_t workspace_bytes, void* stream) {
+  LRPX_CHECK_ARG(r_out && x && W && r_in && n_out > 0 && n_in > 0, "bad argument");
+  LRPX_CHECK_ARG(workspace && workspace_bytes >= lrpx_lrp_linear_eps_workspace_bytes(n_out, n_in), "workspace too small");
+  cudaStream_t st = as_stream(stream);
+  float* t = reinterpret_cast<float*>(workspace);
+  float* part = t + n_out;
+  const int slices = lin_eps_slices(n_out), rps = (n_out + slices - 1) / slices;
+  lin_eps_t_kernel<<<(n_out + 7) / 8, 256, 0, st>>>(r_out, x, z, W, t, n_out, n_in);
+  LRPX_CHECK_LAUNCH();
+  lin_eps_part_kernel<<<dim3((n_in + 127) / 128, slices), 128, 0, st>>>(W, t, part, n_out, n_in, rps);
+  LRPX_CHECK_LAUNCH();
+  lin_eps_final_kernel<<<(n_in + 127) / 128, 128, 0, st>>>(part, x, r_in, n_in, slices);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_lrp_mha_f32(const float* alpha, const float* value, const float* r_context, const float* context, float* r_value,
+                     int P, int H, int num_head, int head_idx, void* stream) {
+  LRPX_CHECK_ARG(alpha && value && r_context && context && r_value && P > 0 && H > 0 && num_head > 0 && H % num_head == 0 &&
+                     head_idx >= 0 && head_idx < num_head, "bad argument");
+  lrp_mha_kernel<<<grid_for((long long)P * H), 256, 0, as_stream(stream)>>>(alpha, value, r_context, context, r_value, P, H,
+                                                                           num_head, head_idx);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;
 }

@@ -329,11 +329,262 @@ __global__ void im2col3_split_kernel(const float* __restrict__ x, uint32_t* __re
   }
 }
 
+
+// ---------------------------------------------------------------- companions of the general (groups / split) modes
+// A hi|lo split row of C logical channels holds 2*C bf16: [hi(0..C) | lo(0..C)], value = hi + lo (16 significant bits).
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __uint_as_float(hi << 16), v1 - __uint_as_float(hi & 0xFFFF0000u));
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+// sign-split im2col with hi|lo rows: 128 columns [hi of the 64 | lo of the 64]; one thread per (PF row, 8 columns)
+__global__ void im2col3_split_x_kernel(const float* __restrict__ x, uint4* __restrict__ dst, int n, int h, int w) {
+  const int wp1 = w + 1, blk = (h + 1) * wp1;
+  const long long total = (long long)n * blk * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i & 7);
+    const long long prow = i >> 3;
+    const int img = (int)(prow / blk), rem = (int)(prow % blk);
+    const int a = rem / wp1, b = rem % wp1;
+    uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+    if (a > 0 && b > 0) {
+      const float* xi = x + (size_t)img * 3 * h * w;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = cg * 8 + k;                 // column 0..26: x+ of tap e, 27..53: x- of tap e-27, 54..63: 0
+        float f = 0.f;
+        if (e < 54) {
+          const int t = e < 27 ? e : e - 27;
+          const int ci = t / 9, rr = (t % 9) / 3, ss = t % 3;
+          const int yy = a - 1 + rr - 1, xs = b - 1 + ss - 1;
+          const float xv = (yy >= 0 && yy < h && xs >= 0 && xs < w) ? __ldg(xi + ((size_t)ci * h + yy) * w + xs) : 0.f;
+          f = e < 27 ? fmaxf(xv, 0.f) : fminf(xv, 0.f);
+        }
+        v[k] = f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
+    }
+    dst[prow * 16 + cg] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    dst[prow * 16 + 8 + cg] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// 2x2/2 max-pool, 8 channels per thread, for bf16 or hi|lo rows and up to two gain tensors (bf16, or fp32 with split).
+// Scan order (0,0),(0,1),(1,0),(1,1); strict '>' so the first maximum wins, NaN wins (max_pool2d_with_indices).
+template <bool SPLIT>
+__global__ void maxpool2_x_kernel(const uint4* __restrict__ act, const void* __restrict__ g0, const void* __restrict__ g1,
+                                  uint4* __restrict__ pooled, uint2* __restrict__ idx, void* __restrict__ gp0,
+                                  void* __restrict__ gp1, int n, int h, int w, int c8) {
+  const int oh = h / 2, ow = w / 2;
+  const int wp1 = w + 1, owp1 = ow + 1;
+  const long long blk_f = (long long)(h + 1) * wp1, blk_p = (long long)(oh + 1) * owp1;
+  const long long total = (long long)n * blk_p * c8;
+  const int rowv = SPLIT ? 2 * c8 : c8;            // uint4 per activation row
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long prow = i / c8;
+    const int cc = (int)(i - prow * c8);
+    const long long img = prow / blk_p;
+    const int rem = (int)(prow - img * blk_p);
+    const int a = rem / owp1, b = rem - a * owp1;
+    uint32_t ohi[4] = {0u, 0u, 0u, 0u}, olo[4] = {0u, 0u, 0u, 0u};
+    uint32_t bidx[8];
+    float og0[8], og1[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { bidx[e] = 0u; og0[e] = 0.f; og1[e] = 0.f; }
+    if (a > 0 && b > 0) {
+      const long long frow0 = img * blk_f + (long long)(2 * a - 1) * wp1 + (2 * b - 1);
+      const long long frow[4] = {frow0, frow0 + 1, frow0 + wp1, frow0 + wp1 + 1};
+      float best[8];
+      uint32_t bh[8], bl[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bh[e] = 0u; bl[e] = 0u; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint4 vh = act[frow[k] * rowv + cc];
+        const uint4 vl = SPLIT ? act[frow[k] * rowv + c8 + cc] : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w}, lw[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t hb = (hw[e >> 1] >> (16 * (e & 1))) & 0xFFFFu, lb = (lw[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+          const float f = __uint_as_float(hb << 16) + __uint_as_float(lb << 16);
+          if (f > best[e] || f != f) { best[e] = f; bh[e] = hb; bl[e] = lb; bidx[e] = (uint32_t)k; }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        ohi[e >> 1] |= bh[e] << (16 * (e & 1));
+        olo[e >> 1] |= bl[e] << (16 * (e & 1));
+      }
+      // gains gathered at the winner (run-time row choice through the pointer, not through a register array)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const long long fr = frow0 + (bidx[e] >> 1) * wp1 + (bidx[e] & 1);
+        const size_t go = (size_t)fr * (c8 * 8) + cc * 8 + e;
+        if (SPLIT) {
+          if (g0) og0[e] = __ldg(reinterpret_cast<const float*>(g0) + go);
+          if (g1) og1[e] = __ldg(reinterpret_cast<const float*>(g1) + go);
+        } else {
+          if (g0) og0[e] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g0)[go]);
+          if (g1) og1[e] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g1)[go]);
+        }
+      }
+    }
+    pooled[prow * rowv + cc] = make_uint4(ohi[0], ohi[1], ohi[2], ohi[3]);
+    if (SPLIT) pooled[prow * rowv + c8 + cc] = make_uint4(olo[0], olo[1], olo[2], olo[3]);
+    if (idx) idx[i] = make_uint2(bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24),
+                                 bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      void* gp = j ? gp1 : gp0;
+      const float* og = j ? og1 : og0;
+      if (!gp) continue;
+      if (SPLIT) {
+        float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(gp) + (size_t)i * 8);
+        d[0] = make_float4(og[0], og[1], og[2], og[3]);
+        d[1] = make_float4(og[4], og[5], og[6], og[7]);
+      } else {
+        uint32_t wv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          __nv_bfloat162 t = __floats2bfloat162_rn(og[2 * k], og[2 * k + 1]);
+          wv[k] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        reinterpret_cast<uint4*>(gp)[i] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      }
+    }
+  }
+}
+
+// chain entry of the general modes: out row = [r*rz0 | r*rz1] (groups) as bf16 or hi|lo
+template <bool SPLIT>
+__global__ void scale_rows_x_kernel(const float* __restrict__ r, const void* __restrict__ rz0, const void* __restrict__ rz1,
+                                    const int32_t* __restrict__ row_img, uint4* __restrict__ out, int h, int w, int c8,
+                                    int groups, long long total) {
+  const int wp1 = w + 1, blk = (h + 1) * wp1;
+  const int rowv = c8 * groups * (SPLIT ? 2 : 1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c8);
+    const long long prow = i / c8;
+    const int e = (int)(prow / blk), rem = (int)(prow % blk);
+    const int a = rem / wp1, b = rem % wp1;
+    const bool valid = a > 0 && b > 0;
+    float rv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rv[k] = 0.f;
+    int img = 0;
+    if (valid) {
+      img = row_img ? row_img[e] : e;
+      const float4* rp = reinterpret_cast<const float4*>(r + (((size_t)e * h + (a - 1)) * w + (b - 1)) * (c8 * 8) + cc * 8);
+      const float4 r0 = rp[0], r1 = rp[1];
+      rv[0] = r0.x; rv[1] = r0.y; rv[2] = r0.z; rv[3] = r0.w; rv[4] = r1.x; rv[5] = r1.y; rv[6] = r1.z; rv[7] = r1.w;
+    }
+    for (int j = 0; j < groups; ++j) {
+      const void* rz = j ? rz1 : rz0;
+      float gz[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gz[k] = 0.f;
+      if (valid) {
+        const size_t go = ((size_t)img * blk + rem) * (c8 * 8) + cc * 8;
+        if (SPLIT) {
+          const float4* gp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rz) + go);
+          const float4 g0 = gp[0], g1 = gp[1];
+          gz[0] = g0.x; gz[1] = g0.y; gz[2] = g0.z; gz[3] = g0.w; gz[4] = g1.x; gz[5] = g1.y; gz[6] = g1.z; gz[7] = g1.w;
+        } else {
+          const uint4 g = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(rz) + go);
+          const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { gz[2 * k] = bf_lo(gw[k]); gz[2 * k + 1] = bf_hi(gw[k]); }
+        }
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split2(rv[2 * k] * gz[2 * k], rv[2 * k + 1] * gz[2 * k + 1], hi[k], lo[k]);
+      out[prow * rowv + (size_t)j * c8 + cc] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (SPLIT) out[prow * rowv + (size_t)(groups + j) * c8 + cc] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+__global__ void pf_split_to_dense_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int n, int h,
+                                         int w, int c, int layout) {
+  const int wp1 = w + 1, blk = (h + 1) * wp1;
+  long long total = (long long)n * h * w * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch, y, x, img;
+    if (layout == 0) {
+      ch = (int)(i % c);
+      long long pix = i / c;
+      x = (int)(pix % w); y = (int)((pix / w) % h); img = (int)(pix / ((long long)w * h));
+    } else {
+      x = (int)(i % w); y = (int)((i / w) % h);
+      ch = (int)((i / ((long long)w * h)) % c); img = (int)(i / ((long long)w * h * c));
+    }
+    const size_t o = ((size_t)img * blk + (size_t)(y + 1) * wp1 + (x + 1)) * (2 * c) + ch;
+    dst[i] = __bfloat162float(src[o]) + __bfloat162float(src[o + c]);
+  }
+}
+
 }  // namespace lrpx
 
 using namespace lrpx;
 
 extern "C" {
+
+int lrpx_tc_im2col3_split_x(const float* x, void* dst, int n, int h, int w, int split, void* stream) {
+  if (!split) return lrpx_tc_im2col3_split_bf16(x, dst, n, h, w, stream);
+  LRPX_CHECK_ARG(x && dst && n > 0 && h > 0 && w > 0, "bad argument");
+  long long total = (long long)n * (h + 1) * (w + 1) * 8;
+  im2col3_split_x_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, (uint4*)dst, n, h, w);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_tc_maxpool2_x(const void* act, const void* gain0_fine, const void* gain1_fine, void* pooled, uint8_t* idx,
+                       void* gain0_pooled, void* gain1_pooled, int n, int h, int w, int c, int split, void* stream) {
+  LRPX_CHECK_ARG(act && pooled && n > 0 && h > 0 && w > 0 && c > 0 && (h % 2) == 0 && (w % 2) == 0 && (c % 8) == 0,
+                 "bad argument (h, w even and c % 8 == 0 required)");
+  LRPX_CHECK_ARG((gain0_fine == nullptr) == (gain0_pooled == nullptr) && (gain1_fine == nullptr) == (gain1_pooled == nullptr),
+                 "fine and pooled gains go together");
+  long long total = (long long)n * (h / 2 + 1) * (w / 2 + 1) * (c / 8);
+  if (split)
+    maxpool2_x_kernel<true><<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)act, gain0_fine, gain1_fine,
+        (uint4*)pooled, (uint2*)idx, gain0_pooled, gain1_pooled, n, h, w, c / 8);
+  else
+    maxpool2_x_kernel<false><<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)act, gain0_fine, gain1_fine,
+        (uint4*)pooled, (uint2*)idx, gain0_pooled, gain1_pooled, n, h, w, c / 8);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_tc_scale_rows_x(const float* r, const void* rz0, const void* rz1, const int32_t* row_img, void* out,
+                         int n_expl, int h, int w, int c, int groups, int split, void* stream) {
+  LRPX_CHECK_ARG(r && rz0 && out && n_expl > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "bad argument");
+  LRPX_CHECK_ARG(groups == 1 || (groups == 2 && rz1), "groups must be 1, or 2 with rz1");
+  long long total = (long long)n_expl * (h + 1) * (w + 1) * (c / 8);
+  if (split)
+    scale_rows_x_kernel<true><<<grid_for(total), 256, 0, as_stream(stream)>>>(r, rz0, rz1, row_img, (uint4*)out, h, w,
+                                                                             c / 8, groups, total);
+  else
+    scale_rows_x_kernel<false><<<grid_for(total), 256, 0, as_stream(stream)>>>(r, rz0, rz1, row_img, (uint4*)out, h, w,
+                                                                              c / 8, groups, total);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_tc_pf_split_to_dense_f32(const void* src, float* dst, int n, int h, int w, int c, int layout, void* stream) {
+  LRPX_CHECK_ARG(src && dst && n > 0 && h > 0 && w > 0 && c > 0 && (layout == 0 || layout == 1), "bad argument");
+  long long total = (long long)n * h * w * c;
+  pf_split_to_dense_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, dst, n, h, w, c, layout);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
 
 int lrpx_tc_im2col3_split_bf16(const float* x, void* dst, int n, int h, int w, void* stream) {
   LRPX_CHECK_ARG(x && dst && n > 0 && h > 0 && w > 0, "bad argument");

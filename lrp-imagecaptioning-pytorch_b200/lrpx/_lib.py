@@ -53,7 +53,10 @@ class AdaptiveArgs(C.Structure):
 
 class TcConvArgs(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n_img", "h", "w", "cin", "ncol", "ksize", "epilogue", "gain_mode")] + \
-               [(n, _P) for n in ("a", "wt", "bias", "gain", "row_img", "pool_idx", "x", "out", "out2", "x1")]
+               [(n, _P) for n in ("a", "wt", "bias", "gain", "row_img", "pool_idx", "x", "out", "out2", "x1", "gain2",
+                                  "out3")] + \
+               [(n, C.c_int) for n in ("a_phys", "groups", "split", "n_acc", "rule", "zbias")] + \
+               [("alpha", C.c_float), ("beta", C.c_float)]
 
 
 _LL = C.c_longlong
@@ -124,6 +127,9 @@ SYMBOLS = {
     "lrpx_relu_mask_f32": (_i, [_P, _P, _P, _sz, _P]),
     "lrpx_normalize_relevance_f32": (_i, [_P, _P, _i, _i, _f, _P]),
     "lrpx_sum_f64": (_i, [_P, _sz, _P, _P]),
+    "lrpx_lrp_linear_eps_workspace_bytes": (_sz, [_i, _i]),
+    "lrpx_lrp_linear_eps_f32": (_i, [_P, _P, _P, _P, _P, _i, _i, _P, _sz, _P]),
+    "lrpx_lrp_mha_f32": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "lrpx_gridtd_decoder_workspace_bytes": (_sz, [C.POINTER(GridTDArgs)]),
     "lrpx_gridtd_decoder_lrp_f32": (_i, [C.POINTER(GridTDArgs), _P, _sz, _P]),
     "lrpx_aoa_decoder_workspace_bytes": (_sz, [C.POINTER(AoaArgs)]),
@@ -148,6 +154,10 @@ SYMBOLS = {
     "lrpx_tc_scale_rows": (_i, [_P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "lrpx_tc_pf_to_dense_f32": (_i, [_P, _P, _i, _i, _i, _i, _i, _P]),
     "lrpx_tc_nchw_to_pf_bf16": (_i, [_P, _P, _i, _i, _i, _i, _i, _P]),
+    "lrpx_tc_im2col3_split_x": (_i, [_P, _P, _i, _i, _i, _i, _P]),
+    "lrpx_tc_maxpool2_x": (_i, [_P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _P]),
+    "lrpx_tc_scale_rows_x": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _P]),
+    "lrpx_tc_pf_split_to_dense_f32": (_i, [_P, _P, _i, _i, _i, _i, _i, _P]),
 }
 
 _lib = None

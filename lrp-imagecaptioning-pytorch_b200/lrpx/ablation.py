@@ -23,8 +23,9 @@ class AblationExperiments:
     def __init__(self, explainer, num_delete_patches=20, patch_size=8, num_delete_words=3, chunk=128):
         """explainer: ExplainGridTDAttention / ExplainAOAAttention / ExplainAdaptiveAttention with precision='bf16'
         (VGG encoder on the tensor-core engine).  Defaults: evaluation.py:55-56, :241."""
-        if explainer.precision != "bf16":
-            raise ValueError("AblationExperiments drives the tensor-core encoder: build the explainer with precision='bf16'")
+        if not getattr(explainer, "uses_tc", False):
+            raise ValueError("AblationExperiments drives the tensor-core encoder: it needs a VGG-style encoder and "
+                             "precision='fp32' or 'bf16'")
         self.ex = explainer
         self.num_delete_patches = int(num_delete_patches)
         self.patch_size = int(patch_size)

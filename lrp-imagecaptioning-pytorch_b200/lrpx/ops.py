@@ -235,6 +235,49 @@ def _fill_args(struct, fields: dict, keep: list):
 DEC_TC_GEMM = 1
 
 
+def lrp_linear_eps(r_out, forward_input, forward_output, weight):
+    """The explainers' vector epsilon rule (gridTDmodel.py:744-765) on the device: r_out (n_out,) or (1,n_out),
+    forward_input (n_in,), forward_output (n_out,) or False (recomputed as W x), weight (n_out,n_in) -> (n_in,)."""
+    for t, n in ((r_out, "r_out"), (forward_input, "forward_input"), (weight, "weight")):
+        if not t.is_cuda:
+            raise _lib.LrpxError(f"lrp_linear_eps: {n} must be a CUDA tensor (lrpx has no CPU fallback)")
+    W = _f32(weight, "weight")
+    n_out, n_in = W.shape
+    r = _f32(r_out.reshape(-1), "r_out")
+    x = _f32(forward_input.reshape(-1), "forward_input")
+    if r.numel() != n_out or x.numel() != n_in:
+        raise _lib.LrpxError("lrp_linear_eps: shapes do not match the weight")
+    z = None
+    if not isinstance(forward_output, bool):
+        z = _f32(forward_output.reshape(-1), "forward_output")
+        if z.numel() != n_out:
+            raise _lib.LrpxError("lrp_linear_eps: forward_output must have n_out elements")
+    out = torch.empty(n_in, device=W.device, dtype=torch.float32)
+    nbytes = lib().lrpx_lrp_linear_eps_workspace_bytes(n_out, n_in)
+    ws = torch.empty(nbytes, device=W.device, dtype=torch.uint8)
+    check(lib().lrpx_lrp_linear_eps_f32(_ptr(r), _ptr(x), _ptr(z), _ptr(W), _ptr(out), n_out, n_in, _ptr(ws), nbytes,
+                                        _stream()), "lrpx_lrp_linear_eps_f32")
+    return out.view_as(forward_input) if forward_input.numel() == n_in else out
+
+
+def lrp_mha(alpha, value, r_context, context, num_head, head_idx):
+    """ExplainAOAAttention.lrp_mha (aoamodel.py:812-862): alpha (heads,P), value (P,H), r_context / context (1,H) or
+    (H,) -> (P,H): the value relevance of head ``head_idx``, zeros for the other heads."""
+    for t, n in ((alpha, "alpha"), (value, "value"), (r_context, "r_context"), (context, "context")):
+        if not t.is_cuda:
+            raise _lib.LrpxError(f"lrp_mha: {n} must be a CUDA tensor (lrpx has no CPU fallback)")
+    v = _f32(value, "value")
+    P, H = v.shape
+    a = _f32(alpha, "alpha")
+    rc, c = _f32(r_context.reshape(-1), "r_context"), _f32(context.reshape(-1), "context")
+    if tuple(a.shape) != (num_head, P) or rc.numel() != H or c.numel() != H:
+        raise _lib.LrpxError("lrp_mha: shapes do not match")
+    out = torch.empty_like(v)
+    check(lib().lrpx_lrp_mha_f32(_ptr(a), _ptr(v), _ptr(rc), _ptr(c), _ptr(out), P, H, int(num_head), int(head_idx),
+                                 _stream()), "lrpx_lrp_mha_f32")
+    return out
+
+
 def _check_requests(B, T, V, req_img, req_t, req_word, req_head=None, num_head=0):
     """The decoder kernels index saved state with the request tuples: reject out-of-range requests here (one small
     reduction + read-back; skipped while a CUDA graph is being captured and with LRPX_VALIDATE=0)."""

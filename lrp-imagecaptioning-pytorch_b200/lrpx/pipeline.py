@@ -16,18 +16,23 @@ from . import ops
 
 
 class BatchExplainer:
-    def __init__(self, explainer, chunk=128, use_graph=False, tc_gemm=True, head_idx=0):
+    def __init__(self, explainer, chunk=128, use_graph=False, tc_gemm=None, head_idx=0, deliver="full"):
         """explainer: models.gridTDmodel.ExplainGridTDAttention, models.aoamodel.ExplainAOAAttention or
-        models.adaptiveattention.ExplainAdaptiveAttention with precision='bf16' (VGG encoder); ``head_idx``: the
-        attention head an AoA explanation follows (aoamodel.py:1165, ``explain_caption(img, head_idx)``)."""
-        if explainer.precision != "bf16":
-            raise ValueError("BatchExplainer drives the tensor-core chain: build the explainer with precision='bf16'")
+        models.adaptiveattention.ExplainAdaptiveAttention on a VGG encoder with precision 'fp32' (fp32-accurate chain)
+        or 'bf16'; ``head_idx``: the attention head an AoA explanation follows (aoamodel.py:1165,
+        ``explain_caption(img, head_idx)``); ``deliver``: format of the heat-maps (TcVggEngine.heat_shape): 'full' =
+        fp32 (Q,3,H,W) like the reference, 'channel_mean' = fp32 (Q,H,W), 'fp16'; ``tc_gemm``: decoder GEMMs as bf16x3
+        on tensor cores (default: with precision 'bf16') or on fp32 CUDA cores."""
+        if not getattr(explainer, "uses_tc", False):
+            raise ValueError("BatchExplainer drives the tensor-core chain: it needs a VGG-style encoder and "
+                             "precision='fp32' (fp32-accurate mode) or 'bf16'")
         self.ex = explainer
         self.eng = explainer.engine()
         self.W = explainer._lrp_weights()
         self.chunk = chunk
         self.use_graph = use_graph
-        self.tc_gemm = tc_gemm            # decoder GEMMs as bf16x3 on tensor cores (fp32 CUDA cores when False)
+        self.tc_gemm = (explainer.precision == "bf16") if tc_gemm is None else bool(tc_gemm)
+        self.deliver = deliver
         self.is_aoa = hasattr(explainer, "num_head") and hasattr(explainer.model, "decoder_multihead_attention")
         self.is_adaptive = not self.is_aoa and not hasattr(explainer.model, "LanguageLSTM")   # single-LSTM decoder
         self.head_idx = int(head_idx)
@@ -61,7 +66,7 @@ class BatchExplainer:
         else:
             r_feat, r_words = ops.gridtd_decoder_lrp(st, self.W, req_img, req_t, req_word, tc_gemm=self.tc_gemm)
         if host is None:
-            self.eng.relevance(est, r_feat, req_img, chunk=self.chunk, out=heat)
+            self.eng.relevance(est, r_feat, req_img, chunk=self.chunk, out=heat, deliver=self.deliver)
             return r_words
         # results go to pinned host buffers: the copy of chunk i runs on a side stream under the kernels of chunk i+1
         host_heat, host_words = host
@@ -80,7 +85,7 @@ class BatchExplainer:
         side.wait_stream(main)
         with torch.cuda.stream(side):
             host_words.copy_(r_words, non_blocking=True)
-        self.eng.relevance(est, r_feat, req_img, chunk=self.chunk, out=heat, on_chunk=on_chunk)
+        self.eng.relevance(est, r_feat, req_img, chunk=self.chunk, out=heat, on_chunk=on_chunk, deliver=self.deliver)
         main.wait_stream(side)
         return r_words
 
@@ -96,12 +101,17 @@ class BatchExplainer:
         dev = self.ex.device
         wpi = None if words_per_image is None else tuple(int(v) for v in words_per_image)
         Q = B * T if wpi is None else sum(wpi)
+        # heat-map buffer in the delivery format (the engine's image size is known after its first forward; before
+        # that it is the size of these images)
+        H, W = int(imgs.shape[2]), int(imgs.shape[3])
+        shp = (Q, H, W) if self.deliver == "channel_mean" else (Q, 3, H, W)
+        dt = torch.float16 if self.deliver == "fp16" else torch.float32
         if Q == 0:                                               # nothing to explain
-            return (torch.empty(0, 3, imgs.shape[2], imgs.shape[3], device=dev), torch.empty(0, T, device=dev))
+            return (torch.empty((0,) + shp[1:], device=dev, dtype=dt), torch.empty(0, T, device=dev))
         if not self.use_graph:
             imgs, tokens = imgs.to(dev, non_blocking=True), tokens.to(dev, non_blocking=True)
             req_img, req_t = self._requests(B, T, dev, wpi)
-            heat = out if out is not None else torch.empty(Q, 3, imgs.shape[2], imgs.shape[3], device=dev)
+            heat = out if out is not None else torch.empty(shp, device=dev, dtype=dt)
             return heat, self._run(imgs, tokens, req_img, req_t, heat, host_out)
         key = (tuple(imgs.shape), tuple(tokens.shape), wpi,
                None if host_out is None else (host_out[0].data_ptr(), host_out[1].data_ptr()))
@@ -109,7 +119,7 @@ class BatchExplainer:
         if g is None:
             s_imgs, s_toks = imgs.to(dev).clone(), tokens.to(dev).clone()
             req_img, req_t = self._requests(B, T, dev, wpi)
-            heat = torch.empty(Q, 3, imgs.shape[2], imgs.shape[3], device=dev)
+            heat = torch.empty(shp, device=dev, dtype=dt)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                       # warm-up outside capture (lazy inits, attributes)

@@ -24,7 +24,7 @@ from . import _lib
 from ._lib import TcConvArgs, check, lib
 
 EPI_FWD_GAIN, EPI_MUL, EPI_MUL_UNPOOL, EPI_INPUT, EPI_STORE_F32 = 1, 2, 3, 4, 5
-EPI_INPUT3 = 8
+EPI_INPUT3, EPI_MULX, EPI_MULX_UNPOOL, EPI_FWDX = 8, 9, 10, 11
 
 
 def _ptr(t):
@@ -45,9 +45,14 @@ def pf_rows(n, h, w):
 
 
 def tc_conv(a, wt, n_img, h, w, cin, ncol, ksize, epilogue, out, out2=None, bias=None, gain=None, row_img=None,
-            pool_idx=None, x=None, gain_mode=0):
+            pool_idx=None, x=None, gain_mode=0, gain2=None, out3=None, a_phys=0, groups=1, split=0, n_acc=0, rule=0,
+            zbias=0, alpha=1.0, beta=0.0):
     """Thin wrapper of lrpx_tc_conv (all tensors preallocated by the caller)."""
-    args = TcConvArgs(n_img=n_img, h=h, w=w, cin=cin, ncol=ncol, ksize=ksize, epilogue=epilogue, gain_mode=gain_mode)
+    args = TcConvArgs(n_img=n_img, h=h, w=w, cin=cin, ncol=ncol, ksize=ksize, epilogue=epilogue, gain_mode=gain_mode,
+                      a_phys=a_phys, groups=groups, split=split, n_acc=n_acc, rule=rule, zbias=zbias, alpha=alpha,
+                      beta=beta)
+    args.gain2 = gain2.data_ptr() if gain2 is not None else None
+    args.out3 = out3.data_ptr() if out3 is not None else None
     args.a, args.wt = a.data_ptr(), wt.data_ptr()
     args.bias = bias.data_ptr() if bias is not None else None
     args.gain = gain.data_ptr() if gain is not None else None
@@ -118,8 +123,23 @@ def maxpool2(act, gain, n, h, w, c, want_idx=True):
     return pooled, idx, gpool
 
 
+def _hi_lo(t):
+    """fp32 -> (hi, lo) bf16 with t ~ hi + lo (16 significant bits)."""
+    hi = t.to(torch.bfloat16)
+    return hi, (t - hi.float()).to(torch.bfloat16)
+
+
+def _k_operand(t, split):
+    """Weight tensor (..., K) fp32 -> bf16 B operand along K: as is, or [hi | hi | lo] to meet an A row viewed as
+    [hi | lo | hi] (lrpx_tc_conv_args.a_phys): a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo."""
+    if not split:
+        return t.to(torch.bfloat16)
+    hi, lo = _hi_lo(t)
+    return torch.cat((hi, hi, lo), -1)
+
+
 class _Conv:
-    __slots__ = ("cin", "cout", "h", "w", "pool_after", "w_f32", "bias", "w_dual", "w_rel", "w_rel3")
+    __slots__ = ("cin", "cout", "h", "w", "pool_after", "w_f32", "bias", "w_dual", "w_rel", "w_rel3", "w_fwd", "n_acc")
 
 
 class VggState:
@@ -129,6 +149,9 @@ class VggState:
         self.n = 0
         self.x = None           # fp32 NCHW images
         self.gain = []          # per conv: PF bf16 gain at the resolution the relevance chain needs it
+        self.gain2 = []         # general modes with two gain groups (beta != 0): the neg-net gains
+        self.rz2_last = None
+        self.acts = None        # keep_act=True: the PF input activations of every conv (diagnostics)
         self.idx = []           # per conv: uint8 argmax of the pool after it (or None)
         self.rz_last = None     # 1 / safe(z+) of the last conv
         self.feat_pf = None     # encoder output, PF bf16
@@ -141,11 +164,33 @@ class TcVggEngine:
     for any number of explanation requests against those images."""
 
     def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], cfg: Sequence,
-                 device=None):
+                 device=None, precision="bf16", alpha=1.0, beta=0.0, ignore_bias=True, rule="alpha_beta"):
+        """precision 'bf16': bf16 operands and inter-layer storage.  'fp32': the fp32-accurate mode — operands as
+        error-compensated bf16 pairs (x = hi + lo; a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on the same tcgen05 kernels,
+        K tripled), fp32 gains, hi|lo inter-layer storage.
+        rule 'alpha_beta' (lrp_modules.py:129-150): alpha * R(pos-net) - beta * R(neg-net); beta != 0 doubles K with the
+        operand row [alpha*R/z+ | -beta*R/z-] against [W+^T | W-^T].  rule 'epsilon': the Linear rule
+        (lrp_modules.py:9-24) on the unfolded conv (the reference's Conv2d raises for it: parity unpinned).
+        alpha = 1, beta = 0, bf16, ignore_bias is the specialised fast path (EPI_MUL / EPI_MUL_UNPOOL)."""
         device = torch.device(device or "cuda")
         if device.type != "cuda":
             raise _lib.LrpxError("TcVggEngine needs a CUDA device: lrpx has no CPU fallback")
+        if precision not in ("bf16", "fp32") or rule not in ("alpha_beta", "epsilon"):
+            raise _lib.LrpxError("TcVggEngine: precision must be 'bf16' or 'fp32', rule 'alpha_beta' or 'epsilon'")
+        if rule == "epsilon" and precision != "fp32":
+            # gain = a / (z + 0.01 sign z) with the mixed-sign z = W * a: bf16 operands put an absolute error of
+            # ~2^-9 sum|w a| on z, larger than the 0.01 stabiliser wherever z is small — measured rel-L2 0.47 against
+            # the oracle.  The z+ gains of the alpha-beta rule are same-sign sums and do not have this problem.
+            raise _lib.LrpxError("rule='epsilon' needs precision='fp32' (the epsilon gains are ill-conditioned in bf16)")
         self.device = device
+        self.precision, self.rule = precision, rule
+        self.alpha, self.beta, self.ignore_bias = float(alpha), float(beta), bool(ignore_bias)
+        self.split = precision == "fp32"
+        self.groups = 2 if (rule == "alpha_beta" and self.beta != 0.0) else 1
+        self.general = not (precision == "bf16" and rule == "alpha_beta" and self.alpha == 1.0 and self.beta == 0.0
+                            and self.ignore_bias)
+        self.rm = self.groups * (2 if self.split else 1)        # stored channels per logical channel of a chain row
+        self.km = self.groups * (3 if self.split else 1)        # GEMM K channels per logical channel
         self.convs: List[_Conv] = []
         k = 0
         for v in cfg:
@@ -162,9 +207,15 @@ class TcVggEngine:
             c.pool_after = False
             c.w_f32 = w
             c.bias = None if biases[k] is None else biases[k].detach().to(device=device, dtype=torch.float32).contiguous()
-            if k == 0:
-                if c.cin != 3 or c.cout not in (8, 16, 32, 64):
-                    raise _lib.LrpxError("first conv must be 3 -> {8,16,32,64} channels")
+            c.w_dual = c.w_rel = c.w_rel3 = c.w_fwd = None
+            c.n_acc = 0
+            if k == 0 and (c.cin != 3 or c.cout not in (8, 16, 32, 64)):
+                raise _lib.LrpxError("first conv must be 3 -> {8,16,32,64} channels")
+            if k > 0 and (c.cin % 64 or c.cout % 32):
+                raise _lib.LrpxError("conv channels must be multiples of 64 (in) / 32 (out) on the tensor-core path")
+            if self.general:
+                pass                                     # operands built by _general_weights below
+            elif k == 0:
                 # rows 0..2: W+ (flipped, transposed), rows 3..5: W-, rows 6..15: zero
                 c.w_rel = torch.zeros(16, 9 * c.cout, device=device, dtype=torch.bfloat16)
                 weight_prep(w, 2, out=c.w_rel[0:3])
@@ -184,17 +235,109 @@ class TcVggEngine:
                     c.w_dual = torch.cat((torch.cat((w27, w27, pad), 1),
                                           torch.cat((w27.clamp(min=0), w27.clamp(max=0), pad), 1)), 0).to(torch.bfloat16).contiguous()
             else:
-                if c.cin % 64 or c.cout % 32:
-                    raise _lib.LrpxError("conv channels must be multiples of 64 (in) / 32 (out) on the tensor-core path")
                 c.w_dual = dual_forward_weights(w)
                 c.w_rel = weight_prep(w, 2)          # (cin, 9*cout): W+ flipped & transposed
+            if self.general:
+                self._general_weights(c, w, first=(k == 0))
             self.convs.append(c)
             k += 1
         if self.convs[-1].pool_after:
             raise _lib.LrpxError("the encoder slice must end with a conv (vgg16.features[0:-1])")
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor) -> VggState:
+    def _general_weights(self, c, w, first):
+        """B operands of the general modes, laid out on the device once per model (torch tensor ops: not on the
+        per-explanation path)."""
+        sp, eps = self.split, self.rule == "epsilon"
+        pos, neg = (lambda t: t.clamp(min=0)), (lambda t: t.clamp(max=0))
+        wt = w.flip(2, 3).permute(1, 2, 3, 0)                    # (cin,3,3,cout): W[co][ci][2-r][2-s]  (transposed conv)
+        c.n_acc = 1 if eps else (3 if self.groups == 2 else 2)
+        if first:
+            if c.cout % 64:
+                raise _lib.LrpxError("general modes need a first conv with a multiple of 64 output channels")
+            # relevance (EPI_INPUT3): rows 0..2 multiply x+, rows 3..5 multiply x-  (lrp_modules.py:81-84,111-114)
+            if eps:
+                cp, cn = wt, wt
+            elif self.groups == 2:
+                cp, cn = torch.cat((pos(wt), neg(wt)), -1), torch.cat((neg(wt), pos(wt)), -1)
+            else:
+                cp, cn = pos(wt), neg(wt)
+            rows8 = torch.cat((cp, cn, torch.zeros_like(cp[:2])), 0)                   # (8,3,3,G*cout)
+            t = _k_operand(rows8, sp)                                                  # (8,3,3,Kl)
+            c.w_rel3 = t.permute(2, 0, 1, 3).reshape(24, -1).contiguous()              # row dx*8+r, K = (dy, channel)
+            c.w_rel = None
+            # forward over the sign-split im2col [x+ taps | x- taps | 0]: z, z+ (pos-net), z- (neg-net)
+            w27 = w.reshape(c.cout, 27)
+            pad = w27.new_zeros(c.cout, 10)
+            blocks = [torch.cat((w27, w27, pad), 1)]
+            if not eps:
+                blocks.append(torch.cat((pos(w27), neg(w27), pad), 1))
+                if self.groups == 2:
+                    blocks.append(torch.cat((neg(w27), pos(w27), pad), 1))
+        else:
+            parts = [wt] if eps else ([pos(wt), neg(wt)] if self.groups == 2 else [pos(wt)])
+            c.w_rel = _k_operand(torch.cat(parts, -1), sp).reshape(c.cin, -1).contiguous()    # (cin, 9*Kl)
+            c.w_rel3 = None
+            wf = w.permute(0, 2, 3, 1)                                                 # (cout,3,3,cin)
+            blocks = [wf] if eps else ([wf, pos(wf), neg(wf)] if self.groups == 2 else [wf, pos(wf)])
+        cap = {1: 256, 2: 128, 3: 64}[c.n_acc]
+        half = min(c.cout, cap)
+        if c.cout % half:
+            raise _lib.LrpxError(f"output channels must be < {cap} or a multiple of it in this mode")
+        ops_ = [_k_operand(b, sp).reshape(c.cout, -1) for b in blocks]
+        c.w_fwd = torch.cat([o[j * half:(j + 1) * half] for j in range(c.cout // half) for o in ops_], 0).contiguous()
+        c.w_dual = None
+
+    def _forward_general(self, st, x, keep_act):
+        n, _, h, w = x.shape
+        dev = x.device
+        sp, G = self.split, self.groups
+        gdt = torch.float32 if sp else torch.bfloat16
+        rule = 1 if self.rule == "epsilon" else 0
+        act = None
+        for li, c in enumerate(self.convs):
+            c.h, c.w = h, w
+            rows = pf_rows(n, h, w)
+            out = torch.empty(rows, c.cout * (2 if sp else 1), device=dev, dtype=torch.bfloat16)
+            g0 = torch.empty(rows, c.cout, device=dev, dtype=gdt)
+            g1 = torch.empty(rows, c.cout, device=dev, dtype=gdt) if G == 2 else None
+            last = li == len(self.convs) - 1
+            kw = dict(out2=g0, out3=g1, bias=c.bias, gain_mode=1 if last else 0, split=int(sp), n_acc=c.n_acc, rule=rule,
+                      zbias=0 if self.ignore_bias else 1, alpha=self.alpha, beta=self.beta)
+            if li == 0:
+                cols = torch.empty(rows, 128 if sp else 64, device=dev, dtype=torch.bfloat16)
+                check(lib().lrpx_tc_im2col3_split_x(_ptr(x), _ptr(cols), n, h, w, int(sp), _stream()),
+                      "lrpx_tc_im2col3_split_x")
+                tc_conv(cols, c.w_fwd, n, h, w, 192 if sp else 64, c.n_acc * c.cout, 1, EPI_FWDX, out,
+                        a_phys=128 if sp else 0, **kw)
+                if keep_act:
+                    st.acts.append(None)
+            else:
+                if keep_act:
+                    st.acts.append(act)
+                tc_conv(act, c.w_fwd, n, h, w, c.cin * (3 if sp else 1), c.n_acc * c.cout, 3, EPI_FWDX, out,
+                        a_phys=2 * c.cin if sp else 0, **kw)
+            if c.pool_after:
+                prow = pf_rows(n, h // 2, w // 2)
+                pooled = torch.empty(prow, out.shape[1], device=dev, dtype=torch.bfloat16)
+                idx = torch.empty(prow, c.cout, device=dev, dtype=torch.uint8)
+                gp0 = torch.empty(prow, c.cout, device=dev, dtype=gdt)
+                gp1 = torch.empty(prow, c.cout, device=dev, dtype=gdt) if G == 2 else None
+                check(lib().lrpx_tc_maxpool2_x(_ptr(out), _ptr(g0), _ptr(g1), _ptr(pooled), _ptr(idx), _ptr(gp0),
+                                               _ptr(gp1), n, h, w, c.cout, int(sp), _stream()), "lrpx_tc_maxpool2_x")
+                act, g0, g1 = pooled, gp0, gp1
+                h, w = h // 2, w // 2
+                st.idx.append(idx)
+            else:
+                act = out
+                st.idx.append(None)
+            st.gain.append(g0)
+            st.gain2.append(g1)
+        st.rz_last, st.rz2_last = st.gain[-1], st.gain2[-1]
+        st.feat_pf, st.feat_hw, st.feat_c = act, (h, w), self.convs[-1].cout
+        return st
+
+    def forward(self, x: torch.Tensor, keep_act: bool = False) -> VggState:
         """Activation-producing forward (lrp_wrapper.py:70) + per-layer gains; x is fp32 NCHW (n,3,h,w)."""
         _need_cuda(x, "x")
         x = x.detach().float().contiguous()
@@ -204,6 +347,10 @@ class TcVggEngine:
             raise _lib.LrpxError("images must be (n,3,h,w) with h, w divisible by 2**(number of pools)")
         st = VggState()
         st.n, st.x = n, x
+        if keep_act:
+            st.acts = []
+        if self.general:
+            return self._forward_general(st, x, keep_act)
         dev = x.device
         act = None
         for li, c in enumerate(self.convs):
@@ -223,6 +370,8 @@ class TcVggEngine:
             else:
                 tc_conv(act, c.w_dual, n, h, w, c.cin, 2 * c.cout, 3, EPI_FWD_GAIN, out, out2=gain, bias=c.bias,
                         gain_mode=1 if last else 0)
+            if keep_act:
+                st.acts.append(act if li else None)
             if c.pool_after:
                 act, idx, gain = maxpool2(out, gain, n, h, w, c.cout)
                 h, w = h // 2, w // 2
@@ -238,11 +387,29 @@ class TcVggEngine:
     def features(self, st: VggState, layout="nchw"):
         """Encoder output as dense fp32: 'nchw' (n,C,h,w) or 'pixel' (n,h*w,C)."""
         h, w = st.feat_hw
+        if self.split:
+            out = torch.empty((st.n, st.feat_c, h, w) if layout == "nchw" else (st.n, h * w, st.feat_c),
+                              device=st.feat_pf.device, dtype=torch.float32)
+            check(lib().lrpx_tc_pf_split_to_dense_f32(_ptr(st.feat_pf), _ptr(out), st.n, h, w, st.feat_c,
+                                                      1 if layout == "nchw" else 0, _stream()),
+                  "lrpx_tc_pf_split_to_dense_f32")
+            return out
         return pf_to_dense(st.feat_pf, st.n, h, w, st.feat_c, layout)
 
     # ------------------------------------------------------------------------------------------
+    DELIVER = {"full": 0, "channel_mean": 1, "fp16": 2}
+
+    def heat_shape(self, Q, deliver="full"):
+        """(shape, dtype) of the heat-maps of Q requests in delivery format ``deliver``: 'full' = fp32 (Q,3,H,W), the
+        reference's return value; 'channel_mean' = fp32 (Q,H,W), what evaluation.py:134,411,503 reduce every heat-map
+        to first (torch.mean(relevance, dim=(0,1))); 'fp16' = (Q,3,H,W) half.  Formed in the last layer's epilogue."""
+        H, W = self.convs[0].h, self.convs[0].w
+        if deliver == "channel_mean":
+            return (Q, H, W), torch.float32
+        return (Q, 3, H, W), (torch.float16 if deliver == "fp16" else torch.float32)
+
     def relevance(self, st: VggState, r_feat: torch.Tensor, row_img: Optional[torch.Tensor] = None,
-                  chunk: int = 128, out: Optional[torch.Tensor] = None, on_chunk=None) -> torch.Tensor:
+                  chunk: int = 128, out: Optional[torch.Tensor] = None, on_chunk=None, deliver: str = "full") -> torch.Tensor:
         """Image relevance for Q requests.  r_feat: fp32 (Q, h*w, C) pixel-major relevance of the encoder
         output (what the decoder kernels emit); row_img: int32 (Q,) image of each request (None = identity).
         Returns fp32 (Q, 3, H, W).  ``on_chunk(q0, q1)`` is called after the launches that produce out[q0:q1]
@@ -250,22 +417,25 @@ class TcVggEngine:
         = ``relevance_tail(relevance_head(...))`` per group of at most ``GROUP`` requests (the stage-1 buffers of a
         group stay within their memory budget however many requests a call brings)."""
         Q = r_feat.shape[0]
+        if deliver not in self.DELIVER:
+            raise _lib.LrpxError(f"deliver must be one of {sorted(self.DELIVER)}")
         if Q <= self.GROUP:
             head = self.relevance_head(st, r_feat, row_img, chunk)
-            return self.relevance_tail(st, head, out=out, on_chunk=on_chunk)
+            return self.relevance_tail(st, head, out=out, on_chunk=on_chunk, deliver=deliver)
         _need_cuda(r_feat, "r_feat")
         if row_img is None:
             if Q != st.n:
                 raise _lib.LrpxError("row_img is required when the number of requests differs from the images")
             row_img = torch.arange(Q, device=r_feat.device, dtype=torch.int32)
         if out is None:
-            out = torch.empty(Q, 3, self.convs[0].h, self.convs[0].w, device=r_feat.device, dtype=torch.float32)
+            shp, dt = self.heat_shape(Q, deliver)
+            out = torch.empty(shp, device=r_feat.device, dtype=dt)
         group = max(chunk, self.GROUP // max(1, chunk) * chunk)
         for g0 in range(0, Q, group):
             g1 = min(Q, g0 + group)
             head = self.relevance_head(st, r_feat[g0:g1], row_img[g0:g1], chunk)
             cb = None if on_chunk is None else (lambda q0, q1, g0=g0: on_chunk(g0 + q0, g0 + q1))
-            self.relevance_tail(st, head, out=out[g0:g1], on_chunk=cb)
+            self.relevance_tail(st, head, out=out[g0:g1], on_chunk=cb, deliver=deliver)
         return out
 
     GROUP = 2048          # requests per stage-1 group
@@ -275,7 +445,12 @@ class TcVggEngine:
         for li in range(hi - 1, lo - 1, -1):
             c, below = self.convs[li], self.convs[li - 1]
             dst = bufs[cur ^ 1]
-            if below.pool_after:
+            if self.general:
+                tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout * self.km, c.cin, 3,
+                        EPI_MULX_UNPOOL if below.pool_after else EPI_MULX, dst, gain=st.gain[li - 1],
+                        gain2=st.gain2[li - 1], row_img=rimg, pool_idx=st.idx[li - 1] if below.pool_after else None,
+                        a_phys=c.cout * self.rm if self.split else 0, groups=self.groups, split=int(self.split))
+            elif below.pool_after:
                 tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL_UNPOOL, dst, gain=st.gain[li - 1],
                         row_img=rimg, pool_idx=st.idx[li - 1])
             else:
@@ -283,6 +458,17 @@ class TcVggEngine:
             cur ^= 1
             s = dst
         return s, cur
+
+    def _scale_rows(self, st, r, rimg, out, nq):
+        """chain entry: the top operand row from the decoder's relevance (s = R / z of the last conv)"""
+        fh, fw = st.feat_hw
+        if self.general:
+            check(lib().lrpx_tc_scale_rows_x(_ptr(r), _ptr(st.rz_last), _ptr(st.rz2_last), _ptr(rimg), _ptr(out), nq, fh,
+                                             fw, st.feat_c, self.groups, int(self.split), _stream()),
+                  "lrpx_tc_scale_rows_x")
+        else:
+            check(lib().lrpx_tc_scale_rows(_ptr(r), _ptr(st.rz_last), _ptr(rimg), _ptr(out), nq, fh, fw, st.feat_c,
+                                           _stream()), "lrpx_tc_scale_rows")
 
     def relevance_head(self, st: VggState, r_feat: torch.Tensor, row_img: Optional[torch.Tensor] = None,
                        chunk: int = 128) -> dict:
@@ -309,7 +495,7 @@ class TcVggEngine:
             for li in range(L - 1, 0, -1):
                 c, below = self.convs[li], self.convs[li - 1]
                 oh, ow = (2 * c.h, 2 * c.w) if below.pool_after else (c.h, c.w)
-                need = max(pf_rows(Q, c.h, c.w) * c.cout, pf_rows(Q, oh, ow) * c.cin) * 2
+                need = max(pf_rows(Q, c.h, c.w) * c.cout, pf_rows(Q, oh, ow) * c.cin) * 2 * self.rm
                 if need > budget:
                     break
                 n_wide += 1
@@ -321,23 +507,26 @@ class TcVggEngine:
                 c, below = self.convs[li], self.convs[li - 1]
                 oh, ow = (2 * c.h, 2 * c.w) if below.pool_after else (c.h, c.w)
                 elems = max(elems, pf_rows(Q, c.h, c.w) * c.cout, pf_rows(Q, oh, ow) * c.cin)
-            wide = [torch.empty(elems, device=dev, dtype=torch.bfloat16) for _ in range(2)]
-            check(lib().lrpx_tc_scale_rows(_ptr(r_feat), _ptr(st.rz_last), _ptr(row_img), _ptr(wide[0]), Q, fh, fw,
-                                           st.feat_c, _stream()), "lrpx_tc_scale_rows")
+            wide = [torch.empty(elems * self.rm, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+            self._scale_rows(st, r_feat, row_img, wide[0], Q)
             s_all, _ = self._run_layers(st, wide[0], Q, row_img, split, L, wide, 0)
         return dict(Q=Q, chunk=chunk, split=split, s_all=s_all, r_feat=r_feat, row_img=row_img)
 
-    def relevance_tail(self, st: VggState, head: dict, out: Optional[torch.Tensor] = None, on_chunk=None) -> torch.Tensor:
+    def relevance_tail(self, st: VggState, head: dict, out: Optional[torch.Tensor] = None, on_chunk=None,
+                       deliver: str = "full") -> torch.Tensor:
         """Stage 2 of ``relevance``: the high-resolution layers chunk by chunk, ping-ponging two buffers sized for the
         largest layer of a chunk, so that finished heat-maps can leave for the host while the next chunk runs."""
         Q, chunk, split, s_all, r_feat, row_img = (head[k] for k in ("Q", "chunk", "split", "s_all", "r_feat", "row_img"))
         dev = r_feat.device
         fh, fw = st.feat_hw
-        H, W = self.convs[0].h, self.convs[0].w
+        shp, dt = self.heat_shape(Q, deliver)
         if out is None:
-            out = torch.empty(Q, 3, H, W, device=dev, dtype=torch.float32)
+            out = torch.empty(shp, device=dev, dtype=dt)
+        if tuple(out.shape) != shp or out.dtype != dt:
+            raise _lib.LrpxError(f"out must be {shp} {dt} for deliver={deliver!r}")
+        dmode = self.DELIVER[deliver]
         top = self.convs[split - 1]           # first layer of stage 2: its input is (h, w, cout) of that layer
-        max_elems = max(pf_rows(chunk, c.h, c.w) * c.cout for c in self.convs[:split])
+        max_elems = max(pf_rows(chunk, c.h, c.w) * c.cout for c in self.convs[:split]) * self.rm
         buf = [torch.empty(max_elems, device=dev, dtype=torch.bfloat16) for _ in range(2)]
         bounds = list(range(0, Q, chunk)) + [Q]
         if on_chunk is not None and bounds[-1] - bounds[-2] > 32:
@@ -349,25 +538,74 @@ class TcVggEngine:
             nq = q1 - q0
             rimg = row_img[q0:q1]
             if s_all is not None:
-                per = pf_rows(1, top.h, top.w) * top.cout
+                per = pf_rows(1, top.h, top.w) * top.cout * self.rm
                 s, cur = s_all[q0 * per:q1 * per], 1      # reads the stage-1 result in place, writes into buf[0]
             else:
                 s, cur = buf[0], 0
-                check(lib().lrpx_tc_scale_rows(_ptr(r_feat[q0:q1]), _ptr(st.rz_last), _ptr(rimg), _ptr(s), nq, fh, fw,
-                                               st.feat_c, _stream()), "lrpx_tc_scale_rows")
+                self._scale_rows(st, r_feat[q0:q1], rimg, s, nq)
             s, cur = self._run_layers(st, s, nq, rimg, 1, split, buf, cur)
             c0 = self.convs[0]
-            if c0.w_rel3 is not None:
-                tc_conv(s, c0.w_rel3, nq, c0.h, c0.w, c0.cout, 24, 3, EPI_INPUT3, out[q0:q1], row_img=rimg, x=st.x)
+            if self.general:
+                tc_conv(s, c0.w_rel3, nq, c0.h, c0.w, c0.cout * self.km, 24, 3, EPI_INPUT3, out[q0:q1], row_img=rimg,
+                        x=st.x, a_phys=c0.cout * self.rm if self.split else 0, gain_mode=dmode)
+            elif c0.w_rel3 is not None:
+                tc_conv(s, c0.w_rel3, nq, c0.h, c0.w, c0.cout, 24, 3, EPI_INPUT3, out[q0:q1], row_img=rimg, x=st.x,
+                        gain_mode=dmode)
+            elif dmode:
+                raise _lib.LrpxError("deliver != 'full' needs a first conv with a multiple of 64 output channels")
             else:
                 tc_conv(s, c0.w_rel, nq, c0.h, c0.w, c0.cout, 16, 3, EPI_INPUT, out[q0:q1], row_img=rimg, x=st.x)
             if on_chunk is not None:
                 on_chunk(q0, q1)
         return out
 
+    def conservation(self, st: VggState, r_feat: torch.Tensor, row_img: Optional[torch.Tensor] = None):
+        """Diagnostic (north_star: "relevance conservation reported per layer"): [(name, sum R)] from the encoder output
+        down to the image, summed over the given requests.  R at the input of conv l is a_l (.) c_l, formed by the SAME
+        contraction kernels with the layer's input activation as the gain; needs ``forward(..., keep_act=True)``."""
+        if st.acts is None:
+            raise _lib.LrpxError("conservation needs the state of forward(x, keep_act=True)")
+        r_feat = r_feat.detach().float().contiguous()
+        Q = r_feat.shape[0]
+        dev = r_feat.device
+        if row_img is None:
+            row_img = torch.arange(Q, device=dev, dtype=torch.int32)
+        row_img = row_img.to(device=dev, dtype=torch.int32).contiguous()
+        L = len(self.convs)
+        top = self.convs[-1]
+        s = torch.empty(pf_rows(Q, top.h, top.w) * top.cout * self.rm, device=dev, dtype=torch.bfloat16)
+        self._scale_rows(st, r_feat, row_img, s, Q)
+        trace = [("encoder output", float(r_feat.double().sum()))]
+        sp = int(self.split)
+        for li in range(L - 1, 0, -1):
+            c, below = self.convs[li], self.convs[li - 1]
+            # R at the input of conv li: acc (.) a_li through the general epilogue with ONE output group
+            a = st.acts[li]
+            if self.split:
+                g = (a[:, :c.cin].float() + a[:, c.cin:].float()).contiguous()
+            else:
+                g = a
+            R = torch.empty(pf_rows(Q, c.h, c.w), c.cin * (2 if self.split else 1), device=dev, dtype=torch.bfloat16)
+            tc_conv(s, c.w_rel, Q, c.h, c.w, c.cout * self.km, c.cin, 3, EPI_MULX, R, gain=g, row_img=row_img,
+                    a_phys=c.cout * self.rm if self.split else 0, groups=1, split=sp)
+            tot = R.double().sum() if not self.split else (R[:, :c.cin].double().sum() + R[:, c.cin:].double().sum())
+            trace.append((f"conv{li} input", float(tot)))
+            oh, ow = (2 * c.h, 2 * c.w) if below.pool_after else (c.h, c.w)
+            nxt = torch.empty(pf_rows(Q, oh, ow) * c.cin * self.rm, device=dev, dtype=torch.bfloat16)
+            s, _ = self._run_layers(st, s, Q, row_img, li, li + 1, [None, nxt], 0)
+        head = dict(Q=Q, chunk=Q, split=1, s_all=s, r_feat=r_feat, row_img=row_img)
+        heat = self.relevance_tail(st, head)
+        trace.append(("image", float(heat.double().sum())))
+        return trace
+
     def flops_per_explanation(self) -> float:
         """Algorithmic FLOPs of one explanation's relevance chain (one contraction per conv layer)."""
         return float(sum(2.0 * c.h * c.w * c.cin * c.cout * 9 for c in self.convs))
+
+    def mma_flops_per_explanation(self) -> float:
+        """FLOPs the tensor cores execute per explanation in this mode (K x3 for the error-compensated operands,
+        x2 for two gain groups)."""
+        return self.flops_per_explanation() * self.km
 
     def flops_forward_per_image(self) -> float:
         """Forward + z+ (two contractions per layer)."""

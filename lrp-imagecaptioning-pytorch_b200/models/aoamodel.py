@@ -445,18 +445,11 @@ class ExplainAOAAttention(ExplainGridTDAttention):
                                    i32([toks[t + 1] for t in ts]), i32([head_idx] * len(ts)),
                                    tc_gemm=(self.precision == 'bf16'))
 
-    def lrp_mha(self, alpha, value, context, r_context, head_idx):
-        """reference :812-862: relevance of the values of ONE head (others get 0, Q5).
-        alpha (heads,P), value (P,H), context (H,), r_context (H,) -> (P,H).  Tensor expression kept for API
-        compatibility; explain_caption_wordt runs the fused kernel."""
-        P, H = value.shape
-        dk = H // self.num_head
-        sl = slice(head_idx * dk, (head_idx + 1) * dk)
-        z = self.EPS * context.sign() + context
-        z = z.masked_fill(z == 0, self.EPS)
-        out = torch.zeros_like(value)
-        out[:, sl] = value[:, sl] * alpha[head_idx][:, None] * (r_context.reshape(-1)[sl] / z[sl])[None, :]
-        return out
+    def lrp_mha(self, alpha, value, r_context, context, head_idx):
+        """reference :812-862 (same argument order): relevance of the values of ONE head (others get 0, Q5).
+        alpha (heads,P), value (P,H), r_context / context (1,H) or (H,) -> (P,H), on the device
+        (``lrpx_lrp_mha_f32``; CUDA tensors only).  explain_caption_wordt runs the fused decoder kernel."""
+        return ops.lrp_mha(alpha, value, r_context, context, self.num_head, head_idx)
 
     def explain_caption_wordt(self, t, head_idx):
         """reference :1064-1156 -> (r_img_feature (1,C,h,w), r_words (t+1,))."""
@@ -473,13 +466,13 @@ class ExplainAOAAttention(ExplainGridTDAttention):
         if T == 0:
             return [], []
         r_feat, r_words = self._decoder_lrp(list(range(T)), head_idx)
-        if self.precision == 'bf16':
+        if self.uses_tc:
             heat = self.engine().relevance(self._enc_state, r_feat, torch.zeros(T, dtype=torch.int32, device=self.device))
         else:
             enc = self.model.img_encoder.encoder
             lrp_wrapper.add_lrp(enc)
             fh, fw = self._feat_hw
-            heat = torch.cat([lrp_wrapper.compute_lrp(enc, self.img.detach().clone(),
+            heat = torch.cat([lrp_wrapper.compute_lrp(enc, self.img.detach().clone(), precision='simt',
                                                       target=r_feat[t].t().reshape(1, -1, fh, fw)) for t in range(T)])
         if self.ACCUMULATE_LIKE_REFERENCE:
             heat = torch.cumsum(heat, 0)

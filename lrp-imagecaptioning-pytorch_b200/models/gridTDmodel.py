@@ -328,14 +328,9 @@ class GridTDModel(nn.Module):
 
     # ------------------------------------------------------------------ lrp_tune
     def lrp_linear_eps(self, r_out, forward_input, forward_output, weight):
-        """Vector epsilon rule (reference :522-547) as a tensor expression; kept for API compatibility — the
-        tuner and the explainer use the batched kernels instead of calling this per vector."""
-        assert r_out.dim() == 1 and forward_input.dim() == 1 and weight.dim() == 2
-        if type(forward_output) == bool:
-            forward_output = torch.matmul(forward_input, weight.transpose(0, 1))
-        z = self.EPS * forward_output.sign() + forward_output
-        z = z.masked_fill(z == 0, self.EPS)
-        return forward_input * torch.matmul(r_out / z, weight)
+        """Vector epsilon rule (reference :522-547) on the device: ``lrpx_lrp_linear_eps_f32``.  CUDA tensors only
+        (no CPU fallback).  The tuner and the explainer call the batched kernels, which fuse the same arithmetic."""
+        return ops.lrp_linear_eps(r_out, forward_input, forward_output, weight)
 
     def _stop_mask(self, rev_word_map, device):
         key = (id(rev_word_map), str(device))
@@ -454,8 +449,13 @@ class GridTDModelBU(GridTDModel):
 
 # ----------------------------------------------------------------------------------------------------
 class ExplainGridTDAttention(object):
-    """reference :705-1211.  ``precision``: 'bf16' = tcgen05 encoder chain (VGG encoders), 'fp32' = the fp32
-    rule kernels through LRPtools (any supported encoder; the parity path)."""
+    """reference :705-1211.  ``precision`` (a keyword the reference does not have; default 'fp32'):
+      'fp32' — the reference's fp32 bar.  VGG encoders: the tcgen05 chain in its fp32-accurate mode (error-compensated
+               bf16x3 operands, fp32 gains, hi|lo inter-layer storage); other encoders: the fp32 CUDA-core rule kernels
+               through LRPtools.  Decoder GEMMs on fp32 CUDA cores.
+      'bf16' — VGG encoders only: the tcgen05 chain with bf16 operands / storage (Spearman >= 0.99, rel-L2 <= 5e-2 vs
+               the reference), decoder GEMMs as bf16x3 on tensor cores.  The throughput mode of bench.py.
+      'simt' — the fp32 CUDA-core rule kernels through LRPtools whatever the encoder."""
     EPS = LRPutil.EPSILON
     EX_TYPE = 'lrp'
     # the reference never zeroes sample.grad, so relevance_imgs[t] of explain_caption is the running sum over
@@ -487,9 +487,16 @@ class ExplainGridTDAttention(object):
         # bottom-up twins (GridTDModelBU / AOAModelBU) have no CNN: the explanation ends at the region features
         self.has_encoder = hasattr(self.model, 'img_encoder')
         is_vgg = self.has_encoder and isinstance(self.model.img_encoder.encoder, nn.Sequential)
-        self.precision = precision or ('bf16' if is_vgg else 'fp32')
-        if self.precision == 'bf16' and not is_vgg and self.has_encoder:
+        self.precision = precision or 'fp32'
+        if self.precision not in ('fp32', 'bf16', 'simt'):
+            raise ValueError(f"precision must be 'fp32', 'bf16' or 'simt', got {self.precision!r}")
+        tcp = lrp_wrapper._tc_cfg(self.model.img_encoder.encoder) if is_vgg else None
+        # the general kernels (fp32-accurate mode) need a first conv with a multiple of 64 output channels
+        tc_ok = tcp is not None and (self.precision == 'bf16' or tcp[0][0].out_channels % 64 == 0)
+        if self.precision == 'bf16' and not tc_ok and self.has_encoder:
             raise NotImplementedError("the tensor-core chain supports VGG-style encoders; use precision='fp32'")
+        # the encoder runs on the tcgen05 engine (one forward per image shared by all its words)
+        self.uses_tc = tc_ok and self.precision in ('fp32', 'bf16')
         self.mean = [0.485, 0.456, 0.406]
         self.std = [0.229, 0.224, 0.225]
         m = self.model
@@ -505,12 +512,8 @@ class ExplainGridTDAttention(object):
 
     # ------------------------------------------------------------------ helpers
     def lrp_linear_eps(self, r_out, forward_input, forward_output, weight):
-        """reference :744-765 (tensor expression, API compatibility)."""
-        if type(forward_output) == bool:
-            forward_output = torch.matmul(forward_input, weight.transpose(0, 1))
-        z = self.EPS * forward_output.sign() + forward_output
-        z = z.masked_fill(z == 0, self.EPS)
-        return forward_input * torch.matmul(r_out.reshape(-1) / z, weight)
+        """reference :744-765 on the device: ``lrpx_lrp_linear_eps_f32`` (CUDA tensors only, no CPU fallback)."""
+        return ops.lrp_linear_eps(r_out, forward_input, forward_output, weight)
 
     def preprocess_img(self, img_filepath):
         """reference :767-771: Resize((height,width)) -> ToTensor -> Normalize."""
@@ -538,12 +541,13 @@ class ExplainGridTDAttention(object):
                     cfg.append(m.out_channels)
                 elif isinstance(m, nn.MaxPool2d):
                     cfg.append("M")
-            self._engine = tc.TcVggEngine([c.weight for c in convs], [c.bias for c in convs], cfg, self.device)
+            self._engine = tc.TcVggEngine([c.weight for c in convs], [c.bias for c in convs], cfg, self.device,
+                                          precision=self.precision)
         return self._engine
 
     def encode_images(self, imgs):
         """Encoder forward -> (features (B,P,C) fp32 pixel-major, feature map size, encoder state)."""
-        if self.precision == 'bf16':
+        if self.uses_tc:
             eng = self.engine()
             est = eng.forward(imgs)
             return eng.features(est, "pixel"), est.feat_hw, est
@@ -678,7 +682,7 @@ class ExplainGridTDAttention(object):
         encoder pass when it was already needed for the search (device search), else None."""
         m = self.model
         enc = None
-        if (self.DEVICE_BEAM_SEARCH and self.precision == 'bf16' and self.has_encoder and self.img.is_cuda
+        if (self.DEVICE_BEAM_SEARCH and self.uses_tc and self.has_encoder and self.img.is_cuda
                 and 'beam_search' not in m.__dict__):
             from lrpx import beam
             if getattr(self, "_beam", None) is None:
@@ -753,13 +757,13 @@ class ExplainGridTDAttention(object):
 
     def explain_cnn(self, r_img_feature):
         """reference :1137-1139: relevance of the encoder output -> relevance of the image (1,3,H,W)."""
-        if self.precision == 'bf16':
+        if self.uses_tc:
             r_pix = r_img_feature.flatten(2).transpose(1, 2).contiguous()
             return self.engine().relevance(self._enc_state, r_pix)
         enc = self.model.img_encoder.encoder
         if not hasattr(enc, "_lrpx_plan"):
             lrp_wrapper.add_lrp(enc)
-        return enc.compute_lrp(self.img, target=r_img_feature)
+        return enc.compute_lrp(self.img, target=r_img_feature, precision='simt')
 
     def explain_caption(self, img_filepath, t_list=None):
         """reference :1141-1156 -> (relevance_imgs [T x (1,3,H,W)], relevance_preceeding_words [T x (t+1,)]).
@@ -770,14 +774,14 @@ class ExplainGridTDAttention(object):
         if T == 0:
             return [], []
         r_feat, r_words = self._decoder_lrp(list(range(T)))
-        if self.precision == 'bf16':
+        if self.uses_tc:
             rows = torch.zeros(T, dtype=torch.int32, device=self.device)
             heat = self.engine().relevance(self._enc_state, r_feat, rows)
         else:
             enc = self.model.img_encoder.encoder
             lrp_wrapper.add_lrp(enc)
             fh, fw = self._feat_hw
-            heat = torch.cat([lrp_wrapper.compute_lrp(enc, self.img.detach().clone(),
+            heat = torch.cat([lrp_wrapper.compute_lrp(enc, self.img.detach().clone(), precision='simt',
                                                       target=r_feat[t].t().reshape(1, -1, fh, fw)) for t in range(T)])
         if self.ACCUMULATE_LIKE_REFERENCE:
             heat = torch.cumsum(heat, 0)

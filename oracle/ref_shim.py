@@ -25,7 +25,20 @@ import types
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("LRPX_REFERENCE_ROOT", "/root/reference")
+def _find_reference():
+    """/root/reference in the build container; on the GPU box the copy oracle/stage_reference.py left under
+    baseline/_ref (git-ignored, travels with the gpurun snapshot)."""
+    env = os.environ.get("LRPX_REFERENCE_ROOT")
+    if env:
+        return env
+    staged = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    for cand in ("/root/reference", staged):
+        if os.path.isdir(os.path.join(cand, "LRPtools")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 # A fixed English stop-word subset (nltk is not installed, SURVEY.md §8c(iii)); the
 # synthetic vocabulary used by the tests draws stop words from here.
@@ -110,9 +123,14 @@ def load_reference(cpu: bool = True):
         torch.Tensor.cuda = lambda self, *a, **k: self
         nn.Module.cuda = lambda self, *a, **k: self
     # Make sure the reference's own top-level packages win over the repo's mirrors.
-    for k in [k for k in sys.modules if k.split(".")[0] in ("LRPtools", "models")]:
-        del sys.modules[k]
-    sys.path.insert(0, REFERENCE_ROOT)
+    # (the product's mirrors are regular packages and would shadow the reference's namespace packages whatever the
+    # path order: take every other tree that carries an LRPtools package off sys.path while importing; the mirrors
+    # already imported are put back under their names afterwards)
+    mirrors = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split(".")[0] in ("LRPtools", "models")}
+    saved_path = list(sys.path)
+    sys.path[:] = [REFERENCE_ROOT] + [q for q in saved_path
+                                      if not os.path.isdir(os.path.join(q or ".", "LRPtools")) or
+                                      os.path.abspath(q or ".") == os.path.abspath(REFERENCE_ROOT)]
     try:
         import LRPtools.utils as ref_utils  # noqa
         import models.vgg as ref_vgg
@@ -151,7 +169,7 @@ def load_reference(cpu: bool = True):
         ref_aoa = _load_patched("models.aoamodel", "models/aoamodel.py")
         ref_ada = _load_patched("models.adaptiveattention", "models/adaptiveattention.py")
     finally:
-        sys.path.remove(REFERENCE_ROOT)
+        sys.path[:] = saved_path
     ns = types.SimpleNamespace(utils=ref_utils, lrp_modules=ref_lrp_modules, lrp_wrapper=ref_lrp_wrapper,
                                vgg=ref_vgg, resnet=ref_resnet, gridTDmodel=ref_grid, aoamodel=ref_aoa,
                                adaptiveattention=ref_ada)
@@ -159,4 +177,5 @@ def load_reference(cpu: bool = True):
     # leave the reference's modules registered under private names only
     for k in [k for k in sys.modules if k.split(".")[0] in ("LRPtools", "models")]:
         sys.modules["_lrpx_ref_." + k] = sys.modules.pop(k)
+    sys.modules.update(mirrors)
     return ns

@@ -93,13 +93,15 @@ def test_explain_caption_end_to_end_both_precisions(tmp_path):
     img = synth.images(83, 1)
     toks = synth.tokens(84, 3, V)
     outs = {}
-    for prec in ("fp32", "bf16"):
+    for prec in ("simt", "fp32", "bf16"):
         ex = G.ExplainGridTDAttention(_args(E, H, tmp_path), synth.word_map(V), model=model, precision=prec)
+        assert ex.uses_tc == (prec != "simt")
         ex.ACCUMULATE_LIKE_REFERENCE = False
         ex.preprocess_img = lambda p: img.to(DEV)
         model.beam_search = lambda *a, **k: (["a b c"], toks[1:])
         outs[prec] = ex.explain_caption("synthetic.jpg")
-    heat32, words32 = outs["fp32"]
+    heat32, words32 = outs["simt"]
+    heatx3, wordsx3 = outs["fp32"]
     heat16, words16 = outs["bf16"]
     assert len(heat32) == 3 and heat32[0].shape == (1, 3, 224, 224)
     # fp32 path vs the oracle
@@ -111,12 +113,28 @@ def test_explain_caption_end_to_end_both_precisions(tmp_path):
         rf, rw, _ = O.gridtd_explain_wordt(sd, st, t)
         ref = O.sequential_lrp(layers, img, rf.t().reshape(1, 512, 14, 14))
         scale = ref.abs().max()
-        assert_close(heat32[t] / scale, ref / scale, rtol=2e-3, atol=2e-4, what=f"fp32 heat-map t={t}")
-        assert_close(words32[t], rw, rtol=1e-3, atol=1e-4, what=f"r_words t={t}")
-        sp = spearman(heat16[t], heat32[t])
-        l2 = float((heat16[t] - heat32[t]).norm() / heat32[t].norm())
-        print(f"word {t}: bf16 vs fp32 spearman {sp:.5f} rel L2 {l2:.3e}")
-        assert sp >= 0.99 and l2 <= 1e-1
+        _check_three_precisions(t, ref, rw, scale, heat32[t], words32[t], heatx3[t], wordsx3[t], heat16[t])
+
+
+def _check_three_precisions(t, ref, rw, scale, h_simt, w_simt, h_x3, w_x3, h_bf16):
+    """One explained word against the CPU oracle: 'simt' (fp32 CUDA-core rules + fp32 decoder GEMMs) at the fp32 bar,
+    scale-relative (rtol 1e-4 / atol 1e-4 x max|R|: the end-to-end heat-map goes through 13 conv layers whose
+    divisions by z+ are guarded at exact zero only); 'fp32' (tcgen05 chain, bf16x3) by rel-L2 / share of pixels at
+    that bar / worst pixel (max-pool winners tied within ~1e-5 may flip, see test_gpu_tcx.py); 'bf16' by Spearman."""
+    assert_close(h_simt / scale, ref / scale, rtol=1e-4, atol=1e-4, what=f"simt heat-map t={t}")
+    assert_close(w_simt, rw, rtol=1e-4, atol=1e-5, what=f"r_words t={t}")
+    a, b = (h_x3 / scale).cpu().double(), (ref / scale).double()
+    err = (a - b).abs()
+    l2 = float((a - b).norm() / b.norm())
+    far = float((err > 1e-4 * b.abs() + 1e-4).double().mean())
+    print(f"word {t}: fp32-accurate chain rel L2 {l2:.3e}, worst pixel {float(err.max()):.3e} of max, "
+          f"share beyond rtol 1e-4 + 1e-4 max: {far:.3e}")
+    assert l2 <= 1e-3 and far <= 1e-2 and float(err.max()) <= 1e-2
+    assert_close(w_x3, rw, rtol=1e-4, atol=1e-5, what=f"r_words (chain) t={t}")
+    sp = spearman(h_bf16, h_simt)
+    l2b = float((h_bf16 - h_simt).norm() / h_simt.norm())
+    print(f"word {t}: bf16 vs simt spearman {sp:.5f} rel L2 {l2b:.3e}")
+    assert sp >= 0.99 and l2b <= 1e-1
 
 
 @pytest.mark.parametrize("name", ["aoa_dec_512", "aoa_dec_bu"])
@@ -457,12 +475,13 @@ def test_adaptive_explain_caption_end_to_end(tmp_path):
     T = len(toks) - 1
     model.beam_search = lambda *a, **k: ([" ".join(f"w{t}" for t in toks[1:])], toks[1:])
     outs = {}
-    for prec in ("fp32", "bf16"):
+    for prec in ("simt", "fp32", "bf16"):
         ex = AA.ExplainAdaptiveAttention(_args(E, H, tmp_path), wm, model=model, precision=prec)
         ex.ACCUMULATE_LIKE_REFERENCE = False
         ex.preprocess_img = lambda p: img.to(DEV)
         outs[prec] = ex.explain_caption("synthetic.jpg")
-    heat32, words32 = outs["fp32"]
+    heat32, words32 = outs["simt"]
+    heatx3, wordsx3 = outs["fp32"]
     heat16, words16 = outs["bf16"]
     assert len(heat32) == T and heat32[0].shape == (1, 3, 224, 224)
     layers = O.vgg_layers_from_state(vsd)
@@ -473,12 +492,7 @@ def test_adaptive_explain_caption_end_to_end(tmp_path):
         rf, rw, _ = O.adaptive_explain_wordt(sd, st, t)
         ref = O.sequential_lrp(layers, img, rf.t().reshape(1, 512, 14, 14))
         scale = ref.abs().max()
-        assert_close(heat32[t] / scale, ref / scale, rtol=2e-3, atol=2e-4, what=f"fp32 heat-map t={t}")
-        assert_close(words32[t], rw, rtol=1e-3, atol=1e-4, what=f"r_words t={t}")
-        sp = spearman(heat16[t], heat32[t])
-        l2 = float((heat16[t] - heat32[t]).norm() / heat32[t].norm())
-        print(f"adaptive word {t}: bf16 vs fp32 spearman {sp:.5f} rel L2 {l2:.3e}")
-        assert sp >= 0.99 and l2 <= 1e-1
+        _check_three_precisions(t, ref, rw, scale, heat32[t], words32[t], heatx3[t], wordsx3[t], heat16[t])
 
 
 def test_batch_pipeline_adaptive_equals_single_image_api(tmp_path):

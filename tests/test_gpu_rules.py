@@ -180,3 +180,31 @@ def test_lrp_weights(golden):
     assert torch.equal(am.cpu().long(), logits.argmax(-1))
     assert_close(wc, rc, atol=1e-5, what="w_ctx big")
     assert_close(wh, rh, atol=1e-5, what="w_h big")
+
+
+def test_named_vector_rules_on_device():
+    """The explainers' named methods as CUDA entry points: lrp_linear_eps (gridTDmodel.py:744-765) against the oracle's
+    restatement, with the pre-activation given and recomputed (forward_output=False), at the sizes the reference calls
+    it with (fc: V x H, identity: H x H, gate GEMV: H x 3H); lrp_mha (aoamodel.py:812-862, reference argument order)."""
+    from lrpx import ops
+    g = torch.Generator().manual_seed(11)
+    for n_out, n_in in ((5, 6), (512, 512), (512, 1536), (10000, 512)):
+        x, w, r = torch.randn(n_in, generator=g), torch.randn(n_out, n_in, generator=g) * 0.1, torch.randn(n_out, generator=g)
+        z = w @ x + 0.1 * torch.randn(n_out, generator=g)            # "with bias"
+        z[0] = 0.0                                                    # exact zero -> 0.01
+        for zz in (z, False):
+            want = O.lrp_linear_eps(r.double(), x.double(), zz if isinstance(zz, bool) else zz.double(), w.double())
+            got = ops.lrp_linear_eps(r.to(DEV), x.to(DEV), zz if isinstance(zz, bool) else zz.to(DEV), w.to(DEV))
+            assert_close(got, want, rtol=1e-4, atol=1e-5 * float(want.abs().max()), what=f"lrp_linear_eps {n_out}x{n_in}")
+        got = ops.lrp_linear_eps(r.view(1, -1).to(DEV), x.to(DEV), z.to(DEV), w.to(DEV))     # (1, n_out) relevance as at :1047
+        assert_close(got, O.lrp_linear_eps(r.double(), x.double(), z.double(), w.double()), rtol=1e-4,
+                     atol=1e-5 * float(want.abs().max()), what="lrp_linear_eps row-vector r_out")
+    P, H, nh, hd = 36, 512, 8, 5
+    alpha = torch.softmax(torch.randn(nh, P, generator=g), -1)
+    value, ctx, r_ctx = torch.randn(P, H, generator=g), torch.randn(1, H, generator=g), torch.randn(1, H, generator=g)
+    ctx[0, hd * 64] = 0.0
+    got = ops.lrp_mha(alpha.to(DEV), value.to(DEV), r_ctx.to(DEV), ctx.to(DEV), nh, hd)
+    sl = slice(hd * 64, (hd + 1) * 64)
+    want = torch.zeros(P, H, dtype=torch.double)
+    want[:, sl] = value[:, sl].double() * alpha[hd][:, None].double() * (r_ctx[0, sl].double() / O.stab(ctx[0, sl].double()))[None, :]
+    assert_close(got, want, rtol=1e-5, atol=1e-6, what="lrp_mha")

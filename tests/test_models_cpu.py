@@ -69,14 +69,16 @@ def test_beam_search_runs_and_uses_floor_division():
     assert isinstance(sent, list) and all(0 < i < V - 3 for i in idx) and len(idx) <= 20
 
 
-def test_lrp_linear_eps_expression_matches_oracle():
+def test_lrp_linear_eps_has_no_cpu_form():
+    """The named vector rule is a CUDA entry point (lrpx_lrp_linear_eps_f32; parity in tests/test_gpu_rules.py): on
+    CPU tensors it raises instead of falling back to a tensor expression."""
     from models import gridTDmodel as G
+    from lrpx._lib import LrpxError
     m = G.GridTDModel(8, 8, 20, "vgg16")
     g = torch.Generator().manual_seed(1)
     x, w, r = torch.randn(6, generator=g), torch.randn(5, 6, generator=g), torch.randn(5, generator=g)
-    z = w @ x
-    assert_close(m.lrp_linear_eps(r, x, z, w), O.lrp_linear_eps(r, x, z, w), what="lrp_linear_eps")
-    assert_close(m.lrp_linear_eps(r, x, False, w), O.lrp_linear_eps(r, x, False, w), what="lrp_linear_eps recompute")
+    with pytest.raises(LrpxError):
+        m.lrp_linear_eps(r, x, w @ x, w)
 
 
 @pytest.mark.parametrize("name", ["aoa_dec_512", "aoa_dec_bu"])
@@ -103,16 +105,8 @@ def test_aoa_explainer_forward_matches_reference_fixture(golden, tmp_path, name)
     assert_close(st["alpha"][0], g["alphas"].reshape(st["alpha"][0].shape), atol=1e-6, what="alphas")
     assert_close(st["h"][0], g["ht"], atol=1e-5, what="ht")
     assert_close(st["caoa"][0], g["context_aoa"], atol=1e-5, what="context_aoa")
-    # lrp_mha tensor expression vs the oracle's single-head rule
-    ost = O.aoa_explainer_forward(sd, g["feats"][0], g["tokens"].tolist(), 8)
-    t, hd = g["cases"].tolist()[0]
-    r_ctx = torch.randn(H, generator=torch.Generator().manual_seed(1))
-    got = ex.lrp_mha(ost["alpha"][t], ost["value"], ost["ctx"][t], r_ctx, hd)
-    dk = H // 8
-    sl = slice(hd * dk, (hd + 1) * dk)
-    want = torch.zeros_like(got)
-    want[:, sl] = ost["value"][:, sl] * ost["alpha"][t][hd][:, None] * (r_ctx[sl] / O.stab(ost["ctx"][t][sl]))[None, :]
-    assert_close(got, want, what="lrp_mha")
+    with pytest.raises(LrpxError):                       # lrp_mha is a CUDA entry point too (tests/test_gpu_rules.py)
+        ex.lrp_mha(st["alpha"][0, 0], st["value"][0], st["ctx"][0, :1], st["ctx"][0, :1], 0)
 
 
 def _bu_models(g):
