@@ -312,9 +312,13 @@ def parity_config2(args, ex, eng, W, imgs_d, toks_d, heat, r_words, ref_out, T):
         l2.append(float((a - r).norm() / r.norm()))
         mx.append(float((a - r).abs().max() / r.abs().max()))
         wd.append(float((r_words[q, :t + 1].detach().cpu().double() - rw_ref.double()).abs().max()))
+    med = lambda v: sorted(v)[len(v) // 2]
     out = {"requests_checked": len(ref_out), "against": "reference" if _ref_runner() is not None else "oracle port",
-           "heatmap_spearman_min": min(sp), "heatmap_rel_l2_max": max(l2), "heatmap_max_err_over_max_abs": max(mx),
-           "words_max_abs": max(wd)}
+           "heatmap_spearman_min": min(sp), "heatmap_spearman_median": med(sp),
+           "heatmap_rel_l2_max": max(l2), "heatmap_rel_l2_median": med(l2),
+           "heatmap_max_err_over_max_abs": max(mx), "words_max_abs": max(wd), "words_max_abs_median": med(wd),
+           "note": "end to end against the fp32 reference: encoder features -> decoder (LSTM chain over the caption) -> "
+                   "decoder relevance -> encoder chain; `decoder_*` isolate the decoder kernels on identical features"}
     # ---- decoder isolated: product decoder kernels vs the oracle decoder on the SAME (product) encoder features
     seed = 0
     p = synth.gridtd_decoder_state(1000 + seed, args.vocab, 512, 512)

@@ -517,6 +517,26 @@ typedef struct {
   int rule;             /* FWDX: 0 alpha-beta, 1 epsilon                                          */
   int zbias;            /* FWDX: the bias enters the rule's divisor (ignore_bias = False)         */
   float alpha, beta;    /* FWDX                                                                   */
+  /* ---- residual networks (models/resnet.py:95-140, lrp_modules.py:197-280) */
+  const void* add;      /* MULX: per-block addend rows (bf16, `add_pitch` elements per row): the relevance of the other
+                         * branch at a fork;  out_j = acc * gain_j + add * gainB_j   (gainB_0 = gain3, gainB_1 = gain4).
+                         * With out2 set and two groups the groups go to two separate (rows, ncol) bf16 tensors
+                         * (out, out2) instead of one K-concatenated row.
+                         * MULX_UNPOOL with pool_idx == NULL writes every product at the FIRST pixel of its 2x2 block:
+                         * the zero-stuffing of a stride-2 transposed convolution.                              */
+  const void* gain3;
+  const void* gain4;
+  const float* bn_w;    /* FWDX: folded BatchNorm y = z*bn_w[n] + bn_b[n] (eval mode) and its rule
+                         * R = |z w| / (|z w| + |b|) R_out (lrp_modules.py:204-215) as a factor of gain0           */
+  const float* bn_b;
+  const void* idn;      /* FWDX: identity branch (bf16 PF, cout channels): out = relu(y + idn), Add rule ratios
+                         * rho1 = y / stab'(y+idn) (factor of gain0), rho2 = idn / stab'(y+idn); out3 = rho2 * hd   */
+  const void* hd;       /* FWDX: bf16 PF factor of the identity-branch gain (the downsample conv's ratio / z+) or NULL */
+  void* out4;           /* FWDX: act * gain0                                                       */
+  void* out5;           /* FWDX: act * out3                                                        */
+  int add_pitch;
+  int fwd_flags;        /* FWDX: bit 0 = no ReLU (downsample branch), bit 1 = keep the even pixels only and store
+                         * them into a PF tensor of half the resolution (stride-2 convolution)            */
 } lrpx_tc_conv_args;
 
 int lrpx_tc_conv(const lrpx_tc_conv_args* args, void* stream);
@@ -572,6 +592,24 @@ int lrpx_tc_maxpool2_x(const void* act, const void* gain0_fine, const void* gain
 /* lrpx_tc_scale_rows for the general chain: out row = [r*rz0 | r*rz1] (groups), bf16 or hi|lo split */
 int lrpx_tc_scale_rows_x(const float* r, const void* rz0, const void* rz1, const int32_t* row_img, void* out,
                          int n_expl, int h, int w, int c, int groups, int split, void* stream);
+/* ---- residual-network encoder (models/resnet.py:143-239): stem and strides, bf16 PF */
+/* conv1 (7x7 / stride 2 / pad 3, mixed-sign input): sign-split im2col at the output resolution (h/2, w/2): rows of 320
+ * bf16 [x+ over the 147 (ci,ky,kx) taps | x- over the 147 taps | 26 zeros] for lrpx_tc_conv(ksize 1, cin 320, FWDX). */
+int lrpx_tc_im2col7s2_split_bf16(const float* x, void* dst, int n, int h, int w, void* stream);
+/* 3x3 / stride 2 / pad 1 max-pool of a post-ReLU PF tensor (h, w even): pooled (h/2, w/2) and idx = ky*3+kx of the winner
+ * (PyTorch scan order, first maximum wins), 255 where the maximum is 0 (no relevance passes, lrp_modules.py:186-191). */
+int lrpx_tc_maxpool3s2_bf16(const void* act, void* pooled, uint8_t* idx, int n, int h, int w, int c, void* stream);
+/* relevance through that pool, gather form over the overlapping windows, times the per-image gain of the layer below:
+ * out[e][i][j][c] = gain[row_img[e]][i][j][c] * sum_{windows (y,x) containing (i,j) with winner (i,j)} r[e][y][x][c] */
+int lrpx_tc_unpool3s2_bf16(const void* r, const uint8_t* idx, const void* gain, const int32_t* row_img, void* out, int n_expl,
+                           int h, int w, int c, void* stream);
+/* dst (n, h/2, w/2) <- src (n, h, w) at the even pixels (input of a 1x1 / stride 2 convolution) */
+int lrpx_tc_subsample2_bf16(const void* src, void* dst, int n, int h, int w, int c, void* stream);
+/* stem relevance: gathers the image relevance from P (n_expl * (h/2+1)*(w/2+1) rows of ldp floats, column
+ * (ky*7+kx)*6 + s*3 + c = sum_ch A[q][ch] W(s)[ch][c][ky][kx], s = 0: W+, 1: W-) written by the 1x1 GEMM
+ * (lrpx_tc_conv, STORE_F32):  heat = x+ * sum P[..][0][c] + x- * sum P[..][1][c];  mode as LRPX_TC_EPI_INPUT3's. */
+int lrpx_tc_stem_col2im_f32(const float* P, int ldp, const float* x, const int32_t* row_img, void* out, int n_expl, int h,
+                            int w, int mode, void* stream);
 /* lrpx_tc_pf_to_dense_f32 for hi|lo rows of 2*c channels (value = hi + lo) */
 int lrpx_tc_pf_split_to_dense_f32(const void* src, float* dst, int n, int h, int w, int c, int layout, void* stream);
 

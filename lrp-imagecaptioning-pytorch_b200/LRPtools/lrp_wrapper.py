@@ -215,6 +215,35 @@ def _tc_cfg(model):
     return convs, cfg
 
 
+def _is_bottleneck_resnet(model):
+    """models/resnet.py ResNet made of Bottleneck blocks with the explicit Add module (what lrpx.tc_resnet runs)."""
+    if not all(hasattr(model, a) for a in ("conv1", "bn1", "maxpool", "layer1", "layer2", "layer3", "layer4")):
+        return False
+    blocks = [b for L in (model.layer1, model.layer2, model.layer3, model.layer4) for b in L]
+    return bool(blocks) and all(all(hasattr(b, a) for a in ("conv1", "bn1", "conv2", "bn2", "conv3", "bn3", "add"))
+                                for b in blocks)
+
+
+class _TcResNetPlan:
+    """Tensor-core route of ``compute_lrp(precision='bf16')`` for Bottleneck ResNets (alpha=1, beta=0 preset)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.convs = [m for m in model.modules() if isinstance(m, nn.Conv2d)]
+        self._eng = None
+
+    def engine(self, precision, lrp_params):
+        from lrpx import tc_resnet
+        if precision != "bf16" or float(lrp_params.get("alpha", 1.)) != 1. or float(lrp_params.get("beta", 0.)) != 0. \
+                or not lrp_params.get("ignore_bias", True):
+            return None
+        ps = [p for p in self.model.parameters()] + [b for b in self.model.buffers()]
+        stamp = tuple((t.data_ptr(), t._version) for t in ps)
+        if self._eng is None or self._eng[0] != stamp:
+            self._eng = (stamp, tc_resnet.TcResNetEngine(self.model, ps[0].device))
+        return self._eng[1]
+
+
 class _TcPlan:
     """Tensor-core route of ``compute_lrp`` for VGG-style encoders: ONE TcVggEngine per (precision, alpha, beta),
     rebuilt when a weight tensor changes (data pointer / in-place version)."""
@@ -257,7 +286,7 @@ def add_lrp(model):
             module.lrp_params = preset.lrp_params
     model._lrpx_plan = _build_plan(model)
     tcp = _tc_cfg(model)
-    model._lrpx_tc = _TcPlan(*tcp) if tcp is not None else None
+    model._lrpx_tc = _TcPlan(*tcp) if tcp is not None else (_TcResNetPlan(model) if _is_bottleneck_resnet(model) else None)
     model.compute_lrp = lambda sample, **kwargs: compute_lrp(model, sample, **kwargs)
 
 
@@ -295,7 +324,9 @@ def compute_lrp(model, sample, target=None, return_output=False, rectify_logits=
         use_tc = all(c.lrp_method == "alpha_beta" and c.lrp_params == params for c in tcp.convs)
         general = not (precision == "bf16" and params.get("alpha", 1.) == 1. and params.get("beta", 0.) == 0.
                        and params.get("ignore_bias", True))
-        if general and tcp.convs[0].out_channels % 64:
+        if isinstance(tcp, _TcResNetPlan):
+            use_tc = use_tc and not general and not model.training   # ResNets: the bf16 chain only
+        elif general and tcp.convs[0].out_channels % 64:
             use_tc = False                    # the general kernels need a 64-channel first layer: CUDA-core walker
     if precision == "bf16" and not use_tc:
         raise NotImplementedError("compute_lrp(precision='bf16'): the tensor-core chain covers VGG-style encoders "

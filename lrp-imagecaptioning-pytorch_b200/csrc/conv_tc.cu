@@ -87,6 +87,18 @@ struct TcParams {
   float alpha, beta;
   const void* gain2;
   void* out3;
+  // ---- residual-network extensions (MULX: fork sum; FWDX: folded BatchNorm, residual Add, strided store)
+  const void* add;   // MULX: per-request addend rows (bf16, pitch add_pitch): out_j = acc*gain_j + add*gainB_j
+  int add_pitch;
+  const void* gain3; // MULX: gainB of group 0
+  const void* gain4; // MULX: gainB of group 1
+  const float* bn_w; // FWDX: folded BatchNorm scale / shift per output channel (nullptr: plain bias)
+  const float* bn_b;
+  const void* idn;   // FWDX: residual identity branch (bf16 PF, cout channels): Add rule ratios
+  const void* hd;    // FWDX: per-element factor of the identity-branch gain (bf16 PF) or nullptr
+  void* out4;        // FWDX: act * gain0
+  void* out5;        // FWDX: act * (identity-branch gain)
+  int fwd_flags;     // FWDX: bit 0 = no ReLU, bit 1 = store only the even pixels into a half-resolution PF tensor
   const float* bias;
   const __nv_bfloat16* gain;
   const int32_t* row_img;
@@ -613,10 +625,10 @@ __device__ __forceinline__ void epi_mulx(const TcParams& p, const RowInfo& r, ui
     float g[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) g[k] = 0.f;
-    uint4 sidx = make_uint4(0u, 0u, 0u, 0u);
+    uint4 sidx = make_uint4(0u, 0u, 0u, 0u);          // pool_idx == nullptr: every winner is the window's first pixel
     if (r.valid) {
       load_gain16(p.gain, gbase + col, sp, g);
-      if (UNPOOL) sidx = ldg_nc_v4(p.pool_idx + gbase + col);
+      if (UNPOOL && p.pool_idx) sidx = ldg_nc_v4(p.pool_idx + gbase + col);
     }
     uint32_t v[16];
     TMEM_LD_X16(taddr + c + 16 * q, v);
@@ -626,17 +638,36 @@ __device__ __forceinline__ void epi_mulx(const TcParams& p, const RowInfo& r, ui
 #pragma unroll 1
     for (int j = 0; j < G; ++j) {
       if (j == 1 && r.valid) load_gain16(p.gain2, gbase + col, sp, g);
+      float t[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t[k] = 0.f;
+      if (!UNPOOL && p.add && r.valid) {      // fork of a residual block: the other branch's relevance joins here
+        float ad[16], gb[16];
+        load_gain16(p.add, (size_t)r.row * p.add_pitch + col, false, ad);
+        const void* gbp = j ? p.gain4 : p.gain3;           // nullptr: the addend joins unscaled
+        if (gbp) load_gain16(gbp, gbase + col, sp, gb);
+        else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) gb[k] = 1.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) t[k] = ad[k] * gb[k];
+      }
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float a0 = r.valid ? __uint_as_float(v[2 * k]) * g[2 * k] : 0.f;
-        const float a1 = r.valid ? __uint_as_float(v[2 * k + 1]) * g[2 * k + 1] : 0.f;
+        const float a0 = r.valid ? fmaf(__uint_as_float(v[2 * k]), g[2 * k], t[2 * k]) : 0.f;
+        const float a1 = r.valid ? fmaf(__uint_as_float(v[2 * k + 1]), g[2 * k + 1], t[2 * k + 1]) : 0.f;
         split_pack(a0, a1, hi[k], lo[k]);
       }
       if (!UNPOOL) {
-        __nv_bfloat16* dst = out + (size_t)r.row * p.out_c + col;
-        stg_v8(dst + (size_t)j * N, hi);
-        if (sp) stg_v8(dst + (size_t)(G + j) * N, lo);
+        if (j == 1 && p.out2) {               // two separate tensors instead of one K-concatenated row
+          stg_v8(reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)r.row * N + col, hi);
+        } else {
+          __nv_bfloat16* dst = out + (size_t)r.row * p.out_c + col;
+          stg_v8(dst + (size_t)j * N, hi);
+          if (sp) stg_v8(dst + (size_t)(G + j) * N, lo);
+        }
       } else {
         const int wf1 = 2 * p.w + 1;
         const size_t blk_f = (size_t)(2 * p.h + 1) * wf1;
@@ -675,10 +706,44 @@ __device__ __forceinline__ void stg_f32x16(float* dst, const float (&v)[16]) {
 }
 
 // FWDX: 32 output channels [c, c+32) of tile column block n_tile (see LRPX_TC_EPI_FWDX in lrpx.h)
+__device__ __forceinline__ void load_bf16x16(const void* base, size_t off, float (&g)[16]) {
+  const U8 a = ldg_nc_v8(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { g[2 * k] = bf16_lo(a.w[k]); g[2 * k + 1] = bf16_hi(a.w[k]); }
+}
+__device__ __forceinline__ void store_act16(void* base, size_t off, size_t lo_off, bool sp, const float (&v)[16]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) split_pack(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(base) + off;
+  stg_v8(dst, hi);
+  if (sp) stg_v8(dst + lo_off, lo);
+}
+__device__ __forceinline__ void store_gain16(void* base, size_t off, bool f32, const float (&v)[16]) {
+  if (f32) {
+    stg_f32x16(reinterpret_cast<float*>(base) + off, v);
+  } else {
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = pack_bf16(v[2 * k], v[2 * k + 1]);
+    stg_v8(reinterpret_cast<__nv_bfloat16*>(base) + off, w);
+  }
+}
+
 __device__ __forceinline__ void epi_fwdx(const TcParams& p, const RowInfo& r, uint32_t taddr, int n_tile, int c,
                                          uint32_t release_bar) {
   const bool sp = p.split != 0;
   const int cout = p.cout;
+  // strided store (fwd_flags bit 1): a stride-2 convolution is the stride-1 result at the even pixels; only those rows
+  // are written, into a PF tensor of half the resolution (whose padding rows the caller has zeroed)
+  const bool sub2 = (p.fwd_flags & 2) != 0;
+  bool store = r.in_range;
+  size_t orow = (size_t)r.row;
+  if (sub2) {
+    store = r.valid && ((r.a - 1) & 1) == 0 && ((r.b - 1) & 1) == 0;
+    const int hc = p.h >> 1, wc = p.w >> 1;
+    orow = (size_t)r.e * (size_t)((hc + 1) * (wc + 1)) + (size_t)(((r.a - 1) >> 1) + 1) * (wc + 1) + (((r.b - 1) >> 1) + 1);
+  }
 #pragma unroll 1
   for (int q = 0; q < 2; ++q) {
     const int ch = n_tile * p.half + c + 16 * q;
@@ -688,33 +753,63 @@ __device__ __forceinline__ void epi_fwdx(const TcParams& p, const RowInfo& r, ui
     if (p.n_acc >= 3) TMEM_LD_X16(taddr + 2 * p.half + c + 16 * q, vn);
     tmem_ld_wait();
     if (q == 1) epi_release(release_bar);
-    if (!r.in_range) continue;
-    float bv[16];
+    if (!store) continue;
+    float bv[16], sw[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) bv[k] = 0.f;
-    if (p.bias) {
+    for (int k = 0; k < 16; ++k) { bv[k] = 0.f; sw[k] = 1.f; }
+    const float* shift = p.bn_w ? p.bn_b : p.bias;
+    if (shift) {
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + ch) + k4);
+        const float4 t = __ldg(reinterpret_cast<const float4*>(shift + ch) + k4);
         bv[4 * k4] = t.x; bv[4 * k4 + 1] = t.y; bv[4 * k4 + 2] = t.z; bv[4 * k4 + 3] = t.w;
       }
     }
-    float act[16], g0[16], g1[16];
+    if (p.bn_w) {
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bn_w + ch) + k4);
+        sw[4 * k4] = t.x; sw[4 * k4 + 1] = t.y; sw[4 * k4 + 2] = t.z; sw[4 * k4 + 3] = t.w;
+      }
+    }
+    float idv[16], hdv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { idv[k] = 0.f; hdv[k] = 1.f; }
+    const size_t go = orow * cout + ch;
+    if (p.idn && r.valid) load_bf16x16(p.idn, go, idv);
+    if (p.hd && r.valid) load_bf16x16(p.hd, go, hdv);
+    float act[16], g0[16], g1[16], ag0[16], ag1[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const float zw = __uint_as_float(vw[k]);
-      const float a = r.valid ? fmaxf(zw + bv[k], 0.f) : 0.f;
+      const float y = fmaf(zw, sw[k], bv[k]);                        // conv + bias, or the folded BatchNorm
+      const float o = y + idv[k];                                    // residual Add (resnet.py:33-38)
+      const float a = r.valid ? ((p.fwd_flags & 1) ? o : fmaxf(o, 0.f)) : 0.f;
       act[k] = a;
+      // BatchNorm rule (lrp_modules.py:204-215): R = |x w| / (|x w| + |b|) R_out, safe_divide
+      float ratio = 1.f;
+      if (p.bn_w) {
+        const float xw = fabsf(zw * sw[k]), den = xw + fabsf(bv[k]);
+        ratio = xw / (den + (den == 0.f ? LRPX_Z_EPSILON : 0.f));
+      }
+      // Add rule (lrp_modules.py:262-275): x_i / (out + 0.01 sign out); out == 0 -> 0.5 each
+      float rho1 = 1.f, rho2 = 0.f;
+      if (p.idn) {
+        if (o == 0.f) { rho1 = 0.5f; rho2 = 0.5f; }
+        else { const float so = o + (o > 0.f ? 0.01f : -0.01f); rho1 = y / so; rho2 = idv[k] / so; }
+      }
       const float num = p.gain_mode ? 1.f : a;
       float q0 = 0.f, q1 = 0.f;
       if (p.rule == 0) {
         float zp = __uint_as_float(vp[k]) + (p.zbias ? bv[k] : 0.f);
         zp += (zp == 0.f ? LRPX_Z_EPSILON : 0.f);                   // safe_divide, utils.py:16-18
-        q0 = p.alpha * num / zp;
+        q0 = p.alpha * num * ratio * rho1 / zp;
         if (p.n_acc >= 3) {
           float zn = __uint_as_float(vn[k]) + (p.zbias ? bv[k] : 0.f);
           zn += (zn == 0.f ? LRPX_Z_EPSILON : 0.f);
           q1 = -p.beta * num / zn;
+        } else if (p.idn) {
+          q1 = rho2 * hdv[k];                                        // identity-branch gain
         }
       } else {
         const float zr = zw + (p.zbias ? bv[k] : 0.f);
@@ -723,27 +818,14 @@ __device__ __forceinline__ void epi_fwdx(const TcParams& p, const RowInfo& r, ui
       }
       g0[k] = r.valid ? q0 : 0.f;
       g1[k] = r.valid ? q1 : 0.f;
+      ag0[k] = a * g0[k];
+      ag1[k] = a * g1[k];
     }
-    // activations: bf16 row, or hi | lo halves of a 2*cout row
-    {
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) split_pack(act[2 * k], act[2 * k + 1], hi[k], lo[k]);
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * (size_t)(cout * (sp ? 2 : 1)) + ch;
-      stg_v8(dst, hi);
-      if (sp) stg_v8(dst + cout, lo);
-    }
-    const size_t go = (size_t)r.row * cout + ch;
-    if (sp) {
-      stg_f32x16(reinterpret_cast<float*>(p.out2) + go, g0);
-      if (p.out3) stg_f32x16(reinterpret_cast<float*>(p.out3) + go, g1);
-    } else {
-      uint32_t w0[8], w1[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { w0[k] = pack_bf16(g0[2 * k], g0[2 * k + 1]); w1[k] = pack_bf16(g1[2 * k], g1[2 * k + 1]); }
-      stg_v8(reinterpret_cast<__nv_bfloat16*>(p.out2) + go, w0);
-      if (p.out3) stg_v8(reinterpret_cast<__nv_bfloat16*>(p.out3) + go, w1);
-    }
+    store_act16(p.out, orow * (size_t)(cout * (sp ? 2 : 1)) + ch, cout, sp, act);
+    store_gain16(p.out2, go, sp, g0);
+    if (p.out3) store_gain16(p.out3, go, sp, g1);
+    if (p.out4) store_gain16(p.out4, go, sp, ag0);
+    if (p.out5) store_gain16(p.out5, go, sp, ag1);
   }
 }
 
@@ -1600,11 +1682,16 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
   p.groups = a->groups > 0 ? a->groups : 1;
   p.split = a->split; p.n_acc = a->n_acc; p.rule = a->rule; p.zbias = a->zbias;
   p.alpha = a->alpha; p.beta = a->beta; p.gain2 = a->gain2; p.out3 = a->out3;
+  p.add = a->add; p.add_pitch = a->add_pitch; p.gain3 = a->gain3; p.gain4 = a->gain4;
+  p.bn_w = a->bn_w; p.bn_b = a->bn_b; p.idn = a->idn; p.hd = a->hd; p.out4 = a->out4; p.out5 = a->out5;
+  p.fwd_flags = a->fwd_flags;
 
   if (epi == LRPX_TC_EPI_FWDX) {
     LRPX_CHECK_ARG(a->out2 && a->n_acc >= 1 && a->n_acc <= 3 && a->ncol % a->n_acc == 0, "FWDX: out2 and n_acc in 1..3");
     LRPX_CHECK_ARG((a->rule == 0 && a->n_acc >= 2) || (a->rule == 1 && a->n_acc == 1), "FWDX: alpha-beta needs W and W+ (n_acc >= 2), epsilon n_acc == 1");
-    LRPX_CHECK_ARG(a->out3 == nullptr || a->n_acc == 3, "FWDX: out3 (gain of the neg-net) needs n_acc == 3");
+    LRPX_CHECK_ARG(a->out3 == nullptr || a->n_acc == 3 || a->idn, "FWDX: out3 needs n_acc == 3 (neg-net gain) or idn (identity-branch gain)");
+    LRPX_CHECK_ARG((a->bn_w == nullptr) == (a->bn_b == nullptr), "FWDX: bn_w and bn_b go together");
+    LRPX_CHECK_ARG(!(a->fwd_flags & 2) || (a->h % 2 == 0 && a->w % 2 == 0 && !a->idn && !a->hd), "FWDX: strided store needs even h, w and no idn / hd");
     const int cout = a->ncol / a->n_acc;
     LRPX_CHECK_ARG(cout % 32 == 0, "FWDX: output channels must be a multiple of 32");
     const int cap = a->n_acc == 3 ? 64 : (a->n_acc == 2 ? 128 : 256);      // n_acc * half <= 256 TMEM columns per buffer
@@ -1615,11 +1702,13 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     p.out_c = cout;
   } else if (epi == LRPX_TC_EPI_MULX || epi == LRPX_TC_EPI_MULX_UNPOOL) {
     LRPX_CHECK_ARG(a->gain && (p.groups == 1 || (p.groups == 2 && a->gain2)), "MULX: gain (and gain2 for two groups) required");
-    LRPX_CHECK_ARG(epi != LRPX_TC_EPI_MULX_UNPOOL || a->pool_idx, "pool_idx required");
     LRPX_CHECK_ARG(a->ncol % 32 == 0, "ncol must be a multiple of 32 for this epilogue");
+    LRPX_CHECK_ARG(!a->add || (epi == LRPX_TC_EPI_MULX && a->add_pitch >= a->ncol),
+                   "MULX add: add_pitch >= ncol required; not with UNPOOL");
+    LRPX_CHECK_ARG(!(a->out2 && p.groups == 2) || !p.split, "MULX: separate group tensors (out2) are bf16 only");
     p.bn = a->ncol <= 256 ? a->ncol : 256;
     LRPX_CHECK_ARG(a->ncol % p.bn == 0, "ncol must be <= 256 or a multiple of 256");
-    p.out_c = a->ncol * p.groups * (p.split ? 2 : 1);
+    p.out_c = (a->out2 && p.groups == 2) ? a->ncol : a->ncol * p.groups * (p.split ? 2 : 1);
   } else if (epi == LRPX_TC_EPI_FWD_GAIN) {
     // Wt holds, per tile of `half` output channels, the W rows followed by the W+ rows: ncol = 2 * cout
     LRPX_CHECK_ARG(a->out2, "FWD_GAIN needs out2 (gain)");
@@ -1650,7 +1739,8 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     } else if (epi != LRPX_TC_EPI_STORE_F32) LRPX_CHECK_ARG(a->gain, "gain required");
     if (epi == LRPX_TC_EPI_MUL_UNPOOL) LRPX_CHECK_ARG(a->pool_idx, "pool_idx required");
     p.bn = a->ncol <= 256 ? a->ncol : 256;
-    LRPX_CHECK_ARG(a->ncol % p.bn == 0, "ncol must be <= 256 or a multiple of 256");
+    if (epi == LRPX_TC_EPI_STORE_F32 && a->ncol > 256 && a->ncol % 256 && a->ncol % 64 == 0) p.bn = 64;
+    LRPX_CHECK_ARG(a->ncol % p.bn == 0, "ncol must be <= 256 or a multiple of 256 (STORE_F32: or of 64)");
     // plain GEMMs with few rows (the decoder's per-step GEMMs: 1216 x 1536 x 1536): 256-column tiles give fewer tiles
     // than SMs; 128-column tiles fill the machine (LRPX_TC_GEMM_BN=256 keeps the wide tiles)
     if (a->ksize == 1 && epi == LRPX_TC_EPI_STORE_F32 && p.bn == 256) {

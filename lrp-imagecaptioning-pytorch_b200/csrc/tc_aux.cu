@@ -2,6 +2,7 @@
 // gain gather, chain entry scaling and PF <-> dense conversions.  All HBM-bound, 16-byte vector accesses.
 // PF layout: see include/lrpx.h ("padded-flat NHWC bf16").
 #include "lrpx_common.cuh"
+#include <cuda_fp16.h>
 
 namespace lrpx {
 
@@ -531,11 +532,260 @@ __global__ void pf_split_to_dense_kernel(const __nv_bfloat16* __restrict__ src, 
   }
 }
 
+
+// ---------------------------------------------------------------- ResNet stem and strides (models/resnet.py:143-239)
+// conv1 = 7x7 / stride 2 / pad 3 on the mixed-sign image: sign-split im2col at the OUTPUT resolution (ho, wo) = (h/2, w/2):
+// PF row of output pixel (y,x) <- 320 bf16: [x+ over the 147 (ci,ky,kx) taps | x- over the 147 taps | 26 zeros], so that the
+// layer is a 1x1 "convolution" with K = 320 for lrpx_tc_conv(FWDX) with rows [w | w | 0] (z) and [w+ | w- | 0] (z+).
+__global__ void im2col7s2_split_kernel(const float* __restrict__ x, uint4* __restrict__ dst, int n, int h, int w) {
+  const int ho = h / 2, wo = w / 2, wp1 = wo + 1, blk = (ho + 1) * wp1;
+  const long long total = (long long)n * blk * 40;          // 40 groups of 8 columns per row
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % 40);
+    const long long prow = i / 40;
+    const int img = (int)(prow / blk), rem = (int)(prow % blk);
+    const int a = rem / wp1, b = rem % wp1;
+    uint32_t o[4] = {0u, 0u, 0u, 0u};
+    if (a > 0 && b > 0) {
+      const float* xi = x + (size_t)img * 3 * h * w;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = cg * 8 + k;
+        float f = 0.f;
+        if (e < 294) {
+          const int t = e < 147 ? e : e - 147;
+          const int ci = t / 49, ky = (t % 49) / 7, kx = t % 7;
+          const int yy = 2 * (a - 1) - 3 + ky, xs = 2 * (b - 1) - 3 + kx;
+          const float xv = (yy >= 0 && yy < h && xs >= 0 && xs < w) ? __ldg(xi + ((size_t)ci * h + yy) * w + xs) : 0.f;
+          f = e < 147 ? fmaxf(xv, 0.f) : fminf(xv, 0.f);
+        }
+        v[k] = f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        o[k] = *reinterpret_cast<uint32_t*>(&t2);
+      }
+    }
+    dst[prow * 40 + cg] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// 3x3 / stride 2 / pad 1 max-pool on PF bf16 (post-ReLU input), 8 channels per thread.  Window of output (y,x): input rows
+// 2y-1..2y+1, columns 2x-1..2x+1, padding skipped (PyTorch pads with -inf); scan order (ky,kx) row-major, strict '>' so
+// the first maximum wins (max_pool2d_with_indices).  idx = ky*3+kx of the winner, 255 when the maximum is 0: such a
+// window passes no relevance (Z = 0: R_in = X * S = 0, lrp_modules.py:186-191).
+__global__ void maxpool3s2_pf_kernel(const uint4* __restrict__ act, uint4* __restrict__ pooled, uint2* __restrict__ idx,
+                                     int n, int h, int w, int c8) {
+  const int oh = h / 2, ow = w / 2, wp1 = w + 1, owp1 = ow + 1;
+  const long long blk_f = (long long)(h + 1) * wp1, blk_p = (long long)(oh + 1) * owp1;
+  const long long total = (long long)n * blk_p * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long prow = i / c8;
+    const int cc = (int)(i - prow * c8);
+    const long long img = prow / blk_p;
+    const int rem = (int)(prow - img * blk_p);
+    const int a = rem / owp1, b = rem - a * owp1;
+    uint32_t ov[4] = {0u, 0u, 0u, 0u};
+    uint32_t bi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bi[e] = 255u;
+    if (a > 0 && b > 0) {
+      float best[8];
+      uint32_t bb[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { best[e] = 0.f; bb[e] = 0u; }       // inputs are >= 0: a maximum of 0 keeps idx = 255
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int fa = 2 * (a - 1) + ky;          // PF row of input row 2y-1+ky
+        if (fa < 1) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int fb = 2 * (b - 1) + kx;
+          if (fb < 1) continue;
+          const uint4 v = act[(img * blk_f + (long long)fa * wp1 + fb) * c8 + cc];
+          const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t bits = (vw[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+            const float f = __uint_as_float(bits << 16);
+            if (f > best[e]) { best[e] = f; bb[e] = bits; bi[e] = (uint32_t)(ky * 3 + kx); }
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ov[e >> 1] |= bb[e] << (16 * (e & 1));
+    }
+    pooled[i] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+    idx[i] = make_uint2(bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24), bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24));
+  }
+}
+
+// Relevance through that pool (gather form, deterministic for the overlapping windows) fused with the gain of the layer
+// below:  out[e][i][j][c] = gain[img][i][j][c] * sum over the (up to 4) windows (y,x) that contain (i,j) and whose winner
+// is (i,j) of r[e][y][x][c].   r: per-request PF (oh, ow); gain / idx: per image; out: per-request PF (h, w).
+__global__ void unpool3s2_pf_kernel(const uint4* __restrict__ r, const uint2* __restrict__ idx, const uint4* __restrict__ gain,
+                                    const int32_t* __restrict__ row_img, uint4* __restrict__ out, int nq, int h, int w, int c8) {
+  const int oh = h / 2, ow = w / 2, wp1 = w + 1, owp1 = ow + 1;
+  const long long blk_f = (long long)(h + 1) * wp1, blk_p = (long long)(oh + 1) * owp1;
+  const long long total = (long long)nq * blk_f * c8;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long prow = t / c8;
+    const int cc = (int)(t - prow * c8);
+    const long long e = prow / blk_f;
+    const int rem = (int)(prow - e * blk_f);
+    const int a = rem / wp1, b = rem - a * wp1;
+    uint32_t ow4[4] = {0u, 0u, 0u, 0u};
+    if (a > 0 && b > 0) {
+      const int img = row_img ? row_img[e] : (int)e;
+      const int i = a - 1, j = b - 1;
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      // windows: y with 2y-1 <= i <= 2y+1  <=>  y in {i/2, (i+1)/2} (deduplicated), same for x
+      const int y0 = i >> 1, y1 = (i + 1) >> 1, x0 = j >> 1, x1 = (j + 1) >> 1;
+      for (int yy = y0; yy <= y1; ++yy) {
+        if (yy >= oh) continue;
+        const int ky = i - (2 * yy - 1);
+        for (int xx = x0; xx <= x1; ++xx) {
+          if (xx >= ow) continue;
+          const int kx = j - (2 * xx - 1);
+          const uint32_t want = (uint32_t)(ky * 3 + kx);
+          const long long pr = (long long)(yy + 1) * owp1 + (xx + 1);
+          const uint2 id = idx[((long long)img * blk_p + pr) * c8 + cc];
+          const uint4 rv = r[(e * blk_p + pr) * c8 + cc];
+          const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t byte = ((k < 4 ? id.x : id.y) >> (8 * (k & 3))) & 0xFFu;
+            if (byte == want) acc[k] += __uint_as_float(((rw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu) << 16);
+          }
+        }
+      }
+      const uint4 g = gain[((long long)img * blk_f + rem) * c8 + cc];
+      const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float lo = acc[2 * k] * __uint_as_float(gw[k] << 16), hi = acc[2 * k + 1] * __uint_as_float(gw[k] & 0xFFFF0000u);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(lo, hi);
+        ow4[k] = *reinterpret_cast<uint32_t*>(&t2);
+      }
+    }
+    out[t] = make_uint4(ow4[0], ow4[1], ow4[2], ow4[3]);
+  }
+}
+
+// dst (n, h/2, w/2) PF <- src (n, h, w) PF at the even pixels (the input of a 1x1 / stride 2 convolution)
+__global__ void subsample2_pf_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n, int h, int w, int c8) {
+  const int oh = h / 2, ow = w / 2, wp1 = w + 1, owp1 = ow + 1;
+  const long long blk_f = (long long)(h + 1) * wp1, blk_p = (long long)(oh + 1) * owp1;
+  const long long total = (long long)n * blk_p * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long prow = i / c8;
+    const int cc = (int)(i - prow * c8);
+    const long long img = prow / blk_p;
+    const int rem = (int)(prow - img * blk_p);
+    const int a = rem / owp1, b = rem - a * owp1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (a > 0 && b > 0) v = src[(img * blk_f + (long long)(2 * (a - 1) + 1) * wp1 + (2 * (b - 1) + 1)) * c8 + cc];
+    dst[i] = v;
+  }
+}
+
+// Stem relevance, second half: the 1x1 GEMM produced P[q][tap*6 + s*3 + c] = sum_ch A[q][ch] * W(s)[ch][c][ky][kx]
+// (tap = ky*7+kx, s = 0: W+, 1: W-) for every output pixel q = (y,x) of conv1; the image relevance gathers
+//   heat[e][c][i][j] = x+ * sum P[(y,x)][tap][0][c] + x- * sum P[(y,x)][tap][1][c]   over 2y-3+ky = i, 2x-3+kx = j
+// (lrp_modules.py:81-84, utils.py:26-30 for the stride-2 convolution).  mode: 0 fp32 (n,3,h,w), 1 channel mean, 2 fp16.
+__global__ void stem_col2im_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ x,
+                                   const int32_t* __restrict__ row_img, void* __restrict__ out, int nq, int h, int w, int mode) {
+  const int ho = h / 2, wo = w / 2, wp1 = wo + 1, blk = (ho + 1) * wp1;
+  const long long total = (long long)nq * h * w;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % w), i = (int)((t / w) % h);
+    const long long e = t / ((long long)w * h);
+    const int img = row_img ? row_img[e] : (int)e;
+    float cp[3] = {0.f, 0.f, 0.f}, cn[3] = {0.f, 0.f, 0.f};
+    for (int ky = (i + 3) & 1; ky < 7; ky += 2) {
+      const int y = (i + 3 - ky) >> 1;
+      if (y < 0 || y >= ho) continue;
+      for (int kx = (j + 3) & 1; kx < 7; kx += 2) {
+        const int xx = (j + 3 - kx) >> 1;
+        if (xx < 0 || xx >= wo) continue;
+        const float* pr = P + ((size_t)e * blk + (size_t)(y + 1) * wp1 + (xx + 1)) * ldp + (ky * 7 + kx) * 6;
+        const float2 p0 = *reinterpret_cast<const float2*>(pr), p1 = *reinterpret_cast<const float2*>(pr + 2),
+                     p2 = *reinterpret_cast<const float2*>(pr + 4);
+        cp[0] += p0.x; cp[1] += p0.y; cp[2] += p1.x; cn[0] += p1.y; cn[1] += p2.x; cn[2] += p2.y;
+      }
+    }
+    const size_t hw = (size_t)h * w, pix = (size_t)i * w + j;
+    float res[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xv = __ldg(x + ((size_t)img * 3 + c) * hw + pix);
+      res[c] = fmaxf(xv, 0.f) * cp[c] + fminf(xv, 0.f) * cn[c];
+    }
+    if (mode == 1) {
+      reinterpret_cast<float*>(out)[(size_t)e * hw + pix] = ((res[0] + res[1]) + res[2]) / 3.f;
+    } else if (mode == 2) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) reinterpret_cast<__half*>(out)[((size_t)e * 3 + c) * hw + pix] = __float2half_rn(res[c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) reinterpret_cast<float*>(out)[((size_t)e * 3 + c) * hw + pix] = res[c];
+    }
+  }
+}
+
 }  // namespace lrpx
 
 using namespace lrpx;
 
 extern "C" {
+
+int lrpx_tc_im2col7s2_split_bf16(const float* x, void* dst, int n, int h, int w, void* stream) {
+  LRPX_CHECK_ARG(x && dst && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "bad argument (h, w even)");
+  long long total = (long long)n * (h / 2 + 1) * (w / 2 + 1) * 40;
+  im2col7s2_split_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, (uint4*)dst, n, h, w);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_tc_maxpool3s2_bf16(const void* act, void* pooled, uint8_t* idx, int n, int h, int w, int c, void* stream) {
+  LRPX_CHECK_ARG(act && pooled && idx && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "bad argument");
+  long long total = (long long)n * (h / 2 + 1) * (w / 2 + 1) * (c / 8);
+  maxpool3s2_pf_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)act, (uint4*)pooled, (uint2*)idx, n, h, w, c / 8);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_tc_unpool3s2_bf16(const void* r, const uint8_t* idx, const void* gain, const int32_t* row_img, void* out, int n_expl,
+                           int h, int w, int c, void* stream) {
+  LRPX_CHECK_ARG(r && idx && gain && out && n_expl > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "bad argument");
+  long long total = (long long)n_expl * (h + 1) * (w + 1) * (c / 8);
+  unpool3s2_pf_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)r, (const uint2*)idx, (const uint4*)gain,
+                                                                     row_img, (uint4*)out, n_expl, h, w, c / 8);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_tc_subsample2_bf16(const void* src, void* dst, int n, int h, int w, int c, void* stream) {
+  LRPX_CHECK_ARG(src && dst && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "bad argument");
+  long long total = (long long)n * (h / 2 + 1) * (w / 2 + 1) * (c / 8);
+  subsample2_pf_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)src, (uint4*)dst, n, h, w, c / 8);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_tc_stem_col2im_f32(const float* P, int ldp, const float* x, const int32_t* row_img, void* out, int n_expl, int h,
+                            int w, int mode, void* stream) {
+  LRPX_CHECK_ARG(P && x && out && n_expl > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && ldp >= 294 && ldp % 2 == 0 &&
+                     mode >= 0 && mode <= 2, "bad argument");
+  long long total = (long long)n_expl * h * w;
+  stem_col2im_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(P, ldp, x, row_img, out, n_expl, h, w, mode);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
 
 int lrpx_tc_im2col3_split_x(const float* x, void* dst, int n, int h, int w, int split, void* stream) {
   if (!split) return lrpx_tc_im2col3_split_bf16(x, dst, n, h, w, stream);

@@ -56,7 +56,9 @@ class TcConvArgs(C.Structure):
                [(n, _P) for n in ("a", "wt", "bias", "gain", "row_img", "pool_idx", "x", "out", "out2", "x1", "gain2",
                                   "out3")] + \
                [(n, C.c_int) for n in ("a_phys", "groups", "split", "n_acc", "rule", "zbias")] + \
-               [("alpha", C.c_float), ("beta", C.c_float)]
+               [("alpha", C.c_float), ("beta", C.c_float)] + \
+               [(n, _P) for n in ("add", "gain3", "gain4", "bn_w", "bn_b", "idn", "hd", "out4", "out5")] + \
+               [("add_pitch", C.c_int), ("fwd_flags", C.c_int)]
 
 
 _LL = C.c_longlong
@@ -158,6 +160,11 @@ SYMBOLS = {
     "lrpx_tc_maxpool2_x": (_i, [_P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _P]),
     "lrpx_tc_scale_rows_x": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _P]),
     "lrpx_tc_pf_split_to_dense_f32": (_i, [_P, _P, _i, _i, _i, _i, _i, _P]),
+    "lrpx_tc_im2col7s2_split_bf16": (_i, [_P, _P, _i, _i, _i, _P]),
+    "lrpx_tc_maxpool3s2_bf16": (_i, [_P, _P, _P, _i, _i, _i, _i, _P]),
+    "lrpx_tc_unpool3s2_bf16": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
+    "lrpx_tc_subsample2_bf16": (_i, [_P, _P, _i, _i, _i, _i, _P]),
+    "lrpx_tc_stem_col2im_f32": (_i, [_P, _i, _P, _P, _P, _i, _i, _i, _i, _P]),
 }
 
 _lib = None

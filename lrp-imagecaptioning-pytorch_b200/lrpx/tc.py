@@ -46,13 +46,15 @@ def pf_rows(n, h, w):
 
 def tc_conv(a, wt, n_img, h, w, cin, ncol, ksize, epilogue, out, out2=None, bias=None, gain=None, row_img=None,
             pool_idx=None, x=None, gain_mode=0, gain2=None, out3=None, a_phys=0, groups=1, split=0, n_acc=0, rule=0,
-            zbias=0, alpha=1.0, beta=0.0):
+            zbias=0, alpha=1.0, beta=0.0, add=None, add_pitch=0, gain3=None, gain4=None, bn_w=None, bn_b=None, idn=None,
+            hd=None, out4=None, out5=None, fwd_flags=0):
     """Thin wrapper of lrpx_tc_conv (all tensors preallocated by the caller)."""
     args = TcConvArgs(n_img=n_img, h=h, w=w, cin=cin, ncol=ncol, ksize=ksize, epilogue=epilogue, gain_mode=gain_mode,
                       a_phys=a_phys, groups=groups, split=split, n_acc=n_acc, rule=rule, zbias=zbias, alpha=alpha,
-                      beta=beta)
-    args.gain2 = gain2.data_ptr() if gain2 is not None else None
-    args.out3 = out3.data_ptr() if out3 is not None else None
+                      beta=beta, add_pitch=add_pitch, fwd_flags=fwd_flags)
+    for name, t in (("gain2", gain2), ("out3", out3), ("add", add), ("gain3", gain3), ("gain4", gain4), ("bn_w", bn_w),
+                    ("bn_b", bn_b), ("idn", idn), ("hd", hd), ("out4", out4), ("out5", out5)):
+        setattr(args, name, t.data_ptr() if t is not None else None)
     args.a, args.wt = a.data_ptr(), wt.data_ptr()
     args.bias = bias.data_ptr() if bias is not None else None
     args.gain = gain.data_ptr() if gain is not None else None

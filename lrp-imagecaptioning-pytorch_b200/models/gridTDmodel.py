@@ -493,6 +493,10 @@ class ExplainGridTDAttention(object):
         tcp = lrp_wrapper._tc_cfg(self.model.img_encoder.encoder) if is_vgg else None
         # the general kernels (fp32-accurate mode) need a first conv with a multiple of 64 output channels
         tc_ok = tcp is not None and (self.precision == 'bf16' or tcp[0][0].out_channels % 64 == 0)
+        # Bottleneck ResNets run the bf16 chain of lrpx.tc_resnet (their fp32 bar is the CUDA-core rule path)
+        self.is_resnet = self.has_encoder and lrp_wrapper._is_bottleneck_resnet(self.model.img_encoder.encoder)
+        if self.is_resnet and self.precision == 'bf16':
+            tc_ok = True
         if self.precision == 'bf16' and not tc_ok and self.has_encoder:
             raise NotImplementedError("the tensor-core chain supports VGG-style encoders; use precision='fp32'")
         # the encoder runs on the tcgen05 engine (one forward per image shared by all its words)
@@ -531,6 +535,9 @@ class ExplainGridTDAttention(object):
         return self._weights
 
     def engine(self):
+        if self._engine is None and getattr(self, "is_resnet", False):
+            from lrpx import tc_resnet
+            self._engine = tc_resnet.TcResNetEngine(self.model.img_encoder.encoder, self.device)
         if self._engine is None:
             from lrpx import tc
             enc = self.model.img_encoder.encoder

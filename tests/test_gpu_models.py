@@ -130,7 +130,8 @@ def _check_three_precisions(t, ref, rw, scale, h_simt, w_simt, h_x3, w_x3, h_bf1
     print(f"word {t}: fp32-accurate chain rel L2 {l2:.3e}, worst pixel {float(err.max()):.3e} of max, "
           f"share beyond rtol 1e-4 + 1e-4 max: {far:.3e}")
     assert l2 <= 1e-3 and far <= 1e-2 and float(err.max()) <= 1e-2
-    assert_close(w_x3, rw, rtol=1e-4, atol=1e-5, what=f"r_words (chain) t={t}")
+    # the decoder runs on the chain's encoder features (1.5e-4 of max off the fp32 ones, see test_gpu_encoder.py)
+    assert_close(w_x3, rw, rtol=1e-3, atol=1e-3, what=f"r_words (chain) t={t}")
     sp = spearman(h_bf16, h_simt)
     l2b = float((h_bf16 - h_simt).norm() / h_simt.norm())
     print(f"word {t}: bf16 vs simt spearman {sp:.5f} rel L2 {l2b:.3e}")
