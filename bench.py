@@ -53,7 +53,8 @@ def parse(argv=None):
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5],
                     help="BASELINE.json configuration; 0 (default) = config 2 plus short 'also' runs of the others at N = 1")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp32"],
+                    help="default: bf16 (config 5: fp32 — the fixed encoder's features at fp32 accuracy)")
     ap.add_argument("--deliver", default="full", choices=["full", "channel_mean", "fp16"])
     ap.add_argument("--images", type=int, default=0, help="images (config 2/4: requests) per GPU per step; 0 = the config's size")
     ap.add_argument("--words", type=int, default=19, help="caption words per image (random-init captions run to max length)")
@@ -62,6 +63,8 @@ def parse(argv=None):
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--library-encoder", action="store_true",
+                    help="config 5: run the fixed VGG16 forward through the library convolutions instead of the tcgen05 engine")
     ap.add_argument("--profile-step", action="store_true",
                     help="run 1 warm-up + 1 step and exit (the command line captured under ncu for profiles/)")
     ap.add_argument("--cpu-words", type=int, default=19, help="words per image of the bounded CPU sample")
@@ -72,6 +75,8 @@ def parse(argv=None):
         a.config = 2
     if a.images == 0:
         a.images = {2: 64, 3: 64, 4: 512, 5: 128}[a.config]
+    if a.precision is None:
+        a.precision = "fp32" if a.config == 5 else "bf16"
     return a
 
 
@@ -849,7 +854,8 @@ def run_config5(args, ctx, brief=False):
     torch.backends.cudnn.allow_tf32 = False
     B = args.images
     model, wm, imgs, caps, caplens, T = build_config5(args, dev, rank, B)
-    st = LrpTuneStep(model, wm, lr=1e-4, grad_clip=5.0)
+    tc_enc = {"bf16": "bf16", "fp32": "fp32"}[args.precision] if not getattr(args, "library_encoder", False) else None
+    st = LrpTuneStep(model, wm, lr=1e-4, grad_clip=5.0, tc_encoder=tc_enc)
     imgs_h, caps_h = imgs.pin_memory(), caps.pin_memory()
     imgs_d, caps_d = imgs_h.to(dev), caps_h.to(dev)
     loss_h = torch.empty(3).pin_memory()
@@ -898,11 +904,15 @@ def run_config5(args, ctx, brief=False):
         total = world * B * steps
         out = {"metric": "lrp_tune_samples_per_s", "value": total / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
                "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32 training graph; fixed VGG16 forward " + ({"fp32": "bf16x3 (fp32-accurate) on tcgen05", "bf16": "bf16 on tcgen05",
+                                                                        None: "f32 library convolutions"}[tc_enc]),
+               "data": "synthetic",
                "config": {"workload": f"config 5: lrp_tune step (train.py:211-233) on gridTD/VGG16 (fixed CNN), batch {B} per "
                                       f"GPU, {T} words, V={args.vocab}; forward with get_lrp_weight_step per word "
                                       "(lrpx_fc_lrp_weights_f32), 2 x CE, backward, clamp, Adam",
-                          "baseline_config": 5, "parallelism": f"data-parallel x{world} (DistributedDataParallel, NCCL)",
+                          "baseline_config": 5, "fixed_encoder_forward": tc_enc or "library",
+                          "parallelism": f"data-parallel x{world} (DistributedDataParallel, NCCL)",
                           "trainable_params": nparam, "allreduce_bytes_per_step": 4 * nparam,
                           "l2": "a batch of images (77 MB) + activations far exceed the 126 MB L2"},
                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e / steps,
@@ -1063,7 +1073,8 @@ def run_ours(args):
         for name, cfg, extra in (("config2_fp32_accurate", 2, dict(precision="fp32", steps=4)),
                                  ("config3", 3, dict(steps=8)), ("config4", 4, dict(steps=4)),
                                  ("config4_fp32_accurate", 4, dict(precision="fp32", steps=2, images=128)),
-                                 ("config5", 5, dict(steps=4))):
+                                 ("config5", 5, dict(steps=4, precision="fp32")),
+                                 ("config5_library_encoder", 5, dict(steps=4, precision="fp32", library_encoder=True))):
             a2 = argparse.Namespace(**vars(args))
             a2.config, a2.also, a2.warmup = cfg, False, 3
             a2.images = {2: 64, 3: 64, 4: 512, 5: 128}[cfg]

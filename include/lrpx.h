@@ -537,6 +537,9 @@ typedef struct {
   int add_pitch;
   int fwd_flags;        /* FWDX: bit 0 = no ReLU (downsample branch), bit 1 = keep the even pixels only and store
                          * them into a PF tensor of half the resolution (stride-2 convolution)            */
+  int out_pitch;        /* STORE_F32: floats per row of `out` (0 = ncol) and                                */
+  int n_valid;          /*            the columns that exist (<= ncol; the weight rows beyond are padding);
+                         *            `bias` (n_valid floats) is added when given                           */
 } lrpx_tc_conv_args;
 
 int lrpx_tc_conv(const lrpx_tc_conv_args* args, void* stream);
@@ -545,6 +548,16 @@ int lrpx_tc_conv(const lrpx_tc_conv_args* args, void* stream);
  *   a (m,k) bf16 row-major, wt (n,k) bf16 row-major, out (m,n) fp32.  k % 64 == 0, n % 32 == 0, n <= 256 or n % 256 == 0.
  * Used by the decoder kernels for their error-compensated bf16x3 GEMMs (LRPX_DEC_TC_GEMM). */
 int lrpx_tc_gemm_bf16_f32(const void* a, const void* wt, float* out, int m, int n, int k, void* stream);
+
+/* Linear layer / GEMM at fp32 accuracy on the tensor cores (error-compensated bf16x3, see a_phys above):
+ *   out[m][n] = sum_k a[m][k] * W[n][k] + bias[n]         a fp32 (m, k) with row pitch lda, out fp32 with row pitch ldo
+ * w3 = the prepared weight: bf16 (n_pad, 3k) rows [hi | hi | lo] of W, n_pad >= n a multiple of 32 (<= 256) or of 256, rows
+ * beyond n zero.  k % 64 == 0, n % 4 == 0, ldo % 4 == 0.  workspace: lrpx_gemm_x3_workspace_bytes(m, k) bytes (the hi | lo
+ * split of a).  Replaces the library GEMMs of the explainer forward (gridTDmodel.py:941-1012: projector, attention
+ * projections, gate pre-activations, vocabulary projection). */
+size_t lrpx_gemm_x3_workspace_bytes(int m, int k);
+int lrpx_gemm_x3_f32(const float* a, int lda, const void* w3, int n_pad, const float* bias, float* out, int ldo, int m, int n,
+                     int k, void* workspace, size_t workspace_bytes, void* stream);
 
 /* First VGG layer forward on CUDA cores (cin = 3 is no tensor-core shape): from fp32 NCHW images
  *   act  = relu(conv(x, W) + b)                       -> PF bf16 (n, blk, cout)

@@ -99,6 +99,7 @@ struct TcParams {
   void* out4;        // FWDX: act * gain0
   void* out5;        // FWDX: act * (identity-branch gain)
   int fwd_flags;     // FWDX: bit 0 = no ReLU, bit 1 = store only the even pixels into a half-resolution PF tensor
+  int n_valid;       // STORE_F32: columns that exist in `out` (<= ncol)
   const float* bias;
   const __nv_bfloat16* gain;
   const int32_t* row_img;
@@ -877,11 +878,18 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
     tmem_ld_wait();
     epi_release(release_bar);
     if (r.in_range) {
-      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c);
+      // out_c = row pitch, n_valid = columns that exist (a multiple of 4; the tile may be padded beyond it); the bias
+      // (one value per column) turns the plain GEMM into a Linear layer
+      const int col0 = n0 + c;
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + col0);
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                             __uint_as_float(v[4 * q + 3]));
+      for (int q = 0; q < 8; ++q) {
+        if (col0 + 4 * q >= p.n_valid) break;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
+        dst[q] = make_float4(__uint_as_float(v[4 * q]) + b4.x, __uint_as_float(v[4 * q + 1]) + b4.y,
+                             __uint_as_float(v[4 * q + 2]) + b4.z, __uint_as_float(v[4 * q + 3]) + b4.w);
+      }
     }
   } else if (EPI == LRPX_TC_EPI_FEAT || EPI == LRPX_TC_EPI_FEAT_DIV) {
     // rows = (request q = r.e, pixel p = r.rem); x / x1 are indexed by the request's image
@@ -1749,6 +1757,13 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       if (!(env_bn && atoi(env_bn) == 256) && m_tiles * (a->ncol / 256) < sm_count()) p.bn = 128;
     }
     p.out_c = a->ncol;
+    p.n_valid = a->ncol;
+    if (epi == LRPX_TC_EPI_STORE_F32 && a->out_pitch > 0) {
+      LRPX_CHECK_ARG(a->n_valid > 0 && a->n_valid <= a->ncol && a->n_valid % 4 == 0 && a->out_pitch >= a->n_valid &&
+                         a->out_pitch % 4 == 0, "STORE_F32: n_valid / out_pitch must be multiples of 4, n_valid <= ncol");
+      p.out_c = a->out_pitch;
+      p.n_valid = a->n_valid;
+    }
   }
   p.num_n_tiles = a->ncol / p.bn;
   cudaStream_t st = as_stream(stream);

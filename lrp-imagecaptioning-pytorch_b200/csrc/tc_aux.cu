@@ -533,6 +533,23 @@ __global__ void pf_split_to_dense_kernel(const __nv_bfloat16* __restrict__ src, 
 }
 
 
+// fp32 rows (pitch lda) -> bf16 rows of 2K [hi | lo]: the A operand of an error-compensated GEMM (a_phys = 2K, cin = 3K)
+__global__ void split2_rows_kernel(const float* __restrict__ x, int lda, uint4* __restrict__ out, long long rows, int k8) {
+  const long long total = rows * k8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / k8;
+    const int cg = (int)(i - r * k8);
+    const float4* src = reinterpret_cast<const float4*>(x + r * lda + cg * 8);
+    const float4 a = src[0], b = src[1];
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
+    out[r * 2 * k8 + cg] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    out[r * 2 * k8 + k8 + cg] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 // ---------------------------------------------------------------- ResNet stem and strides (models/resnet.py:143-239)
 // conv1 = 7x7 / stride 2 / pad 3 on the mixed-sign image: sign-split im2col at the OUTPUT resolution (ho, wo) = (h/2, w/2):
 // PF row of output pixel (y,x) <- 320 bf16: [x+ over the 147 (ci,ky,kx) taps | x- over the 147 taps | 26 zeros], so that the
@@ -742,6 +759,27 @@ __global__ void stem_col2im_kernel(const float* __restrict__ P, int ldp, const f
 using namespace lrpx;
 
 extern "C" {
+
+size_t lrpx_gemm_x3_workspace_bytes(int m, int k) {
+  if (m <= 0 || k <= 0) return 0;
+  return (size_t)m * 2 * k * sizeof(__nv_bfloat16);
+}
+
+int lrpx_gemm_x3_f32(const float* a, int lda, const void* w3, int n_pad, const float* bias, float* out, int ldo, int m, int n,
+                     int k, void* workspace, size_t workspace_bytes, void* stream) {
+  LRPX_CHECK_ARG(a && w3 && out && m > 0 && n > 0 && k > 0, "bad argument");
+  LRPX_CHECK_ARG(k % 64 == 0 && lda >= k && lda % 4 == 0 && n % 4 == 0 && ldo >= n && ldo % 4 == 0, "k % 64, n % 4, pitches % 4");
+  LRPX_CHECK_ARG(n_pad >= n && n_pad % 32 == 0 && (n_pad <= 256 || n_pad % 256 == 0), "n_pad: multiple of 32 (<= 256) or of 256");
+  LRPX_CHECK_ARG(workspace && workspace_bytes >= lrpx_gemm_x3_workspace_bytes(m, k), "workspace too small");
+  LRPX_CHECK_ARG((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "a / out must be 16-byte aligned");
+  split2_rows_kernel<<<grid_for((long long)m * (k / 8)), 256, 0, as_stream(stream)>>>(a, lda, (uint4*)workspace, m, k / 8);
+  LRPX_CHECK_LAUNCH();
+  lrpx_tc_conv_args g{};
+  g.n_img = 1; g.h = 0; g.w = m - 1; g.cin = 3 * k; g.a_phys = 2 * k; g.ncol = n_pad; g.ksize = 1;
+  g.epilogue = LRPX_TC_EPI_STORE_F32;
+  g.a = workspace; g.wt = w3; g.out = out; g.bias = bias; g.out_pitch = ldo; g.n_valid = n;
+  return lrpx_tc_conv(&g, stream);
+}
 
 int lrpx_tc_im2col7s2_split_bf16(const float* x, void* dst, int n, int h, int w, void* stream) {
   LRPX_CHECK_ARG(x && dst && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "bad argument (h, w even)");

@@ -58,7 +58,7 @@ class TcConvArgs(C.Structure):
                [(n, C.c_int) for n in ("a_phys", "groups", "split", "n_acc", "rule", "zbias")] + \
                [("alpha", C.c_float), ("beta", C.c_float)] + \
                [(n, _P) for n in ("add", "gain3", "gain4", "bn_w", "bn_b", "idn", "hd", "out4", "out5")] + \
-               [("add_pitch", C.c_int), ("fwd_flags", C.c_int)]
+               [("add_pitch", C.c_int), ("fwd_flags", C.c_int), ("out_pitch", C.c_int), ("n_valid", C.c_int)]
 
 
 _LL = C.c_longlong
@@ -149,6 +149,8 @@ SYMBOLS = {
     "lrpx_lstm_step_f32": (_i, [C.POINTER(LstmStepArgs), _P]),
     "lrpx_tc_conv": (_i, [C.POINTER(TcConvArgs), _P]),
     "lrpx_tc_gemm_bf16_f32": (_i, [_P, _P, _P, _i, _i, _i, _P]),
+    "lrpx_gemm_x3_workspace_bytes": (_sz, [_i, _i]),
+    "lrpx_gemm_x3_f32": (_i, [_P, _i, _P, _i, _P, _P, _i, _i, _i, _i, _P, _sz, _P]),
     "lrpx_weight_prep_bf16": (_i, [_P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),
     "lrpx_tc_first_fwd": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "lrpx_tc_im2col3_split_bf16": (_i, [_P, _P, _i, _i, _i, _P]),

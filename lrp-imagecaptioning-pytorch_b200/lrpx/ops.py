@@ -235,6 +235,57 @@ def _fill_args(struct, fields: dict, keep: list):
 DEC_TC_GEMM = 1
 
 
+class LinearX3:
+    """A Linear layer / GEMM at fp32 accuracy on the tensor cores (``lrpx_gemm_x3_f32``: error-compensated bf16x3
+    operands, fp32 accumulation): y = x @ W^T + b for W (n, k) as nn.Linear stores it.  The weight is split once
+    ([hi | hi | lo] rows, zero-padded to the tile width) and re-split when the source tensor changes.  Shapes the
+    kernel does not take (k % 64, n % 4) are refused at construction — callers keep such layers on ``torch.addmm``."""
+
+    def __init__(self, weight, bias=None):
+        self.src = (weight, bias)
+        self.key = None
+        n, k = weight.shape
+        if k % 64 or n % 4:
+            raise _lib.LrpxError("LinearX3: in_features must be a multiple of 64 and out_features a multiple of 4")
+        self.n, self.k = int(n), int(k)
+        self.n_pad = (self.n + 31) // 32 * 32 if self.n <= 256 else (self.n + 255) // 256 * 256
+
+    @staticmethod
+    def supports(weight):
+        return weight.shape[1] % 64 == 0 and weight.shape[0] % 4 == 0
+
+    def _prep(self):
+        w, b = self.src
+        key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version))
+        if key != self.key:
+            with torch.no_grad():
+                wf = w.detach().float()
+                if self.n_pad != self.n:
+                    wf = torch.cat((wf, wf.new_zeros(self.n_pad - self.n, self.k)), 0)
+                hi = wf.to(torch.bfloat16)
+                lo = (wf - hi.float()).to(torch.bfloat16)
+                self.w3 = torch.cat((hi, hi, lo), 1).contiguous()
+                self.b = None if b is None else b.detach().float().contiguous()
+            self.key = key
+        return self.w3, self.b
+
+    def __call__(self, x, out=None):
+        """x (m, k) fp32 CUDA (rows may be strided: pitch = x.stride(0)) -> (m, n) fp32"""
+        if not x.is_cuda:
+            raise _lib.LrpxError("LinearX3 needs CUDA tensors: lrpx has no CPU fallback")
+        w3, b = self._prep()
+        if x.dtype != torch.float32 or x.stride(-1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16:
+            x = x.float().contiguous()
+        m = x.shape[0]
+        if out is None:
+            out = torch.empty(m, self.n, device=x.device, dtype=torch.float32)
+        nbytes = lib().lrpx_gemm_x3_workspace_bytes(m, self.k)
+        ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+        check(lib().lrpx_gemm_x3_f32(_ptr(x), x.stride(0), _ptr(w3), self.n_pad, _ptr(b), _ptr(out), out.stride(0), m, self.n,
+                                     self.k, _ptr(ws), nbytes, _stream()), "lrpx_gemm_x3_f32")
+        return out
+
+
 def lrp_linear_eps(r_out, forward_input, forward_output, weight):
     """The explainers' vector epsilon rule (gridTDmodel.py:744-765) on the device: r_out (n_out,) or (1,n_out),
     forward_input (n_in,), forward_output (n_out,) or False (recomputed as W x), weight (n_out,n_in) -> (n_in,)."""

@@ -41,7 +41,10 @@ class LrpTuneStep:
     (GridTDModel / AOAModel and their BU twins).  With an initialised process group the gradients are averaged
     over the ranks by DistributedDataParallel."""
 
-    def __init__(self, model, word_map, optimizer=None, lr=1e-4, grad_clip=None, fix_encoder=True):
+    def __init__(self, model, word_map, optimizer=None, lr=1e-4, grad_clip=None, fix_encoder=True, tc_encoder="fp32"):
+        """``tc_encoder``: with a fixed CNN (the reference's default, train.py:100-104) the VGG encoder forward runs on
+        the tcgen05 engine ('fp32' = bf16x3, features within ~1.5e-4 of the library's fp32 convolutions; 'bf16'; None =
+        the torch / cuDNN forward).  Ignored for models without ``use_tc_encoder`` and while the encoder is trained."""
         self.model = model
         self.word_map = word_map
         self.rev_word_map = {v: k for k, v in word_map.items()}
@@ -49,6 +52,8 @@ class LrpTuneStep:
             for name, p in model.named_parameters():
                 if 'img_encoder' in name:
                     p.requires_grad = False
+        if fix_encoder and tc_encoder and hasattr(model, "use_tc_encoder"):
+            model.use_tc_encoder(tc_encoder)
         params = [p for p in model.parameters() if p.requires_grad]
         self.optimizer = optimizer or torch.optim.Adam(params=params, lr=lr, betas=(0.8, 0.999))     # train.py:107-109
         self.grad_clip = grad_clip

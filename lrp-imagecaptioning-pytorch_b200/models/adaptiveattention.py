@@ -233,21 +233,25 @@ class ExplainAdaptiveAttention(ExplainGridTDAttention):
         with torch.no_grad():
             feat = feat.contiguous()
             avg = feat.mean(1)
-            Wp = m.img_projector.weight.reshape(H, C)
-            z_proj = torch.mm(feat.view(B * P, C), Wp.t()).view(B, P, H)            # without bias (:762)
+            # every GEMM of this forward runs on the tcgen05 kernels (ops.LinearX3: bf16x3, fp32 accuracy)
+            ipw = m.img_projector.weight
+            z_proj = self._lx("proj", ipw, None, lambda: (ipw.detach().reshape(H, C), None))(feat.view(B * P, C)).view(B, P, H)   # without bias (:762)
             A = (z_proj + m.img_projector.bias).clamp(min=0).contiguous()
-            z_glob = torch.mm(avg, m.global_img_feature_proj.weight.t())           # without bias (:745)
+            z_glob = self._lx("glob", m.global_img_feature_proj.weight)(avg)       # without bias (:745)
             glob = (z_glob + m.global_img_feature_proj.bias).clamp(min=0)
-            img_proj = att.W_v_proj(A).contiguous()                                 # (B,P,K)
+            img_proj = self._lx("wv", att.W_v_proj.weight, att.W_v_proj.bias)(A.view(B * P, H)).view(B, P, K)   # (B,P,K)
             Wrec_p, W_in, b = self._explainer_weights()
-            Wa = torch.zeros(2 * H, 2 * K, device=dev)
-            Wa[:H, :K] = att.W_g_proj.weight.t()
-            Wa[H:, K:] = att.W_s_proj.weight.t()
-            ba = torch.cat((torch.zeros(K, device=dev), att.W_s_proj.bias))
+
+            def _att_layer():                        # [h | s] @ blockdiag(W_g^T, W_s^T) + [0 | b_s] as one Linear
+                Wa = torch.zeros(2 * K, 2 * H, device=dev)
+                Wa[:K, :H] = att.W_g_proj.weight
+                Wa[K:, H:] = att.W_s_proj.weight
+                return Wa, torch.cat((torch.zeros(K, device=dev), att.W_s_proj.bias))
+            att_lin = self._lx("att", [att.W_g_proj.weight, att.W_s_proj.weight], att.W_s_proj.bias, _att_layer)
             w_h = att.w_h.weight.reshape(-1).contiguous()
             emb = m.embedding(tokens[:, :T])                                                     # (B,T,E)
             x = torch.cat((emb, glob.unsqueeze(1).expand(B, T, E)), -1).contiguous()             # (B,T,2E)  :649
-            pre = torch.addmm(b, x.transpose(0, 1).reshape(T * B, 2 * E), W_in).view(T, B, 5 * H)
+            pre = self._lx("pre", W_in, b, lambda: (W_in.t().contiguous(), b))(x.transpose(0, 1).reshape(T * B, 2 * E)).view(T, B, 5 * H)
             h, c = torch.zeros(B, T + 1, H, device=dev), torch.zeros(B, T + 1, H, device=dev)
             g, i, f, st, ctx, ctx_hat = (new(B, T, H) for _ in range(6))
             alpha, beta = new(B, T, P), new(B, T)
@@ -259,10 +263,10 @@ class ExplainAdaptiveAttention(ExplainGridTDAttention):
                 p, q = t & 1, (t & 1) ^ 1
                 ops.lstm_step(hin[p], Wrec_p, pre[t], 5, c[:, t], h[:, t + 1], c[:, t + 1], g[:, t], i[:, t], f[:, t],
                               s=st[:, t], h_copy0=hin[q], h_copy2=hs[:, :H], s_copy=hs[:, H:])
-                hsp = torch.addmm(ba, hs, Wa)                                                     # (B,2K)
+                hsp = att_lin(hs)                                                                 # (B,2K)
                 ops.adaptive_attention(A, img_proj, hsp, w_h, st[:, t], ctx[:, t], ctx_hat[:, t], alpha[:, t],
                                        beta[:, t])
-            pred = torch.addmm(m.fc.bias, (ctx_hat + h[:, 1:]).view(B * T, H), m.fc.weight.t()).view(B, T, -1)
+            pred = self._lx("fc", m.fc.weight, m.fc.bias)((ctx_hat + h[:, 1:]).view(B * T, H)).view(B, T, -1)
         return dict(x=x, h=h, c=c, g=g, i=i, f=f, st=st, ctx=ctx, ctx_hat=ctx_hat, alpha=alpha, beta=beta, pred=pred,
                     feat=feat, avg=avg, z_proj=z_proj.contiguous(), A=A, z_glob=z_glob)
 

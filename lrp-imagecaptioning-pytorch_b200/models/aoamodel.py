@@ -374,17 +374,21 @@ class ExplainAOAAttention(ExplainGridTDAttention):
         dev = feat.device
         with torch.no_grad():
             feat = feat.contiguous()
-            Wp = m.img_projector.weight.reshape(H, C)
-            A_pre = torch.addmm(m.img_projector.bias, feat.view(B * P, C), Wp.t()).view(B, P, H)
+            # every GEMM of this forward runs on the tcgen05 kernels (ops.LinearX3: bf16x3, fp32 accuracy)
+            ipw = m.img_projector.weight
+            A_pre = self._lx("proj", ipw, m.img_projector.bias,
+                             lambda: (ipw.detach().reshape(H, C), m.img_projector.bias.detach()))(feat.view(B * P, C)).view(B, P, H)
             A = A_pre.clamp(min=0)
             glob = A.mean(1)
-            key, value = m.decoder_k_proj(A), m.decoder_v_proj(A)
+            A2 = A.view(B * P, H)
+            key = self._lx("k", m.decoder_k_proj.weight, m.decoder_k_proj.bias)(A2).view(B, P, H)
+            value = self._lx("v", m.decoder_v_proj.weight, m.decoder_v_proj.bias)(A2).view(B, P, H)
             kT = key.view(B, P, nh, dk).permute(0, 2, 3, 1)                      # (B,nh,dk,P)
             vh = value.view(B, P, nh, dk).transpose(1, 2)                        # (B,nh,P,dk)
             mha = m.decoder_multihead_attention
             Wp_hh, W_in, b = self._explainer_weights(quirk_double_bias_ih)
             x = torch.cat((m.embedding(tokens[:, :T]), glob.unsqueeze(1).expand(B, T, H)), -1).contiguous()   # (B,T,E+H)
-            pre = torch.addmm(b, x.transpose(0, 1).reshape(T * B, E + H), W_in).view(T, B, 4 * H)
+            pre = self._lx("pre", W_in, b, lambda: (W_in.t().contiguous(), b))(x.transpose(0, 1).reshape(T * B, E + H)).view(T, B, 4 * H)
             h, c = torch.zeros(B, T + 1, H, device=dev), torch.zeros(B, T + 1, H, device=dev)
             g, i, f = (torch.empty(B, T, H, device=dev) for _ in range(3))
             hin = torch.zeros(2, B, H, device=dev)           # the step kernel's input rows, ping-ponged over the steps
@@ -393,13 +397,14 @@ class ExplainAOAAttention(ExplainGridTDAttention):
                 ops.lstm_step(hin[p], Wp_hh, pre[t], 4, c[:, t], h[:, t + 1], c[:, t + 1], g[:, t], i[:, t], f[:, t],
                               h_copy0=hin[q])
             hn = h[:, 1:]                                                         # (B,T,H)
-            qv = mha.q_proj(hn).view(B, T, nh, dk).transpose(1, 2)                # (B,nh,T,dk)
+            hn2 = hn.reshape(B * T, H)
+            qv = self._lx("q", mha.q_proj.weight, mha.q_proj.bias)(hn2).view(B, T, nh, dk).transpose(1, 2)   # (B,nh,T,dk)
             alpha = torch.softmax(torch.matmul(qv, kT) / math.sqrt(dk), dim=-1)   # (B,nh,T,P)
             ctx = torch.matmul(alpha, vh).transpose(1, 2).reshape(B, T, H)
-            gate = m.decoder_aoa_linear_gate(hn)
-            lin = m.decoder_aoa_linear(ctx)
+            gate = self._lx("gate", m.decoder_aoa_linear_gate.weight, m.decoder_aoa_linear_gate.bias)(hn2).view(B, T, H)
+            lin = self._lx("lin", m.decoder_aoa_linear.weight, m.decoder_aoa_linear.bias)(ctx.reshape(B * T, H)).view(B, T, H)
             caoa = torch.sigmoid(gate) * lin
-            pred = torch.addmm(m.fc.bias, (caoa + hn).reshape(B * T, H), m.fc.weight.t()).view(B, T, m.vocab_size)
+            pred = self._lx("fc", m.fc.weight, m.fc.bias)((caoa + hn).reshape(B * T, H)).view(B, T, m.vocab_size)
             st = dict(x=x, g=g, i=i, f=f, ctx=ctx.contiguous(), caoa=caoa.contiguous(), caoa_lin=lin.contiguous(),
                       caoa_gate=gate.contiguous(), alpha=alpha.transpose(1, 2).contiguous(), pred=pred, h=h, c=c,
                       feat=feat, A_pre=A_pre.contiguous(), A=A.contiguous(), glob=glob, key=key,

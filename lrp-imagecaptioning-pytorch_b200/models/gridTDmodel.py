@@ -166,9 +166,42 @@ class GridTDModel(nn.Module):
         predict_score_t = self.fc(self.dropout(context_t_hat + h2t))
         return predict_score_t, alpha_t, beta_t, (h1t, c1t, h2t, c2t)
 
+    def use_tc_encoder(self, precision="fp32"):
+        """Frozen VGG encoder ("Training with fixed CNN", train.py:100-104) on the tcgen05 forward: features through
+        lrpx.tc.TcVggEngine instead of the library convolutions — 'fp32' = error-compensated bf16x3 (features within
+        ~1.5e-4 of the fp32 ones), 'bf16', or None to go back.  Only used while no encoder parameter requires grad."""
+        self._tc_encoder_precision = precision
+        self._tc_encoder = None
+
+    def _encoder_features(self, images):
+        prec = getattr(self, "_tc_encoder_precision", None)
+        enc = self.img_encoder.encoder
+        if prec and images.is_cuda and isinstance(enc, nn.Sequential) and not any(p.requires_grad for p in enc.parameters()):
+            from lrpx import tc
+            from LRPtools import lrp_wrapper
+            stamp = tuple((p.data_ptr(), p._version) for p in enc.parameters())
+            if self._tc_encoder is None or self._tc_encoder[0] != stamp:
+                cfgd = lrp_wrapper._tc_cfg(enc)
+                if cfgd is None:
+                    raise NotImplementedError("use_tc_encoder: the encoder is not a VGG-style conv3x3/ReLU/max-pool stack")
+                convs, cfg = cfgd
+                if prec == "fp32" and convs[0].out_channels % 64:
+                    prec = self._tc_encoder_precision = None          # shapes the general kernels do not take: library forward
+                    return self.img_encoder(images)
+                # rule='epsilon' keeps ONE accumulator per output channel in the forward (no z+ needed here)
+                eng = tc.TcVggEngine([c.weight for c in convs], [c.bias for c in convs], cfg, images.device,
+                                     precision="fp32", rule="epsilon") if prec == "fp32" else \
+                    tc.TcVggEngine([c.weight for c in convs], [c.bias for c in convs], cfg, images.device)
+                self._tc_encoder = (stamp, eng)
+            eng = self._tc_encoder[1]
+            with torch.no_grad():
+                feats = eng.features(eng.forward(images), "nchw")
+            return feats, feats.mean((2, 3)).squeeze()
+        return self.img_encoder(images)
+
     def _encode(self, images):
         batch_size = images.size(0)
-        image_features, avg_feature = self.img_encoder(images)
+        image_features, avg_feature = self._encoder_features(images)
         before_act = self.img_projector(image_features)
         image_feature_proj = self.relu(before_act).contiguous().view(batch_size, self.hidden_dim, -1)
         global_before_act = self.global_img_feature_proj(avg_feature)
@@ -588,6 +621,57 @@ class ExplainGridTDAttention(object):
             self._expl_w_key = key
         return self._expl_w
 
+    def _lx(self, name, weight, bias=None, derive=None):
+        """Cached tensor-core Linear for the explainer forwards: ``weight`` (out, in) and ``bias`` are (views of) model
+        parameters; ``derive()`` (optional) builds the actual (weight, bias) from them (concatenations, transposes) and
+        is re-run only when a source tensor changes (data pointer / in-place version)."""
+        src = [t for t in (weight if isinstance(weight, (list, tuple)) else [weight]) if t is not None]
+        src += [t for t in (bias if isinstance(bias, (list, tuple)) else [bias]) if t is not None]
+        key = tuple((t.data_ptr(), t._version) for t in src)
+        cache = self.__dict__.setdefault("_lx_cache", {})
+        hit = cache.get(name)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                w, b = derive() if derive is not None else (weight.detach(), None if bias is None else bias.detach())
+            hit = cache[name] = (key, self._linear(w, b), (w, b))
+        return hit[1]
+
+    @staticmethod
+    def _linear(weight, bias):
+        """``ops.LinearX3`` (tcgen05, bf16x3) for the shapes it takes, else the library GEMM on the same device."""
+        if ops.LinearX3.supports(weight):
+            return ops.LinearX3(weight, bias)
+        return lambda x: torch.addmm(bias, x, weight.t()) if bias is not None else x @ weight.t()
+
+    def _linears(self):
+        """The explainer forward's Linear layers on the tensor-core GEMM (built once, rebuilt when a source parameter
+        changes): 1x1 projector, global projection, W_v, the input-side gate pre-activations, the two attention
+        projections as one block-diagonal layer, the vocabulary projection."""
+        m = self.model
+        att, cell, xg = m.AdaAttention, m.AdaLSTM.lstm_cell, m.AdaLSTM.x_gate
+        src = [m.img_projector.weight, m.img_projector.bias, m.global_img_feature_proj.weight, att.W_v_proj.weight,
+               att.W_g_proj.weight, att.W_s_proj.weight, att.W_s_proj.bias, m.fc.weight, m.fc.bias, cell.weight_ih,
+               cell.bias_ih, cell.bias_hh, xg.weight, xg.bias]
+        key = tuple((t.data_ptr(), t._version) for t in src)
+        if getattr(self, "_lin_key", None) != key:
+            H, K = m.hidden_dim, att.num_pixel
+            dev = m.fc.weight.device
+            _, W1_in, b1, _, _ = self._explainer_weights()
+            with torch.no_grad():
+                Wa = torch.zeros(2 * K, 2 * H, device=dev)                 # (out, in): rows 0..K-1 <- h1, K..2K-1 <- s
+                Wa[:K, :H] = att.W_g_proj.weight
+                Wa[K:, H:] = att.W_s_proj.weight
+                ba = torch.cat((torch.zeros(K, device=dev), att.W_s_proj.bias))
+                Wp = m.img_projector.weight.detach().reshape(H, -1)
+                W1t = W1_in.t().contiguous()
+            L = self._linear
+            self._lin = dict(proj=L(Wp, m.img_projector.bias.detach()),
+                             glob=L(m.global_img_feature_proj.weight.detach(), m.global_img_feature_proj.bias.detach()),
+                             wv=L(att.W_v_proj.weight.detach(), att.W_v_proj.bias.detach()), pre1=L(W1t, b1), att=L(Wa, ba),
+                             fc=L(m.fc.weight.detach(), m.fc.bias.detach()))
+            self._lin_key = key
+        return self._lin
+
     def explainer_forward(self, feat, tokens, quirk_double_bias_ih=True):
         """The explainer's teacher-forced forward (reference :941-1012) batched over images.
 
@@ -612,28 +696,24 @@ class ExplainGridTDAttention(object):
         att = m.AdaAttention
         K = att.num_pixel
         new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+        lin = self._linears()         # the forward's GEMMs on the tcgen05 kernels (bf16x3: fp32 accuracy), no library GEMM
         with torch.no_grad():
             feat = feat.contiguous()
             avg = feat.mean(1)
-            Wp = m.img_projector.weight.reshape(H, C)
-            A_pre = torch.addmm(m.img_projector.bias, feat.view(B * P, C), Wp.t()).view(B, P, H)
+            A_pre = lin["proj"](feat.view(B * P, C)).view(B, P, H)
             A = A_pre.clamp(min=0)
-            glob_pre = m.global_img_feature_proj(avg)
+            glob_pre = lin["glob"](avg)
             glob = glob_pre.clamp(min=0)
-            img_proj = att.W_v_proj(A).contiguous()                                  # (B,P,K)
+            img_proj = lin["wv"](A.view(B * P, H)).view(B, P, K)                     # (B,P,K)
             cell, L = m.AdaLSTM.lstm_cell, m.LanguageLSTM
             W1p, W1_in, b1, W2p, b2 = self._explainer_weights(quirk_double_bias_ih)
-            # both attention projections as ONE library GEMM per step: [h1 | s] @ blockdiag(W_g^T, W_s^T) + [0 | b_s]
+            # both attention projections as ONE GEMM per step: [h1 | s] @ blockdiag(W_g^T, W_s^T) + [0 | b_s]
             # (computing them inside the attention kernel re-reads 0.8 MB of weights per image and step: measured slower)
-            Wa = torch.zeros(2 * H, 2 * K, device=dev)
-            Wa[:H, :K] = att.W_g_proj.weight.t()
-            Wa[H:, K:] = att.W_s_proj.weight.t()
-            ba = torch.cat((torch.zeros(K, device=dev), att.W_s_proj.bias))
             w_h = att.w_h.weight.reshape(-1).contiguous()
             # ---- state-independent halves for all T steps at once
             emb = m.embedding(tokens[:, :T])                                                     # (B,T,E)
             xin = torch.cat((glob.unsqueeze(1).expand(B, T, E), emb), -1)                        # (B,T,2E)
-            pre1 = torch.addmm(b1, xin.transpose(0, 1).reshape(T * B, 2 * E), W1_in).view(T, B, 5 * H)
+            pre1 = lin["pre1"](xin.transpose(0, 1).reshape(T * B, 2 * E)).view(T, B, 5 * H)
             # ---- saved state
             h1, c1, h2, c2 = (torch.zeros(B, T + 1, H, device=dev) for _ in range(4))
             g1, i1, f1, g2, i2, f2, st, ctx, ctx_hat = (new(B, T, H) for _ in range(9))
@@ -649,13 +729,13 @@ class ExplainGridTDAttention(object):
                 ops.lstm_step(hcat[p], W1p, pre1[t], 5, c1[:, t], h1[:, t + 1], c1[:, t + 1], g1[:, t], i1[:, t],
                               f1[:, t], s=st[:, t], h_copy0=hcat[q][:, H:], h_copy1=x2c[p][:, H:2 * H],
                               h_copy2=hs[:, :H], s_copy=hs[:, H:])
-                hsp = torch.addmm(ba, hs, Wa)                                                     # (B,2K)
+                hsp = lin["att"](hs)                                                              # (B,2K)
                 ops.adaptive_attention(A, img_proj, hsp, w_h, st[:, t], ctx[:, t], ctx_hat[:, t], alpha[:, t],
                                        beta[:, t], ctx_hat_copy=x2c[p][:, :H])
                 # LanguageLSTM from [ctx_hat_t | h1_{t+1} | h2_t]                                             :984-990
                 ops.lstm_step(x2c[p], W2p, b2, 4, c2[:, t], h2[:, t + 1], c2[:, t + 1], g2[:, t], i2[:, t], f2[:, t],
                               h_copy0=hcat[q][:, :H], h_copy1=x2c[q][:, 2 * H:])
-            pred = torch.addmm(m.fc.bias, (ctx_hat + h2[:, 1:]).view(B * T, H), m.fc.weight.t()).view(B, T, m.vocab_size)
+            pred = lin["fc"]((ctx_hat + h2[:, 1:]).view(B * T, H)).view(B, T, m.vocab_size)
             x1 = torch.cat((h2[:, :T], xin), -1)
             x2 = torch.cat((ctx_hat, h1[:, 1:]), -1)
             st_ = dict(x1=x1, x2=x2, g1=g1, i1=i1, f1=f1, g2=g2, i2=i2, f2=f2, st=st, ctx=ctx, ctx_hat=ctx_hat,

@@ -129,6 +129,15 @@ def test_config5_tuner_weights_and_step_at_full_size():
     assert torch.isfinite(loss) and torch.isfinite(ls) and torch.isfinite(ll)
     assert torch.equal(enc_before, model.img_encoder.encoder[0].weight.detach())
     assert not torch.equal(fc_before, model.fc.weight.detach())
+    # the fixed CNN ran on the tcgen05 forward (LrpTuneStep's default tc_encoder='fp32': bf16x3); the same batch through
+    # the library convolutions gives the same losses to ~1e-4 (features within 1.5e-4 of fp32)
+    assert model._tc_encoder is not None
+    with torch.no_grad():
+        l_tc = [float(v) for v in st.losses(imgs, caps.to(DEV), torch.full((B,), L))]
+        model.use_tc_encoder(None)
+        l_lib = [float(v) for v in st.losses(imgs, caps.to(DEV), torch.full((B,), L))]
+    print("lrp_tune losses, tcgen05 encoder vs library encoder:", l_tc, l_lib)
+    assert all(abs(a - b) <= 2e-3 * abs(b) for a, b in zip(l_tc, l_lib))
 
 
 def test_adaptive_decoder_full_size_properties(tmp_path):
