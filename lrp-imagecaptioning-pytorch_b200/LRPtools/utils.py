@@ -44,53 +44,49 @@ def normalize_relevance(X, dim=-1, temperature=1):
 
 # ---------------------------------------------------------------------------------- heat-map post-processing (host)
 def project(X, output_range=(0, 1), absmax=None, input_is_postive_only=False):
-    """utils.py:34-52: scale by max|X| (per leading index), map [-1,1] -> [0,1] unless the input is positive only,
-    clip, stretch to ``output_range``.  Like the reference it divides ``X`` in place."""
-    if absmax is None:
-        absmax = np.max(np.abs(X), axis=tuple(range(1, len(X.shape))))
-    absmax = np.asarray(absmax)
-    mask = absmax != 0
-    if mask.sum() > 0:
-        X[mask] /= absmax[mask]
-    if input_is_postive_only is False:
-        X = (X + 1) / 2
-    X = X.clip(0, 1)
-    return output_range[0] + (X * (output_range[1] - output_range[0]))
+    """utils.py:34-52.  X / max|X| (one maximum per leading index, zero maxima left alone; the division happens IN
+    the caller's array, as in the reference), then [-1, 1] -> [0, 1] unless the input is positive only, clipped and
+    stretched to ``output_range``."""
+    amax = np.asarray(np.abs(X).max(axis=tuple(range(1, X.ndim))) if absmax is None else absmax)
+    nz = amax != 0
+    if nz.any():
+        X[nz] /= amax[nz]
+    unit = (X if input_is_postive_only else 0.5 * (X + 1)).clip(0, 1)
+    lo, hi = output_range
+    return lo + unit * (hi - lo)
 
 
-def _lut(nodes):
-    """256-entry RGB table of a matplotlib LinearSegmentedColormap.from_list(colors): linear interpolation between
-    evenly spaced nodes at i / 255."""
-    nodes = np.asarray(nodes, dtype=np.float64)
-    x = np.linspace(0.0, 1.0, 256)
-    xp = np.linspace(0.0, 1.0, len(nodes))
-    return np.stack([np.interp(x, xp, nodes[:, c]) for c in range(3)], axis=1)
+def _lut(colors):
+    """The 256-entry RGB table matplotlib builds for LinearSegmentedColormap.from_list(colors): evenly spaced colour
+    nodes, linear interpolation at i / 255."""
+    colors = np.asarray(colors, dtype=np.float64)
+    at, nodes = np.linspace(0.0, 1.0, 256), np.linspace(0.0, 1.0, len(colors))
+    return np.stack([np.interp(at, nodes, colors[:, c]) for c in range(3)], axis=1)
 
 
-_CMAPS = {"seismic": _lut([(0, 0, 0.3), (0, 0, 1), (1, 1, 1), (1, 0, 0), (0.5, 0, 0)]),      # matplotlib _cm.py: _seismic_data
-          "gray": _lut([(0, 0, 0), (1, 1, 1)])}
+# 'seismic' = dark blue - blue - white - red - dark red (matplotlib _cm.py: _seismic_data); 'gray' = black - white
+_CMAPS = {"seismic": _lut([(0, 0, 0.3), (0, 0, 1), (1, 1, 1), (1, 0, 0), (0.5, 0, 0)]), "gray": _lut([(0, 0, 0), (1, 1, 1)])}
 
 
 def heatmap(X, cmap_type="seismic", reduce_op="sum", reduce_axis=-1, **kwargs):
-    """utils.py:67-94: reduce the channel axis (sum, or the entry of largest magnitude), project to 0..255, colour."""
-    if cmap_type not in _CMAPS:
-        raise NotImplementedError(f"colour map {cmap_type!r}: only 'seismic' and 'gray' (what the reference uses) are built in")
-    tmp = X
-    shape = tmp.shape
+    """utils.py:67-94: collapse ``reduce_axis`` (sum, or the signed entry of largest magnitude, ties to the positive
+    one), ``project`` to 0..255, look the colour up; the collapsed axis becomes RGB."""
+    table = _CMAPS.get(cmap_type)
+    if table is None:
+        raise NotImplementedError(f"colour map {cmap_type!r}: 'seismic' and 'gray' (the ones the reference uses) are built in")
     if reduce_op == "sum":
-        tmp = tmp.sum(axis=reduce_axis)
+        flat = X.sum(axis=reduce_axis)
     elif reduce_op == "absmax":
-        pos_max = tmp.max(axis=reduce_axis)
-        neg_max = (-tmp).max(axis=reduce_axis)
-        abs_neg_max = -neg_max
-        tmp = np.select([pos_max >= abs_neg_max, pos_max < abs_neg_max], [pos_max, neg_max])
+        # Reference quirk kept (utils.py:76-81): it compares the positive extreme with the SIGNED negative extreme
+        # (`abs_neg_max = -neg_max` is the minimum itself), which always holds, so "absmax" returns the maximum.
+        top, bottom = X.max(axis=reduce_axis), X.min(axis=reduce_axis)
+        flat = np.where(top >= bottom, top, -bottom)
     else:
         raise NotImplementedError()
-    tmp = project(tmp, output_range=(0, 255), **kwargs).astype(np.int64)
-    tmp = _CMAPS[cmap_type][tmp.flatten().clip(0, 255)]
-    shape = list(shape)
-    shape[reduce_axis] = 3
-    return tmp.reshape(shape).astype(np.float32)
+    idx = project(flat, output_range=(0, 255), **kwargs).astype(np.int64).clip(0, 255)
+    out_shape = list(X.shape)
+    out_shape[reduce_axis] = 3
+    return table[idx.ravel()].reshape(out_shape).astype(np.float32)
 
 
 def graymap(X, **kwargs):
@@ -99,20 +95,10 @@ def graymap(X, **kwargs):
 
 
 def gamma(X, gamma=0.7, minamp=0, maxamp=None):
-    """utils.py:101-145: gamma correction of positive and negative values separately around ``minamp``."""
-    if maxamp is None:
-        maxamp = np.abs(X).max()
+    """utils.py:101-145: sign-preserving gamma curve around ``minamp``: y = sign(u) |u|^gamma with u = (X - minamp) /
+    maxamp, scaled back by maxamp (default max|X|; an all-zero input is returned as it is)."""
+    maxamp = np.abs(X).max() if maxamp is None else maxamp
     if maxamp == 0:
         return X
-    Y = np.zeros_like(X)
-    X = X - minamp
-    X = X / maxamp
-    i_pos = X >= 0
-    if i_pos.sum() > 0:
-        Y[i_pos] = X[i_pos] ** gamma
-    i_neg = np.invert(i_pos)
-    if i_neg.sum() > 0:
-        Y[i_neg] = -(-X[i_neg]) ** gamma
-    Y *= maxamp
-    Y += minamp
-    return Y
+    u = (X - minamp) / maxamp
+    return np.sign(u) * np.abs(u) ** gamma * maxamp + minamp

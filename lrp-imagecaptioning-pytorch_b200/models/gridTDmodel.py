@@ -636,10 +636,12 @@ class ExplainGridTDAttention(object):
             hit = cache[name] = (key, self._linear(w, b), (w, b))
         return hit[1]
 
-    @staticmethod
-    def _linear(weight, bias):
-        """``ops.LinearX3`` (tcgen05, bf16x3) for the shapes it takes, else the library GEMM on the same device."""
-        if ops.LinearX3.supports(weight):
+    def _linear(self, weight, bias):
+        """A Linear layer of the explainer forward.  precision 'bf16' (the throughput mode): ``ops.LinearX3`` — the
+        tcgen05 GEMM with error-compensated bf16x3 operands (measured 2-3e-6 of sum |x w| off fp64, one-sided by the
+        tensor cores' round-toward-zero accumulation) — for the shapes it takes.  'fp32' / 'simt' keep the fp32 library
+        GEMM: their bar is the reference's elementwise rtol 1e-4 / atol 1e-6 on the saved state."""
+        if self.precision == 'bf16' and ops.LinearX3.supports(weight):
             return ops.LinearX3(weight, bias)
         return lambda x: torch.addmm(bias, x, weight.t()) if bias is not None else x @ weight.t()
 

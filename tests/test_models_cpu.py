@@ -275,3 +275,23 @@ def test_encoder_mirrors_forward_vs_reference_fixtures(golden):
     enc.eval()
     with torch.no_grad():
         assert_close(enc(g["x"]), g["feats"], atol=2e-5, what="vgg mirror forward")
+
+
+def test_heatmap_postprocessing_matches_reference_fixture(golden):
+    """LRPtools.utils.project / gamma (utils.py:34-52,101-145) against values the reference's own functions produced
+    (fixture utils_viz, generated through oracle/ref_shim.py); heatmap's colour tables: 'seismic' runs dark blue - blue -
+    white - red - dark red, 'gray' black - white, 256 entries like matplotlib's."""
+    import numpy as np
+    import LRPtools.utils as U
+    g = golden("utils_viz")
+    x = g["x"].numpy()
+    assert np.array_equal(U.project(x.copy()), g["proj"].numpy())
+    assert np.array_equal(U.project(x.copy(), output_range=(0, 255)), g["proj255"].numpy())
+    assert np.allclose(U.gamma(x.copy(), 0.7), g["gamma"].numpy(), rtol=1e-6, atol=1e-7)
+    lut = U._CMAPS["seismic"]
+    assert lut.shape == (256, 3) and np.allclose(lut[0], (0, 0, 0.3)) and np.allclose(lut[-1], (0.5, 0, 0))
+    assert np.allclose(lut[127], lut[128][::-1], atol=2e-2) and lut[127:129].min() > 0.98          # white in the middle
+    hm = U.heatmap(np.stack([x[0]] * 3, -1)[None])                         # (1,16,16,3) -> RGB
+    assert hm.shape == (1, 16, 16, 3) and hm.dtype == np.float32
+    gm = U.graymap(np.stack([x[0]] * 3, -1)[None])
+    assert np.allclose(gm[..., 0], gm[..., 1]) and np.allclose(gm[..., 1], gm[..., 2])
