@@ -251,6 +251,9 @@ def problem_inputs(args, seed):
     return imgs, toks
 
 
+_REF_CACHE = {}
+
+
 def cpu_config2(args, seed, nimg, nwords, keep=False, use_reference=True):
     """The reference's per-word formulation on the host cores for the first `nimg` images of rank `seed`'s batch, the
     last `nwords` words of each: the UNMODIFIED reference when it is staged (kind "reference"), else the oracle port.
@@ -270,7 +273,10 @@ def cpu_config2(args, seed, nimg, nwords, keep=False, use_reference=True):
     out = {} if keep else None
     t0 = time.perf_counter()
     if rr is not None:
-        ref = rr.GridTDReference(p, vsd, V, H, E, synth.word_map(V))
+        key = (seed, V)
+        if key not in _REF_CACHE:                 # model construction is not part of the timed work
+            _REF_CACHE[key] = rr.GridTDReference(p, vsd, V, H, E, synth.word_map(V))
+        ref = _REF_CACHE[key]
         t0 = time.perf_counter()
         for b in range(nimg):
             img = imgs[b:b + 1]
