@@ -127,11 +127,12 @@ __device__ __forceinline__ void put_operand(float* u, __nv_bfloat16* a3, size_t 
   if (a3) {
     __nv_bfloat16 hi, lo;
     split_bf16(x, hi, lo);
-    __nv_bfloat16* o = a3 + row * 3 * K;
-    o[k] = hi; o[K + k] = hi; o[2 * K + k] = lo;
+    __nv_bfloat16* o = a3 + row * 2 * K;
+    o[k] = hi; o[K + k] = lo;
   }
 }
-// rows x K fp32 (row pitch lda) -> rows x 3K bf16 [hi | hi | lo]
+// rows x K fp32 (row pitch lda) -> rows x 2K bf16 [hi | lo]; the GEMM reads a row as K = [hi | lo | hi] (a_phys wrap of
+// lrpx_tc_conv: the third block group re-reads the first), so hi is stored once: 2/3 of the bytes of [hi | hi | lo]
 __global__ void split3_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int K,
                                   int lda) {
   long long total = rows * K;
@@ -141,11 +142,11 @@ __global__ void split3_act_kernel(const float* __restrict__ x, __nv_bfloat16* __
     int k = (int)(i - r * K);
     __nv_bfloat16 hi, lo;
     split_bf16(x[r * lda + k], hi, lo);
-    __nv_bfloat16* o = out + r * 3 * K;
-    o[k] = hi; o[K + k] = hi; o[2 * K + k] = lo;
+    __nv_bfloat16* o = out + r * 2 * K;
+    o[k] = hi; o[K + k] = lo;
   }
 }
-// W (K x N fp32 row-major, i.e. [k][n]) -> N x 3K bf16 [hi | lo | hi] of W^T
+// W (K x N fp32 row-major, i.e. [k][n]) -> N x 3K bf16 [hi | hi | lo] of W^T:  a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
 __global__ void split3_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int K, int N) {
   long long total = (long long)K * N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -155,7 +156,7 @@ __global__ void split3_weight_kernel(const float* __restrict__ w, __nv_bfloat16*
     __nv_bfloat16 hi, lo;
     split_bf16(w[i], hi, lo);
     __nv_bfloat16* o = out + (size_t)n * 3 * K;
-    o[k] = hi; o[K + k] = lo; o[2 * K + k] = hi;
+    o[k] = hi; o[K + k] = hi; o[2 * K + k] = lo;
   }
 }
 // GE_FEAT / GE_AOA_PROJ epilogues applied to a plain GEMM result in place
@@ -183,19 +184,24 @@ static inline int ew_grid(long long total) {
 static bool tc_shape_ok(int N, int K) { return K % 64 == 0 && N % 32 == 0 && (N <= 256 || N % 256 == 0); }
 
 // C[M,N] = A[M,K] @ W[K,N] (+ epilogue): tensor cores when `wt3` (prepared W') is given, CUDA cores otherwise
-// a3_ready: the producer kernel already wrote the split operand [hi | hi | lo] into a3 (no fp32 A exists then)
+// a3_ready: the producer kernel already wrote the split operand [hi | lo] into a3 (no fp32 A exists then)
 template <int EPI>
 static int gemm_any(const float* A, const float* W, const __nv_bfloat16* wt3, __nv_bfloat16* a3, float* C, int M, int N,
                     int K, const GemmEpi& e, cudaStream_t st, bool a3_ready = false) {
   if (M == 0) return LRPX_OK;
   if (!wt3) return sgemm<EPI>(A, W, C, M, N, K, e, st);
   if (!a3_ready) split3_act_kernel<<<ew_grid((long long)M * K), 256, 0, st>>>(A, a3, M, K, K);
-  if (EPI == GE_STORE) return lrpx_tc_gemm_bf16_f32(a3, wt3, C, M, N, 3 * K, st);
-  // projector rules fused into the GEMM's epilogue: rows are (request, pixel) = one PF "block" of P rows per request
   lrpx_tc_conv_args g{};
-  g.n_img = M / e.P; g.h = 0; g.w = e.P - 1; g.cin = 3 * K; g.ncol = N; g.ksize = 1;
-  g.epilogue = EPI == GE_FEAT ? LRPX_TC_EPI_FEAT : LRPX_TC_EPI_FEAT_DIV;
+  g.cin = 3 * K; g.a_phys = 2 * K; g.ncol = N; g.ksize = 1;
   g.a = a3; g.wt = wt3; g.out = C;
+  if (EPI == GE_STORE) {          // one PF "block" of M rows: the STORE_F32 epilogue writes every in-range row
+    g.n_img = 1; g.h = 0; g.w = M - 1;
+    g.epilogue = LRPX_TC_EPI_STORE_F32;
+    return lrpx_tc_conv(&g, st);
+  }
+  // projector rules fused into the GEMM's epilogue: rows are (request, pixel) = one PF "block" of P rows per request
+  g.n_img = M / e.P; g.h = 0; g.w = e.P - 1;
+  g.epilogue = EPI == GE_FEAT ? LRPX_TC_EPI_FEAT : LRPX_TC_EPI_FEAT_DIV;
   g.x = e.x0; g.x1 = e.x1; g.bias = e.add_q; g.row_img = e.req_img;
   return lrpx_tc_conv(&g, st);
 }
@@ -363,7 +369,7 @@ __global__ void grid_attn_kernel(lrpx_gridtd_args a, GridWs w) {
 // LDS.128 (four alphas, broadcast) feed four FMAs, i = t..0 like the reference loop, then
 // wproj = A * acc / stab(A_pre).  (The per-(request, pixel) form above re-reads uctx 196 times and spends ~4
 // instructions per multiply-add: 1.4 ms per 1216 requests; this form is bound by its 0.7 GB of output.)
-// SPLIT: the result leaves directly as the split bf16 operand [hi | hi | lo] of the tensor-core projector GEMM.
+// SPLIT: the result leaves directly as the split bf16 operand [hi | lo] of the tensor-core projector GEMM.
 template <bool SPLIT>
 __global__ void __launch_bounds__(512) grid_attn_rows_kernel(lrpx_gridtd_args a, GridWs w) {
   extern __shared__ __align__(16) float att_s[];          // alpha[(t+1)][P4] | uctx[(t+1)][H]
@@ -421,10 +427,9 @@ __global__ void __launch_bounds__(512) grid_attn_rows_kernel(lrpx_gridtd_args a,
               hi2[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
               lo2[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
             }
-            __nv_bfloat16* o = w.a3 + row * 3 * H + h4;
+            __nv_bfloat16* o = w.a3 + row * 2 * H + h4;
             *reinterpret_cast<uint2*>(o) = make_uint2(hi2[0], hi2[1]);
-            *reinterpret_cast<uint2*>(o + H) = make_uint2(hi2[0], hi2[1]);
-            *reinterpret_cast<uint2*>(o + 2 * H) = make_uint2(lo2[0], lo2[1]);
+            *reinterpret_cast<uint2*>(o + H) = make_uint2(lo2[0], lo2[1]);
           } else {
             *reinterpret_cast<float4*>(w.wproj + row * H + h4) =
                 make_float4(acc[k][0] * av[0] / stab(ap[0]), acc[k][1] * av[1] / stab(ap[1]),
@@ -463,8 +468,8 @@ __global__ void __launch_bounds__(512) grid_attn_rows_kernel(lrpx_gridtd_args a,
           const float r = __fdividef(acc[k] * Av[k], stab(Ap[k]));
           __nv_bfloat16 hi, lo;
           split_bf16(r, hi, lo);
-          __nv_bfloat16* o = w.a3 + row * 3 * H;
-          o[h] = hi; o[H + h] = hi; o[2 * H + h] = lo;
+          __nv_bfloat16* o = w.a3 + row * 2 * H;
+          o[h] = hi; o[H + h] = lo;
         } else {
           w.wproj[row * H + h] = acc[k] * Av[k] / stab(Ap[k]);
         }
@@ -763,8 +768,8 @@ __global__ void __launch_bounds__(256) ada_attn_kernel(lrpx_adaptive_args a, Ada
       if (SPLIT) {
         __nv_bfloat16 hi, lo;
         split_bf16(__fdividef(num, den), hi, lo);       // bf16 hi + lo keeps 16 mantissa bits: above the 2-ulp division
-        __nv_bfloat16* o = w.a3 + row * 3 * H;
-        o[h] = hi; o[H + h] = hi; o[2 * H + h] = lo;
+        __nv_bfloat16* o = w.a3 + row * 2 * H;
+        o[h] = hi; o[H + h] = lo;
       } else {
         w.wproj[row * H + h] = num / den;
       }
