@@ -120,6 +120,20 @@ class AblationExperiments:
                     mean_pos=torch.where(npos > 0, pos / npos.clamp(min=1), torch.zeros_like(pos)),
                     max=m.max(1).values, quantile=torch.quantile(m, q, dim=1).t().contiguous())
 
+    @staticmethod
+    def tpfp_split(tokens, frequent_ids, ref_encoded_caps, special_ids):
+        """Which words of a predicted caption ``tpfp_experiment`` files under TP / FP (evaluation.py:462-481, :516):
+        ``tokens`` = [<start>, w1, ..., wT]; a word counts if it is in ``frequent_ids`` (the reference's
+        ``frequent_list``); it is a true positive if it occurs in any reference caption (``ref_encoded_caps``, lists of
+        token ids; <start> / <pad> / <end> / <unk> = ``special_ids`` are dropped from that vocabulary), else a false
+        positive.  -> (tp, fp): lists of word positions t (0-based, word t = tokens[t+1])."""
+        special = set(int(v) for v in special_ids)
+        vocab = {int(w) for cap in ref_encoded_caps for w in cap} - special
+        frequent = set(int(v) for v in frequent_ids)
+        tp = [t for t, w in enumerate(tokens[1:]) if int(w) in frequent and int(w) in vocab]
+        fp = [t for t, w in enumerate(tokens[1:]) if int(w) in frequent and int(w) not in vocab]
+        return tp, fp
+
     # ------------------------------------------------------------------ evaluation.py:234-262
     def word_ablation(self, feat, tokens, r_words, req_img, req_t, pred):
         """feat (B,P,C) encoder features, r_words (Q,T) linguistic relevance of each request (entry 0 = <start>).

@@ -345,6 +345,68 @@ def golden_block_image(ns):
     save("block_image", **out)
 
 
+def golden_ablation(ns):
+    """EvaluationExperiments.ablation_experiment (evaluation.py:82-290) run END TO END by the reference on a small
+    random gridTD / VGG16 model and a seeded 224x224 image: explain_caption (Q1-accumulated heat-maps), then per word the
+    image ablation (block_image, beam search on the masked image, teacher-forced score drop or "disappeared") and, from
+    word 6 on, the word ablation (3 most relevant preceding words deleted).  The object-word list is widened to the
+    synthetic vocabulary (every word counts as a category word) and the caption search is capped at 9 words."""
+    ev = ref_shim.load_reference_evaluation()
+    V, H, E, seed = 60, 64, 32, 181
+    wm = synth.word_map(V)
+    with quiet():
+        model = ns.gridTDmodel.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(seed, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(seed + 1))
+    model.eval()
+    img = synth.images(seed + 2, 1)
+    orig_search = model.beam_search
+    model.beam_search = lambda im, w, beam_size=3, max_cap_length=20: orig_search(im, w, beam_size=beam_size, max_cap_length=9)
+    args = argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                              save_path="/tmp/lrpx_ref", dataset="syn", weight="")
+    ex = ns.gridTDmodel.ExplainGridTDAttention(args, wm, model=model)
+    ex.preprocess_img = lambda p: img.clone()
+    ex.visualize_explanations = lambda *a, **k: None
+    ev.object_words_list = [w for w in wm if w.startswith("w")]
+    exp = ev.EvaluationExperiments(ex)
+    os.makedirs("/tmp/lrpx_ref/abl", exist_ok=True)
+    with quiet():
+        exp.ablation_experiment({"image_path": "/tmp/lrpx_ref/synthetic.jpg"}, "lrp", "/tmp/lrpx_ref/abl", do_attention=False)
+    toks = ex.beam_caption_encode
+    T = len(toks) - 1
+    disappear = np.zeros(T, dtype=np.int64)
+    img_diff = np.full(T, np.nan)
+    for t, w in exp.image_disappear_count:
+        disappear[int(t)] = 1
+    for t, w, d in exp.image_category_score_diff:
+        img_diff[int(t)] = d
+    word_diff = np.full(T, np.nan)
+    for t, ds in exp.category_scores_diff.items():
+        word_diff[int(t)] = ds[0]
+    assert not exp.stop_word_scores_diff
+    # tpfp_experiment (evaluation.py:450-573) on the same image: every synthetic word is "frequent"; the reference
+    # captions contain the caption's last word but not its first, so both a TP and an FP branch are taken
+    ref_caps = [[wm["<start>"], toks[-1], 7, wm["<end>"]], [wm["<start>"], 9, toks[-1], wm["<end>"], wm["<pad>"]]]
+    with quiet():
+        exp.tpfp_experiment({"image_path": "/tmp/lrpx_ref/synthetic.jpg", "encoded_all_caps": [list(c) for c in ref_caps]},
+                            "lrp", "/tmp/lrpx_ref/abl", [w for w in wm if w.startswith("w")], do_attention=False)
+    assert ex.beam_caption_encode == toks
+    stat = lambda rows, k: np.array([float(r[k]) for r in rows])
+    quant = lambda rows: np.array([[float(v) for v in r["quantile"]] for r in rows])
+    tp, fp = exp.TP_statistics, exp.FP_statistics
+    tpfp = dict(ref_caps_0=np.array(ref_caps[0]), ref_caps_1=np.array(ref_caps[1]),
+                tp_words=np.array([wm[r["word"]] for r in tp]), fp_words=np.array([wm[r["word"]] for r in fp]),
+                tp_beta=np.array([float(r["1-beta"]) for r in exp.TP_statistics_beta]),
+                fp_beta=np.array([float(r["1-beta"]) for r in exp.FP_statistics_beta]))
+    for k in ("mean", "mean_abs", "mean_pos", "max"):
+        tpfp["tp_" + k], tpfp["fp_" + k] = stat(tp, k), stat(fp, k)
+    tpfp["tp_quantile"], tpfp["fp_quantile"] = quant(tp), quant(fp)
+    save("ablation_e2e", seed=np.array(seed), V=np.array(V), H=np.array(H), E=np.array(E), tokens=np.array(toks),
+         disappear=disappear, img_diff=img_diff, word_diff=word_diff, predictions=ex.predictions.detach(), **tpfp)
+    print("tpfp:", len(tp), "TP words,", len(fp), "FP words")
+    print("ablation fixture:", toks, disappear.tolist(), img_diff.tolist(), word_diff.tolist())
+
+
 def _rev_word_map(V, stop):
     wm = synth.word_map(V)
     rev = {v: k for k, v in wm.items()}
@@ -443,7 +505,8 @@ def main():
     torch.manual_seed(0)
     only = set(sys.argv[1:])          # optional: names of the generators to (re)run
     for fn in (golden_rules, golden_sequential_small, golden_vgg16, golden_resnet, golden_gridtd_decoder,
-               golden_aoa_decoder, golden_adaptive_decoder, golden_block_image, golden_lrp_weights, golden_tune, golden_tune_bu):
+               golden_aoa_decoder, golden_adaptive_decoder, golden_block_image, golden_lrp_weights, golden_tune, golden_tune_bu,
+               golden_ablation):
         if only and fn.__name__ not in only:
             continue
         print(fn.__name__)

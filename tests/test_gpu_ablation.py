@@ -8,6 +8,7 @@ import torch
 
 import lrp_oracle as O
 import synth
+from conftest import assert_close
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -158,3 +159,100 @@ def test_batched_ablation_equals_per_request_walk(tmp_path):
         new_scores = ex.teacherforce_forward(imgs[b:b + 1], [int(v) for v in deleted])
         want = torch.softmax(pred[b, t], -1)[word] - torch.softmax(new_scores[-1], -1)[word]
         assert abs(float(diff[n]) - float(want)) <= 1e-3 * abs(float(want)) + 1e-6, (q, diff[n], want)
+
+
+def test_ablation_experiment_end_to_end_vs_reference_fixture(golden, tmp_path):
+    """evaluation.py:82-290 END TO END against the reference itself (fixture ablation_e2e: the reference's own
+    ablation_experiment on a seeded random gridTD / VGG16 model, caption search capped at 9 words, every word a category
+    word): explain_caption with the reference's Q1 accumulation, image ablation of the words t >= 1 (mask of the 20 most
+    relevant patches of the ACCUMULATED heat-map, beam search on the masked image, teacher-forced score drop) and word
+    ablation of the words t >= 6.  fp32-accurate mode; the caption, the disappear flags and the score drops must come
+    out as the reference's (scores are softmax values ~1/60: drops of ~3e-4 compared at 5e-6 absolute)."""
+    import numpy as np
+    from models import gridTDmodel as G
+    from lrpx.ablation import AblationExperiments
+    g = golden("ablation_e2e")
+    V, H, E, seed = int(g["V"]), int(g["H"]), int(g["E"]), int(g["seed"])
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(seed, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(seed + 1))
+    model.to(DEV).eval()
+    wm = synth.word_map(V)
+    args = argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                              save_path=str(tmp_path), dataset="syn", weight="")
+    ex = G.ExplainGridTDAttention(args, wm, model=model, precision="fp32")
+    img = synth.images(seed + 2, 1).to(DEV)
+    ex.preprocess_img = lambda p: img
+    # the explainer's own caption search is beam 2 / max 50 (gridTDmodel.py:935); the fixture capped the reference at 9
+    find = ex._find_caption
+    ex._find_caption = lambda path, beam_size, max_cap_length: find(path, beam_size, 9)
+    heat_l, words_l = ex.explain_caption("synthetic.jpg")               # Q1: running sums, like the reference
+    toks = ex.beam_caption_encode
+    assert toks == g["tokens"].tolist(), (toks, g["tokens"].tolist())
+    T = len(toks) - 1
+    assert_close(ex.predictions, g["predictions"], rtol=1e-3, atol=1e-4, what="explainer predictions")
+    heat = torch.cat(heat_l)
+    tokens = torch.tensor([toks], device=DEV)
+    pred = ex.predictions.unsqueeze(0)
+    ab = AblationExperiments(ex)
+    ts = list(range(1, T))
+    req_img = torch.zeros(len(ts), dtype=torch.int32, device=DEV)
+    req_t = torch.tensor(ts, dtype=torch.int32, device=DEV)
+    out = ab.image_ablation(img, tokens, heat[1:], req_img, req_t, pred, beam_size=3, max_cap_length=9)
+    want_gone, want_diff = g["disappear"].numpy(), g["img_diff"].numpy()
+    for n, t in enumerate(ts):
+        assert bool(out["disappear"][n]) == bool(want_gone[t]), (t, out["captions"][n])
+        if not want_gone[t]:
+            assert abs(float(out["score_diff"][n]) - want_diff[t]) <= 5e-6, (t, float(out["score_diff"][n]), want_diff[t])
+    # word ablation from word 6 on
+    ts6 = [t for t in range(6, T)]
+    r_words = torch.zeros(len(ts6), T, device=DEV)
+    for n, t in enumerate(ts6):
+        r_words[n, :t + 1] = words_l[t]
+    feat = ex._state["feat"]
+    diff = ab.word_ablation(feat, tokens, r_words, torch.zeros(len(ts6), dtype=torch.int32, device=DEV),
+                            torch.tensor(ts6, dtype=torch.int32, device=DEV), pred)
+    want_w = g["word_diff"].numpy()
+    for n, t in enumerate(ts6):
+        assert abs(float(diff[n]) - want_w[t]) <= 5e-6, (t, float(diff[n]), want_w[t])
+    print("image ablation drops", [float(v) for v in out["score_diff"]], "word ablation drops", [float(v) for v in diff])
+
+
+def test_tpfp_experiment_end_to_end_vs_reference_fixture(golden, tmp_path):
+    """evaluation.py:450-573 END TO END against the reference (same fixture): which caption words are true / false
+    positives against the reference captions, and per word the statistics of the channel-mean of its (Q1-accumulated)
+    heat-map — mean, mean |.|, mean of the positive part, max, the 100 quantiles — plus 1 - beta of the sentinel gate.
+    fp32-accurate chain: statistics within 2e-3 relative (+1e-4 of the largest quantile)."""
+    from models import gridTDmodel as G
+    from lrpx.ablation import AblationExperiments
+    g = golden("ablation_e2e")
+    V, H, E, seed = int(g["V"]), int(g["H"]), int(g["E"]), int(g["seed"])
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(seed, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(seed + 1))
+    model.to(DEV).eval()
+    wm = synth.word_map(V)
+    args = argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                              save_path=str(tmp_path), dataset="syn", weight="")
+    ex = G.ExplainGridTDAttention(args, wm, model=model, precision="fp32")
+    img = synth.images(seed + 2, 1).to(DEV)
+    ex.preprocess_img = lambda p: img
+    find = ex._find_caption
+    ex._find_caption = lambda path, beam_size, max_cap_length: find(path, beam_size, 9)
+    heat_l, _ = ex.explain_caption("synthetic.jpg")
+    toks = ex.beam_caption_encode
+    assert toks == g["tokens"].tolist()
+    frequent = [i for w, i in wm.items() if w.startswith("w")]
+    special = [wm[k] for k in ("<start>", "<pad>", "<end>", "<unk>")]
+    tp, fp = AblationExperiments.tpfp_split(toks, frequent, [g["ref_caps_0"].tolist(), g["ref_caps_1"].tolist()], special)
+    assert [toks[t + 1] for t in tp] == g["tp_words"].tolist() and [toks[t + 1] for t in fp] == g["fp_words"].tolist()
+    assert tp and fp
+    heat = torch.cat(heat_l)
+    for name, ts in (("tp", tp), ("fp", fp)):
+        st = AblationExperiments.tpfp_statistics(heat[torch.tensor(ts, device=DEV)])
+        scale = float(g[name + "_quantile"].abs().max())
+        for k in ("mean", "mean_abs", "mean_pos", "max"):
+            assert_close(st[k], g[name + "_" + k], rtol=2e-3, atol=1e-4 * scale, what=f"{name} {k}")
+        assert_close(st["quantile"], g[name + "_quantile"], rtol=2e-3, atol=1e-4 * scale, what=f"{name} quantiles")
+        one_minus_beta = 1 - ex.betas[torch.tensor(ts, device=DEV)]
+        assert_close(one_minus_beta, g[name + "_beta"], rtol=1e-4, atol=1e-5, what=f"{name} 1-beta")

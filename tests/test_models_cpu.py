@@ -295,3 +295,18 @@ def test_heatmap_postprocessing_matches_reference_fixture(golden):
     assert hm.shape == (1, 16, 16, 3) and hm.dtype == np.float32
     gm = U.graymap(np.stack([x[0]] * 3, -1)[None])
     assert np.allclose(gm[..., 0], gm[..., 1]) and np.allclose(gm[..., 1], gm[..., 2])
+
+
+def test_tpfp_split_host_logic(golden):
+    """lrpx.ablation.AblationExperiments.tpfp_split (evaluation.py:462-481,:516) against the reference's own TP / FP
+    filing recorded in fixture ablation_e2e."""
+    from lrpx.ablation import AblationExperiments
+    g = golden("ablation_e2e")
+    V = int(g["V"])
+    wm = synth.word_map(V)
+    toks = g["tokens"].tolist()
+    frequent = [i for w, i in wm.items() if w.startswith("w")]
+    special = [wm[k] for k in ("<start>", "<pad>", "<end>", "<unk>")]
+    tp, fp = AblationExperiments.tpfp_split(toks, frequent, [g["ref_caps_0"].tolist(), g["ref_caps_1"].tolist()], special)
+    assert [toks[t + 1] for t in tp] == g["tp_words"].tolist() and [toks[t + 1] for t in fp] == g["fp_words"].tolist()
+    assert AblationExperiments.tpfp_split(toks, [], [toks], special) == ([], [])
