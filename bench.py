@@ -56,6 +56,8 @@ def parse(argv=None):
     ap.add_argument("--precision", default=None, choices=["bf16", "fp32"],
                     help="default: bf16 (config 5: fp32 — the fixed encoder's features at fp32 accuracy)")
     ap.add_argument("--deliver", default="full", choices=["full", "channel_mean", "fp16"])
+    ap.add_argument("--encoder", default="vgg16", choices=["vgg16", "resnet101"],
+                    help="config 2: the image encoder (resnet101: 7x7 grid of 2048-d features, bf16 chain of lrpx.tc_resnet)")
     ap.add_argument("--images", type=int, default=0, help="images (config 2/4: requests) per GPU per step; 0 = the config's size")
     ap.add_argument("--words", type=int, default=19, help="caption words per image (random-init captions run to max length)")
     ap.add_argument("--vocab", type=int, default=10000)
@@ -229,13 +231,25 @@ def build_problem(args, device, seed):
     from models import gridTDmodel as G
     V, H, E = args.vocab, 512, 512
     torch.manual_seed(seed)
-    model = G.GridTDModel(E, H, V, "vgg16")
-    model.load_state_dict(synth.gridtd_decoder_state(1000 + seed, V, H, E), strict=False)
-    model.img_encoder.encoder.load_state_dict(synth.vgg_state(2000 + seed))
+    enc = getattr(args, "encoder", "vgg16")
+    if enc == "resnet101":
+        model = G.GridTDModel(E, H, V, "resnet101", n_pixel=49)
+        model.load_state_dict(synth.gridtd_decoder_state(1000 + seed, V, H, E, C=2048, n_pixel=49), strict=False)
+        g = torch.Generator().manual_seed(2000 + seed)
+        for m in model.img_encoder.encoder.modules():            # kaiming-normal convs (constructor) + non-trivial BatchNorm statistics
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+    else:
+        model = G.GridTDModel(E, H, V, "vgg16")
+        model.load_state_dict(synth.gridtd_decoder_state(1000 + seed, V, H, E), strict=False)
+        model.img_encoder.encoder.load_state_dict(synth.vgg_state(2000 + seed))
     if device is not None:
         model.to(device)
     model.eval()
-    ns = ap.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+    ns = ap.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder=enc, height=224, width=224,
                       save_path="/tmp/lrpx_bench", dataset="syn", weight="")
     ex = G.ExplainGridTDAttention(ns, synth.word_map(V), model=model, precision=getattr(args, "precision", "bf16"))
     imgs, toks = problem_inputs(args, seed)
@@ -357,6 +371,36 @@ def parity_config2(args, ex, eng, W, imgs_d, toks_d, heat, r_words, ref_out, T):
                                 f"the {T} requests of image 0 (alpha=1/beta=0 without bias conserves up to the relevance "
                                 "dropped where z+ == 0 or a pooled maximum is 0)")
     return out
+
+
+def parity_resnet(args, model, ex, eng, W, imgs_d, toks_d, T):
+    """ResNet101 variant of config 2: the encoder chain of the timed path against the oracle's restatement of the
+    reference's ResNet rules (lrp_modules.py:197-280, fp64 on the host) for two requests of image 0, with the
+    product decoder's own feature relevance as the target (the decoder kernels are pinned by the VGG variant)."""
+    from lrpx import ops
+    O = _oracle()
+    est = eng.forward(imgs_d[:1])
+    feat = eng.features(est, "pixel")
+    st = ex.explainer_forward(feat, toks_d[:1])
+    ts = torch.tensor([0, T - 1], dtype=torch.int32, device=feat.device)
+    r_feat, _ = ops.gridtd_decoder_lrp(st, W, torch.zeros_like(ts), ts, toks_d[0, 1:][ts.long()].to(torch.int32),
+                                       tc_gemm=True)
+    heat = eng.relevance(est, r_feat, torch.zeros_like(ts))
+    sd = {k: (v.detach().cpu().double() if v.is_floating_point() else v.detach().cpu())
+          for k, v in model.img_encoder.encoder.state_dict().items()}
+    fh, fw = est.feat_hw
+    t0 = time.perf_counter()
+    tgt = r_feat.cpu().double().transpose(1, 2).reshape(2, -1, fh, fw)
+    ref = O.resnet_lrp(sd, imgs_d[:1].cpu().double().expand(2, -1, -1, -1), tgt)
+    dt = time.perf_counter() - t0
+    a = heat.cpu().double()
+    par = {"requests_checked": 2, "against": "oracle port (fp64) of the ResNet rules, same feature relevance in",
+           "heatmap_spearman_min": min(spearman(a[i], ref[i]) for i in range(2)),
+           "heatmap_rel_l2_max": max(float((a[i] - ref[i]).norm() / ref[i].norm()) for i in range(2)),
+           "conservation_sum_rin_over_sum_rout": [float(a[i].sum() / tgt[i].sum()) for i in range(2)]}
+    cb = {"value": 2 / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+          "sample": f"2 requests, ResNet101 encoder relevance only (oracle port, fp64 torch-CPU), {dt:.2f} s"}
+    return cb, par
 
 
 def run_config2(args, ctx, brief=False):
@@ -520,12 +564,21 @@ def run_config2(args, ctx, brief=False):
                          "reference_formulation_gflop_per_explanation": 2.0 * flops_alg / 1e9},
         }
         out["breakdown_ms"] = phase_ms
-        if not brief:
+        is_resnet = getattr(args, "encoder", "vgg16") == "resnet101"
+        if is_resnet:
+            out["config"]["workload"] = out["config"]["workload"].replace("gridTD VGG16", "gridTD ResNet101 (7x7 x 2048 features)")
+            out["roofline"]["kernel"] = "tc_conv_kernel / tc_conv_slab_kernel <MULX> (ResNet101 relevance chain, ~100 GEMMs)"
+        if not brief and not is_resnet:
             try:
                 out["roofline"]["layers"] = layer_table(eng, args.chunk, dev, pk, requests=Q)
             except Exception as e:  # never lose the bench line to the per-layer microbenchmark
                 out["roofline"]["layers_error"] = repr(e)
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and is_resnet:
+            try:
+                out["cpu_baseline"], out["parity"] = parity_resnet(args, model, ex, eng, W, imgs_d, toks_d, T)
+            except Exception as e:
+                out["parity"] = {"error": repr(e)}
+        elif not args.no_cpu_baseline and world == 1:
             nimg = 1 if brief else max(1, args.cpu_images)
             nwords = max(1, min(args.cpu_words, T)) if not brief else min(4, T)
             cb, ref_out = cpu_config2(args, 0, nimg, nwords, keep=True)
@@ -1077,6 +1130,7 @@ def run_ours(args):
     if out is not None and args.also and ctx.world == 1:
         also = {}
         for name, cfg, extra in (("config2_fp32_accurate", 2, dict(precision="fp32", steps=4)),
+                                 ("config2_resnet101", 2, dict(encoder="resnet101", precision="bf16", steps=4)),
                                  ("config3", 3, dict(steps=8)), ("config4", 4, dict(steps=4)),
                                  ("config4_fp32_accurate", 4, dict(precision="fp32", steps=2, images=128)),
                                  ("config5", 5, dict(steps=4, precision="fp32")),

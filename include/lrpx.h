@@ -536,7 +536,8 @@ typedef struct {
   void* out5;           /* FWDX: act * out3                                                        */
   int add_pitch;
   int fwd_flags;        /* FWDX: bit 0 = no ReLU (downsample branch), bit 1 = keep the even pixels only and store
-                         * them into a PF tensor of half the resolution (stride-2 convolution)            */
+                         * them into a PF tensor of half the resolution (stride-2 convolution);
+                         * STORE_F32: bit 2 = store bf16 (rows of ncol bf16) instead of fp32              */
   int out_pitch;        /* STORE_F32: floats per row of `out` (0 = ncol) and                                */
   int n_valid;          /*            the columns that exist (<= ncol; the weight rows beyond are padding);
                          *            `bias` (n_valid floats) is added when given                           */
@@ -623,6 +624,9 @@ int lrpx_tc_subsample2_bf16(const void* src, void* dst, int n, int h, int w, int
  * (lrpx_tc_conv, STORE_F32):  heat = x+ * sum P[..][0][c] + x- * sum P[..][1][c];  mode as LRPX_TC_EPI_INPUT3's. */
 int lrpx_tc_stem_col2im_f32(const float* P, int ldp, const float* x, const int32_t* row_img, void* out, int n_expl, int h,
                             int w, int mode, void* stream);
+/* the same with P stored as bf16 (lrpx_tc_conv STORE_F32 with fwd_flags bit 2): half the bytes of the intermediate */
+int lrpx_tc_stem_col2im_bf16(const void* P, int ldp, const float* x, const int32_t* row_img, void* out, int n_expl, int h,
+                             int w, int mode, void* stream);
 /* lrpx_tc_pf_to_dense_f32 for hi|lo rows of 2*c channels (value = hi + lo) */
 int lrpx_tc_pf_split_to_dense_f32(const void* src, float* dst, int n, int h, int w, int c, int layout, void* stream);
 

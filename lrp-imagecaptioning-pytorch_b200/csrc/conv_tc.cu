@@ -877,7 +877,17 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
     TMEM_LD_X32(taddr + c, v);
     tmem_ld_wait();
     epi_release(release_bar);
-    if (r.in_range) {
+    if (r.in_range && (p.fwd_flags & 4)) {
+      // bf16 output (fwd_flags bit 2): halves the bytes of a GEMM whose result is only an intermediate (ResNet stem)
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * p.out_c + n0 + c;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = pack_bf16(__uint_as_float(v[16 * q + 2 * k]), __uint_as_float(v[16 * q + 2 * k + 1]));
+        stg_v8(dst + 16 * q, w);
+      }
+    } else if (r.in_range) {
       // out_c = row pitch, n_valid = columns that exist (a multiple of 4; the tile may be padded beyond it); the bias
       // (one value per column) turns the plain GEMM into a Linear layer
       const int col0 = n0 + c;

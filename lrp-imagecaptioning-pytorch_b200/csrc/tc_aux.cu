@@ -714,7 +714,8 @@ __global__ void subsample2_pf_kernel(const uint4* __restrict__ src, uint4* __res
 // (tap = ky*7+kx, s = 0: W+, 1: W-) for every output pixel q = (y,x) of conv1; the image relevance gathers
 //   heat[e][c][i][j] = x+ * sum P[(y,x)][tap][0][c] + x- * sum P[(y,x)][tap][1][c]   over 2y-3+ky = i, 2x-3+kx = j
 // (lrp_modules.py:81-84, utils.py:26-30 for the stride-2 convolution).  mode: 0 fp32 (n,3,h,w), 1 channel mean, 2 fp16.
-__global__ void stem_col2im_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ x,
+template <bool PBF16>
+__global__ void stem_col2im_kernel(const void* __restrict__ Pv, int ldp, const float* __restrict__ x,
                                    const int32_t* __restrict__ row_img, void* __restrict__ out, int nq, int h, int w, int mode) {
   const int ho = h / 2, wo = w / 2, wp1 = wo + 1, blk = (ho + 1) * wp1;
   const long long total = (long long)nq * h * w;
@@ -729,10 +730,17 @@ __global__ void stem_col2im_kernel(const float* __restrict__ P, int ldp, const f
       for (int kx = (j + 3) & 1; kx < 7; kx += 2) {
         const int xx = (j + 3 - kx) >> 1;
         if (xx < 0 || xx >= wo) continue;
-        const float* pr = P + ((size_t)e * blk + (size_t)(y + 1) * wp1 + (xx + 1)) * ldp + (ky * 7 + kx) * 6;
-        const float2 p0 = *reinterpret_cast<const float2*>(pr), p1 = *reinterpret_cast<const float2*>(pr + 2),
-                     p2 = *reinterpret_cast<const float2*>(pr + 4);
-        cp[0] += p0.x; cp[1] += p0.y; cp[2] += p1.x; cn[0] += p1.y; cn[1] += p2.x; cn[2] += p2.y;
+        const size_t po = ((size_t)e * blk + (size_t)(y + 1) * wp1 + (xx + 1)) * ldp + (ky * 7 + kx) * 6;
+        if (PBF16) {
+          const uint32_t* pr = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(Pv) + po);
+          const uint32_t a = pr[0], b = pr[1], c = pr[2];
+          cp[0] += bf_lo(a); cp[1] += bf_hi(a); cp[2] += bf_lo(b); cn[0] += bf_hi(b); cn[1] += bf_lo(c); cn[2] += bf_hi(c);
+        } else {
+          const float* pr = reinterpret_cast<const float*>(Pv) + po;
+          const float2 p0 = *reinterpret_cast<const float2*>(pr), p1 = *reinterpret_cast<const float2*>(pr + 2),
+                       p2 = *reinterpret_cast<const float2*>(pr + 4);
+          cp[0] += p0.x; cp[1] += p0.y; cp[2] += p1.x; cn[0] += p1.y; cn[1] += p2.x; cn[2] += p2.y;
+        }
       }
     }
     const size_t hw = (size_t)h * w, pix = (size_t)i * w + j;
@@ -820,7 +828,17 @@ int lrpx_tc_stem_col2im_f32(const float* P, int ldp, const float* x, const int32
   LRPX_CHECK_ARG(P && x && out && n_expl > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && ldp >= 294 && ldp % 2 == 0 &&
                      mode >= 0 && mode <= 2, "bad argument");
   long long total = (long long)n_expl * h * w;
-  stem_col2im_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(P, ldp, x, row_img, out, n_expl, h, w, mode);
+  stem_col2im_kernel<false><<<grid_for(total), 256, 0, as_stream(stream)>>>(P, ldp, x, row_img, out, n_expl, h, w, mode);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+int lrpx_tc_stem_col2im_bf16(const void* P, int ldp, const float* x, const int32_t* row_img, void* out, int n_expl, int h,
+                             int w, int mode, void* stream) {
+  LRPX_CHECK_ARG(P && x && out && n_expl > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && ldp >= 294 && ldp % 2 == 0 &&
+                     mode >= 0 && mode <= 2, "bad argument");
+  long long total = (long long)n_expl * h * w;
+  stem_col2im_kernel<true><<<grid_for(total), 256, 0, as_stream(stream)>>>(P, ldp, x, row_img, out, n_expl, h, w, mode);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;
 }

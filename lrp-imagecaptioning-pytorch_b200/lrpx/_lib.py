@@ -167,6 +167,7 @@ SYMBOLS = {
     "lrpx_tc_unpool3s2_bf16": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "lrpx_tc_subsample2_bf16": (_i, [_P, _P, _i, _i, _i, _i, _P]),
     "lrpx_tc_stem_col2im_f32": (_i, [_P, _i, _P, _P, _P, _i, _i, _i, _i, _P]),
+    "lrpx_tc_stem_col2im_bf16": (_i, [_P, _i, _P, _P, _P, _i, _i, _i, _i, _P]),
 }
 
 _lib = None

@@ -266,10 +266,11 @@ class TcResNetEngine:
                 A = torch.empty(pf_rows(nq, h, w), 64, device=dev, dtype=torch.bfloat16)
                 check(lib().lrpx_tc_unpool3s2_bf16(_ptr(r0), _ptr(st.stem["idx"]), _ptr(st.stem["G"]), _ptr(rimg), _ptr(A), nq,
                                                    h, w, 64, _stream()), "lrpx_tc_unpool3s2_bf16")
-                P = torch.empty(pf_rows(nq, h, w), 320, device=dev, dtype=torch.float32)
-                tc_conv(A, self.stem_w_rel, nq, h, w, 64, 320, 1, EPI_STORE_F32, P)
-                check(lib().lrpx_tc_stem_col2im_f32(_ptr(P), 320, _ptr(st.x), _ptr(rimg), _ptr(out[q0:q1]), nq, H, W,
-                                                    self.DELIVER[deliver], _stream()), "lrpx_tc_stem_col2im_f32")
+                # P (one row of 49 taps x 6 per stem output pixel) is an intermediate: bf16 halves its 2 x 2.1 GB per chunk
+                P = torch.empty(pf_rows(nq, h, w), 320, device=dev, dtype=torch.bfloat16)
+                tc_conv(A, self.stem_w_rel, nq, h, w, 64, 320, 1, EPI_STORE_F32, P, fwd_flags=4)
+                check(lib().lrpx_tc_stem_col2im_bf16(_ptr(P), 320, _ptr(st.x), _ptr(rimg), _ptr(out[q0:q1]), nq, H, W,
+                                                     self.DELIVER[deliver], _stream()), "lrpx_tc_stem_col2im_bf16")
                 del A, P
                 if on_chunk is not None:
                     on_chunk(q0, q1)

@@ -232,7 +232,7 @@ def test_compute_lrp_and_explainer_route_resnets_to_the_chain(golden, tmp_path):
     r32 = net.compute_lrp(x.clone(), target=tgt)
     before = dict(_lib.CALLS)
     r16 = net.compute_lrp(x.clone(), target=tgt, precision="bf16")
-    assert _lib.CALLS.get("lrpx_tc_stem_col2im_f32", 0) > before.get("lrpx_tc_stem_col2im_f32", 0)
+    assert _lib.CALLS.get("lrpx_tc_stem_col2im_bf16", 0) > before.get("lrpx_tc_stem_col2im_bf16", 0)
     l2, sp = _report("compute_lrp bf16 vs simt", r16, r32)
     assert sp >= 0.99 and l2 <= 6e-2
     from models import gridTDmodel as G
