@@ -351,8 +351,7 @@ def parity_config2(args, ex, eng, W, imgs_d, toks_d, heat, r_words, ref_out, T):
     feat = eng.features(est, "pixel")
     st = ex.explainer_forward(feat, toks_d[:1])
     ts = torch.arange(T, dtype=torch.int32, device=feat.device)
-    r_feat, rw = ops.gridtd_decoder_lrp(st, W, torch.zeros_like(ts), ts, toks_d[0, 1:].to(torch.int32),
-                                        tc_gemm=(ex.precision == "bf16"))
+    r_feat, rw = ops.gridtd_decoder_lrp(st, W, torch.zeros_like(ts), ts, toks_d[0, 1:].to(torch.int32), tc_gemm=True)
     fmap = feat[0].t().reshape(512, 14, 14).cpu()
     ost = O.gridtd_explainer_forward(p, fmap, toks_d[0].tolist())
     dmax, wmax = 0.0, 0.0
@@ -428,7 +427,7 @@ def run_config2(args, ctx, brief=False):
     words_h = torch.empty(Q, T, dtype=torch.float32).pin_memory()
     imgs_d, toks_d = imgs_h.to(dev), toks_h.to(dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    tc_gemm = ex.precision == "bf16"
+    tc_gemm = True                    # decoder GEMMs as bf16x3 on tensor cores in both chain modes (BatchExplainer's default)
     pipe = BatchExplainer(ex, chunk=args.chunk, use_graph=not args.no_graph, tc_gemm=tc_gemm)
     pipe_e2e = pipe if deliver == "full" else BatchExplainer(ex, chunk=args.chunk, use_graph=not args.no_graph,
                                                              tc_gemm=tc_gemm, deliver=deliver)

@@ -100,6 +100,8 @@ struct TcParams {
   void* out5;        // FWDX: act * (identity-branch gain)
   int fwd_flags;     // FWDX: bit 0 = no ReLU, bit 1 = store only the even pixels into a half-resolution PF tensor
   int n_valid;       // STORE_F32: columns that exist in `out` (<= ncol)
+  int pair;          // CTA pairs issue ONE tcgen05.mma.cta_group::2 (M = 256 = 128 rows of each CTA, each CTA holding bn/2
+                     // rows of every B tile in its own shared memory): halves the B operand reads per SM
   const float* bias;
   const __nv_bfloat16* gain;
   const int32_t* row_img;
@@ -190,6 +192,33 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// ---- 2-SM (cta_group::2) forms
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// TMA tile load into THIS CTA's shared memory that signals the mbarrier `bar` (a shared::cluster address: the leader's)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {      // arrives on `bar` at the same offset in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -254,8 +283,8 @@ constexpr uint32_t TC_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t desc_pack(uint32_t lo) { return ((uint64_t)TC_DESC_HI << 32) | (uint64_t)lo; }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
-__device__ __forceinline__ uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int bn, int m = TC_BM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 #define TMEM_LD_X32(taddr, v)                                                                                   \
@@ -503,11 +532,19 @@ __device__ __forceinline__ void epi_input(const TcParams& p, const RowInfo& r, c
 // soon as this warp's last TMEM read has landed in registers, i.e. before the epilogue math and the global stores —
 // the stores are the slow part of the epilogue (measured: 8-22 % of a layer's time) and must not sit on the
 // TMEM hand-over path.
-__device__ __forceinline__ void epi_release(uint32_t release_bar) {
+// pair mode (tcgen05.mma.cta_group::2): the accumulators of BOTH CTAs are written by the leader's MMAs, so the peer's
+// epilogue warps hand their buffer back on the LEADER's barrier (release_bar is then a shared::cluster address)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_release(const TcParams& p, uint32_t release_bar) {
   if (release_bar) {
     tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(release_bar);
+    if ((threadIdx.x & 31) == 0) {
+      if (p.pair) mbar_arrive_cluster(release_bar);
+      else mbar_arrive(release_bar);
+    }
   }
 }
 
@@ -540,7 +577,7 @@ __device__ __forceinline__ void epi_input3(const TcParams& p, const RowInfo& r, 
     TMEM_LD_X8(taddr + 16, v8);
   }
   tmem_ld_wait();
-  epi_release(release_bar);
+  epi_release(p, release_bar);
   float up[6], dn[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
@@ -634,7 +671,7 @@ __device__ __forceinline__ void epi_mulx(const TcParams& p, const RowInfo& r, ui
     uint32_t v[16];
     TMEM_LD_X16(taddr + c + 16 * q, v);
     tmem_ld_wait();
-    if (q == 1) epi_release(release_bar);
+    if (q == 1) epi_release(p, release_bar);
     if (!r.in_range) continue;
 #pragma unroll 1
     for (int j = 0; j < G; ++j) {
@@ -753,7 +790,7 @@ __device__ __forceinline__ void epi_fwdx(const TcParams& p, const RowInfo& r, ui
     if (p.n_acc >= 2) TMEM_LD_X16(taddr + p.half + c + 16 * q, vp);
     if (p.n_acc >= 3) TMEM_LD_X16(taddr + 2 * p.half + c + 16 * q, vn);
     tmem_ld_wait();
-    if (q == 1) epi_release(release_bar);
+    if (q == 1) epi_release(p, release_bar);
     if (!store) continue;
     float bv[16], sw[16];
 #pragma unroll
@@ -844,7 +881,7 @@ template <int EPI>
 __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, uint32_t taddr, int n_tile, int c,
                                          uint32_t release_bar, uint32_t stage = 0, const CUtensorMap* tmo = nullptr,
                                          float* scratch = nullptr, int quarter = 0, int bar_id = 0) {
-  if (p.debug_flags & 16) { epi_release(release_bar); return; }      // timing experiment: only hands the accumulator back
+  if (p.debug_flags & 16) { epi_release(p, release_bar); return; }      // timing experiment: only hands the accumulator back
   RowInfo r = r0;
   if (p.debug_flags & 1) { r.in_range = false; r.valid = false; }
   const int n0 = n_tile * p.bn;
@@ -860,7 +897,7 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
     uint32_t v[16];
     TMEM_LD_X16(taddr, v);
     tmem_ld_wait();
-    epi_release(release_bar);
+    epi_release(p, release_bar);
     epi_input(p, r, v);
   } else if (EPI == LRPX_TC_EPI_FWD_GAIN) {
 #pragma unroll
@@ -869,14 +906,14 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
       TMEM_LD_X16(taddr + c + 16 * q, vw);
       TMEM_LD_X16(taddr + p.half + c + 16 * q, vp);
       tmem_ld_wait();
-      if (q == 1) epi_release(release_bar);
+      if (q == 1) epi_release(p, release_bar);
       epi_fwd_gain16(p, r, n_tile * p.half + c + 16 * q, vw, vp);
     }
   } else if (EPI == LRPX_TC_EPI_STORE_F32) {
     uint32_t v[32];
     TMEM_LD_X32(taddr + c, v);
     tmem_ld_wait();
-    epi_release(release_bar);
+    epi_release(p, release_bar);
     if (r.in_range && (p.fwd_flags & 4)) {
       // bf16 output (fwd_flags bit 2): halves the bytes of a GEMM whose result is only an intermediate (ResNet stem)
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * p.out_c + n0 + c;
@@ -926,7 +963,7 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
       uint32_t v[16];
       TMEM_LD_X16(taddr + c + 16 * q, v);
       tmem_ld_wait();
-      if (q == 1) epi_release(release_bar);
+      if (q == 1) epi_release(p, release_bar);
       if (r.in_range) {
         float* dst = reinterpret_cast<float*>(p.out) + (size_t)r.row * p.out_c + n0 + c + 16 * q;
 #pragma unroll
@@ -965,7 +1002,7 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
       uint32_t v[32];
       TMEM_LD_X32(taddr + c, v);
       tmem_ld_wait();
-      epi_release(release_bar);
+      epi_release(p, release_bar);
       if (stage && !(p.debug_flags & 64)) epi_mul_tma(p, r, n0 + c, v, g, stage, tmo);
       else epi_mul(p, r, n0 + c, v, g);
     } else {
@@ -974,7 +1011,7 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
         uint32_t v[16];
         TMEM_LD_X16(taddr + c + 16 * q, v);
         tmem_ld_wait();
-        if (q == 1) epi_release(release_bar);
+        if (q == 1) epi_release(p, release_bar);
         epi_mul_unpool16(p, r, n0 + c + 16 * q, v, g[q], s4[q]);
       }
     }
@@ -1016,7 +1053,7 @@ __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_bas
     if (sub < 0 || sub >= 2) sub = n_units;          // not this warp's tile
   }
   if (sub >= n_units) {                 // nothing to read for this warp: hand the buffer back at once
-    epi_release(release_bar);
+    epi_release(p, release_bar);
     return;
   }
   int h_cached = -1;
@@ -1176,7 +1213,10 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& m_
 // so neither issuer can run more than one ring revolution ahead of the other (mbarrier parity waits are only
 // unambiguous one phase apart — giving the issuers alternate TILES on a shared ring is not safe).
 // With mh == 1 only issuer 0 works (N = 256 MMAs occupy the tensor pipe for 128 cycles, one thread keeps up).
-template <bool BRES, bool MODE3, int ISSUER>
+// PAIR: tcgen05.mma.cta_group::2 issued by the leader CTA of a pair for both (M = 256: this CTA's 128 rows and the same
+// rows of the peer's slab at the same shared-memory offset; B: each CTA holds bn/2 rows of every tile); every commit
+// arrives in both CTAs.
+template <bool BRES, bool MODE3, int ISSUER, bool PAIR>
 __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full,
                                               uint64_t* b_empty, uint64_t* bres_bar, uint64_t* tmem_full_bar,
                                               uint64_t* tmem_empty_bar, uint32_t a_base, uint32_t b_base,
@@ -1184,8 +1224,9 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
   // ISSUER is a template parameter (not a value derived from threadIdx) so that ptxas can prove every descriptor
   // warp-uniform and keep it in uniform registers
   constexpr int issuer = ISSUER;
-  const uint32_t idesc = make_idesc(p.bn);
-  const uint32_t b16 = ((uint32_t)p.bn * TC_BK * 2) >> 4;       // B tile size in 16-byte units
+  const uint32_t idesc = make_idesc(p.bn, PAIR ? 2 * TC_BM : TC_BM);
+  // B tile pitch in 16-byte units (pair mode: each CTA stores its half tile at a half-size pitch)
+  const uint32_t b16 = (((uint32_t)p.bn * TC_BK * 2) >> 4) >> (PAIR ? 1 : 0);
   const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
   const uint32_t row16 = (TC_BK * 2) >> 4;                        // one PF row of 64 channels, 16-byte units
   const uint32_t dy16 = MODE3 ? 0u : (uint32_t)p.wp1 * row16;      // MODE3: each filter row has its own slab (stage)
@@ -1237,27 +1278,36 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
           for (int h = h0; h < h1 && !skip_mma; ++h) {
             const uint32_t ah = a_lo + (uint32_t)(h - h0) * half16;
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k)
-              tc_mma_f16(d_tmem + (uint32_t)(h - h0) * bn, desc_pack(ah + 2 * k), desc_pack(b_lo + 2 * k), idesc,
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              if (PAIR)
+                tc_mma_f16_2sm(d_tmem + (uint32_t)(h - h0) * bn, desc_pack(ah + 2 * k), desc_pack(b_lo + 2 * k), idesc,
                                (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
+              else
+                tc_mma_f16(d_tmem + (uint32_t)(h - h0) * bn, desc_pack(ah + 2 * k), desc_pack(b_lo + 2 * k), idesc,
+                           (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
+            }
           }
           if (!BRES) {
-            if (p.cluster == 2) tc_commit_mc(smem_u32(&b_empty[bs]), (uint16_t)3);      // frees the stage in both CTAs
+            if (PAIR) tc_commit_2sm(smem_u32(&b_empty[bs]));
+            else if (p.cluster == 2) tc_commit_mc(smem_u32(&b_empty[bs]), (uint16_t)3);      // frees the stage in both CTAs
             else tc_commit(smem_u32(&b_empty[bs]));
             if (++bs == b_stages) { bs = 0; bph ^= 1; }
           }
         }
         if (MODE3) {
-          tc_commit(smem_u32(&a_empty[as]));
+          if (PAIR) tc_commit_2sm(smem_u32(&a_empty[as]));
+          else tc_commit(smem_u32(&a_empty[as]));
           if (++as == a_stages) { as = 0; aph ^= 1; }
         }
       }
       if (!MODE3) {
-        tc_commit(smem_u32(&a_empty[as]));
+        if (PAIR) tc_commit_2sm(smem_u32(&a_empty[as]));
+        else tc_commit(smem_u32(&a_empty[as]));
         if (++as == a_stages) { as = 0; aph ^= 1; }
       }
     }
-    tc_commit(smem_u32(&tmem_full_bar[buf]));
+    if (PAIR) tc_commit_2sm(smem_u32(&tmem_full_bar[buf]));
+    else tc_commit(smem_u32(&tmem_full_bar[buf]));
   }
 }
 
@@ -1272,8 +1322,14 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
 // B tiles stream through their own ring (kc-major, tap-minor) or, when the whole layer's B fits (<= 80 KB),
 // stay resident for the lifetime of the persistent CTA.  With mh == 2 every B tile feeds two 128-row MMAs.
 constexpr int TC_A_MAX_STAGES = 6;
+#ifndef LRPX_TC_PAIR_DEFAULT
+#define LRPX_TC_PAIR_DEFAULT true
+#endif
 
-template <int EPI>
+// PAIR is a template parameter, not p.pair: a kernel that CONTAINS cta_group::2 instructions can only be launched as a
+// cluster of CTA pairs (a plain launch of it fails with cudaErrorInvalidClusterSize, measured), so the pair-mode code lives
+// in its own instantiations.
+template <int EPI, bool PAIR = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
@@ -1310,28 +1366,39 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     for (int s = 0; s < p.b_stages; ++s) {
       mbar_init(smem_u32(&b_full[s]), 1);
-      mbar_init(smem_u32(&b_empty[s]), p.n_issuers * p.cluster);      // cluster: both CTAs' issuers release a B stage
+      // cluster (multicast B): both CTAs' issuers release a B stage; pair: only the leader's issuers commit (to both CTAs)
+      mbar_init(smem_u32(&b_empty[s]), PAIR ? p.n_issuers : p.n_issuers * p.cluster);
     }
     mbar_init(smem_u32(&bres_bar), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tmem_full_bar[b]), p.n_issuers);
-      mbar_init(smem_u32(&tmem_empty_bar[b]), TC_EPI_WARPS);
+      // pair: the leader's issuers wait for the epilogue warps of BOTH CTAs (the peer's arrive remotely)
+      mbar_init(smem_u32(&tmem_empty_bar[b]), PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
+  if (PAIR) cluster_sync_all();               // both CTAs are resident before the paired TMEM allocation
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (p.cluster == 2) cluster_sync_all();      // the peer's barriers exist before any multicast traffic or remote arrive
   const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
 
   if (warp == 0) {
     // ================================ A producer (one thread)
@@ -1350,6 +1417,15 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const uint32_t dst = a_base + (uint32_t)as * p.a_stage_bytes;
             if (p.debug_flags & 4) {          // timing experiment: no A traffic
               mbar_arrive(fb);
+            } else if (PAIR) {
+              // each CTA fetches its own slab into its own shared memory; both signal the LEADER's barrier, on which
+              // the leader expects the bytes of both
+              const uint32_t fbl = pair_rank ? mapa_u32(fb, 0) : fb;
+              if (!pair_rank) mbar_expect_tx(fb, 2 * a_tx);
+              const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
+              const int kca = (p.a_wrap && kc >= p.a_wrap) ? kc - p.a_wrap : kc;
+              tma_load_2d_2sm(dst, &tmA0, fbl, kca * TC_BK, row0);
+              if (p.box1_rows) tma_load_2d_2sm(dst + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fbl, kca * TC_BK, row0 + p.box0_rows);
             } else {
               mbar_expect_tx(fb, a_tx);
               const int row0 = (p.slab_mode == 1) ? m0 - p.wp1 - 1 : m0 + (j - 1) * p.wp1 - 1;
@@ -1365,12 +1441,40 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp == TC_BPROD_WARP) {
     // ================================ B producer (one thread)
     if (elect_one()) {
-      if (p.b_resident) {
+      if (p.b_resident && PAIR) {
+        // pair: this CTA keeps rows [rank*bn/2, +bn/2) of every B tile (half-size pitch); the leader's barrier counts both
+        const uint32_t bb = smem_u32(&bres_bar);
+        const uint32_t bbl = pair_rank ? mapa_u32(bb, 0) : bb;
+        const uint32_t hb = b_bytes >> 1;
+        if (!pair_rank) mbar_expect_tx(bb, (uint32_t)(p.taps * p.kc_per_tap) * b_bytes);
+        for (int tap = 0; tap < p.taps; ++tap)
+          for (int kc = 0; kc < p.kc_per_tap; ++kc)
+            tma_load_2d_2sm(b_base + (uint32_t)(tap * p.kc_per_tap + kc) * hb, &tmBh, bbl, tap * p.cin + kc * TC_BK,
+                            (int)pair_rank * (p.bn >> 1));
+      } else if (p.b_resident) {
         const uint32_t bb = smem_u32(&bres_bar);
         mbar_expect_tx(bb, (uint32_t)(p.taps * p.kc_per_tap) * b_bytes);
         for (int tap = 0; tap < p.taps; ++tap)
           for (int kc = 0; kc < p.kc_per_tap; ++kc)
             tma_load_2d(b_base + (uint32_t)(tap * p.kc_per_tap + kc) * b_bytes, &tmB, bb, tap * p.cin + kc * TC_BK, 0);
+      } else if (PAIR) {
+        int bs = 0;
+        uint32_t bph = 0;
+        const uint32_t hb = b_bytes >> 1;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          int m_tile_unused, n_tile;
+          tile_coords(p, tile, m_tile_unused, n_tile);
+          const int n0 = n_tile * p.bn;
+          for (int kc = 0; kc < p.kc_per_tap; ++kc)
+            for (int tap = 0; tap < p.taps; ++tap) {
+              mbar_wait_relaxed(smem_u32(&b_empty[bs]), bph ^ 1);
+              const uint32_t bb = smem_u32(&b_full[bs]);
+              const uint32_t bbl = pair_rank ? mapa_u32(bb, 0) : bb;
+              if (!pair_rank) mbar_expect_tx(bb, b_bytes);
+              tma_load_2d_2sm(b_base + (uint32_t)bs * hb, &tmBh, bbl, tap * p.cin + kc * TC_BK, n0 + (int)pair_rank * (p.bn >> 1));
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+            }
+        }
       } else {
         int bs = 0;
         uint32_t bph = 0;
@@ -1400,20 +1504,27 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp == 1 || warp == TC_MMA2_WARP) {
     // ================================ MMA issuers (one elected thread per issuer warp)
     const int issuer = warp == 1 ? 0 : 1;
-    if (issuer < p.n_issuers && elect_one()) {
-#define LRPX_SLAB_LOOP(BRES, MODE3)                                                                                   \
+    // pair mode: only the leader CTA issues (its MMAs run on both SMs)
+    if (issuer < p.n_issuers && pair_rank == 0 && elect_one()) {
+#define LRPX_SLAB_LOOP(BRES, MODE3, PAIR)                                                                             \
   do {                                                                                                                \
     if (issuer == 0)                                                                                                  \
-      slab_mma_loop<BRES, MODE3, 0>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar,    \
-                                    a_base, b_base, tmem_base, num_tiles);                                            \
+      slab_mma_loop<BRES, MODE3, 0, PAIR>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar,              \
+                                          tmem_empty_bar, a_base, b_base, tmem_base, num_tiles);                      \
     else                                                                                                              \
-      slab_mma_loop<BRES, MODE3, 1>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar, tmem_empty_bar,    \
-                                    a_base, b_base, tmem_base, num_tiles);                                            \
+      slab_mma_loop<BRES, MODE3, 1, PAIR>(p, a_full, a_empty, b_full, b_empty, &bres_bar, tmem_full_bar,              \
+                                          tmem_empty_bar, a_base, b_base, tmem_base, num_tiles);                      \
   } while (0)
-      if (p.b_resident) {
-        if (p.slab_mode == 3) LRPX_SLAB_LOOP(true, true); else LRPX_SLAB_LOOP(true, false);
+      if (PAIR) {
+        if (p.b_resident) {
+          if (p.slab_mode == 3) LRPX_SLAB_LOOP(true, true, PAIR); else LRPX_SLAB_LOOP(true, false, PAIR);
+        } else {
+          if (p.slab_mode == 3) LRPX_SLAB_LOOP(false, true, PAIR); else LRPX_SLAB_LOOP(false, false, PAIR);
+        }
+      } else if (p.b_resident) {
+        if (p.slab_mode == 3) LRPX_SLAB_LOOP(true, true, false); else LRPX_SLAB_LOOP(true, false, false);
       } else {
-        if (p.slab_mode == 3) LRPX_SLAB_LOOP(false, true); else LRPX_SLAB_LOOP(false, false);
+        if (p.slab_mode == 3) LRPX_SLAB_LOOP(false, true, false); else LRPX_SLAB_LOOP(false, false, false);
       }
 #undef LRPX_SLAB_LOOP
     }
@@ -1435,8 +1546,10 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int pf_row = (n_pf == n_tile) ? m_pf * tile_rows + quarter * 32 + lane : -1;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
       const uint32_t stage = (EPI == LRPX_TC_EPI_MUL && p.store_off) ? smem_base + (uint32_t)p.store_off + (uint32_t)(warp - 2) * 1024u : 0u;
+      uint32_t rel_bar = smem_u32(&tmem_empty_bar[buf]);
+      if (PAIR) rel_bar = mapa_u32(rel_bar, 0);          // shared::cluster address of the LEADER's barrier (both ranks)
       run_epilogue_tile<EPI>(p, m_tile * tile_rows - p.fold + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh,
-                             pf_row, smem_u32(&tmem_empty_bar[buf]), stage, &tmO,
+                             pf_row, rel_bar, stage, &tmO,
                              EPI == LRPX_TC_EPI_INPUT3 ? &in3_scratch[buf][(it >> 1) & 1][0][0] : nullptr, quarter, it);
     }
     if (EPI == LRPX_TC_EPI_MUL && p.store_off) {      // the staging block must outlive the last tile store's read
@@ -1450,7 +1563,8 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   if (p.cluster == 2) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -1536,13 +1650,31 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
   return LRPX_OK;
 }
 
+template <int EPI, bool PAIR>
+static int launch_tc_slab_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mbh,
+                               const CUtensorMap& mo, const TcParams& p, int grid, cudaStream_t st);
+
 template <int EPI>
 static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mbh,
                           const CUtensorMap& mo, const TcParams& p, int grid, cudaStream_t st) {
+  if constexpr (EPI == LRPX_TC_EPI_MUL || EPI == LRPX_TC_EPI_MUL_UNPOOL || EPI == LRPX_TC_EPI_MULX ||
+                EPI == LRPX_TC_EPI_MULX_UNPOOL) {
+    if (p.pair) return launch_tc_slab_impl<EPI, true>(ma0, ma1, mb, mbh, mo, p, grid, st);
+  }
+  if (p.pair) {
+    set_error("pair mode is not built for this epilogue");
+    return LRPX_E_INVALID;
+  }
+  return launch_tc_slab_impl<EPI, false>(ma0, ma1, mb, mbh, mo, p, grid, st);
+}
+
+template <int EPI, bool PAIR>
+static int launch_tc_slab_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mbh,
+                               const CUtensorMap& mo, const TcParams& p, int grid, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc_conv_slab_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(tc_conv_slab_kernel<EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) {
     set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
@@ -1562,7 +1694,7 @@ static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const 
       qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
       q.attrs = qa; q.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, tc_conv_slab_kernel<EPI>, &q) != cudaSuccess || n <= 0) n = 64;
+      if (cudaOccupancyMaxActiveClusters(&n, tc_conv_slab_kernel<EPI, PAIR>, &q) != cudaSuccess || n <= 0) n = 64;
       max_clusters = n;
     }
     if (grid > 2 * max_clusters) grid = 2 * max_clusters;
@@ -1578,14 +1710,14 @@ static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, tc_conv_slab_kernel<EPI>, ma0, ma1, mb, mbh, mo, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, tc_conv_slab_kernel<EPI, PAIR>, ma0, ma1, mb, mbh, mo, p);
     if (le != cudaSuccess) {
       set_error("tc_conv_slab_kernel cluster launch failed: %s", cudaGetErrorString(le));
       return LRPX_E_CUDA;
     }
     return LRPX_OK;
   }
-  tc_conv_slab_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma0, ma1, mb, mbh, mo, p);
+  tc_conv_slab_kernel<EPI, PAIR><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma0, ma1, mb, mbh, mo, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("tc_conv_slab_kernel launch failed: %s", cudaGetErrorString(e));
@@ -1817,7 +1949,27 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       CUtensorMap mbh = mb;
       p.cluster = 1;
       p.tiles_sched = p.num_m_tiles * p.num_n_tiles;
-      if (want_cluster && !p.b_resident && p.bn >= 16 && sm_count() >= 2) {
+      // CTA pairs on ONE tcgen05.mma.cta_group::2 (M = 256 across the pair, each CTA holding bn/2 rows of B in its own
+      // shared memory): halves the B operand reads per SM.  Measured per layer, A/B inside one process
+      // (scripts/pair_ab.py, outputs bit-identical): 128-column layers -10 % (56^2 un-pool) and -20 % (112^2), 256-column
+      // layers -4...9 %; the 64-column layers do NOT gain (224^2: +19 %, 112^2 un-pool: +-0: their tiles are short, K = 576 /
+      // 1152, and the hand-over between the two CTAs costs more than the saved operand reads), so pairs start at 128 columns.
+      // LRPX_TC_PAIR=0: off, =2: every width.
+      const char* env_pair = getenv("LRPX_TC_PAIR");
+      const bool pair_on = env_pair ? env_pair[0] != '0' : LRPX_TC_PAIR_DEFAULT;
+      const int pair_min_bn = (env_pair && env_pair[0] == '2') ? 32 : 128;
+      const bool want_pair = want_cluster && pair_on && !p.fold && p.bn % 32 == 0 && p.bn >= pair_min_bn &&
+                             (epi == LRPX_TC_EPI_MUL || epi == LRPX_TC_EPI_MUL_UNPOOL || epi == LRPX_TC_EPI_MULX ||
+                              epi == LRPX_TC_EPI_MULX_UNPOOL) &&
+                             p.num_m_tiles >= 2 && sm_count() >= 2;
+      p.pair = 0;
+      if (want_pair) {
+        p.pair = 1;
+        p.cluster = 2;
+        p.tiles_sched = p.num_n_tiles * 2 * ((p.num_m_tiles + 1) / 2);
+        rc = make_map_2d(&mbh, a->wt, (uint64_t)a->ncol, (uint64_t)p.taps * a->cin, (uint32_t)(p.bn / 2));
+        if (rc) return rc;
+      } else if (want_cluster && !p.b_resident && p.bn >= 16 && sm_count() >= 2) {
         p.cluster = 2;
         p.tiles_sched = p.num_n_tiles * 2 * ((p.num_m_tiles + 1) / 2);
         rc = make_map_2d(&mbh, a->wt, (uint64_t)a->ncol, (uint64_t)p.taps * a->cin, (uint32_t)(p.bn / 2));
