@@ -262,6 +262,91 @@ typedef struct {
 size_t lrpx_adaptive_decoder_workspace_bytes(const lrpx_adaptive_args* args);
 int lrpx_adaptive_decoder_lrp_f32(const lrpx_adaptive_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Gradient-family explainers, decoder part: the reference's hand-written backward pass of the
+ * decoder with the attention weights and gates held constant, batched over Q requests like the relevance above.
+ *   gridTD: ExplainGridTDGradient.explain_caption_wordt (gridTDmodel.py:1424-1508); LRPX_DEC_GUIDED adds the guided
+ *           variant's mask d_feat[feat <= 0] = 0 (ExplainiGridTDGuidedGradient, :1663-1674)
+ *   AoA:    ExplainAOAGradient.explain_caption_wordt (aoamodel.py:1435-1499) with gradient_mha (:1415-1433)
+ * Saved state: that of get_hidden_parameters (:1323-1422 / aoamodel.py:1309-1375) — the relevance state plus the output
+ * gates and the sentinel gate (lrpx_lstm_step_args.o / .sg) — stacked over B images, padded to T steps.
+ * ------------------------------------------------------------------------------------------- */
+#define LRPX_DEC_GUIDED 2
+
+typedef struct {
+  int B, T, H, E, P, C, V, Q;
+  int flags, reserved_;    /* LRPX_DEC_TC_GEMM | LRPX_DEC_GUIDED */
+  const float* feat;      /* (B,P,C) encoder output, pixel-major: the guided mask (NULL otherwise)   :1674 */
+  const float* c1;        /* (B,T+1,H) AdaLSTM cell states, row 0 = zeros                            :1401 */
+  const float* c2;        /* (B,T+1,H) LanguageLSTM                                                  :1411 */
+  const float* g1;        /* (B,T,H) pre-tanh cell candidate (the kernels take tanh)                 :1404,:1408 */
+  const float* i1;        /* (B,T,H) sigmoid(input gate)                                             :1406 */
+  const float* f1;
+  const float* o1;        /* (B,T,H) sigmoid(output gate)                                            :1409 */
+  const float* g2;
+  const float* i2;
+  const float* f2;
+  const float* o2;
+  const float* sg;        /* (B,T,H) sigmoid(x_gate(x) + h_gate(h)), the sentinel gate               :1381,:1394 */
+  const float* alpha;     /* (B,T,P) */
+  const float* beta;      /* (B,T)   */
+  const float* W1;        /* (4H, H+2E) AdaLSTM weight_ih: columns [h2 | glob | emb]                  :1495 */
+  const float* W2;        /* (4H, 3H)   LanguageLSTM [weight_ih | weight_hh]: columns [ctx_hat | h1 | h2]  :1474-1475 */
+  const float* W_fc;      /* (V,H)                                                                   :1459 */
+  const float* W_glob;    /* (E,C)                                                                   :1499 */
+  const float* W_proj;    /* (H,C)                                                                   :1502 */
+  const int32_t* req_img;   /* (Q) */
+  const int32_t* req_t;     /* (Q) 0 <= t_q < T */
+  const int32_t* req_word;  /* (Q) tokens[b_q][t_q+1]                                                :1427 */
+  float* d_feat;            /* (Q,P,C) gradient with respect to the encoder output, pixel-major      :1507 */
+  float* r_words;           /* (Q,T) sum over the embedding of d logits / d emb_i, max-abs normalised :1503-1506 */
+  float* r_words_raw;       /* (Q,T) before the normalisation (may be NULL) */
+} lrpx_gridtd_grad_args;
+
+size_t lrpx_gridtd_decoder_grad_workspace_bytes(const lrpx_gridtd_grad_args* args);
+int lrpx_gridtd_decoder_grad_f32(const lrpx_gridtd_grad_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
+typedef struct {
+  int B, T, H, E, P, C, V, Q, num_head;
+  int flags;               /* LRPX_DEC_TC_GEMM */
+  const float* c;         /* (B,T+1,H)                                             aoamodel.py:1363 */
+  const float* g;         /* (B,T,H) pre-tanh cell candidate                                  :1366 */
+  const float* i;         /* (B,T,H) gate activations                                         :1368-1371 */
+  const float* f;
+  const float* o;
+  const float* caoa_gate; /* (B,T,H) decoder_aoa_linear_gate(h), before the sigmoid           :1375 */
+  const float* caoa_lin;  /* (B,T,H) decoder_aoa_linear(ctx)                                  :1374 */
+  const float* alpha;     /* (B,T,heads,P)                                                    :1361 */
+  const float* W_g;       /* (4H, E+2H) LanguageLSTM [weight_ih | weight_hh]: columns [emb | glob | h]   :1486-1487 */
+  const float* W_fc;      /* (V,H) */
+  const float* W_aoa;     /* (H,H) decoder_aoa_linear.weight                                  :1469 */
+  const float* W_gate;    /* (H,H) decoder_aoa_linear_gate.weight                             :1470 */
+  const float* W_v;       /* (H,H) decoder_v_proj.weight                                      :1490 */
+  const float* W_proj;    /* (H,C)                                                            :1493 */
+  const int32_t* req_img;
+  const int32_t* req_t;
+  const int32_t* req_word;
+  const int32_t* req_head;  /* (Q) head_idx                                                   :1472 */
+  float* d_feat;            /* (Q,P,C) */
+  float* r_words;           /* (Q,T) */
+  float* r_words_raw;
+} lrpx_aoa_grad_args;
+
+size_t lrpx_aoa_decoder_grad_workspace_bytes(const lrpx_aoa_grad_args* args);
+int lrpx_aoa_decoder_grad_f32(const lrpx_aoa_grad_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Grad-CAM (gridTDmodel.py:1760-1771, aoamodel.py:1676-1689), one map per request:
+ *   weights[c] = mean_p grads[q][p][c];  cam[p] = relu(sum_c feat[img(q)][p][c] * weights[c]);  out[q][p] = cam[p] / (max cam + 1e-6)
+ * feat (B,P,C) and grads (Q,P,C) pixel-major; req_img (Q) or NULL = identity; out (Q,P). */
+int lrpx_grad_cam_f32(const float* feat, const float* grads, const int32_t* req_img, float* out, int Q, int P, int C,
+                      void* stream);
+
+/* Guided Grad-CAM (gridTDmodel.py:1812-1833): out[q][c][y][x] = g[q][c][y][x] * (Kh cam_q Kw^T)[y][x].  g / out (Q,C,H,W)
+ * (may alias), cam (Q,h,w), Kh (H,h) and Kw (W,w): skimage.transform.pyramid_expand along one axis as a matrix (bilinear
+ * resize then Gaussian smoothing, both separable), built by the host (models/_gradient.py::expand_operator). */
+int lrpx_cam_expand_mul_f32(const float* g, const float* cam, const float* Kh, const float* Kw, float* out, int Q, int C,
+                            int h, int w, int H, int W, void* stream);
+
 /* lrp_tune weights, batched (gridTDmodel.py:549-578, aoamodel.py:597-626, utils.py:55-64):
  *   w = argmax logits[b]; if is_stop[w] -> weights 1; else r = fc-row eps rule, split to h / ctx,
  *   weights = r / max|r| + 1.   No host synchronisation; is_stop is a device byte mask (V). */
@@ -368,6 +453,8 @@ typedef struct {
   float* h_copy1;         long long ld_copy1;
   float* h_copy2;         long long ld_copy2;
   float* s_copy;          long long ld_s_copy;
+  float *o, *sg;                                /* optional (stride ld_gate): sigmoid(output gate), sigmoid(sentinel gate) —
+                                                   the saved state of the gradient explainers, gridTDmodel.py:1381,1409 */
 } lrpx_lstm_cell_args;
 
 int lrpx_lstm_cell_f32(const lrpx_lstm_cell_args* args, void* stream);
@@ -391,6 +478,7 @@ typedef struct {
   float* h_copy1;         long long ld_copy1;
   float* h_copy2;         long long ld_copy2;
   float* s_copy;          long long ld_s_copy;
+  float *o, *sg;                                /* optional, as in lrpx_lstm_cell_args                       */
 } lrpx_lstm_step_args;
 
 int lrpx_lstm_step_f32(const lrpx_lstm_step_args* args, void* stream);
@@ -480,6 +568,10 @@ enum {
    *                        gain1 = -beta * num / safe(acc_W- [+ bias if zbias])                      (n_acc == 3)
    *   rule 1 (epsilon, lrp_modules.py:9-24 on the unfolded conv): gain0 = num' / stab(acc_W [+ bias if zbias]),
    *                        num' = num with exact zeros replaced by -1e-6 (Q9), stab(z) = z + 0.01 sign z, 0 -> 0.01
+   *   rule 2 (gradient, gridTDmodel.py:1510-1523) / 3 (guided backpropagation, :1677-1723): n_acc == 1,
+   *                        gain0 = [act > 0], the ReLU's derivative.  With rule 3 the MULX epilogues pass only the positive
+   *                        part of the accumulator (the ReLU backward hook of :1680-1686); with rule >= 2 INPUT3 returns
+   *                        W^T g itself (rows 0..2 of its weight), not multiplied by the image.
    * out = act (bf16 PF, or hi|lo split with 2*cout channels per row when split), out2 = gain0, out3 = gain1
    * (bf16, or fp32 when split). */
   LRPX_TC_EPI_FWDX = 11,
@@ -603,7 +695,8 @@ int lrpx_tc_im2col3_split_x(const float* x, void* dst, int n, int h, int w, int 
 /* lrpx_tc_maxpool2_bf16 for split rows (the winner is the largest hi+lo) and up to two gain tensors */
 int lrpx_tc_maxpool2_x(const void* act, const void* gain0_fine, const void* gain1_fine, void* pooled, uint8_t* idx,
                        void* gain0_pooled, void* gain1_pooled, int n, int h, int w, int c, int split, void* stream);
-/* lrpx_tc_scale_rows for the general chain: out row = [r*rz0 | r*rz1] (groups), bf16 or hi|lo split */
+/* lrpx_tc_scale_rows for the general chain: out row = [r*rz0 | r*rz1] (groups), bf16 or hi|lo split.
+ * split bit 1 (value 2): r is clamped at 0 first — the entry of guided backpropagation (gridTDmodel.py:1680-1686) */
 int lrpx_tc_scale_rows_x(const float* r, const void* rz0, const void* rz1, const int32_t* row_img, void* out,
                          int n_expl, int h, int w, int c, int groups, int split, void* stream);
 /* ---- residual-network encoder (models/resnet.py:143-239): stem and strides, bf16 PF */

@@ -365,3 +365,49 @@ def compute_lrp(model, sample, target=None, return_output=False, rectify_logits=
     if return_output:
         return output, logits
     return output
+
+
+# ------------------------------------------------------------------------------------------------ gradient family (f4)
+def encoder_gradient_simt(model, sample, target, guided=False, return_output=False):
+    """The encoder half of the gradient-family explainers on the fp32 CUDA-core kernels: the input gradient of a
+    conv / ReLU / max-pool Sequential for the output gradient ``target`` (ExplainGridTDGradient.explain_cnn, reference
+    models/gridTDmodel.py:1510-1523, where autograd does it), or its guided-backpropagation variant (``guided``: every
+    ReLU passes only the positive part of the incoming gradient where its output is positive, :1677-1723).
+        conv     : W^T * g            = lrpx_conv_rule_rin_f32 in its PLAIN form against a tensor of ones
+        ReLU     : g (.) [out > 0]    = lrpx_relu_mask_f32  (guided: of the clamped g)
+        max-pool : g to the argmax    = lrpx_maxpool_wta_f32 (a window whose maximum is 0 gets 0: the ReLU below would
+                                        zero it anyway)
+    The precision='simt' path of the gradient explainers; the tensor-core chain (lrpx.tc, rule 'gradient' / 'guided') is
+    the fast one."""
+    if not isinstance(model, nn.Sequential):
+        raise NotImplementedError("the gradient explainers cover Sequential conv / ReLU / max-pool encoders")
+    if not sample.is_cuda:
+        raise RuntimeError("lrpx: encoder_gradient_simt needs a CUDA tensor (there is no CPU fallback)")
+    leaves = _flatten_sequential(model)
+    for i, m in enumerate(leaves):
+        if not isinstance(m, (nn.Conv2d, nn.ReLU, nn.MaxPool2d)):
+            raise NotImplementedError(f"gradient explainers: unsupported layer {type(m)}")
+        if isinstance(m, nn.MaxPool2d) and (i == 0 or not isinstance(leaves[i - 1], nn.ReLU)):
+            raise NotImplementedError("gradient explainers: a max-pool must follow a ReLU")
+    with torch.no_grad():
+        x = sample.detach().float()
+        outs = []
+        for m in leaves:
+            x = _leaf_forward(m, x)
+            outs.append(x)
+        if tuple(target.shape) != tuple(x.shape):
+            raise RuntimeError(f"Mismatch in shape: grad_output[0] has a shape of {tuple(target.shape)} and "
+                               f"output[0] has a shape of {tuple(x.shape)}.")
+        g = target.detach().float().contiguous()
+        for m, out in zip(reversed(leaves), reversed(outs)):
+            a = m.input[0]
+            if isinstance(m, nn.Conv2d):
+                g = ops.conv_rule_rin(torch.ones_like(a), m.weight.detach(), g, m.stride, m.padding, m.dilation,
+                                      net=ops.NET_PLAIN)
+            elif isinstance(m, nn.ReLU):
+                if guided:
+                    g = ops.relu_mask(g, g)            # clamp(g, min=0)
+                g = ops.relu_mask(out, g)
+            else:
+                g = ops.maxpool_wta(a, g, m.kernel_size, m.stride, m.padding)
+    return (g, x) if return_output else g

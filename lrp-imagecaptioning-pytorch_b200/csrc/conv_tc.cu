@@ -81,7 +81,8 @@ struct TcParams {
   int groups;        // MULX*: gain groups (1 | 2)
   int split;         // 0: bf16 rows, bf16 gains; 1: hi|lo split rows, fp32 gains
   int n_acc;         // FWDX: accumulators per output channel (W [, W+ [, W-]])
-  int rule;          // FWDX: 0 alpha-beta, 1 epsilon
+  int rule;          // 0 alpha-beta, 1 epsilon, 2 gradient (gain = the ReLU's derivative), 3 guided backpropagation (as 2,
+                     // and MULX passes only the positive part of the accumulator); INPUT3 with rule >= 2 returns W^T g as is
   int zbias;         // FWDX: bias enters the divisor
   int cout;          // FWDX: output channels (row pitch of the gains; act pitch = cout * (1 + split))
   float alpha, beta;
@@ -608,7 +609,8 @@ __device__ __forceinline__ void epi_input3(const TcParams& p, const RowInfo& r, 
     const float xv = xin[c];
     const float cp = up[c] + __uint_as_float(v[8 + c]) + dn[c];
     const float cn = up[3 + c] + __uint_as_float(v[8 + 3 + c]) + dn[3 + c];
-    res[c] = fmaxf(xv, 0.f) * cp + fminf(xv, 0.f) * cn;
+    // rules 2 / 3 (gradient family): the gradient with respect to the image itself, no multiplication by x
+    res[c] = p.rule >= 2 ? cp : fmaxf(xv, 0.f) * cp + fminf(xv, 0.f) * cn;
   }
   // delivery format (gain_mode): 0 = fp32 (Q,3,h,w), the reference's return value; 1 = channel mean fp32 (Q,h,w) — what
   // every consumer in evaluation.py reduces a heat-map to first (:134,:411,:503: torch.mean(relevance, dim=(0,1)));
@@ -692,10 +694,15 @@ __device__ __forceinline__ void epi_mulx(const TcParams& p, const RowInfo& r, ui
         for (int k = 0; k < 16; ++k) t[k] = ad[k] * gb[k];
       }
       uint32_t hi[8], lo[8];
+      // rule 3 (guided backpropagation, gridTDmodel.py:1680-1686): only the positive part of the incoming gradient
+      // passes a ReLU
+      const bool guided = p.rule == 3;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float a0 = r.valid ? fmaf(__uint_as_float(v[2 * k]), g[2 * k], t[2 * k]) : 0.f;
-        const float a1 = r.valid ? fmaf(__uint_as_float(v[2 * k + 1]), g[2 * k + 1], t[2 * k + 1]) : 0.f;
+        float v0 = __uint_as_float(v[2 * k]), v1 = __uint_as_float(v[2 * k + 1]);
+        if (guided) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        const float a0 = r.valid ? fmaf(v0, g[2 * k], t[2 * k]) : 0.f;
+        const float a1 = r.valid ? fmaf(v1, g[2 * k + 1], t[2 * k + 1]) : 0.f;
         split_pack(a0, a1, hi[k], lo[k]);
       }
       if (!UNPOOL) {
@@ -849,10 +856,12 @@ __device__ __forceinline__ void epi_fwdx(const TcParams& p, const RowInfo& r, ui
         } else if (p.idn) {
           q1 = rho2 * hdv[k];                                        // identity-branch gain
         }
-      } else {
+      } else if (p.rule == 1) {
         const float zr = zw + (p.zbias ? bv[k] : 0.f);
         const float nq = (num == 0.f) ? -1e-6f : num;               // zeros of the input count as -1e-6 (Q9)
         q0 = p.zbias ? nq / zr : nq / stab(zr);                     // the bias branch is unstabilised (lrp_modules.py:20-21)
+      } else {
+        q0 = a > 0.f ? 1.f : 0.f;                                   // rule 2 / 3: the ReLU's derivative (gradient family)
       }
       g0[k] = r.valid ? q0 : 0.f;
       g1[k] = r.valid ? q1 : 0.f;
@@ -1838,7 +1847,8 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
 
   if (epi == LRPX_TC_EPI_FWDX) {
     LRPX_CHECK_ARG(a->out2 && a->n_acc >= 1 && a->n_acc <= 3 && a->ncol % a->n_acc == 0, "FWDX: out2 and n_acc in 1..3");
-    LRPX_CHECK_ARG((a->rule == 0 && a->n_acc >= 2) || (a->rule == 1 && a->n_acc == 1), "FWDX: alpha-beta needs W and W+ (n_acc >= 2), epsilon n_acc == 1");
+    LRPX_CHECK_ARG((a->rule == 0 && a->n_acc >= 2) || (a->rule >= 1 && a->rule <= 3 && a->n_acc == 1),
+                   "FWDX: alpha-beta needs W and W+ (n_acc >= 2); epsilon / gradient / guided n_acc == 1");
     LRPX_CHECK_ARG(a->out3 == nullptr || a->n_acc == 3 || a->idn, "FWDX: out3 needs n_acc == 3 (neg-net gain) or idn (identity-branch gain)");
     LRPX_CHECK_ARG((a->bn_w == nullptr) == (a->bn_b == nullptr), "FWDX: bn_w and bn_b go together");
     LRPX_CHECK_ARG(!(a->fwd_flags & 2) || (a->h % 2 == 0 && a->w % 2 == 0 && !a->idn && !a->hd), "FWDX: strided store needs even h, w and no idn / hd");

@@ -25,18 +25,22 @@ __global__ void lstm_cell_kernel(lrpx_lstm_cell_args a) {
   const float i = sigmoidf_(zi), f = sigmoidf_(zf);
   const float c = f * a.c_prev[(size_t)b * a.ld_cprev + j] + i * tanhf(zg);
   const float tc = tanhf(c);
-  const float h = sigmoidf_(zo) * tc;
+  const float og = sigmoidf_(zo);
+  const float h = og * tc;
   a.h[(size_t)b * a.ld_state + j] = h;
   a.c[(size_t)b * a.ld_state + j] = c;
   a.g[(size_t)b * a.ld_gate + j] = zg;
   a.i[(size_t)b * a.ld_gate + j] = i;
   a.f[(size_t)b * a.ld_gate + j] = f;
+  if (a.o) a.o[(size_t)b * a.ld_gate + j] = og;
   if (a.h_copy0) a.h_copy0[(size_t)b * a.ld_copy0 + j] = h;
   if (a.h_copy1) a.h_copy1[(size_t)b * a.ld_copy1 + j] = h;
   if (a.h_copy2) a.h_copy2[(size_t)b * a.ld_copy2 + j] = h;
   if (a.gate_pre) {      // sentinel  s = sigmoid(x_gate(x) + h_gate(h_old)) * tanh(c_new)   (:982-983)
-    const float s = sigmoidf_(a.gate_pre[(size_t)b * a.ld_gate_pre + j]) * tc;
+    const float sgv = sigmoidf_(a.gate_pre[(size_t)b * a.ld_gate_pre + j]);
+    const float s = sgv * tc;
     a.s[(size_t)b * a.ld_gate + j] = s;
+    if (a.sg) a.sg[(size_t)b * a.ld_gate + j] = sgv;
     if (a.s_copy) a.s_copy[(size_t)b * a.ld_s_copy + j] = s;
   }
 }
@@ -164,18 +168,22 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(lrpx_lstm_step_args a) {
       const float ig = sigmoidf_(z[0]), fg = sigmoidf_(z[1]);
       const float c = fg * cprev + ig * tanhf(z[2]);
       const float tc = tanhf(c);
-      const float h = sigmoidf_(z[3]) * tc;
+      const float og = sigmoidf_(z[3]);
+      const float h = og * tc;
       a.h[(size_t)b * a.ld_state + j] = h;
       a.c[(size_t)b * a.ld_state + j] = c;
       a.g[(size_t)b * a.ld_gate + j] = z[2];
       a.i[(size_t)b * a.ld_gate + j] = ig;
       a.f[(size_t)b * a.ld_gate + j] = fg;
+      if (a.o) a.o[(size_t)b * a.ld_gate + j] = og;
       if (a.h_copy0) a.h_copy0[(size_t)b * a.ld_copy0 + j] = h;
       if (a.h_copy1) a.h_copy1[(size_t)b * a.ld_copy1 + j] = h;
       if (a.h_copy2) a.h_copy2[(size_t)b * a.ld_copy2 + j] = h;
       if (G == 5) {
-        const float sv = sigmoidf_(z[G - 1]) * tc;
+        const float sgv = sigmoidf_(z[G - 1]);
+        const float sv = sgv * tc;
         a.s[(size_t)b * a.ld_gate + j] = sv;
+        if (a.sg) a.sg[(size_t)b * a.ld_gate + j] = sgv;
         if (a.s_copy) a.s_copy[(size_t)b * a.ld_s_copy + j] = sv;
       }
     }

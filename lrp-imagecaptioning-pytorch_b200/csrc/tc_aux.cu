@@ -466,7 +466,7 @@ __global__ void maxpool2_x_kernel(const uint4* __restrict__ act, const void* __r
 template <bool SPLIT>
 __global__ void scale_rows_x_kernel(const float* __restrict__ r, const void* __restrict__ rz0, const void* __restrict__ rz1,
                                     const int32_t* __restrict__ row_img, uint4* __restrict__ out, int h, int w, int c8,
-                                    int groups, long long total) {
+                                    int groups, long long total, bool clamp) {
   const int wp1 = w + 1, blk = (h + 1) * wp1;
   const int rowv = c8 * groups * (SPLIT ? 2 : 1);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -484,6 +484,9 @@ __global__ void scale_rows_x_kernel(const float* __restrict__ r, const void* __r
       const float4* rp = reinterpret_cast<const float4*>(r + (((size_t)e * h + (a - 1)) * w + (b - 1)) * (c8 * 8) + cc * 8);
       const float4 r0 = rp[0], r1 = rp[1];
       rv[0] = r0.x; rv[1] = r0.y; rv[2] = r0.z; rv[3] = r0.w; rv[4] = r1.x; rv[5] = r1.y; rv[6] = r1.z; rv[7] = r1.w;
+      if (clamp)        // guided backpropagation: the last ReLU passes only the positive part (gridTDmodel.py:1684)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rv[k] = fmaxf(rv[k], 0.f);
     }
     for (int j = 0; j < groups; ++j) {
       const void* rz = j ? rz1 : rz0;
@@ -874,12 +877,13 @@ int lrpx_tc_scale_rows_x(const float* r, const void* rz0, const void* rz1, const
   LRPX_CHECK_ARG(r && rz0 && out && n_expl > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "bad argument");
   LRPX_CHECK_ARG(groups == 1 || (groups == 2 && rz1), "groups must be 1, or 2 with rz1");
   long long total = (long long)n_expl * (h + 1) * (w + 1) * (c / 8);
-  if (split)
+  const bool clamp = (split & 2) != 0;
+  if (split & 1)
     scale_rows_x_kernel<true><<<grid_for(total), 256, 0, as_stream(stream)>>>(r, rz0, rz1, row_img, (uint4*)out, h, w,
-                                                                             c / 8, groups, total);
+                                                                             c / 8, groups, total, clamp);
   else
     scale_rows_x_kernel<false><<<grid_for(total), 256, 0, as_stream(stream)>>>(r, rz0, rz1, row_img, (uint4*)out, h, w,
-                                                                              c / 8, groups, total);
+                                                                              c / 8, groups, total, clamp);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;
 }

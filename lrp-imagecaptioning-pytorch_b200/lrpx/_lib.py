@@ -41,6 +41,24 @@ class AoaArgs(C.Structure):
                [(n, _P) for n in _AOA_PTRS]
 
 
+_GRID_GRAD_PTRS = ["feat", "c1", "c2", "g1", "i1", "f1", "o1", "g2", "i2", "f2", "o2", "sg", "alpha", "beta", "W1", "W2",
+                   "W_fc", "W_glob", "W_proj", "req_img", "req_t", "req_word", "d_feat", "r_words", "r_words_raw"]
+
+
+class GridTDGradArgs(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("B", "T", "H", "E", "P", "C", "V", "Q", "flags", "reserved_")] + \
+               [(n, _P) for n in _GRID_GRAD_PTRS]
+
+
+_AOA_GRAD_PTRS = ["c", "g", "i", "f", "o", "caoa_gate", "caoa_lin", "alpha", "W_g", "W_fc", "W_aoa", "W_gate", "W_v",
+                  "W_proj", "req_img", "req_t", "req_word", "req_head", "d_feat", "r_words", "r_words_raw"]
+
+
+class AoaGradArgs(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("B", "T", "H", "E", "P", "C", "V", "Q", "num_head", "flags")] + \
+               [(n, _P) for n in _AOA_GRAD_PTRS]
+
+
 _ADA_PTRS = ["feat", "avg", "z_proj", "A", "z_glob", "x", "h", "c", "g", "i", "f", "st", "ctx", "ctx_hat", "alpha", "beta",
              "pred", "W_g", "W_fc", "W_glob", "W_proj", "req_img", "req_t", "req_word", "r_feat", "r_words",
              "r_words_raw"]
@@ -68,7 +86,8 @@ class LstmCellArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("H", C.c_int), ("z", _P), ("ldz", _LL), ("c_prev", _P), ("ld_cprev", _LL),
                 ("gate_pre", _P), ("ld_gate_pre", _LL), ("h", _P), ("c", _P), ("ld_state", _LL), ("g", _P), ("i", _P),
                 ("f", _P), ("s", _P), ("ld_gate", _LL), ("h_copy0", _P), ("ld_copy0", _LL), ("h_copy1", _P),
-                ("ld_copy1", _LL), ("h_copy2", _P), ("ld_copy2", _LL), ("s_copy", _P), ("ld_s_copy", _LL)]
+                ("ld_copy1", _LL), ("h_copy2", _P), ("ld_copy2", _LL), ("s_copy", _P), ("ld_s_copy", _LL),
+                ("o", _P), ("sg", _P)]
 
 
 class LstmStepArgs(C.Structure):
@@ -76,7 +95,7 @@ class LstmStepArgs(C.Structure):
                 ("add", _P), ("ld_add", _LL), ("c_prev", _P), ("ld_cprev", _LL), ("h", _P), ("c", _P),
                 ("ld_state", _LL), ("g", _P), ("i", _P), ("f", _P), ("s", _P), ("ld_gate", _LL), ("h_copy0", _P),
                 ("ld_copy0", _LL), ("h_copy1", _P), ("ld_copy1", _LL), ("h_copy2", _P), ("ld_copy2", _LL),
-                ("s_copy", _P), ("ld_s_copy", _LL)]
+                ("s_copy", _P), ("ld_s_copy", _LL), ("o", _P), ("sg", _P)]
 
 
 class AdaAttentionArgs(C.Structure):
@@ -134,6 +153,12 @@ SYMBOLS = {
     "lrpx_lrp_mha_f32": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "lrpx_gridtd_decoder_workspace_bytes": (_sz, [C.POINTER(GridTDArgs)]),
     "lrpx_gridtd_decoder_lrp_f32": (_i, [C.POINTER(GridTDArgs), _P, _sz, _P]),
+    "lrpx_gridtd_decoder_grad_workspace_bytes": (_sz, [C.POINTER(GridTDGradArgs)]),
+    "lrpx_gridtd_decoder_grad_f32": (_i, [C.POINTER(GridTDGradArgs), _P, _sz, _P]),
+    "lrpx_aoa_decoder_grad_workspace_bytes": (_sz, [C.POINTER(AoaGradArgs)]),
+    "lrpx_aoa_decoder_grad_f32": (_i, [C.POINTER(AoaGradArgs), _P, _sz, _P]),
+    "lrpx_grad_cam_f32": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
+    "lrpx_cam_expand_mul_f32": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _P]),
     "lrpx_aoa_decoder_workspace_bytes": (_sz, [C.POINTER(AoaArgs)]),
     "lrpx_aoa_decoder_lrp_f32": (_i, [C.POINTER(AoaArgs), _P, _sz, _P]),
     "lrpx_adaptive_decoder_workspace_bytes": (_sz, [C.POINTER(AdaptiveArgs)]),

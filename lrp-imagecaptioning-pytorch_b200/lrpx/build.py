@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.path.join(HERE, "liblrpx.so")
-SOURCES = ["elementwise.cu", "conv_simt.cu", "decoder.cu", "conv_tc.cu", "tc_aux.cu", "explainer_fwd.cu", "beam.cu", "ablation.cu"]
+SOURCES = ["elementwise.cu", "conv_simt.cu", "decoder.cu", "decoder_grad.cu", "conv_tc.cu", "tc_aux.cu", "explainer_fwd.cu", "beam.cu", "ablation.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -436,6 +436,98 @@ def adaptive_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, w
     return (r_feat, r_words, r_raw) if want_raw else (r_feat, r_words)
 
 
+# ------------------------------------------------------------------------------------------ gradient family (f4)
+DEC_GUIDED = 2
+
+
+def gridtd_decoder_grad(state: dict, weights: dict, req_img, req_t, req_word, guided=False, want_raw=False, tc_gemm=False):
+    """ExplainGridTDGradient.explain_caption_wordt (gridTDmodel.py:1424-1508; ``guided``: :1588-1675) batched over
+    requests.  state: the explainer forward's tensors incl. the output / sentinel gates (o1, o2, sg); weights: W1 (4H,
+    H+2E), W2 (4H, 3H), W_fc, W_glob, W_proj.  Returns d_feat (Q,P,C), r_words (Q,T)[, r_words_raw]."""
+    dev = state["feat"].device
+    B, P, Cc = state["feat"].shape
+    T, H = state["g1"].shape[1], state["g1"].shape[2]
+    E = weights["W_glob"].shape[0]
+    V = weights["W_fc"].shape[0]
+    Q = int(req_img.numel())
+    _check_requests(B, T, V, req_img, req_t, req_word)
+    keep = []
+    a = _lib.GridTDGradArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q,
+                            flags=(DEC_TC_GEMM if tc_gemm else 0) | (DEC_GUIDED if guided else 0))
+    f = {k: _f32(state[k], k) for k in ["feat", "c1", "c2", "g1", "i1", "f1", "o1", "g2", "i2", "f2", "o2", "sg", "alpha",
+                                        "beta"]}
+    f.update({k: _f32(weights[k], k) for k in ["W1", "W2", "W_fc", "W_glob", "W_proj"]})
+    for k, v in (("req_img", req_img), ("req_t", req_t), ("req_word", req_word)):
+        f[k] = v.to(device=dev, dtype=torch.int32).contiguous()
+    d_feat = torch.empty(Q, P, Cc, device=dev, dtype=torch.float32)
+    r_words = torch.zeros(Q, T, device=dev, dtype=torch.float32)
+    r_raw = torch.zeros(Q, T, device=dev, dtype=torch.float32) if want_raw else None
+    f.update(d_feat=d_feat, r_words=r_words, r_words_raw=r_raw)
+    _fill_args(a, f, keep)
+    nbytes = lib().lrpx_gridtd_decoder_grad_workspace_bytes(C.byref(a))
+    ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
+    check(lib().lrpx_gridtd_decoder_grad_f32(C.byref(a), _ptr(ws), nbytes, _stream()), "lrpx_gridtd_decoder_grad_f32")
+    return (d_feat, r_words, r_raw) if want_raw else (d_feat, r_words)
+
+
+def aoa_decoder_grad(state: dict, weights: dict, num_head, req_img, req_t, req_word, req_head, want_raw=False,
+                     tc_gemm=False):
+    """ExplainAOAGradient.explain_caption_wordt (aoamodel.py:1435-1499) batched over requests.  state: the explainer
+    forward's tensors incl. the output gate ``o`` and the gate pre-activation ``caoa_gate``; weights: W_g (4H, E+2H),
+    W_fc, W_aoa, W_gate, W_v, W_proj."""
+    dev = state["feat"].device
+    B, P, Cc = state["feat"].shape
+    T, H = state["g"].shape[1], state["g"].shape[2]
+    E = weights["W_g"].shape[1] - 2 * H
+    V = weights["W_fc"].shape[0]
+    Q = int(req_img.numel())
+    _check_requests(B, T, V, req_img, req_t, req_word, req_head, num_head)
+    keep = []
+    a = _lib.AoaGradArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q, num_head=num_head, flags=DEC_TC_GEMM if tc_gemm else 0)
+    f = {k: _f32(state[k], k) for k in ["c", "g", "i", "f", "o", "caoa_gate", "caoa_lin", "alpha"]}
+    f.update({k: _f32(weights[k], k) for k in ["W_g", "W_fc", "W_aoa", "W_gate", "W_v", "W_proj"]})
+    for k, v in (("req_img", req_img), ("req_t", req_t), ("req_word", req_word), ("req_head", req_head)):
+        f[k] = v.to(device=dev, dtype=torch.int32).contiguous()
+    d_feat = torch.empty(Q, P, Cc, device=dev, dtype=torch.float32)
+    r_words = torch.zeros(Q, T, device=dev, dtype=torch.float32)
+    r_raw = torch.zeros(Q, T, device=dev, dtype=torch.float32) if want_raw else None
+    f.update(d_feat=d_feat, r_words=r_words, r_words_raw=r_raw)
+    _fill_args(a, f, keep)
+    nbytes = lib().lrpx_aoa_decoder_grad_workspace_bytes(C.byref(a))
+    ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
+    check(lib().lrpx_aoa_decoder_grad_f32(C.byref(a), _ptr(ws), nbytes, _stream()), "lrpx_aoa_decoder_grad_f32")
+    return (d_feat, r_words, r_raw) if want_raw else (d_feat, r_words)
+
+
+def grad_cam(feat, grads, req_img=None):
+    """grad_cam (gridTDmodel.py:1760-1771) for Q requests: feat (B,P,C) encoder output, grads (Q,P,C) its gradient,
+    both pixel-major; req_img (Q,) int32 or None (identity).  Returns (Q,P) maps in [0, 1]."""
+    feat, grads = _f32(feat, "feat"), _f32(grads, "grads")
+    Q, P, Cc = grads.shape
+    if req_img is not None:
+        req_img = req_img.to(device=feat.device, dtype=torch.int32).contiguous()
+    elif Q != feat.shape[0]:
+        raise _lib.LrpxError("grad_cam: req_img is required when requests and images differ in number")
+    out = torch.empty(Q, P, device=feat.device, dtype=torch.float32)
+    check(lib().lrpx_grad_cam_f32(_ptr(feat), _ptr(grads), _ptr(req_img), _ptr(out), Q, P, Cc, _stream()),
+          "lrpx_grad_cam_f32")
+    return out
+
+
+def cam_expand_mul(g, cam, Kh, Kw, out=None):
+    """Guided Grad-CAM's product (gridTDmodel.py:1826-1828): g (Q,C,H,W) times the pyramid-expanded cam (Q,h,w);
+    Kh (H,h), Kw (W,w) the expansion along each axis (models/_gradient.py::expand_operator)."""
+    g, cam, Kh, Kw = _f32(g, "g"), _f32(cam, "cam"), _f32(Kh, "Kh"), _f32(Kw, "Kw")
+    Q, Cc, H, W = g.shape
+    h, w = cam.shape[1:]
+    if tuple(Kh.shape) != (H, h) or tuple(Kw.shape) != (W, w) or cam.shape[0] != Q:
+        raise _lib.LrpxError("cam_expand_mul: shapes do not match")
+    out = torch.empty_like(g) if out is None else out
+    check(lib().lrpx_cam_expand_mul_f32(_ptr(g), _ptr(cam), _ptr(Kh), _ptr(Kw), _ptr(out), Q, Cc, h, w, H, W, _stream()),
+          "lrpx_cam_expand_mul_f32")
+    return out
+
+
 # ------------------------------------------------------------------------------------------ explainer forward
 def _ld(t):
     """row stride (elements) of a 2-D view whose last dimension is contiguous"""
@@ -444,9 +536,19 @@ def _ld(t):
     return t.stride(0)
 
 
-def lstm_cell(z, c_prev, h, c, g, i, f, gate_pre=None, s=None, h_copy0=None, h_copy1=None, h_copy2=None, s_copy=None):
+def _gate_outputs(a, g, o, sg):
+    """optional extra saved gates (the gradient explainers' state): rows share the stride of g/i/f"""
+    for name, t in (("o", o), ("sg", sg)):
+        if t is not None:
+            if not t.is_cuda or t.dtype != torch.float32 or _ld(t) != _ld(g):
+                raise _lib.LrpxError(f"{name} must be an fp32 CUDA view with the row stride of g/i/f")
+            setattr(a, name, t.data_ptr())
+
+
+def lstm_cell(z, c_prev, h, c, g, i, f, gate_pre=None, s=None, h_copy0=None, h_copy1=None, h_copy2=None, s_copy=None,
+              o=None, sg=None):
     """lrpx_lstm_cell_f32: all arguments are 2-D fp32 CUDA views (B, H) (z: (B, >=4H)) with contiguous rows; outputs
-    are written in place.  h/c share one row stride, g/i/f/s share one."""
+    are written in place.  h/c share one row stride, g/i/f/s (and the optional o / sg) share one."""
     B, H = c_prev.shape
     for t in (z, c_prev, h, c, g, i, f):
         if not t.is_cuda or t.dtype != torch.float32:
@@ -466,6 +568,7 @@ def lstm_cell(z, c_prev, h, c, g, i, f, gate_pre=None, s=None, h_copy0=None, h_c
         if t is not None:
             setattr(a, name, t.data_ptr())
             setattr(a, ldn, _ld(t))
+    _gate_outputs(a, g, o, sg)
     check(lib().lrpx_lstm_cell_f32(C.byref(a), _stream()), "lrpx_lstm_cell_f32")
 
 
@@ -478,7 +581,8 @@ def lstm_prep_weights(w, G):
     return out
 
 
-def lstm_step(x, wp, add, G, c_prev, h, c, g, i, f, s=None, h_copy0=None, h_copy1=None, h_copy2=None, s_copy=None):
+def lstm_step(x, wp, add, G, c_prev, h, c, g, i, f, s=None, h_copy0=None, h_copy1=None, h_copy2=None, s_copy=None,
+              o=None, sg=None):
     """lrpx_lstm_step_f32: z = add + x @ W (skinny fp32 GEMM) and the LSTM cell rule in one kernel.  x (B,K) row
     view, wp from lstm_prep_weights, add (B,G*H) rows or a (G*H,) vector; the other arguments as in lstm_cell."""
     B, H = c_prev.shape
@@ -500,6 +604,7 @@ def lstm_step(x, wp, add, G, c_prev, h, c, g, i, f, s=None, h_copy0=None, h_copy
         if t is not None:
             setattr(a, name, t.data_ptr())
             setattr(a, ldn, _ld(t))
+    _gate_outputs(a, g, o, sg)
     check(lib().lrpx_lstm_step_f32(C.byref(a), _stream()), "lrpx_lstm_step_f32")
 
 

@@ -165,6 +165,11 @@ class TcVggEngine:
     """conv3x3/ReLU/max-pool encoder on the tcgen05 kernels: ``forward`` once per image batch, ``relevance``
     for any number of explanation requests against those images."""
 
+    # rule -> lrpx_tc_conv_args.rule.  'gradient' / 'guided' (SURVEY.md §8 f4) reuse the relevance chain for the plain and
+    # the guided-backpropagation input gradient: full weights W^T, gain = the ReLU's derivative [a > 0] (exact in bf16),
+    # the max-pool scatter unchanged; 'guided' also clamps the gradient at every ReLU (gridTDmodel.py:1680-1686)
+    RULES = {"alpha_beta": 0, "epsilon": 1, "gradient": 2, "guided": 3}
+
     def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], cfg: Sequence,
                  device=None, precision="bf16", alpha=1.0, beta=0.0, ignore_bias=True, rule="alpha_beta"):
         """precision 'bf16': bf16 operands and inter-layer storage.  'fp32': the fp32-accurate mode — operands as
@@ -177,8 +182,8 @@ class TcVggEngine:
         device = torch.device(device or "cuda")
         if device.type != "cuda":
             raise _lib.LrpxError("TcVggEngine needs a CUDA device: lrpx has no CPU fallback")
-        if precision not in ("bf16", "fp32") or rule not in ("alpha_beta", "epsilon"):
-            raise _lib.LrpxError("TcVggEngine: precision must be 'bf16' or 'fp32', rule 'alpha_beta' or 'epsilon'")
+        if precision not in ("bf16", "fp32") or rule not in self.RULES:
+            raise _lib.LrpxError(f"TcVggEngine: precision must be 'bf16' or 'fp32', rule one of {sorted(self.RULES)}")
         if rule == "epsilon" and precision != "fp32":
             # gain = a / (z + 0.01 sign z) with the mixed-sign z = W * a: bf16 operands put an absolute error of
             # ~2^-9 sum|w a| on z, larger than the 0.01 stabiliser wherever z is small — measured rel-L2 0.47 against
@@ -186,6 +191,7 @@ class TcVggEngine:
             raise _lib.LrpxError("rule='epsilon' needs precision='fp32' (the epsilon gains are ill-conditioned in bf16)")
         self.device = device
         self.precision, self.rule = precision, rule
+        self.rule_id = self.RULES[rule]
         self.alpha, self.beta, self.ignore_bias = float(alpha), float(beta), bool(ignore_bias)
         self.split = precision == "fp32"
         self.groups = 2 if (rule == "alpha_beta" and self.beta != 0.0) else 1
@@ -250,7 +256,8 @@ class TcVggEngine:
     def _general_weights(self, c, w, first):
         """B operands of the general modes, laid out on the device once per model (torch tensor ops: not on the
         per-explanation path)."""
-        sp, eps = self.split, self.rule == "epsilon"
+        sp, eps = self.split, self.rule != "alpha_beta"       # eps: ONE accumulator of the full weights (also gradient rules)
+        grad = self.rule_id >= 2
         pos, neg = (lambda t: t.clamp(min=0)), (lambda t: t.clamp(max=0))
         wt = w.flip(2, 3).permute(1, 2, 3, 0)                    # (cin,3,3,cout): W[co][ci][2-r][2-s]  (transposed conv)
         c.n_acc = 1 if eps else (3 if self.groups == 2 else 2)
@@ -258,7 +265,9 @@ class TcVggEngine:
             if c.cout % 64:
                 raise _lib.LrpxError("general modes need a first conv with a multiple of 64 output channels")
             # relevance (EPI_INPUT3): rows 0..2 multiply x+, rows 3..5 multiply x-  (lrp_modules.py:81-84,111-114)
-            if eps:
+            if grad:
+                cp, cn = wt, torch.zeros_like(wt)                # the epilogue returns rows 0..2 as they are
+            elif eps:
                 cp, cn = wt, wt
             elif self.groups == 2:
                 cp, cn = torch.cat((pos(wt), neg(wt)), -1), torch.cat((neg(wt), pos(wt)), -1)
@@ -295,7 +304,7 @@ class TcVggEngine:
         dev = x.device
         sp, G = self.split, self.groups
         gdt = torch.float32 if sp else torch.bfloat16
-        rule = 1 if self.rule == "epsilon" else 0
+        rule = self.rule_id
         act = None
         for li, c in enumerate(self.convs):
             c.h, c.w = h, w
@@ -451,7 +460,8 @@ class TcVggEngine:
                 tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout * self.km, c.cin, 3,
                         EPI_MULX_UNPOOL if below.pool_after else EPI_MULX, dst, gain=st.gain[li - 1],
                         gain2=st.gain2[li - 1], row_img=rimg, pool_idx=st.idx[li - 1] if below.pool_after else None,
-                        a_phys=c.cout * self.rm if self.split else 0, groups=self.groups, split=int(self.split))
+                        a_phys=c.cout * self.rm if self.split else 0, groups=self.groups, split=int(self.split),
+                        rule=self.rule_id)
             elif below.pool_after:
                 tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL_UNPOOL, dst, gain=st.gain[li - 1],
                         row_img=rimg, pool_idx=st.idx[li - 1])
@@ -466,7 +476,8 @@ class TcVggEngine:
         fh, fw = st.feat_hw
         if self.general:
             check(lib().lrpx_tc_scale_rows_x(_ptr(r), _ptr(st.rz_last), _ptr(st.rz2_last), _ptr(rimg), _ptr(out), nq, fh,
-                                             fw, st.feat_c, self.groups, int(self.split), _stream()),
+                                             fw, st.feat_c, self.groups, int(self.split) | (2 if self.rule_id == 3 else 0),
+                                             _stream()),
                   "lrpx_tc_scale_rows_x")
         else:
             check(lib().lrpx_tc_scale_rows(_ptr(r), _ptr(st.rz_last), _ptr(rimg), _ptr(out), nq, fh, fw, st.feat_c,
@@ -549,7 +560,7 @@ class TcVggEngine:
             c0 = self.convs[0]
             if self.general:
                 tc_conv(s, c0.w_rel3, nq, c0.h, c0.w, c0.cout * self.km, 24, 3, EPI_INPUT3, out[q0:q1], row_img=rimg,
-                        x=st.x, a_phys=c0.cout * self.rm if self.split else 0, gain_mode=dmode)
+                        x=st.x, a_phys=c0.cout * self.rm if self.split else 0, gain_mode=dmode, rule=self.rule_id)
             elif c0.w_rel3 is not None:
                 tc_conv(s, c0.w_rel3, nq, c0.h, c0.w, c0.cout, 24, 3, EPI_INPUT3, out[q0:q1], row_img=rimg, x=st.x,
                         gain_mode=dmode)

@@ -355,9 +355,10 @@ class ExplainAOAAttention(ExplainGridTDAttention):
             self._expl_w_key = key
         return self._expl_w
 
-    def explainer_forward(self, feat, tokens, quirk_double_bias_ih=True):
+    def explainer_forward(self, feat, tokens, quirk_double_bias_ih=True, want_gates=False):
         """The explainer's teacher-forced forward (reference :999-1062) batched over images; returns the saved
-        state in the layout of lrpx_aoa_args.  Q3: the LSTM adds bias_ih twice (:873).
+        state in the layout of lrpx_aoa_args.  Q3: the LSTM adds bias_ih twice (:873).  ``want_gates`` also saves the
+        output gate ``o`` (the gradient explainers' state, reference :1371).
 
         The AoA decoder feeds nothing of the attention back into its LSTM (x_t = [emb_t | glob], :1030), so only the
         recurrence is sequential: T launches of ``lrpx_lstm_step_f32`` writing h, c, g, i, f straight into the (B,T,.)
@@ -391,11 +392,12 @@ class ExplainAOAAttention(ExplainGridTDAttention):
             pre = self._lx("pre", W_in, b, lambda: (W_in.t().contiguous(), b))(x.transpose(0, 1).reshape(T * B, E + H)).view(T, B, 4 * H)
             h, c = torch.zeros(B, T + 1, H, device=dev), torch.zeros(B, T + 1, H, device=dev)
             g, i, f = (torch.empty(B, T, H, device=dev) for _ in range(3))
+            o = torch.empty(B, T, H, device=dev) if want_gates else None
             hin = torch.zeros(2, B, H, device=dev)           # the step kernel's input rows, ping-ponged over the steps
             for t in range(T):
                 p, q = t & 1, (t & 1) ^ 1
                 ops.lstm_step(hin[p], Wp_hh, pre[t], 4, c[:, t], h[:, t + 1], c[:, t + 1], g[:, t], i[:, t], f[:, t],
-                              h_copy0=hin[q])
+                              h_copy0=hin[q], o=None if o is None else o[:, t])
             hn = h[:, 1:]                                                         # (B,T,H)
             hn2 = hn.reshape(B * T, H)
             qv = self._lx("q", mha.q_proj.weight, mha.q_proj.bias)(hn2).view(B, T, nh, dk).transpose(1, 2)   # (B,nh,T,dk)
@@ -409,6 +411,8 @@ class ExplainAOAAttention(ExplainGridTDAttention):
                       caoa_gate=gate.contiguous(), alpha=alpha.transpose(1, 2).contiguous(), pred=pred, h=h, c=c,
                       feat=feat, A_pre=A_pre.contiguous(), A=A.contiguous(), glob=glob, key=key,
                       value=value.contiguous())
+            if want_gates:
+                st["o"] = o
         return st
 
     _BEAM = "AoaBeamSearch"
@@ -540,3 +544,87 @@ class ExplainAOAAttention(ExplainGridTDAttention):
         T = self.caption_length
         _, r_words = self._decoder_lrp(list(range(T)), 0)
         return [r_words[t, :t + 1] for t in range(T)]
+
+
+# ================================================================================================ gradient family (f4)
+from models._gradient import GradientFamily, aoa_grad_weights      # noqa: E402
+
+
+class ExplainAOAGradient(GradientFamily, ExplainAOAAttention):
+    """reference :1257-1592."""
+    EX_TYPE = 'gradient'
+
+    def __init__(self, args, word_map, model=None, precision=None):
+        ExplainAOAAttention.__init__(self, args, word_map, model=model, precision=precision)
+        self._check_encoder()
+
+    def _grad_weights(self):
+        if getattr(self, "_gw", None) is None:
+            self._gw = aoa_grad_weights({k: v.detach() for k, v in self.model.state_dict().items()})
+        return self._gw
+
+    def _set_state(self, img, tokens, enc=None):
+        ExplainAOAAttention._set_state(self, img, tokens, enc)
+        if self._state is not None:
+            self.ot_act = self._state["o"][0]
+
+    def gradient_mha(self, d_context, alpha, head_idx):
+        """reference :1415-1433: d_value[p, head block] = d_context[head block] * alpha[head, p], zero on the other
+        heads.  d_context (1,H) or (H,), alpha (heads,P) -> (P,H).  A tensor expression on the inputs' device; the
+        batched path (``lrpx_aoa_decoder_grad_f32``) fuses it."""
+        H = self.model.hidden_dim
+        dk = H // alpha.size(0)
+        d_value = torch.zeros(alpha.size(1), H, device=alpha.device)
+        sl = slice(head_idx * dk, (head_idx + 1) * dk)
+        d_value[:, sl] = alpha[head_idx].unsqueeze(1) * d_context.reshape(-1)[sl].unsqueeze(0)
+        return d_value
+
+    def _decoder_grad(self, ts, head_idx):
+        toks = self.beam_caption_encode
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=self.device)
+        return ops.aoa_decoder_grad(self._state, self._grad_weights(), self.num_head, i32([0] * len(ts)), i32(list(ts)),
+                                    i32([toks[t + 1] for t in ts]), i32([head_idx] * len(ts)),
+                                    tc_gemm=(self.precision == 'bf16'))
+
+    def explain_caption_wordt(self, t, head_idx):
+        """reference :1435-1499 -> (d_img_feature (1,C,h,w), r_words (t+1,))."""
+        assert t < self.caption_length
+        d_feat, r_words = self._decoder_grad([t], head_idx)
+        fh, fw = self._feat_hw
+        return d_feat[0].t().reshape(1, -1, fh, fw), r_words[0, :t + 1]
+
+    def explain_caption(self, img_filepath, head_idx, t_list=None):
+        """reference :1517-1534."""
+        self.img_filepath = img_filepath
+        self.get_hidden_parameters(img_filepath)
+        if self.caption_length == 0:
+            return [], []
+        d_feat, r_words = self._decoder_grad(list(range(self.caption_length)), head_idx)
+        relevance_imgs, relevance_preceeding_words = self._explain_all(d_feat, r_words)
+        self.save_linguistic_explanation(relevance_preceeding_words)
+        return relevance_imgs, relevance_preceeding_words
+
+    def explain_caption_words(self, img_filepath, head_idx=0):
+        """reference :1536-1548 (whose call omits head_idx and cannot run): linguistic part only."""
+        self.img_filepath = img_filepath
+        self.get_hidden_parameters(img_filepath)
+        _, r_words = self._decoder_grad(list(range(self.caption_length)), head_idx)
+        return [r_words[t, :t + 1] for t in range(self.caption_length)]
+
+
+class ExplainAOAGuidedGradient(ExplainAOAGradient):
+    """reference :1594-1666: the decoder half is the plain gradient's, the encoder half guided backpropagation."""
+    EX_TYPE = 'GuidedBackpropagate'
+    RULE = "guided"
+
+
+class ExplainAOAGradCam(ExplainAOAGradient):
+    """reference :1669-1711."""
+    EX_TYPE = 'GradCam'
+    CAM = "cam"
+
+
+class ExplainAOAGuidedGradCam(ExplainAOAGuidedGradient):
+    """reference :1714-1776."""
+    EX_TYPE = 'GuidedGradCam'
+    CAM = "guided"

@@ -674,7 +674,7 @@ class ExplainGridTDAttention(object):
             self._lin_key = key
         return self._lin
 
-    def explainer_forward(self, feat, tokens, quirk_double_bias_ih=True):
+    def explainer_forward(self, feat, tokens, quirk_double_bias_ih=True, want_gates=False):
         """The explainer's teacher-forced forward (reference :941-1012) batched over images.
 
         feat: (B,P,C) pixel-major encoder output; tokens: (B,L) long, column 0 = <start>.  Returns the saved
@@ -687,7 +687,8 @@ class ExplainGridTDAttention(object):
         everything that does not depend on the recurrent state (embeddings, the input-side halves of the gate
         pre-activations, the vocabulary projection) is one batched GEMM over all T steps.  CUDA only: there is no
         CPU form in the product (tests/helpers.py holds the step-by-step tensor-op restatement the kernels are
-        checked against)."""
+        checked against).  ``want_gates`` also saves the output gates and the sentinel gate (o1, o2, sg): the state
+        of the gradient explainers (reference :1381-1419)."""
         if not feat.is_cuda:
             raise ops._lib.LrpxError("explainer_forward needs CUDA tensors: lrpx has no CPU fallback")
         m = self.model
@@ -720,6 +721,8 @@ class ExplainGridTDAttention(object):
             h1, c1, h2, c2 = (torch.zeros(B, T + 1, H, device=dev) for _ in range(4))
             g1, i1, f1, g2, i2, f2, st, ctx, ctx_hat = (new(B, T, H) for _ in range(9))
             alpha, beta = new(B, T, P), new(B, T)
+            o1, o2, sg = (new(B, T, H) for _ in range(3)) if want_gates else (None, None, None)
+            row = lambda x, t: None if x is None else x[:, t]
             # ---- staging rows of the recurrent GEMMs, ping-ponged over the steps: a step kernel reads ALL columns of
             # its input rows in every CTA while its CTAs write the new state, so the new state goes to the other copy
             hcat = torch.zeros(2, B, 2 * H, device=dev)       # [h2_t | h1_t]
@@ -730,19 +733,21 @@ class ExplainGridTDAttention(object):
                 # AdaLSTM: 4 gates + sentinel gate from [h2_t | h1_t] (+ the input-side halves in pre1[t])   :975-983
                 ops.lstm_step(hcat[p], W1p, pre1[t], 5, c1[:, t], h1[:, t + 1], c1[:, t + 1], g1[:, t], i1[:, t],
                               f1[:, t], s=st[:, t], h_copy0=hcat[q][:, H:], h_copy1=x2c[p][:, H:2 * H],
-                              h_copy2=hs[:, :H], s_copy=hs[:, H:])
+                              h_copy2=hs[:, :H], s_copy=hs[:, H:], o=row(o1, t), sg=row(sg, t))
                 hsp = lin["att"](hs)                                                              # (B,2K)
                 ops.adaptive_attention(A, img_proj, hsp, w_h, st[:, t], ctx[:, t], ctx_hat[:, t], alpha[:, t],
                                        beta[:, t], ctx_hat_copy=x2c[p][:, :H])
                 # LanguageLSTM from [ctx_hat_t | h1_{t+1} | h2_t]                                             :984-990
                 ops.lstm_step(x2c[p], W2p, b2, 4, c2[:, t], h2[:, t + 1], c2[:, t + 1], g2[:, t], i2[:, t], f2[:, t],
-                              h_copy0=hcat[q][:, :H], h_copy1=x2c[q][:, 2 * H:])
+                              h_copy0=hcat[q][:, :H], h_copy1=x2c[q][:, 2 * H:], o=row(o2, t))
             pred = lin["fc"]((ctx_hat + h2[:, 1:]).view(B * T, H)).view(B, T, m.vocab_size)
             x1 = torch.cat((h2[:, :T], xin), -1)
             x2 = torch.cat((ctx_hat, h1[:, 1:]), -1)
             st_ = dict(x1=x1, x2=x2, g1=g1, i1=i1, f1=f1, g2=g2, i2=i2, f2=f2, st=st, ctx=ctx, ctx_hat=ctx_hat,
                        alpha=alpha, beta=beta, pred=pred, h1=h1, c1=c1, h2=h2, c2=c2, feat=feat, avg=avg,
                        A_pre=A_pre.contiguous(), A=A.contiguous(), glob_pre=glob_pre)
+            if want_gates:
+                st_.update(o1=o1, o2=o2, sg=sg)
         return st_
 
     def teacherforce_forward(self, img, beam_caption_encode):
@@ -897,3 +902,77 @@ class ExplainGridTDAttention(object):
     def visualize_explanations(self, relevance_imgs, t=None):
         """The reference renders matplotlib figures (:1176-1211); plotting is out of scope (SURVEY.md §2 #3)."""
         return None
+
+
+# ================================================================================================ gradient family (f4)
+from models._gradient import GradientFamily, gridtd_grad_weights      # noqa: E402  (after the classes it extends)
+
+
+class ExplainGridTDGradient(GradientFamily, ExplainGridTDAttention):
+    """reference :1214-1582.  Gradient of the target word's logit with respect to the image (the decoder's attention
+    weights and gates held constant, as the reference's hand-written backward does) and the per-word sums of the
+    embedding gradients.  ``model=`` / ``precision=`` are keywords the reference does not have."""
+    EX_TYPE = 'gradient'
+
+    def __init__(self, args, word_map, model=None, precision=None):
+        ExplainGridTDAttention.__init__(self, args, word_map, model=model, precision=precision)
+        self._check_encoder()
+
+    def _grad_weights(self):
+        if getattr(self, "_gw", None) is None:
+            self._gw = gridtd_grad_weights({k: v.detach() for k, v in self.model.state_dict().items()})
+        return self._gw
+
+    def get_hidden_parameters(self, img_filepath):
+        """reference :1323-1422 (beam size 3, up to 50 words)."""
+        self.img = self.preprocess_img(img_filepath)
+        enc = self._find_caption(img_filepath, beam_size=3, max_cap_length=50)
+        self._set_state(self.img, self.beam_caption_encode, enc)
+
+    def _set_state(self, img, tokens, enc=None):
+        ExplainGridTDAttention._set_state(self, img, tokens, enc)
+        if self._state is not None:
+            st = self._state
+            self.o1t_act, self.o2t_act, self.sen_gate = st["o1"][0], st["o2"][0], st["sg"][0]
+
+    def _decoder_grad(self, ts):
+        toks = self.beam_caption_encode
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=self.device)
+        return ops.gridtd_decoder_grad(self._state, self._grad_weights(), i32([0] * len(ts)), i32(list(ts)),
+                                       i32([toks[t + 1] for t in ts]), guided=self.GUIDED_DECODER,
+                                       tc_gemm=(self.precision == 'bf16'))
+
+    def explain_caption_wordt(self, t):
+        """reference :1424-1508 (guided: :1588-1675) -> (d_img_feature (1,C,h,w), r_words (t+1,))."""
+        assert t < self.caption_length
+        d_feat, r_words = self._decoder_grad([t])
+        fh, fw = self._feat_hw
+        return d_feat[0].t().reshape(1, -1, fh, fw), r_words[0, :t + 1]
+
+    def explain_caption(self, img_filepath, t_list=None):
+        """reference :1525-1539: every word of the caption in one batched decoder call + one batched encoder pass."""
+        self.img_filepath = img_filepath
+        self.get_hidden_parameters(img_filepath)
+        if self.caption_length == 0:
+            return [], []
+        d_feat, r_words = self._decoder_grad(list(range(self.caption_length)))
+        return self._explain_all(d_feat, r_words)
+
+
+class ExplainiGridTDGuidedGradient(ExplainGridTDGradient):
+    """reference :1585-1749 (the class name's typo is the reference's): guided backpropagation."""
+    EX_TYPE = 'GuidedBackpropagate'
+    RULE = "guided"
+    GUIDED_DECODER = True
+
+
+class ExplainGridTDGradCam(ExplainGridTDGradient):
+    """reference :1752-1793: explain_cnn returns the (1, P) Grad-CAM map of the encoder output."""
+    EX_TYPE = 'GradCam'
+    CAM = "cam"
+
+
+class ExplainGridTDGuidedGradCam(ExplainiGridTDGuidedGradient):
+    """reference :1796-1859: guided backpropagation times the pyramid-expanded Grad-CAM map."""
+    EX_TYPE = 'GuidedGradCam'
+    CAM = "guided"

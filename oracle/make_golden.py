@@ -407,6 +407,114 @@ def golden_ablation(ns):
     print("ablation fixture:", toks, disappear.tolist(), img_diff.tolist(), word_diff.tolist())
 
 
+def _ref_gradient_explainer(ns_mod, cls_name, model, args, wm, tag):
+    """Builds one of the reference's gradient-family explainers through its own constructor (which loads a checkpoint
+    from args.weight), then swaps in the seeded model."""
+    path = f"/tmp/lrpx_ref/{tag}.pth"
+    torch.save({"state_dict": model.state_dict()}, path)
+    args = argparse.Namespace(**{**vars(args), "weight": path})
+    with quiet():
+        ex = getattr(ns_mod, cls_name)(args, wm)
+    return ex
+
+
+def golden_gradient(ns):
+    """Gradient-family explainers, run by the reference itself.
+    gridtd_grad_512 / aoa_grad_512: the hand-written decoder backward at the benched decoder size over fixed features
+    (stub encoder): saved gates, d_img_feature and r_words of ExplainGridTDGradient / ExplainiGridTDGuidedGradient /
+    ExplainAOAGradient, and the Grad-CAM maps.
+    gradient_e2e: a small decoder on a seeded VGG16 at 224x224: explain_cnn of the plain gradient (autograd) and of
+    guided backpropagation (the reference's ReLU hooks).  Guided Grad-CAM needs skimage (absent here): unpinned."""
+    # ---------------------------------------------------------------- gridTD decoder
+    V, H, E, T, seed, ts = 1000, 512, 512, 12, 201, [0, 7, 11]
+    wm = synth.word_map(V)
+    args = argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                              save_path="/tmp/lrpx_ref", dataset="syn", weight="")
+    with quiet():
+        model = ns.gridTDmodel.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(seed, V, H, E), strict=False)
+    feats = _features(seed + 1, 512, 14, 14)
+    toks = synth.tokens(seed + 2, T, V)
+    out = dict(V=V, H=H, E=E, T=T, seed=seed, tokens=np.array(toks), ts=np.array(ts), feats=feats)
+    for cls, key in (("ExplainGridTDGradient", "grad"), ("ExplainiGridTDGuidedGradient", "guided"),
+                     ("ExplainGridTDGradCam", "cam")):
+        ex = _ref_gradient_explainer(ns.gridTDmodel, cls, model, args, wm, "gridtd_grad")
+        ex.model.img_encoder = _StubEncoder(feats)
+        ex.model.beam_search = lambda *a, **k: ([" ".join(f"w{t}" for t in toks[1:])], toks[1:])
+        ex.preprocess_img = lambda p: torch.zeros(1, 3, 224, 224)
+        with torch.no_grad(), quiet():
+            ex.get_hidden_parameters("x")
+            ex.image_feature_proj = ex.image_feature_proj.transpose(1, 2)          # as explain_caption does (:1528)
+        if key == "grad":
+            out.update(predictions=ex.predictions, o1=ex.o1t_act, o2=ex.o2t_act, sen_gate=ex.sen_gate, betas=ex.betas,
+                       c1t=ex.c1t, c2t=ex.c2t)
+        for t in ts:
+            with torch.no_grad():
+                df, rw = ex.explain_caption_wordt(t)
+                if key == "cam":
+                    out[f"cam_{t}"] = ex.explain_cnn(df)
+                else:
+                    out[f"{key}_d_feat_{t}"] = df
+                    out[f"{key}_r_words_{t}"] = rw
+    save("gridtd_grad_512", **out)
+    # ---------------------------------------------------------------- AoA decoder
+    V, H, E, C, T, seed, cases = 1000, 512, 512, 512, 8, 211, [(0, 0), (5, 3), (7, 7)]
+    wm = synth.word_map(V)
+    with quiet():
+        model = ns.aoamodel.AOAModel(E, H, 8, V, "vgg16")
+    model.load_state_dict(synth.aoa_decoder_state(seed, V, H, E, C), strict=False)
+    feats = _features(seed + 1, C, 14, 14)
+    toks = synth.tokens(seed + 2, T, V)
+    out = dict(V=V, H=H, E=E, C=C, T=T, seed=seed, tokens=np.array(toks), cases=np.array(cases), feats=feats)
+    for cls, key in (("ExplainAOAGradient", "grad"), ("ExplainAOAGradCam", "cam")):
+        ex = _ref_gradient_explainer(ns.aoamodel, cls, model, args, wm, "aoa_grad")
+        ex.model.img_encoder = _StubEncoder(feats)
+        ex.model.beam_search = lambda *a, **k: ([" ".join(f"w{t}" for t in toks[1:])], toks[1:])
+        ex.preprocess_img = lambda p: torch.zeros(1, 3, 224, 224)
+        with torch.no_grad(), quiet():
+            ex.get_hidden_parameters("x")
+        if key == "grad":
+            out.update(predictions=ex.predictions, ot=ex.ot_act, context_aoa_gate=ex.context_aoa_gate)
+        for t, hd in cases:
+            with torch.no_grad():
+                df, rw = ex.explain_caption_wordt(t, hd)
+                if key == "cam":
+                    out[f"cam_{t}_{hd}"] = ex.explain_cnn(df)
+                else:
+                    out[f"d_feat_{t}_{hd}"] = df
+                    out[f"r_words_{t}_{hd}"] = rw
+    save("aoa_grad_512", **out)
+    # ---------------------------------------------------------------- end to end through a seeded VGG16
+    V, H, E, seed = 60, 64, 32, 221
+    wm = synth.word_map(V)
+    args = argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                              save_path="/tmp/lrpx_ref", dataset="syn", weight="")
+    with quiet():
+        model = ns.gridTDmodel.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(seed, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(seed + 1))
+    img = synth.images(seed + 2, 1)
+    out = dict(V=V, H=H, E=E, seed=seed)
+    toks = None
+    for cls, key in (("ExplainGridTDGradient", "grad"), ("ExplainiGridTDGuidedGradient", "guided")):
+        ex = _ref_gradient_explainer(ns.gridTDmodel, cls, model, args, wm, "grad_e2e")
+        orig = ex.model.beam_search
+        ex.model.beam_search = lambda im, w, beam_size=3, max_cap_length=50, orig=orig: orig(im, w, beam_size=beam_size, max_cap_length=7)
+        ex.preprocess_img = lambda p: img.clone()
+        with quiet():
+            imgs, words = ex.explain_caption("x")
+        if toks is None:
+            toks = list(ex.beam_caption_encode)
+            out["tokens"] = np.array(toks)
+        assert list(ex.beam_caption_encode) == toks
+        T = len(toks) - 1
+        for t in (0, T - 1):
+            out[f"{key}_img_{t}"] = imgs[t].detach()
+        out[f"{key}_words"] = np.concatenate([w.detach().numpy() for w in words])
+    save("gradient_e2e", **out)
+    print("gradient_e2e tokens:", toks)
+
+
 def _rev_word_map(V, stop):
     wm = synth.word_map(V)
     rev = {v: k for k, v in wm.items()}
@@ -506,7 +614,7 @@ def main():
     only = set(sys.argv[1:])          # optional: names of the generators to (re)run
     for fn in (golden_rules, golden_sequential_small, golden_vgg16, golden_resnet, golden_gridtd_decoder,
                golden_aoa_decoder, golden_adaptive_decoder, golden_block_image, golden_lrp_weights, golden_tune, golden_tune_bu,
-               golden_ablation):
+               golden_ablation, golden_gradient):
         if only and fn.__name__ not in only:
             continue
         print(fn.__name__)

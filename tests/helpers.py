@@ -120,3 +120,16 @@ def aoa_explainer_forward_ops(model, feat, tokens, quirk_double_bias_ih=True):
         st.update(feat=feat.contiguous(), A_pre=A_pre.contiguous(), A=A.contiguous(), glob=glob, key=key,
                   value=value.contiguous())
     return st
+
+
+def gridtd_grad_kernel_state(oracle_states, device):
+    """oracle.gridtd_explainer_forward(..., gradient=True) dicts -> stacked state of lrpx_gridtd_grad_args"""
+    step = D.GRIDTD_STEP_KEYS + ["o1", "o2", "sg"]
+    conv = [{k: st[_GRID_RENAME.get(k, k)] for k in D.GRIDTD_IMAGE_KEYS + step + D.GRIDTD_STEP1_KEYS} for st in oracle_states]
+    return D.stack_states(conv, D.GRIDTD_IMAGE_KEYS, step, D.GRIDTD_STEP1_KEYS, device)
+
+
+def aoa_grad_kernel_state(oracle_states, device):
+    step = D.AOA_STEP_KEYS + ["f", "o", "caoa_gate"]
+    conv = [{k: st[_AOA_RENAME.get(k, k)] for k in D.AOA_IMAGE_KEYS + step + D.AOA_STEP1_KEYS} for st in oracle_states]
+    return D.stack_states(conv, D.AOA_IMAGE_KEYS, step, D.AOA_STEP1_KEYS, device)

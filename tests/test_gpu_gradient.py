@@ -1,0 +1,269 @@
+"""GPU parity of the gradient-family explainers: the batched decoder-gradient kernels, Grad-CAM, the
+'gradient' / 'guided' rules of the tcgen05 chain and the mirrors of the reference's Explain*Gradient / *GuidedGradient /
+*GradCam / *GuidedGradCam classes — against fixtures the reference itself produced (gridtd_grad_512, aoa_grad_512,
+gradient_e2e) and against the oracle on ragged multi-image batches."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import lrp_oracle as O
+import synth
+from conftest import assert_close, spearman
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _pix(r):
+    """(1,C,h,w) -> (P,C) pixel-major"""
+    return r[0].reshape(r.shape[1], -1).t()
+
+
+def _rel_l2(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).norm() / b.norm())
+
+
+def _args(E, H, tmp_path):
+    return argparse.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                              save_path=str(tmp_path), dataset="syn", weight="")
+
+
+@pytest.mark.parametrize("tc_gemm", [False, True])
+def test_gridtd_decoder_grad_vs_reference_fixture(golden, tmp_path, tc_gemm):
+    """Explainer forward (fused kernels, incl. the extra gates) + lrpx_gridtd_decoder_grad_f32 vs the reference's own
+    ExplainGridTDGradient / ExplainiGridTDGuidedGradient / ExplainGridTDGradCam at the benched decoder size.
+    fp32 CUDA-core GEMMs: scale-relative 1e-5; bf16x3 tensor-core GEMMs: 1e-4."""
+    from lrpx import ops
+    from models import gridTDmodel as G
+    g = golden("gridtd_grad_512")
+    V, H, E = int(g["V"]), int(g["H"]), int(g["E"])
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(int(g["seed"]), V, H, E), strict=False)
+    model.to(DEV).eval()
+    ex = G.ExplainGridTDGradient(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="simt")
+    toks = g["tokens"].tolist()
+    feat = _pix(g["feats"]).unsqueeze(0).to(DEV).contiguous()
+    st = ex.explainer_forward(feat, torch.tensor([toks], device=DEV))
+    assert_close(st["pred"][0], g["predictions"], rtol=1e-4, atol=2e-5, what="predictions")
+    for k, ref in (("o1", "o1"), ("o2", "o2"), ("sg", "sen_gate")):
+        assert_close(st[k][0], g[ref], rtol=1e-4, atol=2e-6, what=k)
+    ts = g["ts"].tolist()
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    atol = 1e-4 if tc_gemm else 1e-5
+    for key, guided in (("grad", False), ("guided", True)):
+        d_feat, r_words = ops.gridtd_decoder_grad(st, ex._grad_weights(), i32([0] * len(ts)), i32(ts),
+                                                  i32([toks[t + 1] for t in ts]), guided=guided, tc_gemm=tc_gemm)
+        for q, t in enumerate(ts):
+            ref = _pix(g[f"{key}_d_feat_{t}"])
+            scale = ref.abs().max()
+            print(f"gridTD {key} tc_gemm={tc_gemm} t={t}: max scale-relative error "
+                  f"{float((d_feat[q].cpu() - ref).abs().max() / scale):.3e}")
+            assert_close(d_feat[q] / scale, ref / scale, rtol=1e-3, atol=atol, what=f"{key} d_feat t={t}")
+            assert_close(r_words[q, :t + 1], g[f"{key}_r_words_{t}"], rtol=1e-3, atol=atol, what=f"{key} r_words t={t}")
+            assert float(r_words[q, t + 1:].abs().sum()) == 0.0
+            if not guided:
+                cam = ops.grad_cam(feat, d_feat[q:q + 1])
+                assert_close(cam[0], g[f"cam_{t}"].reshape(-1), rtol=1e-3, atol=10 * atol, what=f"cam t={t}")
+
+
+@pytest.mark.parametrize("tc_gemm", [False, True])
+def test_aoa_decoder_grad_vs_reference_fixture(golden, tmp_path, tc_gemm):
+    from lrpx import ops
+    from models import aoamodel as A
+    g = golden("aoa_grad_512")
+    V, H, E, C = int(g["V"]), int(g["H"]), int(g["E"]), int(g["C"])
+    model = A.AOAModel(E, H, 8, V, "vgg16")
+    model.load_state_dict(synth.aoa_decoder_state(int(g["seed"]), V, H, E, C), strict=False)
+    model.to(DEV).eval()
+    ex = A.ExplainAOAGradient(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="simt")
+    toks = g["tokens"].tolist()
+    feat = _pix(g["feats"]).unsqueeze(0).to(DEV).contiguous()
+    st = ex.explainer_forward(feat, torch.tensor([toks], device=DEV))
+    assert_close(st["pred"][0], g["predictions"], rtol=1e-4, atol=2e-5, what="predictions")
+    assert_close(st["o"][0], g["ot"], rtol=1e-4, atol=2e-6, what="output gate")
+    assert_close(st["caoa_gate"][0], g["context_aoa_gate"], rtol=1e-4, atol=2e-5, what="aoa gate")
+    cases = g["cases"].tolist()
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    d_feat, r_words = ops.aoa_decoder_grad(st, ex._grad_weights(), 8, i32([0] * len(cases)), i32([t for t, _ in cases]),
+                                           i32([toks[t + 1] for t, _ in cases]), i32([h for _, h in cases]), tc_gemm=tc_gemm)
+    atol = 1e-4 if tc_gemm else 1e-5
+    for q, (t, hd) in enumerate(cases):
+        ref = _pix(g[f"d_feat_{t}_{hd}"])
+        scale = ref.abs().max()
+        print(f"AoA tc_gemm={tc_gemm} t={t} head={hd}: max scale-relative error "
+              f"{float((d_feat[q].cpu() - ref).abs().max() / scale):.3e}")
+        assert_close(d_feat[q] / scale, ref / scale, rtol=1e-3, atol=atol, what=f"d_feat {t},{hd}")
+        assert_close(r_words[q, :t + 1], g[f"r_words_{t}_{hd}"], rtol=1e-3, atol=atol, what=f"r_words {t},{hd}")
+        cam = ops.grad_cam(feat, d_feat[q:q + 1])
+        assert_close(cam[0], g[f"cam_{t}_{hd}"].reshape(-1), rtol=1e-3, atol=10 * atol, what=f"cam {t},{hd}")
+    # the named helper (reference :1415-1433)
+    dv = ex.gradient_mha(torch.arange(H, device=DEV, dtype=torch.float32), st["alpha"][0, 2], 3)
+    assert dv.shape == (st["alpha"].shape[-1], H) and float(dv[:, :3 * 64].abs().sum()) == 0.0
+    assert_close(dv[:, 3 * 64:4 * 64], st["alpha"][0, 2, 3].unsqueeze(1) * torch.arange(192, 256, device=DEV).float(), what="gradient_mha")
+
+
+def test_decoder_grad_batched_ragged_vs_oracle():
+    """several images, ragged captions, requests in arbitrary order incl. duplicates and t = 0; both decoders"""
+    from lrpx import ops
+    from models._gradient import gridtd_grad_weights, aoa_grad_weights
+    V, H, E = 120, 64, 32
+    p = synth.gridtd_decoder_state(7, V, H, E, C=64, n_pixel=16)
+    pa = synth.aoa_decoder_state(8, V, H, E, C=64)
+    gs, as_, toks = [], [], []
+    for b, T in enumerate([5, 3, 1]):
+        f = torch.randn(64, 4, 4, generator=torch.Generator().manual_seed(100 + b)).clamp(min=0)
+        tk = synth.tokens(200 + b, T, V)
+        toks.append(tk)
+        gs.append(O.gridtd_explainer_forward(p, f, tk, gradient=True))
+        as_.append(O.aoa_explainer_forward(pa, f, tk, 8, gradient=True))
+    reqs = [(0, 4), (1, 0), (2, 0), (0, 0), (1, 2), (0, 4), (0, 2)]
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    req_img, req_t = i32([b for b, _ in reqs]), i32([t for _, t in reqs])
+    req_word = i32([toks[b][t + 1] for b, t in reqs])
+    ks = helpers.gridtd_grad_kernel_state(gs, DEV)
+    W = helpers.to_dev(gridtd_grad_weights(p), DEV)
+    for guided in (False, True):
+        d_feat, r_words = ops.gridtd_decoder_grad(ks, W, req_img, req_t, req_word, guided=guided)
+        for q, (b, t) in enumerate(reqs):
+            df, rw = O.gridtd_gradient_wordt(p, gs[b], t, guided=guided)
+            scale = df.abs().max()
+            assert_close(d_feat[q] / scale, df / scale, rtol=1e-3, atol=1e-5, what=f"gridTD guided={guided} request {q}")
+            assert_close(r_words[q, :t + 1], rw, rtol=1e-3, atol=1e-5, what=f"gridTD r_words request {q}")
+    ka = helpers.aoa_grad_kernel_state(as_, DEV)
+    Wa = helpers.to_dev(aoa_grad_weights(pa), DEV)
+    heads = [q % 8 for q in range(len(reqs))]
+    d_feat, r_words = ops.aoa_decoder_grad(ka, Wa, 8, req_img, req_t, req_word, i32(heads))
+    for q, (b, t) in enumerate(reqs):
+        df, rw = O.aoa_gradient_wordt(pa, as_[b], t, heads[q])
+        scale = df.abs().max()
+        assert_close(d_feat[q] / scale, df / scale, rtol=1e-3, atol=1e-5, what=f"AoA request {q}")
+        assert_close(r_words[q, :t + 1], rw, rtol=1e-3, atol=1e-5, what=f"AoA r_words request {q}")
+
+
+@pytest.mark.parametrize("guided", [False, True])
+@pytest.mark.parametrize("precision", ["simt", "fp32", "bf16"])
+def test_encoder_gradient_vs_oracle(precision, guided):
+    """The image gradient / guided backpropagation through a VGG-style encoder at 64x64: the tcgen05 chain in its
+    'gradient' / 'guided' rule (fp32-accurate and bf16 modes) and the fp32 CUDA-core path vs the oracle's layer-by-layer
+    backward (= autograd; guided = the reference's ReLU hooks).  Two images, five requests."""
+    import torch.nn as nn
+    from LRPtools import lrp_wrapper
+    from lrpx import tc
+    cfg = [64, 64, "M", 128, 128, "M", 256, "M", 256]
+    sd = synth.vgg_state(91, cfg)
+    layers = O.vgg_layers_from_state(sd, cfg)
+    x = synth.images(92, 2, 64)
+    feat = O.sequential_forward(layers, x)[-1]                                  # (2,256,8,8)
+    gen = torch.Generator().manual_seed(93)
+    rows = [0, 1, 1, 0, 1]
+    tgt = torch.randn(len(rows), *feat.shape[1:], generator=gen)
+    want = torch.cat([O.sequential_gradient(layers, x[b:b + 1], tgt[q:q + 1], guided=guided) for q, b in enumerate(rows)])
+    if precision == "simt":
+        mods, idx = [], 0
+        for v in cfg:
+            if v == "M":
+                mods.append(nn.MaxPool2d(2, 2)); idx += 1
+            else:
+                c = nn.Conv2d(sd[f"{idx}.weight"].shape[1], v, 3, padding=1)
+                c.load_state_dict({"weight": sd[f"{idx}.weight"], "bias": sd[f"{idx}.bias"]})
+                mods += [c, nn.ReLU(True)]; idx += 2
+        enc = nn.Sequential(*mods).to(DEV)
+        got = torch.cat([lrp_wrapper.encoder_gradient_simt(enc, x[b:b + 1].to(DEV), tgt[q:q + 1].to(DEV), guided)
+                         for q, b in enumerate(rows)])
+    else:
+        ws = [sd[k] for k in sd if k.endswith("weight")]
+        bs = [sd[k] for k in sd if k.endswith("bias")]
+        eng = tc.TcVggEngine(ws, bs, cfg, DEV, precision=precision, rule="guided" if guided else "gradient")
+        st = eng.forward(x.to(DEV))
+        assert_close(eng.features(st, "nchw"), feat, rtol=2e-2 if precision == "bf16" else 1e-4,
+                     atol=(2e-2 if precision == "bf16" else 2e-5) * float(feat.abs().max()), what="features")
+        got = eng.relevance(st, tgt.flatten(2).transpose(1, 2).contiguous().to(DEV), torch.tensor(rows, dtype=torch.int32, device=DEV))
+    scale = want.abs().max()
+    err = float((got.cpu() - want).abs().max() / scale)
+    print(f"encoder gradient precision={precision} guided={guided}: max scale-relative error {err:.3e}, rel-L2 "
+          f"{_rel_l2(got, want):.3e}, Spearman {spearman(got, want):.5f}")
+    if precision == "simt":
+        assert_close(got / scale, want / scale, rtol=1e-4, atol=1e-5, what="simt gradient")
+    elif precision == "fp32":
+        assert _rel_l2(got, want) < 2e-3 and err < 5e-3
+    else:
+        assert _rel_l2(got, want) < 8e-2 and spearman(got, want) > 0.98
+
+
+@pytest.mark.parametrize("cls,key", [("ExplainGridTDGradient", "grad"), ("ExplainiGridTDGuidedGradient", "guided")])
+@pytest.mark.parametrize("precision", ["fp32", "simt"])
+def test_gradient_explainers_end_to_end_vs_reference_fixture(golden, tmp_path, cls, key, precision):
+    """explain_caption of the mirrors vs the reference's own run (fixture gradient_e2e: seeded VGG16 at 224x224, small
+    decoder, caption search capped at 7 words): same caption, heat-maps of the first and the last word, all word
+    relevances.  'simt' = fp32 CUDA cores (scale-relative 2e-4: 13 conv layers of fp32 summation-order noise on a signed
+    gradient); 'fp32' = the tcgen05 chain in its fp32-accurate mode (rel-L2 5e-3)."""
+    from models import gridTDmodel as G
+    g = golden("gradient_e2e")
+    V, H, E, seed = int(g["V"]), int(g["H"]), int(g["E"]), int(g["seed"])
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(seed, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(seed + 1))
+    model.to(DEV).eval()
+    ex = getattr(G, cls)(_args(E, H, tmp_path), synth.word_map(V), model=model, precision=precision)
+    img = synth.images(seed + 2, 1).to(DEV)
+    ex.preprocess_img = lambda p: img
+    find = ex._find_caption
+    ex._find_caption = lambda path, beam_size, max_cap_length: find(path, beam_size, 7)
+    imgs, words = ex.explain_caption("synthetic.jpg")
+    toks = ex.beam_caption_encode
+    assert toks == g["tokens"].tolist(), (toks, g["tokens"].tolist())
+    T = len(toks) - 1
+    assert_close(torch.cat(words), g[f"{key}_words"], rtol=1e-3, atol=1e-4, what="word relevances")
+    for t in (0, T - 1):
+        ref = g[f"{key}_img_{t}"]
+        scale = ref.abs().max()
+        err = float((imgs[t].cpu() - ref).abs().max() / scale)
+        print(f"{cls} precision={precision} t={t}: max scale-relative error {err:.3e}, rel-L2 {_rel_l2(imgs[t], ref):.3e}, "
+              f"Spearman {spearman(imgs[t], ref):.5f}")
+        if precision == "simt":
+            assert_close(imgs[t] / scale, ref / scale, rtol=1e-3, atol=2e-4, what=f"heat-map t={t}")
+        else:
+            assert _rel_l2(imgs[t], ref) < 5e-3, (t, _rel_l2(imgs[t], ref))
+    # explain_caption_wordt / explain_cnn, one word at a time, give the same as the batched call
+    d_img, rw = ex.explain_caption_wordt(T - 1)
+    one = ex.explain_cnn(d_img)
+    assert_close(one, imgs[T - 1], rtol=1e-5, atol=1e-6 * float(imgs[T - 1].abs().max()), what="single-word path")
+
+
+def test_gradcam_classes_and_guided_gradcam(golden, tmp_path):
+    """ExplainGridTDGradCam.explain_cnn -> (1, P) map (checked against the oracle's grad_cam of the oracle's gradient);
+    ExplainGridTDGuidedGradCam = guided backpropagation x the pyramid-expanded map (expansion operator checked against
+    scipy in tests/test_models_cpu.py; skimage itself is absent: unpinned)."""
+    from models import gridTDmodel as G
+    from models._gradient import expand_operator
+    g = golden("gradient_e2e")
+    V, H, E, seed = int(g["V"]), int(g["H"]), int(g["E"]), int(g["seed"])
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(seed, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(seed + 1))
+    model.to(DEV).eval()
+    img = synth.images(seed + 2, 1).to(DEV)
+    toks = g["tokens"].tolist()
+    out = {}
+    for cls in ("ExplainGridTDGradCam", "ExplainGridTDGuidedGradCam", "ExplainiGridTDGuidedGradient"):
+        ex = getattr(G, cls)(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="fp32")
+        ex.img = img
+        ex.beam_caption_encode = toks
+        ex._set_state(img, toks)
+        t = len(toks) - 2
+        d_img, _ = ex.explain_caption_wordt(t)
+        out[cls] = (ex, d_img, ex.explain_cnn(d_img))
+    ex, d_img, cam = out["ExplainGridTDGradCam"]
+    assert cam.shape == (1, 196)
+    want = O.grad_cam(ex._state["feat"][0].cpu(), _pix(d_img.cpu()))
+    assert_close(cam[0], want, rtol=1e-3, atol=1e-5, what="Grad-CAM map")
+    ex2, d_img2, ggc = out["ExplainGridTDGuidedGradCam"]
+    guided = out["ExplainiGridTDGuidedGradient"][2]
+    cam2 = O.grad_cam(ex2._state["feat"][0].cpu(), _pix(d_img2.cpu())).reshape(14, 14).double()
+    K = torch.tensor(expand_operator(14, 16))
+    up = (K @ cam2 @ K.t()).float()
+    assert_close(ggc.cpu(), guided.cpu() * up, rtol=1e-4, atol=1e-6 * float(guided.abs().max()), what="guided Grad-CAM")

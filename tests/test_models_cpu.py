@@ -310,3 +310,35 @@ def test_tpfp_split_host_logic(golden):
     tp, fp = AblationExperiments.tpfp_split(toks, frequent, [g["ref_caps_0"].tolist(), g["ref_caps_1"].tolist()], special)
     assert [toks[t + 1] for t in tp] == g["tp_words"].tolist() and [toks[t + 1] for t in fp] == g["fp_words"].tolist()
     assert AblationExperiments.tpfp_split(toks, [], [toks], special) == ([], [])
+
+
+def test_expand_operator_matches_scipy():
+    """models/_gradient.py::expand_operator (pyramid_expand along one axis as a matrix) against the same two steps done
+    with scipy: bilinear interpolation at (r + 0.5)/16 - 0.5 with mirrored borders, then gaussian_filter(sigma = 16/3,
+    mode='reflect').  (skimage, whose pyramid_expand this restates, is not installed: parity unpinned.)"""
+    import numpy as np
+    from scipy import ndimage
+    from models._gradient import expand_operator
+    rng = np.random.default_rng(5)
+    cam = rng.random((14, 14))
+    K = expand_operator(14, 16)
+    assert K.shape == (224, 14) and np.allclose(K.sum(1), 1.0)
+    coords = (np.arange(224) + 0.5) / 16 - 0.5
+    yy, xx = np.meshgrid(coords, coords, indexing="ij")
+    resized = ndimage.map_coordinates(cam, [yy, xx], order=1, mode="mirror")
+    want = ndimage.gaussian_filter(resized, sigma=2 * 16 / 6.0, mode="reflect")
+    got = K @ cam @ K.T
+    assert np.abs(got - want).max() < 1e-12
+
+
+def test_gradient_family_classes_mirror_the_reference_names():
+    from models import gridTDmodel as G, aoamodel as A
+    for mod, names in ((G, ["ExplainGridTDGradient", "ExplainiGridTDGuidedGradient", "ExplainGridTDGradCam",
+                            "ExplainGridTDGuidedGradCam"]),
+                       (A, ["ExplainAOAGradient", "ExplainAOAGuidedGradient", "ExplainAOAGradCam", "ExplainAOAGuidedGradCam"])):
+        for n in names:
+            cls = getattr(mod, n)
+            for meth in ("get_hidden_parameters", "explain_caption_wordt", "explain_cnn", "explain_caption",
+                         "teacherforce_forward"):
+                assert callable(getattr(cls, meth)), (n, meth)
+    assert G.ExplainGridTDGuidedGradCam.EX_TYPE == "GuidedGradCam" and A.ExplainAOAGradCam.EX_TYPE == "GradCam"
