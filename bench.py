@@ -67,6 +67,8 @@ def parse(argv=None):
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--library-encoder", action="store_true",
                     help="config 5: run the fixed VGG16 forward through the library convolutions instead of the tcgen05 engine")
+    ap.add_argument("--method", default="lrp", choices=["lrp", "gradient", "guided"],
+                    help="config 2: the explainer family (gradient / guided: the f4 explainers, device-resident timing only)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run 1 warm-up + 1 step and exit (the command line captured under ncu for profiles/)")
     ap.add_argument("--cpu-words", type=int, default=19, help="words per image of the bounded CPU sample")
@@ -1123,8 +1125,73 @@ class _Cpu5Stub:
 RUNNERS = {2: run_config2, 3: run_config3, 4: run_config4, 5: run_config5}
 
 
+def run_gradient(args, ctx, brief=True):
+    """config 2 with the gradient-family explainers in place of LRP: 64 images x 19 words through
+    ExplainGridTDGradient (``method`` 'gradient') or ExplainiGridTDGuidedGradient ('guided'): encoder forward + ReLU masks,
+    explainer forward, batched decoder gradient, the tcgen05 chain in its gradient / guided rule.  Device-resident
+    timing plus a parity figure against the oracle's backward (= autograd / the reference's ReLU hooks) on one image."""
+    import argparse as ap
+    import synth
+    from models import gridTDmodel as G
+    from lrpx.pipeline import BatchExplainer
+    dev = ctx.dev
+    method = args.method
+    V, H, E = args.vocab, 512, 512
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(1000, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(2000))
+    model.to(dev).eval()
+    ns = ap.Namespace(embed_dim=E, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                      save_path="/tmp/lrpx_bench", dataset="syn", weight="")
+    cls = G.ExplainGridTDGradient if method == "gradient" else G.ExplainiGridTDGuidedGradient
+    ex = cls(ns, synth.word_map(V), model=model, precision=args.precision)
+    imgs_h, toks_h = problem_inputs(args, 0)
+    imgs_d, toks_d = imgs_h.to(dev), toks_h.to(dev)
+    B, T = args.images, args.words
+    Q = B * T
+    heat = torch.empty(Q, 3, 224, 224, device=dev, dtype=torch.float32)
+    pipe = BatchExplainer(ex, chunk=args.chunk, use_graph=not args.no_graph)
+    for _ in range(args.warmup):
+        pipe.explain(imgs_d, toks_d, out=heat)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        heat, _ = pipe.explain(imgs_d, toks_d, out=heat)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    out = {"metric": method + "_explanations_per_s", "value": round(Q / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 3),
+           "dtype": "bf16" if args.precision == "bf16" else "bf16x3", "config": {"workload": f"config2 with the {method} "
+           f"explainer: {B} images x {T} words, VGG16 224x224, precision {args.precision}, inputs resident in HBM"}}
+    if not args.no_cpu_baseline:
+        O = _oracle()
+        p = {k: v.detach().cpu() for k, v in model.state_dict().items() if not k.startswith("img_encoder")}
+        layers = O.vgg_layers_from_state({k[len("img_encoder.encoder."):]: v.detach().cpu() for k, v in model.state_dict().items()
+                                          if k.startswith("img_encoder.encoder.")})
+        x = imgs_h[:1]
+        feat = O.sequential_forward(layers, x)[-1]
+        st = O.gridtd_explainer_forward(p, feat[0], toks_h[0].tolist(), gradient=True)
+        rl2, sp = [], []
+        for t in (0, T - 1):
+            df, _ = O.gridtd_gradient_wordt(p, st, t, guided=(method == "guided"))
+            want = O.sequential_gradient(layers, x, df.t().reshape(1, -1, *feat.shape[-2:]), guided=(method == "guided"))
+            got = heat[t:t + 1].cpu()
+            rl2.append(float((got - want).norm() / want.norm()))
+            sp.append(spearman(got, want))
+        out["parity"] = {"against": "oracle backward (autograd-equivalent; guided = the reference's ReLU hooks), image 0, words 0 and T-1",
+                         "rel_l2_max": max(rl2), "spearman_min": min(sp)}
+    return out
+
+
 def run_ours(args):
     ctx = Ctx()
+    if args.method != "lrp":
+        if args.config != 2 or ctx.world != 1:
+            raise SystemExit("--method gradient / guided: config 2 on one GPU")
+        print(json.dumps(run_gradient(args, ctx)), flush=True)
+        ctx.close()
+        return
     out = RUNNERS[args.config](args, ctx)
     if out is not None and args.also and ctx.world == 1:
         also = {}
@@ -1133,7 +1200,10 @@ def run_ours(args):
                                  ("config3", 3, dict(steps=8)), ("config4", 4, dict(steps=4)),
                                  ("config4_fp32_accurate", 4, dict(precision="fp32", steps=2, images=128)),
                                  ("config5", 5, dict(steps=4, precision="fp32")),
-                                 ("config5_library_encoder", 5, dict(steps=4, precision="fp32", library_encoder=True))):
+                                 ("config5_library_encoder", 5, dict(steps=4, precision="fp32", library_encoder=True)),
+                                 ("config2_gradient", 2, dict(method="gradient", precision="fp32", steps=3)),
+                                 ("config2_guided", 2, dict(method="guided", precision="fp32", steps=3)),
+                                 ("config2_guided_bf16", 2, dict(method="guided", precision="bf16", steps=4))):
             a2 = argparse.Namespace(**vars(args))
             a2.config, a2.also, a2.warmup = cfg, False, 3
             a2.images = {2: 64, 3: 64, 4: 512, 5: 128}[cfg]
@@ -1141,7 +1211,7 @@ def run_ours(args):
                 setattr(a2, k, v)
             try:
                 torch.cuda.empty_cache()
-                r = RUNNERS[cfg](a2, ctx, brief=True)
+                r = (run_gradient if name.startswith("config2_g") else RUNNERS[cfg])(a2, ctx, brief=True)
                 also[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "config", "e2e", "roofline",
                                                 "cpu_baseline", "parity", "allreduce", "breakdown_ms") if k in r}
                 also[name]["config"] = r["config"]["workload"]

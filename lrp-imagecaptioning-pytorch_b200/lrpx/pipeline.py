@@ -28,7 +28,12 @@ class BatchExplainer:
                              "precision='fp32' (fp32-accurate mode) or 'bf16'")
         self.ex = explainer
         self.eng = explainer.engine()
-        self.W = explainer._lrp_weights()
+        # gradient-family explainers (models/_gradient.py): same pipeline, the decoder-gradient kernels and the chain's
+        # 'gradient' / 'guided' rule instead of the relevance ones
+        self.is_gradient = hasattr(explainer, "_grad_weights")
+        if self.is_gradient and getattr(explainer, "CAM", None):
+            raise ValueError("BatchExplainer covers the gradient and guided-backpropagation explainers, not the CAM variants")
+        self.W = explainer._grad_weights() if self.is_gradient else explainer._lrp_weights()
         self.chunk = chunk
         self.use_graph = use_graph
         # decoder GEMMs as bf16x3 on the tensor cores in both chain modes (measured 1e-5 of max off the fp32 CUDA-core
@@ -60,7 +65,13 @@ class BatchExplainer:
         feat = self.eng.features(est, "pixel")
         st = self.ex.explainer_forward(feat, tokens)
         req_word = tokens[req_img.long(), req_t.long() + 1].to(torch.int32)       # the word each request explains
-        if self.is_aoa:
+        if self.is_gradient and self.is_aoa:
+            r_feat, r_words = ops.aoa_decoder_grad(st, self.W, self.ex.num_head, req_img, req_t, req_word,
+                                                   torch.full_like(req_t, self.head_idx), tc_gemm=self.tc_gemm)
+        elif self.is_gradient:
+            r_feat, r_words = ops.gridtd_decoder_grad(st, self.W, req_img, req_t, req_word,
+                                                      guided=self.ex.GUIDED_DECODER, tc_gemm=self.tc_gemm)
+        elif self.is_aoa:
             r_feat, r_words = ops.aoa_decoder_lrp(st, self.W, self.ex.num_head, req_img, req_t, req_word,
                                                   torch.full_like(req_t, self.head_idx), tc_gemm=self.tc_gemm)
         elif self.is_adaptive:

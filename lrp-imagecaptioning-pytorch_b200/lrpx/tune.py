@@ -131,14 +131,18 @@ class LrpCiderTuneStep:
     sampled captions with ``model.sample_lrp`` (the LRP weights of every step come from ``lrpx_fc_lrp_weights_f32``),
     self-critical reward, RewardCriterion, gradient clamp, optimizer step.
 
-    ``reward_fn(greedy_seq, all_caps, sampled_seq, word_map) -> (B, L) array / tensor`` is the caller's scorer — the
-    reference's ``get_self_critical_reward`` (modelutils.py:200-238) runs the CIDEr / BLEU scorers of pycocoevalcap on
-    the host, which are outside this path (SURVEY.md §8 out of scope).  Single process, like the reference's loop."""
+    ``reward_fn(greedy_seq, all_caps, sampled_seq, word_map) -> (B, L) array / tensor``; None = the reference's
+    ``get_self_critical_reward`` with its training weights (train.py:264: CIDEr 1, BLEU 0), restated in ``lrpx.scst``
+    (host n-gram counting like the reference's pycocoevalcap scorers; pinned by fixture scst_reward).  Single process,
+    like the reference's loop."""
 
-    def __init__(self, model, word_map, reward_fn, optimizer=None, lr=1e-5, grad_clip=None, fix_encoder=True):
+    def __init__(self, model, word_map, reward_fn=None, optimizer=None, lr=1e-5, grad_clip=None, fix_encoder=True):
         self.model = model
         self.word_map = word_map
         self.rev_word_map = {v: k for k, v in word_map.items()}
+        if reward_fn is None:
+            from . import scst
+            reward_fn = lambda greedy, caps, gen, wm: scst.self_critical_reward(greedy, caps, gen, wm, 1.0, 0.0)
         self.reward_fn = reward_fn
         if fix_encoder:
             for name, p in model.named_parameters():

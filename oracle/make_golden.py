@@ -515,6 +515,46 @@ def golden_gradient(ns):
     print("gradient_e2e tokens:", toks)
 
 
+def golden_scst(ns):
+    """get_self_critical_reward (models/modelutils.py:200-238) run by the reference with its vendored CIDEr / BLEU
+    scorers on seeded sampled / greedy / ground-truth captions: CIDEr-only (the training setting, train.py:193), BLEU-only
+    and a mix; plus RewardCriterion."""
+    sys.path.insert(0, ref_shim.REFERENCE_ROOT)
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_modelutils", os.path.join(ref_shim.REFERENCE_ROOT, "models/modelutils.py"))
+        mu = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mu)
+    finally:
+        sys.path.remove(ref_shim.REFERENCE_ROOT)
+    V, B, L, R = 40, 12, 9, 3
+    wm = synth.word_map(V)
+    g = torch.Generator().manual_seed(231)
+
+    def caps(n, length):
+        out = torch.randint(1, 14, (n, length), generator=g)              # a small active vocabulary: n-grams repeat
+        for i in range(n):
+            k = int(torch.randint(3, length + 1, (1,), generator=g))
+            if k < length:
+                out[i, k] = wm['<end>']
+                out[i, k + 1:] = 0
+        return out
+    gen, greedy = caps(B, L), caps(B, L)
+    greedy[0] = gen[0]
+    gts = caps(B * R, L + 2).view(B, R, L + 2)
+    gts[:, :, 0] = wm['<start>']
+    gts[1, 0, 1:L + 1] = gen[1]                                            # an exact match among the references
+    data_gts = [[gts[b, r].numpy() for r in range(R)] for b in range(B)]
+    out = dict(V=V, gen=gen, greedy=greedy, gts=gts)
+    for tag, (cw, bw) in {"cider": (1.0, 0.0), "bleu": (0.0, 1.0), "mix": (0.7, 0.3)}.items():
+        out["reward_" + tag] = mu.get_self_critical_reward(greedy, data_gts, gen, wm, cw, bw)
+    logp = -torch.rand(B, L, generator=g)
+    rew = torch.from_numpy(out["reward_cider"]).float()
+    out["logp"] = logp
+    out["loss"] = mu.RewardCriterion()(logp, gen, rew)
+    save("scst_reward", **out)
+
+
 def _rev_word_map(V, stop):
     wm = synth.word_map(V)
     rev = {v: k for k, v in wm.items()}
@@ -614,7 +654,7 @@ def main():
     only = set(sys.argv[1:])          # optional: names of the generators to (re)run
     for fn in (golden_rules, golden_sequential_small, golden_vgg16, golden_resnet, golden_gridtd_decoder,
                golden_aoa_decoder, golden_adaptive_decoder, golden_block_image, golden_lrp_weights, golden_tune, golden_tune_bu,
-               golden_ablation, golden_gradient):
+               golden_ablation, golden_gradient, golden_scst):
         if only and fn.__name__ not in only:
             continue
         print(fn.__name__)

@@ -342,3 +342,28 @@ def test_gradient_family_classes_mirror_the_reference_names():
                          "teacherforce_forward"):
                 assert callable(getattr(cls, meth)), (n, meth)
     assert G.ExplainGridTDGuidedGradCam.EX_TYPE == "GuidedGradCam" and A.ExplainAOAGradCam.EX_TYPE == "GradCam"
+
+
+def test_self_critical_reward_vs_reference_fixture(golden):
+    """models/modelutils.get_self_critical_reward (own CIDEr / BLEU restatement in lrpx.scst) and RewardCriterion vs
+    the reference's own functions with its vendored pycocoevalcap scorers (fixture scst_reward): CIDEr only (the
+    training setting), BLEU only, and a weighted mix."""
+    import numpy as np
+    import torch
+    from models import modelutils as mu
+    g = golden("scst_reward")
+    wm = synth.word_map(int(g["V"]))
+    gen, greedy, gts = g["gen"], g["greedy"], g["gts"]
+    data_gts = [[gts[b, r].numpy() for r in range(gts.shape[1])] for b in range(gts.shape[0])]
+    for tag, (cw, bw) in {"cider": (1.0, 0.0), "bleu": (0.0, 1.0), "mix": (0.7, 0.3)}.items():
+        got = mu.get_self_critical_reward(greedy, data_gts, gen, wm, cw, bw)
+        want = g["reward_" + tag].numpy()
+        assert got.shape == want.shape and got.dtype == np.float64
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), tag
+        assert np.abs(want).max() > 0.05
+    assert float(got[0].max()) == 0.0                      # identical sampled and greedy captions: no advantage
+    loss = mu.RewardCriterion()(g["logp"], gen, torch.from_numpy(g["reward_cider"].numpy()).float())
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    rev = {v: k for k, v in wm.items()}
+    s = mu.array_to_str(gen[2].tolist(), rev, wm['<end>'])
+    assert '<start>' not in s and '<pad>' not in s
