@@ -278,3 +278,73 @@ def test_gradcam_classes_and_guided_gradcam(golden, tmp_path):
     K = torch.tensor(expand_operator(14, 16))
     up = (K @ cam2 @ K.t()).float()
     assert_close(ggc.cpu(), guided.cpu() * up, rtol=1e-4, atol=1e-6 * float(guided.abs().max()), what="guided Grad-CAM")
+
+
+@pytest.mark.parametrize("cls,guided", [("ExplainAOAGradient", False), ("ExplainAOAGuidedGradient", True)])
+def test_aoa_gradient_explainers_end_to_end_vs_oracle(tmp_path, cls, guided):
+    """ExplainAOAGradient / ExplainAOAGuidedGradient.explain_caption(img, head) through a seeded VGG-style encoder at 64x64
+    (fp32 CUDA-core path, so that the ReLU masks are the oracle's): caption from the mirror's own search, decoder gradient
+    + encoder backward of the oracle on that caption."""
+    import torch.nn as nn
+    from models import aoamodel as A
+    V, H, E, head = 80, 64, 32, 5
+    model = A.AOAModel(E, H, 8, V, "vgg16")
+    dec = synth.aoa_decoder_state(301, V, H, E, 512)
+    model.load_state_dict(dec, strict=False)
+    vs = synth.vgg_state(302)
+    model.img_encoder.encoder.load_state_dict(vs)
+    model.to(DEV).eval()
+    ex = getattr(A, cls)(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="simt")
+    img = synth.images(303, 1, 64)
+    ex.preprocess_img = lambda p: img.to(DEV)
+    find = ex._find_caption
+    ex._find_caption = lambda path, beam_size, max_cap_length: find(path, beam_size, 6)
+    imgs, words = ex.explain_caption("synthetic.jpg", head)
+    toks = ex.beam_caption_encode
+    T = len(toks) - 1
+    assert T >= 1 and len(imgs) == T and imgs[0].shape == (1, 3, 64, 64)
+    layers = O.vgg_layers_from_state(vs)
+    feat = O.sequential_forward(layers, img)[-1]
+    st = O.aoa_explainer_forward(dec, feat[0], toks, 8, gradient=True)
+    assert_close(ex.predictions, st["pred"], rtol=1e-3, atol=1e-4, what="predictions")
+    for t in range(T):
+        df, rw = O.aoa_gradient_wordt(dec, st, t, head)
+        want = O.sequential_gradient(layers, img, df.t().reshape(1, -1, *feat.shape[-2:]), guided=guided)
+        scale = want.abs().max()
+        assert _rel_l2(imgs[t], want) < 5e-3, (t, _rel_l2(imgs[t], want))
+        off = ((imgs[t].cpu() - want).abs() > 2e-4 * scale + 1e-3 * want.abs()).float().mean()
+        assert float(off) < 5e-2, (t, float(off))
+        assert_close(words[t], rw, rtol=1e-3, atol=1e-5, what=f"r_words t={t}")
+
+
+@pytest.mark.parametrize("cls", ["ExplainGridTDGradient", "ExplainiGridTDGuidedGradient"])
+def test_batch_explainer_with_gradient_explainers(tmp_path, cls):
+    """lrpx.pipeline.BatchExplainer drives the gradient-family explainers like the relevance ones: 2 images x 4 words in
+    one pass (eager and CUDA-graph replay) = the per-image explain_caption_wordt / explain_cnn results."""
+    from models import gridTDmodel as G
+    from lrpx.pipeline import BatchExplainer
+    V, H, E, T = 60, 64, 32, 4
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(311, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(312))
+    model.to(DEV).eval()
+    ex = getattr(G, cls)(_args(E, H, tmp_path), synth.word_map(V), model=model, precision="fp32")
+    imgs = synth.images(313, 2).to(DEV)
+    toks = torch.tensor([synth.tokens(314, T, V), synth.tokens(315, T, V)], device=DEV)
+    # tc_gemm=False: the decoder GEMMs on fp32 CUDA cores, as the one-word path of precision 'fp32' runs them
+    heat, r_words = BatchExplainer(ex, chunk=4, tc_gemm=False).explain(imgs, toks)
+    heat = heat.clone()
+    heat_g, words_g = BatchExplainer(ex, chunk=4, use_graph=True, tc_gemm=False).explain(imgs, toks)
+    assert_close(heat_g, heat, rtol=0, atol=0, what="graph replay")
+    assert_close(words_g, r_words, rtol=0, atol=0, what="graph replay words")
+    for b in range(2):
+        ex.img = imgs[b:b + 1]
+        ex.beam_caption_encode = toks[b].tolist()
+        ex._set_state(ex.img, ex.beam_caption_encode)
+        for t in (0, T - 1):
+            d_img, rw = ex.explain_caption_wordt(t)
+            one = ex.explain_cnn(d_img)
+            q = b * T + t
+            # the explainer forward's library GEMMs pick another algorithm for 2 rows than for 1: ~1e-5 of the maximum
+            assert_close(heat[q:q + 1], one, rtol=1e-3, atol=1e-4 * float(one.abs().max()), what=f"image {b} word {t}")
+            assert_close(r_words[q, :t + 1], rw, rtol=1e-3, atol=1e-5, what=f"words image {b} word {t}")
