@@ -101,6 +101,8 @@ struct TcParams {
   void* out5;        // FWDX: act * (identity-branch gain)
   int fwd_flags;     // FWDX: bit 0 = no ReLU, bit 1 = store only the even pixels into a half-resolution PF tensor
   int n_valid;       // STORE_F32: columns that exist in `out` (<= ncol)
+  int fwd_simple;    // FWDX: plain conv + bias + ReLU with one gain group (no BatchNorm fold, residual Add, strided store,
+                     // extra outputs or neg-net accumulator): the short epilogue epi_fwdx_simple
   int pair;          // CTA pairs issue ONE tcgen05.mma.cta_group::2 (M = 256 = 128 rows of each CTA, each CTA holding bn/2
                      // rows of every B tile in its own shared memory): halves the B operand reads per SM
   const float* bias;
@@ -775,6 +777,64 @@ __device__ __forceinline__ void store_gain16(void* base, size_t off, bool f32, c
   }
 }
 
+// FWDX for a VGG-style layer (p.fwd_simple): act = relu(acc_W + bias), ONE gain group — alpha * num / safe(acc_W+)
+// (rule 0), num' / stab(acc_W) (rule 1) or [act > 0] (rules 2 / 3).  Same arithmetic as epi_fwdx below, without the
+// BatchNorm / Add / strided-store / extra-output state, whose registers made the general form spill 350 bytes per thread:
+// the fp32-accurate forward of VGG16 ran at a sixth of its bf16 speed because of that.
+__device__ __forceinline__ void epi_fwdx_simple(const TcParams& p, const RowInfo& r, uint32_t taddr, int n_tile, int c,
+                                                uint32_t release_bar) {
+  const bool sp = p.split != 0;
+  const int cout = p.cout;
+#pragma unroll 1
+  for (int q = 0; q < 2; ++q) {
+    const int ch = n_tile * p.half + c + 16 * q;
+    uint32_t vw[16], vp[16];
+    TMEM_LD_X16(taddr + c + 16 * q, vw);
+    if (p.n_acc >= 2) TMEM_LD_X16(taddr + p.half + c + 16 * q, vp);
+    tmem_ld_wait();
+    if (q == 1) epi_release(p, release_bar);
+    if (!r.in_range) continue;
+    float bv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) bv[k] = 0.f;
+    if (p.bias) {
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + ch) + k4);
+        bv[4 * k4] = t.x; bv[4 * k4 + 1] = t.y; bv[4 * k4 + 2] = t.z; bv[4 * k4 + 3] = t.w;
+      }
+    }
+    float act[16], g0[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float zw = __uint_as_float(vw[k]);
+      const float a = r.valid ? fmaxf(zw + bv[k], 0.f) : 0.f;
+      act[k] = a;
+      const float num = p.gain_mode ? 1.f : a;
+      float q0;
+      // gains as numerator x correctly-rounded reciprocal (<= 1.5 ulp off the IEEE quotient).  The IEEE division's
+      // fast path rejects a zero dividend — half of the post-ReLU numerators — and a warp with ONE such lane runs the
+      // slow-path subroutine for all 16 elements with its registers spilled to local memory (L1 is ~28 KB next to the
+      // 200 KB of shared memory): measured 6.5 M slow-path calls per layer-0 launch, 2.5 ms instead of ~1 ms
+      if (p.rule == 0) {
+        float zp = __uint_as_float(vp[k]) + (p.zbias ? bv[k] : 0.f);
+        zp += (zp == 0.f ? LRPX_Z_EPSILON : 0.f);
+        q0 = p.alpha * num * __frcp_rn(zp);
+      } else if (p.rule == 1) {
+        const float zr = zw + (p.zbias ? bv[k] : 0.f);
+        const float nq = (num == 0.f) ? -1e-6f : num;
+        q0 = nq * __frcp_rn(p.zbias ? zr : stab(zr));
+      } else {
+        q0 = a > 0.f ? 1.f : 0.f;
+      }
+      g0[k] = r.valid ? q0 : 0.f;
+    }
+    const size_t go = (size_t)r.row * cout + ch;
+    store_act16(p.out, (size_t)r.row * (size_t)(cout * (sp ? 2 : 1)) + ch, cout, sp, act);
+    store_gain16(p.out2, go, sp, g0);
+  }
+}
+
 __device__ __forceinline__ void epi_fwdx(const TcParams& p, const RowInfo& r, uint32_t taddr, int n_tile, int c,
                                          uint32_t release_bar) {
   const bool sp = p.split != 0;
@@ -848,11 +908,11 @@ __device__ __forceinline__ void epi_fwdx(const TcParams& p, const RowInfo& r, ui
       if (p.rule == 0) {
         float zp = __uint_as_float(vp[k]) + (p.zbias ? bv[k] : 0.f);
         zp += (zp == 0.f ? LRPX_Z_EPSILON : 0.f);                   // safe_divide, utils.py:16-18
-        q0 = p.alpha * num * ratio * rho1 / zp;
+        q0 = p.alpha * num * ratio * rho1 * __frcp_rn(zp);           // reciprocal, not division: see epi_fwdx_simple
         if (p.n_acc >= 3) {
           float zn = __uint_as_float(vn[k]) + (p.zbias ? bv[k] : 0.f);
           zn += (zn == 0.f ? LRPX_Z_EPSILON : 0.f);
-          q1 = -p.beta * num / zn;
+          q1 = -p.beta * num * __frcp_rn(zn);
         } else if (p.idn) {
           q1 = rho2 * hdv[k];                                        // identity-branch gain
         }
@@ -876,10 +936,14 @@ __device__ __forceinline__ void epi_fwdx(const TcParams& p, const RowInfo& r, ui
   }
 }
 
+// internal epilogue code (not part of the ABI): FWDX of a VGG-style layer, instantiated on its own so that the general
+// FWDX epilogue's register pressure (BatchNorm / Add / strided-store state, 470 bytes of stack) stays out of it
+constexpr int TC_EPI_FWDX_SIMPLE = 12;
+
 // number of 32-column units per (lane quarter, M half) of a tile
 __device__ __forceinline__ int epi_units_per_half(const TcParams& p, int epi) {
   if (epi == LRPX_TC_EPI_INPUT || epi == LRPX_TC_EPI_INPUT3) return 1;
-  const int ncols = (epi == LRPX_TC_EPI_FWD_GAIN || epi == LRPX_TC_EPI_FWDX) ? p.half : p.bn;
+  const int ncols = (epi == LRPX_TC_EPI_FWD_GAIN || epi == LRPX_TC_EPI_FWDX || epi == TC_EPI_FWDX_SIMPLE) ? p.half : p.bn;
   return ncols >> 5;
 }
 
@@ -900,6 +964,8 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
     epi_mulx<false>(p, r, taddr, n0, c, release_bar);
   } else if (EPI == LRPX_TC_EPI_MULX_UNPOOL) {
     epi_mulx<true>(p, r, taddr, n0, c, release_bar);
+  } else if (EPI == TC_EPI_FWDX_SIMPLE) {
+    epi_fwdx_simple(p, r, taddr, n_tile, c, release_bar);
   } else if (EPI == LRPX_TC_EPI_FWDX) {
     epi_fwdx(p, r, taddr, n_tile, c, release_bar);
   } else if (EPI == LRPX_TC_EPI_INPUT) {
@@ -1860,6 +1926,9 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     p.bn = a->n_acc * p.half;
     p.cout = cout;
     p.out_c = cout;
+    const char* env_fs = getenv("LRPX_TC_FWD_SIMPLE");       // "0": always the general epilogue (A/B runs)
+    p.fwd_simple = (a->n_acc <= 2 && !a->bn_w && !a->idn && !a->hd && !a->out3 && !a->out4 && !a->out5 && a->fwd_flags == 0 &&
+                    !(env_fs && env_fs[0] == '0')) ? 1 : 0;
   } else if (epi == LRPX_TC_EPI_MULX || epi == LRPX_TC_EPI_MULX_UNPOOL) {
     LRPX_CHECK_ARG(a->gain && (p.groups == 1 || (p.groups == 2 && a->gain2)), "MULX: gain (and gain2 for two groups) required");
     LRPX_CHECK_ARG(a->ncol % 32 == 0, "ncol must be a multiple of 32 for this epilogue");
@@ -1996,7 +2065,9 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
         case LRPX_TC_EPI_INPUT3: return launch_tc_slab<LRPX_TC_EPI_INPUT3>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_MULX: return launch_tc_slab<LRPX_TC_EPI_MULX>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_MULX_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MULX_UNPOOL>(ma0, ma1, mb, mbh, mo, p, grid, st);
-        case LRPX_TC_EPI_FWDX: return launch_tc_slab<LRPX_TC_EPI_FWDX>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        case LRPX_TC_EPI_FWDX:
+          if (p.fwd_simple) return launch_tc_slab<TC_EPI_FWDX_SIMPLE>(ma0, ma1, mb, mbh, mo, p, grid, st);
+          return launch_tc_slab<LRPX_TC_EPI_FWDX>(ma0, ma1, mb, mbh, mo, p, grid, st);
         default: return launch_tc_slab<LRPX_TC_EPI_STORE_F32>(ma0, ma1, mb, mbh, mo, p, grid, st);
       }
     }
@@ -2026,7 +2097,9 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     case LRPX_TC_EPI_FEAT_DIV: return launch_tc<LRPX_TC_EPI_FEAT_DIV>(ma, mb, p, grid, st);
     case LRPX_TC_EPI_MULX: return launch_tc<LRPX_TC_EPI_MULX>(ma, mb, p, grid, st);
     case LRPX_TC_EPI_MULX_UNPOOL: return launch_tc<LRPX_TC_EPI_MULX_UNPOOL>(ma, mb, p, grid, st);
-    case LRPX_TC_EPI_FWDX: return launch_tc<LRPX_TC_EPI_FWDX>(ma, mb, p, grid, st);
+    case LRPX_TC_EPI_FWDX:
+      if (p.fwd_simple) return launch_tc<TC_EPI_FWDX_SIMPLE>(ma, mb, p, grid, st);
+      return launch_tc<LRPX_TC_EPI_FWDX>(ma, mb, p, grid, st);
     default: return launch_tc<LRPX_TC_EPI_STORE_F32>(ma, mb, p, grid, st);
   }
 }

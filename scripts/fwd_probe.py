@@ -8,7 +8,8 @@ from lrpx import tc, _lib
 
 n = int(os.environ.get("IMAGES", "64"))
 sd = synth.vgg_state(1)
-eng = tc.TcVggEngine([sd[k] for k in sd if k.endswith("weight")], [sd[k] for k in sd if k.endswith("bias")], synth.VGG16_CFG, "cuda")
+eng = tc.TcVggEngine([sd[k] for k in sd if k.endswith("weight")], [sd[k] for k in sd if k.endswith("bias")], synth.VGG16_CFG, "cuda",
+                     precision=os.environ.get("PRECISION", "bf16"), rule=os.environ.get("RULE", "alpha_beta"))
 x = torch.randn(n, 3, 224, 224, device="cuda")
 for _ in range(2):
     eng.forward(x)
