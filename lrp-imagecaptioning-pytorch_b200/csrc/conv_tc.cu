@@ -101,6 +101,7 @@ struct TcParams {
   void* out5;        // FWDX: act * (identity-branch gain)
   int fwd_flags;     // FWDX: bit 0 = no ReLU, bit 1 = store only the even pixels into a half-resolution PF tensor
   int n_valid;       // STORE_F32: columns that exist in `out` (<= ncol)
+  int mulx_simple;   // MULX / MULX_UNPOOL: one gain group, no addend, no second output: the _S instantiations
   int fwd_simple;    // FWDX: plain conv + bias + ReLU with one gain group (no BatchNorm fold, residual Add, strided store,
                      // extra outputs or neg-net accumulator): the short epilogue epi_fwdx_simple
   int pair;          // CTA pairs issue ONE tcgen05.mma.cta_group::2 (M = 256 = 128 rows of each CTA, each CTA holding bn/2
@@ -653,10 +654,13 @@ __device__ __forceinline__ void load_gain16(const void* base, size_t off, bool f
 // MULX / MULX_UNPOOL: 32 accumulator columns [c, c+32) of this thread's row as two halves of 16.
 //   group j:  v = acc * gain_j  ->  out[row][j*N + n] (hi)  and, when split, out[row][(G+j)*N + n] (lo)
 // UNPOOL: the row is a pooled pixel; the products go to the winner of its 2x2 fine block, zeros to the other three.
-template <bool UNPOOL>
+// SIMPLE: one gain group, no residual addend, no second output tensor (every layer of a VGG-style chain in the
+// fp32-accurate / gradient modes) — instantiated on its own (TC_EPI_MULX_S / TC_EPI_MULX_UNPOOL_S) so that the group loop
+// and the fork state of the general form do not cost it registers (the general un-pool epilogue spills 160-200 bytes).
+template <bool UNPOOL, bool SIMPLE>
 __device__ __forceinline__ void epi_mulx(const TcParams& p, const RowInfo& r, uint32_t taddr, int n0, int c,
                                          uint32_t release_bar) {
-  const int N = p.ncol, G = p.groups;
+  const int N = p.ncol, G = SIMPLE ? 1 : p.groups;
   const bool sp = p.split != 0;
   const int img = (r.valid && p.row_img) ? p.row_img[r.e] : r.e;
   const size_t gbase = ((size_t)img * p.blk + r.rem) * (size_t)N;
@@ -683,7 +687,7 @@ __device__ __forceinline__ void epi_mulx(const TcParams& p, const RowInfo& r, ui
       float t[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) t[k] = 0.f;
-      if (!UNPOOL && p.add && r.valid) {      // fork of a residual block: the other branch's relevance joins here
+      if (!SIMPLE && !UNPOOL && p.add && r.valid) {      // fork of a residual block: the other branch's relevance joins here
         float ad[16], gb[16];
         load_gain16(p.add, (size_t)r.row * p.add_pitch + col, false, ad);
         const void* gbp = j ? p.gain4 : p.gain3;           // nullptr: the addend joins unscaled
@@ -708,7 +712,7 @@ __device__ __forceinline__ void epi_mulx(const TcParams& p, const RowInfo& r, ui
         split_pack(a0, a1, hi[k], lo[k]);
       }
       if (!UNPOOL) {
-        if (j == 1 && p.out2) {               // two separate tensors instead of one K-concatenated row
+        if (!SIMPLE && j == 1 && p.out2) {    // two separate tensors instead of one K-concatenated row
           stg_v8(reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)r.row * N + col, hi);
         } else {
           __nv_bfloat16* dst = out + (size_t)r.row * p.out_c + col;
@@ -720,7 +724,7 @@ __device__ __forceinline__ void epi_mulx(const TcParams& p, const RowInfo& r, ui
         const size_t blk_f = (size_t)(2 * p.h + 1) * wf1;
         __nv_bfloat16* const outb = out + (size_t)r.e * blk_f * p.out_c + col;
         const uint32_t sw[4] = {sidx.x, sidx.y, sidx.z, sidx.w};
-#pragma unroll
+#pragma unroll 1          // one fine pixel at a time: unrolled, the four address chains pushed the epilogue into 200 B of spills
         for (int k = 0; k < 4; ++k) {
           const int fr = 2 * r.a - 1 + (k >> 1), fc = 2 * r.b - 1 + (k & 1);
           if (fr < 0 || fc < 0) continue;
@@ -939,6 +943,7 @@ __device__ __forceinline__ void epi_fwdx(const TcParams& p, const RowInfo& r, ui
 // internal epilogue code (not part of the ABI): FWDX of a VGG-style layer, instantiated on its own so that the general
 // FWDX epilogue's register pressure (BatchNorm / Add / strided-store state, 470 bytes of stack) stays out of it
 constexpr int TC_EPI_FWDX_SIMPLE = 12;
+constexpr int TC_EPI_MULX_S = 13, TC_EPI_MULX_UNPOOL_S = 14;      // MULX / MULX_UNPOOL with one gain group, no addend (epi_mulx)
 
 // number of 32-column units per (lane quarter, M half) of a tile
 __device__ __forceinline__ int epi_units_per_half(const TcParams& p, int epi) {
@@ -961,9 +966,13 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
   if (EPI == LRPX_TC_EPI_INPUT3) {
     epi_input3(p, r0, taddr, release_bar, scratch, quarter, bar_id);
   } else if (EPI == LRPX_TC_EPI_MULX) {
-    epi_mulx<false>(p, r, taddr, n0, c, release_bar);
+    epi_mulx<false, false>(p, r, taddr, n0, c, release_bar);
   } else if (EPI == LRPX_TC_EPI_MULX_UNPOOL) {
-    epi_mulx<true>(p, r, taddr, n0, c, release_bar);
+    epi_mulx<true, false>(p, r, taddr, n0, c, release_bar);
+  } else if (EPI == TC_EPI_MULX_S) {
+    epi_mulx<false, true>(p, r, taddr, n0, c, release_bar);
+  } else if (EPI == TC_EPI_MULX_UNPOOL_S) {
+    epi_mulx<true, true>(p, r, taddr, n0, c, release_bar);
   } else if (EPI == TC_EPI_FWDX_SIMPLE) {
     epi_fwdx_simple(p, r, taddr, n_tile, c, release_bar);
   } else if (EPI == LRPX_TC_EPI_FWDX) {
@@ -1096,11 +1105,19 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
 // L2 prefetch of the gain (and argmax) bytes a unit will read, issued a couple of tiles ahead
 template <int EPI>
 __device__ __forceinline__ void epi_prefetch_unit(const TcParams& p, int row, int n_tile, int c) {
-  if (EPI != LRPX_TC_EPI_MUL && EPI != LRPX_TC_EPI_MUL_UNPOOL) return;
+  constexpr bool simple_x = EPI == TC_EPI_MULX_S || EPI == TC_EPI_MULX_UNPOOL_S;
+  if (EPI != LRPX_TC_EPI_MUL && EPI != LRPX_TC_EPI_MUL_UNPOOL && !simple_x) return;
   if (row >= p.m_total || (p.debug_flags & 128)) return;      // 128: timing experiment without the L2 prefetch
   const RowInfo q = row_info(p, row);
   if (!q.valid) return;
   const int img = p.row_img ? p.row_img[q.e] : q.e;
+  if (simple_x) {                                             // gains of ncol channels per row, bf16 or fp32 (split)
+    const size_t po = ((size_t)img * p.blk + q.rem) * (size_t)p.ncol + n_tile * p.bn + c;
+    const char* g = reinterpret_cast<const char*>(p.gain) + po * (p.split ? 4 : 2);
+    prefetch_l2(g);                                           // 32 columns: 64 bytes (bf16) or one 128-byte line (fp32)
+    if (EPI == TC_EPI_MULX_UNPOOL_S && p.pool_idx) prefetch_l2(p.pool_idx + po);
+    return;
+  }
   const size_t po = ((size_t)img * p.blk + q.rem) * p.out_c + n_tile * p.bn + c;
   prefetch_l2(p.gain + po);                                   // 32 columns of bf16 = 64 bytes: one line
   if (EPI == LRPX_TC_EPI_MUL_UNPOOL) prefetch_l2(p.pool_idx + po);
@@ -1733,7 +1750,7 @@ template <int EPI>
 static int launch_tc_slab(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mbh,
                           const CUtensorMap& mo, const TcParams& p, int grid, cudaStream_t st) {
   if constexpr (EPI == LRPX_TC_EPI_MUL || EPI == LRPX_TC_EPI_MUL_UNPOOL || EPI == LRPX_TC_EPI_MULX ||
-                EPI == LRPX_TC_EPI_MULX_UNPOOL) {
+                EPI == LRPX_TC_EPI_MULX_UNPOOL || EPI == TC_EPI_MULX_S || EPI == TC_EPI_MULX_UNPOOL_S) {
     if (p.pair) return launch_tc_slab_impl<EPI, true>(ma0, ma1, mb, mbh, mo, p, grid, st);
   }
   if (p.pair) {
@@ -1937,6 +1954,10 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     LRPX_CHECK_ARG(!(a->out2 && p.groups == 2) || !p.split, "MULX: separate group tensors (out2) are bf16 only");
     p.bn = a->ncol <= 256 ? a->ncol : 256;
     LRPX_CHECK_ARG(a->ncol % p.bn == 0, "ncol must be <= 256 or a multiple of 256");
+    {
+      const char* env_ms = getenv("LRPX_TC_MULX_SIMPLE");    // "0": always the general epilogue (A/B runs)
+      p.mulx_simple = (p.groups == 1 && !a->add && !a->out2 && !(env_ms && env_ms[0] == '0')) ? 1 : 0;
+    }
     p.out_c = (a->out2 && p.groups == 2) ? a->ncol : a->ncol * p.groups * (p.split ? 2 : 1);
   } else if (epi == LRPX_TC_EPI_FWD_GAIN) {
     // Wt holds, per tile of `half` output channels, the W rows followed by the W+ rows: ncol = 2 * cout
@@ -2063,8 +2084,12 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
         case LRPX_TC_EPI_MUL_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MUL_UNPOOL>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_INPUT: return launch_tc_slab<LRPX_TC_EPI_INPUT>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_INPUT3: return launch_tc_slab<LRPX_TC_EPI_INPUT3>(ma0, ma1, mb, mbh, mo, p, grid, st);
-        case LRPX_TC_EPI_MULX: return launch_tc_slab<LRPX_TC_EPI_MULX>(ma0, ma1, mb, mbh, mo, p, grid, st);
-        case LRPX_TC_EPI_MULX_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MULX_UNPOOL>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        case LRPX_TC_EPI_MULX:
+          if (p.mulx_simple) return launch_tc_slab<TC_EPI_MULX_S>(ma0, ma1, mb, mbh, mo, p, grid, st);
+          return launch_tc_slab<LRPX_TC_EPI_MULX>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        case LRPX_TC_EPI_MULX_UNPOOL:
+          if (p.mulx_simple) return launch_tc_slab<TC_EPI_MULX_UNPOOL_S>(ma0, ma1, mb, mbh, mo, p, grid, st);
+          return launch_tc_slab<LRPX_TC_EPI_MULX_UNPOOL>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_FWDX:
           if (p.fwd_simple) return launch_tc_slab<TC_EPI_FWDX_SIMPLE>(ma0, ma1, mb, mbh, mo, p, grid, st);
           return launch_tc_slab<LRPX_TC_EPI_FWDX>(ma0, ma1, mb, mbh, mo, p, grid, st);
@@ -2095,8 +2120,12 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     case LRPX_TC_EPI_INPUT: return launch_tc<LRPX_TC_EPI_INPUT>(ma, mb, p, grid, st);
     case LRPX_TC_EPI_FEAT: return launch_tc<LRPX_TC_EPI_FEAT>(ma, mb, p, grid, st);
     case LRPX_TC_EPI_FEAT_DIV: return launch_tc<LRPX_TC_EPI_FEAT_DIV>(ma, mb, p, grid, st);
-    case LRPX_TC_EPI_MULX: return launch_tc<LRPX_TC_EPI_MULX>(ma, mb, p, grid, st);
-    case LRPX_TC_EPI_MULX_UNPOOL: return launch_tc<LRPX_TC_EPI_MULX_UNPOOL>(ma, mb, p, grid, st);
+    case LRPX_TC_EPI_MULX:
+      if (p.mulx_simple) return launch_tc<TC_EPI_MULX_S>(ma, mb, p, grid, st);
+      return launch_tc<LRPX_TC_EPI_MULX>(ma, mb, p, grid, st);
+    case LRPX_TC_EPI_MULX_UNPOOL:
+      if (p.mulx_simple) return launch_tc<TC_EPI_MULX_UNPOOL_S>(ma, mb, p, grid, st);
+      return launch_tc<LRPX_TC_EPI_MULX_UNPOOL>(ma, mb, p, grid, st);
     case LRPX_TC_EPI_FWDX:
       if (p.fwd_simple) return launch_tc<TC_EPI_FWDX_SIMPLE>(ma, mb, p, grid, st);
       return launch_tc<LRPX_TC_EPI_FWDX>(ma, mb, p, grid, st);
