@@ -1203,6 +1203,7 @@ def run_ours(args):
                                  ("config5_library_encoder", 5, dict(steps=4, precision="fp32", library_encoder=True)),
                                  ("config2_gradient", 2, dict(method="gradient", precision="fp32", steps=3)),
                                  ("config2_guided", 2, dict(method="guided", precision="fp32", steps=3)),
+                                 ("config2_gradient_bf16", 2, dict(method="gradient", precision="bf16", steps=4)),
                                  ("config2_guided_bf16", 2, dict(method="guided", precision="bf16", steps=4))):
             a2 = argparse.Namespace(**vars(args))
             a2.config, a2.also, a2.warmup = cfg, False, 3

@@ -177,10 +177,11 @@ def test_encoder_gradient_vs_oracle(precision, guided):
     else:
         ws = [sd[k] for k in sd if k.endswith("weight")]
         bs = [sd[k] for k in sd if k.endswith("bias")]
-        eng = tc.TcVggEngine(ws, bs, cfg, DEV, precision=precision, rule="guided" if guided else "gradient")
+        rule = "guided" if guided else "gradient"
+        eng = (tc.TcVggGradientHybrid(ws, bs, cfg, DEV, rule=rule) if precision == "bf16" else
+               tc.TcVggEngine(ws, bs, cfg, DEV, precision=precision, rule=rule))
         st = eng.forward(x.to(DEV))
-        assert_close(eng.features(st, "nchw"), feat, rtol=2e-2 if precision == "bf16" else 1e-4,
-                     atol=(2e-2 if precision == "bf16" else 2e-5) * float(feat.abs().max()), what="features")
+        assert_close(eng.features(st, "nchw"), feat, rtol=1e-4, atol=2e-5 * float(feat.abs().max()), what="features")
         got = eng.relevance(st, tgt.flatten(2).transpose(1, 2).contiguous().to(DEV), torch.tensor(rows, dtype=torch.int32, device=DEV))
     scale = want.abs().max()
     err = float((got.cpu() - want).abs().max() / scale)
@@ -190,14 +191,16 @@ def test_encoder_gradient_vs_oracle(precision, guided):
     # error of zero flips its mask and moves the ~600 input-gradient entries it feeds by ~4 % each.  The fp32 CUDA-core
     # forward (1e-7 relative) reproduces the oracle's masks; the error-compensated tensor-core forward (1e-5 relative,
     # one-sided by the round-toward-zero accumulation) flips ~2e-6 of the units per layer, the bf16 forward (4e-3) many
-    # more.  Bars = 2x the measured figures (profiles/README.md): guided backpropagation, which zeroes negative
-    # gradients at every ReLU, is an order of magnitude less sensitive than the plain gradient.
+    # more — which is why precision 'bf16' of the gradient family keeps the fp32-accurate FORWARD and runs only the chain
+    # in bf16 (measured: same error as the fp32-accurate chain).  Bars = 2x the measured figures (profiles/README.md):
+    # guided backpropagation, which zeroes negative gradients at every ReLU, is an order of magnitude less sensitive
+    # than the plain gradient.
     if precision == "simt":
         assert_close(got / scale, want / scale, rtol=1e-4, atol=1e-5, what="simt gradient")
     elif precision == "fp32":
         assert _rel_l2(got, want) < (3e-3 if guided else 3e-2) and spearman(got, want) > 0.999
-    else:
-        assert _rel_l2(got, want) < (8e-2 if guided else 0.4) and spearman(got, want) > (0.99 if guided else 0.9)
+    else:       # bf16 chain on the fp32-accurate forward's masks (TcVggGradientHybrid): the mask flips dominate, as above
+        assert _rel_l2(got, want) < (5e-3 if guided else 4e-2) and spearman(got, want) > 0.999
 
 
 @pytest.mark.parametrize("cls,key", [("ExplainGridTDGradient", "grad"), ("ExplainiGridTDGuidedGradient", "guided")])
