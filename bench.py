@@ -53,7 +53,7 @@ def parse(argv=None):
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5],
                     help="BASELINE.json configuration; 0 (default) = config 2 plus short 'also' runs of the others at N = 1")
-    ap.add_argument("--precision", default=None, choices=["bf16", "fp32"],
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp32", "mixed"],
                     help="default: bf16 (config 5: fp32 — the fixed encoder's features at fp32 accuracy)")
     ap.add_argument("--deliver", default="full", choices=["full", "channel_mean", "fp16"])
     ap.add_argument("--encoder", default="vgg16", choices=["vgg16", "resnet101"],
@@ -527,7 +527,8 @@ def run_config2(args, ctx, brief=False):
         out = {
             "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if ex.precision == "bf16" else "bf16x3 (fp32-accurate)",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "mixed": "bf16 chain on a bf16x3 (fp32-accurate) forward"}.get(
+                ex.precision, "bf16x3 (fp32-accurate)"),
             "data": "synthetic",
             "config": {"workload": "config 2: gridTD VGG16 LRP alpha1beta0 image+linguistic explanations, "
                                    f"{B} images x {T} words per GPU per step, 224x224, V={args.vocab}, H=E=512",
@@ -538,7 +539,7 @@ def run_config2(args, ctx, brief=False):
                        "l2": "working set (gains 1.9 GB + chain buffers) far larger than the 126 MB L2; no flush needed",
                        "decoder_relevance_dtype": ("f32 element-wise, GEMMs as error-compensated bf16x3 on tensor cores (f32 accumulate)"
                                                    if tc_gemm else "f32 (CUDA-core GEMMs)"),
-                       "encoder_relevance_dtype": ("bf16 operands, f32 accumulate" if ex.precision == "bf16" else
+                       "encoder_relevance_dtype": ("bf16 operands, f32 accumulate" if ex.precision in ("bf16", "mixed") else
                                                    "bf16x3 error-compensated operands (hi|lo storage, fp32 gains), f32 accumulate")},
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": imgs_h.numel() * 4 + toks_h.numel() * 8,
@@ -554,7 +555,7 @@ def run_config2(args, ctx, brief=False):
                                           "phases); `achieved_eager` is the same over the chain's own CUDA-event time in an "
                                           "instrumented eager step",
                          "achieved_eager": ach_eager, "frac_eager": ach_eager / pk["tf_sustained"],
-                         "traffic": chain_traffic(args.chunk) if ex.precision == "bf16" else None,
+                         "traffic": chain_traffic(args.chunk) if ex.precision in ("bf16", "mixed") else None,
                          "traffic_note": "dram read+write bytes of the 13 chain layers per chunk of explanations (ncu --set "
                                          "full, profiles/r1_chain_full.md); algorithmic FLOPs per chunk = chunk x "
                                          "algorithmic_gflop_per_explanation",
@@ -1196,6 +1197,7 @@ def run_ours(args):
     if out is not None and args.also and ctx.world == 1:
         also = {}
         for name, cfg, extra in (("config2_fp32_accurate", 2, dict(precision="fp32", steps=4)),
+                                 ("config2_mixed", 2, dict(precision="mixed", steps=6)),
                                  ("config2_resnet101", 2, dict(encoder="resnet101", precision="bf16", steps=4)),
                                  ("config3", 3, dict(steps=8)), ("config4", 4, dict(steps=4)),
                                  ("config4_fp32_accurate", 4, dict(precision="fp32", steps=2, images=128)),

@@ -262,8 +262,11 @@ class _TcPlan:
         key = (precision, alpha, beta, ignore_bias)
         hit = self._eng.get(key)
         if hit is None or hit[0] != stamp:
-            eng = tc.TcVggEngine(ws, bs, self.cfg, ws[0].device, precision=precision, alpha=alpha, beta=beta,
-                                 ignore_bias=ignore_bias)
+            if precision == "mixed":          # fp32-accurate forward, bf16 chain (alpha 1 / beta 0 preset only)
+                eng = tc.TcVggMixed(ws, bs, self.cfg, ws[0].device)
+            else:
+                eng = tc.TcVggEngine(ws, bs, self.cfg, ws[0].device, precision=precision, alpha=alpha, beta=beta,
+                                     ignore_bias=ignore_bias)
             hit = self._eng[key] = (stamp, eng)
         return hit[1]
 
@@ -295,6 +298,7 @@ def add_lrp(model):
 #            chain with error-compensated bf16x3 operands and fp32 gains / inter-layer storage; every other
 #            topology runs the fp32 CUDA-core rule kernels.
 #   'bf16' — the tcgen05 chain with bf16 operands and storage (Spearman >= 0.99 / rel-L2 <= 5e-2 vs the reference).
+#   'mixed' — fp32-accurate forward (activations, max-pool winners, gains), bf16 chain: lrpx.tc.TcVggMixed.
 #   'simt' — the fp32 CUDA-core rule kernels whatever the topology (the rule-by-rule walker).
 DEFAULT_PRECISION = os.environ.get("LRPX_PRECISION", "fp32")
 
@@ -315,22 +319,25 @@ def compute_lrp(model, sample, target=None, return_output=False, rectify_logits=
     if target is None:
         raise RuntimeError("grad can be implicitly created only for scalar outputs")   # what .backward(None) raises
     precision = precision or DEFAULT_PRECISION
-    if precision not in ("fp32", "bf16", "simt"):
+    if precision not in ("fp32", "bf16", "simt", "mixed"):
         raise ValueError(f"compute_lrp: unknown precision {precision!r}")
     tcp = getattr(model, "_lrpx_tc", None)
-    use_tc = tcp is not None and precision in ("fp32", "bf16") and conservation_trace is None and sample.dim() == 4
+    use_tc = tcp is not None and precision in ("fp32", "bf16", "mixed") and conservation_trace is None and sample.dim() == 4
     if use_tc:
         params = tcp.convs[0].lrp_params
         use_tc = all(c.lrp_method == "alpha_beta" and c.lrp_params == params for c in tcp.convs)
         general = not (precision == "bf16" and params.get("alpha", 1.) == 1. and params.get("beta", 0.) == 0.
                        and params.get("ignore_bias", True))
+        preset = params.get("alpha", 1.) == 1. and params.get("beta", 0.) == 0. and params.get("ignore_bias", True)
+        if precision == "mixed":
+            use_tc = use_tc and preset and not isinstance(tcp, _TcResNetPlan) and tcp.convs[0].out_channels % 64 == 0
         if isinstance(tcp, _TcResNetPlan):
             use_tc = use_tc and not general and not model.training   # ResNets: the bf16 chain only
         elif general and tcp.convs[0].out_channels % 64:
             use_tc = False                    # the general kernels need a 64-channel first layer: CUDA-core walker
-    if precision == "bf16" and not use_tc:
-        raise NotImplementedError("compute_lrp(precision='bf16'): the tensor-core chain covers VGG-style encoders "
-                                  "(conv3x3/ReLU/max-pool 2x2) under the alpha-beta rule only")
+    if precision in ("bf16", "mixed") and not use_tc:
+        raise NotImplementedError(f"compute_lrp(precision={precision!r}): the tensor-core chain covers VGG-style encoders "
+                                  "(conv3x3/ReLU/max-pool 2x2) under the alpha-beta rule only ('mixed': alpha 1 / beta 0)")
     with torch.no_grad():
         x = sample.detach()
         if use_tc:

@@ -625,20 +625,26 @@ class TcVggEngine:
         return float(sum(4.0 * c.h * c.w * c.cin * c.cout * 9 for c in self.convs))
 
 
-class TcVggGradientHybrid:
-    """Gradient / guided-backpropagation engine for precision 'bf16': the FORWARD (and with it the ReLU masks and the
-    max-pool winners) in the fp32-accurate mode, the per-explanation chain with bf16 operands and storage.  A gradient
-    is discontinuous in the forward pass — a ReLU whose pre-activation lies within the forward's rounding error of zero
-    flips its mask — so the bf16 forward (4e-3 relative) costs the plain gradient an order of magnitude more than the
-    bf16 chain itself does (measured rel-L2 0.33 / Spearman 0.94 against autograd with a bf16 forward).  The masks are 0 / 1
-    and convert to bf16 exactly; the forward runs once per image, the chain once per explanation."""
+class TcVggMixed:
+    """The per-image FORWARD in the fp32-accurate mode, the per-explanation chain with bf16 operands and storage
+    (precision 'mixed'; for the gradient rules this is what precision 'bf16' means).
 
-    def __init__(self, weights, biases, cfg, device=None, rule="gradient"):
-        if rule not in ("gradient", "guided"):
-            raise _lib.LrpxError("TcVggGradientHybrid serves the 'gradient' and 'guided' rules")
+    * alpha-beta rule (alpha = 1, beta = 0): the encoder features the decoder consumes are fp32-accurate (1e-5 instead of
+      the bf16 forward's 7e-3, which the 19-step LSTM chain of the decoder amplifies to a worst request of 9e-2), the
+      max-pool winners are the accurate forward's, and the gains a / z+ are rounded to bf16 ONCE instead of being formed
+      from bf16 activations; the chain is the specialised bf16 one (EPI_MUL / EPI_MUL_UNPOOL).
+    * gradient / guided rules: a gradient is discontinuous in the forward pass — a ReLU whose pre-activation lies within
+      the forward's rounding error of zero flips its mask — so a bf16 forward costs the plain gradient far more than the
+      bf16 chain does (measured rel-L2 0.33 against autograd with a bf16 forward, 1.8e-2 with this class, the same as the
+      fp32-accurate chain).  The masks are 0 / 1 and convert to bf16 exactly.
+    The forward runs once per image, the chain once per explanation."""
+
+    def __init__(self, weights, biases, cfg, device=None, rule="alpha_beta"):
+        if rule not in ("alpha_beta", "gradient", "guided"):
+            raise _lib.LrpxError("TcVggMixed serves the alpha-beta (alpha 1, beta 0), 'gradient' and 'guided' rules")
         self.fwd = TcVggEngine(weights, biases, cfg, device, precision="fp32", rule=rule)
         self.chain = TcVggEngine(weights, biases, cfg, device, precision="bf16", rule=rule)
-        self.precision, self.rule = "bf16", rule
+        self.precision, self.rule = "mixed", rule
 
     def forward(self, x, keep_act=False):
         src = self.fwd.forward(x, keep_act)
@@ -646,10 +652,12 @@ class TcVggGradientHybrid:
             cc.h, cc.w = cf.h, cf.w
         st = VggState()
         st.n, st.x, st.idx = src.n, src.x, src.idx
-        st.gain = [g.to(torch.bfloat16) for g in src.gain]          # 0 / 1: exact
+        st.gain = [g.to(torch.bfloat16) for g in src.gain]          # gradient rules: 0 / 1, exact
         st.gain2 = [None] * len(st.gain)
         st.rz_last, st.rz2_last = st.gain[-1], None
         st.feat_pf, st.feat_hw, st.feat_c = src.feat_pf, src.feat_hw, src.feat_c
+        if src.acts is not None:          # keep_act (conservation report): the bf16 head of every hi|lo activation row
+            st.acts = [None if a is None else a[:, :a.shape[1] // 2].contiguous() for a in src.acts]
         st.src = src
         return st
 
@@ -658,3 +666,6 @@ class TcVggGradientHybrid:
 
     def __getattr__(self, name):          # relevance, relevance_head / _tail, heat_shape, convs, flop counters: the chain's
         return getattr(self.chain, name)
+
+
+TcVggGradientHybrid = TcVggMixed          # the name the gradient-family explainers use

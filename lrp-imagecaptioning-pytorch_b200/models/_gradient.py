@@ -99,7 +99,7 @@ class GradientFamily:
             enc = self.model.img_encoder.encoder
             convs = [m for m in enc if isinstance(m, nn.Conv2d)]
             cfg = [m.out_channels if isinstance(m, nn.Conv2d) else "M" for m in enc if isinstance(m, (nn.Conv2d, nn.MaxPool2d))]
-            if self.precision == "bf16":       # bf16 chain on the masks of the fp32-accurate forward (see the class)
+            if self.precision in ("bf16", "mixed"):       # bf16 chain on the masks of the fp32-accurate forward (see the class)
                 self._engine = tc.TcVggGradientHybrid([c.weight for c in convs], [c.bias for c in convs], cfg, self.device,
                                                       rule=self.RULE)
             else:

@@ -317,4 +317,4 @@ class ExplainAdaptiveAttention(ExplainGridTDAttention):
         req_word = torch.tensor([toks[t + 1] for t in ts], dtype=torch.int32, device=dev)
         req_img = torch.zeros(len(ts), dtype=torch.int32, device=dev)
         return ops.adaptive_decoder_lrp(self._state, self._lrp_weights(), req_img, req_t, req_word,
-                                        tc_gemm=(self.precision == 'bf16'))
+                                        tc_gemm=(self.precision in ('bf16', 'mixed')))

@@ -452,7 +452,7 @@ class ExplainAOAAttention(ExplainGridTDAttention):
         i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
         return ops.aoa_decoder_lrp(self._state, self._lrp_weights(), self.num_head, i32([0] * len(ts)), i32(list(ts)),
                                    i32([toks[t + 1] for t in ts]), i32([head_idx] * len(ts)),
-                                   tc_gemm=(self.precision == 'bf16'))
+                                   tc_gemm=(self.precision in ('bf16', 'mixed')))
 
     def lrp_mha(self, alpha, value, r_context, context, head_idx):
         """reference :812-862 (same argument order): relevance of the values of ONE head (others get 0, Q5).
@@ -534,7 +534,7 @@ class ExplainAOAAttention(ExplainGridTDAttention):
         req_t = i32([t for b in range(B) for t in range(len(caps[b]))])
         req_word = i32([w for c in caps for w in c])
         r_feat, r_words = ops.aoa_decoder_lrp(st, self._lrp_weights(), self.num_head, req_img, req_t, req_word,
-                                              torch.full_like(req_t, int(head_idx)), tc_gemm=(self.precision == 'bf16'))
+                                              torch.full_like(req_t, int(head_idx)), tc_gemm=(self.precision in ('bf16', 'mixed')))
         return r_feat, r_words, req_img, req_t, caps
 
     def explain_caption_words(self, img_filepath):
@@ -584,7 +584,7 @@ class ExplainAOAGradient(GradientFamily, ExplainAOAAttention):
         i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=self.device)
         return ops.aoa_decoder_grad(self._state, self._grad_weights(), self.num_head, i32([0] * len(ts)), i32(list(ts)),
                                     i32([toks[t + 1] for t in ts]), i32([head_idx] * len(ts)),
-                                    tc_gemm=(self.precision == 'bf16'))
+                                    tc_gemm=(self.precision in ('bf16', 'mixed')))
 
     def explain_caption_wordt(self, t, head_idx):
         """reference :1435-1499 -> (d_img_feature (1,C,h,w), r_words (t+1,))."""

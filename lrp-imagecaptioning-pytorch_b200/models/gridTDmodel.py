@@ -488,6 +488,9 @@ class ExplainGridTDAttention(object):
                through LRPtools.  Decoder GEMMs on fp32 CUDA cores.
       'bf16' — VGG encoders only: the tcgen05 chain with bf16 operands / storage (Spearman >= 0.99, rel-L2 <= 5e-2 vs
                the reference), decoder GEMMs as bf16x3 on tensor cores.  The throughput mode of bench.py.
+      'mixed' — VGG encoders: the encoder FORWARD in the fp32-accurate mode (once per image), the relevance chain in
+               bf16 (lrpx.tc.TcVggMixed): accurate features for the decoder and accurate max-pool winners at ~0.85 of
+               the bf16 mode's throughput.
       'simt' — the fp32 CUDA-core rule kernels through LRPtools whatever the encoder."""
     EPS = LRPutil.EPSILON
     EX_TYPE = 'lrp'
@@ -521,8 +524,8 @@ class ExplainGridTDAttention(object):
         self.has_encoder = hasattr(self.model, 'img_encoder')
         is_vgg = self.has_encoder and isinstance(self.model.img_encoder.encoder, nn.Sequential)
         self.precision = precision or 'fp32'
-        if self.precision not in ('fp32', 'bf16', 'simt'):
-            raise ValueError(f"precision must be 'fp32', 'bf16' or 'simt', got {self.precision!r}")
+        if self.precision not in ('fp32', 'bf16', 'simt', 'mixed'):
+            raise ValueError(f"precision must be 'fp32', 'bf16', 'mixed' or 'simt', got {self.precision!r}")
         tcp = lrp_wrapper._tc_cfg(self.model.img_encoder.encoder) if is_vgg else None
         # the general kernels (fp32-accurate mode) need a first conv with a multiple of 64 output channels
         tc_ok = tcp is not None and (self.precision == 'bf16' or tcp[0][0].out_channels % 64 == 0)
@@ -533,7 +536,9 @@ class ExplainGridTDAttention(object):
         if self.precision == 'bf16' and not tc_ok and self.has_encoder:
             raise NotImplementedError("the tensor-core chain supports VGG-style encoders; use precision='fp32'")
         # the encoder runs on the tcgen05 engine (one forward per image shared by all its words)
-        self.uses_tc = tc_ok and self.precision in ('fp32', 'bf16')
+        if self.precision == 'mixed' and not (tc_ok and not self.is_resnet):
+            raise NotImplementedError("precision='mixed' needs a VGG-style encoder with a 64-channel first layer")
+        self.uses_tc = tc_ok and self.precision in ('fp32', 'bf16', 'mixed')
         self.mean = [0.485, 0.456, 0.406]
         self.std = [0.229, 0.224, 0.225]
         m = self.model
@@ -581,8 +586,11 @@ class ExplainGridTDAttention(object):
                     cfg.append(m.out_channels)
                 elif isinstance(m, nn.MaxPool2d):
                     cfg.append("M")
-            self._engine = tc.TcVggEngine([c.weight for c in convs], [c.bias for c in convs], cfg, self.device,
-                                          precision=self.precision)
+            if self.precision == 'mixed':
+                self._engine = tc.TcVggMixed([c.weight for c in convs], [c.bias for c in convs], cfg, self.device)
+            else:
+                self._engine = tc.TcVggEngine([c.weight for c in convs], [c.bias for c in convs], cfg, self.device,
+                                              precision=self.precision)
         return self._engine
 
     def encode_images(self, imgs):
@@ -641,7 +649,7 @@ class ExplainGridTDAttention(object):
         tcgen05 GEMM with error-compensated bf16x3 operands (measured 2-3e-6 of sum |x w| off fp64, one-sided by the
         tensor cores' round-toward-zero accumulation) — for the shapes it takes.  'fp32' / 'simt' keep the fp32 library
         GEMM: their bar is the reference's elementwise rtol 1e-4 / atol 1e-6 on the saved state."""
-        if self.precision == 'bf16' and ops.LinearX3.supports(weight):
+        if self.precision in ('bf16', 'mixed') and ops.LinearX3.supports(weight):
             return ops.LinearX3(weight, bias)
         return lambda x: torch.addmm(bias, x, weight.t()) if bias is not None else x @ weight.t()
 
@@ -839,7 +847,7 @@ class ExplainGridTDAttention(object):
         req_word = torch.tensor([toks[t + 1] for t in ts], dtype=torch.int32, device=dev)
         req_img = torch.zeros(len(ts), dtype=torch.int32, device=dev)
         return ops.gridtd_decoder_lrp(self._state, self._lrp_weights(), req_img, req_t, req_word,
-                                      tc_gemm=(self.precision == 'bf16'))
+                                      tc_gemm=(self.precision in ('bf16', 'mixed')))
 
     def explain_caption_wordt(self, t):
         """reference :1014-1135 -> (r_img_feature (1,C,h,w), r_words (t+1,))."""
@@ -940,7 +948,7 @@ class ExplainGridTDGradient(GradientFamily, ExplainGridTDAttention):
         i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=self.device)
         return ops.gridtd_decoder_grad(self._state, self._grad_weights(), i32([0] * len(ts)), i32(list(ts)),
                                        i32([toks[t + 1] for t in ts]), guided=self.GUIDED_DECODER,
-                                       tc_gemm=(self.precision == 'bf16'))
+                                       tc_gemm=(self.precision in ('bf16', 'mixed')))
 
     def explain_caption_wordt(self, t):
         """reference :1424-1508 (guided: :1588-1675) -> (d_img_feature (1,C,h,w), r_words (t+1,))."""

@@ -93,7 +93,7 @@ def test_explain_caption_end_to_end_both_precisions(tmp_path):
     img = synth.images(83, 1)
     toks = synth.tokens(84, 3, V)
     outs = {}
-    for prec in ("simt", "fp32", "bf16"):
+    for prec in ("simt", "fp32", "bf16", "mixed"):
         ex = G.ExplainGridTDAttention(_args(E, H, tmp_path), synth.word_map(V), model=model, precision=prec)
         assert ex.uses_tc == (prec != "simt")
         ex.ACCUMULATE_LIKE_REFERENCE = False
@@ -104,6 +104,15 @@ def test_explain_caption_end_to_end_both_precisions(tmp_path):
     heatx3, wordsx3 = outs["fp32"]
     heat16, words16 = outs["bf16"]
     assert len(heat32) == 3 and heat32[0].shape == (1, 3, 224, 224)
+    # 'mixed' (fp32-accurate forward, bf16 chain): the word relevances are the fp32-accurate mode's (same features into
+    # the decoder), the heat-maps carry only the bf16 chain's own rounding
+    for t in range(3):
+        hm, wm = outs["mixed"][0][t], outs["mixed"][1][t]
+        l2m = float((hm - heat32[t]).norm() / heat32[t].norm())
+        l2b = float((heat16[t] - heat32[t]).norm() / heat32[t].norm())
+        print(f"word {t}: mixed vs simt rel L2 {l2m:.3e} (bf16: {l2b:.3e}), spearman {spearman(hm, heat32[t]):.6f}")
+        assert l2m <= 2e-2 and spearman(hm, heat32[t]) >= 0.9995
+        assert_close(wm, words32[t], rtol=1e-3, atol=1e-3, what=f"mixed r_words t={t}")
     # fp32 path vs the oracle
     layers = O.vgg_layers_from_state(vsd)
     feats = O.sequential_forward(layers, img)[-1]
