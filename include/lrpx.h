@@ -577,6 +577,12 @@ enum {
   LRPX_TC_EPI_FWDX = 11,
 };
 
+/* lrpx_tc_conv_args.fwd_flags bit for LRPX_TC_EPI_MUL with ncol == 64 (3x3): the three filter COLUMNS are folded into
+ * the GEMM's N — Wt holds 3 * ncol rows, row dx * ncol + n, K ordered (filter row, channel), 3 * cin columns — and the
+ * epilogue adds the three column-shifted partial sums.  A 64-column MMA is bound by its shared-memory operand reads;
+ * the folded form does a third of the MMAs at three times the width.  Same result up to the fp32 summation order. */
+#define LRPX_TC_FOLD_COLUMNS 8
+
 typedef struct {
   int n_img;            /* PF blocks in A (images or explanations)                                */
   int h, w;             /* unpadded spatial size of A's blocks (== output size)                   */

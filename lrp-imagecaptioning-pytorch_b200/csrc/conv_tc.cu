@@ -940,14 +940,78 @@ __device__ __forceinline__ void epi_fwdx(const TcParams& p, const RowInfo& r, ui
   }
 }
 
+// MUL with folded filter columns (p.fold, 64 output channels): the tile's accumulator holds, per P' row q, three blocks of
+// 64 columns   P'[q][dx, n] = sum_{dy, c} A[q + dy (w+1)][c] W[n][(dy, dx), c]   and the output row is
+//   out[p][n] = gain[p][n] * (P'[p-1][0, n] + P'[p][1, n] + P'[p+1][2, n]).
+// A 64-column MMA reads 4 KB of A and 2 KB of B from shared memory for 128 x 64 x 16 MACs and is bound by those reads
+// (l1tex__data_pipe_tc_wavefronts_mem_shared 78 % at 52 % tensor-pipe activity, profiles/r2_chain_full.md); the folded form
+// reads 4 + 6 KB for three times the MACs and a third of the MMAs.  Neighbouring rows are neighbouring TMEM lanes =
+// neighbouring threads: warp shuffles, plus a 64-byte exchange through shared memory at the three warp boundaries of the
+// 128-row tile; its first and last row have no neighbour, so a tile yields 126 output rows (as in epi_input3).
+// One unit = 16 output channels [ch0, ch0 + 16): the four warps of a lane quarter take one unit each.
+__device__ __forceinline__ void epi_mul_fold(const TcParams& p, const RowInfo& r, uint32_t taddr, int ch0,
+                                             uint32_t release_bar, float* scratch /* [4 quarters][2][16] of this (buffer, unit) */,
+                                             int quarter, int bar_id) {
+  const int lane = threadIdx.x & 31;
+  const int N = p.ncol;                                   // 64
+  const bool edge = (quarter == 0 && lane == 0) || (quarter == 3 && lane == 31);
+  U8 g;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) g.w[k] = 0u;
+  if (r.valid && !edge) {
+    const int img = p.row_img ? p.row_img[r.e] : r.e;
+    g = ldg_nc_v8(p.gain + ((size_t)img * p.blk + r.rem) * N + ch0);
+  }
+  uint32_t v0[16], v1[16], v2[16];
+  TMEM_LD_X16(taddr + ch0, v0);
+  TMEM_LD_X16(taddr + N + ch0, v1);
+  TMEM_LD_X16(taddr + 2 * N + ch0, v2);
+  tmem_ld_wait();
+  epi_release(p, release_bar);
+  float up[16], dn[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    up[k] = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[k]), 1);       // P'[q-1][dx = 0]
+    dn[k] = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[k]), 1);     // P'[q+1][dx = 2]
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) scratch[(quarter * 2 + 0) * 16 + k] = __uint_as_float(v2[k]);   // for the previous quarter's lane 31
+  if (lane == 31)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) scratch[(quarter * 2 + 1) * 16 + k] = __uint_as_float(v0[k]);   // for the next quarter's lane 0
+  // the four quarter warps of this unit meet on their own named barrier (immediate ids: ptxas counts them)
+  if (bar_id == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else if (bar_id == 2) asm volatile("bar.sync 2, 128;" ::: "memory");
+  else if (bar_id == 3) asm volatile("bar.sync 3, 128;" ::: "memory");
+  else asm volatile("bar.sync 4, 128;" ::: "memory");
+  if (lane == 0 && quarter > 0)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) up[k] = scratch[((quarter - 1) * 2 + 1) * 16 + k];
+  if (lane == 31 && quarter < 3)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dn[k] = scratch[((quarter + 1) * 2 + 0) * 16 + k];
+  if (!r.in_range || edge || (p.debug_flags & 1)) return;
+  uint32_t ow[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float a0 = (up[2 * k] + __uint_as_float(v1[2 * k]) + dn[2 * k]) * bf16_lo(g.w[k]);
+    const float a1 = (up[2 * k + 1] + __uint_as_float(v1[2 * k + 1]) + dn[2 * k + 1]) * bf16_hi(g.w[k]);
+    ow[k] = r.valid ? pack_bf16(a0, a1) : 0u;             // padding rows are written as zeros
+  }
+  stg_v8(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.row * N + ch0, ow);
+}
+
 // internal epilogue code (not part of the ABI): FWDX of a VGG-style layer, instantiated on its own so that the general
 // FWDX epilogue's register pressure (BatchNorm / Add / strided-store state, 470 bytes of stack) stays out of it
 constexpr int TC_EPI_FWDX_SIMPLE = 12;
+constexpr int TC_EPI_MUL_FOLD = 15;         // MUL with the three filter COLUMNS folded into N (64-channel layers, epi_mul_fold)
 constexpr int TC_EPI_MULX_S = 13, TC_EPI_MULX_UNPOOL_S = 14;      // MULX / MULX_UNPOOL with one gain group, no addend (epi_mulx)
 
 // number of 32-column units per (lane quarter, M half) of a tile
 __device__ __forceinline__ int epi_units_per_half(const TcParams& p, int epi) {
   if (epi == LRPX_TC_EPI_INPUT || epi == LRPX_TC_EPI_INPUT3) return 1;
+  if (epi == TC_EPI_MUL_FOLD) return 4;                   // four units of 16 output channels (`c` counts 32 per unit: c >> 1)
   const int ncols = (epi == LRPX_TC_EPI_FWD_GAIN || epi == LRPX_TC_EPI_FWDX || epi == TC_EPI_FWDX_SIMPLE) ? p.half : p.bn;
   return ncols >> 5;
 }
@@ -965,6 +1029,8 @@ __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, u
   const int n0 = n_tile * p.bn;
   if (EPI == LRPX_TC_EPI_INPUT3) {
     epi_input3(p, r0, taddr, release_bar, scratch, quarter, bar_id);
+  } else if (EPI == TC_EPI_MUL_FOLD) {
+    epi_mul_fold(p, r0, taddr, c >> 1, release_bar, scratch, quarter, bar_id);
   } else if (EPI == LRPX_TC_EPI_MULX) {
     epi_mulx<false, false>(p, r, taddr, n0, c, release_bar);
   } else if (EPI == LRPX_TC_EPI_MULX_UNPOOL) {
@@ -1146,6 +1212,11 @@ __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_bas
   }
   if (sub >= n_units) {                 // nothing to read for this warp: hand the buffer back at once
     epi_release(p, release_bar);
+    return;
+  }
+  if (EPI == TC_EPI_MUL_FOLD) {         // one unit (16 output channels) per warp of the lane quarter
+    const RowInfo rf = row_info(p, row_base);
+    epi_unit<EPI>(p, rf, taddr_q, n_tile, sub << 5, release_bar, stage, tmo, scratch + sub * 128, quarter, 1 + sub);
     return;
   }
   int h_cached = -1;
@@ -1439,7 +1510,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   // rows BEFORE the named barrier of a tile and reads its neighbours' right after it; with two copies alternating per
   // tile a slot is rewritten only after the barrier of the tile in between, which every reader of the old value has
   // passed its reads to reach.
-  __shared__ float in3_scratch[2][2][2][64];
+  __shared__ float in3_scratch[2][4][128];      // INPUT3: [buffer][tile parity][2 halves x 64]; MUL_FOLD: [buffer][unit][4 quarters x 2 x 16]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1642,7 +1713,9 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       if (PAIR) rel_bar = mapa_u32(rel_bar, 0);          // shared::cluster address of the LEADER's barrier (both ranks)
       run_epilogue_tile<EPI>(p, m_tile * tile_rows - p.fold + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh,
                              pf_row, rel_bar, stage, &tmO,
-                             EPI == LRPX_TC_EPI_INPUT3 ? &in3_scratch[buf][(it >> 1) & 1][0][0] : nullptr, quarter, it);
+                             EPI == LRPX_TC_EPI_INPUT3 ? &in3_scratch[buf][(it >> 1) & 1][0]
+                                                       : (EPI == TC_EPI_MUL_FOLD ? &in3_scratch[buf][0][0] : nullptr),
+                             quarter, it);
     }
     if (EPI == LRPX_TC_EPI_MUL && p.store_off) {      // the staging block must outlive the last tile store's read
       if (lane == 0) bulk_wait_read0();
@@ -1989,8 +2062,15 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     } else if (epi != LRPX_TC_EPI_STORE_F32) LRPX_CHECK_ARG(a->gain, "gain required");
     if (epi == LRPX_TC_EPI_MUL_UNPOOL) LRPX_CHECK_ARG(a->pool_idx, "pool_idx required");
     p.bn = a->ncol <= 256 ? a->ncol : 256;
+    if (a->fwd_flags & LRPX_TC_FOLD_COLUMNS) {
+      // Wt holds 3 * ncol rows (row dx * ncol + n, K ordered (filter row, channel)): see epi_mul_fold
+      LRPX_CHECK_ARG(epi == LRPX_TC_EPI_MUL && a->ncol == 64 && a->ksize == 3, "folded filter columns: MUL epilogue, 64 columns, 3x3");
+      p.fold = 1;
+      p.taps = 3;
+      p.bn = 3 * a->ncol;
+    }
     if (epi == LRPX_TC_EPI_STORE_F32 && a->ncol > 256 && a->ncol % 256 && a->ncol % 64 == 0) p.bn = 64;
-    LRPX_CHECK_ARG(a->ncol % p.bn == 0, "ncol must be <= 256 or a multiple of 256 (STORE_F32: or of 64)");
+    LRPX_CHECK_ARG(p.fold || a->ncol % p.bn == 0, "ncol must be <= 256 or a multiple of 256 (STORE_F32: or of 64)");
     // plain GEMMs with few rows (the decoder's per-step GEMMs: 1216 x 1536 x 1536): 256-column tiles give fewer tiles
     // than SMs; 128-column tiles fill the machine (LRPX_TC_GEMM_BN=256 keeps the wide tiles)
     if (a->ksize == 1 && epi == LRPX_TC_EPI_STORE_F32 && p.bn == 256) {
@@ -2007,7 +2087,7 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       p.n_valid = a->n_valid;
     }
   }
-  p.num_n_tiles = a->ncol / p.bn;
+  p.num_n_tiles = p.fold ? 1 : a->ncol / p.bn;
   cudaStream_t st = as_stream(stream);
   {
     const char* e2 = getenv("LRPX_TC_DEBUG");
@@ -2019,7 +2099,7 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     const bool want_slab = a->ksize == 3 && !(env && env[0] == '0');
     // EPI_MUL: results leave through a 16 KB staging area (1 KB per epilogue warp) and TMA tile stores
     const char* env_ts = getenv("LRPX_TC_TMASTORE");
-    const bool tma_store = epi == LRPX_TC_EPI_MUL && !(env_ts && env_ts[0] == '0');
+    const bool tma_store = epi == LRPX_TC_EPI_MUL && !p.fold && !(env_ts && env_ts[0] == '0');
     const int reserve = tma_store ? TC_EPI_WARPS * 1024 : 0;
     if (want_slab && plan_slab(p, reserve)) {
       p.half_rows = p.fold ? TC_BM - 2 : TC_BM;
@@ -2040,7 +2120,8 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       if (rc) return rc;
       rc = make_map_2d(&ma1, a->a, (uint64_t)p.m_total, (uint64_t)a_phys, (uint32_t)(p.box1_rows ? p.box1_rows : 8));
       if (rc) return rc;
-      rc = make_map_2d(&mb, a->wt, (uint64_t)a->ncol, (uint64_t)p.taps * a->cin, (uint32_t)p.bn);
+      rc = make_map_2d(&mb, a->wt, (uint64_t)(epi == LRPX_TC_EPI_MUL && p.fold ? 3 * a->ncol : a->ncol),
+                       (uint64_t)p.taps * a->cin, (uint32_t)p.bn);
       if (rc) return rc;
       // CTA pairs sharing the streamed B tiles through TMA multicast (halves the L2 -> SM weight traffic, which is
       // what bounds the 256/512-channel layers: ~12 TB/s of B re-fetches at 128-row tiles)
@@ -2080,7 +2161,9 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       if (p.cluster == 2) grid &= ~1;
       switch (epi) {
         case LRPX_TC_EPI_FWD_GAIN: return launch_tc_slab<LRPX_TC_EPI_FWD_GAIN>(ma0, ma1, mb, mbh, mo, p, grid, st);
-        case LRPX_TC_EPI_MUL: return launch_tc_slab<LRPX_TC_EPI_MUL>(ma0, ma1, mb, mbh, mo, p, grid, st);
+        case LRPX_TC_EPI_MUL:
+          if (p.fold) return launch_tc_slab<TC_EPI_MUL_FOLD>(ma0, ma1, mb, mbh, mo, p, grid, st);
+          return launch_tc_slab<LRPX_TC_EPI_MUL>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_MUL_UNPOOL: return launch_tc_slab<LRPX_TC_EPI_MUL_UNPOOL>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_INPUT: return launch_tc_slab<LRPX_TC_EPI_INPUT>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_INPUT3: return launch_tc_slab<LRPX_TC_EPI_INPUT3>(ma0, ma1, mb, mbh, mo, p, grid, st);
@@ -2097,7 +2180,7 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       }
     }
   }
-  LRPX_CHECK_ARG(epi != LRPX_TC_EPI_INPUT3, "INPUT3 needs the slab kernel (3x3, LRPX_TC_SLAB != 0)");
+  LRPX_CHECK_ARG(epi != LRPX_TC_EPI_INPUT3 && !p.fold, "folded filter columns need the slab kernel (3x3, LRPX_TC_SLAB != 0)");
   p.slab_mode = 0; p.mh = 1; p.n_issuers = 1; p.cluster = 1; p.half_rows = TC_BM; p.tile_out_rows = TC_BM;
   p.num_m_tiles = (p.m_total + TC_BM - 1) / TC_BM;
   const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;

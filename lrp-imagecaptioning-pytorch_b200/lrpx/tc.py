@@ -141,7 +141,8 @@ def _k_operand(t, split):
 
 
 class _Conv:
-    __slots__ = ("cin", "cout", "h", "w", "pool_after", "w_f32", "bias", "w_dual", "w_rel", "w_rel3", "w_fwd", "n_acc")
+    __slots__ = ("cin", "cout", "h", "w", "pool_after", "w_f32", "bias", "w_dual", "w_rel", "w_rel3", "w_fwd", "n_acc",
+                 "w_rel_fold")
 
 
 class VggState:
@@ -215,7 +216,7 @@ class TcVggEngine:
             c.pool_after = False
             c.w_f32 = w
             c.bias = None if biases[k] is None else biases[k].detach().to(device=device, dtype=torch.float32).contiguous()
-            c.w_dual = c.w_rel = c.w_rel3 = c.w_fwd = None
+            c.w_dual = c.w_rel = c.w_rel3 = c.w_fwd = c.w_rel_fold = None
             c.n_acc = 0
             if k == 0 and (c.cin != 3 or c.cout not in (8, 16, 32, 64)):
                 raise _lib.LrpxError("first conv must be 3 -> {8,16,32,64} channels")
@@ -245,6 +246,13 @@ class TcVggEngine:
             else:
                 c.w_dual = dual_forward_weights(w)
                 c.w_rel = weight_prep(w, 2)          # (cin, 9*cout): W+ flipped & transposed
+                # 64-column layers without a pool below (VGG16: the 64 -> 64 layer at full resolution) can run with the
+                # filter columns folded into N (LRPX_TC_FOLD_COLUMNS: row dx*cin + n, K ordered (filter row, channel)).
+                # OFF by default: a third of the MMAs, but the shifted-sum epilogue is one latency-bound pass per
+                # 126-row tile and the layer takes 1.25 ms per 128 requests instead of 0.61.
+                if c.cin == 64 and not self.convs[-1].pool_after and os.environ.get("LRPX_TC_FOLD64", "0") == "1":
+                    c.w_rel_fold = (c.w_rel.reshape(c.cin, 3, 3, c.cout).permute(2, 0, 1, 3)
+                                    .reshape(3 * c.cin, 3 * c.cout).contiguous())
             if self.general:
                 self._general_weights(c, w, first=(k == 0))
             self.convs.append(c)
@@ -465,6 +473,9 @@ class TcVggEngine:
             elif below.pool_after:
                 tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL_UNPOOL, dst, gain=st.gain[li - 1],
                         row_img=rimg, pool_idx=st.idx[li - 1])
+            elif c.w_rel_fold is not None:
+                tc_conv(s, c.w_rel_fold, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL, dst, gain=st.gain[li - 1], row_img=rimg,
+                        fwd_flags=8)
             else:
                 tc_conv(s, c.w_rel, nq, c.h, c.w, c.cout, c.cin, 3, EPI_MUL, dst, gain=st.gain[li - 1], row_img=rimg)
             cur ^= 1

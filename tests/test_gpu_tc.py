@@ -253,3 +253,28 @@ def test_first_layer_folded_columns_equals_plain_form(n, h, w):
     cn = torch.nn.grad.conv2d_input((n, 3, h, w), wb.clamp(max=0), s, 1, 1)
     ref = x.clamp(min=0) * cp + x.clamp(max=0) * cn
     assert_close(out24, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()), what="folded first layer vs rule")
+
+
+def test_folded_filter_columns_equal_the_plain_contraction():
+    """LRPX_TC_FOLD_COLUMNS (the 64-column MUL layer with its three filter columns folded into N, off by default in the
+    engine): same result as the nine-tap contraction up to the fp32 summation order (bf16 output: 1 ulp)."""
+    from lrpx import tc
+    g = torch.Generator().manual_seed(5)
+    n, h, w, cout, cin = 3, 20, 28, 64, 64
+    wgt = torch.randn(cout, cin, 3, 3, generator=g).to(DEV)
+    w_rel = tc.weight_prep(wgt, 2)                                                   # (cin, 9*cout)
+    w_fold = w_rel.reshape(cin, 3, 3, cout).permute(2, 0, 1, 3).reshape(3 * cin, 3 * cout).contiguous()
+    s = tc.nchw_to_pf(torch.randn(n, cout, h, w, generator=g).to(DEV))
+    gain = tc.nchw_to_pf(torch.rand(2, cin, h, w, generator=g).to(DEV))
+    rimg = torch.tensor([1, 0, 1], dtype=torch.int32, device=DEV)
+    rows = tc.pf_rows(n, h, w)
+    a = torch.empty(rows, cin, device=DEV, dtype=torch.bfloat16)
+    b = torch.full((rows, cin), 7.0, device=DEV, dtype=torch.bfloat16)
+    tc.tc_conv(s, w_rel, n, h, w, cout, cin, 3, tc.EPI_MUL, a, gain=gain, row_img=rimg)
+    tc.tc_conv(s, w_fold, n, h, w, cout, cin, 3, tc.EPI_MUL, b, gain=gain, row_img=rimg, fwd_flags=8)
+    assert torch.isfinite(b.float()).all()
+    err = (a.float() - b.float()).abs()
+    assert float(err.max()) <= 2.0 ** -7 * float(a.float().abs().max())
+    assert float((err > 0).float().mean()) < 0.2                                      # most elements round identically
+    pad = tc.pf_to_dense(b, n, h, w, cin)                                             # and the padding rows stay zero
+    assert float(b.float().abs().sum()) == pytest.approx(float(pad.abs().sum()), rel=1e-3)
