@@ -386,10 +386,13 @@ def encoder_gradient_simt(model, sample, target, guided=False, return_output=Fal
                                         zero it anyway)
     The precision='simt' path of the gradient explainers; the tensor-core chain (lrpx.tc, rule 'gradient' / 'guided') is
     the fast one."""
-    if not isinstance(model, nn.Sequential):
-        raise NotImplementedError("the gradient explainers cover Sequential conv / ReLU / max-pool encoders")
     if not sample.is_cuda:
         raise RuntimeError("lrpx: encoder_gradient_simt needs a CUDA tensor (there is no CPU fallback)")
+    if _is_bottleneck_resnet(model):
+        return _resnet_gradient_simt(model, sample, target, guided, return_output)
+    if not isinstance(model, nn.Sequential):
+        raise NotImplementedError("the gradient explainers cover Sequential conv / ReLU / max-pool encoders and the "
+                                  "Bottleneck ResNet of models/resnet.py")
     leaves = _flatten_sequential(model)
     for i, m in enumerate(leaves):
         if not isinstance(m, (nn.Conv2d, nn.ReLU, nn.MaxPool2d)):
@@ -417,4 +420,52 @@ def encoder_gradient_simt(model, sample, target, guided=False, return_output=Fal
                 g = ops.relu_mask(out, g)
             else:
                 g = ops.maxpool_wta(a, g, m.kernel_size, m.stride, m.padding)
+    return (g, x) if return_output else g
+
+
+def _resnet_gradient_simt(model, sample, target, guided=False, return_output=False):
+    """encoder_gradient_simt for the Bottleneck ResNet of models/resnet.py (eval mode): convolutions of any stride through
+    lrpx_conv_rule_rin_f32 (PLAIN, against ones), BatchNorm as its per-channel scale, ReLU masks, the overlapping 3x3/s2
+    max-pool through lrpx_maxpool_wta_f32, the residual Add as a copy into both branches whose gradients meet again at
+    the block input.  ``guided``: the reference hooks only the ReLUs that are direct children of the encoder
+    (gridTDmodel.py:1687-1691: ``named_children``), i.e. the stem's; the ReLUs inside the blocks keep their plain
+    derivative."""
+    m = model
+    if m.training:
+        raise NotImplementedError("the gradient explainers need eval() mode (BatchNorm running statistics)")
+    blocks = [b for L in (m.layer1, m.layer2, m.layer3, m.layer4) for b in L]
+    conv = lambda c, x: ops.conv_forward(x, c.weight.detach(), None if c.bias is None else c.bias.detach(), c.stride,
+                                         c.padding, c.dilation)
+    scale = lambda bn: (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().view(1, -1, 1, 1)
+    bnf = lambda bn, x: x * scale(bn) + (bn.bias - bn.running_mean * bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().view(1, -1, 1, 1)
+    dconv = lambda c, x_in, g: ops.conv_rule_rin(torch.ones_like(x_in), c.weight.detach(), g.contiguous(), c.stride, c.padding,
+                                                 c.dilation, net=ops.NET_PLAIN)
+    with torch.no_grad():
+        x0 = sample.detach().float()
+        r1 = torch.relu(bnf(m.bn1, conv(m.conv1, x0)))
+        x = ops.maxpool_forward(r1, m.maxpool.kernel_size, m.maxpool.stride, m.maxpool.padding, return_indices=False)
+        saved = []
+        for b in blocks:
+            o1 = torch.relu(bnf(b.bn1, conv(b.conv1, x)))
+            o2 = torch.relu(bnf(b.bn2, conv(b.conv2, o1)))
+            o3 = bnf(b.bn3, conv(b.conv3, o2))
+            idn = x if b.downsample is None else bnf(b.downsample[1], conv(b.downsample[0], x))
+            out = torch.relu(o3 + idn)
+            saved.append((x, o1, o2, out))
+            x = out
+        if tuple(target.shape) != tuple(x.shape):
+            raise RuntimeError(f"Mismatch in shape: grad_output[0] has a shape of {tuple(target.shape)} and "
+                               f"output[0] has a shape of {tuple(x.shape)}.")
+        g = target.detach().float().contiguous()
+        for b, (x_in, o1, o2, out) in zip(reversed(blocks), reversed(saved)):
+            g = ops.relu_mask(out, g)
+            go = dconv(b.conv3, o2, g * scale(b.bn3))
+            go = dconv(b.conv2, o1, ops.relu_mask(o2, go) * scale(b.bn2))
+            go = dconv(b.conv1, x_in, ops.relu_mask(o1, go) * scale(b.bn1))
+            gi = g if b.downsample is None else dconv(b.downsample[0], x_in, g * scale(b.downsample[1]))
+            g = go + gi
+        g = ops.maxpool_wta(r1, g, m.maxpool.kernel_size, m.maxpool.stride, m.maxpool.padding)
+        if guided:
+            g = ops.relu_mask(g, g)
+        g = dconv(m.conv1, x0, ops.relu_mask(r1, g) * scale(m.bn1))
     return (g, x) if return_output else g

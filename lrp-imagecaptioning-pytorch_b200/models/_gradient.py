@@ -108,8 +108,10 @@ class GradientFamily:
         return self._engine
 
     def _check_encoder(self):
-        if getattr(self, "is_resnet", False):
-            raise NotImplementedError("the gradient-family explainers cover VGG-style encoders (conv3x3 / ReLU / max-pool)")
+        # Bottleneck ResNets: the fp32 CUDA-core path only (LRPtools.lrp_wrapper.encoder_gradient_simt)
+        if getattr(self, "is_resnet", False) and self.precision in ("bf16", "mixed"):
+            raise NotImplementedError("ResNet encoders: the gradient-family explainers run on the fp32 CUDA-core kernels "
+                                      "(precision 'fp32' or 'simt')")
 
     def explainer_forward(self, feat, tokens, quirk_double_bias_ih=False, want_gates=True):
         # the gradient explainers' LSTM forwards add bias_ih + bias_hh (gridTDmodel.py:1265): no Q3 here

@@ -351,3 +351,83 @@ def test_batch_explainer_with_gradient_explainers(tmp_path, cls):
             # the explainer forward's library GEMMs pick another algorithm for 2 rows than for 1: ~1e-5 of the maximum
             assert_close(heat[q:q + 1], one, rtol=1e-3, atol=1e-4 * float(one.abs().max()), what=f"image {b} word {t}")
             assert_close(r_words[q, :t + 1], rw, rtol=1e-3, atol=1e-5, what=f"words image {b} word {t}")
+
+
+@pytest.mark.parametrize("guided", [False, True])
+def test_resnet_encoder_gradient_vs_autograd(guided):
+    """Gradient explainers on a Bottleneck ResNet encoder (fp32 CUDA-core path): input gradient vs torch autograd through
+    the same module (eval mode), 64x64 image, blocks [2, 1, 1, 1]; guided = the reference's hooks, which reach only the
+    stem's ReLU of a ResNet (named_children of the encoder, gridTDmodel.py:1687-1691)."""
+    import models.resnet as R
+    from LRPtools import lrp_wrapper
+    torch.manual_seed(17)
+    net = R.ResNet(R.Bottleneck, [2, 1, 1, 1])
+    g = torch.Generator().manual_seed(18)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+    enc = torch.nn.Sequential(*list(net.children())[:-2]).to(DEV).eval()
+    body = enc                     # conv1, bn1, relu, maxpool, layer1..4
+    x = synth.images(19, 1, 64).to(DEV)
+    xr = x.clone().requires_grad_(True)
+    handles = []
+    if guided:
+        relu = body[2]
+        relu.inplace = False
+        handles.append(relu.register_full_backward_hook(lambda mod, gi, go: (go[0].clamp(min=0) * (mod._out > 0).float(),)))
+        handles.append(relu.register_forward_hook(lambda mod, i, o: setattr(mod, "_out", o.detach())))
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the autograd side in true fp32 (cuDNN's default would be TF32)
+    try:
+        feat = body(xr)
+        tgt = torch.randn(feat.shape, generator=torch.Generator().manual_seed(20)).to(DEV)
+        feat.backward(tgt)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    want = xr.grad.detach()
+    for h in handles:
+        h.remove()
+    # the plan walks the ResNet object: rebuild one that shares the Sequential's modules
+    res = R.ResNet(R.Bottleneck, [2, 1, 1, 1])
+    res.conv1, res.bn1, res.relu, res.maxpool, res.layer1, res.layer2, res.layer3, res.layer4 = list(body.children())
+    res.to(DEV).eval()
+    got, f2 = lrp_wrapper.encoder_gradient_simt(res, x, tgt, guided=guided, return_output=True)
+    assert_close(f2, feat.detach(), rtol=1e-3, atol=1e-4 * float(feat.abs().max()), what="features")
+    print(f"ResNet gradient guided={guided}: rel-L2 {_rel_l2(got, want):.3e}, Spearman {spearman(got, want):.6f}")
+    assert _rel_l2(got, want) < 1e-2 and spearman(got, want) > 0.999
+
+
+def test_gradient_explainer_with_resnet101_encoder(tmp_path):
+    """ExplainGridTDGradient on a ResNet101 encoder (7x7 grid of 2048-d features): the encoder half runs on the fp32
+    CUDA-core path; explain_cnn of the word's decoder gradient = torch autograd through the same encoder."""
+    from models import gridTDmodel as G
+    V, H, E = 60, 64, 32
+    torch.manual_seed(23)
+    model = G.GridTDModel(E, H, V, "resnet101", n_pixel=49)
+    model.load_state_dict(synth.gridtd_decoder_state(331, V, H, E, C=2048, n_pixel=49), strict=False)
+    model.to(DEV).eval()
+    args = _args(E, H, tmp_path)
+    args.encoder = "resnet101"
+    ex = G.ExplainGridTDGradient(args, synth.word_map(V), model=model)
+    assert not ex.uses_tc and ex.is_resnet
+    with pytest.raises(NotImplementedError):
+        G.ExplainGridTDGradient(args, synth.word_map(V), model=model, precision="bf16")
+    img = synth.images(332, 1).to(DEV)
+    toks = synth.tokens(333, 2, V)
+    ex.preprocess_img = lambda p: img
+    model.beam_search = lambda *a, **k: (["a b"], toks[1:])
+    heat, words = ex.explain_caption("synthetic.jpg")
+    assert len(heat) == 2 and heat[0].shape == (1, 3, 224, 224) and words[1].shape == (2,)
+    d_img, _ = ex.explain_caption_wordt(1)
+    assert d_img.shape == (1, 2048, 7, 7)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        xr = img.clone().requires_grad_(True)
+        model.img_encoder.encoder(xr).backward(d_img)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert _rel_l2(heat[1], xr.grad) < 2e-2 and spearman(heat[1], xr.grad) > 0.999, _rel_l2(heat[1], xr.grad)
