@@ -789,15 +789,16 @@ __device__ __forceinline__ void epi_fwdx_simple(const TcParams& p, const RowInfo
                                                 uint32_t release_bar) {
   const bool sp = p.split != 0;
   const int cout = p.cout;
-#pragma unroll 1
-  for (int q = 0; q < 2; ++q) {
-    const int ch = n_tile * p.half + c + 16 * q;
+  // one unit = 16 output channels (epi_units_per_half): a 64-channel layer then keeps all four warps of a lane quarter
+  // busy (with 32-column units two of them had nothing to do and the other two ran two serial passes)
+  {
+    const int ch = n_tile * p.half + c;
     uint32_t vw[16], vp[16];
-    TMEM_LD_X16(taddr + c + 16 * q, vw);
-    if (p.n_acc >= 2) TMEM_LD_X16(taddr + p.half + c + 16 * q, vp);
+    TMEM_LD_X16(taddr + c, vw);
+    if (p.n_acc >= 2) TMEM_LD_X16(taddr + p.half + c, vp);
     tmem_ld_wait();
-    if (q == 1) epi_release(p, release_bar);
-    if (!r.in_range) continue;
+    epi_release(p, release_bar);
+    if (!r.in_range) return;
     float bv[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) bv[k] = 0.f;
@@ -1012,6 +1013,7 @@ constexpr int TC_EPI_MULX_S = 13, TC_EPI_MULX_UNPOOL_S = 14;      // MULX / MULX
 __device__ __forceinline__ int epi_units_per_half(const TcParams& p, int epi) {
   if (epi == LRPX_TC_EPI_INPUT || epi == LRPX_TC_EPI_INPUT3) return 1;
   if (epi == TC_EPI_MUL_FOLD) return 4;                   // four units of 16 output channels (`c` counts 32 per unit: c >> 1)
+  if (epi == TC_EPI_FWDX_SIMPLE) return p.half >> 4;      // 16-column units (run_epilogue_tile: c = u << 4)
   const int ncols = (epi == LRPX_TC_EPI_FWD_GAIN || epi == LRPX_TC_EPI_FWDX || epi == TC_EPI_FWDX_SIMPLE) ? p.half : p.bn;
   return ncols >> 5;
 }
@@ -1222,7 +1224,7 @@ __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_bas
   int h_cached = -1;
   RowInfo r{};
   for (int u = sub; u < n_units; u += step) {
-    const int h = u / uph, c = (u - h * uph) << 5;
+    const int h = u / uph, c = (u - h * uph) << (EPI == TC_EPI_FWDX_SIMPLE ? 4 : 5);
     const int hr = (EPI == LRPX_TC_EPI_INPUT3) ? p.half_rows : TC_BM;
     if (h != h_cached) { r = row_info(p, row_base + h * hr); h_cached = h; }
     if (pf_row_base >= 0) epi_prefetch_unit<EPI>(p, pf_row_base + h * TC_BM, n_tile, c);
