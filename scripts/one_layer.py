@@ -8,15 +8,25 @@ import synth
 from lrpx import tc
 
 sd = synth.vgg_state(1)
-eng = tc.TcVggEngine([sd[k] for k in sd if k.endswith("weight")], [sd[k] for k in sd if k.endswith("bias")], synth.VGG16_CFG, "cuda")
+PREC = os.environ.get("PRECISION", "bf16")          # fp32: the general (MULX) kernels with hi|lo rows
+eng = tc.TcVggEngine([sd[k] for k in sd if k.endswith("weight")], [sd[k] for k in sd if k.endswith("bias")], synth.VGG16_CFG, "cuda",
+                     precision=PREC)
 st = eng.forward(torch.randn(1, 3, 224, 224, device="cuda"))
 n = int(os.environ.get("CHUNK", "128"))
 reps = int(os.environ.get("REPS", "3"))
 rimg = torch.zeros(n, dtype=torch.int32, device="cuda")
 for li in [int(v) for v in os.environ.get("LAYERS", "1").split(",")]:
     c = eng.convs[li]
-    a = torch.randn(tc.pf_rows(n, c.h, c.w), c.cout, device="cuda").to(torch.bfloat16)
-    if li == 0:
+    a = torch.randn(tc.pf_rows(n, c.h, c.w), c.cout * eng.rm, device="cuda").to(torch.bfloat16)
+    if eng.general and li > 0:
+        below = eng.convs[li - 1]
+        oh, ow = (2 * c.h, 2 * c.w) if below.pool_after else (c.h, c.w)
+        out = torch.empty(tc.pf_rows(n, oh, ow), c.cin * eng.rm, device="cuda", dtype=torch.bfloat16)
+        fn = lambda: tc.tc_conv(a, c.w_rel, n, c.h, c.w, c.cout * eng.km, c.cin, 3,
+                                tc.EPI_MULX_UNPOOL if below.pool_after else tc.EPI_MULX, out, gain=st.gain[li - 1],
+                                row_img=rimg, pool_idx=st.idx[li - 1] if below.pool_after else None,
+                                a_phys=c.cout * eng.rm if eng.split else 0, groups=1, split=int(eng.split))
+    elif li == 0:
         out = torch.empty(n, 3, c.h, c.w, device="cuda")
         if c.w_rel3 is not None:
             fn = lambda: tc.tc_conv(a, c.w_rel3, n, c.h, c.w, c.cout, 24, 3, tc.EPI_INPUT3, out, row_img=rimg, x=st.x)
