@@ -238,6 +238,11 @@ def test_compute_lrp_routes_to_the_chain(golden):
     assert_close(rel, ref, rtol=1e-4, atol=1e-4 * scale, what="compute_lrp default (fp32-accurate chain)")
     r_bf = net.compute_lrp(x.clone(), target=tgt, precision="bf16").cpu().double()
     assert float((r_bf - ref).norm() / ref.norm()) <= 5e-2 and spearman(r_bf, ref) >= 0.99
+    # 'mixed': fp32-accurate forward (gains, max-pool winners), bf16 chain — only the chain's own rounding is left
+    r_mx = net.compute_lrp(x.clone(), target=tgt, precision="mixed").cpu().double()
+    l2_mx, l2_bf = float((r_mx - ref).norm() / ref.norm()), float((r_bf - ref).norm() / ref.norm())
+    print(f"compute_lrp rel-L2 vs the reference: mixed {l2_mx:.3e}, bf16 {l2_bf:.3e}")
+    assert l2_mx <= 1e-2 and spearman(r_mx, ref) >= 0.9999
     r_simt = net.compute_lrp(x.clone(), target=tgt, precision="simt")
     assert_close(r_simt, ref, what="compute_lrp simt")
     # Q1: accumulation into sample.grad
@@ -257,3 +262,5 @@ def test_compute_lrp_routes_to_the_chain(golden):
     e_tc, e_simt = float((r21 - ref21).abs().max()), float((r21_simt - ref21).abs().max())
     print(f"alpha2beta1 through compute_lrp: chain err {e_tc:.3e}, simt err {e_simt:.3e}, |2R+| max {pos_mag:.3e}")
     assert e_tc <= 2e-4 * pos_mag
+    with pytest.raises(NotImplementedError):          # 'mixed' is the alpha 1 / beta 0 preset only
+        net.compute_lrp(x.clone(), target=tgt, precision="mixed")
