@@ -214,6 +214,22 @@ __global__ void __launch_bounds__(512) ggrad_attn_kernel(const float* __restrict
   }
 }
 
+// the same sum, one block per (pixel, request): for captions too long for the shared-memory form above
+template <bool SPLIT>
+__global__ void ggrad_attn_slow_kernel(const float* __restrict__ alpha, const float* __restrict__ uctx,
+                                       const int32_t* __restrict__ req_img, const int32_t* __restrict__ req_t,
+                                       float* __restrict__ dproj, __nv_bfloat16* __restrict__ a3, int T, int P, int H) {
+  const int q = blockIdx.y, p = blockIdx.x;
+  const int b = req_img[q], t = req_t[q];
+  const float* al = alpha + (size_t)b * T * P + p;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float acc = 0.f;
+    for (int i = t; i >= 0; --i) acc = fmaf(uctx[((size_t)q * T + i) * H + h], al[(size_t)i * P], acc);
+    if (SPLIT) put_operand(dproj, a3, (size_t)q * P + p, H, h, acc);
+    else dproj[((size_t)q * P + p) * H + h] = acc;
+  }
+}
+
 static size_t ggrad_carve(const lrpx_gridtd_grad_args* a, float* base, GGradWs* w) {
   size_t off = 0;
   auto take = [&](size_t n) {
@@ -463,16 +479,20 @@ int lrpx_gridtd_decoder_grad_f32(const lrpx_gridtd_grad_args* a, void* workspace
   RUN(gemm_any<GE_STORE>(w.d_glob, a->W_glob, w3_glob, w.a3, w.v, Q, C, E, none, st));
   ggrad_avg_kernel<<<Q, 128, 0, st>>>(*a, w);
   const size_t att_smem = (size_t)T * (((P + 3) & ~3) + H) * sizeof(float);
-  LRPX_CHECK_ARG(att_smem <= 200 * 1024, "T * (P + H) too large for the attention accumulation kernel");
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(ggrad_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(ggrad_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
+  if (att_smem <= 200 * 1024) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(ggrad_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(ggrad_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_done = true;
+    }
+    const int at = H / 4 >= 512 ? 512 : ((H / 4 + 31) & ~31);
+    if (w3_proj) ggrad_attn_kernel<true><<<Q, at, att_smem, st>>>(a->alpha, w.uctx, a->req_img, a->req_t, w.dproj, w.a3, T, P, H);
+    else ggrad_attn_kernel<false><<<Q, at, att_smem, st>>>(a->alpha, w.uctx, a->req_img, a->req_t, w.dproj, w.a3, T, P, H);
+  } else {          // long captions x wide hidden state: alpha and d_context rows do not fit one block's shared memory
+    if (w3_proj) ggrad_attn_slow_kernel<true><<<dim3(P, Q), nt, 0, st>>>(a->alpha, w.uctx, a->req_img, a->req_t, w.dproj, w.a3, T, P, H);
+    else ggrad_attn_slow_kernel<false><<<dim3(P, Q), nt, 0, st>>>(a->alpha, w.uctx, a->req_img, a->req_t, w.dproj, w.a3, T, P, H);
   }
-  const int at = H / 4 >= 512 ? 512 : ((H / 4 + 31) & ~31);
-  if (w3_proj) ggrad_attn_kernel<true><<<Q, at, att_smem, st>>>(a->alpha, w.uctx, a->req_img, a->req_t, w.dproj, w.a3, T, P, H);
-  else ggrad_attn_kernel<false><<<Q, at, att_smem, st>>>(a->alpha, w.uctx, a->req_img, a->req_t, w.dproj, w.a3, T, P, H);
   GemmEpi fe{a->feat, nullptr, w.coefavg, a->req_img, P};
   if (guided) RUN(gemm_any<GE_ADD_MASK>(w.dproj, a->W_proj, w3_proj, w.a3, a->d_feat, Q * P, C, H, fe, st, w3_proj != nullptr));
   else RUN(gemm_any<GE_ADD>(w.dproj, a->W_proj, w3_proj, w.a3, a->d_feat, Q * P, C, H, fe, st, w3_proj != nullptr));

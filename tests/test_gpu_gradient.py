@@ -431,3 +431,26 @@ def test_gradient_explainer_with_resnet101_encoder(tmp_path):
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
     assert _rel_l2(heat[1], xr.grad) < 2e-2 and spearman(heat[1], xr.grad) > 0.999, _rel_l2(heat[1], xr.grad)
+
+
+def test_decoder_grad_long_caption_wide_state_vs_oracle():
+    """T x (P + H) beyond one block's shared memory (45 steps, H = 1152): the per-(pixel, request) form of the attention
+    accumulation takes over; same result as the oracle."""
+    from lrpx import ops
+    from models._gradient import gridtd_grad_weights
+    V, H, E, T = 50, 1152, 64, 45
+    p = synth.gridtd_decoder_state(41, V, H, E, C=64, n_pixel=16)
+    f = torch.randn(64, 4, 4, generator=torch.Generator().manual_seed(42)).clamp(min=0)
+    tk = synth.tokens(43, T, V)
+    st = O.gridtd_explainer_forward(p, f, tk, gradient=True)
+    ks = helpers.gridtd_grad_kernel_state([st], DEV)
+    W = helpers.to_dev(gridtd_grad_weights(p), DEV)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    ts = [T - 1, 7]
+    for tc_gemm in (False, True):
+        d_feat, r_words = ops.gridtd_decoder_grad(ks, W, i32([0, 0]), i32(ts), i32([tk[t + 1] for t in ts]), tc_gemm=tc_gemm)
+        for q, t in enumerate(ts):
+            df, rw = O.gridtd_gradient_wordt(p, st, t)
+            scale = df.abs().max()
+            assert_close(d_feat[q] / scale, df / scale, rtol=1e-3, atol=1e-4 if tc_gemm else 1e-5, what=f"d_feat t={t}")
+            assert_close(r_words[q, :t + 1], rw, rtol=1e-3, atol=1e-4 if tc_gemm else 1e-5, what=f"r_words t={t}")
