@@ -72,6 +72,7 @@ def main(dst):
                 f"({tot['UTMALDG.MULTICAST']} multicast), UTMASTG {tot['UTMASTG']}, UTCBAR {tot['UTCBAR']}, HMMA {tot['HMMA']} "
                 f"over {len(counts)} kernels.\n\nEpilogue codes of `tc_conv_kernel<E>` / `tc_conv_slab_kernel<E>` (include/lrpx.h): "
                 "1 FWD_GAIN, 2 MUL, 3 MUL_UNPOOL, 4 INPUT, 5 STORE_F32, 6 FEAT, 7 FEAT_DIV, 8 INPUT3, 9 MULX, 10 MULX_UNPOOL, 11 FWDX; "
+                "internal instantiations: 12 FWDX of a VGG-style layer, 13 / 14 MULX / MULX_UNPOOL with one gain group, 15 MUL with folded filter columns; "
                 "`<E, true>` = the pair-mode instantiation (tcgen05 cta_group::2).\n")
         # whole-library mnemonic census with the modifiers kept: .2CTA = cta_group::2 (pair mode), .MULTICAST = cluster multicast
         census = collections.Counter(re.findall(r"\b(UTCHMMA[.\w]*|UTMALDG[.\w]*|UTCBAR[.\w]*|UTCATOMSWS[.\w]*)", sass))
