@@ -335,6 +335,35 @@ typedef struct {
 size_t lrpx_aoa_decoder_grad_workspace_bytes(const lrpx_aoa_grad_args* args);
 int lrpx_aoa_decoder_grad_f32(const lrpx_aoa_grad_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ExplainAdaptiveGradient.explain_caption_wordt (adaptiveattention.py:965-1021; the guided variant :1100-1163 differs
+ * only by masks that never fire): the attention / sentinel split is applied at the explained step only, the loop walks
+ * the single AdaLSTM. */
+typedef struct {
+  int B, T, H, E, P, C, V, Q;
+  int flags, reserved_;    /* LRPX_DEC_TC_GEMM */
+  const float* c;         /* (B,T+1,H)                                              adaptiveattention.py:952 */
+  const float* g;         /* (B,T,H) pre-tanh cell candidate                                    :955,:959 */
+  const float* i;         /* (B,T,H) gate activations                                           :957-960  */
+  const float* f;
+  const float* o;
+  const float* sg;        /* (B,T,H) sigmoid(x_gate(x) + h_gate(h)), the sentinel gate          :941,:946 */
+  const float* alpha;     /* (B,T,P) */
+  const float* beta;      /* (B,T)   */
+  const float* W_g;       /* (4H, 2E+H) AdaLSTM [weight_ih | weight_hh]: columns [emb | glob | h]  :1007-1008 */
+  const float* W_fc;      /* (V,H) */
+  const float* W_glob;    /* (E,C)                                                              :1011 */
+  const float* W_proj;    /* (H,C)                                                              :1015 */
+  const int32_t* req_img;
+  const int32_t* req_t;
+  const int32_t* req_word;
+  float* d_feat;          /* (Q,P,C) */
+  float* r_words;         /* (Q,T) */
+  float* r_words_raw;
+} lrpx_adaptive_grad_args;
+
+size_t lrpx_adaptive_decoder_grad_workspace_bytes(const lrpx_adaptive_grad_args* args);
+int lrpx_adaptive_decoder_grad_f32(const lrpx_adaptive_grad_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Grad-CAM (gridTDmodel.py:1760-1771, aoamodel.py:1676-1689), one map per request:
  *   weights[c] = mean_p grads[q][p][c];  cam[p] = relu(sum_c feat[img(q)][p][c] * weights[c]);  out[q][p] = cam[p] / (max cam + 1e-6)
  * feat (B,P,C) and grads (Q,P,C) pixel-major; req_img (Q) or NULL = identity; out (Q,P). */

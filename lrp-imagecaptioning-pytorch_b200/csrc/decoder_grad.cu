@@ -366,6 +366,103 @@ static size_t agrad_carve(const lrpx_aoa_grad_args* a, float* base, AGradWs* w) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Adaptive attention (single AdaLSTM): ExplainAdaptiveGradient.explain_caption_wordt, adaptiveattention.py:965-1021.
+// The reference applies the attention / sentinel split ONLY at the explained step t (:987-994, outside its loop); the
+// loop then walks the LSTM alone.  d_img_feature_proj = d_context (x) alpha_t is rank one, so the projector needs one
+// (Q x H) @ (H x C) GEMM and an outer-product kernel instead of a GEMM over all Q * P rows.
+// ------------------------------------------------------------------------------------------------
+struct DGradWs {
+  float *d_h, *d_c, *d_glob, *dctx, *u, *v, *y;
+  __nv_bfloat16 *a3, *w3_g, *w3_glob, *w3_proj;
+};
+
+__global__ void dgrad_init_kernel(lrpx_adaptive_grad_args a, DGradWs w) {
+  const int q = blockIdx.x, H = a.H;
+  const int b = a.req_img[q], t = a.req_t[q];
+  const float* wr = a.W_fc + (size_t)a.req_word[q] * H;
+  const float beta = a.beta[(size_t)b * a.T + t];
+  const size_t bt = ((size_t)b * a.T + t) * H, bt1 = ((size_t)b * (a.T + 1) + t + 1) * H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const size_t o = (size_t)q * H + j;
+    const float d0 = wr[j];                                                    // :987
+    const float tc = tanhf(a.c[bt1 + j]);
+    w.dctx[o] = d0 * (1.f - beta);                                             // :989
+    w.d_c[o] = d0 * beta * a.sg[bt + j] * (1.f - tc * tc);                     // :990-991
+    w.d_h[o] = d0;                                                             // :992
+  }
+  for (int j = threadIdx.x; j < a.E; j += blockDim.x) w.d_glob[(size_t)q * a.E + j] = 0.f;
+  for (int j = threadIdx.x; j < a.T; j += blockDim.x) {
+    a.r_words[(size_t)q * a.T + j] = 0.f;
+    if (a.r_words_raw) a.r_words_raw[(size_t)q * a.T + j] = 0.f;
+  }
+}
+__global__ void dgrad_cell_kernel(lrpx_adaptive_grad_args a, DGradWs w, int i) {
+  const int q = blockIdx.x, H = a.H;
+  const int b = a.req_img[q], t = a.req_t[q];
+  const size_t bi = ((size_t)b * a.T + i) * H, bi1 = ((size_t)b * (a.T + 1) + i + 1) * H, bi0 = bi1 - H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    if (i > t) { zero_gates(w.u, nullptr, q, H, j); continue; }
+    const size_t o = (size_t)q * H + j;
+    const CellGrad g = cell_backward(w.d_h[o], w.d_c[o], a.c[bi1 + j], a.c[bi0 + j], a.g[bi + j], a.i[bi + j],
+                                     a.f[bi + j], a.o[bi + j]);
+    w.d_c[o] = g.dc_prev;
+    put_gates(w.u, nullptr, q, H, j, g);
+  }
+}
+// after v = u @ [W_ih | W_hh]: slices [emb | glob | h] (:1007-1010)
+__global__ void dgrad_post_kernel(lrpx_adaptive_grad_args a, DGradWs w, int i) {
+  const int q = blockIdx.x, H = a.H, E = a.E;
+  if (i > a.req_t[q]) return;
+  const float* vq = w.v + (size_t)q * (2 * E + H);
+  float wsum = 0.f;
+  for (int k = threadIdx.x; k < 2 * E + H; k += blockDim.x) {
+    const float d = vq[k];
+    if (k < E) wsum += d;
+    else if (k < 2 * E) w.d_glob[(size_t)q * E + (k - E)] += d;
+    else w.d_h[(size_t)q * H + (k - 2 * E)] = d;
+  }
+  block_sum_store(wsum, [&](float s) {
+    a.r_words[(size_t)q * a.T + i] = s;
+    if (a.r_words_raw) a.r_words_raw[(size_t)q * a.T + i] = s;
+  });
+}
+// d_feat[q][p][c] = (d_glob @ W_glob)[c] / P + alpha_t[p] * (d_context @ W_proj)[c]     (:1011-1015)
+__global__ void dgrad_out_kernel(lrpx_adaptive_grad_args a, const float* __restrict__ avg /* (Q,C) */,
+                                 const float* __restrict__ y /* (Q,C) */) {
+  const int q = blockIdx.y, p = blockIdx.x;
+  const int b = a.req_img[q], t = a.req_t[q];
+  const float al = a.alpha[((size_t)b * a.T + t) * a.P + p];
+  float* dst = a.d_feat + ((size_t)q * a.P + p) * a.C;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x)
+    dst[c] = 1.0f * avg[(size_t)q * a.C + c] / (float)a.P + al * y[(size_t)q * a.C + c];
+}
+
+static size_t dgrad_carve(const lrpx_adaptive_grad_args* a, float* base, DGradWs* w) {
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    float* p = base ? base + off : nullptr;
+    off += align_up(n);
+    return p;
+  };
+  const size_t Q = a->Q, H = a->H, E = a->E, C = a->C;
+  size_t nmax = 2 * E + H > C ? 2 * E + H : C;
+  DGradWs t{};
+  t.d_h = take(Q * H); t.d_c = take(Q * H); t.d_glob = take(Q * E); t.dctx = take(Q * H);
+  t.u = take(Q * 4 * H);
+  t.v = take(Q * nmax);
+  t.y = take(Q * C);
+  if (a->flags & LRPX_DEC_TC_GEMM) {
+    auto take16 = [&](size_t n) { return reinterpret_cast<__nv_bfloat16*>(take((n + 1) / 2)); };
+    t.a3 = take16(Q * 2 * 4 * H);
+    t.w3_g = take16((2 * E + H) * 3 * 4 * H);
+    t.w3_glob = take16(C * 3 * E);
+    t.w3_proj = take16(C * 3 * H);
+  }
+  if (w) *w = t;
+  return off * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Grad-CAM (gridTDmodel.py:1760-1771): weights[c] = mean_p grads[q][p][c];  cam[p] = relu(sum_c feat[b][p][c] weights[c]);
 // out[q][p] = cam[p] / (max|cam| + 1e-6).  One block per request.
 // ------------------------------------------------------------------------------------------------
@@ -549,6 +646,44 @@ int lrpx_aoa_decoder_grad_f32(const lrpx_aoa_grad_args* a, void* workspace, size
   // d_img_feature_proj = d_value @ W_v + d_glob / P   (:1490-1492), then the projector (:1493)
   gemm_epilogue_kernel<GE_ADD><<<ew_grid((long long)Q * P * H), 256, 0, st>>>(w.dproj, (long long)Q * P, H, ge);
   RUN(gemm_any<GE_STORE>(w.dproj, a->W_proj, w3_proj, w.a3, a->d_feat, Q * P, C, H, none, st));
+  words_norm_kernel<<<Q, 32, 0, st>>>(a->r_words, a->req_t, T);
+  LRPX_CHECK_LAUNCH();
+  return LRPX_OK;
+}
+
+size_t lrpx_adaptive_decoder_grad_workspace_bytes(const lrpx_adaptive_grad_args* a) {
+  if (!a) return 0;
+  return dgrad_carve(a, nullptr, nullptr);
+}
+
+int lrpx_adaptive_decoder_grad_f32(const lrpx_adaptive_grad_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  LRPX_CHECK_ARG(a, "null args");
+  LRPX_CHECK_ARG(a->B > 0 && a->T > 0 && a->H > 0 && a->E > 0 && a->P > 0 && a->C > 0 && a->V > 0 && a->Q >= 0,
+                 "bad dimensions");
+  if (a->Q == 0) return LRPX_OK;
+  LRPX_CHECK_ARG(a->c && a->g && a->i && a->f && a->o && a->sg && a->alpha && a->beta && a->W_g && a->W_fc && a->W_glob &&
+                     a->W_proj && a->req_img && a->req_t && a->req_word && a->d_feat && a->r_words,
+                 "null pointer in args");
+  DGradWs w;
+  const size_t need = dgrad_carve(a, (float*)workspace, &w);
+  LRPX_CHECK_ARG(workspace && workspace_bytes >= need, "workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int Q = a->Q, H = a->H, E = a->E, T = a->T, C = a->C;
+  const int nt = H >= 256 ? 256 : 128;
+  GemmEpi none{};
+  const bool tc = (a->flags & LRPX_DEC_TC_GEMM) != 0;
+  const __nv_bfloat16* w3_g = (tc && tc_shape_ok(2 * E + H, 4 * H)) ? prep_weight3(a->W_g, w.w3_g, 4 * H, 2 * E + H, st) : nullptr;
+  const __nv_bfloat16* w3_glob = (tc && tc_shape_ok(C, E)) ? prep_weight3(a->W_glob, w.w3_glob, E, C, st) : nullptr;
+  const __nv_bfloat16* w3_proj = (tc && tc_shape_ok(C, H)) ? prep_weight3(a->W_proj, w.w3_proj, H, C, st) : nullptr;
+  dgrad_init_kernel<<<Q, nt, 0, st>>>(*a, w);
+  for (int i = T - 1; i >= 0; --i) {
+    dgrad_cell_kernel<<<Q, nt, 0, st>>>(*a, w, i);
+    RUN(gemm_any<GE_STORE>(w.u, a->W_g, w3_g, w.a3, w.v, Q, 2 * E + H, 4 * H, none, st));
+    dgrad_post_kernel<<<Q, 256, 0, st>>>(*a, w, i);
+  }
+  RUN(gemm_any<GE_STORE>(w.d_glob, a->W_glob, w3_glob, w.a3, w.v, Q, C, E, none, st));      // d_average_img_feature
+  RUN(gemm_any<GE_STORE>(w.dctx, a->W_proj, w3_proj, w.a3, w.y, Q, C, H, none, st));        // d_context @ W_proj
+  dgrad_out_kernel<<<dim3(a->P, Q), 256, 0, st>>>(*a, w.v, w.y);
   words_norm_kernel<<<Q, 32, 0, st>>>(a->r_words, a->req_t, T);
   LRPX_CHECK_LAUNCH();
   return LRPX_OK;

@@ -59,6 +59,15 @@ class AoaGradArgs(C.Structure):
                [(n, _P) for n in _AOA_GRAD_PTRS]
 
 
+_ADA_GRAD_PTRS = ["c", "g", "i", "f", "o", "sg", "alpha", "beta", "W_g", "W_fc", "W_glob", "W_proj", "req_img", "req_t",
+                  "req_word", "d_feat", "r_words", "r_words_raw"]
+
+
+class AdaptiveGradArgs(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("B", "T", "H", "E", "P", "C", "V", "Q", "flags", "reserved_")] + \
+               [(n, _P) for n in _ADA_GRAD_PTRS]
+
+
 _ADA_PTRS = ["feat", "avg", "z_proj", "A", "z_glob", "x", "h", "c", "g", "i", "f", "st", "ctx", "ctx_hat", "alpha", "beta",
              "pred", "W_g", "W_fc", "W_glob", "W_proj", "req_img", "req_t", "req_word", "r_feat", "r_words",
              "r_words_raw"]
@@ -157,6 +166,8 @@ SYMBOLS = {
     "lrpx_gridtd_decoder_grad_f32": (_i, [C.POINTER(GridTDGradArgs), _P, _sz, _P]),
     "lrpx_aoa_decoder_grad_workspace_bytes": (_sz, [C.POINTER(AoaGradArgs)]),
     "lrpx_aoa_decoder_grad_f32": (_i, [C.POINTER(AoaGradArgs), _P, _sz, _P]),
+    "lrpx_adaptive_decoder_grad_workspace_bytes": (_sz, [C.POINTER(AdaptiveGradArgs)]),
+    "lrpx_adaptive_decoder_grad_f32": (_i, [C.POINTER(AdaptiveGradArgs), _P, _sz, _P]),
     "lrpx_grad_cam_f32": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
     "lrpx_cam_expand_mul_f32": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _P]),
     "lrpx_aoa_decoder_workspace_bytes": (_sz, [C.POINTER(AoaArgs)]),

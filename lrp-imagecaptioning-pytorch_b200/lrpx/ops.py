@@ -499,6 +499,34 @@ def aoa_decoder_grad(state: dict, weights: dict, num_head, req_img, req_t, req_w
     return (d_feat, r_words, r_raw) if want_raw else (d_feat, r_words)
 
 
+def adaptive_decoder_grad(state: dict, weights: dict, req_img, req_t, req_word, want_raw=False, tc_gemm=False):
+    """ExplainAdaptiveGradient.explain_caption_wordt (adaptiveattention.py:965-1021) batched over requests.  state: the
+    explainer forward's tensors incl. the output gate ``o`` and the sentinel gate ``sg``; weights: W_g (4H, 2E+H), W_fc,
+    W_glob, W_proj."""
+    dev = state["feat"].device
+    B, P, Cc = state["feat"].shape
+    T, H = state["g"].shape[1], state["g"].shape[2]
+    E = weights["W_glob"].shape[0]
+    V = weights["W_fc"].shape[0]
+    Q = int(req_img.numel())
+    _check_requests(B, T, V, req_img, req_t, req_word)
+    keep = []
+    a = _lib.AdaptiveGradArgs(B=B, T=T, H=H, E=E, P=P, C=Cc, V=V, Q=Q, flags=DEC_TC_GEMM if tc_gemm else 0)
+    f = {k: _f32(state[k], k) for k in ["c", "g", "i", "f", "o", "sg", "alpha", "beta"]}
+    f.update({k: _f32(weights[k], k) for k in ["W_g", "W_fc", "W_glob", "W_proj"]})
+    for k, v in (("req_img", req_img), ("req_t", req_t), ("req_word", req_word)):
+        f[k] = v.to(device=dev, dtype=torch.int32).contiguous()
+    d_feat = torch.empty(Q, P, Cc, device=dev, dtype=torch.float32)
+    r_words = torch.zeros(Q, T, device=dev, dtype=torch.float32)
+    r_raw = torch.zeros(Q, T, device=dev, dtype=torch.float32) if want_raw else None
+    f.update(d_feat=d_feat, r_words=r_words, r_words_raw=r_raw)
+    _fill_args(a, f, keep)
+    nbytes = lib().lrpx_adaptive_decoder_grad_workspace_bytes(C.byref(a))
+    ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
+    check(lib().lrpx_adaptive_decoder_grad_f32(C.byref(a), _ptr(ws), nbytes, _stream()), "lrpx_adaptive_decoder_grad_f32")
+    return (d_feat, r_words, r_raw) if want_raw else (d_feat, r_words)
+
+
 def grad_cam(feat, grads, req_img=None):
     """grad_cam (gridTDmodel.py:1760-1771) for Q requests: feat (B,P,C) encoder output, grads (Q,P,C) its gradient,
     both pixel-major; req_img (Q,) int32 or None (identity).  Returns (Q,P) maps in [0, 1]."""

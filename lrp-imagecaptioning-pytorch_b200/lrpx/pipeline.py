@@ -68,6 +68,8 @@ class BatchExplainer:
         if self.is_gradient and self.is_aoa:
             r_feat, r_words = ops.aoa_decoder_grad(st, self.W, self.ex.num_head, req_img, req_t, req_word,
                                                    torch.full_like(req_t, self.head_idx), tc_gemm=self.tc_gemm)
+        elif self.is_gradient and self.is_adaptive:
+            r_feat, r_words = ops.adaptive_decoder_grad(st, self.W, req_img, req_t, req_word, tc_gemm=self.tc_gemm)
         elif self.is_gradient:
             r_feat, r_words = ops.gridtd_decoder_grad(st, self.W, req_img, req_t, req_word,
                                                       guided=self.ex.GUIDED_DECODER, tc_gemm=self.tc_gemm)

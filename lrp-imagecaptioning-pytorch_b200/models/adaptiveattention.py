@@ -214,8 +214,11 @@ class ExplainAdaptiveAttention(ExplainGridTDAttention):
             self._expl_w_key = key
         return self._expl_w
 
-    def explainer_forward(self, feat, tokens):
-        """The explainer's teacher-forced forward (reference :631-677) batched over images.  feat: (B,P,C) pixel-major
+    def explainer_forward(self, feat, tokens, quirk_double_bias_ih=None, want_gates=False):
+        """(``quirk_double_bias_ih`` is accepted for the shared gradient-family plumbing and has no effect: this model's
+        explainers add both LSTM biases, reference :554-565, :883.  ``want_gates`` also saves the output gate and the
+        sentinel gate, the state of the gradient explainers, reference :941-960.)
+        The explainer's teacher-forced forward (reference :631-677) batched over images.  feat: (B,P,C) pixel-major
         encoder output; tokens: (B,L) long, column 0 = <start>.  Returns the saved state in the layout of
         lrpx_adaptive_args, T = L-1 steps.  Per step: ``lrpx_lstm_step_f32`` (4 gates + sentinel gate from h_t, the
         input-side halves precomputed for all steps), one library GEMM for both attention projections,
@@ -255,6 +258,7 @@ class ExplainAdaptiveAttention(ExplainGridTDAttention):
             h, c = torch.zeros(B, T + 1, H, device=dev), torch.zeros(B, T + 1, H, device=dev)
             g, i, f, st, ctx, ctx_hat = (new(B, T, H) for _ in range(6))
             alpha, beta = new(B, T, P), new(B, T)
+            og, sg = (new(B, T, H), new(B, T, H)) if want_gates else (None, None)
             # the step kernel reads every column of its input rows in every CTA while its CTAs write the new state:
             # the recurrent input is ping-ponged between two copies
             hin = torch.zeros(2, B, H, device=dev)
@@ -262,13 +266,17 @@ class ExplainAdaptiveAttention(ExplainGridTDAttention):
             for t in range(T):
                 p, q = t & 1, (t & 1) ^ 1
                 ops.lstm_step(hin[p], Wrec_p, pre[t], 5, c[:, t], h[:, t + 1], c[:, t + 1], g[:, t], i[:, t], f[:, t],
-                              s=st[:, t], h_copy0=hin[q], h_copy2=hs[:, :H], s_copy=hs[:, H:])
+                              s=st[:, t], h_copy0=hin[q], h_copy2=hs[:, :H], s_copy=hs[:, H:],
+                              o=None if og is None else og[:, t], sg=None if sg is None else sg[:, t])
                 hsp = att_lin(hs)                                                                 # (B,2K)
                 ops.adaptive_attention(A, img_proj, hsp, w_h, st[:, t], ctx[:, t], ctx_hat[:, t], alpha[:, t],
                                        beta[:, t])
             pred = self._lx("fc", m.fc.weight, m.fc.bias)((ctx_hat + h[:, 1:]).view(B * T, H)).view(B, T, -1)
-        return dict(x=x, h=h, c=c, g=g, i=i, f=f, st=st, ctx=ctx, ctx_hat=ctx_hat, alpha=alpha, beta=beta, pred=pred,
-                    feat=feat, avg=avg, z_proj=z_proj.contiguous(), A=A, z_glob=z_glob)
+        out = dict(x=x, h=h, c=c, g=g, i=i, f=f, st=st, ctx=ctx, ctx_hat=ctx_hat, alpha=alpha, beta=beta, pred=pred,
+                   feat=feat, avg=avg, z_proj=z_proj.contiguous(), A=A, z_glob=z_glob)
+        if want_gates:
+            out.update(o=og, sg=sg)
+        return out
 
     def teacherforce_forward(self, img, beam_caption_encode):
         feat, _, _ = self.encode_images(img)
@@ -318,3 +326,81 @@ class ExplainAdaptiveAttention(ExplainGridTDAttention):
         req_img = torch.zeros(len(ts), dtype=torch.int32, device=dev)
         return ops.adaptive_decoder_lrp(self._state, self._lrp_weights(), req_img, req_t, req_word,
                                         tc_gemm=(self.precision in ('bf16', 'mixed')))
+
+
+# ================================================================================================ gradient family (f4)
+from models._gradient import GradientFamily      # noqa: E402
+
+
+def adaptive_grad_weights(sd):
+    """B operands of lrpx_adaptive_grad_args from an AdaptiveAttentionCaptioningModel state_dict."""
+    H = sd["fc.weight"].shape[1]
+    return {
+        "W_g": torch.cat((sd["AdaLSTM.lstm_cell.weight_ih"], sd["AdaLSTM.lstm_cell.weight_hh"]), 1).contiguous(),   # (4H, 2E+H)
+        "W_fc": sd["fc.weight"].contiguous(),
+        "W_glob": sd["global_img_feature_proj.weight"].contiguous(),
+        "W_proj": sd["img_projector.weight"].reshape(H, -1).contiguous(),
+    }
+
+
+class ExplainAdaptiveGradient(GradientFamily, ExplainAdaptiveAttention):
+    """reference :851-1095: gradient of the word's logit through the single-LSTM adaptive-attention decoder (attention and
+    sentinel split applied at the explained step only, :987-994) and the image encoder."""
+    EX_TYPE = 'gradient'
+
+    def __init__(self, args, word_map, model=None, precision=None):
+        ExplainAdaptiveAttention.__init__(self, args, word_map, model=model, precision=precision)
+        self._check_encoder()
+
+    def _grad_weights(self):
+        if getattr(self, "_gw", None) is None:
+            self._gw = adaptive_grad_weights({k: v.detach() for k, v in self.model.state_dict().items()})
+        return self._gw
+
+    def _set_state(self, img, tokens, enc=None):
+        ExplainAdaptiveAttention._set_state(self, img, tokens, enc)
+        if self._state is not None:
+            self.ot_act, self.sen_gate = self._state["o"][0], self._state["sg"][0]
+
+    def _decoder_grad(self, ts):
+        toks = self.beam_caption_encode
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=self.device)
+        return ops.adaptive_decoder_grad(self._state, self._grad_weights(), i32([0] * len(ts)), i32(list(ts)),
+                                         i32([toks[t + 1] for t in ts]), tc_gemm=(self.precision in ('bf16', 'mixed')))
+
+    def explain_caption_wordt(self, t):
+        """reference :965-1021 (guided: :1100-1163, same values) -> (d_img_feature (1,C,h,w), r_words (t+1,))."""
+        assert t < self.caption_length
+        d_feat, r_words = self._decoder_grad([t])
+        fh, fw = self._feat_hw
+        return d_feat[0].t().reshape(1, -1, fh, fw), r_words[0, :t + 1]
+
+    def explain_caption(self, img_filepath, t_list=None):
+        """reference :1038-1052."""
+        self.img_filepath = img_filepath
+        self.get_hidden_parameters(img_filepath)
+        if self.caption_length == 0:
+            return [], []
+        d_feat, r_words = self._decoder_grad(list(range(self.caption_length)))
+        relevance_imgs, relevance_preceeding_words = self._explain_all(d_feat, r_words)
+        self.save_linguistic_explanation(relevance_preceeding_words)
+        return relevance_imgs, relevance_preceeding_words
+
+
+class ExplainiAdaptiveGuidedGradient(ExplainAdaptiveGradient):
+    """reference :1098-1216 (the class name's typo is the reference's): the decoder half equals the plain gradient's (its
+    masks compare ReLU outputs with `< 0`), the encoder half is guided backpropagation."""
+    EX_TYPE = 'GuidedBackpropagate'
+    RULE = "guided"
+
+
+class ExplainAdaptiveGradCam(ExplainAdaptiveGradient):
+    """reference :1218-1259."""
+    EX_TYPE = 'GradCam'
+    CAM = "cam"
+
+
+class ExplainAdaptiveGuidedGradCam(ExplainiAdaptiveGuidedGradient):
+    """reference :1261-1325."""
+    EX_TYPE = 'GuidedGradCam'
+    CAM = "guided"

@@ -515,6 +515,37 @@ def golden_gradient(ns):
     print("gradient_e2e tokens:", toks)
 
 
+def golden_gradient_adaptive(ns):
+    """ExplainAdaptiveGradient / ExplainiAdaptiveGuidedGradient (adaptiveattention.py:851-1216) run by the reference over
+    fixed features (stub encoder): saved gates, d_img_feature and r_words."""
+    V, H, T, seed, ts = 1000, 512, 10, 241, [0, 6, 9]
+    wm = synth.word_map(V)
+    args = argparse.Namespace(embed_dim=H, hidden_dim=H, num_head=8, encoder="vgg16", height=224, width=224,
+                              save_path="/tmp/lrpx_ref", dataset="syn", weight="")
+    with quiet():
+        model = ns.adaptiveattention.AdaptiveAttentionCaptioningModel(H, H, V, "vgg16")
+    model.load_state_dict(synth.adaptive_decoder_state(seed, V, H, H), strict=False)
+    feats = _features(seed + 1, 512, 14, 14)
+    toks = synth.tokens(seed + 2, T, V)
+    out = dict(V=V, H=H, T=T, seed=seed, tokens=np.array(toks), ts=np.array(ts), feats=feats)
+    for cls, key in (("ExplainAdaptiveGradient", "grad"), ("ExplainiAdaptiveGuidedGradient", "guided")):
+        ex = _ref_gradient_explainer(ns.adaptiveattention, cls, model, args, wm, "adaptive_grad")
+        ex.model.img_encoder = _StubEncoder(feats)
+        ex.model.beam_search = lambda *a, **k: ([" ".join(f"w{t}" for t in toks[1:])], toks[1:])
+        ex.preprocess_img = lambda p: torch.zeros(1, 3, 224, 224)
+        with torch.no_grad(), quiet():
+            ex.get_hidden_parameters("x")
+            ex.image_feature_proj = ex.image_feature_proj.transpose(1, 2)
+        if key == "grad":
+            out.update(predictions=ex.predictions, ot=ex.ot_act, sen_gate=ex.sen_gate, betas=ex.betas)
+        for t in (ts if key == "grad" else ts[-1:]):         # the guided decoder half has the same values: one word suffices
+            with torch.no_grad():
+                df, rw = ex.explain_caption_wordt(t)
+            out[f"{key}_d_feat_{t}"] = df
+            out[f"{key}_r_words_{t}"] = rw
+    save("adaptive_grad_512", **out)
+
+
 def golden_scst(ns):
     """get_self_critical_reward (models/modelutils.py:200-238) run by the reference with its vendored CIDEr / BLEU
     scorers on seeded sampled / greedy / ground-truth captions: CIDEr-only (the training setting, train.py:193), BLEU-only
@@ -654,7 +685,7 @@ def main():
     only = set(sys.argv[1:])          # optional: names of the generators to (re)run
     for fn in (golden_rules, golden_sequential_small, golden_vgg16, golden_resnet, golden_gridtd_decoder,
                golden_aoa_decoder, golden_adaptive_decoder, golden_block_image, golden_lrp_weights, golden_tune, golden_tune_bu,
-               golden_ablation, golden_gradient, golden_scst):
+               golden_ablation, golden_gradient, golden_gradient_adaptive, golden_scst):
         if only and fn.__name__ not in only:
             continue
         print(fn.__name__)

@@ -53,6 +53,7 @@ def test_struct_layout_matches_header(tmp_path):
              ("lrpx_block_image_args", _lib.BlockImageArgs), ("lrpx_bbox_args", _lib.BboxArgs),
              ("lrpx_lstm_cell_args", _lib.LstmCellArgs), ("lrpx_lstm_step_args", _lib.LstmStepArgs),
              ("lrpx_gridtd_grad_args", _lib.GridTDGradArgs), ("lrpx_aoa_grad_args", _lib.AoaGradArgs),
+             ("lrpx_adaptive_grad_args", _lib.AdaptiveGradArgs),
              ("lrpx_ada_attention_args", _lib.AdaAttentionArgs)]
     gcc = shutil.which("gcc")
     if gcc is None:

@@ -454,3 +454,67 @@ def test_decoder_grad_long_caption_wide_state_vs_oracle():
             scale = df.abs().max()
             assert_close(d_feat[q] / scale, df / scale, rtol=1e-3, atol=1e-4 if tc_gemm else 1e-5, what=f"d_feat t={t}")
             assert_close(r_words[q, :t + 1], rw, rtol=1e-3, atol=1e-4 if tc_gemm else 1e-5, what=f"r_words t={t}")
+
+
+@pytest.mark.parametrize("tc_gemm", [False, True])
+def test_adaptive_decoder_grad_vs_reference_fixture(golden, tmp_path, tc_gemm):
+    """ExplainAdaptiveGradient (single-LSTM adaptive attention): explainer forward incl. the extra gates and
+    lrpx_adaptive_decoder_grad_f32 vs the reference's own outputs (fixture adaptive_grad_512)."""
+    from lrpx import ops
+    from models import adaptiveattention as AA
+    g = golden("adaptive_grad_512")
+    V, H = int(g["V"]), int(g["H"])
+    model = AA.AdaptiveAttentionCaptioningModel(H, H, V, "vgg16")
+    model.load_state_dict(synth.adaptive_decoder_state(int(g["seed"]), V, H, H), strict=False)
+    model.to(DEV).eval()
+    ex = AA.ExplainAdaptiveGradient(_args(H, H, tmp_path), synth.word_map(V), model=model, precision="simt")
+    toks = g["tokens"].tolist()
+    feat = _pix(g["feats"]).unsqueeze(0).to(DEV).contiguous()
+    st = ex.explainer_forward(feat, torch.tensor([toks], device=DEV))
+    assert_close(st["pred"][0], g["predictions"], rtol=1e-4, atol=2e-5, what="predictions")
+    assert_close(st["o"][0], g["ot"], rtol=1e-4, atol=2e-6, what="output gate")
+    assert_close(st["sg"][0], g["sen_gate"], rtol=1e-4, atol=2e-6, what="sentinel gate")
+    ts = g["ts"].tolist()
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    d_feat, r_words = ops.adaptive_decoder_grad(st, ex._grad_weights(), i32([0] * len(ts)), i32(ts),
+                                                i32([toks[t + 1] for t in ts]), tc_gemm=tc_gemm)
+    atol = 1e-4 if tc_gemm else 1e-5
+    for q, t in enumerate(ts):
+        ref = _pix(g[f"grad_d_feat_{t}"])
+        scale = ref.abs().max()
+        print(f"adaptive tc_gemm={tc_gemm} t={t}: max scale-relative error {float((d_feat[q].cpu() - ref).abs().max() / scale):.3e}")
+        assert_close(d_feat[q] / scale, ref / scale, rtol=1e-3, atol=atol, what=f"d_feat t={t}")
+        assert_close(r_words[q, :t + 1], g[f"grad_r_words_{t}"], rtol=1e-3, atol=atol, what=f"r_words t={t}")
+        assert float(r_words[q, t + 1:].abs().sum()) == 0.0
+    t = ts[-1]
+    assert_close(d_feat[-1] / scale, _pix(g[f"guided_d_feat_{t}"]) / scale, rtol=1e-3, atol=atol, what="guided = plain decoder half")
+
+
+def test_adaptive_gradient_explainers_end_to_end_vs_oracle(tmp_path):
+    """ExplainiAdaptiveGuidedGradient.explain_caption through a seeded VGG-style encoder at 64x64 (fp32 CUDA-core path) vs
+    the oracle's decoder gradient + guided backward on the caption the mirror found."""
+    from models import adaptiveattention as AA
+    V, H = 80, 64
+    model = AA.AdaptiveAttentionCaptioningModel(H, H, V, "vgg16", n_pixel=16)
+    dec = synth.adaptive_decoder_state(341, V, H, H, 512, n_pixel=16)
+    model.load_state_dict(dec, strict=False)
+    vs = synth.vgg_state(342)
+    model.img_encoder.encoder.load_state_dict(vs)
+    model.to(DEV).eval()
+    ex = AA.ExplainiAdaptiveGuidedGradient(_args(H, H, tmp_path), synth.word_map(V), model=model, precision="simt")
+    img = synth.images(343, 1, 64)
+    ex.preprocess_img = lambda p: img.to(DEV)
+    find = ex._find_caption
+    ex._find_caption = lambda path, beam_size, max_cap_length: find(path, beam_size, 5)
+    imgs, words = ex.explain_caption("synthetic.jpg")
+    toks = ex.beam_caption_encode
+    T = len(toks) - 1
+    assert T >= 1 and len(imgs) == T
+    layers = O.vgg_layers_from_state(vs)
+    feat = O.sequential_forward(layers, img)[-1]
+    st = O.adaptive_explainer_forward(dec, feat[0], toks)
+    for t in range(T):
+        df, rw = O.adaptive_gradient_wordt(dec, st, t)
+        want = O.sequential_gradient(layers, img, df.t().reshape(1, -1, *feat.shape[-2:]), guided=True)
+        assert _rel_l2(imgs[t], want) < 5e-3, (t, _rel_l2(imgs[t], want))
+        assert_close(words[t], rw, rtol=1e-3, atol=1e-5, what=f"r_words t={t}")
