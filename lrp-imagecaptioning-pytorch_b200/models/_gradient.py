@@ -134,6 +134,12 @@ class GradientFamily:
     def _cam(self, d_pix, rows):
         return ops.grad_cam(self._state["feat"], d_pix, rows)
 
+    def grad_cam(self, img_feature, grads):
+        """reference gridTDmodel.py:1760-1771 / :1799-1810 on (1, C, h, w) tensors: the (h*w,) map of the Grad-CAM
+        classes, the (h, w) map of the guided Grad-CAM ones (``lrpx_grad_cam_f32``)."""
+        cam = ops.grad_cam(self._pix(img_feature), self._pix(grads))[0]
+        return cam.view(img_feature.shape[2], img_feature.shape[3]) if self.CAM == "guided" else cam
+
     def _expand_ops(self):
         fh, fw = self._feat_hw
         key = (fh, fw, self.img.shape[2], self.img.shape[3])

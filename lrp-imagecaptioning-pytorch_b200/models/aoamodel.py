@@ -121,6 +121,30 @@ class AOAModel(nn.Module):
                                             self.decoder_v_proj(image_feature_proj))
         return self.fc(self.dropout(context_aoa + ht)), alpha_t, None, (ht, ct)
 
+    def greedy_search(self, imgs, word_map, max_cap_length=20):
+        """reference :487-530 -> (sentences with the bad endings removed, token lists incl. <start>).  (The reference
+        returns the filtered word list of the LAST image as its second value; the token lists of all rows are returned
+        here, like its gridTD sibling.)"""
+        self.eval()
+        rev_word_map = {v: k for k, v in word_map.items()}
+        with torch.no_grad():
+            k_prev_words = torch.zeros(imgs.size(0), max_cap_length, dtype=torch.long, device=imgs.device)
+            k_prev_words[:, 0] = word_map['<start>']
+            _, proj, glob = self._encode(imgs)
+            state = self.init_hidden_state(proj)
+            unfinished = None
+            for step in range(max_cap_length - 1):
+                xt = torch.cat((self.embedding(k_prev_words[:, step]), glob), dim=-1)
+                predict_score_t, _, _, state = self.predict_next_word(proj, xt, state)
+                top_words = torch.log_softmax(predict_score_t, dim=-1).topk(1, -1, True, True)[1]
+                not_end = top_words != word_map['<end>']
+                unfinished = not_end if unfinished is None else unfinished & not_end
+                k_prev_words[:, step + 1] = (top_words * unfinished.type_as(top_words))[:, 0]
+            seqs = k_prev_words.tolist()
+        special = {word_map['<start>'], word_map['<end>'], word_map['<unk>'], word_map['<pad>']}
+        sentences = [' '.join(rev_word_map[w] for w in s if w not in special) for s in seqs]
+        return self.remove_bad_endings(sentences), seqs
+
     def forward(self, images, encoded_captions, caption_lengths, ss_prob=None):
         if ss_prob is not None:
             raise NotImplementedError("scheduled sampling is outside the LRP hot path (SURVEY.md §2 #9)")
@@ -427,6 +451,12 @@ class ExplainAOAAttention(ExplainGridTDAttention):
     def get_hidden_parameters(self, img_filepath):
         self.img = self.preprocess_img(img_filepath)
         enc = self._find_caption(img_filepath, beam_size=3, max_cap_length=20)
+        self._set_state(self.img, self.beam_caption_encode, enc)
+
+    def forward_greedy(self, img_filepath):
+        """reference :883-950: the saved state for the beam-size-1 caption."""
+        self.img = self.preprocess_img(img_filepath)
+        enc = self._find_caption(img_filepath, beam_size=1, max_cap_length=20)
         self._set_state(self.img, self.beam_caption_encode, enc)
 
     def _set_state(self, img, tokens, enc=None):

@@ -327,6 +327,29 @@ class GridTDModel(nn.Module):
                 break
         return seq, seq_logprobs, max_length
 
+    def greedy_search(self, imgs, word_map, max_cap_length=20):
+        """reference :480-520 -> (sentences with the bad endings removed, token lists incl. <start>; a finished row
+        continues with <pad> = 0).  The BU twin (:2242-2285) is this code over its own ``_encode``."""
+        self.eval()
+        rev_word_map = {v: k for k, v in word_map.items()}
+        with torch.no_grad():
+            k_prev_words = torch.zeros(imgs.size(0), max_cap_length, dtype=torch.long, device=imgs.device)
+            k_prev_words[:, 0] = word_map['<start>']
+            _, image_feature_proj, global_img_feature = self._encode(imgs)
+            state = self.init_hidden_state(image_feature_proj) + self.init_hidden_state(image_feature_proj)
+            unfinished = None
+            for step in range(max_cap_length - 1):
+                xt = torch.cat((state[2], global_img_feature, self.embedding(k_prev_words[:, step])), dim=-1)
+                predict_score_t, _, _, state = self.predict_next_word(image_feature_proj, xt, state)
+                top_words = torch.log_softmax(predict_score_t, dim=-1).topk(1, -1, True, True)[1]
+                not_end = top_words != word_map['<end>']
+                unfinished = not_end if unfinished is None else unfinished & not_end
+                k_prev_words[:, step + 1] = (top_words * unfinished.type_as(top_words))[:, 0]
+            seqs = k_prev_words.tolist()
+        special = {word_map['<start>'], word_map['<end>'], word_map['<unk>'], word_map['<pad>']}
+        sentences = [' '.join(rev_word_map[w] for w in s if w not in special) for s in seqs]
+        return self.remove_bad_endings(sentences), seqs
+
     def beam_search_device(self, imgs, word_map, beam_size=3, max_cap_length=20):
         """``beam_search`` with the whole step loop on the device (lrpx.beam.GridTDBeamSearch: fused step kernels +
         ``lrpx_beam_step`` bookkeeping, one CUDA graph, one read-back) and for B >= 1 images at once.  Same word
@@ -809,6 +832,12 @@ class ExplainGridTDAttention(object):
     def get_hidden_parameters(self, img_filepath):
         self.img = self.preprocess_img(img_filepath)
         enc = self._find_caption(img_filepath, beam_size=2, max_cap_length=50)
+        self._set_state(self.img, self.beam_caption_encode, enc)
+
+    def forward_greedy(self, img_filepath):
+        """reference :799-890: the saved state for the beam-size-1 caption of at most 20 words."""
+        self.img = self.preprocess_img(img_filepath)
+        enc = self._find_caption(img_filepath, beam_size=1, max_cap_length=20)
         self._set_state(self.img, self.beam_caption_encode, enc)
 
     def _empty_caption(self, tokens):

@@ -518,3 +518,27 @@ def test_adaptive_gradient_explainers_end_to_end_vs_oracle(tmp_path):
         want = O.sequential_gradient(layers, img, df.t().reshape(1, -1, *feat.shape[-2:]), guided=True)
         assert _rel_l2(imgs[t], want) < 5e-3, (t, _rel_l2(imgs[t], want))
         assert_close(words[t], rw, rtol=1e-3, atol=1e-5, what=f"r_words t={t}")
+
+
+def test_forward_greedy_and_named_grad_cam(tmp_path):
+    """forward_greedy (reference gridTDmodel.py:799-890: the beam-size-1 caption's saved state) and the named grad_cam
+    method of the CAM classes (:1760-1771)."""
+    from models import gridTDmodel as G
+    V, H, E = 60, 64, 32
+    model = G.GridTDModel(E, H, V, "vgg16")
+    model.load_state_dict(synth.gridtd_decoder_state(351, V, H, E), strict=False)
+    model.img_encoder.encoder.load_state_dict(synth.vgg_state(352))
+    model.to(DEV).eval()
+    ex = G.ExplainGridTDGradCam(_args(E, H, tmp_path), synth.word_map(V), model=model)
+    img = synth.images(353, 1).to(DEV)
+    ex.preprocess_img = lambda p: img
+    ex.forward_greedy("synthetic.jpg")
+    _, seqs = model.greedy_search(img, synth.word_map(V), max_cap_length=20)
+    words = [w for w in seqs[0][1:] if w != 0]
+    n = min(len(words), ex.caption_length)
+    assert n > 0 and ex.beam_caption_encode[1:1 + n] == words[:n]
+    d_img, _ = ex.explain_caption_wordt(0)
+    cam = ex.grad_cam(ex.image_features, d_img)
+    assert cam.shape == (196,)
+    assert_close(cam, O.grad_cam(_pix(ex.image_features.cpu()), _pix(d_img.cpu())), rtol=1e-3, atol=1e-5, what="grad_cam")
+    assert_close(ex.explain_cnn(d_img)[0], cam, rtol=0, atol=0, what="explain_cnn of the CAM class")

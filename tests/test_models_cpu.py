@@ -367,3 +367,24 @@ def test_self_critical_reward_vs_reference_fixture(golden):
     rev = {v: k for k, v in wm.items()}
     s = mu.array_to_str(gen[2].tolist(), rev, wm['<end>'])
     assert '<start>' not in s and '<pad>' not in s
+
+
+def test_greedy_search_equals_beam_size_one():
+    """GridTDModel / AOAModel.greedy_search (reference gridTDmodel.py:480-520, aoamodel.py:487-530): for one image the
+    words are those of beam_search with one beam (what the explainers' forward_greedy runs), until <end>."""
+    import torch
+    from models import gridTDmodel as G, aoamodel as A
+    V, H, E = 40, 32, 16
+    wm = synth.word_map(V)
+    torch.manual_seed(3)
+    for model in (G.GridTDModel(E, H, V, "vgg16"), A.AOAModel(E, H, 4, V, "vgg16")):
+        model.eval()
+        img = synth.images(4, 1)
+        sent_b, idx_b = model.beam_search(img, wm, beam_size=1, max_cap_length=8)
+        sent_g, seqs = model.greedy_search(img, wm, max_cap_length=8)
+        special = {wm['<start>'], wm['<end>'], wm['<unk>'], wm['<pad>']}
+        words_g = [w for w in seqs[0] if w not in special]
+        words_b = [w for w in idx_b if w not in special]
+        n = min(len(words_g), len(words_b))
+        assert n > 0 and words_g[:n] == words_b[:n], (words_g, words_b)
+        assert seqs[0][0] == wm['<start>'] and len(seqs[0]) == 8 and isinstance(sent_g[0], str)
