@@ -16,12 +16,15 @@ every number.
   4  VGG16 encoder LRP only through LRPtools.compute_lrp: 512 (image, target relevance) requests per GPU per step.
   5  one lrp_tune training step (train.py:211-233) on gridTD, batch 128 per GPU, DDP gradient all-reduce over NCCL.
 --precision: bf16 (tcgen05 chain with bf16 operands; the headline mode) | fp32 (the fp32-accurate mode: bf16x3 operands,
-  fp32 gains, hi|lo storage — the reference's rtol 1e-4 bar on tensor cores).
+  fp32 gains, hi|lo storage — the reference's rtol 1e-4 bar on tensor cores) | mixed (fp32-accurate forward once per
+  image, bf16 chain per explanation).
+--method (config 2): lrp (default) | gradient | guided — the reference's comparison explainers (ExplainGridTDGradient /
+  ExplainiGridTDGuidedGradient) through the same pipeline; device-resident timing + parity against the oracle's backward.
 --deliver (config 2, end-to-end leg): full (Q,3,224,224 fp32, the reference's return value) | channel_mean
   ((Q,224,224): what evaluation.py:134,411,503 reduces every heat-map to) | fp16.
 
-Without --config the N = 1 run also measures configs 3, 4, 5 and the fp32-accurate mode of config 2 briefly and
-attaches them under "also" (each with its own parity figures), so that one driver run covers every configuration.
+Without --config the N = 1 run also measures configs 3, 4, 5, the mixed / fp32-accurate modes, the ResNet101 variant and
+the gradient-family explainers of config 2 briefly and attaches them under "also" (each with its own parity figures), so that one driver run covers every configuration.
 Under torchrun (N > 1) each rank works on its own shard (requests are independent: no collective on the data path;
 config 5: DDP all-reduce); timing = CUDA events, max over ranks.
 """
