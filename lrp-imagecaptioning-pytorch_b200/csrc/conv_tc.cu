@@ -2140,7 +2140,9 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       // LRPX_TC_PAIR=0: off, =2: every width.
       const char* env_pair = getenv("LRPX_TC_PAIR");
       const bool pair_on = env_pair ? env_pair[0] != '0' : LRPX_TC_PAIR_DEFAULT;
-      const int pair_min_bn = (env_pair && env_pair[0] == '2') ? 32 : 128;
+      // error-compensated operands (K wrap: three times the K, hence three times the B tiles per accumulator tile): the
+      // pair pays from 64 columns on — 224^2 64->64: 1.71 -> 1.52 ms, 112^2 128->64 un-pool: 0.84 -> 0.73 ms per 128 requests
+      const int pair_min_bn = (env_pair && env_pair[0] == '2') ? 32 : (p.a_wrap ? 64 : 128);
       const bool want_pair = want_cluster && pair_on && !p.fold && p.bn % 32 == 0 && p.bn >= pair_min_bn &&
                              (epi == LRPX_TC_EPI_MUL || epi == LRPX_TC_EPI_MUL_UNPOOL || epi == LRPX_TC_EPI_MULX ||
                               epi == LRPX_TC_EPI_MULX_UNPOOL) &&
