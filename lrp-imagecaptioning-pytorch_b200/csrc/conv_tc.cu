@@ -1897,10 +1897,11 @@ static int launch_tc_slab_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, c
 //   mh = 2 (256-row tiles, one issuer warp per half) whenever two accumulators of the tile fit one TMEM buffer
 //   (bn <= 128); slab_mode 1 when the single slab is the smaller fetch and fits two TMA boxes, else one slab per
 //   filter row; B resident when the whole layer's B fits next to >= 2 (mode 1) / 4 (mode 3) A stages.
-static bool plan_slab(TcParams& p, int reserve) {
+static bool plan_slab(TcParams& p, int reserve, bool pair) {
   const int budget = TC_SMEM_BYTES - 1024 - reserve;
   const int b_bytes = p.bn * TC_BK * 2;
-  const long long b_total = (long long)p.taps * p.kc_per_tap * b_bytes;
+  // pair mode: each CTA of the pair keeps half of every B tile, so a layer's B is resident from twice the size on
+  const long long b_total = (long long)p.taps * p.kc_per_tap * b_bytes / (pair ? 2 : 1);
   const char* env_mh = getenv("LRPX_TC_MH");             // experiment switches (timing probes only)
   const char* env_iss = getenv("LRPX_TC_ISSUERS");
   const char* env_res = getenv("LRPX_TC_RES3");           // "0": do not trade slab mode 1 for a resident B
@@ -2103,16 +2104,36 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     const char* env_ts = getenv("LRPX_TC_TMASTORE");
     const bool tma_store = epi == LRPX_TC_EPI_MUL && !p.fold && !(env_ts && env_ts[0] == '0');
     const int reserve = tma_store ? TC_EPI_WARPS * 1024 : 0;
-    if (want_slab && plan_slab(p, reserve)) {
+    // the pair decision up to the tile count (known after planning): it decides how much of B a CTA holds
+    const char* env_cl = getenv("LRPX_TC_CLUSTER");             // LRPX_TC_CLUSTER=0: one CTA per cluster
+    const bool want_cluster = !(env_cl && env_cl[0] == '0');
+    const char* env_pair = getenv("LRPX_TC_PAIR");
+    const bool pair_on = env_pair ? env_pair[0] != '0' : LRPX_TC_PAIR_DEFAULT;
+    // error-compensated operands (K wrap: three times the K, hence three times the B tiles per accumulator tile): the
+    // pair pays from 64 columns on — 224^2 64->64: 1.71 -> 1.52 ms, 112^2 128->64 un-pool: 0.84 -> 0.73 ms per 128 requests
+    const int pair_min_bn = (env_pair && env_pair[0] == '2') ? 32 : (p.a_wrap ? 64 : 128);
+    const char* env_pres = getenv("LRPX_TC_PAIR_RES");          // "0": plan the B residency as if each CTA held all of B
+    bool pair_pre = want_cluster && pair_on && !p.fold && p.bn % 32 == 0 && p.bn >= pair_min_bn &&
+                    (epi == LRPX_TC_EPI_MUL || epi == LRPX_TC_EPI_MUL_UNPOOL || epi == LRPX_TC_EPI_MULX ||
+                     epi == LRPX_TC_EPI_MULX_UNPOOL) && sm_count() >= 2;
+    const bool pair_res = pair_pre && !(env_pres && env_pres[0] == '0');
+    if (want_slab && plan_slab(p, reserve, pair_res)) {
       p.half_rows = p.fold ? TC_BM - 2 : TC_BM;
       p.tile_out_rows = p.mh * p.half_rows;
+      p.num_m_tiles = (p.m_total + p.tile_out_rows - 1) / p.tile_out_rows;
+      if (pair_res && p.num_m_tiles < 2) {          // no pair after all: plan again with the whole B per CTA
+        pair_pre = false;
+        if (!plan_slab(p, reserve, false)) { set_error("slab planning failed"); return LRPX_E_INVALID; }
+        p.tile_out_rows = p.mh * p.half_rows;
+        p.num_m_tiles = (p.m_total + p.tile_out_rows - 1) / p.tile_out_rows;
+      }
       const int tile_rows = p.tile_out_rows;
-      p.num_m_tiles = (p.m_total + tile_rows - 1) / tile_rows;
+      const bool want_pair = pair_pre && p.num_m_tiles >= 2;
       CUtensorMap ma0, ma1, mb, mo;
       mo = CUtensorMap{};
       p.store_off = 0;
       if (tma_store) {
-        const long long b_region = p.b_resident ? (long long)p.taps * p.kc_per_tap * p.bn * TC_BK * 2
+        const long long b_region = p.b_resident ? (long long)p.taps * p.kc_per_tap * p.bn * TC_BK * 2 / (want_pair ? 2 : 1)
                                                 : (long long)p.b_stages * p.bn * TC_BK * 2;
         p.store_off = (int)((p.a_stages * (long long)p.a_stage_bytes + b_region + 1023) & ~1023LL);
         int rco = make_map_out(&mo, a->out, (uint64_t)p.m_total, (uint64_t)p.out_c);
@@ -2127,8 +2148,6 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       if (rc) return rc;
       // CTA pairs sharing the streamed B tiles through TMA multicast (halves the L2 -> SM weight traffic, which is
       // what bounds the 256/512-channel layers: ~12 TB/s of B re-fetches at 128-row tiles)
-      const char* env_cl = getenv("LRPX_TC_CLUSTER");             // LRPX_TC_CLUSTER=0: one CTA per cluster
-      const bool want_cluster = !(env_cl && env_cl[0] == '0');
       CUtensorMap mbh = mb;
       p.cluster = 1;
       p.tiles_sched = p.num_m_tiles * p.num_n_tiles;
@@ -2138,15 +2157,6 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       // layers -4...9 %; the 64-column layers do NOT gain (224^2: +19 %, 112^2 un-pool: +-0: their tiles are short, K = 576 /
       // 1152, and the hand-over between the two CTAs costs more than the saved operand reads), so pairs start at 128 columns.
       // LRPX_TC_PAIR=0: off, =2: every width.
-      const char* env_pair = getenv("LRPX_TC_PAIR");
-      const bool pair_on = env_pair ? env_pair[0] != '0' : LRPX_TC_PAIR_DEFAULT;
-      // error-compensated operands (K wrap: three times the K, hence three times the B tiles per accumulator tile): the
-      // pair pays from 64 columns on — 224^2 64->64: 1.71 -> 1.52 ms, 112^2 128->64 un-pool: 0.84 -> 0.73 ms per 128 requests
-      const int pair_min_bn = (env_pair && env_pair[0] == '2') ? 32 : (p.a_wrap ? 64 : 128);
-      const bool want_pair = want_cluster && pair_on && !p.fold && p.bn % 32 == 0 && p.bn >= pair_min_bn &&
-                             (epi == LRPX_TC_EPI_MUL || epi == LRPX_TC_EPI_MUL_UNPOOL || epi == LRPX_TC_EPI_MULX ||
-                              epi == LRPX_TC_EPI_MULX_UNPOOL) &&
-                             p.num_m_tiles >= 2 && sm_count() >= 2;
       p.pair = 0;
       if (want_pair) {
         p.pair = 1;
