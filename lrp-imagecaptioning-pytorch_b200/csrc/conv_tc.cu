@@ -50,6 +50,8 @@ struct TcParams {
   int wp1;           // w + 1
   uint32_t blk_mul, wp1_mul;   // fast_div multipliers / shifts for blk and wp1
   int blk_sh, wp1_sh;
+  uint32_t nnt_mul;  // fast_div multiplier / shift for num_n_tiles (tile_coords)
+  int nnt_sh;
   int cin;           // channels of A
   int ncol;          // GEMM N (rows of Wt)
   int bn;            // N tile
@@ -68,7 +70,15 @@ struct TcParams {
   int fold;          // EPI_INPUT3: the three filter columns are folded into N (see epi_input3); 0 otherwise
   int half_rows;     // row distance between the M halves of a tile (128; 126 with fold: the halves overlap by two rows)
   int tile_out_rows; // output rows per tile (mh*128; 252 with fold)
-  int cluster;       // 2: CTA pairs (thread-block clusters) share every streamed B tile through TMA multicast; else 1
+  int tile_stride;   // row distance between consecutive M tiles (= tile_out_rows; = w + 1 in walk mode)
+  int walk;          // row walk (slab mode 3, resident B, one channel block): a CTA takes a contiguous run of tiles ONE IMAGE
+                     // ROW apart, so two of a tile's three slabs are the previous tile's — see tc_conv_slab_kernel
+  int tiles_per_cta; // walk: length of a CTA's run
+  int a_group;       // slab mode 3: slabs per ring stage. 1 = one barrier round trip per filter row's slab; 3 = the three slabs
+                     // of a tile share ONE stage (one wait + one commit per tile for the issuers, one wait for the producer)
+  int nbuf_log2;     // accumulator ring of the slab kernel: 1 = two buffers of 256 TMEM columns, 2 = four of 128
+  int sleep_ns;      // back-off of the producers' and the epilogue warps' barrier waits (mbar_wait_ns)
+  int cluster;      // 2: CTA pairs (thread-block clusters) share every streamed B tile through TMA multicast; else 1
   int tiles_sched;   // tiles the persistent loop walks (cluster mode pads the M tiles to an even count)
   int store_off;     // EPI_MUL: byte offset (from the aligned smem base) of the TMA-store staging area, 0 = plain stores
   int a_stages, b_stages;
@@ -164,6 +174,35 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_t<0>(bar, parity); }
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) { mbar_wait_t<200>(bar, parity); }
+// the same with the back-off as a launch parameter (TcParams::sleep_ns; 0 = poll): how long a waiter may oversleep depends
+// on how long a tile of the layer takes
+__device__ __forceinline__ void mbar_wait_ns(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (ok) return;
+  long long t0 = clock64();
+  for (uint32_t it = 1;; ++it) {
+    if (ns) __nanosleep(ns);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((it & 1023) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("lrpx tc_conv: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -562,7 +601,7 @@ __device__ __forceinline__ void epi_release(const TcParams& p, uint32_t release_
 // so the M halves of a tile start 126 rows apart and a tile yields 252 output rows.
 __device__ __forceinline__ void epi_input3(const TcParams& p, const RowInfo& r, uint32_t taddr, uint32_t release_bar,
                                            float* scratch /* [4 quarters][2][8] of this (buffer, half) */, int quarter,
-                                           int bar_id) {
+                                           int bar_id, uint32_t full_bar, uint32_t full_parity) {
   const int lane = threadIdx.x & 31;
   const bool edge = (quarter == 0 && lane == 0) || (quarter == 3 && lane == 31);
   const bool writes = r.valid && !edge && !(p.debug_flags & 1);
@@ -574,6 +613,11 @@ __device__ __forceinline__ void epi_input3(const TcParams& p, const RowInfo& r, 
   if (writes)
 #pragma unroll
     for (int c = 0; c < 3; ++c) xin[c] = __ldg(p.x + ((size_t)img * 3 + c) * hw + pix);
+  // only now wait for the tile's accumulator: the row arithmetic and the two dependent loads above (request -> image, image
+  // -> pixel values) used to start AFTER the wait and sat, with the integer divisions of tile_coords, on the pass's critical
+  // path — the layer's tile time is the latency of one such pass (two warp sets alternate), not its bytes or its MMAs
+  mbar_wait_ns(full_bar, full_parity, (uint32_t)p.sleep_ns);
+  tc_fence_after();
   uint32_t v[24];
   TMEM_LD_X16(taddr, v);
   {
@@ -1024,13 +1068,18 @@ __device__ __forceinline__ int epi_units_per_half(const TcParams& p, int epi) {
 template <int EPI>
 __device__ __forceinline__ void epi_unit(const TcParams& p, const RowInfo& r0, uint32_t taddr, int n_tile, int c,
                                          uint32_t release_bar, uint32_t stage = 0, const CUtensorMap* tmo = nullptr,
-                                         float* scratch = nullptr, int quarter = 0, int bar_id = 0) {
-  if (p.debug_flags & 16) { epi_release(p, release_bar); return; }      // timing experiment: only hands the accumulator back
+                                         float* scratch = nullptr, int quarter = 0, int bar_id = 0, uint32_t full_bar = 0,
+                                         uint32_t full_parity = 0) {
+  if (p.debug_flags & 16) {             // timing experiment: only hands the accumulator back
+    if (EPI == LRPX_TC_EPI_INPUT3) { mbar_wait_ns(full_bar, full_parity, (uint32_t)p.sleep_ns); tc_fence_after(); }
+    epi_release(p, release_bar);
+    return;
+  }
   RowInfo r = r0;
   if (p.debug_flags & 1) { r.in_range = false; r.valid = false; }
   const int n0 = n_tile * p.bn;
   if (EPI == LRPX_TC_EPI_INPUT3) {
-    epi_input3(p, r0, taddr, release_bar, scratch, quarter, bar_id);
+    epi_input3(p, r, taddr, release_bar, scratch, quarter, bar_id, full_bar, full_parity);
   } else if (EPI == TC_EPI_MUL_FOLD) {
     epi_mul_fold(p, r0, taddr, c >> 1, release_bar, scratch, quarter, bar_id);
   } else if (EPI == LRPX_TC_EPI_MULX) {
@@ -1199,7 +1248,9 @@ __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_bas
                                                   uint32_t release_bar /* tmem_empty barrier of the tile's buffer */,
                                                   uint32_t stage = 0, const CUtensorMap* tmo = nullptr,
                                                   float* scratch = nullptr /* INPUT3: [2 halves][4][2][8] */, int quarter = 0,
-                                                  int it = 0 /* this CTA's tile counter */) {
+                                                  int it = 0 /* this CTA's tile counter */,
+                                                  uint32_t full_bar = 0 /* INPUT3: the caller has NOT waited for the */,
+                                                  uint32_t full_parity = 0 /* accumulator yet (epi_input3 does) */) {
   const int uph = epi_units_per_half(p, EPI);
   const int n_units = mh * uph;
   constexpr int step = TC_EPI_WARPS / 4;
@@ -1213,6 +1264,7 @@ __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_bas
     if (sub < 0 || sub >= 2) sub = n_units;          // not this warp's tile
   }
   if (sub >= n_units) {                 // nothing to read for this warp: hand the buffer back at once
+    if (EPI == LRPX_TC_EPI_INPUT3) { mbar_wait_ns(full_bar, full_parity, (uint32_t)p.sleep_ns); tc_fence_after(); }
     epi_release(p, release_bar);
     return;
   }
@@ -1224,12 +1276,18 @@ __device__ __forceinline__ void run_epilogue_tile(const TcParams& p, int row_bas
   int h_cached = -1;
   RowInfo r{};
   for (int u = sub; u < n_units; u += step) {
-    const int h = u / uph, c = (u - h * uph) << (EPI == TC_EPI_FWDX_SIMPLE ? 4 : 5);
+    const int h = u >= uph ? 1 : 0, c = (u - h * uph) << (EPI == TC_EPI_FWDX_SIMPLE ? 4 : 5);      // mh <= 2
     const int hr = (EPI == LRPX_TC_EPI_INPUT3) ? p.half_rows : TC_BM;
-    if (h != h_cached) { r = row_info(p, row_base + h * hr); h_cached = h; }
+    if (h != h_cached) {
+      r = row_info(p, row_base + h * hr);
+      h_cached = h;
+      // walk mode: the tiles are tile_stride (< tile_out_rows) rows apart; rows past the stride belong to the next tile
+      if (EPI == LRPX_TC_EPI_INPUT3 && p.walk && h * hr + quarter * 32 + (int)(threadIdx.x & 31) - p.fold >= p.tile_stride)
+        r.valid = false;
+    }
     if (pf_row_base >= 0) epi_prefetch_unit<EPI>(p, pf_row_base + h * TC_BM, n_tile, c);
     epi_unit<EPI>(p, r, taddr_q + (uint32_t)(h * p.bn), n_tile, c, (u + step >= n_units) ? release_bar : 0u, stage, tmo,
-                  scratch ? scratch + h * 64 : nullptr, quarter, 1 + 2 * set + h);
+                  scratch ? scratch + h * 64 : nullptr, quarter, 1 + 2 * set + h, full_bar, full_parity);
   }
 }
 
@@ -1358,13 +1416,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // neighbouring M tiles, so they consume the same B tiles in the same order; m_tile may be one past the end (a padding
 // tile: its A rows are zero-filled by TMA and its results are clipped by the row bound).
 __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& m_tile, int& n_tile) {
+  // (host-prepared multiplier: the generic integer division is ~40 dependent instructions, twice per tile on every
+  // epilogue warp's critical path — 8 % of the first layer's stall samples)
   if (p.cluster == 2) {
     const int pr = tile >> 1;
-    n_tile = pr % p.num_n_tiles;
-    m_tile = (pr / p.num_n_tiles) * 2 + (tile & 1);
+    const int q = fast_div(pr, p.nnt_mul, p.nnt_sh);
+    n_tile = pr - q * p.num_n_tiles;
+    m_tile = q * 2 + (tile & 1);
   } else {
-    n_tile = tile % p.num_n_tiles;
-    m_tile = tile / p.num_n_tiles;
+    m_tile = fast_div(tile, p.nnt_mul, p.nnt_sh);
+    n_tile = tile - m_tile * p.num_n_tiles;
   }
 }
 
@@ -1394,7 +1455,9 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
   const uint32_t b16 = (((uint32_t)p.bn * TC_BK * 2) >> 4) >> (PAIR ? 1 : 0);
   const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
   const uint32_t row16 = (TC_BK * 2) >> 4;                        // one PF row of 64 channels, 16-byte units
-  const uint32_t dy16 = MODE3 ? 0u : (uint32_t)p.wp1 * row16;      // MODE3: each filter row has its own slab (stage)
+  // MODE3: each filter row has its own slab — a ring stage of its own, or (a_group == 3) the dy-th third of the tile's stage
+  const bool grouped = MODE3 && p.a_group == 3;
+  const uint32_t dy16 = MODE3 ? (grouped ? (uint32_t)p.a_stage_bytes / 48u : 0u) : (uint32_t)p.wp1 * row16;
   const int kcpt = p.kc_per_tap, a_stages = p.a_stages, b_stages = p.b_stages;
   const uint32_t bn = (uint32_t)p.bn;
   const bool skip_mma = (p.debug_flags & 2) != 0;     // timing experiment
@@ -1410,11 +1473,18 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
     mbar_wait(smem_u32(bres_bar), 0);
     tc_fence_after();
   }
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((it >> 1) & 1) ^ 1);
+  // walk mode (MODE3 only): tile i of the run uses the ring stages of slabs i, i+1, i+2 and frees only the oldest
+  const int nbuf_log2 = p.nbuf_log2, nbuf_mask = (1 << p.nbuf_log2) - 1;      // accumulator ring: 2 x 256 or 4 x 128 columns
+  const uint32_t buf_cols = 512u >> p.nbuf_log2;
+  const bool walk = MODE3 && p.walk;
+  const int tile_begin = walk ? (int)blockIdx.x * p.tiles_per_cta : (int)blockIdx.x;
+  const int tile_end = walk ? min(tile_begin + p.tiles_per_cta, num_tiles) : num_tiles;
+  const int tile_step = walk ? 1 : (int)gridDim.x;
+  for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
+    const int buf = it & nbuf_mask;
+    mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((it >> nbuf_log2) & 1) ^ 1);
     tc_fence_after();
-    const uint32_t d_tmem = tmem_base + buf * 256 + (uint32_t)h0 * bn;
+    const uint32_t d_tmem = tmem_base + buf * buf_cols + (uint32_t)h0 * bn;
     for (int kc = 0; kc < kcpt; ++kc) {
       if (!MODE3) {
         mbar_wait(smem_u32(&a_full[as]), aph);
@@ -1422,11 +1492,20 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
       }
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) {
-        if (MODE3) {
-          mbar_wait(smem_u32(&a_full[as]), aph);
-          tc_fence_after();
+        int sa = as;                 // ring stage of this filter row's slab
+        if (MODE3 && (!grouped || dy == 0)) {
+          uint32_t ph = aph;
+          if (walk && dy > 0) {      // `as` moved on after filter row 0: rows 1, 2 sit in the next two stages
+            sa = as + dy - 1;
+            if (sa >= a_stages) { sa -= a_stages; ph ^= 1; }
+          }
+          // (walk: two of the three slabs were already waited for by the previous tile)
+          if (!walk || dy == 2 || it == 0) {
+            mbar_wait(smem_u32(&a_full[sa]), ph);
+            tc_fence_after();
+          }
         }
-        const uint32_t a_row = a_lo_base + (uint32_t)as * a_stage16 + (uint32_t)dy * dy16;
+        const uint32_t a_row = a_lo_base + (uint32_t)sa * a_stage16 + (uint32_t)dy * dy16;
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           if (dx >= ndx) break;
@@ -1459,7 +1538,7 @@ __device__ __forceinline__ void slab_mma_loop(const TcParams& p, uint64_t* a_ful
             if (++bs == b_stages) { bs = 0; bph ^= 1; }
           }
         }
-        if (MODE3) {
+        if (MODE3 && (grouped ? dy == 2 : (!walk || dy == 0))) {
           if (PAIR) tc_commit_2sm(smem_u32(&a_empty[as]));
           else tc_commit(smem_u32(&a_empty[as]));
           if (++as == a_stages) { as = 0; aph ^= 1; }
@@ -1505,8 +1584,8 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   __shared__ __align__(8) uint64_t b_full[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t b_empty[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bres_bar;
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t tmem_full_bar[4];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[4];
   __shared__ uint32_t tmem_base_slot;
   // EPI_INPUT3: [accumulator buffer][tile parity of the warp set][M half][quarter][2][8].  A warp writes its boundary
   // rows BEFORE the named barrier of a tile and reads its neighbours' right after it; with two copies alternating per
@@ -1520,7 +1599,15 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)p.a_stages * p.a_stage_bytes;
   const int num_tiles = p.tiles_sched;
-  const int tile_rows = p.tile_out_rows;       // output rows per tile; with fold the computed rows start one row earlier
+  const int tile_rows = p.tile_stride;         // row distance of the M tiles (= output rows per tile; walk: one image row);
+                                               // with fold the computed rows start one row earlier
+  // Row walk (p.walk; the 224^2 first layer): CTA c takes tiles [c * tiles_per_cta, ...) one image row (w + 1 PF rows)
+  // apart.  Slab j of tile m starts at row (m + j - 1)(w + 1) - 1 = slab j - 1 of tile m + 1: after the first tile of a run
+  // only ONE new slab is fetched per tile (L2 -> SM traffic of A 258/225 = 1.15x the rows instead of 3 x 258/252 = 3.07x,
+  // which is what bound the layer).  A tile still computes 252 rows; the rows past the stride are the next tile's.
+  const int tile_begin = p.walk ? (int)blockIdx.x * p.tiles_per_cta : (int)blockIdx.x;
+  const int tile_end = p.walk ? min(tile_begin + p.tiles_per_cta, num_tiles) : num_tiles;
+  const int tile_step = p.walk ? 1 : (int)gridDim.x;
   const int n_slabs = p.slab_mode == 1 ? 1 : 3;
 
   if (threadIdx.x == 0) {
@@ -1535,10 +1622,12 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       mbar_init(smem_u32(&b_empty[s]), PAIR ? p.n_issuers : p.n_issuers * p.cluster);
     }
     mbar_init(smem_u32(&bres_bar), 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(smem_u32(&tmem_full_bar[b]), p.n_issuers);
       // pair: the leader's issuers wait for the epilogue warps of BOTH CTAs (the peer's arrive remotely)
-      mbar_init(smem_u32(&tmem_empty_bar[b]), PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);
+      // (first-layer epilogues: only the 4 * mh warps of the tile's set read the buffer, see the epilogue loop)
+      mbar_init(smem_u32(&tmem_empty_bar[b]), (EPI == LRPX_TC_EPI_INPUT || EPI == LRPX_TC_EPI_INPUT3)
+                                                  ? 4 * p.mh : (PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
@@ -1571,13 +1660,33 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int as = 0;
       uint32_t aph = 0;
       const uint32_t a_tx = (uint32_t)p.slab_rows * (TC_BK * 2);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         int m_tile, n_tile_unused;
         tile_coords(p, tile, m_tile, n_tile_unused);
         const int m0 = m_tile * tile_rows;             // fold: P' rows start at m0 - 1, which is where the slabs start anyway
+        const int j0 = (p.walk && tile != tile_begin) ? n_slabs - 1 : 0;      // walk: slabs 0, 1 are the previous tile's 1, 2
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
-          for (int j = 0; j < n_slabs; ++j) {          // one ring stage per slab
-            mbar_wait_relaxed(smem_u32(&a_empty[as]), aph ^ 1);
+          if (p.a_group == 3) {                        // one ring stage for the tile's three slabs (not with PAIR / walk)
+            mbar_wait_ns(smem_u32(&a_empty[as]), aph ^ 1, (uint32_t)p.sleep_ns);
+            const uint32_t fb = smem_u32(&a_full[as]);
+            const uint32_t dst = a_base + (uint32_t)as * p.a_stage_bytes;
+            const int kca = (p.a_wrap && kc >= p.a_wrap) ? kc - p.a_wrap : kc;
+            if (p.debug_flags & 4) {
+              mbar_arrive(fb);
+            } else {
+              mbar_expect_tx(fb, 3 * a_tx);
+              for (int j = 0; j < 3; ++j) {
+                const int row0 = m0 + (j - 1) * p.wp1 - 1;
+                const uint32_t dj = dst + (uint32_t)j * ((uint32_t)p.a_stage_bytes / 3u);
+                tma_load_2d(dj, &tmA0, fb, kca * TC_BK, row0);
+                if (p.box1_rows) tma_load_2d(dj + (uint32_t)p.box0_rows * (TC_BK * 2), &tmA1, fb, kca * TC_BK, row0 + p.box0_rows);
+              }
+            }
+            if (++as == p.a_stages) { as = 0; aph ^= 1; }
+            continue;
+          }
+          for (int j = j0; j < n_slabs; ++j) {         // one ring stage per slab
+            mbar_wait_ns(smem_u32(&a_empty[as]), aph ^ 1, (uint32_t)p.sleep_ns);
             const uint32_t fb = smem_u32(&a_full[as]);
             const uint32_t dst = a_base + (uint32_t)as * p.a_stage_bytes;
             if (p.debug_flags & 4) {          // timing experiment: no A traffic
@@ -1632,7 +1741,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           const int n0 = n_tile * p.bn;
           for (int kc = 0; kc < p.kc_per_tap; ++kc)
             for (int tap = 0; tap < p.taps; ++tap) {
-              mbar_wait_relaxed(smem_u32(&b_empty[bs]), bph ^ 1);
+              mbar_wait_ns(smem_u32(&b_empty[bs]), bph ^ 1, (uint32_t)p.sleep_ns);
               const uint32_t bb = smem_u32(&b_full[bs]);
               const uint32_t bbl = pair_rank ? mapa_u32(bb, 0) : bb;
               if (!pair_rank) mbar_expect_tx(bb, b_bytes);
@@ -1653,7 +1762,7 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           const int n0 = n_tile * p.bn;
           for (int kc = 0; kc < p.kc_per_tap; ++kc)
             for (int tap = 0; tap < p.taps; ++tap) {
-              mbar_wait_relaxed(smem_u32(&b_empty[bs]), bph ^ 1);
+              mbar_wait_ns(smem_u32(&b_empty[bs]), bph ^ 1, (uint32_t)p.sleep_ns);
               const uint32_t bb = smem_u32(&b_full[bs]);
               mbar_expect_tx(bb, b_bytes);
               if (p.cluster == 2)
@@ -1697,27 +1806,43 @@ tc_conv_slab_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp >= 2 && warp < 2 + TC_EPI_WARPS) {
     // ================================ epilogue warps
     const int quarter = warp & 3;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+    // First-layer epilogues (one unit per M half): the warps form two sets that take alternate tiles (run_epilogue_tile).  A
+    // warp walks ONLY its own set's tiles — a tile of that layer costs the SM ~5300 warp instructions, it is bound by
+    // instruction issue, and a third of them were the other set's (and the unit-less warps') trips through this loop just to
+    // hand the buffer back; the buffer's "empty" barrier counts the 4 * mh warps that actually read it.
+    constexpr bool kSets = EPI == LRPX_TC_EPI_INPUT || EPI == LRPX_TC_EPI_INPUT3;
+    const int sub0 = (warp - 2) >> 2;
+    int it = 0, it_step = 1;
+    bool idle = false;
+    if (kSets) {
+      if ((sub0 & 1) >= p.mh) idle = true;       // no unit for this warp (mh == 1)
+      else { it = sub0 >> 1; it_step = 2; }
+    }
+    for (int tile = tile_begin + it * tile_step; !idle && tile < tile_end; tile += it_step * tile_step, it += it_step) {
+      // accumulator ring: two buffers of 256 TMEM columns, or four of 128 when a tile's accumulators fit (mh * bn <= 128):
+      // the MMAs then run up to four tiles ahead of the epilogue, which is what a layer whose tile time is the round trip
+      // commit -> epilogue wake-up -> TMEM read -> release -> issuer wake-up needs (the first layer: 24 columns per half)
+      const int buf = it & ((1 << p.nbuf_log2) - 1);
+      const uint32_t acc_phase = (it >> p.nbuf_log2) & 1;
       int m_tile, n_tile;
       tile_coords(p, tile, m_tile, n_tile);
-      mbar_wait_relaxed(smem_u32(&tmem_full_bar[buf]), acc_phase);
-      tc_fence_after();
-      const int tile_pf = tile + 2 * (int)gridDim.x;      // L2 prefetch distance: two of this CTA's tiles ahead
+      if (EPI != LRPX_TC_EPI_INPUT3) {          // INPUT3 waits inside its epilogue, after its loads are in flight
+        mbar_wait_ns(smem_u32(&tmem_full_bar[buf]), acc_phase, (uint32_t)p.sleep_ns);
+        tc_fence_after();
+      }
+      const int tile_pf = tile + 2 * tile_step;           // L2 prefetch distance: two of this CTA's tiles ahead
       int m_pf = 0, n_pf = -1;
-      if (tile_pf < num_tiles) tile_coords(p, tile_pf, m_pf, n_pf);
+      if (tile_pf < tile_end) tile_coords(p, tile_pf, m_pf, n_pf);
       const int pf_row = (n_pf == n_tile) ? m_pf * tile_rows + quarter * 32 + lane : -1;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (512u >> p.nbuf_log2);
       const uint32_t stage = (EPI == LRPX_TC_EPI_MUL && p.store_off) ? smem_base + (uint32_t)p.store_off + (uint32_t)(warp - 2) * 1024u : 0u;
       uint32_t rel_bar = smem_u32(&tmem_empty_bar[buf]);
       if (PAIR) rel_bar = mapa_u32(rel_bar, 0);          // shared::cluster address of the LEADER's barrier (both ranks)
       run_epilogue_tile<EPI>(p, m_tile * tile_rows - p.fold + quarter * 32 + lane, taddr, n_tile, (warp - 2) >> 2, p.mh,
                              pf_row, rel_bar, stage, &tmO,
-                             EPI == LRPX_TC_EPI_INPUT3 ? &in3_scratch[buf][(it >> 1) & 1][0]
-                                                       : (EPI == TC_EPI_MUL_FOLD ? &in3_scratch[buf][0][0] : nullptr),
-                             quarter, it);
+                             EPI == LRPX_TC_EPI_INPUT3 ? &in3_scratch[it & 1][(it >> 1) & 1][0]
+                                                       : (EPI == TC_EPI_MUL_FOLD ? &in3_scratch[it & 1][0][0] : nullptr),
+                             quarter, it, smem_u32(&tmem_full_bar[buf]), acc_phase);
     }
     if (EPI == LRPX_TC_EPI_MUL && p.store_off) {      // the staging block must outlive the last tile store's read
       if (lane == 0) bulk_wait_read0();
@@ -2091,10 +2216,18 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
     }
   }
   p.num_n_tiles = p.fold ? 1 : a->ncol / p.bn;
+  {
+    int s = 0;
+    while ((1LL << s) < p.num_n_tiles) ++s;
+    p.nnt_sh = 31 + s;
+    p.nnt_mul = (uint32_t)((((unsigned long long)1 << p.nnt_sh) + (unsigned long long)p.num_n_tiles - 1) / (unsigned long long)p.num_n_tiles);
+  }
   cudaStream_t st = as_stream(stream);
   {
     const char* e2 = getenv("LRPX_TC_DEBUG");
     p.debug_flags = e2 ? atoi(e2) : 0;
+    const char* e3 = getenv("LRPX_TC_SLEEP");
+    p.sleep_ns = e3 ? atoi(e3) : 200;
 
   }
   {
@@ -2127,8 +2260,50 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
         p.tile_out_rows = p.mh * p.half_rows;
         p.num_m_tiles = (p.m_total + p.tile_out_rows - 1) / p.tile_out_rows;
       }
-      const int tile_rows = p.tile_out_rows;
+      p.tile_stride = p.tile_out_rows;
+      p.walk = 0;
+      p.tiles_per_cta = 0;
       const bool want_pair = pair_pre && p.num_m_tiles >= 2;
+      p.a_group = 1;
+      {
+        // First layer: the three slabs of a tile in ONE ring stage (LRPX_TC_AGROUP=0: one stage per slab).  Its tiles are
+        // 24 short MMAs; what bounds it is the issuers' and the producer's barrier traffic per tile (measured with the
+        // timing switches: 0.19 ms per 128 requests with the epilogue reduced to the hand-back, 0.15 ms with neither MMAs
+        // nor A traffic) — three wait / commit round trips per tile become one.
+        const char* env_ag = getenv("LRPX_TC_AGROUP");
+        const char* env_wk = getenv("LRPX_TC_WALK");            // the row walk (below) needs one stage per slab
+        const bool walk_asked = env_wk && env_wk[0] == '1';
+        const long long b_region = (long long)p.taps * p.kc_per_tap * p.bn * TC_BK * 2;
+        const int budget = TC_SMEM_BYTES - 1024 - reserve;
+        if (epi == LRPX_TC_EPI_INPUT3 && !(env_ag && env_ag[0] == '0') && !walk_asked && p.slab_mode == 3 && p.b_resident && !want_pair &&
+            2LL * 3 * p.a_stage_bytes + b_region <= budget) {
+          p.a_group = 3;
+          p.a_stages = (int)((budget - b_region) / (3LL * p.a_stage_bytes));
+          if (p.a_stages > TC_A_MAX_STAGES) p.a_stages = TC_A_MAX_STAGES;
+          p.a_stage_bytes *= 3;
+        }
+      }
+      {
+        // four accumulator buffers where a tile's accumulators fit 128 TMEM columns (LRPX_TC_NBUF=2: never, =4: every
+        // eligible layer; default: the first layer only, whose tiles are a round trip of barrier latencies long)
+        const char* env_nb = getenv("LRPX_TC_NBUF");
+        const bool fits = p.mh * p.bn <= 128 && !want_pair;
+        const int want = env_nb ? atoi(env_nb) : (epi == LRPX_TC_EPI_INPUT3 ? 4 : 2);
+        p.nbuf_log2 = (fits && want == 4) ? 2 : 1;
+      }
+      {
+        // row walk for the wide first layer (LRPX_TC_WALK=1; OFF by default): tiles one image row apart, two of three slabs
+        // reused.  Built on the hypothesis that the layer was bound by its 3x L2 -> SM re-fetch of A; measured on B200 it
+        // is not (0.218 ms per 128 requests with the strided walk, 0.237 ms with the row walk: the tile time is a round trip
+        // of barrier latencies, and the walk's tiles carry 225 instead of 252 rows) — kept as a tested switch
+        const char* env_walk = getenv("LRPX_TC_WALK");
+        if (epi == LRPX_TC_EPI_INPUT3 && env_walk && env_walk[0] == '1' && p.a_group == 1 && p.slab_mode == 3 && p.b_resident &&
+            p.kc_per_tap == 1 && p.a_stages >= 4 && !want_pair && p.wp1 <= p.tile_out_rows && p.wp1 * 5 >= p.tile_out_rows * 4) {
+          p.walk = 1;
+          p.tile_stride = p.wp1;
+          p.num_m_tiles = (p.m_total + p.tile_stride - 1) / p.tile_stride;
+        }
+      }
       CUtensorMap ma0, ma1, mb, mo;
       mo = CUtensorMap{};
       p.store_off = 0;
@@ -2173,6 +2348,10 @@ extern "C" int lrpx_tc_conv(const lrpx_tc_conv_args* a, void* stream) {
       int tiles = p.tiles_sched;
       int grid = tiles < sm_count() ? tiles : sm_count();
       if (p.cluster == 2) grid &= ~1;
+      if (p.walk) {                     // contiguous runs: every CTA of the grid has at least one tile
+        p.tiles_per_cta = (tiles + grid - 1) / grid;
+        grid = (tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+      }
       switch (epi) {
         case LRPX_TC_EPI_FWD_GAIN: return launch_tc_slab<LRPX_TC_EPI_FWD_GAIN>(ma0, ma1, mb, mbh, mo, p, grid, st);
         case LRPX_TC_EPI_MUL:

@@ -30,6 +30,7 @@ __device__ __forceinline__ void fc_split(float a, float b, float wrow, float coe
 // ------------------------------------------------------------------------------------------------
 struct GridWs {
   float *r_h2, *r_c2, *r_c1, *r_cth, *r_glob, *u, *v, *uctx, *coefavg, *wproj;
+  float* gA;               // A / stab(A_pre) per image (B x P x H), the attention rule's per-image factor
   // LRPX_DEC_TC_GEMM: split activations (largest GEMM) and prepared weights, bf16
   __nv_bfloat16 *a3, *w3_g2, *w3_g1, *w3_glob, *w3_proj;
   __nv_bfloat16* a3u;      // split form of u written by the step kernels themselves (null: CUDA-core GEMMs)
@@ -175,8 +176,16 @@ __global__ void grid_attn_kernel(lrpx_gridtd_args a, GridWs w) {
 // wproj = A * acc / stab(A_pre).  (The per-(request, pixel) form above re-reads uctx 196 times and spends ~4
 // instructions per multiply-add: 1.4 ms per 1216 requests; this form is bound by its 0.7 GB of output.)
 // SPLIT: the result leaves directly as the split bf16 operand [hi | lo] of the tensor-core projector GEMM.
+// G = A / stab(A_pre), once per image (B x P x H; every request of the image multiplies by it)
+__global__ void grid_attn_gain_kernel(const float* __restrict__ A, const float* __restrict__ A_pre, float* __restrict__ G,
+                                      size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(A) + i), z = __ldg(reinterpret_cast<const float4*>(A_pre) + i);
+    reinterpret_cast<float4*>(G)[i] = make_float4(x.x / stab(z.x), x.y / stab(z.y), x.z / stab(z.z), x.w / stab(z.w));
+  }
+}
 template <bool SPLIT>
-__global__ void __launch_bounds__(512) grid_attn_rows_kernel(lrpx_gridtd_args a, GridWs w) {
+__global__ void __launch_bounds__(512, 2) grid_attn_rows_kernel(lrpx_gridtd_args a, GridWs w) {
   extern __shared__ __align__(16) float att_s[];          // alpha[(t+1)][P4] | uctx[(t+1)][H]
   const int q = blockIdx.x;
   const int b = a.req_img[q], t = a.req_t[q];
@@ -190,18 +199,23 @@ __global__ void __launch_bounds__(512) grid_attn_rows_kernel(lrpx_gridtd_args a,
   for (int k = threadIdx.x; k < (t + 1) * H; k += blockDim.x) u_s[k] = w.uctx[(size_t)q * a.T * H + k];
   __syncthreads();
   if ((H & 3) == 0) {
-    // four hidden units per thread: per step one LDS.128 of uctx and one of the alphas feed 16 FMAs, A / A_pre come in
-    // 16-byte loads and the results leave as 8- or 16-byte stores (one unit per thread meant 2-byte stores of the split
-    // operand: 0.26 of the copy bandwidth in profiles/r1_hbm_kernels.md)
-    for (int h4 = threadIdx.x * 4; h4 < H; h4 += blockDim.x * 4) {
-      for (int p0 = 0; p0 < P; p0 += 4) {
-        float4 Av[4], Ap[4];
+    // four hidden units x four pixels per thread step: per LSTM step one LDS.128 of uctx and one of the alphas feed 16
+    // FMAs; the per-image factor G = A / stab(A_pre) (grid_attn_gain_kernel) comes in 16-byte loads issued before the
+    // loop, the results leave as 8- or 16-byte stores.  The block's threads are nh = min(H/4, 512) hidden-unit columns x
+    // pgs pixel-group lanes: with one lane (the round-2 form, 128 threads for H = 512) a block walked its 49 pixel groups
+    // one after the other, each a dependent chain of an L2 load and a short loop — 0.28 of the copy bandwidth
+    // (profiles/r2_hbm_kernels.md); four lanes cut the chain to 13 and put 32 warps on an SM.
+    const int nh = min(H >> 2, 512), pgs = max(1, (int)blockDim.x / nh);
+    const int hg = threadIdx.x % nh, pg = threadIdx.x / nh;
+    if (pg >= pgs) return;
+    for (int h4 = hg * 4; h4 < H; h4 += nh * 4) {
+      for (int p0 = pg * 4; p0 < P; p0 += pgs * 4) {
+        float4 G[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const bool ok = p0 + k < P;
           const size_t o0 = ((size_t)b * P + (ok ? p0 + k : 0)) * H + h4;
-          Av[k] = ok ? __ldg(reinterpret_cast<const float4*>(a.A + o0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          Ap[k] = ok ? __ldg(reinterpret_cast<const float4*>(a.A_pre + o0)) : make_float4(1.f, 1.f, 1.f, 1.f);
+          G[k] = ok ? __ldg(reinterpret_cast<const float4*>(w.gA + o0)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float acc[4][4];
 #pragma unroll
@@ -221,14 +235,14 @@ __global__ void __launch_bounds__(512) grid_attn_rows_kernel(lrpx_gridtd_args a,
         for (int k = 0; k < 4; ++k) {
           if (p0 + k >= P) break;
           const size_t row = (size_t)q * P + p0 + k;
-          const float av[4] = {Av[k].x, Av[k].y, Av[k].z, Av[k].w}, ap[4] = {Ap[k].x, Ap[k].y, Ap[k].z, Ap[k].w};
+          const float g[4] = {G[k].x, G[k].y, G[k].z, G[k].w};
           if (SPLIT) {
             uint32_t hi2[2], lo2[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(__fdividef(acc[k][2 * j] * av[2 * j], stab(ap[2 * j])), h0, l0);
-              split_bf16(__fdividef(acc[k][2 * j + 1] * av[2 * j + 1], stab(ap[2 * j + 1])), h1, l1);
+              split_bf16(acc[k][2 * j] * g[2 * j], h0, l0);
+              split_bf16(acc[k][2 * j + 1] * g[2 * j + 1], h1, l1);
               hi2[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
               lo2[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
             }
@@ -237,8 +251,7 @@ __global__ void __launch_bounds__(512) grid_attn_rows_kernel(lrpx_gridtd_args a,
             *reinterpret_cast<uint2*>(o + H) = make_uint2(lo2[0], lo2[1]);
           } else {
             *reinterpret_cast<float4*>(w.wproj + row * H + h4) =
-                make_float4(acc[k][0] * av[0] / stab(ap[0]), acc[k][1] * av[1] / stab(ap[1]),
-                            acc[k][2] * av[2] / stab(ap[2]), acc[k][3] * av[3] / stab(ap[3]));
+                make_float4(acc[k][0] * g[0], acc[k][1] * g[1], acc[k][2] * g[2], acc[k][3] * g[3]);
           }
         }
       }
@@ -300,6 +313,7 @@ static size_t grid_carve(const lrpx_gridtd_args* a, float* base, GridWs* w) {
   t.uctx = take(Q * a->T * H);
   t.coefavg = take(Q * a->C);
   t.wproj = take(Q * a->P * H);
+  t.gA = take((size_t)a->B * a->P * H);
   t.a3 = t.w3_g2 = t.w3_g1 = t.w3_glob = t.w3_proj = nullptr;
   t.a3u = nullptr;
   if (a->flags & LRPX_DEC_TC_GEMM) {
@@ -737,7 +751,12 @@ int lrpx_gridtd_decoder_lrp_f32(const lrpx_gridtd_args* a, void* workspace, size
   const size_t att_smem = (size_t)T * (((a->P + 3) & ~3) + H) * sizeof(float);
   if (att_smem <= 160 * 1024) {
     int at = H >= 512 ? 512 : (H >= 256 ? 256 : 128);
-    if ((H & 3) == 0) at = H / 4 >= 512 ? 512 : ((H / 4 + 31) & ~31);        // four hidden units per thread
+    if ((H & 3) == 0) {                  // four hidden units per thread x as many pixel-group lanes as fit 512 threads
+      const int nh = H / 4 >= 512 ? 512 : H / 4;
+      at = (nh * (512 / nh > 0 ? 512 / nh : 1) + 31) & ~31;
+      const size_t n4 = (size_t)a->B * a->P * H / 4;
+      grid_attn_gain_kernel<<<(unsigned)((n4 + 255) / 256 < 4096 ? (n4 + 255) / 256 : 4096), 256, 0, st>>>(a->A, a->A_pre, w.gA, n4);
+    }
     static bool attr_done = false;
     if (!attr_done) {
       cudaFuncSetAttribute(grid_attn_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

@@ -223,8 +223,9 @@ def test_relevance_groups_and_chunks_do_not_change_results():
     eng.GROUP = 2048
 
 
-@pytest.mark.parametrize("n,h,w", [(1, 8, 8), (3, 12, 20), (2, 56, 56), (5, 224, 224)])
-def test_first_layer_folded_columns_equals_plain_form(n, h, w):
+@pytest.mark.parametrize("n,h,w", [(1, 8, 8), (3, 12, 20), (2, 56, 56), (5, 224, 224), (2, 37, 201), (1, 300, 251),
+                                   (3, 9, 230)])
+def test_first_layer_folded_columns_equals_plain_form(n, h, w, monkeypatch):
     """LRPX_TC_EPI_INPUT3 (filter columns folded into N, column shift in the epilogue, 126-row M halves) vs
     LRPX_TC_EPI_INPUT (one MMA chain per filter tap) on the same operands: same bf16 products, fp32 accumulation in
     another order -> equal within 1e-5 of the largest element; every pixel of every request is written."""
@@ -245,6 +246,15 @@ def test_first_layer_folded_columns_equals_plain_form(n, h, w):
     tc.tc_conv(a, c0.w_rel, n, h, w, cout, 16, 3, tc.EPI_INPUT, out16, row_img=rimg, x=x)
     tc.tc_conv(a, c0.w_rel3, n, h, w, cout, 24, 3, tc.EPI_INPUT3, out24, row_img=rimg, x=x)
     assert torch.isfinite(out24).all()
+    # switches of the same kernel: two accumulator buffers instead of four (LRPX_TC_NBUF=2), one ring stage per slab instead
+    # of one per tile (LRPX_TC_AGROUP=0; wide images) and the row walk (tiles one image row apart, two of three slabs reused;
+    # LRPX_TC_WALK=1, eligible for 201 <= w + 1 <= 252) issue the same MMAs in the same order -> bit-identical
+    for key, val in (("LRPX_TC_NBUF", "2"), ("LRPX_TC_AGROUP", "0"), ("LRPX_TC_WALK", "1")):
+        monkeypatch.setenv(key, val)
+        out24s = torch.full((n, 3, h, w), float("nan"), device=DEV)
+        tc.tc_conv(a, c0.w_rel3, n, h, w, cout, 24, 3, tc.EPI_INPUT3, out24s, row_img=rimg, x=x)
+        monkeypatch.delenv(key)
+        assert torch.equal(out24, out24s), key
     scale = float(out16.abs().max())
     assert float((out24 - out16).abs().max()) <= 1e-5 * scale
     # and against the rule itself: R = x+ (W+^T * s) + x- (W-^T * s)   (lrp_modules.py:81-84, utils.py:26-30)
