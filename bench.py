@@ -560,7 +560,7 @@ def run_config2(args, ctx, brief=False):
                          "achieved_eager": ach_eager, "frac_eager": ach_eager / pk["tf_sustained"],
                          "traffic": chain_traffic(args.chunk) if ex.precision in ("bf16", "mixed") else None,
                          "traffic_note": "dram read+write bytes of the 13 chain layers per chunk of explanations (ncu --set "
-                                         "full, profiles/r1_chain_full.md); algorithmic FLOPs per chunk = chunk x "
+                                         "full, profiles/r2_chain_full.md); algorithmic FLOPs per chunk = chunk x "
                                          "algorithmic_gflop_per_explanation",
                          "peak_source": pk["src"] + " sustained bf16",
                          "share_of_step": chain_in_step / (ms / steps),

@@ -23,7 +23,9 @@ KERNELS = [
                             ("pool 56->28, 256 ch", pool_bytes(56, 256)), ("pool 28->14, 512 ch", pool_bytes(28, 512))]),
     ("scale_rows_kernel", [("r_feat fp32 (Q,196,512) -> s bf16 PF", Q * P * C * 4 + pf(Q, 14) * C * 2)]),
     ("im2col3_split_kernel", [("x fp32 (64,3,224,224) -> 64-column bf16 PF rows", B * 3 * 224 * 224 * 4 + pf(B, 224) * 64 * 2)]),
-    ("grid_attn_rows_kernel", [("A, A_pre fp32 in, split bf16 operand (Q*196, 2*512 [hi|lo]) out", 2 * B * P * H * 4 + Q * P * 2 * H * 2)]),
+    ("grid_attn_rows_kernel", [("G = A/stab(A_pre) fp32 (B,196,512) + uctx fp32 (Q,T,512) in, split bf16 operand (Q*196, 2*512 [hi|lo]) out",
+                                B * P * H * 4 + Q * T * H * 4 + Q * P * 2 * H * 2)]),
+    ("grid_attn_gain_kernel", [("A, A_pre fp32 in, G fp32 out (B,196,512)", 3 * B * P * H * 4)]),
 ]
 
 
