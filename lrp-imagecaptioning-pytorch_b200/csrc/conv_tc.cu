@@ -482,12 +482,29 @@ __device__ __forceinline__ void epi_mul_tma(const TcParams& p, const RowInfo& r,
 
 // tile at pooled resolution; 16 columns starting at `col`: scatter to the 2x2 fine pixels chosen by the argmax bytes
 // (the other three get 0).  g = 16 gains (bf16), sidx = 16 argmax bytes.
+// 16-bit lane masks of "argmax byte == k" for the four channels of one pool_idx word (bytes 0..3 = channels 4i..4i+3):
+// m01 covers the bf16 pair (4i, 4i+1), m23 the pair (4i+2, 4i+3).  0x80 - (byte ^ k) has its top bit set iff the byte equals
+// k (bytes limited to 7 bits by the caller: no borrow between bytes), and PRMT's sign-replicate mode widens that bit to a
+// half-word: 4 instructions per pool_idx word and k where the compare / select form took ~16 — the un-pool epilogue
+// ran 1111 instructions per 32 x 32 unit, half of them this selection, and the layer is bound by instruction issue
+// (profiles/r2_unpool_layer.md).
+__device__ __forceinline__ void unpool_masks(uint32_t idx7 /* pool_idx word & 0x7F7F7F7F */, uint32_t k, uint32_t& m01,
+                                             uint32_t& m23) {
+  const uint32_t s = 0x80808080u - (idx7 ^ (k * 0x01010101u));
+  // (inline PTX: the __byte_perm intrinsic documents only the low three bits of a selector nibble)
+  asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(m01) : "r"(s));
+  asm("prmt.b32 %0, %1, %1, 0xBBAA;" : "=r"(m23) : "r"(s));
+}
+
 __device__ __forceinline__ void epi_mul_unpool16(const TcParams& p, const RowInfo& r, int col, const uint32_t (&v)[16],
                                                  const U8& g, const uint4& sidx) {
   if (!r.in_range) return;
   const int wf1 = 2 * p.w + 1;
-  const size_t blk_f = (size_t)(2 * p.h + 1) * wf1;
-  __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.e * blk_f * p.out_c + col;
+  const long long blk_f = (long long)(2 * p.h + 1) * wf1;
+  // fine pixel (2a-1, 2b-1) of this pooled pixel; the other three are one pixel to the right / one fine row down.  Row -1
+  // (a == 0) and column -1 (b == 0) do not exist: those stores are skipped, the pointer is never dereferenced.
+  __nv_bfloat16* const p00 = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                             ((long long)r.e * blk_f + (long long)(2 * r.a - 1) * wf1 + (2 * r.b - 1)) * p.out_c + col;
   uint32_t prod[8];   // bf16x2 products: prod[j] = channels 2j, 2j+1
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -495,22 +512,19 @@ __device__ __forceinline__ void epi_mul_unpool16(const TcParams& p, const RowInf
     float a1 = __uint_as_float(v[2 * k + 1]) * bf16_hi(g.w[k]);
     prod[k] = r.valid ? pack_bf16(a0, a1) : 0u;
   }
-  const uint32_t sw[4] = {sidx.x, sidx.y, sidx.z, sidx.w};
+  const uint32_t sw[4] = {sidx.x & 0x7F7F7F7Fu, sidx.y & 0x7F7F7F7Fu, sidx.z & 0x7F7F7F7Fu, sidx.w & 0x7F7F7F7Fu};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    int fr = 2 * r.a - 1 + (k >> 1), fc = 2 * r.b - 1 + (k & 1);
-    if (fr < 0 || fc < 0) continue;
-    __nv_bfloat16* dst = outb + ((size_t)fr * wf1 + fc) * p.out_c;
+    const bool ok = ((k >> 1) || r.a > 0) && ((k & 1) || r.b > 0);
     uint32_t ow[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // channels 2j (low half) and 2j+1 (high half); their argmax bytes sit in word j/2 of sidx
-      const uint32_t w4 = sw[j >> 1];
-      const uint32_t b0 = (w4 >> (16 * (j & 1))) & 0xFF, b1 = (w4 >> (16 * (j & 1) + 8)) & 0xFF;
-      const uint32_t pv = prod[j];
-      ow[j] = (b0 == (uint32_t)k ? (pv & 0xFFFFu) : 0u) | (b1 == (uint32_t)k ? (pv & 0xFFFF0000u) : 0u);
+    for (int i = 0; i < 4; ++i) {
+      uint32_t m01, m23;
+      unpool_masks(sw[i], (uint32_t)k, m01, m23);
+      ow[2 * i] = prod[2 * i] & m01;
+      ow[2 * i + 1] = prod[2 * i + 1] & m23;
     }
-    stg_v8(dst, ow);
+    if (ok) stg_v8(p00 + ((long long)(k >> 1) * wf1 + (k & 1)) * p.out_c, ow);
   }
 }
 
@@ -775,12 +789,13 @@ __device__ __forceinline__ void epi_mulx(const TcParams& p, const RowInfo& r, ui
           __nv_bfloat16* dst = outb + ((size_t)fr * wf1 + fc) * p.out_c;
           uint32_t oh[8], ol[8];
 #pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            const uint32_t w4 = sw[m >> 1];
-            const uint32_t b0 = (w4 >> (16 * (m & 1))) & 0xFF, b1 = (w4 >> (16 * (m & 1) + 8)) & 0xFF;
-            const uint32_t mask = (b0 == (uint32_t)k ? 0xFFFFu : 0u) | (b1 == (uint32_t)k ? 0xFFFF0000u : 0u);
-            oh[m] = hi[m] & mask;
-            ol[m] = lo[m] & mask;
+          for (int m = 0; m < 4; ++m) {
+            uint32_t m01, m23;
+            unpool_masks(sw[m] & 0x7F7F7F7Fu, (uint32_t)k, m01, m23);
+            oh[2 * m] = hi[2 * m] & m01;
+            ol[2 * m] = lo[2 * m] & m01;
+            oh[2 * m + 1] = hi[2 * m + 1] & m23;
+            ol[2 * m + 1] = lo[2 * m + 1] & m23;
           }
           stg_v8(dst + (size_t)j * N, oh);
           if (sp) stg_v8(dst + (size_t)(G + j) * N, ol);
