@@ -288,3 +288,39 @@ def test_folded_filter_columns_equal_the_plain_contraction():
     assert float((err > 0).float().mean()) < 0.2                                      # most elements round identically
     pad = tc.pf_to_dense(b, n, h, w, cin)                                             # and the padding rows stay zero
     assert float(b.float().abs().sum()) == pytest.approx(float(pad.abs().sum()), rel=1e-3)
+
+
+@pytest.mark.parametrize("n,h,w,cout,cin,unpool", [(6, 56, 56, 128, 128, False), (6, 28, 28, 256, 128, True),
+                                                   (3, 112, 112, 64, 64, False), (3, 56, 56, 128, 64, True),
+                                                   (40, 14, 14, 512, 256, False)])
+def test_chain_layer_switches_do_not_change_results(n, h, w, cout, cin, unpool, monkeypatch):
+    """One relevance-chain layer (EPI_MUL / EPI_MUL_UNPOOL, bf16) under the kernel's scheduling switches — no
+    `cta_group::2` pair (LRPX_TC_PAIR=0), no clusters (LRPX_TC_CLUSTER=0), plain stores instead of TMA tile stores
+    (LRPX_TC_TMASTORE=0), four accumulator buffers where they fit (LRPX_TC_NBUF=4), 128-row tiles (LRPX_TC_MH=1): every
+    variant issues the same MMAs in the same K order, so the bf16 outputs are bit-identical."""
+    from lrpx import tc
+    g = torch.Generator().manual_seed(n * 100 + h + cout)
+    s = _bf(torch.randn(n, cout, h, w, generator=g)).to(DEV)
+    wt = torch.randn(cout, cin, 3, 3, generator=g).to(DEV) * 0.1
+    a = tc.nchw_to_pf(s)
+    w_rel = tc.weight_prep(wt, 2)
+    oh, ow = (2 * h, 2 * w) if unpool else (h, w)
+    gain = torch.rand(tc.pf_rows(n, h, w), cin, generator=g).to(torch.bfloat16).to(DEV)
+    idx = torch.randint(0, 4, (tc.pf_rows(n, h, w), cin), generator=g, dtype=torch.uint8).to(DEV) if unpool else None
+    rimg = torch.arange(n, dtype=torch.int32, device=DEV)
+
+    def run():
+        out = torch.full((tc.pf_rows(n, oh, ow), cin), float("nan"), device=DEV, dtype=torch.bfloat16)
+        tc.tc_conv(a, w_rel, n, h, w, cout, cin, 3, tc.EPI_MUL_UNPOOL if unpool else tc.EPI_MUL, out, gain=gain,
+                   row_img=rimg, pool_idx=idx)
+        torch.cuda.synchronize()
+        return out
+
+    ref = run()
+    assert torch.isfinite(_pf_valid(ref, n, oh, ow, cin)).all()
+    for key, val in (("LRPX_TC_PAIR", "0"), ("LRPX_TC_CLUSTER", "0"), ("LRPX_TC_TMASTORE", "0"), ("LRPX_TC_NBUF", "4"),
+                     ("LRPX_TC_MH", "1")):
+        monkeypatch.setenv(key, val)
+        got = run()
+        monkeypatch.delenv(key)
+        assert torch.equal(_pf_valid(got, n, oh, ow, cin), _pf_valid(ref, n, oh, ow, cin)), key
