@@ -137,6 +137,10 @@ int lrpx_lrp_mha_f32(const float* alpha, const float* value, const float* r_cont
 /* flags of the decoder entry points */
 #define LRPX_DEC_TC_GEMM 1   /* run the GEMMs on tcgen05 tensor cores as error-compensated bf16x3 (a_hi*w_hi + a_hi*w_lo +
                                 a_lo*w_hi, fp32 accumulate: ~2^-16 relative per product) instead of fp32 CUDA cores */
+#define LRPX_DEC_W3_READY 4  /* with LRPX_DEC_TC_GEMM, the three LRP decoders: the prepared (split bf16) copies of the weight
+                                matrices that an EARLIER call wrote into this same `workspace` are still valid — same
+                                argument dimensions (the workspace layout depends on them), same weight values — and are
+                                not rebuilt (four conversion kernels per call).  The caller owns that guarantee. */
 
 typedef struct {
   int B, T, H, E, P, C, V, Q;

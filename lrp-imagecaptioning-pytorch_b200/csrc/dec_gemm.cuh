@@ -217,8 +217,9 @@ static int gemm_any(const float* A, const float* W, const __nv_bfloat16* wt3, __
   g.x = e.x0; g.x1 = e.x1; g.bias = e.add_q; g.row_img = e.req_img;
   return lrpx_tc_conv(&g, st);
 }
-static __nv_bfloat16* prep_weight3(const float* W, __nv_bfloat16* dst, int K, int N, cudaStream_t st) {
-  split3_weight_kernel<<<ew_grid((long long)K * N), 256, 0, st>>>(W, dst, K, N);
+// ready: dst still holds the split copy of W from an earlier call on the same workspace (LRPX_DEC_W3_READY)
+static __nv_bfloat16* prep_weight3(const float* W, __nv_bfloat16* dst, int K, int N, cudaStream_t st, bool ready = false) {
+  if (!ready) split3_weight_kernel<<<ew_grid((long long)K * N), 256, 0, st>>>(W, dst, K, N);
   return dst;
 }
 

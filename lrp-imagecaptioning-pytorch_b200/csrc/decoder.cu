@@ -726,11 +726,12 @@ int lrpx_gridtd_decoder_lrp_f32(const lrpx_gridtd_args* a, void* workspace, size
   GemmEpi none{};
   // tensor-core GEMMs where the shape allows it (per GEMM), CUDA cores otherwise
   const bool tc = (a->flags & LRPX_DEC_TC_GEMM) != 0;
-  const __nv_bfloat16* w3_g2 = (tc && tc_shape_ok(3 * H, H)) ? prep_weight3(a->W_g2, w.w3_g2, H, 3 * H, st) : nullptr;
+  const bool w3_ready = (a->flags & LRPX_DEC_W3_READY) != 0;
+  const __nv_bfloat16* w3_g2 = (tc && tc_shape_ok(3 * H, H)) ? prep_weight3(a->W_g2, w.w3_g2, H, 3 * H, st, w3_ready) : nullptr;
   const __nv_bfloat16* w3_g1 =
-      (tc && tc_shape_ok(2 * H + 2 * E, H)) ? prep_weight3(a->W_g1, w.w3_g1, H, 2 * H + 2 * E, st) : nullptr;
-  const __nv_bfloat16* w3_glob = (tc && tc_shape_ok(a->C, E)) ? prep_weight3(a->W_glob, w.w3_glob, E, a->C, st) : nullptr;
-  const __nv_bfloat16* w3_proj = (tc && tc_shape_ok(a->C, H)) ? prep_weight3(a->W_proj, w.w3_proj, H, a->C, st) : nullptr;
+      (tc && tc_shape_ok(2 * H + 2 * E, H)) ? prep_weight3(a->W_g1, w.w3_g1, H, 2 * H + 2 * E, st, w3_ready) : nullptr;
+  const __nv_bfloat16* w3_glob = (tc && tc_shape_ok(a->C, E)) ? prep_weight3(a->W_glob, w.w3_glob, E, a->C, st, w3_ready) : nullptr;
+  const __nv_bfloat16* w3_proj = (tc && tc_shape_ok(a->C, H)) ? prep_weight3(a->W_proj, w.w3_proj, H, a->C, st, w3_ready) : nullptr;
   // the step kernels write the split operand themselves when both step GEMMs run on the tensor cores
   const bool fused_split = w3_g2 && w3_g1;
   if (!fused_split) w.a3u = nullptr;
@@ -799,10 +800,11 @@ int lrpx_aoa_decoder_lrp_f32(const lrpx_aoa_args* a, void* workspace, size_t wor
   int nt = H >= 256 ? 256 : 128;
   GemmEpi none{};
   const bool tc = (a->flags & LRPX_DEC_TC_GEMM) != 0;
-  const __nv_bfloat16* w3_aoa = (tc && tc_shape_ok(H, H)) ? prep_weight3(a->W_aoa, w.w3_aoa, H, H, st) : nullptr;
-  const __nv_bfloat16* w3_g = (tc && tc_shape_ok(E + 2 * H, H)) ? prep_weight3(a->W_g, w.w3_g, H, E + 2 * H, st) : nullptr;
-  const __nv_bfloat16* w3_v = (tc && tc_shape_ok(H, H)) ? prep_weight3(a->W_v, w.w3_v, H, H, st) : nullptr;
-  const __nv_bfloat16* w3_proj = (tc && tc_shape_ok(a->C, H)) ? prep_weight3(a->W_proj, w.w3_proj, H, a->C, st) : nullptr;
+  const bool w3_ready = (a->flags & LRPX_DEC_W3_READY) != 0;
+  const __nv_bfloat16* w3_aoa = (tc && tc_shape_ok(H, H)) ? prep_weight3(a->W_aoa, w.w3_aoa, H, H, st, w3_ready) : nullptr;
+  const __nv_bfloat16* w3_g = (tc && tc_shape_ok(E + 2 * H, H)) ? prep_weight3(a->W_g, w.w3_g, H, E + 2 * H, st, w3_ready) : nullptr;
+  const __nv_bfloat16* w3_v = (tc && tc_shape_ok(H, H)) ? prep_weight3(a->W_v, w.w3_v, H, H, st, w3_ready) : nullptr;
+  const __nv_bfloat16* w3_proj = (tc && tc_shape_ok(a->C, H)) ? prep_weight3(a->W_proj, w.w3_proj, H, a->C, st, w3_ready) : nullptr;
   aoa_init_kernel<<<Q, nt, 0, st>>>(*a, w);
   RUN(gemm_any<GE_STORE>(w.u, a->W_aoa, w3_aoa, w.a3, w.v, Q, H, H, none, st));
   aoa_ctx_kernel<<<Q, nt, 0, st>>>(*a, w);
@@ -843,9 +845,10 @@ int lrpx_adaptive_decoder_lrp_f32(const lrpx_adaptive_args* a, void* workspace, 
   int nt = H >= 256 ? 256 : 128;
   GemmEpi none{};
   const bool tc = (a->flags & LRPX_DEC_TC_GEMM) != 0;
-  const __nv_bfloat16* w3_g = (tc && tc_shape_ok(2 * E + H, H)) ? prep_weight3(a->W_g, w.w3_g, H, 2 * E + H, st) : nullptr;
-  const __nv_bfloat16* w3_glob = (tc && tc_shape_ok(a->C, E)) ? prep_weight3(a->W_glob, w.w3_glob, E, a->C, st) : nullptr;
-  const __nv_bfloat16* w3_proj = (tc && tc_shape_ok(a->C, H)) ? prep_weight3(a->W_proj, w.w3_proj, H, a->C, st) : nullptr;
+  const bool w3_ready = (a->flags & LRPX_DEC_W3_READY) != 0;
+  const __nv_bfloat16* w3_g = (tc && tc_shape_ok(2 * E + H, H)) ? prep_weight3(a->W_g, w.w3_g, H, 2 * E + H, st, w3_ready) : nullptr;
+  const __nv_bfloat16* w3_glob = (tc && tc_shape_ok(a->C, E)) ? prep_weight3(a->W_glob, w.w3_glob, E, a->C, st, w3_ready) : nullptr;
+  const __nv_bfloat16* w3_proj = (tc && tc_shape_ok(a->C, H)) ? prep_weight3(a->W_proj, w.w3_proj, H, a->C, st, w3_ready) : nullptr;
   if (!w3_g) w.a3u = nullptr;
   ada_init_kernel<<<Q, nt, 0, st>>>(*a, w);
   for (int i = T - 1; i >= 0; --i) {

@@ -349,7 +349,29 @@ def _check_requests(B, T, V, req_img, req_t, req_word, req_head=None, num_head=0
             raise _lib.LrpxError(f"decoder lrp: {name} out of range [0, {bound}): min {int(lo)}, max {int(hi)}")
 
 
-def gridtd_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, want_raw=False, tc_gemm=False):
+DEC_W3_READY = 4          # LRPX_DEC_W3_READY
+
+
+def _decoder_workspace(ws_cache, kind, dims, nbytes, dev, tc_gemm):
+    """Workspace of one LRP-decoder call -> (ws, extra flags, key to store it under after a successful call).
+    ``ws_cache`` (a dict owned by the caller, living exactly as long as the caller's ``weights`` dict stays unchanged —
+    BatchExplainer keeps one next to its weights) makes the workspace persistent per argument shape, so the split bf16
+    copies of the weight matrices written by the first call are reused (LRPX_DEC_W3_READY: four conversion kernels less
+    per call).  Entries are never evicted — a captured CUDA graph may point into them — and at most four shapes are kept;
+    nothing allocated during a stream capture is cached."""
+    ws = None
+    key = (kind, dims, nbytes)
+    if ws_cache is not None and tc_gemm:
+        ws = ws_cache.get(key)
+        if ws is not None:
+            return ws, DEC_W3_READY, None
+    ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
+    if ws_cache is None or not tc_gemm or len(ws_cache) >= 4 or torch.cuda.is_current_stream_capturing():
+        return ws, 0, None
+    return ws, 0, key
+
+
+def gridtd_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, want_raw=False, tc_gemm=False, ws_cache=None):
     """state: tensors of lrpx_gridtd_args (stacked over B images), weights: W_g1,W_g2,W_fc,W_glob,W_proj.
     tc_gemm: run the GEMMs as error-compensated bf16x3 on the tensor cores (LRPX_DEC_TC_GEMM) instead of fp32
     CUDA cores.  Returns r_feat (Q,P,C), r_words (Q,T)[, r_words_raw]."""
@@ -375,13 +397,16 @@ def gridtd_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, wan
     f.update(r_feat=r_feat, r_words=r_words, r_words_raw=r_raw)
     _fill_args(a, f, keep)
     nbytes = lib().lrpx_gridtd_decoder_workspace_bytes(C.byref(a))
-    ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
+    ws, extra, store = _decoder_workspace(ws_cache, "gridtd", (B, T, H, E, P, Cc, V, Q), nbytes, dev, tc_gemm)
+    a.flags |= extra
     check(lib().lrpx_gridtd_decoder_lrp_f32(C.byref(a), _ptr(ws), nbytes, _stream()), "lrpx_gridtd_decoder_lrp_f32")
+    if store is not None:
+        ws_cache[store] = ws
     return (r_feat, r_words, r_raw) if want_raw else (r_feat, r_words)
 
 
 def aoa_decoder_lrp(state: dict, weights: dict, num_head, req_img, req_t, req_word, req_head, want_raw=False,
-                    tc_gemm=False):
+                    tc_gemm=False, ws_cache=None):
     dev = state["feat"].device
     B, P, Cc = state["feat"].shape
     T, H = state["g"].shape[1], state["g"].shape[2]
@@ -402,12 +427,15 @@ def aoa_decoder_lrp(state: dict, weights: dict, num_head, req_img, req_t, req_wo
     f.update(r_feat=r_feat, r_words=r_words, r_words_raw=r_raw)
     _fill_args(a, f, keep)
     nbytes = lib().lrpx_aoa_decoder_workspace_bytes(C.byref(a))
-    ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
+    ws, extra, store = _decoder_workspace(ws_cache, "aoa", (B, T, H, E, P, Cc, V, Q, num_head), nbytes, dev, tc_gemm)
+    a.flags |= extra
     check(lib().lrpx_aoa_decoder_lrp_f32(C.byref(a), _ptr(ws), nbytes, _stream()), "lrpx_aoa_decoder_lrp_f32")
+    if store is not None:
+        ws_cache[store] = ws
     return (r_feat, r_words, r_raw) if want_raw else (r_feat, r_words)
 
 
-def adaptive_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, want_raw=False, tc_gemm=False):
+def adaptive_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, want_raw=False, tc_gemm=False, ws_cache=None):
     """ExplainAdaptiveAttention.explain_caption_wordt (adaptiveattention.py:679-771) batched over requests.
     state: tensors of lrpx_adaptive_args (stacked over B images), weights: W_g, W_fc, W_glob, W_proj.
     Returns r_feat (Q,P,C), r_words (Q,T)[, r_words_raw]."""
@@ -431,8 +459,11 @@ def adaptive_decoder_lrp(state: dict, weights: dict, req_img, req_t, req_word, w
     f.update(r_feat=r_feat, r_words=r_words, r_words_raw=r_raw)
     _fill_args(a, f, keep)
     nbytes = lib().lrpx_adaptive_decoder_workspace_bytes(C.byref(a))
-    ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
+    ws, extra, store = _decoder_workspace(ws_cache, "adaptive", (B, T, H, E, P, Cc, V, Q), nbytes, dev, tc_gemm)
+    a.flags |= extra
     check(lib().lrpx_adaptive_decoder_lrp_f32(C.byref(a), _ptr(ws), nbytes, _stream()), "lrpx_adaptive_decoder_lrp_f32")
+    if store is not None:
+        ws_cache[store] = ws
     return (r_feat, r_words, r_raw) if want_raw else (r_feat, r_words)
 
 

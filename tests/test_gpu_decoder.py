@@ -167,3 +167,38 @@ def test_adaptive_batched_requests_vs_oracle():
     e = torch.zeros(0, dtype=torch.int32)
     rf0, rw0 = ops.adaptive_decoder_lrp(ks, W, e, e, e)
     assert rf0.shape[0] == 0 and rw0.shape[0] == 0
+
+
+def test_gridtd_persistent_workspace_keeps_prepared_weights(golden):
+    """ops.gridtd_decoder_lrp(..., ws_cache=dict): the workspace of a shape is kept and later calls on it skip the
+    weight conversion (LRPX_DEC_W3_READY) — bit-identical results, one entry per argument shape; other weights need
+    another cache (the caller ties the dict's lifetime to its weights, as BatchExplainer does)."""
+    from lrpx import ops
+    g = golden("gridtd_dec_512")
+    V, H, E = int(g["V"]), int(g["H"]), int(g["E"])
+    p = synth.gridtd_decoder_state(int(g["seed"]), V, H, E)
+    toks = g["tokens"].tolist()
+    st = O.gridtd_explainer_forward(p, g["feats"][0], toks)
+    ks = helpers.gridtd_kernel_state([st], DEV)
+    W = helpers.to_dev(D.gridtd_weights(p), DEV)
+    ts = g["ts"].tolist()
+    req_img = torch.zeros(len(ts), dtype=torch.int32)
+    req_t = torch.tensor(ts, dtype=torch.int32)
+    req_word = torch.tensor([toks[t + 1] for t in ts], dtype=torch.int32)
+    ref = ops.gridtd_decoder_lrp(ks, W, req_img, req_t, req_word, tc_gemm=True)
+    cache = {}
+    first = ops.gridtd_decoder_lrp(ks, W, req_img, req_t, req_word, tc_gemm=True, ws_cache=cache)
+    assert len(cache) == 1
+    ws = next(iter(cache.values()))
+    again = ops.gridtd_decoder_lrp(ks, W, req_img, req_t, req_word, tc_gemm=True, ws_cache=cache)       # READY path
+    assert len(cache) == 1 and next(iter(cache.values())) is ws
+    for a, b, c in zip(ref, first, again):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    # another request count is another shape: its own workspace, same results for the shared requests
+    sub = ops.gridtd_decoder_lrp(ks, W, req_img[:1], req_t[:1], req_word[:1], tc_gemm=True, ws_cache=cache)
+    sub2 = ops.gridtd_decoder_lrp(ks, W, req_img[:1], req_t[:1], req_word[:1], tc_gemm=True, ws_cache=cache)
+    assert len(cache) == 2
+    assert torch.equal(sub[0], ref[0][:1]) and torch.equal(sub2[0], ref[0][:1])
+    # fp32 CUDA-core GEMMs never cache
+    ops.gridtd_decoder_lrp(ks, W, req_img, req_t, req_word, tc_gemm=False, ws_cache=cache)
+    assert len(cache) == 2
