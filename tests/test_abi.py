@@ -104,3 +104,23 @@ def test_argument_validation_of_the_widened_entry_points():
     assert lib.lrpx_bbox_ratio_f32(C.byref(x), None) == -1 and b"8 boxes" in lib.lrpx_last_error()
     x = _lib.BboxArgs(Q=1, C=3, H=512, W=512, n_thr=10, max_boxes=2, sign=1.0)
     assert lib.lrpx_bbox_ratio_f32(C.byref(x), None) == -1 and b"too large" in lib.lrpx_last_error()
+
+
+def test_python_constants_mirror_the_header():
+    """The flag / epilogue numbers the host side passes through the C ABI are the header's: a drifted constant would select
+    another epilogue or drop a flag silently."""
+    from lrpx import _lib, ops, tc
+    src = open(os.path.join(ROOT, "include", "lrpx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    defines = {k: int(v) for k, v in re.findall(r"#define\s+LRPX_([A-Z0-9_]+)\s+\(?(-?\d+)\)?\s*$", src, flags=re.M)}
+    enums = {k: int(v) for k, v in re.findall(r"\bLRPX_TC_(EPI_[A-Z0-9_]+)\s*=\s*(\d+)", src)}
+    assert defines["DEC_TC_GEMM"] == ops.DEC_TC_GEMM and defines["DEC_GUIDED"] == ops.DEC_GUIDED
+    assert defines["DEC_W3_READY"] == ops.DEC_W3_READY
+    assert len({ops.DEC_TC_GEMM, ops.DEC_GUIDED, ops.DEC_W3_READY}) == 3          # distinct bits of one flags word
+    assert defines["BEAM_GATHER_MAX"] == _lib.BEAM_GATHER_MAX
+    seen = 0
+    for name, val in enums.items():
+        if hasattr(tc, name):
+            assert getattr(tc, name) == val, name
+            seen += 1
+    assert seen >= 9
