@@ -17,7 +17,7 @@ import math
 
 import torch
 
-from . import ops
+from . import _graph, ops
 
 
 class _DeviceBeamSearch:
@@ -90,7 +90,7 @@ class _DeviceBeamSearch:
             graphs = []
             for s0, s1 in segs:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g), torch.no_grad():
+                with _graph.capture(g), torch.no_grad():
                     run(s0, s1)
                 graphs.append(g)
         pl = self._plans[key] = (t, run, segs, graphs)

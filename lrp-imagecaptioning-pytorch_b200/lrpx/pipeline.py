@@ -12,7 +12,7 @@ removes the launch latency of the ~2.7k small kernels of the decoder phases.
 """
 import torch
 
-from . import ops
+from . import _graph, ops
 
 
 class BatchExplainer:
@@ -146,7 +146,7 @@ class BatchExplainer:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with _graph.capture(graph):
                 r_words = self._run(s_imgs, s_toks, req_img, req_t, heat, host_out)
             # everything the captured kernels point at must outlive the graph (incl. the request index tensors)
             g = self._graphs[key] = (graph, s_imgs, s_toks, heat, r_words, req_img, req_t)
