@@ -192,11 +192,27 @@ __global__ void __launch_bounds__(512, 2) grid_attn_rows_kernel(lrpx_gridtd_args
   const int H = a.H, P = a.P, P4 = (P + 3) & ~3;
   float* al_s = att_s;
   float* u_s = att_s + (size_t)(t + 1) * P4;
-  for (int k = threadIdx.x; k < (t + 1) * P4; k += blockDim.x) {
-    const int i = k / P4, p = k - i * P4;
-    al_s[k] = p < P ? a.alpha[((size_t)b * a.T + i) * P + p] : 0.f;
+  if ((H & 3) == 0 && (P & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.alpha) | reinterpret_cast<uintptr_t>(w.uctx)) & 15) == 0) {
+    // 16-byte copies, four in flight per thread: the element-wise form was (t+1)(P+H)/blockDim dependent load -> store
+    // rounds per thread (27 at t = 18), each a trip to L2 — a third of the block's time before its first multiply
+    const int p4 = P >> 2, n_al = (t + 1) * p4, n_u = (t + 1) * (H >> 2);
+    float4* al4 = reinterpret_cast<float4*>(al_s);
+    float4* u4 = reinterpret_cast<float4*>(u_s);
+    const float4* usrc = reinterpret_cast<const float4*>(w.uctx + (size_t)q * a.T * H);
+#pragma unroll 4
+    for (int k = threadIdx.x; k < n_al; k += blockDim.x) {
+      const int i = k / p4, c = k - i * p4;
+      al4[k] = __ldg(reinterpret_cast<const float4*>(a.alpha + ((size_t)b * a.T + i) * P) + c);
+    }
+#pragma unroll 4
+    for (int k = threadIdx.x; k < n_u; k += blockDim.x) u4[k] = usrc[k];
+  } else {
+    for (int k = threadIdx.x; k < (t + 1) * P4; k += blockDim.x) {
+      const int i = k / P4, p = k - i * P4;
+      al_s[k] = p < P ? a.alpha[((size_t)b * a.T + i) * P + p] : 0.f;
+    }
+    for (int k = threadIdx.x; k < (t + 1) * H; k += blockDim.x) u_s[k] = w.uctx[(size_t)q * a.T * H + k];
   }
-  for (int k = threadIdx.x; k < (t + 1) * H; k += blockDim.x) u_s[k] = w.uctx[(size_t)q * a.T * H + k];
   __syncthreads();
   if ((H & 3) == 0) {
     // four hidden units x four pixels per thread step: per LSTM step one LDS.128 of uctx and one of the alphas feed 16
