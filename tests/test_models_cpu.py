@@ -388,3 +388,47 @@ def test_greedy_search_equals_beam_size_one():
         n = min(len(words_g), len(words_b))
         assert n > 0 and words_g[:n] == words_b[:n], (words_g, words_b)
         assert seqs[0][0] == wm['<start>'] and len(seqs[0]) == 8 and isinstance(sent_g[0], str)
+
+
+def test_decoder_workspace_cache_policy(monkeypatch):
+    """ops._decoder_workspace (host logic, no GPU): a workspace is kept per argument shape only for the tensor-core GEMM
+    mode, is handed back with LRPX_DEC_W3_READY on the next call of that shape, is stored by the caller only AFTER a
+    successful call, never during a stream capture, and at most four shapes are kept (nothing is ever evicted: a captured
+    graph may point into an entry)."""
+    import torch
+    from lrpx import ops
+    made = []
+
+    def fake_empty(n, device=None, dtype=None):
+        made.append(n)
+        return ("ws", len(made))
+
+    capturing = {"on": False}
+    monkeypatch.setattr(torch, "empty", fake_empty)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: capturing["on"])
+    cache = {}
+    ws, extra, key = ops._decoder_workspace(cache, "gridtd", (1, 2, 3), 100, "cuda", True)
+    assert extra == 0 and key == ("gridtd", (1, 2, 3), 100) and cache == {}       # miss: the caller stores it after the call
+    cache[key] = ws
+    ws2, extra2, key2 = ops._decoder_workspace(cache, "gridtd", (1, 2, 3), 100, "cuda", True)
+    assert ws2 is ws and extra2 == ops.DEC_W3_READY and key2 is None
+    # another shape / another decoder: another entry
+    _, e3, k3 = ops._decoder_workspace(cache, "gridtd", (1, 2, 4), 100, "cuda", True)
+    _, e4, k4 = ops._decoder_workspace(cache, "aoa", (1, 2, 3), 100, "cuda", True)
+    assert e3 == 0 and e4 == 0 and k3 != key and k4 != key and k3 != k4
+    # fp32 CUDA-core GEMMs, no cache dict, or a running capture: a fresh workspace that is not kept
+    assert ops._decoder_workspace(cache, "gridtd", (1, 2, 3), 100, "cuda", False)[1:] == (0, None)
+    assert ops._decoder_workspace(None, "gridtd", (1, 2, 3), 100, "cuda", True)[1:] == (0, None)
+    capturing["on"] = True
+    assert ops._decoder_workspace(cache, "gridtd", (9, 9, 9), 100, "cuda", True)[1:] == (0, None)
+    assert ops._decoder_workspace(cache, "gridtd", (1, 2, 3), 100, "cuda", True)[1] == ops.DEC_W3_READY   # a hit is fine
+    capturing["on"] = False
+    # the cap: four shapes
+    for i in range(3):
+        _, _, k = ops._decoder_workspace(cache, "gridtd", (7, i), 100, "cuda", True)
+        assert k is not None
+        cache[k] = ("ws", i)
+    assert len(cache) == 4
+    assert ops._decoder_workspace(cache, "gridtd", (8, 8), 100, "cuda", True)[1:] == (0, None)
+    assert ops._decoder_workspace(cache, "gridtd", (1, 2, 3), 0, "cuda", True)[0] is not None            # nbytes 0 -> 4-byte dummy
+    assert made[-1] == 4
